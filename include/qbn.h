@@ -1,0 +1,212 @@
+/*
+ * libqbn — C ABI of the B200-native stochastic-layer hot path.
+ *
+ * The reference (martinferianc/quantised-bayesian-nets) has NO FFI layer: its boundary is the
+ * Python nn.Module protocol.  This header is therefore the interface a
+ * maintainer would bind with ctypes; each entry point cites the reference
+ * lines whose arithmetic it replaces.  Paths are relative to the reference repo root.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative QBN_ERR_*; qbn_last_error() gives text.
+ *     Nothing is thrown across the ABI and no entry point falls back to the CPU.
+ *   - all tensor pointers are DEVICE pointers owned by the caller (outputs and workspaces too);
+ *     `stream` is a cudaStream_t passed as void*; launches are asynchronous on that stream.
+ *   - activations are dense NHWC ("channels last"): [B][H][W][C].  A linear layer is the
+ *     degenerate conv H=W=R=S=1 (rows = batch, C = in_features).
+ *   - "packed" weights are OHWI: [N][R][S][C] (K = R*S*C contiguous per output channel);
+ *     parameters in the nn.Module stay OIHW like the reference (state-dict compatible) and
+ *     are packed by qbn_weight_prep.
+ *   - RNG: Philox4x32-10, stream = (seed, stream_a = layer/purpose id, stream_b = GLOBAL
+ *     Monte-Carlo sample index or training step), counter = element index / 4.  Passing an
+ *     explicit noise pointer ("injected noise") bypasses Philox; that is how the parity tests
+ *     replay the reference's torch.Generator draws.
+ */
+#ifndef QBN_H_
+#define QBN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QBN_OK 0
+#define QBN_ERR_INVALID_ARG (-1)
+#define QBN_ERR_UNSUPPORTED (-2)
+#define QBN_ERR_CUDA (-3)
+#define QBN_ERR_WORKSPACE (-4)
+
+/* math_mode for the contraction kernels */
+#define QBN_MATH_FP32 0 /* CUDA-core FFMA, fp32 exact ordering-insensitive parity (rtol 1e-5) */
+#define QBN_MATH_TF32 1 /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (rtol 1e-3)        */
+
+typedef struct qbn_conv_desc {
+  int32_t B, H, W, C;           /* input  [B][H][W][C]                      */
+  int32_t N, R, S;              /* filter [N][R][S][C]                      */
+  int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int32_t Ho, Wo;               /* output [B][Ho][Wo][N]                    */
+} qbn_conv_desc;
+
+const char* qbn_last_error(void);
+int qbn_version(void);
+/* sm_count / compute capability of the current device; fails (QBN_ERR_CUDA) without a GPU. */
+int qbn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- Philox test hooks (statistical tests; oracle/philox.py is the bit-exact restatement) ---- */
+int qbn_philox_u32(uint32_t* out, int64_t n, uint64_t seed, uint32_t stream_a, uint32_t stream_b,
+                   void* stream);
+int qbn_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t stream_a, uint32_t stream_b,
+                      void* stream);
+/* out[i] = 1.0f with probability keep_prob else 0 — dropout.py:19-30 (bernoulli_(1-p)) */
+int qbn_philox_bernoulli(float* out, int64_t n, float keep_prob, uint64_t seed, uint32_t stream_a,
+                         uint32_t stream_b, void* stream);
+
+/* ---- parameter packing ------------------------------------------------------------------- */
+/* mu, second: OIHW [N][C][R][S].  second is rho (second_is_sigma=0: sigma=softplus(rho),
+ * linear.py:35, conv.py:26) or sigma itself (=1, QAT path where sigma was fake-quantised,
+ * conv_qat.py:28,143).  chan_scale[N] (nullable) multiplies mu and sigma per output channel
+ * (BN fold, conv.py:70-80 / conv_qat.py:140-143).  Outputs (each nullable) are packed OHWI. */
+int qbn_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int R,
+                    int S, const float* chan_scale, float* mu_p, float* sigma_p, float* sigma2_p,
+                    void* stream);
+/* chain rule back to the nn.Module parameters: d_mu[OIHW] = dmu_p ; d_rho = dsig2_p * 2*sigma *
+ * sigmoid(rho)  (or d_sigma = dsig2_p * 2*sigma when second_is_sigma) — SURVEY §8a row A3.
+ * accumulate!=0 adds into the outputs (used to fold the KL gradient in). */
+int qbn_weight_grad_post(const float* dmu_p, const float* dsig2_p, const float* second,
+                         int second_is_sigma, int N, int C, int R, int S, float* d_mu,
+                         float* d_second, int accumulate, void* stream);
+
+/* ---- A1/A2: local-reparametrisation forward (linear.py:32-40, conv.py:24-32) ---------------
+ * out = x*mu + sqrt(1e-8 + x^2*sigma^2) .* eps + bias, both contractions in ONE pass over x.
+ * eps: injected noise laid out like out ([B][Ho][Wo][N]) or NULL -> Philox(seed, stream_a,
+ * stream_b, offset in out).  std_out (nullable) receives sqrt(1e-8+v) for the backward.       */
+int qbn_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const float* sig2_p,
+                const float* bias, const float* eps, uint64_t seed, uint32_t stream_a,
+                uint32_t stream_b, float* out, float* std_out, int math_mode, void* stream);
+
+/* ---- A3: backward of A1/A2 (autograd of linear.py:32-40 / conv.py:24-32, trainer.py:104) ----
+ * g = dL/dout; dv = g*eps/(2*std); dmu_p = g^T xcol; dsig2_p = dv^T xcol^2;
+ * dx = g*mu + 2x .* (dv*sigma^2); dbias = sum g.  dx/dbias nullable.  eps as in forward.      */
+size_t qbn_lrt_bwd_workspace_bytes(const qbn_conv_desc* d);
+int qbn_lrt_bwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const float* sig2_p,
+                const float* grad_out, const float* std_saved, const float* eps, uint64_t seed,
+                uint32_t stream_a, uint32_t stream_b, float* dx, float* dmu_p, float* dsig2_p,
+                float* dbias, void* workspace, size_t workspace_bytes, int math_mode,
+                void* stream);
+
+/* ---- A4: eval-time weight sampling (linear.py:42-50, conv.py:33-39) ------------------------
+ * w[s][i] = mu_p[i] + sigma_p[i]*eps, i in [0,n): one draw per (sample, layer, weight).
+ * eps: injected [n_samples][n] (same packed order) or NULL -> Philox(seed, layer_id,
+ * sample0+s, i).  The buffer is a few MB and is consumed straight out of L2 by qbn_conv_fwd.  */
+int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n_samples,
+                       const float* eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
+                       float* w, void* stream);
+
+/* y = conv(x, w[s]) for every Monte-Carlo sample s in one launch, with the caller-side glue of
+ * models_bbb.py:170-183,226-245 folded into the epilogue: per-channel affine (eval BatchNorm or
+ * bias), residual add (src/utils.py:49-55), ReLU.  x: [n_samples][B].. or, if x_shared, [B]..
+ * read by every sample.  in_mask (nullable) is the A8 MC-Dropout mask [n_samples*B][C] applied to
+ * the operand load with multiplier in_mult (dropout.py:15-40).  out: [n_samples][B][Ho][Wo][N]. */
+int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x,
+                 const float* w, int w_shared, const float* scale, const float* shift,
+                 const float* residual, int relu, const float* in_mask, float in_mult, float* out,
+                 int math_mode, void* stream);
+
+/* ---- A8 standalone: x[b,h,w,c] * mask[b,c] * mult (dropout.py:35-39); mask NULL -> Philox ---- */
+int qbn_dropout_fwd(const float* x, int64_t rows /*B*/, int64_t hw, int64_t C, const float* mask,
+                    float keep_prob, float mult, uint64_t seed, uint32_t stream_a,
+                    uint32_t stream_b, float* out, float* mask_out, void* stream);
+
+/* ---- A5: KL(q||p) closed form + gradient (utils_bbb.py:3-5, linear.py:24-28, conv.py:43-47) --
+ * kl_out (device scalar) += 0.5*sum(2*log(sp/sigma) - 1 + (sigma/sp)^2 + (mu/sp)^2).
+ * If d_mu/d_rho are non-NULL they are ACCUMULATED with grad_scale * dKL/d(.).                */
+int qbn_kl_fwd_bwd(const float* mu, const float* rho, int64_t n, float sigma_prior, float* kl_out,
+                   float* d_mu, float* d_rho, float grad_scale, void* stream);
+
+/* ---- A7: fake quantisation + MovingAverageMinMax observer (linear_qat.py:18-41,
+ * conv_qat.py:26-52,139-170; torch/ao/quantization/observer.py:374-410,668-683) -------------
+ * state = {min, max, initialised} on device.  observe!=0: one pass computes (min,max) of x and
+ * updates the EMA (c = averaging_const; first call initialises), then scale/zero_point.
+ * y = (clamp(rint(x*(1/scale)) + zp, qmin, qmax) - zp) * scale; mask (nullable) = STE pass mask. */
+int qbn_fake_quant_fwd(const float* x, int64_t n, float* state, float averaging_const, int observe,
+                       int qmin, int qmax, float* scale, int32_t* zero_point, float* y,
+                       uint8_t* mask, void* workspace /* >= 2*sizeof(float)*1024 */, void* stream);
+int qbn_fake_quant_bwd(const float* grad_y, const uint8_t* mask, int64_t n, float* grad_x,
+                       void* stream);
+
+/* ---- A6: true int8 path (linear_q.py:80-94,154-173; conv_q.py:107-125,189-209) ---------------
+ * quantize: q = clamp(rint(x*(1/scale)) + zp, qmin, qmax)  (torch.quantize_per_tensor)         */
+int qbn_quantize_u8(const float* x, int64_t n, float scale, int32_t zp, int qmin, int qmax,
+                    uint8_t* q, void* stream);
+int qbn_quantize_s8(const float* x, int64_t n, float scale, int32_t zp, int qmin, int qmax,
+                    int8_t* q, void* stream);
+int qbn_dequantize_u8(const uint8_t* q, int64_t n, float scale, int32_t zp, float* x, void* stream);
+
+typedef struct qbn_i8_sample_params {
+  float s_mu;    int32_t z_mu;    /* qint8 mu tensor qparams                                  */
+  float s_sigma; int32_t z_sigma; /* qint8 sigma tensor qparams                               */
+  float s_eps;   int32_t z_eps;   /* NOISE_SCALE=3/127, NOISE_ZERO_POINT=0 (quantized/__init__.py) */
+  float s_mul;   int32_t z_mul;   /* mul_noise QFunctional output qparams                     */
+  float s_add;   int32_t z_add;   /* add_weight QFunctional output qparams                    */
+  int32_t w_min, w_max;           /* clamp_weight INT_BOUNDS (src/utils.py:18-20,32-37)       */
+} qbn_i8_sample_params;
+/* w[s][i] = clamp_weight(qadd(mu_q, qmul(sigma_q, quantize(eps)))) — SURVEY §8a A6 steps 1-4.
+ * eps injected fp32 [n_samples][n] or NULL -> Philox.  All arithmetic reproduces ATen's
+ * QuantizedCPU kernels bit for bit (fp32 multipliers, round-half-even).                       */
+int qbn_i8_sample_weights(const int8_t* mu_q, const int8_t* sigma_q, int64_t n, int n_samples,
+                          const qbn_i8_sample_params* p, const float* eps, uint64_t seed,
+                          uint32_t layer_id, uint32_t sample0, int8_t* w, void* stream);
+
+/* u8 x s8 -> s32 contraction with FBGEMM's requantisation (A6 step 6):
+ * acc = sum (x-z_x)(w-z_w); y = clamp(rint((fp32(acc) + bias/(s_x*s_w)) * (s_x*s_w/s_out)) + z_out,
+ * lo, hi), lo = max(z_out if relu else 0, act_min), hi = min(255, act_max) (clamp_activation,
+ * src/utils.py:25-30).  acc_dump (nullable, int32 like out) exposes raw accumulators to tests.  */
+int qbn_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const uint8_t* x,
+                    float s_x, int32_t z_x, const int8_t* w, int w_shared, float s_w, int32_t z_w,
+                    const float* bias, float s_out, int32_t z_out, int relu, int act_min,
+                    int act_max, uint8_t* out, int32_t* acc_dump, void* stream);
+/* quantized::add (+optional relu) — src/utils.py:49-55 via QFunctional.add; A6 step 3 formula
+ * on quint8: f = (a-za)*sa + (b-zb)*sb ; q = clamp(rint(f*(1/so)) + zo, lo, hi)              */
+int qbn_i8_add(const uint8_t* a, float sa, int32_t za, const uint8_t* b, float sb, int32_t zb,
+               int64_t n, float so, int32_t zo, int lo, int hi, uint8_t* out, void* stream);
+/* int8 MC-Dropout (dropout.py:31-39): mask quantised at (s_m,z_m) then quantized::mul with the
+ * output at the same (s_m,z_m); mul_scalar only rescales.  mask fp32 {0,1} [rows][C] injected
+ * or NULL -> Philox.                                                                         */
+int qbn_i8_dropout(const uint8_t* x, float s_x, int32_t z_x, int64_t rows, int64_t hw, int64_t C,
+                   const float* mask, float keep_prob, float s_m, int32_t z_m, uint64_t seed,
+                   uint32_t stream_a, uint32_t stream_b, int lo, int hi, uint8_t* out,
+                   void* stream);
+
+/* ---- A9: Monte-Carlo aggregation (experiments/utils.py:344-355) ----------------------------
+ * logits [n_samples][B][K] -> psum[B][K] (+)= sum_s softmax(logits_s)  (models_bbb.py:131,243)
+ * accumulate==0 overwrites.  The caller divides by the GLOBAL S after the allreduce.           */
+int qbn_softmax_accumulate(const float* logits, int n_samples, int B, int K, float* psum,
+                           int accumulate, void* stream);
+/* probs [n_samples][B][K] -> mean over samples (stack(...).mean(dim=1)) */
+int qbn_mc_mean(const float* probs, int n_samples, int64_t BK, float* mean, void* stream);
+/* regression (experiments/utils.py:349-353): mean_s mu, Var_s(mu) (unbiased) + mean_s var */
+int qbn_reg_mc_reduce(const float* mu, const float* var, int n_samples, int64_t B, float* mean_out,
+                      float* var_out, void* stream);
+
+/* ---- A10: metric reductions (src/metrics.py:20-29,48-57,76-85,104-112,381-383) -------------
+ * out[0..3] += {sum[argmax!=t], sum -log(p_t+1e-8), sum (p-onehot)^2, sum -p log(p+1e-8)};
+ * out[4 + 3*b + {0,1,2}] += {sum conf, sum correct, count} of confidence bin b (n_bins equal-
+ * width bins, ECE l1).  scale multiplies probs first (1/S after an allreduce of sums).        */
+int qbn_cls_metrics(const float* probs, const int64_t* target, int B, int K, float scale,
+                    int n_bins, float* out, void* stream);
+/* out[0..2] += {gaussian nll sum, squared error sum, abs error sum} (metrics.py:135-157,176-225) */
+int qbn_reg_metrics(const float* mean, const float* var, const float* target, int64_t B,
+                    float* out, void* stream);
+
+/* ---- A11 glue kernels that survive fusion only at resolution changes ------------------------ */
+int qbn_maxpool2x2(const float* x, int64_t B, int H, int W, int C, float* out, void* stream);
+/* global average pool HxW -> 1 (nn.AvgPool2d(4) on the 4x4 map, models_bbb.py:209) */
+int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float* out, void* stream);
+/* NCHW <-> NHWC (entry/exit of the NHWC domain) */
+int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QBN_H_ */
