@@ -150,6 +150,9 @@ typedef struct qbn_i8_sample_params {
   float s_mul;   int32_t z_mul;   /* mul_noise QFunctional output qparams                     */
   float s_add;   int32_t z_add;   /* add_weight QFunctional output qparams                    */
   int32_t w_min, w_max;           /* clamp_weight INT_BOUNDS (src/utils.py:18-20,32-37)       */
+  int64_t n_vec;                  /* elements [0,n_vec) use ATen's vector-body dequantise
+                                     (fma(scale, q, -zp*scale)), the rest its scalar-tail form
+                                     ((q-zp)*scale); ATen's split is n_vec = (n/64)*64; <0 = that */
 } qbn_i8_sample_params;
 /* w[s][i] = clamp_weight(qadd(mu_q, qmul(sigma_q, quantize(eps)))) — SURVEY §8a A6 steps 1-4.
  * eps injected fp32 [n_samples][n] or NULL -> Philox.  All arithmetic reproduces ATen's
@@ -165,11 +168,15 @@ int qbn_i8_sample_weights(const int8_t* mu_q, const int8_t* sigma_q, int64_t n, 
 int qbn_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const uint8_t* x,
                     float s_x, int32_t z_x, const int8_t* w, int w_shared, float s_w, int32_t z_w,
                     const float* bias, float s_out, int32_t z_out, int relu, int act_min,
-                    int act_max, uint8_t* out, int32_t* acc_dump, void* stream);
+                    int act_max, uint8_t* out, int32_t* acc_dump, int path, void* stream);
+#define QBN_I8_AUTO 0  /* tcgen05 kind::i8 when C % 8 == 0 and activations are <= 7 bit, else IMAD */
+#define QBN_I8_IMAD 1  /* CUDA-core integer FMA kernel (any shape)                               */
+#define QBN_I8_UMMA 2  /* force the tcgen05 kernel (QBN_ERR_UNSUPPORTED if the shape is ragged)   */
 /* quantized::add (+optional relu) — src/utils.py:49-55 via QFunctional.add; A6 step 3 formula
  * on quint8: f = (a-za)*sa + (b-zb)*sb ; q = clamp(rint(f*(1/so)) + zo, lo, hi)              */
 int qbn_i8_add(const uint8_t* a, float sa, int32_t za, const uint8_t* b, float sb, int32_t zb,
-               int64_t n, float so, int32_t zo, int lo, int hi, uint8_t* out, void* stream);
+               int64_t n, int64_t n_vec, float so, int32_t zo, int lo, int hi, uint8_t* out,
+               void* stream);
 /* int8 MC-Dropout (dropout.py:31-39): mask quantised at (s_m,z_m) then quantized::mul with the
  * output at the same (s_m,z_m); mul_scalar only rescales.  mask fp32 {0,1} [rows][C] injected
  * or NULL -> Philox.                                                                         */

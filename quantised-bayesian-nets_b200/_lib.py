@@ -1,0 +1,96 @@
+"""ctypes binding of libqbn.so (include/qbn.h).  No torch types cross the ABI: tensors are passed
+as raw device pointers and sizes.  If the library is missing or a call fails, this module raises —
+there is deliberately NO CPU or PyTorch fallback for any op."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libqbn.so")
+
+QBN_MATH_FP32 = 0
+QBN_MATH_TF32 = 1
+
+
+class ConvDesc(Structure):
+    _fields_ = [(n, c_int32) for n in ("B", "H", "W", "C", "N", "R", "S", "stride_h", "stride_w", "pad_h", "pad_w",
+                                        "dil_h", "dil_w", "Ho", "Wo")]
+
+
+class I8SampleParams(Structure):
+    _fields_ = [("s_mu", c_float), ("z_mu", c_int32), ("s_sigma", c_float), ("z_sigma", c_int32),
+                ("s_eps", c_float), ("z_eps", c_int32), ("s_mul", c_float), ("z_mul", c_int32),
+                ("s_add", c_float), ("z_add", c_int32), ("w_min", c_int32), ("w_max", c_int32), ("n_vec", c_int64)]
+
+
+P = c_void_p
+_SIGNATURES = {
+    "qbn_last_error": (c_char_p, []),
+    "qbn_version": (c_int, []),
+    "qbn_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "qbn_philox_u32": (c_int, [P, c_int64, c_uint64, c_uint32, c_uint32, P]),
+    "qbn_philox_normal": (c_int, [P, c_int64, c_uint64, c_uint32, c_uint32, P]),
+    "qbn_philox_bernoulli": (c_int, [P, c_int64, c_float, c_uint64, c_uint32, c_uint32, P]),
+    "qbn_weight_prep": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "qbn_weight_grad_post": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
+    "qbn_lrt_fwd": (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_uint64, c_uint32, c_uint32, P, P, c_int, P]),
+    "qbn_lrt_bwd_workspace_bytes": (c_size_t, [POINTER(ConvDesc)]),
+    "qbn_lrt_bwd": (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_uint64, c_uint32, c_uint32, P, P, P, P, P, c_size_t, c_int, P]),
+    "qbn_sample_weights": (c_int, [P, P, c_int64, c_int, P, c_uint64, c_uint32, c_uint32, P, P]),
+    "qbn_conv_fwd": (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, c_int, P, P, P, c_int, P, c_float, P, c_int, P]),
+    "qbn_dropout_fwd": (c_int, [P, c_int64, c_int64, c_int64, P, c_float, c_float, c_uint64, c_uint32, c_uint32, P, P, P]),
+    "qbn_kl_fwd_bwd": (c_int, [P, P, c_int64, c_float, P, P, P, c_float, P]),
+    "qbn_fake_quant_fwd": (c_int, [P, c_int64, P, c_float, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "qbn_fake_quant_bwd": (c_int, [P, P, c_int64, P, P]),
+    "qbn_quantize_u8": (c_int, [P, c_int64, c_float, c_int32, c_int, c_int, P, P]),
+    "qbn_quantize_s8": (c_int, [P, c_int64, c_float, c_int32, c_int, c_int, P, P]),
+    "qbn_dequantize_u8": (c_int, [P, c_int64, c_float, c_int32, P, P]),
+    "qbn_i8_sample_weights": (c_int, [P, P, c_int64, c_int, POINTER(I8SampleParams), P, c_uint64, c_uint32, c_uint32, P, P]),
+    "qbn_i8_conv_fwd": (c_int, [POINTER(ConvDesc), c_int, c_int, P, c_float, c_int32, P, c_int, c_float, c_int32, P, c_float,
+                                c_int32, c_int, c_int, c_int, P, P, c_int, P]),
+    "qbn_i8_add": (c_int, [P, c_float, c_int32, P, c_float, c_int32, c_int64, c_int64, c_float, c_int32, c_int, c_int, P, P]),
+    "qbn_i8_dropout": (c_int, [P, c_float, c_int32, c_int64, c_int64, c_int64, P, c_float, c_float, c_int32, c_uint64, c_uint32,
+                               c_uint32, c_int, c_int, P, P]),
+    "qbn_softmax_accumulate": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
+    "qbn_mc_mean": (c_int, [P, c_int, c_int64, P, P]),
+    "qbn_reg_mc_reduce": (c_int, [P, P, c_int, c_int64, P, P, P]),
+    "qbn_cls_metrics": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P]),
+    "qbn_reg_metrics": (c_int, [P, P, P, c_int64, P, P]),
+    "qbn_maxpool2x2": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
+    "qbn_avgpool_all": (c_int, [P, c_int64, c_int, c_int, P, P]),
+    "qbn_nchw_to_nhwc": (c_int, [P, c_int64, c_int, c_int, P, P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_lib = None
+
+
+class QbnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libqbn.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QbnError("libqbn.so not found at %s — build it with `python -c \"import __graft_entry__ as g; g.build()\"`. "
+                       "There is no CPU/PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export what include/qbn.h declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().qbn_last_error()
+        raise QbnError("%s failed with status %d: %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,705 @@
+// HBM-bound kernels of the stochastic-layer path: Philox hooks, parameter packing, eval-time
+// weight sampling (float A4 and int8 A6 steps 1-4), MC-Dropout (A8), KL (A5), fake-quant +
+// observer (A7), quantise/requantise glue (A6/A11).  All are grid-stride kernels with 128-bit
+// accesses where the layout allows, sized in multiples of the SM count.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error / device plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void qbn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int qbn_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+extern "C" const char* qbn_last_error(void) { return g_err; }
+extern "C" int qbn_version(void) { return 100; }
+
+extern "C" int qbn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  QBN_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  QBN_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox test hooks
+// ---------------------------------------------------------------------------------------------
+__global__ void philox_u32_kernel(uint32_t* __restrict__ out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb) {
+  int64_t n4 = (n + 3) >> 2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n4; c += (int64_t)gridDim.x * blockDim.x) {
+    Philox4 p = philox_at(seed, sa, sb, (uint64_t)c);
+    uint32_t v[4] = {p.x, p.y, p.z, p.w};
+    int64_t base = c << 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (base + j < n) out[base + j] = v[j];
+  }
+}
+
+__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb) {
+  int64_t n4 = (n + 3) >> 2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n4; c += (int64_t)gridDim.x * blockDim.x) {
+    float z[4];
+    philox_normal4(seed, sa, sb, (uint64_t)c, z);
+    int64_t base = c << 2;
+    if (base + 3 < n && ((reinterpret_cast<uintptr_t>(out + base) & 15) == 0)) {
+      *reinterpret_cast<float4*>(out + base) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (base + j < n) out[base + j] = z[j];
+    }
+  }
+}
+
+__global__ void philox_bernoulli_kernel(float* __restrict__ out, int64_t n, float keep, uint64_t seed, uint32_t sa, uint32_t sb) {
+  int64_t n4 = (n + 3) >> 2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n4; c += (int64_t)gridDim.x * blockDim.x) {
+    Philox4 p = philox_at(seed, sa, sb, (uint64_t)c);
+    uint32_t v[4] = {p.x, p.y, p.z, p.w};
+    int64_t base = c << 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (base + j < n) out[base + j] = u01(v[j]) < keep ? 1.0f : 0.0f;
+  }
+}
+
+extern "C" int qbn_philox_u32(uint32_t* out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb, void* stream) {
+  QBN_CHECK_ARG(out && n >= 0, "out/n");
+  if (n == 0) return QBN_OK;
+  philox_u32_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, sa, sb);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+extern "C" int qbn_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb, void* stream) {
+  QBN_CHECK_ARG(out && n >= 0, "out/n");
+  if (n == 0) return QBN_OK;
+  philox_normal_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, sa, sb);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+extern "C" int qbn_philox_bernoulli(float* out, int64_t n, float keep_prob, uint64_t seed, uint32_t sa, uint32_t sb, void* stream) {
+  QBN_CHECK_ARG(out && n >= 0, "out/n");
+  QBN_CHECK_ARG(keep_prob >= 0.f && keep_prob <= 1.f, "keep_prob in [0,1]");
+  if (n == 0) return QBN_OK;
+  philox_bernoulli_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, keep_prob, seed, sa, sb);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter packing OIHW -> OHWI (+softplus, +BN channel scale) and the chain rule back
+// ---------------------------------------------------------------------------------------------
+__global__ void weight_prep_kernel(const float* __restrict__ mu, const float* __restrict__ second, int second_is_sigma,
+                                   int N, int C, int R, int S, const float* __restrict__ chan_scale,
+                                   float* __restrict__ mu_p, float* __restrict__ sigma_p, float* __restrict__ sigma2_p) {
+  int64_t total = (int64_t)N * C * R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the packed OHWI order
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int s = (int)(t % S);
+    t /= S;
+    int r = (int)(t % R);
+    int n = (int)(t / R);
+    int64_t src = (((int64_t)n * C + c) * R + r) * S + s;
+    float cs = chan_scale ? chan_scale[n] : 1.0f;
+    float m = mu[src];
+    float sg = second_is_sigma ? second[src] : softplus_f(second[src]);
+    if (chan_scale) {
+      m = __fmul_rn(m, cs);
+      sg = __fmul_rn(sg, cs);
+    }
+    if (mu_p) mu_p[i] = m;
+    if (sigma_p) sigma_p[i] = sg;
+    if (sigma2_p) sigma2_p[i] = __fmul_rn(sg, sg);
+  }
+}
+
+extern "C" int qbn_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int R, int S,
+                               const float* chan_scale, float* mu_p, float* sigma_p, float* sigma2_p, void* stream) {
+  QBN_CHECK_ARG(mu && second, "mu/second");
+  QBN_CHECK_ARG(N > 0 && C > 0 && R > 0 && S > 0, "N,C,R,S > 0");
+  int64_t total = (int64_t)N * C * R * S;
+  weight_prep_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mu, second, second_is_sigma, N, C, R, S,
+                                                                               chan_scale, mu_p, sigma_p, sigma2_p);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void weight_grad_post_kernel(const float* __restrict__ dmu_p, const float* __restrict__ dsig2_p,
+                                        const float* __restrict__ second, int second_is_sigma, int N, int C, int R, int S,
+                                        float* __restrict__ d_mu, float* __restrict__ d_second, int accumulate) {
+  int64_t total = (int64_t)N * C * R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes OIHW (coalesced parameter-gradient writes); gather from packed OHWI
+    int s = (int)(i % S);
+    int64_t t = i / S;
+    int r = (int)(t % R);
+    t /= R;
+    int c = (int)(t % C);
+    int n = (int)(t / C);
+    int64_t src = (((int64_t)n * R + r) * S + s) * C + c;
+    if (d_mu && dmu_p) {
+      float v = dmu_p[src];
+      d_mu[i] = accumulate ? d_mu[i] + v : v;
+    }
+    if (d_second && dsig2_p) {
+      float sec = second[i];
+      float sg = second_is_sigma ? sec : softplus_f(sec);
+      float v = dsig2_p[src] * 2.0f * sg;
+      if (!second_is_sigma) v *= sigmoid_f(sec);
+      d_second[i] = accumulate ? d_second[i] + v : v;
+    }
+  }
+}
+
+extern "C" int qbn_weight_grad_post(const float* dmu_p, const float* dsig2_p, const float* second, int second_is_sigma,
+                                    int N, int C, int R, int S, float* d_mu, float* d_second, int accumulate, void* stream) {
+  QBN_CHECK_ARG(N > 0 && C > 0 && R > 0 && S > 0, "N,C,R,S > 0");
+  QBN_CHECK_ARG(!(d_second && dsig2_p) || second, "second required for d_second");
+  int64_t total = (int64_t)N * C * R * S;
+  weight_grad_post_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dmu_p, dsig2_p, second, second_is_sigma, N, C,
+                                                                                    R, S, d_mu, d_second, accumulate);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A4: eval-time weight sampling.  grid = (chunks of 4 weights, samples)
+// ---------------------------------------------------------------------------------------------
+__global__ void sample_weights_kernel(const float* __restrict__ mu_p, const float* __restrict__ sigma_p, int64_t n,
+                                      const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
+                                      float* __restrict__ w) {
+  int s = blockIdx.y;
+  int64_t n4 = (n + 3) >> 2;
+  const bool vec_ok = (n & 3) == 0;
+  float* ws = w + (int64_t)s * n;
+  const float* es = eps ? eps + (int64_t)s * n : nullptr;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n4; c += (int64_t)gridDim.x * blockDim.x) {
+    int64_t base = c << 2;
+    float z[4];
+    if (es) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z[j] = (base + j < n) ? es[base + j] : 0.f;
+    } else {
+      philox_normal4(seed, layer_id, sample0 + (uint32_t)s, (uint64_t)c, z);
+    }
+    if (vec_ok) {
+      float4 m = *reinterpret_cast<const float4*>(mu_p + base);
+      float4 sg = *reinterpret_cast<const float4*>(sigma_p + base);
+      // linear.py:46-47: std = mul(noise, softplus) ; weight = add(weight, std) -> two roundings
+      float4 o;
+      o.x = __fadd_rn(m.x, __fmul_rn(z[0], sg.x));
+      o.y = __fadd_rn(m.y, __fmul_rn(z[1], sg.y));
+      o.z = __fadd_rn(m.z, __fmul_rn(z[2], sg.z));
+      o.w = __fadd_rn(m.w, __fmul_rn(z[3], sg.w));
+      *reinterpret_cast<float4*>(ws + base) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (base + j < n) ws[base + j] = __fadd_rn(mu_p[base + j], __fmul_rn(z[j], sigma_p[base + j]));
+    }
+  }
+}
+
+extern "C" int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n_samples, const float* eps,
+                                  uint64_t seed, uint32_t layer_id, uint32_t sample0, float* w, void* stream) {
+  QBN_CHECK_ARG(mu_p && sigma_p && w, "null pointer");
+  QBN_CHECK_ARG(n > 0 && n_samples > 0 && n_samples <= 65535, "n>0, 0<n_samples<=65535");
+  int64_t n4 = (n + 3) / 4;
+  int gx = (int)((n4 + 255) / 256);
+  int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_p, sigma_p, n, eps, seed, layer_id, sample0, w);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A8: MC-Dropout, mask per (row, channel), broadcast over hw
+// ---------------------------------------------------------------------------------------------
+__global__ void dropout_mask_kernel(float* __restrict__ mask_out, int64_t n, float keep, uint64_t seed, uint32_t sa, uint32_t sb) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask_out[i] = philox_uniform1(seed, sa, sb, (uint64_t)i) < keep ? 1.0f : 0.0f;
+}
+
+__global__ void dropout_apply_kernel(const float* __restrict__ x, int64_t rows, int64_t hw, int64_t C,
+                                     const float* __restrict__ mask, float mult, float* __restrict__ out) {
+  int64_t total = rows * hw * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = i % C;
+    int64_t b = i / (hw * C);
+    // dropout.py:38-39: x = mul(x, mask) ; x = mul_scalar(x, multiplier)
+    out[i] = __fmul_rn(__fmul_rn(x[i], mask[b * C + c]), mult);
+  }
+}
+
+extern "C" int qbn_dropout_fwd(const float* x, int64_t rows, int64_t hw, int64_t C, const float* mask, float keep_prob,
+                               float mult, uint64_t seed, uint32_t sa, uint32_t sb, float* out, float* mask_out, void* stream) {
+  QBN_CHECK_ARG(x && out, "x/out");
+  QBN_CHECK_ARG(rows > 0 && hw > 0 && C > 0, "rows,hw,C > 0");
+  QBN_CHECK_ARG(mask || mask_out, "either an injected mask or a mask_out buffer for the Philox mask");
+  const float* m = mask;
+  if (!mask) {
+    dropout_mask_kernel<<<qbn_grid_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(mask_out, rows * C, keep_prob, seed, sa, sb);
+    QBN_CHECK_LAUNCH();
+    m = mask_out;
+  }
+  dropout_apply_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, hw, C, m, mult, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A5: KL + gradient, one pass
+// ---------------------------------------------------------------------------------------------
+__global__ void kl_kernel(const float* __restrict__ mu, const float* __restrict__ rho, int64_t n, float sp,
+                          float* __restrict__ kl_out, float* __restrict__ d_mu, float* __restrict__ d_rho, float gscale) {
+  double acc = 0.0;
+  const float inv_sp = 1.0f / sp;
+  const float inv_sp2 = inv_sp * inv_sp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float m = mu[i], r = rho[i];
+    float sg = softplus_f(r);
+    float a = sg * inv_sp, b = m * inv_sp;
+    acc += (double)(2.0f * logf(sp / sg) - 1.0f + a * a + b * b);
+    if (d_mu) d_mu[i] += gscale * m * inv_sp2;
+    if (d_rho) d_rho[i] += gscale * (sg * inv_sp2 - 1.0f / sg) * sigmoid_f(r);
+  }
+  // block reduction in double, one atomic per block
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(kl_out, (float)(0.5 * acc));
+  }
+}
+
+extern "C" int qbn_kl_fwd_bwd(const float* mu, const float* rho, int64_t n, float sigma_prior, float* kl_out, float* d_mu,
+                              float* d_rho, float grad_scale, void* stream) {
+  QBN_CHECK_ARG(mu && rho && kl_out, "null pointer");
+  QBN_CHECK_ARG(n > 0 && sigma_prior > 0.f, "n>0, sigma_prior>0");
+  kl_kernel<<<qbn_grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(mu, rho, n, sigma_prior, kl_out, d_mu, d_rho, grad_scale);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A7: fused observer (min/max + EMA + qparams) and fake-quantise
+//   workspace: [0] uint32 ticket counter (zero on entry, reset on exit), [16..] float2 partials
+// ---------------------------------------------------------------------------------------------
+#define FQ_MAX_BLOCKS 1024
+
+__global__ void fq_observe_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ state, float c, int qmin, int qmax,
+                                  float* __restrict__ scale, int32_t* __restrict__ zp, uint32_t* __restrict__ ticket,
+                                  float2* __restrict__ partial) {
+  float mn = INFINITY, mx = -INFINITY;
+  int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const bool al = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (al) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 v = x4[i];
+      mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+      mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      mn = fminf(mn, x[i]);
+      mx = fmaxf(mx, x[i]);
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      mn = fminf(mn, x[i]);
+      mx = fmaxf(mx, x[i]);
+    }
+  }
+  __shared__ float smn[32], smx[32];
+  __shared__ bool is_last;
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
+  __syncthreads();
+  if (wid == 0) {
+    mn = lane < (blockDim.x >> 5) ? smn[lane] : INFINITY;
+    mx = lane < (blockDim.x >> 5) ? smx[lane] : -INFINITY;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+      partial[blockIdx.x] = make_float2(mn, mx);
+      __threadfence();
+      uint32_t t = atomicAdd(ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // last block: fold partials, EMA (observer.py:668-683), qparams (observer.py:374-410)
+  __threadfence();
+  mn = INFINITY; mx = -INFINITY;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    float2 p = __ldcg(&partial[i]);
+    mn = fminf(mn, p.x);
+    mx = fmaxf(mx, p.y);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    float omin = state[0], omax = state[1];
+    if (state[2] == 0.0f) { omin = mn; omax = mx; }
+    else {
+      omin = __fadd_rn(omin, __fmul_rn(c, __fsub_rn(mn, omin)));
+      omax = __fadd_rn(omax, __fmul_rn(c, __fsub_rn(mx, omax)));
+    }
+    state[0] = omin; state[1] = omax; state[2] = 1.0f;
+    float mneg = fminf(omin, 0.0f), mpos = fmaxf(omax, 0.0f);
+    float sc = __fdiv_rn(__fsub_rn(mpos, mneg), (float)(qmax - qmin));
+    sc = fmaxf(sc, 1.1920928955078125e-07f);
+    int z = qmin - (int)rintf(__fdiv_rn(mneg, sc));
+    z = max(qmin, min(qmax, z));
+    *scale = sc;
+    *zp = z;
+    *ticket = 0u;
+  }
+}
+
+__global__ void fq_quant_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ scale,
+                                const int32_t* __restrict__ zp, int qmin, int qmax, float* __restrict__ y, uint8_t* __restrict__ mask) {
+  const float sc = *scale;
+  const float inv = __fdiv_rn(1.0f, sc);
+  const float z = (float)(*zp);
+  const float lo = (float)qmin, hi = (float)qmax;
+  int64_t n4 = n >> 2;
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                  (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0);
+  if (al) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      float q[4] = {rintf(__fmul_rn(v.x, inv)) + z, rintf(__fmul_rn(v.y, inv)) + z, rintf(__fmul_rn(v.z, inv)) + z,
+                    rintf(__fmul_rn(v.w, inv)) + z};
+      float o[4];
+      uint32_t mk = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bool in = q[j] >= lo && q[j] <= hi;
+        mk |= (in ? 1u : 0u) << (8 * j);
+        o[j] = __fmul_rn(fminf(fmaxf(q[j], lo), hi) - z, sc);
+      }
+      reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+      if (mask) reinterpret_cast<uint32_t*>(mask)[i] = mk;
+    }
+  }
+  int64_t start = al ? (n4 << 2) : 0;
+  for (int64_t i = start + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float q = rintf(__fmul_rn(x[i], inv)) + z;
+    bool in = q >= lo && q <= hi;
+    y[i] = __fmul_rn(fminf(fmaxf(q, lo), hi) - z, sc);
+    if (mask) mask[i] = in ? 1 : 0;
+  }
+}
+
+extern "C" int qbn_fake_quant_fwd(const float* x, int64_t n, float* state, float averaging_const, int observe, int qmin, int qmax,
+                                  float* scale, int32_t* zero_point, float* y, uint8_t* mask, void* workspace, void* stream) {
+  QBN_CHECK_ARG(x && scale && zero_point, "null pointer");
+  QBN_CHECK_ARG(n > 0 && qmin < qmax, "n>0, qmin<qmax");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (observe) {
+    QBN_CHECK_ARG(state && workspace, "observe needs state and workspace");
+    int blocks = qbn_grid_for((n + 3) / 4, 256, 4);
+    if (blocks > FQ_MAX_BLOCKS) blocks = FQ_MAX_BLOCKS;
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(workspace);
+    float2* partial = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + 16);
+    fq_observe_kernel<<<blocks, 256, 0, st>>>(x, n, state, averaging_const, qmin, qmax, scale, zero_point, ticket, partial);
+    QBN_CHECK_LAUNCH();
+  }
+  if (y) {
+    fq_quant_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, st>>>(x, n, scale, zero_point, qmin, qmax, y, mask);
+    QBN_CHECK_LAUNCH();
+  }
+  return QBN_OK;
+}
+
+__global__ void fq_bwd_kernel(const float* __restrict__ g, const uint8_t* __restrict__ mask, int64_t n, float* __restrict__ gx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    gx[i] = mask[i] ? g[i] : 0.0f;
+}
+
+extern "C" int qbn_fake_quant_bwd(const float* grad_y, const uint8_t* mask, int64_t n, float* grad_x, void* stream) {
+  QBN_CHECK_ARG(grad_y && mask && grad_x && n > 0, "null pointer / n");
+  fq_bwd_kernel<<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(grad_y, mask, n, grad_x);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A6 glue: quantise / dequantise, int8 weight sampling, quantised add, int8 dropout
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void quantize_kernel(const float* __restrict__ x, int64_t n, float inv, int zp, int qmin, int qmax, T* __restrict__ q) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int v = (int)rintf(__fmul_rn(x[i], inv)) + zp;
+    q[i] = (T)max(qmin, min(qmax, v));
+  }
+}
+
+extern "C" int qbn_quantize_u8(const float* x, int64_t n, float scale, int32_t zp, int qmin, int qmax, uint8_t* q, void* stream) {
+  QBN_CHECK_ARG(x && q && n > 0 && scale > 0.f, "x/q/n/scale");
+  QBN_CHECK_ARG(qmin >= 0 && qmax <= 255 && qmin <= qmax, "0<=qmin<=qmax<=255");
+  quantize_kernel<uint8_t><<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, 1.0f / scale, zp, qmin, qmax, q);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+extern "C" int qbn_quantize_s8(const float* x, int64_t n, float scale, int32_t zp, int qmin, int qmax, int8_t* q, void* stream) {
+  QBN_CHECK_ARG(x && q && n > 0 && scale > 0.f, "x/q/n/scale");
+  QBN_CHECK_ARG(qmin >= -128 && qmax <= 127 && qmin <= qmax, "-128<=qmin<=qmax<=127");
+  quantize_kernel<int8_t><<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, 1.0f / scale, zp, qmin, qmax, q);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void dequantize_u8_kernel(const uint8_t* __restrict__ q, int64_t n, float scale, int zp, float* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = __fmul_rn((float)((int)q[i] - zp), scale);
+}
+extern "C" int qbn_dequantize_u8(const uint8_t* q, int64_t n, float scale, int32_t zp, float* x, void* stream) {
+  QBN_CHECK_ARG(x && q && n > 0, "x/q/n");
+  dequantize_u8_kernel<<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(q, n, scale, zp, x);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+struct I8SampleConsts {
+  float inv_eps;   // 1.0f / s_eps
+  float mul_mult;  // s_sigma * s_eps * (1.0f / s_mul)   (ATen qmul)
+  float s_mu, premul_mu;    // vector-body dequantise: fma(s, q, -z*s)
+  float s_mul, premul_mul;
+  float inv_add;   // 1.0f / s_add
+  int z_mu, z_sigma, z_eps, z_mul, z_add, w_min, w_max;
+  int64_t n_vec;
+};
+
+QBN_DEVINL int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
+
+__global__ void i8_sample_weights_kernel(const int8_t* __restrict__ mu_q, const int8_t* __restrict__ sigma_q, int64_t n,
+                                         I8SampleConsts k, const float* __restrict__ eps, uint64_t seed, uint32_t layer_id,
+                                         uint32_t sample0, int8_t* __restrict__ w) {
+  int s = blockIdx.y;
+  int64_t n4 = (n + 3) >> 2;
+  int8_t* ws = w + (int64_t)s * n;
+  const float* es = eps ? eps + (int64_t)s * n : nullptr;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n4; c += (int64_t)gridDim.x * blockDim.x) {
+    int64_t base = c << 2;
+    float z[4];
+    if (es) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z[j] = (base + j < n) ? es[base + j] : 0.f;
+    } else {
+      philox_normal4(seed, layer_id, sample0 + (uint32_t)s, (uint64_t)c, z);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t i = base + j;
+      if (i >= n) break;
+      // (1) quantize_per_tensor(eps, NOISE_SCALE, 0, qint8)
+      int eq = clampi((int)rintf(__fmul_rn(z[j], k.inv_eps)) + k.z_eps, -128, 127);
+      // (2) quantized::mul(sigma_q, eps_q)
+      int prod = ((int)sigma_q[i] - k.z_sigma) * (eq - k.z_eps);
+      int r = clampi((int)rintf(__fmul_rn((float)prod, k.mul_mult)) + k.z_mul, -128, 127);
+      // (3) quantized::add(mu_q, r)
+      float da, db;
+      if (i < k.n_vec) {
+        da = __fmaf_rn(k.s_mu, (float)mu_q[i], k.premul_mu);
+        db = __fmaf_rn(k.s_mul, (float)r, k.premul_mul);
+      } else {
+        da = __fmul_rn((float)((int)mu_q[i] - k.z_mu), k.s_mu);
+        db = __fmul_rn((float)(r - k.z_mul), k.s_mul);
+      }
+      int wq = clampi((int)rintf(__fmul_rn(__fadd_rn(da, db), k.inv_add)) + k.z_add, -128, 127);
+      // (4) clamp_weight
+      ws[i] = (int8_t)clampi(wq, k.w_min, k.w_max);
+    }
+  }
+}
+
+extern "C" int qbn_i8_sample_weights(const int8_t* mu_q, const int8_t* sigma_q, int64_t n, int n_samples,
+                                     const qbn_i8_sample_params* p, const float* eps, uint64_t seed, uint32_t layer_id,
+                                     uint32_t sample0, int8_t* w, void* stream) {
+  QBN_CHECK_ARG(mu_q && sigma_q && p && w, "null pointer");
+  QBN_CHECK_ARG(n > 0 && n_samples > 0 && n_samples <= 65535, "n>0, 0<n_samples<=65535");
+  QBN_CHECK_ARG(p->s_mu > 0 && p->s_sigma > 0 && p->s_eps > 0 && p->s_mul > 0 && p->s_add > 0, "scales must be > 0");
+  I8SampleConsts k;
+  k.inv_eps = 1.0f / p->s_eps;
+  k.mul_mult = p->s_sigma * p->s_eps * (1.0f / p->s_mul);
+  k.s_mu = p->s_mu;
+  k.premul_mu = p->s_mu * (float)(-p->z_mu);
+  k.s_mul = p->s_mul;
+  k.premul_mul = p->s_mul * (float)(-p->z_mul);
+  k.inv_add = 1.0f / p->s_add;
+  k.z_mu = p->z_mu; k.z_sigma = p->z_sigma; k.z_eps = p->z_eps; k.z_mul = p->z_mul; k.z_add = p->z_add;
+  k.w_min = p->w_min; k.w_max = p->w_max;
+  k.n_vec = p->n_vec < 0 ? (n / 64) * 64 : p->n_vec;
+  int64_t n4 = (n + 3) / 4;
+  int gx = (int)((n4 + 255) / 256);
+  int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  i8_sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_q, sigma_q, n, k, eps, seed, layer_id, sample0, w);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void i8_add_kernel(const uint8_t* __restrict__ a, float sa, float pa, int za, const uint8_t* __restrict__ b, float sb,
+                              float pb, int zb, int64_t n, int64_t n_vec, float inv_so, int zo, int lo, int hi,
+                              uint8_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float da, db;
+    if (i < n_vec) {
+      da = __fmaf_rn(sa, (float)a[i], pa);
+      db = __fmaf_rn(sb, (float)b[i], pb);
+    } else {
+      da = __fmul_rn((float)((int)a[i] - za), sa);
+      db = __fmul_rn((float)((int)b[i] - zb), sb);
+    }
+    int q = (int)rintf(__fmul_rn(__fadd_rn(da, db), inv_so)) + zo;
+    out[i] = (uint8_t)clampi(q, lo, hi);
+  }
+}
+
+extern "C" int qbn_i8_add(const uint8_t* a, float sa, int32_t za, const uint8_t* b, float sb, int32_t zb, int64_t n,
+                          int64_t n_vec, float so, int32_t zo, int lo, int hi, uint8_t* out, void* stream) {
+  QBN_CHECK_ARG(a && b && out && n > 0, "null pointer / n");
+  QBN_CHECK_ARG(sa > 0 && sb > 0 && so > 0, "scales must be > 0");
+  QBN_CHECK_ARG(lo >= 0 && hi <= 255 && lo <= hi, "0<=lo<=hi<=255");
+  if (n_vec < 0) n_vec = (n / 64) * 64;
+  i8_add_kernel<<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, sa, sa * (float)(-za), za, b, sb, sb * (float)(-zb), zb, n,
+                                                                      n_vec, 1.0f / so, zo, lo, hi, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void i8_dropout_kernel(const uint8_t* __restrict__ x, int zx, int64_t rows, int64_t hw, int64_t C,
+                                  const float* __restrict__ mask, float keep, float inv_sm, int zm, float mult, uint64_t seed,
+                                  uint32_t sa, uint32_t sb, int lo, int hi, uint8_t* __restrict__ out) {
+  int64_t total = rows * hw * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = i % C;
+    int64_t b = i / (hw * C);
+    float m = mask ? mask[b * C + c] : (philox_uniform1(seed, sa, sb, (uint64_t)(b * C + c)) < keep ? 1.0f : 0.0f);
+    int mq = clampi((int)rintf(__fmul_rn(m, inv_sm)) + zm, 0, 255);  // dropout.py:34
+    int prod = ((int)x[i] - zx) * (mq - zm);
+    int q = (int)rintf(__fmul_rn((float)prod, mult)) + zm;           // quantized::mul, out at (s_m, z_m)
+    out[i] = (uint8_t)clampi(q, lo, hi);
+  }
+}
+
+extern "C" int qbn_i8_dropout(const uint8_t* x, float s_x, int32_t z_x, int64_t rows, int64_t hw, int64_t C, const float* mask,
+                              float keep_prob, float s_m, int32_t z_m, uint64_t seed, uint32_t sa, uint32_t sb, int lo, int hi,
+                              uint8_t* out, void* stream) {
+  QBN_CHECK_ARG(x && out, "x/out");
+  QBN_CHECK_ARG(rows > 0 && hw > 0 && C > 0 && s_x > 0 && s_m > 0, "sizes/scales");
+  float mult = s_x * s_m * (1.0f / s_m);
+  i8_dropout_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, z_x, rows, hw, C, mask, keep_prob,
+                                                                                     1.0f / s_m, z_m, mult, seed, sa, sb, lo, hi, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A11 glue at resolution changes
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool2x2_kernel(const float* __restrict__ x, int64_t B, int H, int W, int C, float* __restrict__ out) {
+  int Ho = H >> 1, Wo = W >> 1;
+  int64_t total = B * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int64_t b = t / Ho;
+    const float* p = x + ((b * H + 2 * ho) * W + 2 * wo) * C + c;
+    out[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(int64_t)W * C], p[(int64_t)W * C + C]));
+  }
+}
+extern "C" int qbn_maxpool2x2(const float* x, int64_t B, int H, int W, int C, float* out, void* stream) {
+  QBN_CHECK_ARG(x && out && B > 0 && H > 1 && W > 1 && C > 0, "args");
+  maxpool2x2_kernel<<<qbn_grid_for(B * (H / 2) * (W / 2) * C, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void avgpool_all_kernel(const float* __restrict__ x, int64_t B, int HW, int C, float* __restrict__ out) {
+  int64_t total = B * C;
+  const float inv = 1.0f / (float)HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t b = i / C;
+    float acc = 0.f;
+    for (int p = 0; p < HW; ++p) acc += x[(b * HW + p) * C + c];
+    out[i] = acc * inv;
+  }
+}
+extern "C" int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float* out, void* stream) {
+  QBN_CHECK_ARG(x && out && B > 0 && HW > 0 && C > 0, "args");
+  avgpool_all_kernel<<<qbn_grid_for(B * C, 256), 256, 0, (cudaStream_t)stream>>>(x, B, HW, C, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int64_t B, int C, int HW, float* __restrict__ out) {
+  // 32x32 smem transpose of the [C][HW] plane of each image
+  __shared__ float tile[32][33];
+  int64_t b = blockIdx.z;
+  int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* xb = x + b * (int64_t)C * HW;
+  float* ob = out + b * (int64_t)C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? xb[(int64_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    if (c < C && p < HW) ob[(int64_t)p * C + c] = tile[threadIdx.x][j];
+  }
+}
+extern "C" int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float* out, void* stream) {
+  QBN_CHECK_ARG(x && out && B > 0 && B <= 65535 && C > 0 && HW > 0, "args");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)B);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, B, C, HW, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

@@ -1,0 +1,522 @@
+// tcgen05 / TMEM implicit-GEMM kernels (QBN_MATH_TF32 and the int8 path) for sm_100a.
+//
+//   D[128 output pixels][N] (TMEM, fp32 or s32)  +=  A[128][K] (smem)  x  B[N][K]^T (smem)
+//
+// * One CTA owns a 128-pixel tile of ONE Monte-Carlo sample and the FULL output-channel extent,
+//   so the activation tile is read exactly once.  grid = (M/128, 1, samples).
+// * Operands are staged by four producer warps (LDG.128 -> registers -> STS.128) straight into
+//   the UMMA canonical K-major no-swizzle ("interleaved") layout: 16-byte K-chunks, 8-row core
+//   matrices of 128 contiguous bytes; LBO = distance between K-chunks, SBO = 128 B.  Going
+//   through registers is what lets the operand load be *fused*: im2col gather + zero padding,
+//   MC-Dropout mask (A8), x^2 for the LRT variance contraction (A1/A2) and the (x - z_x) shift
+//   of the int8 path all happen here, so none of those tensors ever exists in HBM.
+// * One elected thread of warp 4 issues tcgen05.mma (kind::tf32 / kind::i8); accumulators live in
+//   TMEM (LRT: two accumulators side by side: mean in columns [0,N), variance in [N,2N)).
+// * smem ring of `stages` slots, mbarrier full/empty pipeline; tcgen05.commit releases slots and
+//   finally signals the epilogue.
+// * Epilogue (the four producer warps again, one TMEM lane = one output pixel each):
+//   tcgen05.ld -> LRT: mean + sqrt(1e-8+var)*eps(+Philox) + bias | eval: affine (BN/bias),
+//   residual add, ReLU | int8: FBGEMM requantisation -> global.
+// All mbarrier waits are bounded (trap instead of hanging the GPU).
+#include <string.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int UM = 128;          // rows per CTA tile = TMEM lanes
+constexpr int KCH = 8;           // 16-byte K-chunks per stage (BLOCK_K = 128 bytes)
+constexpr int NPROD = 128;       // producer threads (warps 0-3), also the epilogue warps
+constexpr int NTHREADS = 160;    // + warp 4: TMEM allocator and MMA issuer
+
+enum { MODE_EVAL = 0, MODE_LRT = 1, MODE_I8 = 2 };
+
+QBN_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+QBN_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+QBN_DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+QBN_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait (2 s of %globaltimer): a protocol bug must trap (context error), never hang the GPU
+QBN_DEVINL uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+QBN_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it)
+      if (mbar_try_wait(bar, parity)) return;
+    if (global_ns() - t0 > 2000000000ull) {
+      printf("libqbn umma: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+QBN_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+QBN_DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+QBN_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+QBN_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+QBN_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+QBN_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+QBN_DEVINL void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+template <int MODE>
+QBN_DEVINL void umma_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (MODE == MODE_I8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// 32 lanes x 8 consecutive 32-bit columns: thread t of the warp gets lane (base+t)
+QBN_DEVINL void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+QBN_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1)
+QBN_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+struct UParams {
+  // geometry
+  int B, H, W, C, N, R, S, sh, sw, ph, pw, dh, dw, Ho, Wo, K;
+  int M;            // B*Ho*Wo (per sample)
+  int n_pad;        // MMA N (multiple of 16)
+  int acc_cols;     // TMEM columns used
+  int tmem_cols;    // allocated (power of two >= 32)
+  int stages;
+  int a_pitch;      // rows+pad per K-chunk in A stage (chunks of 16 B)
+  int b_pitch;
+  int x_shared, w_shared, relu;
+  uint32_t idesc;
+  // tensors
+  const void* x; const void* w; const void* w2;
+  const float* scale; const float* shift; const float* residual; const float* in_mask; float in_mult;
+  const float* bias; const float* eps; uint64_t seed; uint32_t sa, sb;
+  void* out; float* std_out;
+  // int8
+  int z_x, z_w, z_out, lo, hi; float atw, mult; int32_t* acc_dump;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool LRT = MODE == MODE_LRT;
+  constexpr bool I8 = MODE == MODE_I8;
+  constexpr int ESZ = I8 ? 1 : 4;           // operand element size
+  constexpr int EPC = 16 / ESZ;             // elements per 16-byte chunk
+  constexpr int BLOCK_K = KCH * EPC;        // 32 (tf32) or 128 (i8) K-elements per stage
+  constexpr int MMA_K = 32 / ESZ;           // 8 (tf32) or 32 (i8) per instruction = 2 chunks
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.x * UM;
+
+  // ---- shared memory carve-up -----------------------------------------------------------------
+  const uint32_t a_bytes = (uint32_t)KCH * p.a_pitch * 16;
+  const uint32_t b_bytes = (uint32_t)KCH * p.b_pitch * 16;
+  const uint32_t stage_bytes = (LRT ? 2 : 1) * (a_bytes + b_bytes);
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* accum_bar = bars + 2 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), NPROD);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp < 4) {
+    // =========================== PRODUCERS ======================================================
+    const int kc = tid & 7;          // this thread's 16-byte K-chunk inside every stage
+    const int r0 = tid >> 3;         // rows r0 + 16*i
+    const uint8_t* xs = reinterpret_cast<const uint8_t*>(p.x) + (p.x_shared ? 0 : (size_t)z * p.B * p.H * p.W * p.C * ESZ);
+    const uint8_t* ws = reinterpret_cast<const uint8_t*>(p.w) + (p.w_shared ? 0 : (size_t)z * p.N * p.K * ESZ);
+    const uint8_t* ws2 = LRT ? reinterpret_cast<const uint8_t*>(p.w2) : nullptr;
+    const float* msk = p.in_mask ? p.in_mask + (size_t)z * p.B * p.C : nullptr;
+
+    int rbase[8], rh0[8], rw0[8], rb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m = m0 + r0 + 16 * i;
+      bool v = m < p.M;
+      int mm = v ? m : 0;
+      int wo = mm % p.Wo;
+      int t = mm / p.Wo;
+      int ho = t % p.Ho;
+      int b = t / p.Ho;
+      rh0[i] = v ? ho * p.sh - p.ph : -(1 << 28);   // invalid rows fail every bounds test -> zeros
+      rw0[i] = wo * p.sw - p.pw;
+      rbase[i] = b * p.H * p.W * p.C;
+      rb[i] = b;
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      uint8_t* sa = ring + (size_t)stage * stage_bytes;
+      uint8_t* sa2 = sa + a_bytes;                              // LRT only
+      uint8_t* sb = sa + (LRT ? 2 : 1) * a_bytes;
+      uint8_t* sb2 = sb + b_bytes;                              // LRT only
+      const int k = kb * BLOCK_K + kc * EPC;                    // first K element of this chunk
+      // ---- A: im2col gather ---------------------------------------------------------------------
+      if constexpr (!I8) {
+        const bool kv = k < p.K;
+        const int kk = kv ? k : 0;
+        const int c = kk % p.C, rs = kk / p.C;
+        const int ds = (rs % p.S) * p.dw, dr = (rs / p.S) * p.dh;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int hi = rh0[i] + dr, wi = rw0[i] + ds;
+          bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            v[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xs) + rbase[i] + (hi * p.W + wi) * p.C + c));
+            if (msk) {  // A8: x * mask[b,c] * 1/(1-p) in the operand load (dropout.py:38-39)
+              float4 mk = __ldg(reinterpret_cast<const float4*>(msk + (size_t)rb[i] * p.C + c));
+              v[i].x = __fmul_rn(__fmul_rn(v[i].x, mk.x), p.in_mult);
+              v[i].y = __fmul_rn(__fmul_rn(v[i].y, mk.y), p.in_mult);
+              v[i].z = __fmul_rn(__fmul_rn(v[i].z, mk.z), p.in_mult);
+              v[i].w = __fmul_rn(__fmul_rn(v[i].w, mk.w), p.in_mult);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int row = r0 + 16 * i;
+          *reinterpret_cast<float4*>(sa + ((size_t)kc * p.a_pitch + row) * 16) = v[i];
+          if constexpr (LRT)
+            *reinterpret_cast<float4*>(sa2 + ((size_t)kc * p.a_pitch + row) * 16) =
+                make_float4(v[i].x * v[i].x, v[i].y * v[i].y, v[i].z * v[i].z, v[i].w * v[i].w);
+        }
+      } else {
+        // int8: two 8-byte pieces per chunk (C % 8 == 0 keeps each piece inside one filter tap);
+        // operand = (x - z_x) as s8 (activations are <= 7 bit, quant_utils.py:120), padding -> 0
+        uint2 pc[8][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k8 = k + 8 * h;
+          const bool kv = k8 < p.K;
+          const int kk = kv ? k8 : 0;
+          const int c = kk % p.C, rs = kk / p.C;
+          const int ds = (rs % p.S) * p.dw, dr = (rs / p.S) * p.dh;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int hi = rh0[i] + dr, wi = rw0[i] + ds;
+            bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            uint2 q = make_uint2(0u, 0u);
+            if (ok) {
+              q = __ldg(reinterpret_cast<const uint2*>(xs + rbase[i] + (hi * p.W + wi) * p.C + c));
+              const uint32_t zz = (uint32_t)p.z_x * 0x01010101u;
+              q.x = __vsub4(q.x, zz);
+              q.y = __vsub4(q.y, zz);
+            }
+            pc[i][h] = q;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int row = r0 + 16 * i;
+          *reinterpret_cast<uint4*>(sa + ((size_t)kc * p.a_pitch + row) * 16) = make_uint4(pc[i][0].x, pc[i][0].y, pc[i][1].x, pc[i][1].y);
+        }
+      }
+      // ---- B: weights [N][K] (per-sample, produced by the sampling kernel, L2 resident) -----------
+      for (int n = r0; n < p.n_pad; n += 16) {
+        uint4 q = make_uint4(0u, 0u, 0u, 0u), q2 = make_uint4(0u, 0u, 0u, 0u);
+        if (n < p.N && k < p.K) {
+          if constexpr (I8) {
+            const uint8_t* src = ws + (size_t)n * p.K + k;
+            if (k + 16 <= p.K) {
+              uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 8);
+              q = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+              uint2 lo = *reinterpret_cast<const uint2*>(src);
+              q = make_uint4(lo.x, lo.y, 0u, 0u);
+            }
+          } else {
+            q = *reinterpret_cast<const uint4*>(ws + ((size_t)n * p.K + k) * 4);
+            if constexpr (LRT) q2 = *reinterpret_cast<const uint4*>(ws2 + ((size_t)n * p.K + k) * 4);
+          }
+        } else if (I8 && n == p.N && k < p.K) {
+          // extra all-ones row: D[:, N] = sum_k (x - z_x), the row sums needed for the z_w correction
+          q = make_uint4(0x01010101u, 0x01010101u, (k + 8 < p.K) ? 0x01010101u : 0u, (k + 8 < p.K) ? 0x01010101u : 0u);
+        }
+        *reinterpret_cast<uint4*>(sb + ((size_t)kc * p.b_pitch + n) * 16) = q;
+        if constexpr (LRT) *reinterpret_cast<uint4*>(sb2 + ((size_t)kc * p.b_pitch + n) * 16) = q2;
+      }
+      fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&full_bar[stage]));
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // =========================== MMA ISSUER (warp 4) =============================================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t lbo_a = (uint32_t)p.a_pitch * 16, lbo_b = (uint32_t)p.b_pitch * 16;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
+        const uint32_t sa2 = sa + a_bytes;
+        const uint32_t sb = sa + (LRT ? 2 : 1) * a_bytes;
+        const uint32_t sb2 = sb + b_bytes;
+        const int krem = p.K - kb * BLOCK_K;
+        const int nmma = krem >= BLOCK_K ? KCH / 2 : (krem + MMA_K - 1) / MMA_K;
+        for (int j = 0; j < nmma; ++j) {
+          const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+          uint64_t ad = make_smem_desc(sa + 2 * j * lbo_a, lbo_a, 128);
+          uint64_t bd = make_smem_desc(sb + 2 * j * lbo_b, lbo_b, 128);
+          umma_mma<MODE>(tmem_base, ad, bd, p.idesc, acc);
+          if constexpr (LRT) {
+            uint64_t ad2 = make_smem_desc(sa2 + 2 * j * lbo_a, lbo_a, 128);
+            uint64_t bd2 = make_smem_desc(sb2 + 2 * j * lbo_b, lbo_b, 128);
+            umma_mma<MODE>(tmem_base + (uint32_t)p.n_pad, ad2, bd2, p.idesc, acc);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));            // slot free once these MMAs retire
+        if (kb == num_kb - 1) umma_commit(smem_u32(accum_bar));  // accumulators complete
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  }
+
+  // =============================== EPILOGUE (warps 0-3) ==========================================
+  if (warp < 4) {
+    mbar_wait(smem_u32(accum_bar), 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;        // TMEM lane == tile row
+    const bool mv = m < p.M;
+    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const size_t orow = ((size_t)z * p.M + (mv ? m : 0)) * p.N;
+    int rowsum = 0;
+    if constexpr (I8) {
+      uint32_t v[8];
+      tmem_ld8(tlane + (uint32_t)(p.N & ~7), v);   // column N holds sum_k (x - z_x)
+      tmem_ld_wait();
+      rowsum = (int)v[p.N & 7];
+    }
+    for (int c0 = 0; c0 < p.N; c0 += 8) {
+      uint32_t v[8], v2[8];
+      tmem_ld8(tlane + (uint32_t)c0, v);
+      if constexpr (LRT) tmem_ld8(tlane + (uint32_t)(p.n_pad + c0), v2);
+      tmem_ld_wait();
+      if (!mv) continue;
+      const int nvalid = min(8, p.N - c0);
+      if constexpr (MODE == MODE_EVAL) {
+        float* out = reinterpret_cast<float*>(p.out);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = __uint_as_float(v[j]);
+          if (j < nvalid) {
+            if (p.scale) a = __fmul_rn(a, __ldg(p.scale + c0 + j));
+            if (p.shift) a = __fadd_rn(a, __ldg(p.shift + c0 + j));
+            if (p.residual) a = __fadd_rn(a, __ldg(p.residual + orow + c0 + j));
+            if (p.relu) a = fmaxf(a, 0.f);
+          }
+          o[j] = a;
+        }
+        if (nvalid == 8 && ((orow + c0) & 3) == 0) {
+          *reinterpret_cast<float4*>(out + orow + c0) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(out + orow + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+          for (int j = 0; j < nvalid; ++j) out[orow + c0 + j] = o[j];
+        }
+      } else if constexpr (LRT) {
+        float* out = reinterpret_cast<float*>(p.out);
+        float e[8];
+        if (p.eps) {
+          for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? __ldg(p.eps + orow + c0 + j) : 0.f;
+        } else {
+          for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? philox_normal1(p.seed, p.sa, p.sb, (uint64_t)(orow + c0 + j)) : 0.f;
+        }
+        for (int j = 0; j < nvalid; ++j) {
+          float sd = sqrtf(1e-8f + __uint_as_float(v2[j]));
+          float r = __fadd_rn(__uint_as_float(v[j]), __fmul_rn(sd, e[j]));
+          if (p.bias) r = __fadd_rn(r, __ldg(p.bias + c0 + j));
+          out[orow + c0 + j] = r;
+          if (p.std_out) p.std_out[orow + c0 + j] = sd;
+        }
+      } else {
+        uint8_t* out = reinterpret_cast<uint8_t*>(p.out);
+        for (int j = 0; j < nvalid; ++j) {
+          // sum (x-z_x)(w-z_w) = sum (x-z_x) w  -  z_w * sum (x-z_x)
+          int acc = (int)v[j] - p.z_w * rowsum;
+          float xf = (float)acc;
+          if (p.bias) xf = __fadd_rn(xf, __fdiv_rn(__ldg(p.bias + c0 + j), p.atw));
+          int q = (int)rintf(__fmul_rn(xf, p.mult)) + p.z_out;
+          out[orow + c0 + j] = (uint8_t)max(p.lo, min(p.hi, q));
+          if (p.acc_dump) p.acc_dump[orow + c0 + j] = acc;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v <<= 1;
+  return v;
+}
+
+template <int MODE>
+static int launch_umma(UParams& p, int n_samples, cudaStream_t st, const char* who) {
+  constexpr bool LRT = MODE == MODE_LRT;
+  constexpr bool I8 = MODE == MODE_I8;
+  const int n_eff = I8 ? p.N + 1 : p.N;            // int8: one extra all-ones row (row sums)
+  p.n_pad = (n_eff + 15) / 16 * 16;
+  if (p.n_pad > 256 || (LRT && 2 * p.n_pad > 512)) {
+    qbn_set_error("%s: N=%d too wide for one TMEM tile", who, p.N);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  p.acc_cols = (LRT ? 2 : 1) * p.n_pad;
+  p.tmem_cols = pow2_cols(p.acc_cols);
+  p.a_pitch = UM + 1;                              // +1 chunk: conflict-free STS for the (row, kc) thread map
+  p.b_pitch = p.n_pad + 1;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format[4,6) a_format[7,10) b_format[10,13)
+  // a/b major = K (0), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
+  if (I8)
+    p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);  // S32, S8 x S8
+  else
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);  // F32, TF32 x TF32
+  const size_t stage_bytes = (size_t)(LRT ? 2 : 1) * KCH * 16 * (p.a_pitch + p.b_pitch);
+  constexpr int BLOCK_K = KCH * (I8 ? 16 : 4);
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages > num_kb) stages = num_kb;
+  if (stages < 1) {
+    qbn_set_error("%s: stage does not fit shared memory", who);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[MODE]) {
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set[MODE] = true;
+  }
+  dim3 grid((unsigned)((p.M + UM - 1) / UM), 1, (unsigned)n_samples);
+  umma_conv_kernel<MODE><<<grid, NTHREADS, smem, st>>>(p);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+static void fill_geom(UParams& p, const qbn_conv_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.N = d->N; p.R = d->R; p.S = d->S;
+  p.sh = d->stride_h; p.sw = d->stride_w; p.ph = d->pad_h; p.pw = d->pad_w; p.dh = d->dil_h; p.dw = d->dil_w;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.K = d->R * d->S * d->C;
+  p.M = d->B * d->Ho * d->Wo;
+}
+
+}  // namespace
+
+int qbn_umma_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const float* sig2_p, const float* bias,
+                     const float* eps, uint64_t seed, uint32_t sa, uint32_t sb, float* out, float* std_out, cudaStream_t st) {
+  if (d->C % 4 != 0) {
+    qbn_set_error("qbn_lrt_fwd(TF32): C=%d must be a multiple of 4 (pad the input channels)", d->C);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  UParams p;
+  fill_geom(p, d);
+  p.x = x; p.w = mu_p; p.w2 = sig2_p; p.x_shared = 1; p.w_shared = 1;
+  p.bias = bias; p.eps = eps; p.seed = seed; p.sa = sa; p.sb = sb; p.out = out; p.std_out = std_out;
+  return launch_umma<MODE_LRT>(p, 1, st, "qbn_lrt_fwd(TF32)");
+}
+
+int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x, const float* w, int w_shared,
+                      const float* scale, const float* shift, const float* residual, int relu, const float* in_mask,
+                      float in_mult, float* out, cudaStream_t st) {
+  if (d->C % 4 != 0) {
+    qbn_set_error("qbn_conv_fwd(TF32): C=%d must be a multiple of 4 (pad the input channels)", d->C);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  UParams p;
+  fill_geom(p, d);
+  p.x = x; p.w = w; p.x_shared = x_shared; p.w_shared = w_shared;
+  p.scale = scale; p.shift = shift; p.residual = residual; p.relu = relu; p.in_mask = in_mask; p.in_mult = in_mult;
+  p.out = out;
+  return launch_umma<MODE_EVAL>(p, n_samples, st, "qbn_conv_fwd(TF32)");
+}
+
+int qbn_umma_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const uint8_t* x, int z_x, const int8_t* w,
+                         int w_shared, int z_w, const float* bias, float act_times_w, float mult, int z_out, int lo, int hi,
+                         uint8_t* out, int32_t* acc_dump, cudaStream_t st) {
+  if (d->C % 8 != 0 || z_x < 0 || z_x > 127) {
+    qbn_set_error("qbn_i8_conv_fwd(tcgen05): needs C %% 8 == 0 and 0 <= z_x <= 127 (C=%d, z_x=%d)", d->C, z_x);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  UParams p;
+  fill_geom(p, d);
+  p.x = x; p.w = w; p.x_shared = x_shared; p.w_shared = w_shared;
+  p.z_x = z_x; p.z_w = z_w; p.bias = bias; p.atw = act_times_w; p.mult = mult; p.z_out = z_out; p.lo = lo; p.hi = hi;
+  p.out = out; p.acc_dump = acc_dump;
+  return launch_umma<MODE_I8>(p, n_samples, st, "qbn_i8_conv_fwd(tcgen05)");
+}

@@ -1,0 +1,95 @@
+"""Multi-GPU plumbing the reference does not have: one process per GPU,
+torch.distributed (NCCL on B200s, gloo in CPU tests).
+
+  * MC-sample sharding (inference): rank r owns a contiguous range of GLOBAL sample indices; noise
+    is keyed by the global index, so the union over ranks equals the single-GPU draw set.  Each
+    rank accumulates sum_s softmax locally; ONE allreduce(SUM) of the [B,K] buffer per batch.
+  * Data-parallel LRT training: parameters replicated, batch sharded, ONE flat allreduce(SUM) of
+    all gradients per step (12.6 MB for the ResNet: latency-bound, so a single bucket), after the
+    per-replica NaN-grad scrub of trainer.py:105-107.  The KL term is parameter-only: every rank
+    computes it and scales it with the GLOBAL batch (losses.py:24), it is not reduced twice.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total, rank, world):
+    """Contiguous split of `total` samples: (start, count) for `rank`; counts differ by at most 1."""
+    base, rem = divmod(total, world)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class ShardedMCPredictor:
+    """predict(x, S): every rank gets the full batch x; returns the same p-bar on every rank."""
+
+    def __init__(self, engine):
+        self.engine = engine
+
+    def predict(self, x, samples):
+        rank, ws = world()
+        start, count = shard_range(samples, rank, ws)
+        out = self.engine.predict_sum(x, count, sample0=start) if count > 0 else None
+        if self.engine.regression:
+            raise NotImplementedError("regression sharding: reduce (sum mu, sum mu^2, sum var) — see reduce_regression()")
+        if out is None:
+            raise RuntimeError("more ranks than samples")
+        if ws > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return out / float(samples)
+
+
+def allreduce_prob_sums(psum):
+    """The single collective of the sample-sharded eval path."""
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(psum, op=dist.ReduceOp.SUM)
+    return psum
+
+
+def reduce_regression(sum_mu, sum_mu2, sum_var, samples):
+    """Regression heads under sample sharding: allreduce the three running sums, then
+    mean = sum_mu/S ; var = (sum_mu2 - S*mean^2)/(S-1) + sum_var/S  (experiments/utils.py:349-353)."""
+    _, ws = world()
+    buf = torch.stack([sum_mu, sum_mu2, sum_var])
+    if ws > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    mean = buf[0] / samples
+    var = (buf[1] - samples * mean * mean) / max(samples - 1, 1) + buf[2] / samples
+    return mean, var
+
+
+def scrub_nan_grads(params):
+    """trainer.py:105-107: p.grad[p.grad != p.grad] = 0, per replica, BEFORE the allreduce."""
+    for p in params:
+        if p.grad is not None:
+            torch.nan_to_num_(p.grad, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+
+
+def allreduce_gradients(params, average=True):
+    """One flat bucket: flatten -> allreduce(SUM) -> (optionally / world) -> unflatten."""
+    _, ws = world()
+    grads = [p.grad for p in params if p.grad is not None]
+    if ws == 1 or not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat.div_(ws)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+def broadcast_parameters(model, src=0):
+    _, ws = world()
+    if ws == 1:
+        return
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src)

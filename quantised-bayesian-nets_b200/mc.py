@@ -1,0 +1,276 @@
+"""The Monte-Carlo loop of experiments/utils.py:330-377, re-designed for one B200.
+
+The reference runs S sequential Python-level forwards, each re-sampling every layer's weights
+through 4 elementwise kernels, appends S [B,10] outputs to a list, stacks and averages.  Here the
+model is compiled once into a short plan of fused steps and ALL samples of a chunk advance through
+a layer together (grid.z = sample):
+
+    sample_weights   W[s] = mu + sigma*eps_s      (Philox, one launch per layer, L2-resident output)
+    conv_forward     y[s] = act(bn(conv(x[s], W[s])) + residual[s])      (tcgen05, one launch per layer)
+    softmax_accumulate  psum += sum_s softmax(logits[s])                 (no [B,S,10] stack)
+
+Noise is keyed by the GLOBAL sample index, so any sharding of the S samples over GPUs (dist.py)
+reproduces the single-GPU result up to summation order.
+"""
+import torch
+import torch.nn as nn
+
+from . import config, noise, ops
+from ._lib import QBN_MATH_FP32, QBN_MATH_TF32
+from .stochastic.bbb.conv import Conv2d as BBBConv2d
+from .stochastic.bbb.linear import Linear as BBBLinear
+
+
+class _ConvStep:
+    __slots__ = ("mod", "src", "dst", "bn", "relu", "residual", "ref_idx", "is_linear", "flatten_hw")
+
+    def __init__(self, mod, src, dst, ref_idx):
+        self.mod, self.src, self.dst, self.ref_idx = mod, src, dst, ref_idx
+        self.bn, self.relu, self.residual = None, False, None
+        self.is_linear = isinstance(mod, BBBLinear)
+        self.flatten_hw = False
+
+
+class _PoolStep:
+    __slots__ = ("kind", "src", "dst")
+
+    def __init__(self, kind, src, dst):
+        self.kind, self.src, self.dst = kind, src, dst
+
+
+def _is_bbb(m):
+    return isinstance(m, (BBBConv2d, BBBLinear))
+
+
+class MCEngine:
+    """Compiled S-sample predictive pass for the reference's BBB model families
+    (LinearNetwork / ConvNetwork_LeNet / ConvNetwork_ResNet of models_bbb.py, or their qbn_b200.zoo
+    mirrors).  predict() == `_evaluate_with_loader`'s inner loop for one batch."""
+
+    def __init__(self, model, math_mode="tf32", chunk=10):
+        self.model = model
+        self.math_mode = {"fp32": QBN_MATH_FP32, "tf32": QBN_MATH_TF32}[math_mode] if isinstance(math_mode, str) else math_mode
+        self.chunk = int(chunk)
+        self.steps = []
+        self.regression = hasattr(model, "mu") and hasattr(model, "log_var")
+        self._nreg = 0
+        self._ref_idx = 0
+        self._compile(model)
+        self.n_noise = self._ref_idx
+        self.launches = 0
+        self._prepared = None
+
+    # ---- compilation ---------------------------------------------------------------------------
+    def _new(self):
+        self._nreg += 1
+        return self._nreg
+
+    def _conv(self, mod, src):
+        st = _ConvStep(mod, src, self._new(), self._ref_idx)
+        self._ref_idx += 1
+        self.steps.append(st)
+        return st
+
+    def _seq(self, mods, cur):
+        """Fuse Conv -> [BN] -> [ReLU] runs; returns (last register, last conv step or None)."""
+        last = None
+        for m in mods:
+            if _is_bbb(m):
+                last = self._conv(m, cur)
+                cur = last.dst
+            elif isinstance(m, nn.BatchNorm2d):
+                assert last is not None and last.bn is None and not last.relu, "BatchNorm must follow a BBB conv"
+                last.bn = m
+            elif isinstance(m, nn.ReLU):
+                assert last is not None and not last.relu, "ReLU must follow a BBB layer"
+                last.relu = True
+            elif isinstance(m, nn.MaxPool2d):
+                assert m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2)), "only 2x2/2 max-pool (models_bbb.py:106-108)"
+                dst = self._new()
+                self.steps.append(_PoolStep("max", cur, dst))
+                cur, last = dst, None
+            elif isinstance(m, nn.AvgPool2d):
+                dst = self._new()
+                self.steps.append(_PoolStep("avg", cur, dst))
+                cur, last = dst, None
+            elif type(m).__name__ in ("Flatten", "Identity", "QuantStub", "DeQuantStub"):
+                last = None
+            elif isinstance(m, nn.ModuleList):
+                for blk in m:
+                    cur = self._block(blk, cur)
+                last = None
+            elif hasattr(m, "stem") and hasattr(m, "shortcut"):
+                cur = self._block(m, cur)
+                last = None
+            else:
+                raise NotImplementedError("MCEngine: unsupported module %s" % type(m).__name__)
+        return cur, last
+
+    def _block(self, blk, cur):
+        """BasicBlock (models_bbb.py:170-183): relu(stem(x) + shortcut(x)); reference noise order is
+        stem.0, stem.3, shortcut.0 but the shortcut is EXECUTED first so that the residual add and
+        the final ReLU ride the epilogue of the second stem conv."""
+        first = len(self.steps)
+        ref0 = self._ref_idx
+        out, last = self._seq(list(blk.stem), cur)
+        n_stem = len(self.steps) - first
+        sc = cur
+        if len(blk.shortcut) > 0:
+            sc, _ = self._seq(list(blk.shortcut), cur)
+            sc_steps = self.steps[first + n_stem:]
+            del self.steps[first + n_stem:]
+            self.steps[first:first] = sc_steps      # run the shortcut first
+        assert last is not None and not last.relu
+        last.residual = sc
+        last.relu = True
+        assert self._ref_idx > ref0
+        return out
+
+    def _compile(self, model):
+        cur = 0  # register 0 = network input
+        if self.regression:
+            cur, _ = self._seq(list(model.layers), cur)
+            self.head_mu = self._conv(model.mu, cur)
+            self.head_lv = self._conv(model.log_var, cur)
+            self.out_reg = None
+        else:
+            cur, _ = self._seq(list(model.layers), cur)
+            self.out_reg = cur
+
+    # ---- per-call preparation: pack parameters once (they are shared by all samples) ---------------
+    def _prepare(self, device):
+        prep = {}
+        for st in self.steps:
+            if not isinstance(st, _ConvStep):
+                continue
+            m = st.mod
+            w, rho = m.weight.detach(), m.std.detach()
+            prep[id(st)] = {"w": w, "rho": rho}
+            scale = shift = None
+            if st.bn is not None:
+                bn = st.bn
+                scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+                shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+                if m.bias is not None:
+                    shift = shift + m.bias.detach() * scale
+            elif m.bias is not None:
+                shift = m.bias.detach().float().contiguous()
+            prep[id(st)].update(scale=scale, shift=shift)
+        return prep
+
+    def _packed(self, st, prep, x):
+        """Pack (mu, sigma) for the geometry this step sees (depends on the input's H, W for the
+        flatten->linear case, which runs as an HxW 'valid' convolution over the NHWC map)."""
+        e = prep[id(st)]
+        key = ("packed", tuple(x.shape[1:]))
+        if key in e:
+            return e[key]
+        m = st.mod
+        w, rho = e["w"], e["rho"]
+        if st.is_linear:
+            if x.dim() == 4 and (x.shape[2] > 1 or x.shape[3] > 1):
+                C, H, W = x.shape[1], x.shape[2], x.shape[3]
+                w4, rho4 = w.reshape(w.shape[0], C, H, W), rho.reshape(w.shape[0], C, H, W)
+                stride, pad, dil = (1, 1), (0, 0), (1, 1)
+            else:
+                w4, rho4 = w.reshape(w.shape[0], -1, 1, 1), rho.reshape(w.shape[0], -1, 1, 1)
+                stride, pad, dil = (1, 1), (0, 0), (1, 1)
+        else:
+            w4, rho4 = w, rho
+            stride, pad, dil = m.stride, m.padding, m.dilation
+        C = w4.shape[1]
+        cpad = 0
+        if self.math_mode == QBN_MATH_TF32 and C % 4 != 0 and C < 4:
+            cpad = 4 - C % 4   # 3-channel input layer: pad channels so 16-byte K-chunks stay inside a tap
+            w4 = torch.nn.functional.pad(w4, (0, 0, 0, 0, 0, cpad))
+            rho4 = torch.nn.functional.pad(rho4, (0, 0, 0, 0, 0, cpad), value=-200.0)  # softplus -> 0
+        packed = ops.weight_prep(w4.contiguous(), rho4.contiguous(), False, None, want=("mu", "sigma"))
+        if cpad:
+            packed["sigma"] = torch.where(packed["sigma"] < 1e-30, torch.zeros_like(packed["sigma"]), packed["sigma"])
+        info = dict(mu=packed["mu"], sigma=packed["sigma"], wshape=tuple(w4.shape), stride=stride, pad=pad, dil=dil, cpad=cpad,
+                    orig_shape=tuple(w.shape) if not st.is_linear else (w.shape[0], w4.shape[1] - cpad, w4.shape[2], w4.shape[3]))
+        e[key] = info
+        return info
+
+    # ---- execution -------------------------------------------------------------------------------
+    def _run_chunk(self, x, n, sample0, prep, injected):
+        """Advance samples [sample0, sample0+n) through every step.  Returns the head output(s)."""
+        regs = {0: x}
+        shared = {0: True}
+        B = x.shape[0]
+        seed = noise.seed()
+        for st in self.steps:
+            src = regs[st.src]
+            if isinstance(st, _PoolStep):
+                regs[st.dst] = ops.maxpool2x2(src) if st.kind == "max" else ops.avgpool_all(src).reshape(src.shape[0], src.shape[1], 1, 1)
+                shared[st.dst] = shared[st.src]
+                self.launches += 1
+                continue
+            info = self._packed(st, prep, src)
+            if info["cpad"]:
+                src = torch.nn.functional.pad(src, (0, 0, 0, 0, 0, info["cpad"])).contiguous(memory_format=ops.CL)
+            if src.dim() == 2:
+                src = src.reshape(src.shape[0], src.shape[1], 1, 1)
+            N, C, R, S_ = info["wshape"]
+            nb = src.shape[0] if shared[st.src] else src.shape[0] // n
+            d = ops.make_desc(nb, src.shape[2], src.shape[3], C, N, R, S_, info["stride"], info["pad"], info["dil"])
+            eps = None
+            if injected is not None:
+                es = []
+                for s in range(n):
+                    e = injected[s][st.ref_idx].reshape(info["orig_shape"]).float()
+                    if info["cpad"]:
+                        e = torch.nn.functional.pad(e, (0, 0, 0, 0, 0, info["cpad"]))
+                    es.append(ops.pack_ohwi(e))
+                eps = torch.stack(es).contiguous()
+            w = ops.sample_weights(info["mu"], info["sigma"], n, eps, seed, st.mod._qbn_layer_id, sample0)
+            e = prep[id(st)]
+            mode = self.math_mode if config.tf32_eligible(C, N, False) else QBN_MATH_FP32
+            res = regs[st.residual] if st.residual is not None else None
+            if res is not None and shared.get(st.residual, False):
+                res = res.repeat(n, 1, 1, 1).contiguous(memory_format=ops.CL)   # only if a block reads the raw input
+            out = ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, st.relu, None, 1.0, mode)
+            self.launches += 2
+            regs[st.dst] = out
+            shared[st.dst] = False
+        if self.regression:
+            return regs[self.head_mu.dst].reshape(n, B), regs[self.head_lv.dst].reshape(n, B)
+        logits = regs[self.out_reg]
+        return logits.reshape(n, B, -1)
+
+    @torch.no_grad()
+    def predict_sum(self, x, samples, sample0=0, injected=None):
+        """Sum over samples [sample0, sample0+samples) of softmax(logits) -> [B,K] (classification) or
+        (sum mu, sum mu^2, sum var) building blocks (regression: returns stacked [S,B] mu and var)."""
+        if not x.is_cuda:
+            raise RuntimeError("MCEngine needs CUDA tensors (no CPU fallback)")
+        x = ops.nhwc(x.float()) if x.dim() == 4 else x.float().contiguous().reshape(x.shape[0], -1, 1, 1)
+        prep = self._prepare(x.device)
+        psum = None
+        mus, lvs = [], []
+        done = 0
+        while done < samples:
+            n = min(self.chunk, samples - done)
+            inj = injected[done:done + n] if injected is not None else None
+            out = self._run_chunk(x, n, sample0 + done, prep, inj)
+            if self.regression:
+                mus.append(out[0])
+                lvs.append(out[1])
+            else:
+                psum = ops.softmax_accumulate(out.contiguous(), psum)
+                self.launches += 1
+            done += n
+        if self.regression:
+            return torch.cat(mus), torch.cat(lvs).exp()
+        return psum
+
+    @torch.no_grad()
+    def predict(self, x, samples, sample0=0, injected=None):
+        """Classification: mean_s softmax (experiments/utils.py:355).  Regression: (mean, var) of
+        experiments/utils.py:349-353."""
+        out = self.predict_sum(x, samples, sample0, injected)
+        if self.regression:
+            mu, var = out
+            self.launches += 1
+            return ops.reg_mc_reduce(mu, var)
+        return out / float(samples)

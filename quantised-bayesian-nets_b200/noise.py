@@ -1,0 +1,68 @@
+"""Noise source of the stochastic layers.
+
+The reference draws every eps / dropout mask from torch's global generator.  Here
+the default source is the device-side Philox stream (seed, layer id, draw counter) — nothing is
+materialised in HBM.  For parity tests a queue of *injected* tensors can be installed; layers then
+consume them in forward order, exactly like the reference consumes its generator."""
+import contextlib
+
+import torch
+
+_state = {"seed": None, "counter": 0, "queue": None, "next_layer_id": 1, "sample_index": None}
+
+
+def manual_seed(seed):
+    _state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _state["counter"] = 0
+
+
+def seed():
+    if _state["seed"] is None:
+        _state["seed"] = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    return _state["seed"]
+
+
+def new_layer_id():
+    i = _state["next_layer_id"]
+    _state["next_layer_id"] += 1
+    return i
+
+
+def next_draw():
+    """A fresh stream_b for one draw (one forward of one layer)."""
+    if _state["sample_index"] is not None:
+        return int(_state["sample_index"])
+    c = _state["counter"]
+    _state["counter"] = (c + 1) & 0xFFFFFFFF
+    return c
+
+
+def pop_injected():
+    q = _state["queue"]
+    if q is None:
+        return None
+    if not q:
+        raise RuntimeError("noise.inject(): queue exhausted — the model drew more noise tensors than were injected")
+    return q.pop(0)
+
+
+@contextlib.contextmanager
+def inject(tensors):
+    """with noise.inject([eps0, eps1, ...]): y = model(x)   # layers consume in forward order"""
+    old = _state["queue"]
+    _state["queue"] = list(tensors)
+    try:
+        yield
+    finally:
+        _state["queue"] = old
+
+
+@contextlib.contextmanager
+def sample_index(idx):
+    """Pin stream_b to a GLOBAL Monte-Carlo sample index: draws become independent of sharding."""
+    old = _state["sample_index"]
+    _state["sample_index"] = idx
+    try:
+        yield
+    finally:
+        _state["sample_index"] = old

@@ -1,0 +1,454 @@
+"""Thin tensor-level wrappers over the C ABI (include/qbn.h) + the autograd Functions.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every arithmetic step of the
+hot path runs in libqbn's sm_100a kernels.  There is no fallback: a non-CUDA tensor raises.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, I8SampleParams, QBN_MATH_FP32, QBN_MATH_TF32  # noqa: F401
+
+CL = torch.channels_last
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.QbnError("libqbn ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t
+
+
+def pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv_out(h, k, s, p, d):
+    return (h + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def make_desc(B, H, W, C, N, R, S, stride=(1, 1), padding=(0, 0), dilation=(1, 1)):
+    stride, padding, dilation = pair(stride), pair(padding), pair(dilation)
+    d = ConvDesc()
+    d.B, d.H, d.W, d.C, d.N, d.R, d.S = B, H, W, C, N, R, S
+    d.stride_h, d.stride_w = stride
+    d.pad_h, d.pad_w = padding
+    d.dil_h, d.dil_w = dilation
+    d.Ho = conv_out(H, R, stride[0], padding[0], dilation[0])
+    d.Wo = conv_out(W, S, stride[1], padding[1], dilation[1])
+    return d
+
+
+def nhwc(x):
+    """Logical NCHW tensor whose memory is dense NHWC (no copy if it already is)."""
+    return x.contiguous(memory_format=CL) if x.dim() == 4 else x.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# RNG hooks
+# ------------------------------------------------------------------------------------------------
+def philox_u32(n, seed, stream_a=0, stream_b=0, device="cuda"):
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    _lib.call("qbn_philox_u32", _ptr(out), n, seed, stream_a, stream_b, _stream())
+    return out
+
+
+def philox_normal(n, seed, stream_a=0, stream_b=0, device="cuda"):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    _lib.call("qbn_philox_normal", _ptr(out), n, seed, stream_a, stream_b, _stream())
+    return out
+
+
+def philox_bernoulli(n, keep_prob, seed, stream_a=0, stream_b=0, device="cuda"):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    _lib.call("qbn_philox_bernoulli", _ptr(out), n, float(keep_prob), seed, stream_a, stream_b, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter packing
+# ------------------------------------------------------------------------------------------------
+def weight_prep(mu, second, second_is_sigma=False, chan_scale=None, want=("mu", "sigma", "sigma2")):
+    """OIHW (or [N,K]) parameters -> packed OHWI operands.  Returns dict of flat [N*K] tensors."""
+    _need_cuda(mu, second)
+    mu, second = _f32(mu).contiguous(), _f32(second).contiguous()
+    if mu.dim() == 2:
+        N, C, R, S = mu.shape[0], mu.shape[1], 1, 1
+    else:
+        N, C, R, S = mu.shape
+    out = {k: torch.empty(N * C * R * S, dtype=torch.float32, device=mu.device) for k in want}
+    _lib.call("qbn_weight_prep", _ptr(mu), _ptr(second), int(second_is_sigma), N, C, R, S,
+              _ptr(chan_scale.contiguous() if chan_scale is not None else None),
+              _ptr(out.get("mu")), _ptr(out.get("sigma")), _ptr(out.get("sigma2")), _stream())
+    return out
+
+
+def weight_grad_post(dmu_p, dsig2_p, second, second_is_sigma, shape):
+    if len(shape) == 2:
+        N, C, R, S = shape[0], shape[1], 1, 1
+    else:
+        N, C, R, S = shape
+    d_mu = torch.empty(shape, dtype=torch.float32, device=dmu_p.device)
+    d_second = torch.empty(shape, dtype=torch.float32, device=dmu_p.device)
+    _lib.call("qbn_weight_grad_post", _ptr(dmu_p), _ptr(dsig2_p), _ptr(second.contiguous()), int(second_is_sigma), N, C, R, S,
+              _ptr(d_mu), _ptr(d_second), 0, _stream())
+    return d_mu, d_second
+
+
+# ------------------------------------------------------------------------------------------------
+# A1-A3 local reparametrisation
+# ------------------------------------------------------------------------------------------------
+def _geom(x, wshape, stride, padding, dilation):
+    if x.dim() == 2:
+        B, C = x.shape
+        H = W = 1
+        N, R, S = wshape[0], 1, 1
+    else:
+        B, C, H, W = x.shape
+        N, _, R, S = wshape
+    return make_desc(B, H, W, C, N, R, S, stride, padding, dilation)
+
+
+def _out_like(x, d, dtype=torch.float32, lead=None):
+    if x.dim() == 2:
+        shape = (d.B, d.N)
+        if lead is not None:
+            shape = (lead,) + shape
+        return torch.empty(shape, dtype=dtype, device=x.device)
+    if lead is not None:
+        return torch.empty((lead * d.B, d.N, d.Ho, d.Wo), dtype=dtype, device=x.device, memory_format=CL)
+    return torch.empty((d.B, d.N, d.Ho, d.Wo), dtype=dtype, device=x.device, memory_format=CL)
+
+
+def lrt_forward(x, mu_p, sig2_p, bias, d, eps=None, key=(0, 0, 0), math_mode=QBN_MATH_FP32, want_std=True):
+    """x already NHWC-dense.  eps (optional) laid out like the output (NHWC-dense)."""
+    out = _out_like(x, d)
+    std = _out_like(x, d) if want_std else None
+    _lib.call("qbn_lrt_fwd", ctypes.byref(d), _ptr(x), _ptr(mu_p), _ptr(sig2_p), _ptr(bias), _ptr(eps),
+              key[0], key[1], key[2], _ptr(out), _ptr(std), math_mode, _stream())
+    return out, std
+
+
+def lrt_backward(x, mu_p, sig2_p, g, std, d, eps=None, key=(0, 0, 0), need_dx=True, need_dbias=False, math_mode=QBN_MATH_FP32):
+    nbytes = _lib.load().qbn_lrt_bwd_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    dx = torch.empty_like(x) if need_dx else None
+    dmu_p = torch.empty_like(mu_p)
+    dsig2_p = torch.empty_like(sig2_p)
+    dbias = torch.empty(d.N, dtype=torch.float32, device=x.device) if need_dbias else None
+    _lib.call("qbn_lrt_bwd", ctypes.byref(d), _ptr(x), _ptr(mu_p), _ptr(sig2_p), _ptr(g), _ptr(std), _ptr(eps),
+              key[0], key[1], key[2], _ptr(dx), _ptr(dmu_p), _ptr(dsig2_p), _ptr(dbias), _ptr(ws), nbytes, math_mode, _stream())
+    return dx, dmu_p, dsig2_p, dbias
+
+
+class LRTFunction(torch.autograd.Function):
+    """out = x*mu + sqrt(1e-8 + x^2*softplus(rho)^2) * eps + bias  (linear.py:32-40, conv.py:24-32)
+    with the closed-form backward of SURVEY §8a row A3.  `second` is rho, or sigma itself when
+    second_is_sigma (QAT: sigma was fake-quantised upstream, conv_qat.py:28-32)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, second, bias, stride, padding, dilation, eps, key, math_mode, second_is_sigma, chan_scale):
+        _need_cuda(x, weight, second)
+        xc = nhwc(_f32(x))
+        d = _geom(xc, weight.shape, stride, padding, dilation)
+        packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))
+        eps_c = nhwc(_f32(eps)) if eps is not None else None
+        out, std = lrt_forward(xc, packed["mu"], packed["sigma2"], _f32(bias), d, eps_c, key, math_mode)
+        ctx.save_for_backward(xc, packed["mu"], packed["sigma2"], std, eps_c, second.detach())
+        ctx.d, ctx.key, ctx.math_mode, ctx.second_is_sigma = d, key, math_mode, second_is_sigma
+        ctx.wshape = tuple(weight.shape)
+        ctx.has_bias = bias is not None
+        ctx.chan_scale = chan_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, mu_p, sig2_p, std, eps_c, second = ctx.saved_tensors
+        gc = nhwc(_f32(g))
+        need_dx = ctx.needs_input_grad[0]
+        dx, dmu_p, dsig2_p, dbias = lrt_backward(xc, mu_p, sig2_p, gc, std, ctx.d, eps_c, ctx.key, need_dx, ctx.has_bias,
+                                                 QBN_MATH_FP32)
+        if ctx.chan_scale is not None:
+            raise _lib.QbnError("LRTFunction.backward with chan_scale: fold the scale outside (QAT ConvBn2d does)")
+        d_mu, d_second = weight_grad_post(dmu_p, dsig2_p, second, ctx.second_is_sigma, ctx.wshape)
+        return dx, d_mu, d_second, dbias, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# A4 eval-time sampling + contraction
+# ------------------------------------------------------------------------------------------------
+def sample_weights(mu_p, sigma_p, n_samples=1, eps=None, seed=0, layer_id=0, sample0=0):
+    n = mu_p.numel()
+    w = torch.empty((n_samples, n), dtype=torch.float32, device=mu_p.device)
+    _lib.call("qbn_sample_weights", _ptr(mu_p), _ptr(sigma_p), n, n_samples, _ptr(eps), seed, layer_id, sample0, _ptr(w), _stream())
+    return w
+
+
+def conv_forward(x, w, d, n_samples=1, x_shared=True, w_shared=False, scale=None, shift=None, residual=None, relu=False,
+                 in_mask=None, in_mult=1.0, math_mode=QBN_MATH_FP32, out=None):
+    """x NHWC-dense ([B,..] if x_shared else [S*B,..]); w [S][N][K] packed.  Returns [S*B, N, Ho, Wo]
+    (channels-last) or [S, B, N] for linear geometry."""
+    if out is None:
+        out = _out_like(x, d, lead=n_samples) if (n_samples > 1 or not x_shared) else _out_like(x, d)
+        if x.dim() == 2 and out.dim() == 3 and n_samples == 1:
+            out = out[0]
+    _lib.call("qbn_conv_fwd", ctypes.byref(d), n_samples, int(x_shared), _ptr(x), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
+              _ptr(residual), int(relu), _ptr(in_mask), float(in_mult), _ptr(out), math_mode, _stream())
+    return out
+
+
+def pack_ohwi(t):
+    """[N,C,R,S] (or [N,K]) tensor -> flat packed OHWI order (host-side plumbing for injected noise)."""
+    if t.dim() == 4:
+        return t.permute(0, 2, 3, 1).contiguous().reshape(-1)
+    return t.contiguous().reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# A5 KL
+# ------------------------------------------------------------------------------------------------
+class KLFunction(torch.autograd.Function):
+    """utils_bbb.py:3-5 with mu_prior=0 and scalar sigma_prior; value and gradient in one pass."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, sigma_prior):
+        _need_cuda(mu, rho)
+        mu_c, rho_c = _f32(mu).contiguous(), _f32(rho).contiguous()
+        kl = torch.zeros((), dtype=torch.float32, device=mu.device)
+        need = mu.requires_grad or rho.requires_grad
+        d_mu = torch.zeros_like(mu_c) if need else None
+        d_rho = torch.zeros_like(rho_c) if need else None
+        _lib.call("qbn_kl_fwd_bwd", _ptr(mu_c), _ptr(rho_c), mu_c.numel(), float(sigma_prior), _ptr(kl), _ptr(d_mu), _ptr(d_rho),
+                  1.0, _stream())
+        if need:
+            ctx.save_for_backward(d_mu, d_rho)
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        d_mu, d_rho = ctx.saved_tensors
+        return g * d_mu, g * d_rho, None
+
+
+def kl_divergence(mu, rho, sigma_prior):
+    return KLFunction.apply(mu, rho, float(sigma_prior))
+
+
+# ------------------------------------------------------------------------------------------------
+# A8 MC-Dropout
+# ------------------------------------------------------------------------------------------------
+def dropout_forward(x, p, mask=None, key=(0, 0, 0)):
+    """dropout.py:15-40 (float branch).  x NCHW-logical/NHWC-dense or [B,C]; mask [B,C] injected or Philox."""
+    _need_cuda(x)
+    xc = nhwc(_f32(x))
+    if xc.dim() == 4:
+        B, C, H, W = xc.shape
+        hw = H * W
+    else:
+        B, C = xc.shape
+        hw = 1
+    out = torch.empty_like(xc)
+    mult = float((torch.ones(1) / (1.0 - torch.ones(1) * p)).item())  # dropout.py:10, fp32 like the Parameter
+    mask_out = torch.empty((B, C), dtype=torch.float32, device=x.device) if mask is None else None
+    _lib.call("qbn_dropout_fwd", _ptr(xc), B, hw, C, _ptr(mask.contiguous() if mask is not None else None), float(1.0 - p), mult,
+              key[0], key[1], key[2], _ptr(out), _ptr(mask_out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# A7 fake quantisation
+# ------------------------------------------------------------------------------------------------
+class FakeQuantState:
+    """Device-side MovingAverageMinMaxObserver + qparams (observer.py:374-410,668-683)."""
+
+    def __init__(self, qmin, qmax, averaging_constant=0.01, device="cuda"):
+        self.qmin, self.qmax, self.c = int(qmin), int(qmax), float(averaging_constant)
+        self.state = torch.tensor([math.inf, -math.inf, 0.0], dtype=torch.float32, device=device)
+        self.scale = torch.ones(1, dtype=torch.float32, device=device)
+        self.zero_point = torch.zeros(1, dtype=torch.int32, device=device)
+        self.workspace = torch.zeros(16 + 8 * 1024, dtype=torch.uint8, device=device)
+
+
+class FakeQuantFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fq, observe):
+        _need_cuda(x)
+        xc = _f32(x).contiguous()
+        y = torch.empty_like(xc)
+        mask = torch.empty(xc.shape, dtype=torch.uint8, device=x.device)
+        _lib.call("qbn_fake_quant_fwd", _ptr(xc), xc.numel(), _ptr(fq.state), fq.c, int(observe), fq.qmin, fq.qmax,
+                  _ptr(fq.scale), _ptr(fq.zero_point), _ptr(y), _ptr(mask), _ptr(fq.workspace), _stream())
+        ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        gc = _f32(g).contiguous()
+        gx = torch.empty_like(gc)
+        _lib.call("qbn_fake_quant_bwd", _ptr(gc), _ptr(mask), gc.numel(), _ptr(gx), _stream())
+        return gx, None, None
+
+
+def fake_quantize(x, fq, observe=True):
+    return FakeQuantFunction.apply(x, fq, observe)
+
+
+# ------------------------------------------------------------------------------------------------
+# A6 int8
+# ------------------------------------------------------------------------------------------------
+def quantize_u8(x, scale, zp, qmin=0, qmax=255):
+    xc = _f32(x).contiguous()
+    q = torch.empty(xc.shape, dtype=torch.uint8, device=x.device)
+    _lib.call("qbn_quantize_u8", _ptr(xc), xc.numel(), float(scale), int(zp), qmin, qmax, _ptr(q), _stream())
+    return q
+
+
+def quantize_s8(x, scale, zp, qmin=-128, qmax=127):
+    xc = _f32(x).contiguous()
+    q = torch.empty(xc.shape, dtype=torch.int8, device=x.device)
+    _lib.call("qbn_quantize_s8", _ptr(xc), xc.numel(), float(scale), int(zp), qmin, qmax, _ptr(q), _stream())
+    return q
+
+
+def dequantize_u8(q, scale, zp):
+    x = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    _lib.call("qbn_dequantize_u8", _ptr(q), q.numel(), float(scale), int(zp), _ptr(x), _stream())
+    return x
+
+
+def i8_sample_weights(mu_q, sigma_q, params, n_samples=1, eps=None, seed=0, layer_id=0, sample0=0):
+    """mu_q/sigma_q flat int8 in packed OHWI order; params: I8SampleParams."""
+    n = mu_q.numel()
+    w = torch.empty((n_samples, n), dtype=torch.int8, device=mu_q.device)
+    _lib.call("qbn_i8_sample_weights", _ptr(mu_q), _ptr(sigma_q), n, n_samples, ctypes.byref(params), _ptr(eps), seed, layer_id,
+              sample0, _ptr(w), _stream())
+    return w
+
+
+def i8_conv_forward(x_q, s_x, z_x, w_q, s_w, z_w, d, bias, s_out, z_out, relu, act_bits=7, n_samples=1, x_shared=True,
+                    w_shared=False, want_acc=False, path=0, linear=False):
+    """x_q uint8 NHWC-dense; w_q int8 [S][N][K] packed.  Returns uint8 NHWC-dense output (+ int32 acc)."""
+    lead = n_samples if (n_samples > 1 or not x_shared) else None
+    if linear:
+        shape = (d.B, d.N) if lead is None else (lead, d.B, d.N)
+        out = torch.empty(shape, dtype=torch.uint8, device=x_q.device)
+        acc = torch.empty(shape, dtype=torch.int32, device=x_q.device) if want_acc else None
+    else:
+        nb = d.B if lead is None else lead * d.B
+        out = torch.empty((nb, d.N, d.Ho, d.Wo), dtype=torch.uint8, device=x_q.device, memory_format=CL)
+        acc = torch.empty((nb, d.N, d.Ho, d.Wo), dtype=torch.int32, device=x_q.device, memory_format=CL) if want_acc else None
+    amax = (1 << act_bits) - 1
+    _lib.call("qbn_i8_conv_fwd", ctypes.byref(d), n_samples, int(x_shared), _ptr(x_q), float(s_x), int(z_x), _ptr(w_q), int(w_shared),
+              float(s_w), int(z_w), _ptr(bias), float(s_out), int(z_out), int(relu), 0, amax, _ptr(out), _ptr(acc), int(path), _stream())
+    return (out, acc) if want_acc else out
+
+
+def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=7, n_vec=-1):
+    out = torch.empty_like(a)
+    _lib.call("qbn_i8_add", _ptr(a), float(sa), int(za), _ptr(b), float(sb), int(zb), a.numel(), n_vec, float(so), int(zo), 0,
+              (1 << act_bits) - 1, _ptr(out), _stream())
+    return out
+
+
+def i8_dropout(x_q, s_x, z_x, p, s_m, z_m, mask=None, key=(0, 0, 0), act_bits=7):
+    if x_q.dim() == 4:
+        B, C, H, W = x_q.shape
+        hw = H * W
+    else:
+        B, C = x_q.shape
+        hw = 1
+    out = torch.empty_like(x_q)
+    _lib.call("qbn_i8_dropout", _ptr(x_q), float(s_x), int(z_x), B, hw, C, _ptr(mask), float(1.0 - p), float(s_m), int(z_m),
+              key[0], key[1], key[2], 0, (1 << act_bits) - 1, _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# A9 / A10
+# ------------------------------------------------------------------------------------------------
+def softmax_accumulate(logits, psum=None):
+    """logits [S,B,K] -> psum [B,K] (+)= sum_s softmax(logits_s)."""
+    S, B, K = logits.shape
+    acc = psum is not None
+    if psum is None:
+        psum = torch.empty((B, K), dtype=torch.float32, device=logits.device)
+    _lib.call("qbn_softmax_accumulate", _ptr(logits.contiguous()), S, B, K, _ptr(psum), int(acc), _stream())
+    return psum
+
+
+def mc_mean(probs):
+    """probs [S, ...] -> mean over S (experiments/utils.py:355)."""
+    S = probs.shape[0]
+    pc = _f32(probs).contiguous()
+    out = torch.empty(pc.shape[1:], dtype=torch.float32, device=probs.device)
+    _lib.call("qbn_mc_mean", _ptr(pc), S, out.numel(), _ptr(out), _stream())
+    return out
+
+
+def reg_mc_reduce(mu, var):
+    """mu, var [S,B] -> (mean, var_total) (experiments/utils.py:349-353)."""
+    S = mu.shape[0]
+    muc, varc = _f32(mu).contiguous(), _f32(var).contiguous()
+    n = muc.numel() // S
+    mean = torch.empty(muc.shape[1:], dtype=torch.float32, device=mu.device)
+    vout = torch.empty(muc.shape[1:], dtype=torch.float32, device=mu.device)
+    _lib.call("qbn_reg_mc_reduce", _ptr(muc), _ptr(varc), S, n, _ptr(mean), _ptr(vout), _stream())
+    return mean, vout
+
+
+def cls_metrics_accumulate(probs, target, out, scale=1.0, n_bins=10):
+    """out [4+3*n_bins] fp32 device accumulator (see include/qbn.h)."""
+    B, K = probs.shape
+    _lib.call("qbn_cls_metrics", _ptr(_f32(probs).contiguous()), _ptr(target.contiguous()), B, K, float(scale), n_bins, _ptr(out), _stream())
+    return out
+
+
+def reg_metrics_accumulate(mean, var, target, out):
+    m, v, t = _f32(mean).contiguous().reshape(-1), _f32(var).contiguous().reshape(-1), _f32(target).contiguous().reshape(-1)
+    _lib.call("qbn_reg_metrics", _ptr(m), _ptr(v), _ptr(t), m.numel(), _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# glue
+# ------------------------------------------------------------------------------------------------
+def maxpool2x2(x):
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device, memory_format=CL)
+    _lib.call("qbn_maxpool2x2", _ptr(x), B, H, W, C, _ptr(out), _stream())
+    return out
+
+
+def avgpool_all(x):
+    B, C, H, W = x.shape
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    _lib.call("qbn_avgpool_all", _ptr(x), B, H * W, C, _ptr(out), _stream())
+    return out
+
+
+def nchw_to_nhwc(x):
+    B, C, H, W = x.shape
+    xc = _f32(x).contiguous()
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device, memory_format=CL)
+    _lib.call("qbn_nchw_to_nhwc", _ptr(xc), B, C, H * W, _ptr(out), _stream())
+    return out
