@@ -69,6 +69,7 @@ int qbn_philox_bernoulli(float* out, int64_t n, float keep_prob, uint64_t seed, 
  * (BN fold, conv.py:70-80 / conv_qat.py:140-143).  Outputs (each nullable) are packed OHWI. */
 int qbn_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int R,
                     int S, const float* chan_scale, float* mu_p, float* sigma_p, float* sigma2_p,
+                    int round_tf32 /* round mu_p and sigma2_p to TF32 (LRT operands of the tcgen05 path) */,
                     void* stream);
 /* chain rule back to the nn.Module parameters: d_mu[OIHW] = dmu_p ; d_rho = dsig2_p * 2*sigma *
  * sigmoid(rho)  (or d_sigma = dsig2_p * 2*sigma when second_is_sigma) — SURVEY §8a row A3.
@@ -101,16 +102,23 @@ int qbn_lrt_bwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const
  * sample0+s, i).  The buffer is a few MB and is consumed straight out of L2 by qbn_conv_fwd.  */
 int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n_samples,
                        const float* eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
-                       float* w, void* stream);
+                       float* w, int round_tf32 /* store W rounded to TF32 (RNA) for the tcgen05 path */,
+                       void* stream);
 
 /* y = conv(x, w[s]) for every Monte-Carlo sample s in one launch, with the caller-side glue of
  * models_bbb.py:170-183,226-245 folded into the epilogue: per-channel affine (eval BatchNorm or
  * bias), residual add (src/utils.py:49-55), ReLU.  x: [n_samples][B].. or, if x_shared, [B]..
  * read by every sample.  in_mask (nullable) is the A8 MC-Dropout mask [n_samples*B][C] applied to
  * the operand load with multiplier in_mult (dropout.py:15-40).  out: [n_samples][B][Ho][Wo][N]. */
+#define QBN_FLAG_RELU 1            /* ReLU in the epilogue                                      */
+#define QBN_FLAG_A_TF32_READY 2    /* TF32 mode: x is already TF32-exact (e.g. written by a previous
+                                      launch with OUT_ROUND_TF32) -> operand goes global->smem by
+                                      cp.async; otherwise it is rounded (cvt.rna) in registers   */
+#define QBN_FLAG_OUT_ROUND_TF32 4  /* TF32 mode: round the stored activations to TF32 (RNA) so the
+                                      next layer can take the cp.async path                      */
 int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x,
                  const float* w, int w_shared, const float* scale, const float* shift,
-                 const float* residual, int relu, const float* in_mask, float in_mult, float* out,
+                 const float* residual, int flags, const float* in_mask, float in_mult, float* out,
                  int math_mode, void* stream);
 
 /* ---- A8 standalone: x[b,h,w,c] * mask[b,c] * mult (dropout.py:35-39); mask NULL -> Philox ---- */

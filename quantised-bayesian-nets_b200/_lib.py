@@ -10,6 +10,9 @@ LIB_PATH = os.path.join(HERE, "csrc", "libqbn.so")
 
 QBN_MATH_FP32 = 0
 QBN_MATH_TF32 = 1
+QBN_FLAG_RELU = 1
+QBN_FLAG_A_TF32_READY = 2
+QBN_FLAG_OUT_ROUND_TF32 = 4
 
 
 class ConvDesc(Structure):
@@ -31,12 +34,12 @@ _SIGNATURES = {
     "qbn_philox_u32": (c_int, [P, c_int64, c_uint64, c_uint32, c_uint32, P]),
     "qbn_philox_normal": (c_int, [P, c_int64, c_uint64, c_uint32, c_uint32, P]),
     "qbn_philox_bernoulli": (c_int, [P, c_int64, c_float, c_uint64, c_uint32, c_uint32, P]),
-    "qbn_weight_prep": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "qbn_weight_prep": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P]),
     "qbn_weight_grad_post": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
     "qbn_lrt_fwd": (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_uint64, c_uint32, c_uint32, P, P, c_int, P]),
     "qbn_lrt_bwd_workspace_bytes": (c_size_t, [POINTER(ConvDesc)]),
     "qbn_lrt_bwd": (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_uint64, c_uint32, c_uint32, P, P, P, P, P, c_size_t, c_int, P]),
-    "qbn_sample_weights": (c_int, [P, P, c_int64, c_int, P, c_uint64, c_uint32, c_uint32, P, P]),
+    "qbn_sample_weights": (c_int, [P, P, c_int64, c_int, P, c_uint64, c_uint32, c_uint32, P, c_int, P]),
     "qbn_conv_fwd": (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, c_int, P, P, P, c_int, P, c_float, P, c_int, P]),
     "qbn_dropout_fwd": (c_int, [P, c_int64, c_int64, c_int64, P, c_float, c_float, c_uint64, c_uint32, c_uint32, P, P, P]),
     "qbn_kl_fwd_bwd": (c_int, [P, P, c_int64, c_float, P, P, P, c_float, P]),

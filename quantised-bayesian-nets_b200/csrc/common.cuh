@@ -120,6 +120,16 @@ QBN_DEVINL float philox_uniform1(uint64_t seed, uint32_t sa, uint32_t sb, uint64
 QBN_DEVINL float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 QBN_DEVINL float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container (cvt.rna.tf32.f32).  The
+// tensor core ignores the 13 low mantissa bits of a kind::tf32 operand, i.e. truncates; rounding
+// first halves the error and removes its bias, which otherwise compounds through 21 layers.
+QBN_DEVINL uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+QBN_DEVINL float tf32_round(float x) { return __uint_as_float(tf32_rna(x)); }
+
 QBN_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

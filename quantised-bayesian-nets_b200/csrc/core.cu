@@ -115,7 +115,8 @@ extern "C" int qbn_philox_bernoulli(float* out, int64_t n, float keep_prob, uint
 // ---------------------------------------------------------------------------------------------
 __global__ void weight_prep_kernel(const float* __restrict__ mu, const float* __restrict__ second, int second_is_sigma,
                                    int N, int C, int R, int S, const float* __restrict__ chan_scale,
-                                   float* __restrict__ mu_p, float* __restrict__ sigma_p, float* __restrict__ sigma2_p) {
+                                   float* __restrict__ mu_p, float* __restrict__ sigma_p, float* __restrict__ sigma2_p,
+                                   int round_tf32) {
   int64_t total = (int64_t)N * C * R * S;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // i indexes the packed OHWI order
@@ -133,19 +134,22 @@ __global__ void weight_prep_kernel(const float* __restrict__ mu, const float* __
       m = __fmul_rn(m, cs);
       sg = __fmul_rn(sg, cs);
     }
+    float s2 = __fmul_rn(sg, sg);
+    if (round_tf32) { m = tf32_round(m); s2 = tf32_round(s2); }
     if (mu_p) mu_p[i] = m;
     if (sigma_p) sigma_p[i] = sg;
-    if (sigma2_p) sigma2_p[i] = __fmul_rn(sg, sg);
+    if (sigma2_p) sigma2_p[i] = s2;
   }
 }
 
 extern "C" int qbn_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int R, int S,
-                               const float* chan_scale, float* mu_p, float* sigma_p, float* sigma2_p, void* stream) {
+                               const float* chan_scale, float* mu_p, float* sigma_p, float* sigma2_p, int round_tf32,
+                               void* stream) {
   QBN_CHECK_ARG(mu && second, "mu/second");
   QBN_CHECK_ARG(N > 0 && C > 0 && R > 0 && S > 0, "N,C,R,S > 0");
   int64_t total = (int64_t)N * C * R * S;
   weight_prep_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mu, second, second_is_sigma, N, C, R, S,
-                                                                               chan_scale, mu_p, sigma_p, sigma2_p);
+                                                                               chan_scale, mu_p, sigma_p, sigma2_p, round_tf32);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -193,7 +197,7 @@ extern "C" int qbn_weight_grad_post(const float* dmu_p, const float* dsig2_p, co
 // ---------------------------------------------------------------------------------------------
 __global__ void sample_weights_kernel(const float* __restrict__ mu_p, const float* __restrict__ sigma_p, int64_t n,
                                       const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
-                                      float* __restrict__ w) {
+                                      float* __restrict__ w, int round_tf32) {
   int s = blockIdx.y;
   int64_t n4 = (n + 3) >> 2;
   const bool vec_ok = (n & 3) == 0;
@@ -217,17 +221,21 @@ __global__ void sample_weights_kernel(const float* __restrict__ mu_p, const floa
       o.y = __fadd_rn(m.y, __fmul_rn(z[1], sg.y));
       o.z = __fadd_rn(m.z, __fmul_rn(z[2], sg.z));
       o.w = __fadd_rn(m.w, __fmul_rn(z[3], sg.w));
+      if (round_tf32) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
       *reinterpret_cast<float4*>(ws + base) = o;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (base + j < n) ws[base + j] = __fadd_rn(mu_p[base + j], __fmul_rn(z[j], sigma_p[base + j]));
+        if (base + j < n) {
+          float o = __fadd_rn(mu_p[base + j], __fmul_rn(z[j], sigma_p[base + j]));
+          ws[base + j] = round_tf32 ? tf32_round(o) : o;
+        }
     }
   }
 }
 
 extern "C" int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n_samples, const float* eps,
-                                  uint64_t seed, uint32_t layer_id, uint32_t sample0, float* w, void* stream) {
+                                  uint64_t seed, uint32_t layer_id, uint32_t sample0, float* w, int round_tf32, void* stream) {
   QBN_CHECK_ARG(mu_p && sigma_p && w, "null pointer");
   QBN_CHECK_ARG(n > 0 && n_samples > 0 && n_samples <= 65535, "n>0, 0<n_samples<=65535");
   int64_t n4 = (n + 3) / 4;
@@ -235,7 +243,7 @@ extern "C" int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64
   int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_p, sigma_p, n, eps, seed, layer_id, sample0, w);
+  sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_p, sigma_p, n, eps, seed, layer_id, sample0, w, round_tf32);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -239,7 +239,7 @@ struct FwdEval : PixelRows {
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; const float* in_mask;
   float* out;
   float in_mult;
-  int x_shared, w_shared, relu;
+  int x_shared, w_shared, flags;
   int64_t x_sample_stride, w_sample_stride;
   const float* xs; const float* ws; const float* ms; int zs;
   __device__ void begin(int z) {
@@ -270,7 +270,7 @@ struct FwdEval : PixelRows {
     if (scale) v = __fmul_rn(v, scale[n]);
     if (shift) v = __fadd_rn(v, shift[n]);
     if (residual) v = __fadd_rn(v, residual[o]);
-    if (relu) v = fmaxf(v, 0.f);
+    if (flags & QBN_FLAG_RELU) v = fmaxf(v, 0.f);
     out[o] = v;
   }
 };
@@ -421,7 +421,7 @@ static void launch(P& p, int64_t rows, int cols, int nz, cudaStream_t st) {
 int qbn_umma_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const float* sig2_p, const float* bias,
                      const float* eps, uint64_t seed, uint32_t sa, uint32_t sb, float* out, float* std_out, cudaStream_t st);
 int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x, const float* w, int w_shared,
-                      const float* scale, const float* shift, const float* residual, int relu, const float* in_mask,
+                      const float* scale, const float* shift, const float* residual, int flags, const float* in_mask,
                       float in_mult, float* out, cudaStream_t st);
 
 extern "C" int qbn_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const float* sig2_p, const float* bias,
@@ -447,19 +447,19 @@ extern "C" int qbn_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* 
 }
 
 extern "C" int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x, const float* w, int w_shared,
-                            const float* scale, const float* shift, const float* residual, int relu, const float* in_mask,
+                            const float* scale, const float* shift, const float* residual, int flags, const float* in_mask,
                             float in_mult, float* out, int math_mode, void* stream) {
   QBN_CHECK_ARG(check_desc(d), "conv descriptor inconsistent");
   QBN_CHECK_ARG(x && w && out, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && n_samples <= 65535, "0 < n_samples <= 65535");
   cudaStream_t st = (cudaStream_t)stream;
   if (math_mode == QBN_MATH_TF32)
-    return qbn_umma_conv_fwd(d, n_samples, x_shared, x, w, w_shared, scale, shift, residual, relu, in_mask, in_mult, out, st);
+    return qbn_umma_conv_fwd(d, n_samples, x_shared, x, w, w_shared, scale, shift, residual, flags, in_mask, in_mult, out, st);
   QBN_CHECK_ARG(math_mode == QBN_MATH_FP32, "math_mode");
   Geom g = make_geom(d);
 #define QBN_FILL_EVAL(p)                                                                                        \
   p.g = g; p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.in_mask = in_mask;      \
-  p.out = out; p.in_mult = in_mult; p.x_shared = x_shared; p.w_shared = w_shared; p.relu = relu;                 \
+  p.out = out; p.in_mult = in_mult; p.x_shared = x_shared; p.w_shared = w_shared; p.flags = flags;                 \
   p.x_sample_stride = (int64_t)g.B * g.H * g.W * g.C; p.w_sample_stride = (int64_t)g.N * g.K;
   if (g.N <= 32) {
     FwdEval<32> p; QBN_FILL_EVAL(p);

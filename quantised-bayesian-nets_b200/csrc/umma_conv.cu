@@ -107,6 +107,17 @@ QBN_DEVINL void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
                : "r"(taddr)
                : "memory");
 }
+// 16-byte LDGSTS with zero-fill: copies src_bytes (0, 8 or 16) and zero-fills the rest of the 16
+QBN_DEVINL void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+QBN_DEVINL void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier arrival is deferred until all cp.async issued so far by this thread have completed
+QBN_DEVINL void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 QBN_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1)
@@ -129,7 +140,7 @@ struct UParams {
   int stages;
   int a_pitch;      // rows+pad per K-chunk in A stage (chunks of 16 B)
   int b_pitch;
-  int x_shared, w_shared, relu;
+  int x_shared, w_shared, flags;
   uint32_t idesc;
   // tensors
   const void* x; const void* w; const void* w2;
@@ -207,8 +218,92 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
       rb[i] = b;
     }
 
+    // Two operand-staging paths:
+    //  (a) cp.async (LDGSTS, zero-fill for padding) straight into the UMMA layout — used whenever the
+    //      operand needs no arithmetic on the way (eval A without dropout mask and TF32-ready, all B);
+    //      the thread never waits for the data: cp.async.mbarrier.arrive.noinc signals the stage's
+    //      full barrier when its copies land, so up to `stages` stages of loads are in flight per CTA.
+    //  (b) registers (LDG.128 -> transform -> STS.128) for fused transforms: MC-Dropout mask, RNA
+    //      rounding to TF32, x^2 for the LRT variance operand, (x - z_x) for int8.  Loads of stage
+    //      kb+1 are issued before stage kb is published (one stage of register prefetch).
+    const bool a_async = (MODE == MODE_EVAL) && msk == nullptr && (p.flags & QBN_FLAG_A_TF32_READY);
+    constexpr int AV = I8 ? 2 : 1;               // 8-byte pieces (i8) or one 16-byte chunk (fp32)
+    uint4 areg[8];
+
+    auto tap_of = [&](int k, int& c, int& dr, int& ds) {
+      const int kk = k < p.K ? k : 0;
+      c = kk % p.C;
+      const int rs = kk / p.C;
+      ds = (rs % p.S) * p.dw;
+      dr = (rs / p.S) * p.dh;
+    };
+    auto load_a_regs = [&](int kb) {
+      const int k = kb * BLOCK_K + kc * EPC;
+      if constexpr (!I8) {
+        int c, dr, ds;
+        tap_of(k, c, dr, ds);
+        const bool kv = k < p.K;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int hi = rh0[i] + dr, wi = rw0[i] + ds;
+          const bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+          areg[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) areg[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(xs) + rbase[i] + (hi * p.W + wi) * p.C + c));
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < AV; ++h) {
+          const int k8 = k + 8 * h;
+          int c, dr, ds;
+          tap_of(k8, c, dr, ds);
+          const bool kv = k8 < p.K;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int hi = rh0[i] + dr, wi = rw0[i] + ds;
+            const bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            uint2 q = make_uint2(0u, 0u);
+            if (ok) {
+              // int8: two 8-byte pieces per chunk (C % 8 == 0 keeps each piece inside one filter tap);
+              // operand = (x - z_x) as s8 (activations are <= 7 bit, quant_utils.py:120), padding -> 0
+              q = __ldg(reinterpret_cast<const uint2*>(xs + rbase[i] + (hi * p.W + wi) * p.C + c));
+              const uint32_t zz = (uint32_t)p.z_x * 0x01010101u;
+              q.x = __vsub4(q.x, zz);
+              q.y = __vsub4(q.y, zz);
+            }
+            if (h == 0) { areg[i].x = q.x; areg[i].y = q.y; } else { areg[i].z = q.x; areg[i].w = q.y; }
+          }
+        }
+      }
+    };
+    auto store_a_regs = [&](int kb, uint8_t* sa, uint8_t* sa2) {
+      if constexpr (I8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sa + ((size_t)kc * p.a_pitch + r0 + 16 * i) * 16) = areg[i];
+      } else {
+        const int k = kb * BLOCK_K + kc * EPC;
+        int c, dr, ds;
+        tap_of(k, c, dr, ds);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 v = make_float4(__uint_as_float(areg[i].x), __uint_as_float(areg[i].y), __uint_as_float(areg[i].z), __uint_as_float(areg[i].w));
+          if (msk) {  // A8: x * mask[b,c] * 1/(1-p) in the operand load (dropout.py:38-39)
+            const float4 mk = __ldg(reinterpret_cast<const float4*>(msk + (size_t)rb[i] * p.C + c));
+            v.x = __fmul_rn(__fmul_rn(v.x, mk.x), p.in_mult);
+            v.y = __fmul_rn(__fmul_rn(v.y, mk.y), p.in_mult);
+            v.z = __fmul_rn(__fmul_rn(v.z, mk.z), p.in_mult);
+            v.w = __fmul_rn(__fmul_rn(v.w, mk.w), p.in_mult);
+          }
+          const size_t off = ((size_t)kc * p.a_pitch + r0 + 16 * i) * 16;
+          *reinterpret_cast<uint4*>(sa + off) = make_uint4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          if constexpr (LRT)
+            *reinterpret_cast<uint4*>(sa2 + off) = make_uint4(tf32_rna(v.x * v.x), tf32_rna(v.y * v.y), tf32_rna(v.z * v.z), tf32_rna(v.w * v.w));
+        }
+      }
+    };
+
     int stage = 0;
     uint32_t phase = 0;
+    if (!a_async) load_a_regs(0);
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
       uint8_t* sa = ring + (size_t)stage * stage_bytes;
@@ -216,94 +311,45 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
       uint8_t* sb = sa + (LRT ? 2 : 1) * a_bytes;
       uint8_t* sb2 = sb + b_bytes;                              // LRT only
       const int k = kb * BLOCK_K + kc * EPC;                    // first K element of this chunk
-      // ---- A: im2col gather ---------------------------------------------------------------------
-      if constexpr (!I8) {
+      // ---- A ---------------------------------------------------------------------------------------
+      if (a_async) {
+        int c, dr, ds;
+        tap_of(k, c, dr, ds);
         const bool kv = k < p.K;
-        const int kk = kv ? k : 0;
-        const int c = kk % p.C, rs = kk / p.C;
-        const int ds = (rs % p.S) * p.dw, dr = (rs / p.S) * p.dh;
-        float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          int hi = rh0[i] + dr, wi = rw0[i] + ds;
-          bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            v[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xs) + rbase[i] + (hi * p.W + wi) * p.C + c));
-            if (msk) {  // A8: x * mask[b,c] * 1/(1-p) in the operand load (dropout.py:38-39)
-              float4 mk = __ldg(reinterpret_cast<const float4*>(msk + (size_t)rb[i] * p.C + c));
-              v[i].x = __fmul_rn(__fmul_rn(v[i].x, mk.x), p.in_mult);
-              v[i].y = __fmul_rn(__fmul_rn(v[i].y, mk.y), p.in_mult);
-              v[i].z = __fmul_rn(__fmul_rn(v[i].z, mk.z), p.in_mult);
-              v[i].w = __fmul_rn(__fmul_rn(v[i].w, mk.w), p.in_mult);
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int row = r0 + 16 * i;
-          *reinterpret_cast<float4*>(sa + ((size_t)kc * p.a_pitch + row) * 16) = v[i];
-          if constexpr (LRT)
-            *reinterpret_cast<float4*>(sa2 + ((size_t)kc * p.a_pitch + row) * 16) =
-                make_float4(v[i].x * v[i].x, v[i].y * v[i].y, v[i].z * v[i].z, v[i].w * v[i].w);
+          const int hi = rh0[i] + dr, wi = rw0[i] + ds;
+          const bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+          const float* src = reinterpret_cast<const float*>(xs) + (ok ? rbase[i] + (hi * p.W + wi) * p.C + c : 0);
+          cp_async16(smem_u32(sa + ((size_t)kc * p.a_pitch + r0 + 16 * i) * 16), src, ok ? 16u : 0u);
         }
       } else {
-        // int8: two 8-byte pieces per chunk (C % 8 == 0 keeps each piece inside one filter tap);
-        // operand = (x - z_x) as s8 (activations are <= 7 bit, quant_utils.py:120), padding -> 0
-        uint2 pc[8][2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k8 = k + 8 * h;
-          const bool kv = k8 < p.K;
-          const int kk = kv ? k8 : 0;
-          const int c = kk % p.C, rs = kk / p.C;
-          const int ds = (rs % p.S) * p.dw, dr = (rs / p.S) * p.dh;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            int hi = rh0[i] + dr, wi = rw0[i] + ds;
-            bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-            uint2 q = make_uint2(0u, 0u);
-            if (ok) {
-              q = __ldg(reinterpret_cast<const uint2*>(xs + rbase[i] + (hi * p.W + wi) * p.C + c));
-              const uint32_t zz = (uint32_t)p.z_x * 0x01010101u;
-              q.x = __vsub4(q.x, zz);
-              q.y = __vsub4(q.y, zz);
-            }
-            pc[i][h] = q;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int row = r0 + 16 * i;
-          *reinterpret_cast<uint4*>(sa + ((size_t)kc * p.a_pitch + row) * 16) = make_uint4(pc[i][0].x, pc[i][0].y, pc[i][1].x, pc[i][1].y);
-        }
+        store_a_regs(kb, sa, sa2);
+        if (kb + 1 < num_kb) load_a_regs(kb + 1);               // prefetch the next stage into registers
       }
-      // ---- B: weights [N][K] (per-sample, produced by the sampling kernel, L2 resident) -----------
+      // ---- B: weights [N][K] (per-sample output of the sampling kernel, L2 resident) -----------------
       for (int n = r0; n < p.n_pad; n += 16) {
-        uint4 q = make_uint4(0u, 0u, 0u, 0u), q2 = make_uint4(0u, 0u, 0u, 0u);
-        if (n < p.N && k < p.K) {
-          if constexpr (I8) {
-            const uint8_t* src = ws + (size_t)n * p.K + k;
-            if (k + 16 <= p.K) {
-              uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 8);
-              q = make_uint4(lo.x, lo.y, hi.x, hi.y);
-            } else {
-              uint2 lo = *reinterpret_cast<const uint2*>(src);
-              q = make_uint4(lo.x, lo.y, 0u, 0u);
-            }
-          } else {
-            q = *reinterpret_cast<const uint4*>(ws + ((size_t)n * p.K + k) * 4);
-            if constexpr (LRT) q2 = *reinterpret_cast<const uint4*>(ws2 + ((size_t)n * p.K + k) * 4);
-          }
-        } else if (I8 && n == p.N && k < p.K) {
+        const uint32_t dst = smem_u32(sb + ((size_t)kc * p.b_pitch + n) * 16);
+        if (I8 && n == p.N) {
           // extra all-ones row: D[:, N] = sum_k (x - z_x), the row sums needed for the z_w correction
-          q = make_uint4(0x01010101u, 0x01010101u, (k + 8 < p.K) ? 0x01010101u : 0u, (k + 8 < p.K) ? 0x01010101u : 0u);
+          const uint32_t one = k < p.K ? 0x01010101u : 0u, two = (k + 8 < p.K) ? 0x01010101u : 0u;
+          *reinterpret_cast<uint4*>(sb + ((size_t)kc * p.b_pitch + n) * 16) = make_uint4(one, one, two, two);
+          continue;
         }
-        *reinterpret_cast<uint4*>(sb + ((size_t)kc * p.b_pitch + n) * 16) = q;
-        if constexpr (LRT) *reinterpret_cast<uint4*>(sb2 + ((size_t)kc * p.b_pitch + n) * 16) = q2;
+        const bool ok = n < p.N && k < p.K;
+        const uint8_t* src = ws + (ok ? ((size_t)n * p.K + k) * ESZ : 0);
+        if constexpr (I8) {
+          // rows are only 8-byte aligned when K % 16 == 8 (e.g. C = 24): two 8-byte LDGSTS
+          cp_async8(dst, src, ok ? 8u : 0u);
+          const bool ok2 = ok && k + 8 < p.K;
+          cp_async8(dst + 8, ok2 ? src + 8 : ws, ok2 ? 8u : 0u);
+        } else {
+          cp_async16(dst, src, ok ? 16u : 0u);
+          if constexpr (LRT) cp_async16(smem_u32(sb2 + ((size_t)kc * p.b_pitch + n) * 16), ws2 + (ok ? ((size_t)n * p.K + k) * ESZ : 0), ok ? 16u : 0u);
+        }
       }
-      fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(smem_u32(&full_bar[stage]));
+      fence_proxy_async();            // this thread's st.shared -> visible to the tensor core (async proxy)
+      cp_async_arrive_noinc(smem_u32(&full_bar[stage]));   // arrives once this thread's cp.asyncs have landed
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else {
@@ -313,6 +359,7 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     const uint32_t lbo_a = (uint32_t)p.a_pitch * 16, lbo_b = (uint32_t)p.b_pitch * 16;
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(smem_u32(&full_bar[stage]), phase);
+      fence_proxy_async();            // cp.async (generic proxy) data -> ordered before the MMAs' async-proxy reads
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
@@ -372,7 +419,8 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
             if (p.scale) a = __fmul_rn(a, __ldg(p.scale + c0 + j));
             if (p.shift) a = __fadd_rn(a, __ldg(p.shift + c0 + j));
             if (p.residual) a = __fadd_rn(a, __ldg(p.residual + orow + c0 + j));
-            if (p.relu) a = fmaxf(a, 0.f);
+            if (p.flags & QBN_FLAG_RELU) a = fmaxf(a, 0.f);
+            if (p.flags & QBN_FLAG_OUT_ROUND_TF32) a = __uint_as_float(tf32_rna(a));
           }
           o[j] = a;
         }
@@ -449,7 +497,7 @@ static int launch_umma(UParams& p, int n_samples, cudaStream_t st, const char* w
   constexpr int BLOCK_K = KCH * (I8 ? 16 : 4);
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   int stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > 6) stages = 6;
   if (stages > num_kb) stages = num_kb;
   if (stages < 1) {
     qbn_set_error("%s: stage does not fit shared memory", who);
@@ -492,7 +540,7 @@ int qbn_umma_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* mu_p, 
 }
 
 int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x, const float* w, int w_shared,
-                      const float* scale, const float* shift, const float* residual, int relu, const float* in_mask,
+                      const float* scale, const float* shift, const float* residual, int flags, const float* in_mask,
                       float in_mult, float* out, cudaStream_t st) {
   if (d->C % 4 != 0) {
     qbn_set_error("qbn_conv_fwd(TF32): C=%d must be a multiple of 4 (pad the input channels)", d->C);
@@ -501,7 +549,7 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
   UParams p;
   fill_geom(p, d);
   p.x = x; p.w = w; p.x_shared = x_shared; p.w_shared = w_shared;
-  p.scale = scale; p.shift = shift; p.residual = residual; p.relu = relu; p.in_mask = in_mask; p.in_mult = in_mult;
+  p.scale = scale; p.shift = shift; p.residual = residual; p.flags = flags; p.in_mask = in_mask; p.in_mult = in_mult;
   p.out = out;
   return launch_umma<MODE_EVAL>(p, n_samples, st, "qbn_conv_fwd(TF32)");
 }

@@ -197,6 +197,7 @@ class MCEngine:
         """Advance samples [sample0, sample0+n) through every step.  Returns the head output(s)."""
         regs = {0: x}
         shared = {0: True}
+        ready = {0: False}   # register holds TF32-exact values (written by a TF32 epilogue with OUT_ROUND_TF32)
         B = x.shape[0]
         seed = noise.seed()
         for st in self.steps:
@@ -204,6 +205,7 @@ class MCEngine:
             if isinstance(st, _PoolStep):
                 regs[st.dst] = ops.maxpool2x2(src) if st.kind == "max" else ops.avgpool_all(src).reshape(src.shape[0], src.shape[1], 1, 1)
                 shared[st.dst] = shared[st.src]
+                ready[st.dst] = ready[st.src] and st.kind == "max"   # max of TF32-exact values is TF32-exact
                 self.launches += 1
                 continue
             info = self._packed(st, prep, src)
@@ -223,16 +225,23 @@ class MCEngine:
                         e = torch.nn.functional.pad(e, (0, 0, 0, 0, 0, info["cpad"]))
                     es.append(ops.pack_ohwi(e))
                 eps = torch.stack(es).contiguous()
-            w = ops.sample_weights(info["mu"], info["sigma"], n, eps, seed, st.mod._qbn_layer_id, sample0)
             e = prep[id(st)]
             mode = self.math_mode if config.tf32_eligible(C, N, False) else QBN_MATH_FP32
+            tf32 = mode == QBN_MATH_TF32
+            w = ops.sample_weights(info["mu"], info["sigma"], n, eps, seed, st.mod._qbn_layer_id, sample0, round_tf32=tf32)
             res = regs[st.residual] if st.residual is not None else None
             if res is not None and shared.get(st.residual, False):
                 res = res.repeat(n, 1, 1, 1).contiguous(memory_format=ops.CL)   # only if a block reads the raw input
-            out = ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, st.relu, None, 1.0, mode)
+            flags = 0
+            if tf32:
+                flags |= ops.QBN_FLAG_OUT_ROUND_TF32
+                if ready[st.src] and not info["cpad"]:
+                    flags |= ops.QBN_FLAG_A_TF32_READY
+            out = ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, st.relu, None, 1.0, mode, None, flags)
             self.launches += 2
             regs[st.dst] = out
             shared[st.dst] = False
+            ready[st.dst] = tf32
         if self.regression:
             return regs[self.head_mu.dst].reshape(n, B), regs[self.head_lv.dst].reshape(n, B)
         logits = regs[self.out_reg]

@@ -9,7 +9,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, I8SampleParams, QBN_MATH_FP32, QBN_MATH_TF32  # noqa: F401
+from ._lib import (ConvDesc, I8SampleParams, QBN_FLAG_A_TF32_READY, QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU,  # noqa: F401
+                   QBN_MATH_FP32, QBN_MATH_TF32)
 
 CL = torch.channels_last
 
@@ -87,7 +88,7 @@ def philox_bernoulli(n, keep_prob, seed, stream_a=0, stream_b=0, device="cuda"):
 # ------------------------------------------------------------------------------------------------
 # parameter packing
 # ------------------------------------------------------------------------------------------------
-def weight_prep(mu, second, second_is_sigma=False, chan_scale=None, want=("mu", "sigma", "sigma2")):
+def weight_prep(mu, second, second_is_sigma=False, chan_scale=None, want=("mu", "sigma", "sigma2"), round_tf32=False):
     """OIHW (or [N,K]) parameters -> packed OHWI operands.  Returns dict of flat [N*K] tensors."""
     _need_cuda(mu, second)
     mu, second = _f32(mu).contiguous(), _f32(second).contiguous()
@@ -98,7 +99,7 @@ def weight_prep(mu, second, second_is_sigma=False, chan_scale=None, want=("mu", 
     out = {k: torch.empty(N * C * R * S, dtype=torch.float32, device=mu.device) for k in want}
     _lib.call("qbn_weight_prep", _ptr(mu), _ptr(second), int(second_is_sigma), N, C, R, S,
               _ptr(chan_scale.contiguous() if chan_scale is not None else None),
-              _ptr(out.get("mu")), _ptr(out.get("sigma")), _ptr(out.get("sigma2")), _stream())
+              _ptr(out.get("mu")), _ptr(out.get("sigma")), _ptr(out.get("sigma2")), int(round_tf32), _stream())
     return out
 
 
@@ -170,9 +171,10 @@ class LRTFunction(torch.autograd.Function):
         _need_cuda(x, weight, second)
         xc = nhwc(_f32(x))
         d = _geom(xc, weight.shape, stride, padding, dilation)
-        packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))
+        packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))   # backward needs them unrounded
+        fw = packed if math_mode != QBN_MATH_TF32 else weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"), round_tf32=True)
         eps_c = nhwc(_f32(eps)) if eps is not None else None
-        out, std = lrt_forward(xc, packed["mu"], packed["sigma2"], _f32(bias), d, eps_c, key, math_mode)
+        out, std = lrt_forward(xc, fw["mu"], fw["sigma2"], _f32(bias), d, eps_c, key, math_mode)
         ctx.save_for_backward(xc, packed["mu"], packed["sigma2"], std, eps_c, second.detach())
         ctx.d, ctx.key, ctx.math_mode, ctx.second_is_sigma = d, key, math_mode, second_is_sigma
         ctx.wshape = tuple(weight.shape)
@@ -196,15 +198,15 @@ class LRTFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # A4 eval-time sampling + contraction
 # ------------------------------------------------------------------------------------------------
-def sample_weights(mu_p, sigma_p, n_samples=1, eps=None, seed=0, layer_id=0, sample0=0):
+def sample_weights(mu_p, sigma_p, n_samples=1, eps=None, seed=0, layer_id=0, sample0=0, round_tf32=False):
     n = mu_p.numel()
     w = torch.empty((n_samples, n), dtype=torch.float32, device=mu_p.device)
-    _lib.call("qbn_sample_weights", _ptr(mu_p), _ptr(sigma_p), n, n_samples, _ptr(eps), seed, layer_id, sample0, _ptr(w), _stream())
+    _lib.call("qbn_sample_weights", _ptr(mu_p), _ptr(sigma_p), n, n_samples, _ptr(eps), seed, layer_id, sample0, _ptr(w), int(round_tf32), _stream())
     return w
 
 
 def conv_forward(x, w, d, n_samples=1, x_shared=True, w_shared=False, scale=None, shift=None, residual=None, relu=False,
-                 in_mask=None, in_mult=1.0, math_mode=QBN_MATH_FP32, out=None):
+                 in_mask=None, in_mult=1.0, math_mode=QBN_MATH_FP32, out=None, flags=0):
     """x NHWC-dense ([B,..] if x_shared else [S*B,..]); w [S][N][K] packed.  Returns [S*B, N, Ho, Wo]
     (channels-last) or [S, B, N] for linear geometry."""
     if out is None:
@@ -212,7 +214,7 @@ def conv_forward(x, w, d, n_samples=1, x_shared=True, w_shared=False, scale=None
         if x.dim() == 2 and out.dim() == 3 and n_samples == 1:
             out = out[0]
     _lib.call("qbn_conv_fwd", ctypes.byref(d), n_samples, int(x_shared), _ptr(x), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
-              _ptr(residual), int(relu), _ptr(in_mask), float(in_mult), _ptr(out), math_mode, _stream())
+              _ptr(residual), int(bool(relu)) | int(flags), _ptr(in_mask), float(in_mult), _ptr(out), math_mode, _stream())
     return out
 
 

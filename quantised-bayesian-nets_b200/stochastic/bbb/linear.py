@@ -54,8 +54,8 @@ def eval_forward(mod, x, stride, padding, dilation, relu=False):
         eps = noise.pop_injected()
         eps_p = ops.pack_ohwi(ops._f32(eps)).reshape(1, -1) if eps is not None else None
         seed, lid, draw = mod._key()
-        w = ops.sample_weights(packed["mu"], packed["sigma"], 1, eps_p, seed, lid, draw)
         mode = config.pick_math_mode(d.C, d.N, lrt=False)
+        w = ops.sample_weights(packed["mu"], packed["sigma"], 1, eps_p, seed, lid, draw, round_tf32=(mode == ops.QBN_MATH_TF32))
         return ops.conv_forward(xc, w, d, 1, True, False, None, mod.bias, None, relu, None, 1.0, mode)
 
 

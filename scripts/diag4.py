@@ -1,0 +1,25 @@
+import sys, os, copy
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "diag2.py")).read().split("y1, g1 = run(False)")[0])
+def run4(cl, cudnn_on=True):
+    torch.backends.cudnn.enabled = cudnn_on
+    net = zoo.resnet_from_params(P).cuda()
+    m2 = copy.deepcopy(net).eval(); order = []
+    names = {mod: name for name, mod in m2.named_modules()}
+    for mod in m2.modules():
+        if isinstance(mod, (Conv2d, Linear)):
+            mod.register_forward_hook(lambda mod, i, o: order.append((names[mod], tuple(o.shape))))
+    with torch.no_grad(): m2(x.cuda())
+    eps = O.replay_noise(710, [o[1] for o in order])
+    swap(net)
+    net.train()
+    xin = x.cuda().contiguous(memory_format=torch.channels_last) if cl else x.cuda()
+    with noise.inject([e.cuda() for e in eps]):
+        y = net(xin)
+    loss = F.nll_loss(torch.log(y + 1e-8), tgt)
+    loss.backward()
+    torch.backends.cudnn.enabled = True
+    return {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+ga = run4(False); gb = run4(True); gc = run4(True, cudnn_on=False)
+for k in ("layers.6.1.stem.3.weight", "layers.0.weight", "layers.1.weight"):
+    print(k, "twin NCHW vs twin CL", rel(gb[k], ga[k]), " twin CL(no cudnn) vs NCHW", rel(gc[k], ga[k]))

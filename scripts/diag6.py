@@ -1,0 +1,38 @@
+import sys, os, copy
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "diag2.py")).read().split("y1, g1 = run(False)")[0])
+def run6(cl):
+    net = zoo.resnet_from_params(P).cuda()
+    m2 = copy.deepcopy(net).eval(); order = []
+    names = {mod: name for name, mod in m2.named_modules()}
+    for mod in m2.modules():
+        if isinstance(mod, (Conv2d, Linear)):
+            mod.register_forward_hook(lambda mod, i, o: order.append((names[mod], tuple(o.shape))))
+    with torch.no_grad(): m2(x.cuda())
+    eps = O.replay_noise(710, [o[1] for o in order])
+    swap(net); net.train()
+    fw, gr = {}, {}
+    lname = {mod: name for name, mod in net.named_modules()}
+    def fh(mod, inp, out):
+        n = lname[mod]
+        fw[n] = out.detach().clone()
+        out.register_hook(lambda g, n=n: gr.__setitem__(n, g.detach().clone()))
+    for n_ in ("layers.6.1.end", "layers.6.1.add", "layers.6.1.stem.4", "layers.7", "layers.6.1"):
+        dict(net.named_modules())[n_].register_forward_hook(fh)
+    xin = x.cuda().contiguous(memory_format=torch.channels_last) if cl else x.cuda()
+    with noise.inject([e.cuda() for e in eps]):
+        y = net(xin)
+    loss = F.nll_loss(torch.log(y + 1e-8), tgt)
+    loss.backward()
+    return fw, gr
+fa, ga = run6(False); fb, gb = run6(True)
+for n in fa:
+    d = (fa[n] - fb[n]).abs()
+    print(n, "fwd maxdiff %.3e (max %.3e)" % (float(d.max()), float(fa[n].abs().max())), "grad maxdiff %.3e (max %.3e) n_diff>1e-6: %d of %d" % (
+        float((ga[n] - gb[n]).abs().max()), float(ga[n].abs().max()), int(((ga[n] - gb[n]).abs() > 1e-6 * float(ga[n].abs().max())).sum()), ga[n].numel()))
+r = fa["layers.6.1.end"]; rb = fb["layers.6.1.end"]
+print("mask mismatches", int(((r > 0) != (rb > 0)).sum()), "zeros", int((r == 0).sum()), int((rb == 0).sum()))
+ge, gadd = ga["layers.6.1.end"], ga["layers.6.1.add"]
+print("NCHW: add_grad == end_grad*mask ?", float((gadd - ge * (r > 0)).abs().max()))
+ge, gadd = gb["layers.6.1.end"], gb["layers.6.1.add"]
+print("CL  : add_grad == end_grad*mask ?", float((gadd - ge * (rb > 0)).abs().max()))

@@ -340,11 +340,11 @@ def test_tiny_int8_layers_bit_exact(golden):
             d = ops.make_desc(B, H, W, C, N, R, S, stride, pad, 1)
             wp = w[0].reshape(N, C, R, S).permute(0, 2, 3, 1).contiguous().reshape(1, -1)
             xq = dev(x_q).contiguous(memory_format=torch.channels_last)
-            y = ops.i8_conv_forward(xq, s_x, z_x, wp, s_add, z_add, d, None, s_o, z_o, relu, act_bits=7, path=1)
+            y = ops.i8_conv_forward(xq, s_x, z_x, wp, s_add, z_add, d, None, s_o, z_o, relu, act_bits=8, path=1)  # module output, before clamp_activation
         else:
             N, K = mu_q.shape
             d = ops.make_desc(x_q.shape[0], 1, 1, K, N, 1, 1)
-            y = ops.i8_conv_forward(dev(x_q), s_x, z_x, w, s_add, z_add, d, None, s_o, z_o, relu, act_bits=7, path=1, linear=True)
+            y = ops.i8_conv_forward(dev(x_q), s_x, z_x, w, s_add, z_add, d, None, s_o, z_o, relu, act_bits=8, path=1, linear=True)
         assert np.array_equal(y.cpu().numpy(), g[n + ".y_q"]), n
 
 

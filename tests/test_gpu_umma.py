@@ -57,6 +57,15 @@ def test_tf32_eval_conv(shape):
     yo = torch.nn.functional.conv2d(xs, w[1].permute(0, 3, 1, 2).cpu(), None, stride, pad)
     yo = torch.relu(yo * scale.cpu().view(1, -1, 1, 1) + shift.cpu().view(1, -1, 1, 1) + res[B:2 * B].cpu())
     close(got[B:2 * B], yo, 1e-3, 1e-3)
+    # cp.async operand path: input already TF32-exact (what a previous TF32 layer's epilogue writes)
+    xt = x.clone()
+    xt_i = xt.view(torch.int32)
+    xt_i.add_(0x1000).bitwise_and_(~0x1FFF)                       # RNA to 10 mantissa bits (ties away, sign-magnitude)
+    ref3 = ops.conv_forward(xt, wf, d, S, False, False, scale, shift, res, True, None, 1.0, ops.QBN_MATH_FP32)
+    got3 = ops.conv_forward(xt, wf, d, S, False, False, scale, shift, res, True, None, 1.0, ops.QBN_MATH_TF32, None,
+                            ops.QBN_FLAG_A_TF32_READY | ops.QBN_FLAG_OUT_ROUND_TF32)
+    close(got3, ref3, 1e-3, 1e-3)
+    assert int((got3.view(torch.int32) & 0x1FFF).abs().max()) == 0     # stored activations are TF32-exact
     # shared input / shared weights variants
     got2 = ops.conv_forward(x[:B].contiguous(memory_format=torch.channels_last), wf, d, S, True, False, None, None, None, False, None, 1.0,
                             ops.QBN_MATH_TF32)
