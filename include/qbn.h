@@ -46,6 +46,10 @@ typedef struct qbn_conv_desc {
   int32_t N, R, S;              /* filter [N][R][S][C]                      */
   int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int32_t Ho, Wo;               /* output [B][Ho][Wo][N]                    */
+  int32_t out_pad_h, out_pad_w; /* tcgen05 path only: the output tensor is [B][Ho+2*out_pad_h][Wo+2*out_pad_w][N]
+                                   and only its interior is written (zero-bordered layout consumed by
+                                   qbn_conv_s1_fwd).  pad_h/pad_w may be negative: reading the interior of a
+                                   zero-bordered input with a 1x1 stride-2 filter is pad = -border.       */
 } qbn_conv_desc;
 
 const char* qbn_last_error(void);
@@ -120,6 +124,15 @@ int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const floa
                  const float* w, int w_shared, const float* scale, const float* shift,
                  const float* residual, int flags, const float* in_mask, float in_mult, float* out,
                  int math_mode, void* stream);
+
+/* Stride-1 "same" convolution (odd RxS, pad (R-1)/2,(S-1)/2) on the zero-bordered layout, TF32
+ * tcgen05, persistent: x [n_samples][B][Hp][Wp][C] with Hp = H+R-1, Wp = W+S-1 and a zero border,
+ * TF32-exact values; w [n_samples][N][R][S][C] (qbn_sample_weights with round_tf32); out and
+ * residual [n_samples][B][Hp][Wp][N] in the same layout (the border of out is written as zeros).
+ * Same epilogue/flags as qbn_conv_fwd.  One smem tile serves all R*S taps (zero-copy im2col). */
+int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x,
+                    const float* w, int w_shared, const float* scale, const float* shift,
+                    const float* residual, int flags, float* out, void* stream);
 
 /* ---- A8 standalone: x[b,h,w,c] * mask[b,c] * mult (dropout.py:35-39); mask NULL -> Philox ---- */
 int qbn_dropout_fwd(const float* x, int64_t rows /*B*/, int64_t hw, int64_t C, const float* mask,
@@ -217,7 +230,7 @@ int qbn_reg_metrics(const float* mean, const float* var, const float* target, in
 /* ---- A11 glue kernels that survive fusion only at resolution changes ------------------------ */
 int qbn_maxpool2x2(const float* x, int64_t B, int H, int W, int C, float* out, void* stream);
 /* global average pool HxW -> 1 (nn.AvgPool2d(4) on the 4x4 map, models_bbb.py:209) */
-int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float* out, void* stream);
+int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float divisor /* <=0: HW */, float* out, void* stream);
 /* NCHW <-> NHWC (entry/exit of the NHWC domain) */
 int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float* out, void* stream);
 

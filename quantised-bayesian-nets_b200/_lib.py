@@ -17,7 +17,7 @@ QBN_FLAG_OUT_ROUND_TF32 = 4
 
 class ConvDesc(Structure):
     _fields_ = [(n, c_int32) for n in ("B", "H", "W", "C", "N", "R", "S", "stride_h", "stride_w", "pad_h", "pad_w",
-                                        "dil_h", "dil_w", "Ho", "Wo")]
+                                        "dil_h", "dil_w", "Ho", "Wo", "out_pad_h", "out_pad_w")]
 
 
 class I8SampleParams(Structure):
@@ -60,7 +60,8 @@ _SIGNATURES = {
     "qbn_cls_metrics": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P]),
     "qbn_reg_metrics": (c_int, [P, P, P, c_int64, P, P]),
     "qbn_maxpool2x2": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
-    "qbn_avgpool_all": (c_int, [P, c_int64, c_int, c_int, P, P]),
+    "qbn_avgpool_all": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
+    "qbn_conv_s1_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
     "qbn_nchw_to_nhwc": (c_int, [P, c_int64, c_int, c_int, P, P]),
 }
 

@@ -669,9 +669,9 @@ extern "C" int qbn_maxpool2x2(const float* x, int64_t B, int H, int W, int C, fl
   return QBN_OK;
 }
 
-__global__ void avgpool_all_kernel(const float* __restrict__ x, int64_t B, int HW, int C, float* __restrict__ out) {
+__global__ void avgpool_all_kernel(const float* __restrict__ x, int64_t B, int HW, int C, float divisor, float* __restrict__ out) {
   int64_t total = B * C;
-  const float inv = 1.0f / (float)HW;
+  const float inv = 1.0f / divisor;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     int64_t b = i / C;
@@ -680,9 +680,10 @@ __global__ void avgpool_all_kernel(const float* __restrict__ x, int64_t B, int H
     out[i] = acc * inv;
   }
 }
-extern "C" int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float* out, void* stream) {
+extern "C" int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float divisor, float* out, void* stream) {
   QBN_CHECK_ARG(x && out && B > 0 && HW > 0 && C > 0, "args");
-  avgpool_all_kernel<<<qbn_grid_for(B * C, 256), 256, 0, (cudaStream_t)stream>>>(x, B, HW, C, out);
+  if (divisor <= 0.f) divisor = (float)HW;   // zero-bordered maps: sum over the padded plane / interior size
+  avgpool_all_kernel<<<qbn_grid_for(B * C, 256), 256, 0, (cudaStream_t)stream>>>(x, B, HW, C, divisor, out);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

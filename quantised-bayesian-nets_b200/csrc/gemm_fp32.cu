@@ -37,7 +37,8 @@ static Geom make_geom(const qbn_conv_desc* d) {
 static int check_desc(const qbn_conv_desc* d) {
   if (!d) return 0;
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->N <= 0 || d->R <= 0 || d->S <= 0) return 0;
-  if (d->stride_h <= 0 || d->stride_w <= 0 || d->dil_h <= 0 || d->dil_w <= 0 || d->pad_h < 0 || d->pad_w < 0) return 0;
+  if (d->stride_h <= 0 || d->stride_w <= 0 || d->dil_h <= 0 || d->dil_w <= 0 || d->pad_h < -8 || d->pad_w < -8) return 0;
+  if (d->out_pad_h < 0 || d->out_pad_w < 0) return 0;
   int ho = (d->H + 2 * d->pad_h - d->dil_h * (d->R - 1) - 1) / d->stride_h + 1;
   int wo = (d->W + 2 * d->pad_w - d->dil_w * (d->S - 1) - 1) / d->stride_w + 1;
   return ho == d->Ho && wo == d->Wo && ho > 0 && wo > 0;
@@ -432,6 +433,7 @@ extern "C" int qbn_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   if (math_mode == QBN_MATH_TF32) return qbn_umma_lrt_fwd(d, x, mu_p, sig2_p, bias, eps, seed, sa, sb, out, std_out, st);
   QBN_CHECK_ARG(math_mode == QBN_MATH_FP32, "math_mode");
+  QBN_CHECK_ARG(d->out_pad_h == 0 && d->out_pad_w == 0, "out_pad is a tcgen05-path feature");
   Geom g = make_geom(d);
   if (g.N <= 32) {
     FwdLRT<32> p; p.g = g; p.x = x; p.mu = mu_p; p.sig2 = sig2_p; p.bias = bias; p.eps = eps; p.out = out; p.std_out = std_out;
@@ -456,6 +458,7 @@ extern "C" int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared,
   if (math_mode == QBN_MATH_TF32)
     return qbn_umma_conv_fwd(d, n_samples, x_shared, x, w, w_shared, scale, shift, residual, flags, in_mask, in_mult, out, st);
   QBN_CHECK_ARG(math_mode == QBN_MATH_FP32, "math_mode");
+  QBN_CHECK_ARG(d->out_pad_h == 0 && d->out_pad_w == 0, "out_pad is a tcgen05-path feature");
   Geom g = make_geom(d);
 #define QBN_FILL_EVAL(p)                                                                                        \
   p.g = g; p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.in_mask = in_mask;      \

@@ -192,30 +192,106 @@ class MCEngine:
         e[key] = info
         return info
 
+    # ---- layout planning: which registers live in the zero-bordered layout -------------------------
+    def _s1_eligible(self, st):
+        """Stride-1 'same' conv that the zero-copy-im2col kernel (qbn_conv_s1_fwd) takes."""
+        if not isinstance(st, _ConvStep) or st.is_linear or self.math_mode != QBN_MATH_TF32:
+            return None
+        m = st.mod
+        R, S_ = m.kernel_size
+        if tuple(m.stride) != (1, 1) or tuple(m.dilation) != (1, 1) or R % 2 == 0 or S_ % 2 == 0:
+            return None
+        if tuple(m.padding) != ((R - 1) // 2, (S_ - 1) // 2) or m.in_channels % 4 != 0 or m.out_channels > 256:
+            return None
+        if R == 1 and S_ == 1:
+            return None
+        return ((R - 1) // 2, (S_ - 1) // 2)
+
+    def _plan_layout(self):
+        if hasattr(self, "_reg_pad"):
+            return self._reg_pad
+        producers = {}
+        for st in self.steps:
+            producers[st.dst] = st
+        want = {}
+        for st in self.steps:
+            pad = self._s1_eligible(st)
+            if pad is not None:
+                want[st.src] = pad
+        changed = True
+        while changed:           # residual and output of a fused add share one geometry
+            changed = False
+            for st in self.steps:
+                if isinstance(st, _ConvStep) and st.residual is not None:
+                    a, b = st.dst, st.residual
+                    for u, v in ((a, b), (b, a)):
+                        if u in want and v not in want:
+                            want[v] = want[u]
+                            changed = True
+        def ok(reg):
+            pr = producers.get(reg)
+            if not isinstance(pr, _ConvStep) or pr.is_linear:
+                return False            # network input / pooled maps are not written zero-bordered
+            for st in self.steps:       # every consumer must understand the layout
+                if isinstance(st, _PoolStep) and st.src == reg and st.kind == "max":
+                    return False
+            return True
+        bad = {r for r in want if not ok(r)}
+        changed = True
+        while changed:
+            changed = False
+            for st in self.steps:
+                if isinstance(st, _ConvStep) and st.residual is not None:
+                    if (st.dst in bad) != (st.residual in bad) and (st.dst in want or st.residual in want):
+                        bad.update((st.dst, st.residual))
+                        changed = True
+        self._reg_pad = {r: p for r, p in want.items() if r not in bad}
+        return self._reg_pad
+
+    def _buffer(self, key, shape, device, zero):
+        """Output buffers are cached per (step, chunk size): stable pointers, no allocator churn, and the
+        zero border of a zero-bordered map is written only once."""
+        cache = self.__dict__.setdefault("_bufs", {})
+        k = (key, tuple(shape))
+        if k not in cache:
+            buf = torch.empty(shape, dtype=torch.float32, device=device, memory_format=ops.CL if len(shape) == 4 else torch.contiguous_format)
+            cache[k] = buf.zero_() if zero else buf
+        return cache[k]
+
     # ---- execution -------------------------------------------------------------------------------
     def _run_chunk(self, x, n, sample0, prep, injected):
         """Advance samples [sample0, sample0+n) through every step.  Returns the head output(s)."""
+        reg_pad = self._plan_layout()
         regs = {0: x}
         shared = {0: True}
         ready = {0: False}   # register holds TF32-exact values (written by a TF32 epilogue with OUT_ROUND_TF32)
         B = x.shape[0]
         seed = noise.seed()
-        for st in self.steps:
+        for si, st in enumerate(self.steps):
             src = regs[st.src]
+            spad = reg_pad.get(st.src, (0, 0)) if st.src in reg_pad else (0, 0)
             if isinstance(st, _PoolStep):
-                regs[st.dst] = ops.maxpool2x2(src) if st.kind == "max" else ops.avgpool_all(src).reshape(src.shape[0], src.shape[1], 1, 1)
+                if st.kind == "max":
+                    regs[st.dst] = ops.maxpool2x2(src)
+                else:
+                    interior = (src.shape[2] - 2 * spad[0]) * (src.shape[3] - 2 * spad[1])
+                    regs[st.dst] = ops.avgpool_all(src, float(interior)).reshape(src.shape[0], src.shape[1], 1, 1)
                 shared[st.dst] = shared[st.src]
                 ready[st.dst] = ready[st.src] and st.kind == "max"   # max of TF32-exact values is TF32-exact
                 self.launches += 1
                 continue
-            info = self._packed(st, prep, src)
-            if info["cpad"]:
-                src = torch.nn.functional.pad(src, (0, 0, 0, 0, 0, info["cpad"])).contiguous(memory_format=ops.CL)
+            # geometry of this conv on the UNPADDED map
             if src.dim() == 2:
                 src = src.reshape(src.shape[0], src.shape[1], 1, 1)
+            unp = src
+            if spad != (0, 0):
+                H0, W0 = src.shape[2] - 2 * spad[0], src.shape[3] - 2 * spad[1]
+                unp = torch.empty((0, src.shape[1], H0, W0), device="meta")          # shape carrier only
+            info = self._packed(st, prep, unp)
+            if info["cpad"]:
+                src = torch.nn.functional.pad(src, (0, 0, 0, 0, 0, info["cpad"])).contiguous(memory_format=ops.CL)
             N, C, R, S_ = info["wshape"]
             nb = src.shape[0] if shared[st.src] else src.shape[0] // n
-            d = ops.make_desc(nb, src.shape[2], src.shape[3], C, N, R, S_, info["stride"], info["pad"], info["dil"])
             eps = None
             if injected is not None:
                 es = []
@@ -232,12 +308,25 @@ class MCEngine:
             res = regs[st.residual] if st.residual is not None else None
             if res is not None and shared.get(st.residual, False):
                 res = res.repeat(n, 1, 1, 1).contiguous(memory_format=ops.CL)   # only if a block reads the raw input
-            flags = 0
-            if tf32:
-                flags |= ops.QBN_FLAG_OUT_ROUND_TF32
-                if ready[st.src] and not info["cpad"]:
+            dpad = reg_pad.get(st.dst, (0, 0))
+            flags = ops.QBN_FLAG_OUT_ROUND_TF32 if tf32 else 0
+            s1 = self._s1_eligible(st)
+            if s1 is not None and tf32 and spad == s1 and dpad == s1 and ready[st.src] and not shared[st.src] and not info["cpad"]:
+                out = self._buffer(("s1", si, n), (src.shape[0], N, src.shape[2], src.shape[3]), src.device, zero=False)
+                ops.conv_s1_forward(src, w, n, N, R, S_, e["scale"], e["shift"], res, st.relu, flags, False, out)
+            else:
+                pad_eff = (info["pad"][0] - spad[0], info["pad"][1] - spad[1])      # reading the interior of a bordered map
+                d = ops.make_desc(nb, src.shape[2], src.shape[3], C, N, R, S_, info["stride"], pad_eff, info["dil"])
+                if dpad != (0, 0):
+                    if not tf32:
+                        raise RuntimeError("zero-bordered output needs the tcgen05 path")
+                    d.out_pad_h, d.out_pad_w = dpad
+                    out = self._buffer(("v1", si, n), (n * nb, N, d.Ho + 2 * dpad[0], d.Wo + 2 * dpad[1]), src.device, zero=True)
+                else:
+                    out = self._buffer(("v1", si, n), (n * nb, N, d.Ho, d.Wo), src.device, zero=False)
+                if tf32 and ready[st.src] and not info["cpad"]:
                     flags |= ops.QBN_FLAG_A_TF32_READY
-            out = ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, st.relu, None, 1.0, mode, None, flags)
+                ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, st.relu, None, 1.0, mode, out, flags)
             self.launches += 2
             regs[st.dst] = out
             shared[st.dst] = False
@@ -263,8 +352,8 @@ class MCEngine:
             inj = injected[done:done + n] if injected is not None else None
             out = self._run_chunk(x, n, sample0 + done, prep, inj)
             if self.regression:
-                mus.append(out[0])
-                lvs.append(out[1])
+                mus.append(out[0].clone())      # the step buffers are reused by the next chunk
+                lvs.append(out[1].clone())
             else:
                 psum = ops.softmax_accumulate(out.contiguous(), psum)
                 self.launches += 1

@@ -441,10 +441,23 @@ def maxpool2x2(x):
     return out
 
 
-def avgpool_all(x):
+def avgpool_all(x, divisor=0.0):
+    """Mean over the HxW plane; for zero-bordered maps pass divisor = interior size."""
     B, C, H, W = x.shape
     out = torch.empty((B, C), dtype=torch.float32, device=x.device)
-    _lib.call("qbn_avgpool_all", _ptr(x), B, H * W, C, _ptr(out), _stream())
+    _lib.call("qbn_avgpool_all", _ptr(x), B, H * W, C, float(divisor), _ptr(out), _stream())
+    return out
+
+
+def conv_s1_forward(x, w, n_samples, N, R, S, scale=None, shift=None, residual=None, relu=False, flags=0, w_shared=False, out=None):
+    """tcgen05 zero-copy-im2col conv on the zero-bordered layout.  x [n_samples*B, C, Hp, Wp] channels-last
+    (Hp = H+R-1), TF32-exact; w [n_samples, N*R*S*C] packed OHWI, TF32-exact.  Returns [n_samples*B, N, Hp, Wp]."""
+    SB, C, Hp, Wp = x.shape
+    B = SB // n_samples
+    if out is None:
+        out = torch.empty((SB, N, Hp, Wp), dtype=torch.float32, device=x.device, memory_format=CL)
+    _lib.call("qbn_conv_s1_fwd", n_samples, B, Hp, Wp, C, N, R, S, _ptr(x), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
+              _ptr(residual), int(bool(relu)) | int(flags), _ptr(out), _stream())
     return out
 
 

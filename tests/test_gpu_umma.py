@@ -135,3 +135,73 @@ def test_tf32_dropout_mask_in_operand_load():
     xm = ops.dropout_forward(x, 0.15, mask)
     ref2 = ops.conv_forward(xm, w, d, S, False, False, None, None, None, False, None, 1.0, ops.QBN_MATH_FP32)
     close(ref, ref2, 1e-5, 1e-5)
+
+
+S1_SHAPES = [
+    # B, C, H, W, N, k
+    (2, 24, 32, 32, 24, 3), (2, 48, 16, 16, 48, 3), (3, 96, 8, 8, 96, 3), (5, 192, 4, 4, 192, 3),
+    (2, 20, 14, 14, 50, 5), (2, 8, 9, 7, 10, 3), (1, 4, 5, 5, 7, 3), (2, 40, 6, 6, 16, 3), (2, 72, 6, 5, 24, 3),
+]
+
+
+def _tf32_round_(t):
+    ti = t.view(torch.int32)
+    ti.add_(0x1000).bitwise_and_(~0x1FFF)
+    return t
+
+
+@pytest.mark.parametrize("shape", S1_SHAPES)
+def test_tf32_s1_zero_copy_im2col(shape):
+    """qbn_conv_s1_fwd (zero-bordered layout, one smem tile for all taps, persistent) == the fp32 conv."""
+    from qbn_b200 import ops
+    B, C, H, W, N, k = shape
+    pad = (k - 1) // 2
+    g = torch.Generator().manual_seed(7 + (hash(shape) & 0xFFFF))
+    S = 3
+    x = _tf32_round_(torch.randn(S * B, C, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last))
+    w = _tf32_round_((torch.randn(S, N, k, k, C, generator=g) / (C * k * k) ** 0.5).cuda()).reshape(S, -1).contiguous()
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    res = torch.randn(S * B, N, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    d = ops.make_desc(B, H, W, C, N, k, k, 1, pad, 1)
+    ref = ops.conv_forward(x, w, d, S, False, False, scale, shift, res, True, None, 1.0, ops.QBN_MATH_FP32)
+    P = torch.nn.functional.pad
+    xp = P(x, (pad, pad, pad, pad)).contiguous(memory_format=torch.channels_last)
+    rp = P(res, (pad, pad, pad, pad)).contiguous(memory_format=torch.channels_last)
+    got = ops.conv_s1_forward(xp, w, S, N, k, k, scale, shift, rp, True, ops.QBN_FLAG_OUT_ROUND_TF32)
+    inner = got[:, :, pad:pad + H, pad:pad + W]
+    close(inner, ref, 1e-3, 1e-3)
+    border = got.clone()
+    border[:, :, pad:pad + H, pad:pad + W] = 0
+    assert float(border.abs().max()) == 0.0                              # the zero border is preserved
+    assert int((got.view(torch.int32) & 0x1FFF).abs().max()) == 0         # TF32-exact outputs
+    # chained: feed the bordered output straight into a second s1 conv (no re-padding)
+    w2 = _tf32_round_((torch.randn(S, N, k, k, N, generator=g) / (N * k * k) ** 0.5).cuda()).reshape(S, -1).contiguous()
+    if N % 4 == 0:
+        got2 = ops.conv_s1_forward(got, w2, S, N, k, k, None, None, None, False, 0)
+        d2 = ops.make_desc(B, H, W, N, N, k, k, 1, pad, 1)
+        ref2 = ops.conv_forward(inner.contiguous(memory_format=torch.channels_last), w2, d2, S, False, False, None, None, None, False, None, 1.0,
+                                ops.QBN_MATH_FP32)
+        close(got2[:, :, pad:pad + H, pad:pad + W], ref2, 1e-3, 1e-3)
+
+
+def test_tf32_v1_bordered_io():
+    """v1 gather kernel writing a zero-bordered output, and reading one (stride 2 3x3, 1x1 stride-2 with pad -1)."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, C, H, N, S = 2, 24, 16, 48, 2
+    x = _tf32_round_(torch.randn(S * B, C, H, H, generator=g).cuda().contiguous(memory_format=torch.channels_last))
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+    for k, stride, pad in ((3, 2, 1), (1, 2, 0), (3, 1, 1)):
+        w = _tf32_round_((torch.randn(S, N, k, k, C, generator=g) / (C * k * k) ** 0.5).cuda()).reshape(S, -1).contiguous()
+        d = ops.make_desc(B, H, H, C, N, k, k, stride, pad, 1)
+        ref = ops.conv_forward(x, w, d, S, False, False, None, None, None, False, None, 1.0, ops.QBN_MATH_FP32)
+        dp = ops.make_desc(B, H + 2, H + 2, C, N, k, k, stride, pad - 1, 1)
+        assert (dp.Ho, dp.Wo) == (d.Ho, d.Wo)
+        dp.out_pad_h = dp.out_pad_w = 1
+        out = torch.zeros(S * B, N, d.Ho + 2, d.Wo + 2, device="cuda").contiguous(memory_format=torch.channels_last)
+        ops.conv_forward(xp, w, dp, S, False, False, None, None, None, False, None, 1.0, ops.QBN_MATH_TF32, out, ops.QBN_FLAG_A_TF32_READY)
+        close(out[:, :, 1:-1, 1:-1], ref, 1e-3, 1e-3)
+        b = out.clone()
+        b[:, :, 1:-1, 1:-1] = 0
+        assert float(b.abs().max()) == 0.0
