@@ -15,14 +15,34 @@ QBN_DEVINL void mbar_arrive(uint32_t bar) {
 }
 QBN_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint
+  // expires, instead of spinning through issue slots
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+QBN_DEVINL bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
+}
+// pure polling wait for latency-critical handshakes (one lane per warp polls, so the issue cost is small)
+QBN_DEVINL void mbar_spin(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 28); ++it)
+    if (mbar_test_wait(bar, parity)) return;
+  printf("libqbn umma: mbarrier spin timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
 }
 // bounded wait (2 s of %globaltimer): a protocol bug must trap (context error), never hang the GPU
 QBN_DEVINL uint64_t global_ns() {

@@ -40,6 +40,8 @@ struct UParams {
   int b_pitch;
   int x_shared, w_shared, flags;
   int oph, opw;     // zero-bordered output layout (interior written only)
+  int n_split;      // >0: the N columns are n_split channels of N/n_split stacked Monte-Carlo samples (shared input)
+  long long sample_out_stride;   // elements between consecutive samples' output tensors
   uint32_t idesc;
   // tensors
   const void* x; const void* w; const void* w2;
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     uint32_t phase = 0;
     if (!a_async) load_a_regs(0);
     for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      if (lane == 0) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);   // one lane polls for the warp
+      __syncwarp();
       uint8_t* sa = ring + (size_t)stage * stage_bytes;
       uint8_t* sa2 = sa + a_bytes;                              // LRT only
       uint8_t* sb = sa + (LRT ? 2 : 1) * a_bytes;
@@ -257,7 +260,8 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     uint32_t phase = 0;
     const uint32_t lbo_a = (uint32_t)p.a_pitch * 16, lbo_b = (uint32_t)p.b_pitch * 16;
     for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      if (lane == 0) mbar_wait(smem_u32(&full_bar[stage]), phase);
+      __syncwarp();
       fence_proxy_async();            // cp.async (generic proxy) data -> ordered before the MMAs' async-proxy reads
       tc_fence_after();
       if (lane == 0) {
@@ -288,17 +292,19 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
 
   // =============================== EPILOGUE (warps 0-3) ==========================================
   if (warp < 4) {
-    mbar_wait(smem_u32(accum_bar), 0);
+    if (lane == 0) mbar_wait(smem_u32(accum_bar), 0);
+    __syncwarp();
     tc_fence_after();
     const int m = m0 + warp * 32 + lane;        // TMEM lane == tile row
     const bool mv = m < p.M;
     const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    size_t orow = ((size_t)z * p.M + (mv ? m : 0)) * p.N;
+    const int Nrow = p.n_split ? p.n_split : p.N;      // channels per stored row
+    size_t orow = ((size_t)z * p.M + (mv ? m : 0)) * Nrow;
     if (p.oph | p.opw) {
       const int mm = mv ? m : 0;
       const int wo = mm % p.Wo, t2 = mm / p.Wo, ho = t2 % p.Ho, b = t2 / p.Ho;
       const int Hop = p.Ho + 2 * p.oph, Wop = p.Wo + 2 * p.opw;
-      orow = ((((size_t)z * p.B + b) * Hop + ho + p.oph) * Wop + wo + p.opw) * p.N;
+      orow = ((((size_t)z * p.B + b) * Hop + ho + p.oph) * Wop + wo + p.opw) * Nrow;
     }
     int rowsum = 0;
     if constexpr (I8) {
@@ -316,24 +322,27 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
       const int nvalid = min(8, p.N - c0);
       if constexpr (MODE == MODE_EVAL) {
         float* out = reinterpret_cast<float*>(p.out);
+        // sample-stacked columns (shared input, first layer): column c = sample (c / n_split), channel (c % n_split)
+        const int ch0 = p.n_split ? c0 % p.n_split : c0;
+        const size_t obase = p.n_split ? orow + (size_t)(c0 / p.n_split) * (size_t)p.sample_out_stride : orow;
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float a = __uint_as_float(v[j]);
           if (j < nvalid) {
-            if (p.scale) a = __fmul_rn(a, __ldg(p.scale + c0 + j));
-            if (p.shift) a = __fadd_rn(a, __ldg(p.shift + c0 + j));
-            if (p.residual) a = __fadd_rn(a, __ldg(p.residual + orow + c0 + j));
+            if (p.scale) a = __fmul_rn(a, __ldg(p.scale + ch0 + j));
+            if (p.shift) a = __fadd_rn(a, __ldg(p.shift + ch0 + j));
+            if (p.residual) a = __fadd_rn(a, __ldg(p.residual + obase + ch0 + j));
             if (p.flags & QBN_FLAG_RELU) a = fmaxf(a, 0.f);
             if (p.flags & QBN_FLAG_OUT_ROUND_TF32) a = __uint_as_float(tf32_rna(a));
           }
           o[j] = a;
         }
-        if (nvalid == 8 && ((orow + c0) & 3) == 0) {
-          *reinterpret_cast<float4*>(out + orow + c0) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(out + orow + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        if (nvalid == 8 && ((obase + ch0) & 3) == 0) {
+          *reinterpret_cast<float4*>(out + obase + ch0) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(out + obase + ch0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
         } else {
-          for (int j = 0; j < nvalid; ++j) out[orow + c0 + j] = o[j];
+          for (int j = 0; j < nvalid; ++j) out[obase + ch0 + j] = o[j];
         }
       } else if constexpr (LRT) {
         float* out = reinterpret_cast<float*>(p.out);
@@ -457,6 +466,14 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
   p.x = x; p.w = w; p.x_shared = x_shared; p.w_shared = w_shared;
   p.scale = scale; p.shift = shift; p.residual = residual; p.flags = flags; p.in_mask = in_mask; p.in_mult = in_mult;
   p.out = out;
+  // Shared input (first layer): stack the samples' weights along N — [S][N][K] IS an [S*N][K] matrix — so
+  // the input tile is staged once for all samples and one accumulator tile holds every sample's channels.
+  if (x_shared && !w_shared && n_samples > 1 && d->N % 8 == 0 && n_samples * d->N <= 256 && !residual && !in_mask) {
+    p.n_split = d->N;
+    p.N = n_samples * d->N;
+    p.sample_out_stride = (long long)d->B * (d->Ho + 2 * d->out_pad_h) * (d->Wo + 2 * d->out_pad_w) * d->N;
+    return launch_umma<MODE_EVAL>(p, 1, st, "qbn_conv_fwd(TF32, sample-stacked)");
+  }
   return launch_umma<MODE_EVAL>(p, n_samples, st, "qbn_conv_fwd(TF32)");
 }
 

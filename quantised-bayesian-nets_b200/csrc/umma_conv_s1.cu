@@ -18,10 +18,29 @@
 //                           channel block) and B (sampled weights, one slot per (channel block, tap))
 // CTAs are persistent (grid = SMs x occupancy) and walk the tile list round-robin, so TMEM
 // allocation, barrier setup and the epilogue of tile i overlap the loads/MMAs of tile i+1.
+#include <stdlib.h>
 #include <string.h>
 #include "umma_common.cuh"
 
 namespace {
+
+QBN_DEVINL float4 ld_nc_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// cycle accounting of CTA 0 (QBN_S1_DBG bit 8192): [role*8 + category] summed over its tiles
+__device__ unsigned long long g_s1_prof[32];
+#define PROF_BEGIN() long long _t0 = (p.dbg & 8192) ? clock64() : 0
+#define PROF_ADD(slot)                                                            \
+  do {                                                                            \
+    if ((p.dbg & 8192) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 5)) { \
+      long long _t1 = clock64();                                                  \
+      g_s1_prof[slot] += (unsigned long long)(_t1 - _t0);                         \
+      _t0 = _t1;                                                                  \
+    }                                                                             \
+  } while (0)
 
 constexpr int TM = 128;
 constexpr int N_EPI = 128, N_PROD = 128;
@@ -34,6 +53,10 @@ struct S1Params {
   int n_pad, CB, cbc, n_cb, K;    // MMA N, channels per block, 16-byte chunks per block (even), #blocks, R*S*C
   int D, RA, RA_p, b_pitch;       // halo rows, A rows per slot, pitches (in 16-byte chunks)
   int SA, SB;                     // ring depths
+  int b_res;                      // 1: the whole per-sample weight tensor stays resident in smem (reloaded on sample change)
+  int TG;                         // streaming mode: filter taps per B slot
+  int ACC;                        // TMEM accumulator stages (MMA may run ACC tiles ahead of the epilogue)
+  int dbg;                        // tuning knobs (QBN_S1_DBG): 1 round-robin tiles, 2 all-lane polling
   int tmem_cols, flags, w_shared;
   uint32_t idesc;
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; float* out;
@@ -43,7 +66,8 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = (uint32_t)p.cbc * p.RA_p * 16;
-  const uint32_t b_bytes = (uint32_t)p.cbc * p.b_pitch * 16;
+  const uint32_t bt_bytes = (uint32_t)p.cbc * p.b_pitch * 16;                 // one (channel block, tap) weight block
+  const uint32_t b_bytes = p.b_res ? bt_bytes * p.n_cb * p.R * p.S : bt_bytes * p.TG;   // one B slot
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + (size_t)p.SA * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.SB * b_bytes);
@@ -51,14 +75,20 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
   uint64_t* a_empty = a_full + p.SA;
   uint64_t* b_full = a_empty + p.SA;
   uint64_t* b_empty = b_full + p.SB;
-  uint64_t* acc_full = b_empty + p.SB;     // [2]
-  uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = b_empty + p.SB;         // [ACC]
+  uint64_t* acc_empty = acc_full + p.ACC;      // [ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + p.ACC);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);        // [256+4] per-channel affine (eval BatchNorm / bias)
+  float* s_shift = s_scale + 260;                                  // [256+4]
+  for (int i = tid; i < 260; i += NTHREADS_S1) {
+    s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
+    s_shift[i] = (p.shift && i < p.N) ? p.shift[i] : 0.f;
+  }
 
   if (tid == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), N_PROD); mbar_init(smem_u32(&a_empty[i]), 1); }
-    for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&b_full[i]), N_PROD); mbar_init(smem_u32(&b_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), N_EPI); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), N_PROD / 32); mbar_init(smem_u32(&a_empty[i]), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&b_full[i]), N_PROD / 32); mbar_init(smem_u32(&b_empty[i]), 1); }
+    for (int i = 0; i < p.ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), N_EPI); }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -68,6 +98,18 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int taps = p.R * p.S;
+  // contiguous tile range per CTA: consecutive tiles share the sample (=> the weights) and their halos hit L2
+  const bool rr = p.dbg & 1;
+  const int tile_begin = rr ? (int)blockIdx.x : (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
+  const int tile_end = rr ? p.total_tiles : (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int tile_step = rr ? (int)gridDim.x : 1;
+  // one lane polls an mbarrier on behalf of its warp (32x fewer smem polls / issue slots)
+  auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
+    if (lane == 0 || (p.dbg & 2)) {
+      if (p.dbg & 256) mbar_spin(smem_u32(bar), parity); else mbar_wait(smem_u32(bar), parity);
+    }
+    __syncwarp();
+  };
 
   if (warp >= 5) {
     // ======================================= PRODUCERS ==========================================
@@ -77,129 +119,274 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
     const int lane_row = pt / CH;
     const int RS = N_PROD / CH;                   // rows advanced per pass
     const bool active = lane_row < RS;            // (128 % CH) threads idle but still arrive
-    int sa = 0, sb = 0;
+    const int ra_iters = ((p.RA + RS - 1) / RS) * RS;
+    int sa = 0, sb = 0, cur_z = -1;
     uint32_t pa = 0, pb = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    // Completion signalling: every lane commits its cp.asyncs of a slot as one group; the slot's full
+    // barrier gets ONE arrival per warp, issued by lane 0 after the whole warp has seen the group land
+    // (cp.async.wait_group) — `lag` slots later, so loads of several slots stay in flight.  (One
+    // cp.async.mbarrier.arrive per THREAD costs ~128 serialized LSU operations per slot: measured
+    // 2.5 us per slot on B200.)
+    uint32_t pend[3] = {0u, 0u, 0u};
+    int npend = 0;
+    const int ring_min = p.b_res ? p.SA : (p.SA < p.SB ? p.SA : p.SB);
+    const int lag = ring_min >= 3 ? 2 : (ring_min == 2 ? 1 : 0);
+    auto signal_older = [&](int keep) {               // signal all pending slots except the newest `keep`
+      if (npend <= keep) return;
+      if (keep == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 2;" ::: "memory");
+      fence_proxy_async();                            // this lane's landed bytes -> visible to the tensor core
+      __syncwarp();
+      while (npend > keep) {
+        if (lane == 0) mbar_arrive(pend[0]);
+        pend[0] = pend[1]; pend[1] = pend[2];
+        --npend;
+      }
+    };
+    auto publish = [&](uint32_t bar) {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      pend[npend++] = bar;
+      signal_older(lag);
+    };
+    auto load_b_block = [&](uint32_t dst_block, const float* ws, int cb, int t) {      // one (cb, tap) weight block
+      const int c = cb * p.CB + 4 * j;
+      const bool cv = active && c < p.C && 4 * j < p.CB;
+      const uint32_t dst0 = dst_block + (uint32_t)(j * p.b_pitch) * 16;
+      const float* wt = ws + (size_t)t * p.C + c;
+      for (int n = lane_row; active && n < p.n_pad; n += RS) {
+        const bool ok = cv && n < p.N;
+        cp_async16(dst0 + (uint32_t)n * 16, ok ? wt + (size_t)n * p.K : p.w, ok ? 16u : 0u);
+      }
+    };
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int z = tile / p.tiles_per_sample;
       const int q0 = (tile - z * p.tiles_per_sample) * TM;
       const float* xs = p.x + (size_t)z * p.Qs * p.C;
       const float* ws = p.w + (p.w_shared ? 0 : (size_t)z * p.N * p.K);
+      PROF_BEGIN();
+      if (p.b_res && z != cur_z) {
+        // resident weights: (re)load the whole sampled tensor of sample z once.  The MMA warp frees the
+        // weight buffer only after the previous sample's last tiles, so their activation slots must be
+        // signalled before blocking here.
+        signal_older(0);
+        warp_wait(&b_empty[0], pb ^ 1);
+        const uint32_t base = smem_u32(b_ring);
+        for (int cb = 0; cb < p.n_cb; ++cb)
+          for (int t = 0; t < taps; ++t) load_b_block(base + (uint32_t)(cb * taps + t) * bt_bytes, ws, cb, t);
+        publish(smem_u32(&b_full[0]));
+        signal_older(0);                                  // one-slot 'ring': signal at once (rare: once per sample)
+        pb ^= 1;
+        cur_z = z;
+      }
+      PROF_ADD(16);
       for (int cb = 0; cb < p.n_cb; ++cb) {
         const int c = cb * p.CB + 4 * j;
         const bool cv = active && c < p.C && 4 * j < p.CB;
         // ---- A slot: rows [q0-D, q0+TM+D) of channel block cb, one contiguous strip of the padded map
-        mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
-        if (active) {
-          const uint32_t dst0 = smem_u32(a_ring + (size_t)sa * a_bytes) + (uint32_t)(j * p.RA_p) * 16;
-          for (int rho = lane_row; rho < p.RA; rho += RS) {
-            const int q = q0 - p.D + rho;
-            const bool ok = cv && q >= 0 && q < p.Qs;
-            cp_async16(dst0 + (uint32_t)rho * 16, ok ? xs + (size_t)q * p.C + c : p.x, ok ? 16u : 0u);
+        warp_wait(&a_empty[sa], pa ^ 1);
+        PROF_ADD(17);
+        {
+          // same trip count for every lane (no divergence); address advanced incrementally
+          uint32_t dst = smem_u32(a_ring + (size_t)sa * a_bytes) + (uint32_t)(j * p.RA_p + lane_row) * 16;
+          int qq = q0 - p.D + lane_row;
+          const float* src = xs + (ptrdiff_t)qq * p.C + c;
+          const ptrdiff_t src_step = (ptrdiff_t)RS * p.C;
+          for (int rho = lane_row; rho < ra_iters && !(p.dbg & 4096); rho += RS) {
+            const bool ok = cv && rho < p.RA && qq >= 0 && qq < p.Qs;
+            if (active && rho < p.RA && !(p.dbg & 64)) cp_async16(dst, ok ? src : p.x, ok ? 16u : 0u);
+            dst += (uint32_t)RS * 16; qq += RS; src += src_step;
           }
         }
-        cp_async_arrive_noinc(smem_u32(&a_full[sa]));
+        PROF_ADD(18);
+        publish(smem_u32(&a_full[sa]));
+        PROF_ADD(19);
         if (++sa == p.SA) { sa = 0; pa ^= 1; }
-        // ---- B slots: sampled weights W[n][tap][cb block] for every tap
-        for (int t = 0; t < taps; ++t) {
-          mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
-          const uint32_t dst0 = smem_u32(b_ring + (size_t)sb * b_bytes) + (uint32_t)(j * p.b_pitch) * 16;
-          const float* wt = ws + (size_t)t * p.C + c;
-          for (int n = lane_row; active && n < p.n_pad; n += RS) {
-            const bool ok = cv && n < p.N;
-            cp_async16(dst0 + (uint32_t)n * 16, ok ? wt + (size_t)n * p.K : p.w, ok ? 16u : 0u);
+        // ---- streamed weights: one slot per group of TG taps of this channel block
+        if (!p.b_res) {
+          for (int t0 = 0; t0 < taps; t0 += p.TG) {
+            warp_wait(&b_empty[sb], pb ^ 1);
+            PROF_ADD(20);
+            const uint32_t base = smem_u32(b_ring + (size_t)sb * b_bytes);
+            for (int t = t0; t < t0 + p.TG && t < taps; ++t) load_b_block(base + (uint32_t)(t - t0) * bt_bytes, ws, cb, t);
+            PROF_ADD(21);
+            publish(smem_u32(&b_full[sb]));
+            PROF_ADD(22);
+            if (++sb == p.SB) { sb = 0; pb ^= 1; }
           }
-          cp_async_arrive_noinc(smem_u32(&b_full[sb]));
-          if (++sb == p.SB) { sb = 0; pb ^= 1; }
         }
       }
     }
+    signal_older(0);                                      // drain
   } else if (warp == 4) {
     // ======================================= MMA ISSUER =========================================
-    int sa = 0, sb = 0, as = 0;
+    int sa = 0, sb = 0, as = 0, cur_z = -1;
     uint32_t pa = 0, pb = 0, pacc = 0;
     const uint32_t lbo_a = (uint32_t)p.RA_p * 16, lbo_b = (uint32_t)p.b_pitch * 16;
     const int nk = p.cbc / 2;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(&acc_empty[as]), pacc ^ 1);      // epilogue has drained this accumulator
-      tc_fence_after();
+    // descriptor = constant high part | (smem address >> 4): only the 14-bit start-address field moves
+    const uint64_t adesc_hi = make_smem_desc(0, lbo_a, 128), bdesc_hi = make_smem_desc(0, lbo_b, 128);
+    const uint32_t a_k = (2 * lbo_a) >> 4, b_k = (2 * lbo_b) >> 4;      // K-step (two 16-byte chunks) in 16-byte units
+    auto issue_tap = [&](uint32_t tacc, uint32_t abase, uint32_t bblock, int t, uint32_t& first) {
+      const int r = t / p.S, s = t - r * p.S;
+      const int shift = p.D + (r - p.ph) * p.Wp + (s - p.pw);       // slot row that output row 0 reads for this tap
+      uint32_t a16 = (abase >> 4) + (uint32_t)shift, b16 = bblock >> 4;
+      for (int jj = 0; jj < ((p.dbg & 32) ? (t == 0 ? 1 : 0) : nk); ++jj) {
+        umma_mma<MODE_EVAL>(tacc, adesc_hi | (uint64_t)(a16 & 0x3FFF), bdesc_hi | (uint64_t)(b16 & 0x3FFF), p.idesc, first ? 0u : 1u);
+        first = 0;
+        a16 += a_k; b16 += b_k;
+      }
+    };
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      const int z = tile / p.tiles_per_sample;
+      const bool last_of_z = (tile + tile_step >= tile_end) || ((tile + tile_step) / p.tiles_per_sample != z);
+      PROF_BEGIN();
+      if (p.b_res && z != cur_z) {
+        warp_wait(&b_full[0], pb);
+        pb ^= 1;
+        cur_z = z;
+      }
+      warp_wait(&acc_empty[as], pacc ^ 1);                // epilogue has drained this accumulator
+      PROF_ADD(8);
       const uint32_t tacc = tmem_base + (uint32_t)(as * p.n_pad);
       uint32_t first = 1;
       for (int cb = 0; cb < p.n_cb; ++cb) {
-        mbar_wait(smem_u32(&a_full[sa]), pa);
+        warp_wait(&a_full[sa], pa);
+        PROF_ADD(9);
         const uint32_t abase = smem_u32(a_ring + (size_t)sa * a_bytes);
-        for (int t = 0; t < taps; ++t) {
-          mbar_wait(smem_u32(&b_full[sb]), pb);
-          fence_proxy_async();          // cp.async data (generic proxy) -> ordered before async-proxy reads
-          tc_fence_after();
+        if (p.b_res) {
           if (lane == 0) {
-            const int r = t / p.S, s = t - r * p.S;
-            const int shift = p.D + (r - p.ph) * p.Wp + (s - p.pw);     // row of the slot that output row 0 reads
-            const uint32_t bbase = smem_u32(b_ring + (size_t)sb * b_bytes);
-            for (int jj = 0; jj < nk; ++jj) {
-              const uint64_t ad = make_smem_desc(abase + (uint32_t)(2 * jj) * lbo_a + (uint32_t)shift * 16, lbo_a, 128);
-              const uint64_t bd = make_smem_desc(bbase + (uint32_t)(2 * jj) * lbo_b, lbo_b, 128);
-              umma_mma<MODE_EVAL>(tacc, ad, bd, p.idesc, first ? 0u : 1u);
-              first = 0;
-            }
-            umma_commit(smem_u32(&b_empty[sb]));
-            if (t == taps - 1) {
-              umma_commit(smem_u32(&a_empty[sa]));
-              if (cb == p.n_cb - 1) umma_commit(smem_u32(&acc_full[as]));
+            if (!(p.dbg & 512)) fence_proxy_async();        // cp.async data (generic proxy) -> ordered before the async-proxy reads
+            tc_fence_after();
+            for (int t = 0; t < taps; ++t) issue_tap(tacc, abase, smem_u32(b_ring) + (uint32_t)(cb * taps + t) * bt_bytes, t, first);
+            umma_commit(smem_u32(&a_empty[sa]));
+            if (cb == p.n_cb - 1) {
+              umma_commit(smem_u32(&acc_full[as]));
+              if (last_of_z) umma_commit(smem_u32(&b_empty[0]));       // weights of sample z no longer needed
             }
           }
           __syncwarp();
-          if (++sb == p.SB) { sb = 0; pb ^= 1; }
+          PROF_ADD(10);
+        } else {
+          for (int t0 = 0; t0 < taps; t0 += p.TG) {
+            warp_wait(&b_full[sb], pb);
+            PROF_ADD(11);
+            if (lane == 0) {
+              fence_proxy_async();
+              tc_fence_after();
+              const uint32_t bbase = smem_u32(b_ring + (size_t)sb * b_bytes);
+              for (int t = t0; t < t0 + p.TG && t < taps; ++t) issue_tap(tacc, abase, bbase + (uint32_t)(t - t0) * bt_bytes, t, first);
+              umma_commit(smem_u32(&b_empty[sb]));
+              if (t0 + p.TG >= taps) {
+                umma_commit(smem_u32(&a_empty[sa]));
+                if (cb == p.n_cb - 1) umma_commit(smem_u32(&acc_full[as]));
+              }
+            }
+            __syncwarp();
+            PROF_ADD(10);
+            if (++sb == p.SB) { sb = 0; pb ^= 1; }
+          }
         }
         if (++sa == p.SA) { sa = 0; pa ^= 1; }
       }
-      if (++as == 2) { as = 0; pacc ^= 1; }
+      if (++as == p.ACC) { as = 0; pacc ^= 1; }
     }
   } else {
     // ======================================= EPILOGUE ===========================================
+    // Per 32-column chunk: TMEM -> registers (one lane = one output row) -> smem transpose -> a
+    // coalesced pass in which 8 consecutive lanes own one 128-byte row segment: residual read,
+    // affine/ReLU/round, store.  The residual loads of a chunk are issued BEFORE the accumulator is
+    // waited for, so their DRAM latency hides behind the MMAs.
     int as = 0;
     uint32_t pacc = 0;
+    // One TMEM lane = one output row per thread: the thread reads/writes its own row segment (N*4 bytes,
+    // whole 32-byte sectors when N % 8 == 0).  Residual values of a 32-column chunk are fetched into
+    // registers BEFORE they are needed (16-column chunks; first chunk: before the accumulator wait; later chunks: before
+    // the previous chunk is processed), so their DRAM latency hides behind the MMAs.
     const int plane = p.Hp * p.Wp;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int n_chunks = (p.N + 15) / 16;
+    const bool vec_ok = (p.N & 3) == 0;
+    const bool relu = p.flags & QBN_FLAG_RELU, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      PROF_BEGIN();
       const int z = tile / p.tiles_per_sample;
-      const int q = (tile - z * p.tiles_per_sample) * TM + warp * 32 + lane;
+      const int q = (tile - z * p.tiles_per_sample) * TM + tid;
       const bool qv = q < p.Qs;
       const int rem = qv ? q % plane : 0;
       const int hh = rem / p.Wp, ww = rem - hh * p.Wp;
       const bool interior = qv && hh >= p.ph && hh < p.Hp - p.ph && ww >= p.pw && ww < p.Wp - p.pw;
       const size_t orow = ((size_t)z * p.Qs + (qv ? q : 0)) * p.N;
-      mbar_wait(smem_u32(&acc_full[as]), pacc);
-      tc_fence_after();
-      const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
-      for (int c0 = 0; c0 < p.N; c0 += 8) {
-        uint32_t v[8];
-        tmem_ld8(tlane + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!qv) continue;
-        const int nvalid = min(8, p.N - c0);
-        float o[8];
+      float* optr = p.out + orow;
+      const float* rptr = (p.residual && interior && !(p.dbg & 128)) ? p.residual + orow : nullptr;
+      float4 rres[4], rnext[4];
+      auto prefetch = [&](float4* dst, int cc) {
 #pragma unroll
-        for (int jx = 0; jx < 8; ++jx) {
-          float a = 0.f;
-          if (interior && jx < nvalid) {
-            a = __uint_as_float(v[jx]);
-            if (p.scale) a = __fmul_rn(a, __ldg(p.scale + c0 + jx));
-            if (p.shift) a = __fadd_rn(a, __ldg(p.shift + c0 + jx));
-            if (p.residual) a = __fadd_rn(a, __ldg(p.residual + orow + c0 + jx));
-            if (p.flags & QBN_FLAG_RELU) a = fmaxf(a, 0.f);
-            if (p.flags & QBN_FLAG_OUT_ROUND_TF32) a = tf32_round(a);
+        for (int i = 0; i < 4; ++i) {
+          const int col = cc * 16 + 4 * i;
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rptr && col < p.N) {
+            if (vec_ok) {
+              dst[i] = ld_nc_f4(rptr + col);
+            } else {                                      // N % 4 != 0: rows are not 16-byte aligned
+              dst[i].x = rptr[col];
+              if (col + 1 < p.N) dst[i].y = rptr[col + 1];
+              if (col + 2 < p.N) dst[i].z = rptr[col + 2];
+              if (col + 3 < p.N) dst[i].w = rptr[col + 3];
+            }
           }
-          o[jx] = a;
         }
-        if (nvalid == 8 && ((orow + c0) & 3) == 0) {
-          *reinterpret_cast<float4*>(p.out + orow + c0) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(p.out + orow + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
-          for (int jx = 0; jx < nvalid; ++jx) p.out[orow + c0 + jx] = o[jx];
+      };
+      prefetch(rres, 0);
+      PROF_ADD(0);
+      warp_wait(&acc_full[as], pacc);
+      tc_fence_after();
+      PROF_ADD(1);
+      const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
+      for (int cc = 0; cc < n_chunks; ++cc) {
+        uint32_t v[16];
+        const int c0 = cc * 16;                           // n_pad is a multiple of 16
+        if (!(p.dbg & 2048)) {
+          tmem_ld8(tlane + (uint32_t)c0, v);
+          tmem_ld8(tlane + (uint32_t)(c0 + 8), v + 8);
         }
+        if (cc + 1 < n_chunks) prefetch(rnext, cc + 1);
+        tmem_ld_wait();
+        PROF_ADD(2);
+        if (cc == n_chunks - 1) {                         // accumulator fully read: release it to the MMA warp
+          tc_fence_before();
+          mbar_arrive(smem_u32(&acc_empty[as]));
+        }
+        if (qv && !(p.dbg & 16)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = c0 + 4 * i;
+            if (col < p.N) {
+              float a[4] = {0.f, 0.f, 0.f, 0.f};
+              if (interior) {
+                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[col]);
+                const float4 sh = *reinterpret_cast<const float4*>(&s_shift[col]);
+                a[0] = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x) + rres[i].x;
+                a[1] = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y) + rres[i].y;
+                a[2] = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z) + rres[i].z;
+                a[3] = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w) + rres[i].w;
+                if (relu) { a[0] = fmaxf(a[0], 0.f); a[1] = fmaxf(a[1], 0.f); a[2] = fmaxf(a[2], 0.f); a[3] = fmaxf(a[3], 0.f); }
+                if (rnd) { a[0] = tf32_round(a[0]); a[1] = tf32_round(a[1]); a[2] = tf32_round(a[2]); a[3] = tf32_round(a[3]); }
+              }
+              if (vec_ok) {
+                *reinterpret_cast<float4*>(optr + col) = make_float4(a[0], a[1], a[2], a[3]);
+              } else {
+                for (int e = 0; e < 4 && col + e < p.N; ++e) optr[col + e] = a[e];
+              }
+            }
+          }
+        }
+        if (cc + 1 < n_chunks) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rres[i] = rnext[i];
+        }
+        PROF_ADD(3);
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&acc_empty[as]));               // accumulator free for tile i+2
-      if (++as == 2) { as = 0; pacc ^= 1; }
+      if (++as == p.ACC) { as = 0; pacc ^= 1; }
     }
   }
   tc_fence_before();
@@ -242,21 +429,51 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   p.flags = flags; p.w_shared = w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-  int cols = 2 * p.n_pad;
+  // accumulator stages: as many as fit 256 TMEM columns (two CTAs per SM keep 512), at least 2, at most 8
+  p.ACC = 256 / p.n_pad;
+  if (p.ACC > 8) p.ACC = 8;
+  if (p.ACC < 2) p.ACC = 2;
+  int cols = p.ACC * p.n_pad;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
-  const size_t a_bytes = (size_t)p.cbc * p.RA_p * 16, b_bytes = (size_t)p.cbc * p.b_pitch * 16;
-  p.SA = 2;
-  p.SB = 4;
-  size_t smem = p.SA * a_bytes + p.SB * b_bytes + (2 * p.SA + 2 * p.SB + 4) * 8 + 16;
+  const size_t a_bytes = (size_t)p.cbc * p.RA_p * 16, bt_bytes = (size_t)p.cbc * p.b_pitch * 16;
+  const size_t epi_bytes = 16 + 2 * 260 * 4 + 16;
   const size_t cap = 220 * 1024;
-  if (smem > cap) { p.SB = 2; smem = p.SA * a_bytes + p.SB * b_bytes + (2 * p.SA + 2 * p.SB + 4) * 8 + 16; }
+  const int taps = R * S;
+  const size_t b_all = bt_bytes * p.n_cb * taps;
+  size_t b_bytes, smem;
+  const char* dbg_env = getenv("QBN_S1_DBG");
+  p.dbg = dbg_env ? atoi(dbg_env) : 0;
+  if (b_all <= 96 * 1024 && !(p.dbg & 4)) {
+    // resident weights: one "slot" holding the whole sampled tensor; spend the rest on a deep activation ring
+    p.b_res = 1; p.SB = 1; p.TG = taps;
+    b_bytes = b_all;
+    p.SA = 2;
+    auto total = [&](int sa) { return sa * a_bytes + b_bytes + (2 * sa + 2 + 2 * 8) * 8 + epi_bytes; };
+    const size_t budget = total(2) <= 110 * 1024 ? 110 * 1024 : cap;      // keep 2 CTAs/SM when that is possible at all
+    while (p.SA < 6 && total(p.SA + 1) <= budget) p.SA++;
+    smem = total(p.SA);
+  } else {
+    p.b_res = 0;
+    p.TG = 1;
+    for (int tg = taps; tg >= 1; --tg)
+      if (taps % tg == 0 && bt_bytes * tg <= 26 * 1024) { p.TG = tg; break; }
+    b_bytes = bt_bytes * p.TG;
+    p.SA = 2; p.SB = 2;
+    auto total = [&](int sa, int sb) { return sa * a_bytes + sb * b_bytes + (2 * sa + 2 * sb + 2 * 8) * 8 + epi_bytes; };
+    while (p.SB < 6 && total(p.SA, p.SB + 1) <= cap) p.SB++;
+    smem = total(p.SA, p.SB);
+  }
+  if (getenv("QBN_S1_SA")) {   // tuning: force the activation ring depth
+    const int sa_new = atoi(getenv("QBN_S1_SA"));
+    smem += (size_t)(sa_new - p.SA) * (a_bytes + 16);
+    p.SA = sa_new;
+  }
+  if (getenv("QBN_S1_ACC")) { p.ACC = atoi(getenv("QBN_S1_ACC")); }
   if (smem > cap) {
     qbn_set_error("qbn_conv_s1_fwd: tile does not fit shared memory (%zu bytes)", smem);
     return QBN_ERR_UNSUPPORTED;
   }
-  // deepen the weight ring while two CTAs still fit per SM
-  while (p.SB < 8 && smem + b_bytes <= 100 * 1024) { p.SB++; smem += b_bytes + 16; }
   static bool attr_set = false;
   if (!attr_set) {
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -266,10 +483,24 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   int occ_t = 512 / p.tmem_cols;
   if (occ > occ_t) occ = occ_t;
   if (occ > 3) occ = 3;
+  if (p.dbg & 8) occ = 1;
   if (occ < 1) occ = 1;
   int grid = qbn_sm_count() * occ;
   if (grid > p.total_tiles) grid = p.total_tiles;
+  if (p.dbg & 8192) {
+    unsigned long long z32[32] = {0};
+    cudaMemcpyToSymbol(g_s1_prof, z32, sizeof(z32));
+  }
   umma_conv_s1_kernel<<<grid, NTHREADS_S1, smem, st>>>(p);
   QBN_CHECK_LAUNCH();
+  if (p.dbg & 8192) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_s1_prof, sizeof(h));
+    const int tiles0 = p.total_tiles / grid;
+    fprintf(stderr, "[s1 prof] C=%d N=%d grid=%d tiles/CTA=%d SA=%d SB=%d ACC=%d b_res=%d TG=%d | epi: pre %llu waitacc %llu tmemld %llu compute+store %llu | mma: wait_acc_empty %llu wait_a %llu issue %llu wait_b %llu | prod: bres %llu wait_a_empty %llu issueA %llu publishA %llu wait_b_empty %llu issueB %llu publishB %llu (cycles per tile)\n",
+            C, N, grid, tiles0, p.SA, p.SB, p.ACC, p.b_res, p.TG, h[0] / tiles0, h[1] / tiles0, h[2] / tiles0, h[3] / tiles0, h[8] / tiles0, h[9] / tiles0,
+            h[10] / tiles0, h[11] / tiles0, h[16] / tiles0, h[17] / tiles0, h[18] / tiles0, h[19] / tiles0, h[20] / tiles0, h[21] / tiles0, h[22] / tiles0);
+  }
   return QBN_OK;
 }
