@@ -234,6 +234,10 @@ int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float divisor /* <
 /* NCHW <-> NHWC (entry/exit of the NHWC domain) */
 int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float* out, void* stream);
 
+/* Diagnostic: per-instruction cycle costs of tcgen05 fence / commit / mma / ld on this device (one
+ * CTA); out_dev receives 12 counters.  Used to size the kernel pipelines, no product use. */
+int qbn_ubench_tcgen05(unsigned long long* out_dev, int n_cols, int reps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

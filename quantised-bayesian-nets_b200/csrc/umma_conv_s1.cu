@@ -24,6 +24,7 @@
 
 namespace {
 
+QBN_DEVINL void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four epilogue warps only
 QBN_DEVINL float4 ld_nc_f4(const float* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
@@ -35,7 +36,7 @@ __device__ unsigned long long g_s1_prof[32];
 #define PROF_BEGIN() long long _t0 = (p.dbg & 8192) ? clock64() : 0
 #define PROF_ADD(slot)                                                            \
   do {                                                                            \
-    if ((p.dbg & 8192) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 5)) { \
+    if ((p.dbg & 8192) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 4 + NW_MMA)) { \
       long long _t1 = clock64();                                                  \
       g_s1_prof[slot] += (unsigned long long)(_t1 - _t0);                         \
       _t0 = _t1;                                                                  \
@@ -44,7 +45,8 @@ __device__ unsigned long long g_s1_prof[32];
 
 constexpr int TM = 128;
 constexpr int N_EPI = 128, N_PROD = 128;
-constexpr int NTHREADS_S1 = N_EPI + 32 + N_PROD;   // 288
+constexpr int NW_MMA = 1;                          // MMA-issuing warps (one tcgen05.mma costs ~83 cycles to ISSUE per thread on B200; two issuers x two CTAs/SM approach the SM-wide dispatch rate, scripts/ubench.py)
+constexpr int NTHREADS_S1 = N_EPI + 32 * NW_MMA + N_PROD;   // 320
 
 struct S1Params {
   int Hp, Wp, C, N, R, S, ph, pw;
@@ -55,6 +57,7 @@ struct S1Params {
   int SA, SB;                     // ring depths
   int b_res;                      // 1: the whole per-sample weight tensor stays resident in smem (reloaded on sample change)
   int TG;                         // streaming mode: filter taps per B slot
+  int bulk_out;                   // narrow layers: stage the output tile in smem and write it with one bulk copy
   int ACC;                        // TMEM accumulator stages (MMA may run ACC tiles ahead of the epilogue)
   int dbg;                        // tuning knobs (QBN_S1_DBG): 1 round-robin tiles, 2 all-lane polling
   int tmem_cols, flags, w_shared;
@@ -62,7 +65,8 @@ struct S1Params {
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; float* out;
 };
 
-__global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Params p) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(const S1Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = (uint32_t)p.cbc * p.RA_p * 16;
@@ -80,14 +84,15 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + p.ACC);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);        // [256+4] per-channel affine (eval BatchNorm / bias)
   float* s_shift = s_scale + 260;                                  // [256+4]
+  float* out_stage = s_shift + 260;                                // [2][128][N] when bulk_out (16-byte aligned)
   for (int i = tid; i < 260; i += NTHREADS_S1) {
     s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
     s_shift[i] = (p.shift && i < p.N) ? p.shift[i] : 0.f;
   }
 
   if (tid == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), N_PROD / 32); mbar_init(smem_u32(&a_empty[i]), 1); }
-    for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&b_full[i]), N_PROD / 32); mbar_init(smem_u32(&b_empty[i]), 1); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), N_PROD); mbar_init(smem_u32(&a_empty[i]), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&b_full[i]), N_PROD); mbar_init(smem_u32(&b_empty[i]), p.b_res ? NW_MMA : 1); }
     for (int i = 0; i < p.ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), N_EPI); }
     fence_mbar_init();
     fence_proxy_async();
@@ -111,9 +116,9 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
     __syncwarp();
   };
 
-  if (warp >= 5) {
+  if (warp >= 4 + NW_MMA) {
     // ======================================= PRODUCERS ==========================================
-    const int pt = tid - (N_EPI + 32);            // 0..127
+    const int pt = tid - (N_EPI + 32 * NW_MMA);   // 0..127
     const int CH = p.cbc;
     const int j = pt % CH;                        // this thread's 16-byte chunk inside every slot
     const int lane_row = pt / CH;
@@ -122,33 +127,12 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
     const int ra_iters = ((p.RA + RS - 1) / RS) * RS;
     int sa = 0, sb = 0, cur_z = -1;
     uint32_t pa = 0, pb = 0;
-    // Completion signalling: every lane commits its cp.asyncs of a slot as one group; the slot's full
-    // barrier gets ONE arrival per warp, issued by lane 0 after the whole warp has seen the group land
-    // (cp.async.wait_group) — `lag` slots later, so loads of several slots stay in flight.  (One
-    // cp.async.mbarrier.arrive per THREAD costs ~128 serialized LSU operations per slot: measured
-    // 2.5 us per slot on B200.)
-    uint32_t pend[3] = {0u, 0u, 0u};
-    int npend = 0;
-    const int ring_min = p.b_res ? p.SA : (p.SA < p.SB ? p.SA : p.SB);
-    const int lag = ring_min >= 3 ? 2 : (ring_min == 2 ? 1 : 0);
-    auto signal_older = [&](int keep) {               // signal all pending slots except the newest `keep`
-      if (npend <= keep) return;
-      if (keep == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-      else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 2;" ::: "memory");
-      fence_proxy_async();                            // this lane's landed bytes -> visible to the tensor core
-      __syncwarp();
-      while (npend > keep) {
-        if (lane == 0) mbar_arrive(pend[0]);
-        pend[0] = pend[1]; pend[1] = pend[2];
-        --npend;
-      }
-    };
-    auto publish = [&](uint32_t bar) {
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      pend[npend++] = bar;
-      signal_older(lag);
-    };
+    // Completion signalling: cp.async.mbarrier.arrive.noinc — each producer thread's arrival on the slot's
+    // full barrier fires when ITS copies have landed, so the threads never wait for data and every ring
+    // slot can be in flight at once.  (A wait_group-based one-arrival-per-warp scheme was measured
+    // slower: it serialises the weight stream behind the L2 latency.)
+    auto publish = [&](uint32_t bar) { cp_async_arrive_noinc(bar); };
+    auto signal_older = [&](int) {};
     auto load_b_block = [&](uint32_t dst_block, const float* ws, int cb, int t) {      // one (cb, tap) weight block
       const int c = cb * p.CB + 4 * j;
       const bool cv = active && c < p.C && 4 * j < p.CB;
@@ -218,8 +202,11 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
       }
     }
     signal_older(0);                                      // drain
-  } else if (warp == 4) {
-    // ======================================= MMA ISSUER =========================================
+  } else if (warp >= 4) {
+    // ======================================= MMA ISSUERS ========================================
+    // Tiles are dealt round-robin to the NW_MMA issuer warps; every warp walks the whole tile list to
+    // keep its ring/phase counters in step, but only issues (and commits) for the tiles it owns.
+    const int mw = warp - 4;
     int sa = 0, sb = 0, as = 0, cur_z = -1;
     uint32_t pa = 0, pb = 0, pacc = 0;
     const uint32_t lbo_a = (uint32_t)p.RA_p * 16, lbo_b = (uint32_t)p.b_pitch * 16;
@@ -227,63 +214,63 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
     // descriptor = constant high part | (smem address >> 4): only the 14-bit start-address field moves
     const uint64_t adesc_hi = make_smem_desc(0, lbo_a, 128), bdesc_hi = make_smem_desc(0, lbo_b, 128);
     const uint32_t a_k = (2 * lbo_a) >> 4, b_k = (2 * lbo_b) >> 4;      // K-step (two 16-byte chunks) in 16-byte units
+    const uint32_t leader = lane == 0 ? 1u : 0u;     // all lanes run the uniform issue code; only this one's tcgen05 ops fire
     auto issue_tap = [&](uint32_t tacc, uint32_t abase, uint32_t bblock, int t, uint32_t& first) {
       const int r = t / p.S, s = t - r * p.S;
       const int shift = p.D + (r - p.ph) * p.Wp + (s - p.pw);       // slot row that output row 0 reads for this tap
       uint32_t a16 = (abase >> 4) + (uint32_t)shift, b16 = bblock >> 4;
       for (int jj = 0; jj < ((p.dbg & 32) ? (t == 0 ? 1 : 0) : nk); ++jj) {
-        umma_mma<MODE_EVAL>(tacc, adesc_hi | (uint64_t)(a16 & 0x3FFF), bdesc_hi | (uint64_t)(b16 & 0x3FFF), p.idesc, first ? 0u : 1u);
+        umma_mma_tf32_pred(tacc, adesc_hi | (uint64_t)(a16 & 0x3FFF), bdesc_hi | (uint64_t)(b16 & 0x3FFF), p.idesc, first ? 0u : 1u, leader);
         first = 0;
         a16 += a_k; b16 += b_k;
       }
     };
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+    int local = 0;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
       const int z = tile / p.tiles_per_sample;
       const bool last_of_z = (tile + tile_step >= tile_end) || ((tile + tile_step) / p.tiles_per_sample != z);
+      const bool mine = (local % NW_MMA) == mw;
       PROF_BEGIN();
       if (p.b_res && z != cur_z) {
         warp_wait(&b_full[0], pb);
         pb ^= 1;
         cur_z = z;
       }
-      warp_wait(&acc_empty[as], pacc ^ 1);                // epilogue has drained this accumulator
+      if (mine) warp_wait(&acc_empty[as], pacc ^ 1);      // epilogue has drained this accumulator
       PROF_ADD(8);
       const uint32_t tacc = tmem_base + (uint32_t)(as * p.n_pad);
       uint32_t first = 1;
       for (int cb = 0; cb < p.n_cb; ++cb) {
-        warp_wait(&a_full[sa], pa);
+        if (mine) warp_wait(&a_full[sa], pa);
         PROF_ADD(9);
         const uint32_t abase = smem_u32(a_ring + (size_t)sa * a_bytes);
         if (p.b_res) {
-          if (lane == 0) {
-            if (!(p.dbg & 512)) fence_proxy_async();        // cp.async data (generic proxy) -> ordered before the async-proxy reads
+          if (mine) {
+            if (!(p.dbg & 512)) fence_proxy_async();      // cp.async data (generic proxy) -> ordered before the async-proxy reads
             tc_fence_after();
             for (int t = 0; t < taps; ++t) issue_tap(tacc, abase, smem_u32(b_ring) + (uint32_t)(cb * taps + t) * bt_bytes, t, first);
-            umma_commit(smem_u32(&a_empty[sa]));
-            if (cb == p.n_cb - 1) {
-              umma_commit(smem_u32(&acc_full[as]));
-              if (last_of_z) umma_commit(smem_u32(&b_empty[0]));       // weights of sample z no longer needed
-            }
+            umma_commit_pred(smem_u32(&a_empty[sa]), leader);
+            if (cb == p.n_cb - 1) umma_commit_pred(smem_u32(&acc_full[as]), leader);
           }
-          __syncwarp();
+          // every issuer warp releases the resident weights of sample z (its commit covers its own MMAs)
+          if (cb == p.n_cb - 1 && last_of_z) umma_commit_pred(smem_u32(&b_empty[0]), leader);
           PROF_ADD(10);
         } else {
           for (int t0 = 0; t0 < taps; t0 += p.TG) {
-            warp_wait(&b_full[sb], pb);
-            PROF_ADD(11);
-            if (lane == 0) {
+            if (mine) {
+              warp_wait(&b_full[sb], pb);
+              PROF_ADD(11);
               fence_proxy_async();
               tc_fence_after();
               const uint32_t bbase = smem_u32(b_ring + (size_t)sb * b_bytes);
               for (int t = t0; t < t0 + p.TG && t < taps; ++t) issue_tap(tacc, abase, bbase + (uint32_t)(t - t0) * bt_bytes, t, first);
-              umma_commit(smem_u32(&b_empty[sb]));
+              umma_commit_pred(smem_u32(&b_empty[sb]), leader);
               if (t0 + p.TG >= taps) {
-                umma_commit(smem_u32(&a_empty[sa]));
-                if (cb == p.n_cb - 1) umma_commit(smem_u32(&acc_full[as]));
+                umma_commit_pred(smem_u32(&a_empty[sa]), leader);
+                if (cb == p.n_cb - 1) umma_commit_pred(smem_u32(&acc_full[as]), leader);
               }
+              PROF_ADD(10);
             }
-            __syncwarp();
-            PROF_ADD(10);
             if (++sb == p.SB) { sb = 0; pb ^= 1; }
           }
         }
@@ -299,26 +286,31 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
     // waited for, so their DRAM latency hides behind the MMAs.
     int as = 0;
     uint32_t pacc = 0;
-    // One TMEM lane = one output row per thread: the thread reads/writes its own row segment (N*4 bytes,
-    // whole 32-byte sectors when N % 8 == 0).  Residual values of a 32-column chunk are fetched into
-    // registers BEFORE they are needed (16-column chunks; first chunk: before the accumulator wait; later chunks: before
-    // the previous chunk is processed), so their DRAM latency hides behind the MMAs.
+    // One TMEM lane = one output row per thread, processed in 16-column chunks with the next chunk's
+    // TMEM load and residual fetch already in flight.  Narrow layers (128 x N x 4 B <= 24 KB: the
+    // HBM-bound ones) stage the finished tile in smem and write it with ONE bulk (TMA-engine) copy —
+    // the tile's rows are contiguous in the zero-bordered layout — instead of 32-way scattered STG.
     const int plane = p.Hp * p.Wp;
-    const int n_chunks = (p.N + 15) / 16;
+    const int n_chunks = p.n_pad / 16;
     const bool vec_ok = (p.N & 3) == 0;
     const bool relu = p.flags & QBN_FLAG_RELU, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
+    const bool bulk_out = p.bulk_out;
+    int buf = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       PROF_BEGIN();
       const int z = tile / p.tiles_per_sample;
-      const int q = (tile - z * p.tiles_per_sample) * TM + tid;
+      const int q0 = (tile - z * p.tiles_per_sample) * TM;
+      const int q = q0 + tid;
       const bool qv = q < p.Qs;
       const int rem = qv ? q % plane : 0;
       const int hh = rem / p.Wp, ww = rem - hh * p.Wp;
       const bool interior = qv && hh >= p.ph && hh < p.Hp - p.ph && ww >= p.pw && ww < p.Wp - p.pw;
       const size_t orow = ((size_t)z * p.Qs + (qv ? q : 0)) * p.N;
       float* optr = p.out + orow;
+      float* sptr = out_stage + (size_t)buf * TM * p.N + (size_t)tid * p.N;      // this row inside the staging tile
       const float* rptr = (p.residual && interior && !(p.dbg & 128)) ? p.residual + orow : nullptr;
       float4 rres[4], rnext[4];
+      uint32_t v[16], vn[16];
       auto prefetch = [&](float4* dst, int cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -342,20 +334,22 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
       tc_fence_after();
       PROF_ADD(1);
       const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
+      if (!(p.dbg & 2048)) tmem_ld16(tlane, v);
+      if (bulk_out) {                                     // staging buffer `buf` must have been drained by its bulk store
+        if (tid == 0) bulk_wait_read<1>();
+        epi_sync();
+      }
       for (int cc = 0; cc < n_chunks; ++cc) {
-        uint32_t v[16];
-        const int c0 = cc * 16;                           // n_pad is a multiple of 16
-        if (!(p.dbg & 2048)) {
-          tmem_ld8(tlane + (uint32_t)c0, v);
-          tmem_ld8(tlane + (uint32_t)(c0 + 8), v + 8);
-        }
-        if (cc + 1 < n_chunks) prefetch(rnext, cc + 1);
-        tmem_ld_wait();
-        PROF_ADD(2);
-        if (cc == n_chunks - 1) {                         // accumulator fully read: release it to the MMA warp
+        const int c0 = cc * 16;
+        tmem_ld_wait();                                   // chunk cc has landed in v
+        if (cc + 1 < n_chunks) {
+          if (!(p.dbg & 2048)) tmem_ld16(tlane + (uint32_t)(c0 + 16), vn);
+          prefetch(rnext, cc + 1);
+        } else {                                          // accumulator fully read: release it to the MMA warp
           tc_fence_before();
           mbar_arrive(smem_u32(&acc_empty[as]));
         }
+        PROF_ADD(2);
         if (qv && !(p.dbg & 16)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -372,7 +366,9 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
                 if (relu) { a[0] = fmaxf(a[0], 0.f); a[1] = fmaxf(a[1], 0.f); a[2] = fmaxf(a[2], 0.f); a[3] = fmaxf(a[3], 0.f); }
                 if (rnd) { a[0] = tf32_round(a[0]); a[1] = tf32_round(a[1]); a[2] = tf32_round(a[2]); a[3] = tf32_round(a[3]); }
               }
-              if (vec_ok) {
+              if (bulk_out) {
+                *reinterpret_cast<float4*>(sptr + col) = make_float4(a[0], a[1], a[2], a[3]);
+              } else if (vec_ok) {
                 *reinterpret_cast<float4*>(optr + col) = make_float4(a[0], a[1], a[2], a[3]);
               } else {
                 for (int e = 0; e < 4 && col + e < p.N; ++e) optr[col + e] = a[e];
@@ -383,11 +379,24 @@ __global__ void __launch_bounds__(NTHREADS_S1) umma_conv_s1_kernel(const S1Param
         if (cc + 1 < n_chunks) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) rres[i] = rnext[i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = vn[i];
         }
         PROF_ADD(3);
       }
+      if (bulk_out) {
+        fence_proxy_async();                              // staged rows (generic proxy) -> visible to the bulk-copy engine
+        epi_sync();
+        if (tid == 0 && !(p.dbg & 16)) {
+          const int rows = min(TM, p.Qs - q0);
+          bulk_store_s2g(p.out + ((size_t)z * p.Qs + q0) * p.N, smem_u32(out_stage + (size_t)buf * TM * p.N), (uint32_t)(rows * p.N * 4));
+          bulk_commit();
+        }
+        buf ^= 1;
+      }
       if (++as == p.ACC) { as = 0; pacc ^= 1; }
     }
+    if (bulk_out && tid == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -429,40 +438,51 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   p.flags = flags; p.w_shared = w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-  // accumulator stages: as many as fit 256 TMEM columns (two CTAs per SM keep 512), at least 2, at most 8
-  p.ACC = 256 / p.n_pad;
-  if (p.ACC > 8) p.ACC = 8;
-  if (p.ACC < 2) p.ACC = 2;
-  int cols = p.ACC * p.n_pad;
-  p.tmem_cols = 32;
-  while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   const size_t a_bytes = (size_t)p.cbc * p.RA_p * 16, bt_bytes = (size_t)p.cbc * p.b_pitch * 16;
-  const size_t epi_bytes = 16 + 2 * 260 * 4 + 16;
+  p.bulk_out = ((size_t)TM * N * 4 <= 24 * 1024 && N % 4 == 0 && getenv("QBN_S1_BULK")) ? 1 : 0;   // measured slower than direct row stores (extra barriers); kept as a tuning knob
+  const size_t epi_bytes = 16 + 2 * 260 * 4 + 16 + (p.bulk_out ? 2 * (size_t)TM * N * 4 : 0);
   const size_t cap = 220 * 1024;
   const int taps = R * S;
   const size_t b_all = bt_bytes * p.n_cb * taps;
   size_t b_bytes, smem;
   const char* dbg_env = getenv("QBN_S1_DBG");
   p.dbg = dbg_env ? atoi(dbg_env) : 0;
+  // Policy: several small CTAs per SM rather than one deep pipeline — one tcgen05.mma costs ~83 cycles to
+  // issue from a thread (scripts/ubench.py), so issuers in different CTAs are what fills the tensor pipe,
+  // and co-resident CTAs hide each other's barrier round trips.
+  const size_t occ_budget[4] = {0, cap, 110 * 1024, 72 * 1024};
+  int want_occ = 1;
   if (b_all <= 96 * 1024 && !(p.dbg & 4)) {
-    // resident weights: one "slot" holding the whole sampled tensor; spend the rest on a deep activation ring
+    // resident weights: one "slot" holding the whole sampled tensor of the current sample
     p.b_res = 1; p.SB = 1; p.TG = taps;
     b_bytes = b_all;
-    p.SA = 2;
     auto total = [&](int sa) { return sa * a_bytes + b_bytes + (2 * sa + 2 + 2 * 8) * 8 + epi_bytes; };
-    const size_t budget = total(2) <= 110 * 1024 ? 110 * 1024 : cap;      // keep 2 CTAs/SM when that is possible at all
-    while (p.SA < 6 && total(p.SA + 1) <= budget) p.SA++;
+    want_occ = total(2) <= occ_budget[2] ? 2 : 1;      // (3 CTAs/SM measured slower: the SM-wide issue rate, not latency, binds)
+    p.SA = 2;
+    while (p.SA < 4 && total(p.SA + 1) <= occ_budget[want_occ]) p.SA++;
     smem = total(p.SA);
   } else {
     p.b_res = 0;
     p.TG = 1;
-    for (int tg = taps; tg >= 1; --tg)
-      if (taps % tg == 0 && bt_bytes * tg <= 26 * 1024) { p.TG = tg; break; }
-    b_bytes = bt_bytes * p.TG;
-    p.SA = 2; p.SB = 2;
+    b_bytes = bt_bytes;
     auto total = [&](int sa, int sb) { return sa * a_bytes + sb * b_bytes + (2 * sa + 2 * sb + 2 * 8) * 8 + epi_bytes; };
-    while (p.SB < 6 && total(p.SA, p.SB + 1) <= cap) p.SB++;
+    want_occ = (total(2, 3) <= occ_budget[2] && p.n_pad <= 128) ? 2 : 1;   // wide layers: one CTA with deep rings + 2 accumulators
+    p.SA = 2; p.SB = 2;
+    while (p.SB < 6 && total(p.SA, p.SB + 1) <= occ_budget[want_occ]) p.SB++;
     smem = total(p.SA, p.SB);
+  }
+  // TMEM: want_occ CTAs share 512 columns
+  {
+    int cols_per_cta = 512 / want_occ;
+    int c2 = 32;
+    while (c2 * 2 <= cols_per_cta) c2 <<= 1;           // power of two <= share
+    p.ACC = c2 / p.n_pad;
+    if (p.ACC > 4) p.ACC = 4;
+    if (p.ACC < 1) { p.ACC = 1; want_occ = 1; }
+    int cols = p.ACC * p.n_pad;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < cols) p.tmem_cols <<= 1;
+    if (p.tmem_cols * want_occ > 512) want_occ = 512 / p.tmem_cols;
   }
   if (getenv("QBN_S1_SA")) {   // tuning: force the activation ring depth
     const int sa_new = atoi(getenv("QBN_S1_SA"));
@@ -476,22 +496,22 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_s1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_s1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
-  int occ_t = 512 / p.tmem_cols;
-  if (occ > occ_t) occ = occ_t;
-  if (occ > 3) occ = 3;
-  if (p.dbg & 8) occ = 1;
+  if (occ > want_occ) occ = want_occ;
   if (occ < 1) occ = 1;
+  if (p.dbg & 8) occ = 1;
   int grid = qbn_sm_count() * occ;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (p.dbg & 8192) {
     unsigned long long z32[32] = {0};
     cudaMemcpyToSymbol(g_s1_prof, z32, sizeof(z32));
   }
-  umma_conv_s1_kernel<<<grid, NTHREADS_S1, smem, st>>>(p);
+  if (occ >= 3) umma_conv_s1_kernel<3><<<grid, NTHREADS_S1, smem, st>>>(p);
+  else umma_conv_s1_kernel<2><<<grid, NTHREADS_S1, smem, st>>>(p);
   QBN_CHECK_LAUNCH();
   if (p.dbg & 8192) {
     unsigned long long h[32];
