@@ -275,8 +275,10 @@ def main():
             peak = peaks["bf16_tflops_sustained"] / 2.0
             alg_bytes = ACT_BYTES_PER_SAMPLE_IMAGE * B * count
             roof = {"kernel": "umma_conv_s1_kernel + umma_conv_kernel<EVAL> (tcgen05 kind::tf32)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "launches": len(um), "avg_launch_ms": t_ms / len(um),
+                    "frac": ach / peak, "traffic": 290.05e6, "launches": len(um), "avg_launch_ms": t_ms / len(um),
                     "peak_source": "1/2 x sustained bf16 of %s (TF32 peak not in MEASURED_PEAKS.json)" % peaks["source"],
+                    "traffic_source": "dram read+write bytes per launch, mean over the 21 conv launches of one 10-sample chunk, ncu --set full (profiles/r01_conv_kernels_ncu_full.csv)",
+                    "algorithmic_bytes_per_launch": alg_bytes / len(um),
                     "hbm_view": {"achieved_gbs": alg_bytes / (t_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                                  "frac": alg_bytes / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                  "note": "algorithmic activation bytes (1.929 MB/sample-image, fp32 NHWC) over the same launches; "
