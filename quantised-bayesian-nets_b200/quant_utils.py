@@ -1,0 +1,242 @@
+"""Quantisation glue of the hot path — mirror of src/quant_utils.py (reference :30-147) and the
+torch.quantization pieces it instantiates, backed by libqbn kernels.
+
+  FakeQuantize      drop-in for torch's FakeQuantize(MovingAverageMinMaxObserver, per_tensor_affine):
+                    one fused observe+EMA+qparams kernel and one quantise kernel (A7), STE backward.
+  QTensor           uint8 activations + (scale, zero_point) on the GPU, NHWC — what the reference keeps
+                    in torch quint8 tensors on the CPU (the reference's int8 path is CPU-only).
+  prepare_model / convert / postprocess_model   same call signatures as the reference.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+UINT_BOUNDS = {8: [0, 255], 7: [0, 127], 6: [0, 63], 5: [0, 31], 4: [0, 15], 3: [0, 7], 2: [0, 3]}            # src/utils.py:18
+INT_BOUNDS = {8: [-128, 127], 7: [-64, 63], 6: [-32, 31], 5: [-16, 15], 4: [-8, 7], 3: [-4, 3], 2: [-2, 1]}  # src/utils.py:19-20
+
+
+class _ObserverView(nn.Module):
+    """`fq.activation_post_process.min_val / max_val` like torch's MovingAverageMinMaxObserver."""
+
+    def __init__(self, owner):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+
+    @property
+    def min_val(self):
+        return self._owner.state[0]
+
+    @property
+    def max_val(self):
+        return self._owner.state[1]
+
+    def calculate_qparams(self):
+        return self._owner.calculate_qparams()
+
+
+class FakeQuantize(nn.Module):
+    """y = (clamp(rint(x/s)+z, qmin, qmax) - z) * s with an EMA(min,max; c=0.01) observer
+    (torch/ao/quantization/fake_quantize.py:228-260, observer.py:374-410,668-683) in two CUDA
+    kernels; gradients pass where the un-clamped integer is inside [qmin, qmax] (STE)."""
+
+    def __init__(self, observer=None, quant_min=0, quant_max=255, dtype=torch.quint8, qscheme=torch.per_tensor_affine,
+                 averaging_constant=0.01, **kw):
+        super().__init__()
+        assert qscheme in (torch.per_tensor_affine,), "the reference only uses per_tensor_affine (quant_utils.py:129-138)"
+        self.quant_min, self.quant_max = int(quant_min), int(quant_max)
+        self.dtype, self.qscheme = dtype, qscheme
+        self.averaging_constant = float(averaging_constant)
+        self.register_buffer("state", torch.tensor([float("inf"), float("-inf"), 0.0]))     # min, max, initialised
+        self.register_buffer("scale", torch.ones(1))
+        self.register_buffer("zero_point", torch.zeros(1, dtype=torch.int32))
+        self._observer_on, self._fq_on = True, True       # host-side switches (no device sync on the hot path)
+        self.register_buffer("workspace", torch.zeros(16 + 8 * 1024, dtype=torch.uint8), persistent=False)
+        self.activation_post_process = _ObserverView(self)
+
+    @classmethod
+    def with_args(cls, **kwargs):
+        from torch.ao.quantization.observer import _PartialWrapper
+        import functools
+        return _PartialWrapper(functools.partial(cls, **kwargs))
+
+    def calculate_qparams(self):
+        return self.scale.detach().clone().float(), self.zero_point.detach().clone().long()
+
+    def enable_observer(self, enabled=True):
+        self._observer_on = bool(enabled)
+        return self
+
+    def enable_fake_quant(self, enabled=True):
+        self._fq_on = bool(enabled)
+        return self
+
+    def disable_fake_quant(self):
+        return self.enable_fake_quant(False)
+
+    def disable_observer(self):
+        return self.enable_observer(False)
+
+    def _fq_state(self):
+        st = ops.FakeQuantState.__new__(ops.FakeQuantState)
+        st.qmin, st.qmax, st.c = self.quant_min, self.quant_max, self.averaging_constant
+        st.state, st.scale, st.zero_point, st.workspace = self.state, self.scale, self.zero_point, self.workspace
+        return st
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("qbn_b200 FakeQuantize runs on CUDA only (no CPU fallback)")
+        if self.state.device != x.device:
+            self.to(x.device)
+        if not self._fq_on:
+            return x
+        return ops.fake_quantize(x, self._fq_state(), observe=self._observer_on)
+
+    def extra_repr(self):
+        return "quant_min=%d, quant_max=%d, dtype=%s" % (self.quant_min, self.quant_max, self.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+class QTensor:
+    """Per-tensor-affine quint8 activation on the GPU: `q` uint8 (NCHW-logical, NHWC-dense, or [B,K])."""
+
+    def __init__(self, q, scale, zero_point):
+        self.q, self.scale, self.zero_point = q, float(scale), int(zero_point)
+
+    @property
+    def shape(self):
+        return self.q.shape
+
+    def dim(self):
+        return self.q.dim()
+
+    def int_repr(self):
+        return self.q
+
+    def q_scale(self):
+        return self.scale
+
+    def q_zero_point(self):
+        return self.zero_point
+
+    def dequantize(self):
+        return ops.dequantize_u8(self.q, self.scale, self.zero_point)
+
+    def clamp_activation(self, args):
+        """src/utils.py:25-30: integer clamp to [0, 2^a - 1] (qparams unchanged)."""
+        lo, hi = UINT_BOUNDS[args.activation_precision]
+        return QTensor(torch.clamp(self.q, lo, hi), self.scale, self.zero_point)
+
+    def reshape(self, *shape):
+        return QTensor(self.q.reshape(*shape), self.scale, self.zero_point)
+
+    def size(self, i=None):
+        return self.q.size() if i is None else self.q.size(i)
+
+
+class Quantize(nn.Module):
+    """nnq.Quantize (QuantStub after convert): float -> QTensor with the calibrated (scale, zp)."""
+
+    def __init__(self, scale, zero_point, qmin=0, qmax=255):
+        super().__init__()
+        self.scale, self.zero_point, self.qmin, self.qmax = float(scale), int(zero_point), qmin, qmax
+
+    def forward(self, x):
+        xc = ops.nhwc(x.float())
+        return QTensor(ops.quantize_u8(xc, self.scale, self.zero_point, self.qmin, self.qmax), self.scale, self.zero_point)
+
+    @classmethod
+    def from_float(cls, mod):
+        s, z = mod.activation_post_process.calculate_qparams()
+        return cls(float(s), int(z))
+
+
+class DeQuantize(nn.Module):
+    def forward(self, x):
+        return x.dequantize() if isinstance(x, QTensor) else x
+
+    @classmethod
+    def from_float(cls, mod):
+        return cls()
+
+
+# ------------------------------------------------------------------------------------------------
+def qconfig_for(args):
+    """quant_utils.py:129-138: activations quint8 [0, 2^a-1], weights qint8 [-2^(w-1), 2^(w-1)-1]."""
+    assert 2 <= args.activation_precision <= 7 and 2 <= args.weight_precision <= 8     # quant_utils.py:120-121
+    a, w = UINT_BOUNDS[args.activation_precision], INT_BOUNDS[args.weight_precision]
+    return torch.ao.quantization.QConfig(
+        activation=FakeQuantize.with_args(quant_min=a[0], quant_max=a[1], dtype=torch.quint8, qscheme=torch.per_tensor_affine),
+        weight=FakeQuantize.with_args(quant_min=w[0], quant_max=w[1], dtype=torch.qint8, qscheme=torch.per_tensor_affine))
+
+
+def _mappings():
+    from .stochastic.bbb import conv as C, linear as L
+    from .stochastic.bbb.quantized import conv_q, conv_qat, linear_q, linear_qat
+    qat = {L.Linear: linear_qat.Linear, L.LinearReLU: linear_qat.LinearReLU, C.Conv2d: conv_qat.Conv2d, C.ConvReLU2d: conv_qat.ConvReLU2d,
+           C.ConvBn2d: conv_qat.ConvBn2d, C.ConvBnReLU2d: conv_qat.ConvBnReLU2d}                      # quant_utils.py:38-43
+    static = {linear_qat.Linear: linear_q.Linear, linear_qat.LinearReLU: linear_q.LinearReLU, conv_qat.Conv2d: conv_q.Conv2d,
+              conv_qat.ConvReLU2d: conv_q.ConvReLU2d, conv_qat.ConvBn2d: conv_q.Conv2d, conv_qat.ConvBnReLU2d: conv_q.ConvReLU2d,
+              torch.ao.quantization.QuantStub: Quantize, torch.ao.quantization.DeQuantStub: DeQuantize}   # quant_utils.py:45-54
+    return qat, static
+
+
+def convert(model, mapping=None, inplace=True):
+    """quant_utils.py:62-99: recursive swap of every module whose type is in `mapping` via from_float."""
+    if mapping is None:
+        mapping = _mappings()[1]
+    if not inplace:
+        model = copy.deepcopy(model)
+    for name, child in list(model.named_children()):
+        if type(child) in mapping:
+            new = mapping[type(child)].from_float(child)
+            model._modules[name] = new
+        else:
+            convert(child, mapping, inplace=True)
+    return model
+
+
+def prepare_model(model, args, q=None, at=None):
+    """quant_utils.py:112-147 for the BBB families: fuse, attach the QConfig, give every quantisable
+    leaf an activation fake-quant, and swap the float BBB modules for their QAT versions."""
+    if hasattr(model, "fuse_model"):
+        model.fuse_model()
+    qconfig = qconfig_for(args)
+    model.qconfig = qconfig
+    qat_map, _ = _mappings()
+
+    def attach(mod):
+        for name, child in list(mod.named_children()):
+            if type(child) in qat_map:
+                child.qconfig = qconfig
+                # observed like torch.quantization.prepare does for leaf modules in the allow-list
+                target = child[-1] if isinstance(child, nn.Sequential) and type(child[-1]) is nn.ReLU else child
+                mod._modules[name] = qat_map[type(child)].from_float(_with_observer(child, qconfig))
+            elif isinstance(child, torch.ao.quantization.QuantStub):
+                child.qconfig = qconfig
+                child.add_module("activation_post_process", qconfig.activation())
+                child.register_forward_hook(lambda m, i, o: m.activation_post_process(o))
+            elif type(child).__name__ == "Add" and hasattr(child, "add"):
+                child.add.activation_post_process = qconfig.activation()
+            else:
+                attach(child)
+    attach(model)
+    return model
+
+
+def _with_observer(mod, qconfig):
+    """torch.quantization.prepare leaves `activation_post_process` on the module (or on the trailing
+    ReLU of a fused Sequential) — the from_float methods of the QAT classes read it from there."""
+    inner = mod[0] if isinstance(mod, nn.Sequential) else mod
+    inner.qconfig = qconfig
+    if not hasattr(inner, "activation_post_process"):
+        inner.activation_post_process = qconfig.activation()
+    mod.qconfig = qconfig
+    return mod
+
+
+def postprocess_model(model, args, q=None, at=None, special_info=""):
+    """quant_utils.py:101-110 without the file I/O: convert the (trained, calibrated) QAT model to int8."""
+    return convert(model)

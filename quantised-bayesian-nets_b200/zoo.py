@@ -39,6 +39,22 @@ def clamp_activation(x, args):
     return x
 
 
+def _apply(layer, x):
+    """Run a non-stochastic glue layer; on int8 activations (QTensor) pooling/ReLU act on the integers
+    (order-preserving per-tensor affine map), like torch's quantised max_pool2d / relu."""
+    from .quant_utils import QTensor
+    if not isinstance(x, QTensor):
+        return layer(x)
+    if isinstance(layer, nn.MaxPool2d):
+        q = F.max_pool2d(x.q.float(), layer.kernel_size, layer.stride).to(torch.uint8).contiguous(memory_format=torch.channels_last)
+        return QTensor(q, x.scale, x.zero_point)
+    if isinstance(layer, nn.ReLU):
+        return QTensor(torch.clamp(x.q, min=x.zero_point), x.scale, x.zero_point)
+    if isinstance(layer, (Flatten, nn.Identity)):
+        return layer(x)
+    return layer(x)
+
+
 class Flatten(nn.Module):
     def forward(self, x):
         if len(x.shape) == 1:
@@ -102,14 +118,26 @@ class ConvNetwork_LeNet(nn.Module):
             nn.ReLU(),
             Linear(500, output_size, sigma_prior=sp, bias=False, args=args)])
         self.q = q
+        if self.q:
+            self.quant = torch.ao.quantization.QuantStub()
+            self.dequant = torch.ao.quantization.DeQuantStub()
 
     def forward(self, x):
+        if self.q:
+            x = clamp_activation(self.quant(x), self.args)
         for layer in self.layers:
-            x = layer(x)
+            x = clamp_activation(_apply(layer, x), self.args)
+        if self.q:
+            x = self.dequant(x)
         return F.softmax(x, dim=-1)
 
     def get_kl_divergence(self):
         return sum(m.get_kl_divergence() for m in self.modules() if isinstance(m, (Linear, Conv2d)))
+
+    def fuse_model(self):
+        """models_bbb.py:142-143: fuse layers 5,6 (Linear + ReLU) into a LinearReLU container."""
+        self.layers[5] = LinearReLU(self.layers[5], self.layers[6])
+        self.layers[6] = nn.Identity()
 
 
 class BasicBlock(nn.Module):

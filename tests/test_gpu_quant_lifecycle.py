@@ -1,0 +1,144 @@
+"""GPU (pytest -m gpu): the quantisation lifecycle of config C3 on the drop-in modules — prepare_model
+(QAT swap + observers), one train forward, one eval forward (calibrates add_weight/mul_noise), convert,
+int8 forward — against the reference run captured in tests/golden/tiny_{qat,int8}.npz.
+
+Fake-quantised values sit on a grid; an fp32 re-association upstream can move a pre-quantisation value
+across a rounding boundary, so float comparisons allow a handful of one-quantum differences."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_net(args):
+    from qbn_b200 import zoo
+    from qbn_b200.stochastic.bbb.conv import Conv2d
+    from qbn_b200.stochastic.bbb.linear import Linear
+    net = zoo.ConvNetwork_LeNet([1, 1, 28, 28], 10, True, args)
+    sp = args.sigma_prior
+    net.layers = nn.ModuleList([
+        Conv2d(1, 6, (5, 5), stride=1, padding=2, sigma_prior=sp, bias=False, args=args), nn.MaxPool2d(2, 2),
+        Conv2d(6, 12, (5, 5), stride=1, padding=2, sigma_prior=sp, bias=False, args=args), nn.MaxPool2d(2, 2),
+        zoo.Flatten(), Linear(12 * 7 * 7, 32, sigma_prior=sp, bias=False, args=args), nn.ReLU(),
+        Linear(32, 10, sigma_prior=sp, bias=False, args=args)])
+    return net
+
+
+def mostly_equal(got, ref, quantum, frac=0.995):
+    got = got.detach().float().cpu().numpy()
+    ref = np.asarray(ref, dtype=np.float32)
+    diff = np.abs(got - ref)
+    ok = diff <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    assert ok.mean() >= frac, "only %.4f of the elements agree" % ok.mean()
+    assert diff.max() <= 2.5 * quantum + 1e-6, "max diff %g vs quantum %g" % (diff.max(), quantum)
+
+
+def test_qat_then_int8_lifecycle(golden):
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import noise, quant_utils as qu, zoo
+    g = golden("tiny_qat")
+    args = zoo.Args(sigma_prior=0.1, model="conv_lenet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    net = _tiny_net(args)
+    names = [str(n) for n in g["qat_names"]]
+    mods = dict(net.named_modules())
+    with torch.no_grad():
+        for n in names:
+            mods[n].weight.copy_(torch.as_tensor(g["p.%s.weight" % n]))
+            mods[n].std.copy_(torch.as_tensor(g["p.%s.std" % n]))
+    net.train()
+    qu.prepare_model(net, args)
+    net = net.cuda()
+    mods = dict(net.named_modules())
+    assert [type(mods[n]).__name__ for n in names] == ["Conv2d", "Conv2d", "LinearReLU", "Linear"]
+    x = torch.as_tensor(g["x"]).cuda()
+    caps = {}
+    hooks = [mods[n].register_forward_hook(lambda m, i, o, n=n: caps.__setitem__(n, (i[0].detach(), o.detach()))) for n in names]
+    # ---- train-mode forward: LRT with fake-quantised (mu~, sigma~), first observer call initialises min/max
+    with noise.inject([torch.as_tensor(g["tr.%s.eps" % n]).cuda() for n in names]):
+        y = net(x)
+    for n in names:
+        m = mods[n]
+        for key, fq in (("wfq", m.weight_fake_quant), ("sfq", m.std_fake_quant), ("afq", m.activation_post_process)):
+            s_ref, z_ref = g["tr.%s.%s" % (n, key)][:2]
+            np.testing.assert_allclose(float(fq.scale), s_ref, rtol=2e-5)
+            assert abs(int(fq.zero_point) - int(z_ref)) <= 1
+        mostly_equal(caps[n][1], g["tr.%s.out" % n], float(m.activation_post_process.scale))
+    mostly_equal(y, g["tr.y"], 1e-3)
+    y.sum().backward()                                              # STE + LRT backward run end to end
+    assert all(torch.isfinite(mods[n].weight.grad).all() and torch.isfinite(mods[n].std.grad).all() for n in names)
+    # ---- eval-mode forward: EMA observer update, calibrates the add_weight / mul_noise fake-quants
+    net.eval()
+    with torch.no_grad(), noise.inject([torch.as_tensor(g["ev.%s.eps" % n]).cuda() for n in names]):
+        ye = net(x)
+    for n in names:
+        m = mods[n]
+        for key, fq in (("mulfq", m.mul_noise.activation_post_process), ("addfq", m.add_weight.activation_post_process),
+                        ("afq", m.activation_post_process)):
+            s_ref, z_ref = g["ev.%s.%s" % (n, key)][:2]
+            np.testing.assert_allclose(float(fq.scale), s_ref, rtol=5e-4)
+            assert abs(int(fq.zero_point) - int(z_ref)) <= 1
+        mostly_equal(caps[n][1], g["ev.%s.out" % n], float(m.activation_post_process.scale), frac=0.98)
+    mostly_equal(ye, g["ev.y"], 2e-3, frac=0.98)
+    for h in hooks:
+        h.remove()
+    # ---- convert to int8 and run with replayed noise
+    gi = golden("tiny_int8")
+    qu.convert(net)
+    net.eval()
+    mods = dict(net.named_modules())
+    assert [type(mods[n]).__name__ for n in names] == ["Conv2d", "Conv2d", "LinearReLU", "Linear"]
+    assert type(net.quant).__name__ == "Quantize"
+    np.testing.assert_allclose(net.quant.scale, gi["quant_qp"][0], rtol=1e-5)
+    for n in names:
+        m = mods[n]
+        np.testing.assert_allclose(m.mu_qp[0], gi[n + ".mu_qp"][0], rtol=5e-4)
+        np.testing.assert_allclose(m.sigma_qp[0], gi[n + ".sigma_qp"][0], rtol=5e-4)
+        np.testing.assert_allclose(m.scale, gi[n + ".out_qp"][0], rtol=5e-4)
+        agree = (m.weight.cpu().numpy() == gi[n + ".mu_q"]).mean()
+        assert agree > 0.97, (n, agree)
+    with torch.no_grad(), noise.inject([torch.as_tensor(gi[n + ".eps"]).cuda() for n in names]):
+        yq = net(x)
+    assert yq.shape == (8, 10) and torch.isfinite(yq).all()
+    assert float((yq.cpu() - torch.as_tensor(gi["y"])).abs().max()) < 0.05           # same predictive distribution
+    # state-dict round trip with the reference's key set (conv_q.py:72-78)
+    sd = mods[names[0]].state_dict()
+    assert {"scale", "zero_point", "weight", "std", "bias_"} <= set(sd.keys())
+    assert sd["weight"].dtype == torch.qint8
+
+
+def test_int8_modules_bit_exact_with_reference_qparams(golden):
+    """Drop-in int8 modules loaded with the reference's own int8 state (mu_q, sigma_q, every qparam):
+    sampled weights and layer outputs are bit-identical to the reference's FBGEMM forward."""
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import noise, zoo
+    from qbn_b200.quant_utils import QTensor
+    from qbn_b200.stochastic.bbb.quantized import conv_q, linear_q
+    g = golden("tiny_int8")
+    args = zoo.Args(activation_precision=7, weight_precision=8)
+    for n in [str(v) for v in g["q_names"]]:
+        mu_q, relu = g[n + ".mu_q"], bool(g[n + ".relu"])
+        if mu_q.ndim == 4:
+            stride, pad = [int(v) for v in g[n + ".conv"]]
+            cls = conv_q.ConvReLU2d if relu else conv_q.Conv2d
+            m = cls(mu_q.shape[1], mu_q.shape[0], mu_q.shape[2:], stride=(stride, stride), padding=(pad, pad), dilation=(1, 1), args=args)
+        else:
+            cls = linear_q.LinearReLU if relu else linear_q.Linear
+            m = cls(mu_q.shape[1], mu_q.shape[0], args=args)
+        m.weight, m.std = torch.as_tensor(mu_q).cuda(), torch.as_tensor(g[n + ".sigma_q"]).cuda()
+        m.mu_qp = (float(g[n + ".mu_qp"][0]), int(g[n + ".mu_qp"][1]))
+        m.sigma_qp = (float(g[n + ".sigma_qp"][0]), int(g[n + ".sigma_qp"][1]))
+        m.mul_qp = (float(g[n + ".mul_qp"][0]), int(g[n + ".mul_qp"][1]))
+        m.add_qp = (float(g[n + ".add_qp"][0]), int(g[n + ".add_qp"][1]))
+        m.scale, m.zero_point = float(g[n + ".out_qp"][0]), int(g[n + ".out_qp"][1])
+        xq = torch.as_tensor(g[n + ".x_q"]).cuda()
+        if xq.dim() == 4:
+            xq = xq.contiguous(memory_format=torch.channels_last)
+        x = QTensor(xq, float(g[n + ".x_qp"][0]), int(g[n + ".x_qp"][1]))
+        with noise.inject([torch.as_tensor(g[n + ".eps"]).cuda()]):
+            y = m(x)
+        assert np.array_equal(y.q.cpu().numpy(), g[n + ".y_q"]), n
+        assert abs(y.scale - g[n + ".y_qp"][0]) < 1e-12 and y.zero_point == int(g[n + ".y_qp"][1])
