@@ -120,6 +120,8 @@ int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n
                                       cp.async; otherwise it is rounded (cvt.rna) in registers   */
 #define QBN_FLAG_OUT_ROUND_TF32 4  /* TF32 mode: round the stored activations to TF32 (RNA) so the
                                       next layer can take the cp.async path                      */
+#define QBN_FLAG_OUT_PHASE_SPLIT 8 /* qbn_conv_p4_fwd: write the output phase-split for a stride-2 consumer */
+#define QBN_FLAG_OUT_P4 16         /* qbn_conv_fwd (TF32): out and residual are planar-C4 (see below)         */
 int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x,
                  const float* w, int w_shared, const float* scale, const float* shift,
                  const float* residual, int flags, const float* in_mask, float in_mult, float* out,
@@ -133,6 +135,30 @@ int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const floa
 int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x,
                     const float* w, int w_shared, const float* scale, const float* shift,
                     const float* residual, int flags, float* out, void* stream);
+
+/* ---- planar-C4 path: the S-batched eval convolution (A4 + A11 glue) with NO operand handling by threads.
+ * Activations "planar C4": [C/4 chunk planes][rows][4 floats], rows = the pixels of the zero-bordered maps
+ * [n_samples*B][Hp][Wp] (border = the conv padding, must be zero, TF32-exact values).  Sampled weights
+ * "blocked": [sample][C/CB][R*S][CB/4][n_pad][4] (CB depends on C and the stride, n_pad = N rounded up to 16: qbn_p4_weight_floats), written by
+ * qbn_sample_weights_blocked from mu/sigma blocked once by qbn_p4_block_weights.  A tile's operands are then
+ * contiguous runs moved by bulk copies, every filter tap is a row-shifted UMMA descriptor on one smem image
+ * (zero-copy im2col), and the epilogue's 16-byte stores are contiguous across a warp.
+ *   stride 1: odd RxS "same" conv, Hp = H + R - 1.
+ *   stride 2: 3x3 pad 1 or 1x1 pad 0; Hp = H_out + 2; x is PHASE-SPLIT: [C/4][4 phases][n_samples*B*Hp*Wp][4]
+ *             where phase (a,b) holds pixels (2i+a, 2j+b) of the full-resolution map at (i+1, j+1), as written
+ *             by the producing qbn_conv_p4_fwd with QBN_FLAG_OUT_PHASE_SPLIT (into a pre-zeroed buffer).
+ * out / residual: planar C4 [N/4][n_samples*B*Hp*Wp][4]; border rows of out are written as zeros. */
+int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long long* out_floats /* host */);
+int qbn_p4_block_weights(const float* w_ohwi /* [n_mats][N][taps][C] */, int n_mats, int N, int C, int taps,
+                         int stride, float* out, void* stream);
+int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_b, int N, int C, int taps, int stride, int n_samples,
+                               const float* eps /* nullable, canonical [n_samples][N][taps][C] */, uint64_t seed,
+                               uint32_t layer_id, uint32_t sample0, float* w, int round_tf32, void* stream);
+int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
+                    const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
+                    int flags, float* out, void* stream);
+/* global average pool of planar-C4 maps -> [n_img][C] (divisor = interior pixel count) */
+int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, float divisor, float* out, void* stream);
 
 /* ---- A8 standalone: x[b,h,w,c] * mask[b,c] * mult (dropout.py:35-39); mask NULL -> Philox ---- */
 int qbn_dropout_fwd(const float* x, int64_t rows /*B*/, int64_t hw, int64_t C, const float* mask,
@@ -237,6 +263,8 @@ int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float* out, void*
 /* Diagnostic: per-instruction cycle costs of tcgen05 fence / commit / mma / ld on this device (one
  * CTA); out_dev receives 12 counters.  Used to size the kernel pipelines, no product use. */
 int qbn_ubench_tcgen05(unsigned long long* out_dev, int n_cols, int reps, void* stream);
+/* same, with ctas_per_sm resident CTAs of n_warps MMA issuer warps each (cross-CTA overlap of the tensor pipe) */
+int qbn_ubench_tcgen05_multi(unsigned long long* out_dev, int n_cols, int reps, int ctas_per_sm, int n_warps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,8 @@ QBN_MATH_TF32 = 1
 QBN_FLAG_RELU = 1
 QBN_FLAG_A_TF32_READY = 2
 QBN_FLAG_OUT_ROUND_TF32 = 4
+QBN_FLAG_OUT_PHASE_SPLIT = 8
+QBN_FLAG_OUT_P4 = 16
 
 
 class ConvDesc(Structure):
@@ -60,10 +62,16 @@ _SIGNATURES = {
     "qbn_cls_metrics": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P]),
     "qbn_reg_metrics": (c_int, [P, P, P, c_int64, P, P]),
     "qbn_ubench_tcgen05": (c_int, [P, c_int, c_int, P]),
+    "qbn_ubench_tcgen05_multi": (c_int, [P, c_int, c_int, c_int, c_int, P]),
     "qbn_maxpool2x2": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "qbn_avgpool_all": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
     "qbn_conv_s1_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
     "qbn_nchw_to_nhwc": (c_int, [P, c_int64, c_int, c_int, P, P]),
+    "qbn_p4_weight_floats": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_longlong)]),
+    "qbn_p4_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "qbn_sample_weights_blocked": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, c_uint64, c_uint32, c_uint32, P, c_int, P]),
+    "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
+    "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -712,3 +712,138 @@ extern "C" int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float*
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// planar-C4 path (p4_layout.cuh): weight blocking, blocked A4 sampler, pooling
+// ---------------------------------------------------------------------------------------------
+#include "p4_layout.cuh"
+
+struct P4Block { int N, C, taps, CB, cbc, n_pad, K; int64_t total4; };
+static bool p4_block_geom(int N, int C, int taps, int stride, P4Block& g) {
+  g.N = N; g.C = C; g.taps = taps; g.CB = qbn_p4_block_channels(C, stride, taps);
+  if (C % 8 != 0 || g.CB == 0 || N > 256 || N <= 0 || taps <= 0) return false;
+  g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(N); g.K = taps * C;
+  g.total4 = (int64_t)(C / g.CB) * taps * g.cbc * g.n_pad;
+  return true;
+}
+// blocked float4 index -> canonical OHWI element index (or -1 for the zero rows n >= N)
+__device__ __forceinline__ int64_t p4_canonical(const P4Block& g, int64_t i) {
+  const int n = (int)(i % g.n_pad);
+  int64_t t1 = i / g.n_pad;
+  const int j = (int)(t1 % g.cbc);
+  t1 /= g.cbc;
+  const int t = (int)(t1 % g.taps);
+  const int cb = (int)(t1 / g.taps);
+  if (n >= g.N) return -1;
+  return (int64_t)n * g.K + (int64_t)t * g.C + cb * g.CB + 4 * j;
+}
+
+__global__ void p4_block_weights_kernel(const float* __restrict__ w, P4Block g, float* __restrict__ out) {
+  const float* ws = w + (int64_t)blockIdx.y * g.N * g.K;
+  float4* os = reinterpret_cast<float4*>(out) + (int64_t)blockIdx.y * g.total4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = p4_canonical(g, i);
+    os[i] = idx < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(ws + idx);
+  }
+}
+extern "C" int qbn_p4_block_weights(const float* w_ohwi, int n_mats, int N, int C, int taps, int stride, float* out, void* stream) {
+  QBN_CHECK_ARG(w_ohwi && out && n_mats > 0 && n_mats <= 65535, "args");
+  P4Block g;
+  if (!p4_block_geom(N, C, taps, stride, g)) {
+    qbn_set_error("qbn_p4_block_weights: needs C %% 8 == 0 and N <= 256 (C=%d N=%d)", C, N);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  int gx = (int)((g.total4 + 255) / 256);
+  int cap = (qbn_sm_count() * 8 + n_mats - 1) / n_mats;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  p4_block_weights_kernel<<<dim3(gx, n_mats), 256, 0, (cudaStream_t)stream>>>(w_ohwi, g, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// A4 on blocked operands: W[s] = mu + sigma * eps_s written straight into the smem image the conv kernel
+// bulk-copies.  The Philox counter is the CANONICAL OHWI element index / 4, so the sampled values are
+// bit-identical to qbn_sample_weights' whatever the blocking.
+__global__ void sample_weights_blocked_kernel(const float* __restrict__ mu_b, const float* __restrict__ sigma_b, P4Block g,
+                                              const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
+                                              float* __restrict__ w, int round_tf32) {
+  const int s = blockIdx.y;
+  float4* ws = reinterpret_cast<float4*>(w) + (int64_t)s * g.total4;
+  const float* es = eps ? eps + (int64_t)s * g.N * g.K : nullptr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = p4_canonical(g, i);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx >= 0) {
+      float z[4];
+      if (es) {
+        const float4 e = *reinterpret_cast<const float4*>(es + idx);
+        z[0] = e.x; z[1] = e.y; z[2] = e.z; z[3] = e.w;
+      } else {
+        philox_normal4(seed, layer_id, sample0 + (uint32_t)s, (uint64_t)(idx >> 2), z);
+      }
+      const float4 m = reinterpret_cast<const float4*>(mu_b)[i];
+      const float4 sg = reinterpret_cast<const float4*>(sigma_b)[i];
+      o.x = __fadd_rn(m.x, __fmul_rn(z[0], sg.x));
+      o.y = __fadd_rn(m.y, __fmul_rn(z[1], sg.y));
+      o.z = __fadd_rn(m.z, __fmul_rn(z[2], sg.z));
+      o.w = __fadd_rn(m.w, __fmul_rn(z[3], sg.w));
+      if (round_tf32) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
+    }
+    ws[i] = o;
+  }
+}
+extern "C" int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_b, int N, int C, int taps, int stride, int n_samples,
+                                          const float* eps, uint64_t seed, uint32_t layer_id, uint32_t sample0, float* w,
+                                          int round_tf32, void* stream) {
+  QBN_CHECK_ARG(mu_b && sigma_b && w, "null pointer");
+  QBN_CHECK_ARG(n_samples > 0 && n_samples <= 65535, "0<n_samples<=65535");
+  P4Block g;
+  if (!p4_block_geom(N, C, taps, stride, g)) {
+    qbn_set_error("qbn_sample_weights_blocked: needs C %% 8 == 0 and N <= 256 (C=%d N=%d)", C, N);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  int gx = (int)((g.total4 + 255) / 256);
+  int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  sample_weights_blocked_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_b, sigma_b, g, eps, seed, layer_id, sample0, w,
+                                                                                     round_tf32);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// global average pool of planar-C4 maps: x [C/4][n_img * HW][4] -> out [n_img][C]; one warp per (image, chunk)
+// reads HW contiguous 16-byte rows.  The zero border contributes nothing; divisor = interior size.
+__global__ void avgpool_p4_kernel(const float* __restrict__ x, int64_t n_img, int HW, int C, float inv, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int chunks = C >> 2;
+  const int64_t plane = n_img * HW;
+  for (int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < n_img * chunks; wi += warps) {
+    const int64_t img = wi / chunks;
+    const int j = (int)(wi - img * chunks);
+    const float4* src = reinterpret_cast<const float4*>(x) + (int64_t)j * plane + img * HW;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = lane; r < HW; r += 32) {
+      const float4 v = src[r];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+      a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+      a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    if (lane == 0) *reinterpret_cast<float4*>(out + img * C + 4 * j) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
+extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, float divisor, float* out, void* stream) {
+  QBN_CHECK_ARG(x && out && n_img > 0 && HW > 0 && C > 0 && C % 4 == 0 && divisor > 0.f, "args");
+  const int64_t warps = n_img * (C / 4);
+  int64_t blocks = (warps + 7) / 8;
+  const int64_t cap = (int64_t)qbn_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  avgpool_p4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_img, HW, C, 1.0f / divisor, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

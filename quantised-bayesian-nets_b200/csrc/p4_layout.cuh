@@ -1,0 +1,29 @@
+// Layouts shared by the planar-C4 convolution kernel (umma_conv_p4.cu), the blocked weight sampler and the
+// layout helpers (core.cu).
+//
+// Activations, "planar C4":  [C/4 chunk planes][rows][4 floats], rows = n_samples * B * Hp * Wp pixels of the
+// zero-bordered maps.  One 16-byte K-chunk of a pixel is contiguous and consecutive pixels of one chunk plane
+// are contiguous, which is exactly one column of UMMA's K-major no-swizzle operand layout: a tile's chunk
+// plane is ONE bulk (TMA-engine) copy, and an epilogue thread (= one pixel) stores 16 bytes next to its
+// neighbour's (fully coalesced).
+//
+// Sampled weights, "blocked":  [sample][channel block cb][tap t][chunk j][n_pad rows][4 floats] — every
+// (cb, tap) block is already the smem image of the B operand, so it is one bulk copy too.
+#pragma once
+
+// channels per block: whole C when small, else the largest of {32, 48, 40, 24, 16, 8} dividing C.
+// A stride-2 3x3 conv stages four phase strips per block, so its blocks are at most 24 channels.
+static inline int qbn_p4_block_channels(int C, int stride = 1, int taps = 9) {
+  if (stride == 2 && taps > 1) {
+    const int c2[3] = {24, 16, 8};
+    for (int i = 0; i < 3; ++i)
+      if (C % c2[i] == 0) return c2[i];
+    return 0;
+  }
+  if (C <= 48) return C;
+  const int cand[6] = {32, 48, 40, 24, 16, 8};
+  for (int i = 0; i < 6; ++i)
+    if (C % cand[i] == 0) return cand[i];
+  return 0;
+}
+static inline int qbn_p4_n_pad(int N) { return (N + 15) / 16 * 16; }

@@ -42,6 +42,7 @@ struct UParams {
   int oph, opw;     // zero-bordered output layout (interior written only)
   int n_split;      // >0: the N columns are n_split channels of N/n_split stacked Monte-Carlo samples (shared input)
   long long sample_out_stride;   // elements between consecutive samples' output tensors
+  long long out_plane;           // QBN_FLAG_OUT_P4: rows per chunk plane of the planar-C4 output (all samples)
   uint32_t idesc;
   // tensors
   const void* x; const void* w; const void* w2;
@@ -299,13 +300,15 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     const bool mv = m < p.M;
     const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int Nrow = p.n_split ? p.n_split : p.N;      // channels per stored row
-    size_t orow = ((size_t)z * p.M + (mv ? m : 0)) * Nrow;
+    size_t prow = (size_t)z * p.M + (mv ? m : 0);          // pixel row of the output tensor
     if (p.oph | p.opw) {
       const int mm = mv ? m : 0;
       const int wo = mm % p.Wo, t2 = mm / p.Wo, ho = t2 % p.Ho, b = t2 / p.Ho;
       const int Hop = p.Ho + 2 * p.oph, Wop = p.Wo + 2 * p.opw;
-      orow = ((((size_t)z * p.B + b) * Hop + ho + p.oph) * Wop + wo + p.opw) * Nrow;
+      prow = (((size_t)z * p.B + b) * Hop + ho + p.oph) * Wop + wo + p.opw;
     }
+    const size_t orow = prow * Nrow;
+    const bool out_p4 = (MODE == MODE_EVAL) && (p.flags & QBN_FLAG_OUT_P4);
     int rowsum = 0;
     if constexpr (I8) {
       uint32_t v[8];
@@ -325,6 +328,9 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
         // sample-stacked columns (shared input, first layer): column c = sample (c / n_split), channel (c % n_split)
         const int ch0 = p.n_split ? c0 % p.n_split : c0;
         const size_t obase = p.n_split ? orow + (size_t)(c0 / p.n_split) * (size_t)p.sample_out_stride : orow;
+        // planar-C4 output (p4_layout.cuh): channel c of pixel row r lives at ((c/4) * out_plane + r) * 4 + c%4
+        const size_t prow_s = p.n_split ? prow + (size_t)(c0 / p.n_split) * (size_t)(p.sample_out_stride / p.n_split) : prow;
+        auto p4_index = [&](int c) { return ((size_t)(c >> 2) * (size_t)p.out_plane + prow_s) * 4 + (size_t)(c & 3); };
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -332,13 +338,16 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
           if (j < nvalid) {
             if (p.scale) a = __fmul_rn(a, __ldg(p.scale + ch0 + j));
             if (p.shift) a = __fadd_rn(a, __ldg(p.shift + ch0 + j));
-            if (p.residual) a = __fadd_rn(a, __ldg(p.residual + obase + ch0 + j));
+            if (p.residual) a = __fadd_rn(a, __ldg(p.residual + (out_p4 ? p4_index(ch0 + j) : obase + ch0 + j)));
             if (p.flags & QBN_FLAG_RELU) a = fmaxf(a, 0.f);
             if (p.flags & QBN_FLAG_OUT_ROUND_TF32) a = __uint_as_float(tf32_rna(a));
           }
           o[j] = a;
         }
-        if (nvalid == 8 && ((obase + ch0) & 3) == 0) {
+        if (out_p4) {
+          *reinterpret_cast<float4*>(out + p4_index(ch0)) = make_float4(o[0], o[1], o[2], o[3]);
+          if (nvalid > 4) *reinterpret_cast<float4*>(out + p4_index(ch0 + 4)) = make_float4(o[4], o[5], o[6], o[7]);
+        } else if (nvalid == 8 && ((obase + ch0) & 3) == 0) {
           *reinterpret_cast<float4*>(out + obase + ch0) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4*>(out + obase + ch0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
         } else {
@@ -466,6 +475,13 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
   p.x = x; p.w = w; p.x_shared = x_shared; p.w_shared = w_shared;
   p.scale = scale; p.shift = shift; p.residual = residual; p.flags = flags; p.in_mask = in_mask; p.in_mult = in_mult;
   p.out = out;
+  if (flags & QBN_FLAG_OUT_P4) {
+    if (d->N % 4 != 0) {
+      qbn_set_error("qbn_conv_fwd: planar-C4 output needs N %% 4 == 0 (N=%d)", d->N);
+      return QBN_ERR_UNSUPPORTED;
+    }
+    p.out_plane = (long long)n_samples * d->B * (d->Ho + 2 * d->out_pad_h) * (d->Wo + 2 * d->out_pad_w);
+  }
   // Shared input (first layer): stack the samples' weights along N — [S][N][K] IS an [S*N][K] matrix — so
   // the input tile is staged once for all samples and one accumulator tile holds every sample's channels.
   if (x_shared && !w_shared && n_samples > 1 && d->N % 8 == 0 && n_samples * d->N <= 256 && !residual && !in_mask) {

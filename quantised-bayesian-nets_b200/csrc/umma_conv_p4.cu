@@ -1,0 +1,507 @@
+// Zero-copy-im2col tcgen05 convolution on the planar-C4 zero-bordered layout (see p4_layout.cuh).
+//
+//   out[q][n] = act( scale[n] * sum_{tap, c} x[strip(tap)][q + shift(tap)][c] * w[z][n][tap][c] + shift[n] + residual[q][n] )
+//
+// q = flat pixel index of the zero-bordered map [n_samples*B][Hp][Wp]; the zero border IS the padding.
+//  * stride 1, odd RxS "same" conv: one input strip, shift(r,s) = (r-ph)*Wp + (s-pw).
+//  * stride 2 (3x3 pad 1, or 1x1 pad 0): the input arrives PHASE-SPLIT — four half-resolution zero-bordered
+//    maps, phase (h&1, w&1) of the full-resolution one, each with the OUTPUT's geometry — so tap (r,s) reads
+//    strip ((r-1)&1, (s-1)&1) at shift floor((r-1)/2)*Wp + floor((s-1)/2): again a pure row shift.
+//    The producing layer writes that layout directly from its epilogue (QBN_FLAG_OUT_PHASE_SPLIT).
+// Every tap is therefore a UMMA descriptor whose start address is shifted by a whole number of 16-byte rows
+// inside ONE smem image of the rows [q0 - d_before, q0 + 128 + d_after) (K-major, no swizzle: a pixel's
+// 16-byte K-chunk is one row of an 8-row core matrix).  Nothing is gathered and nothing is re-read.
+//
+// Persistent, warp-specialised, and no thread ever touches operand data:
+//   warp 5, one lane : bulk copies (cp.async.bulk -> mbarrier complete_tx): one per chunk plane of a tile
+//                      (contiguous in the planar layout), one per weight block (pre-blocked by the sampler)
+//   warp 4           : tcgen05.mma kind::tf32 issue, tcgen05.commit releases the smem slots / signals the epilogue
+//   warps 0-3        : epilogue, one TMEM lane = one pixel per thread: affine (BN/bias) + residual + ReLU + RNA
+//                      rounding, 16-byte stores that are contiguous across the warp
+// TMEM holds ACC accumulator tiles so the MMAs of tile i+1.. overlap the epilogue of tile i.
+#include <stdlib.h>
+#include <string.h>
+#include "p4_layout.cuh"
+#include "umma_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int P4_THREADS = 192;
+constexpr int MAX_TAPS = 25;
+
+struct P4Params {
+  int Hp, Wp, bh, bw, B;
+  int N, n_pad, Qs, tiles_per_sample, total_tiles;
+  int cbc, n_cb, n_strips, taps, nk;
+  int RA, RA_p, d_before;
+  int SA, SB, b_res, ACC, tmem_cols, flags, w_shared, dbg;
+  uint32_t a_bytes, bt_bytes, b_slot_bytes;
+  uint32_t idesc, mg_plane, mg_wp;
+  long long x_plane, strip_rows, out_plane, res_plane, w_sample_floats;
+  int out_split, Hp2, Wp2;
+  long long q2_total;
+  int tap_off[MAX_TAPS];          // 16-byte units inside an A slot: strip * cbc * RA_p + d_before + shift
+  const float* x; const float* w; const float* scale; const float* shift; const float* residual; float* out;
+};
+
+// cycle accounting of CTA 0 (QBN_P4_PROF=1): [role*8 + category], summed over its tiles
+__device__ unsigned long long g_p4_prof[32];
+// (accumulated in registers, flushed once at the end: a global read-modify-write per sample would dominate)
+#define PROF_BEGIN() long long t_prof = PROF ? clock64() : 0
+#define PROF_ADD(slot)                                   \
+  do {                                                   \
+    if (PROF) {                                          \
+      const long long t_now = clock64();                 \
+      prof_acc[(slot) & 7] += (unsigned long long)(t_now - t_prof); \
+      t_prof = t_now;                                    \
+    }                                                    \
+  } while (0)
+
+QBN_DEVINL void warp_wait(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(smem_u32(bar), parity);
+  __syncwarp();
+}
+QBN_DEVINL float4 ld_nc4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// n / d for n*1 < 2^32 with m = floor(2^32 / d): estimate is exact or one too small
+QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
+  q = __umulhi(n, m);
+  r = n - q * d;
+  if (r >= d) { ++q; r -= d; }
+}
+
+template <int DBG_MODE>
+__global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting
+  const int dbg = DBG_MODE == 2 ? p.dbg : 0;              // ablation knobs (QBN_P4_DBG): 1 no stores, 2 one MMA per tile, 4 no A copies, 8 no TMEM loads
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + (size_t)p.SA * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.SB * p.b_slot_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + p.SA;
+  uint64_t* b_full = a_empty + p.SA;
+  uint64_t* b_empty = b_full + p.SB;
+  uint64_t* acc_full = b_empty + p.SB;
+  uint64_t* acc_empty = acc_full + p.ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + p.ACC);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_shift = s_scale + 256;
+  for (int i = tid; i < 256; i += P4_THREADS) {
+    s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
+    s_shift[i] = (p.shift && i < p.N) ? p.shift[i] : 0.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+    for (int i = 0; i < p.ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // contiguous tile range per CTA: consecutive tiles share the sample (=> the resident weights) and their halos hit L2
+  const int tile_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 5) {
+    // ======================================= PRODUCER (one lane) ================================
+    if (lane == 0) {
+      int sa = 0, sb = 0, cur_z = -1;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t strip_bytes = (uint32_t)p.cbc * p.RA_p * 16;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int z = tile / p.tiles_per_sample;
+        const int q0 = (tile - z * p.tiles_per_sample) * TM;
+        const float* ws = p.w + (p.w_shared ? 0 : (size_t)z * p.w_sample_floats);
+        PROF_BEGIN();
+        if (p.b_res && z != cur_z) {
+          mbar_wait(smem_u32(&b_empty[0]), pb ^ 1);          // MMAs of the previous sample have retired
+          const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * p.taps);
+          mbar_arrive_expect_tx(smem_u32(&b_full[0]), total);
+          for (uint32_t off = 0; off < total; off += 32768u)
+            bulk_load_g2s(smem_u32(b_ring) + off, reinterpret_cast<const uint8_t*>(ws) + off, min(32768u, total - off), smem_u32(&b_full[0]));
+          pb ^= 1;
+          cur_z = z;
+        }
+        // rows [g0, g0 + RA) of every strip, clamped to the tensor (rows outside feed border outputs only)
+        const long long g0 = (long long)z * p.Qs + q0 - p.d_before;
+        const long long lo = g0 < 0 ? 0 : g0;
+        const long long hi = (g0 + p.RA > p.strip_rows) ? p.strip_rows : g0 + p.RA;
+        const uint32_t row_bytes = (uint32_t)(hi - lo) * 16;
+        const uint32_t dst_off = (uint32_t)(lo - g0) * 16;
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          PROF_ADD(16);
+          mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
+          PROF_ADD(17);
+          const uint32_t bar = smem_u32(&a_full[sa]);
+          if (dbg & 4) { mbar_arrive(bar); if (++sa == p.SA) { sa = 0; pa ^= 1; } continue; }
+          mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(p.cbc * p.n_strips));
+          const uint32_t slot = smem_u32(a_ring + (size_t)sa * p.a_bytes) + dst_off;
+          for (int s = 0; s < p.n_strips; ++s) {
+            const float* src = p.x + ((size_t)(cb * p.cbc) * p.x_plane + (size_t)s * p.strip_rows + lo) * 4;
+            for (int j = 0; j < p.cbc; ++j)
+              bulk_load_g2s(slot + (uint32_t)s * strip_bytes + (uint32_t)(j * p.RA_p) * 16, src + (size_t)j * p.x_plane * 4, row_bytes, bar);
+          }
+          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+          PROF_ADD(18);
+          if (!p.b_res) {
+            const uint8_t* wb = reinterpret_cast<const uint8_t*>(ws) + (size_t)cb * p.taps * p.bt_bytes;
+            for (int t = 0; t < p.taps; ++t) {
+              mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
+              PROF_ADD(19);
+              mbar_arrive_expect_tx(smem_u32(&b_full[sb]), p.bt_bytes);
+              bulk_load_g2s(smem_u32(b_ring + (size_t)sb * p.b_slot_bytes), wb + (size_t)t * p.bt_bytes, p.bt_bytes, smem_u32(&b_full[sb]));
+              if (++sb == p.SB) { sb = 0; pb ^= 1; }
+              PROF_ADD(20);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ======================================= MMA ISSUER =========================================
+    // ONE elected thread runs the whole issue loop (waits, tcgen05.mma, tcgen05.commit).  Inside an
+    // elect.sync region ptxas keeps the descriptors in uniform registers; issuing from all lanes under a
+    // leader predicate made it wrap every MMA in an ELECT / R2UR.BROADCAST waterfall loop (~100 cycles each).
+    if (elect_one()) {
+      int sa = 0, sb = 0, as = 0, cur_z = -1;
+      uint32_t pa = 0, pb = 0, pacc = 0;
+      const uint32_t lbo_a = (uint32_t)p.RA_p * 16, lbo_b = (uint32_t)p.n_pad * 16;
+      const uint64_t adesc_hi = make_smem_desc(0, lbo_a, 128), bdesc_hi = make_smem_desc(0, lbo_b, 128);
+      const uint32_t a_k = (2 * lbo_a) >> 4, b_k = (2 * lbo_b) >> 4;      // one K=8 step = two 16-byte chunks
+      const uint32_t bt16 = p.bt_bytes >> 4;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int z = tile / p.tiles_per_sample;
+        const bool last_of_z = (tile + 1 >= tile_end) || ((tile + 1) / p.tiles_per_sample != z);
+        PROF_BEGIN();
+        if (p.b_res && z != cur_z) {
+          mbar_wait(smem_u32(&b_full[0]), pb);
+          pb ^= 1;
+          cur_z = z;
+        }
+        PROF_ADD(8);
+        mbar_wait(smem_u32(&acc_empty[as]), pacc ^ 1);      // epilogue has drained this accumulator
+        PROF_ADD(9);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * p.n_pad);
+        uint32_t accum = 0;
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          mbar_wait(smem_u32(&a_full[sa]), pa);
+          PROF_ADD(10);
+          tc_fence_after();
+          const uint32_t a16 = smem_u32(a_ring + (size_t)sa * p.a_bytes) >> 4;
+          uint32_t b16 = (smem_u32(b_ring) >> 4) + (uint32_t)(cb * p.taps) * bt16;
+#pragma unroll 1
+          for (int t = 0; t < p.taps; ++t) {
+            if (!p.b_res) {
+              mbar_wait(smem_u32(&b_full[sb]), pb);
+              PROF_ADD(11);
+              tc_fence_after();
+              b16 = smem_u32(b_ring + (size_t)sb * p.b_slot_bytes) >> 4;
+            }
+            uint32_t ad = a16 + (uint32_t)p.tap_off[t], bd = b16;
+#pragma unroll 1
+            for (int jj = 0; jj < ((dbg & 2) ? (t == 0 && cb == 0 ? 1 : 0) : p.nk); ++jj) {
+              umma_mma<MODE_EVAL>(tacc, adesc_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
+              accum = 1;
+              ad += a_k; bd += b_k;
+            }
+            if (!p.b_res) {
+              umma_commit(smem_u32(&b_empty[sb]));
+              if (++sb == p.SB) { sb = 0; pb ^= 1; }
+            } else {
+              b16 += bt16;
+            }
+            PROF_ADD(12);
+          }
+          umma_commit(smem_u32(&a_empty[sa]));
+          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(smem_u32(&acc_full[as]));
+        if (p.b_res && last_of_z) umma_commit(smem_u32(&b_empty[0]));
+        if (++as == p.ACC) { as = 0; pacc ^= 1; }
+        PROF_ADD(13);
+      }
+      if (PROF && blockIdx.x == 0)
+        for (int i = 0; i < 8; ++i) g_p4_prof[8 + i] = prof_acc[i];
+    }
+    __syncwarp();
+  } else {
+    // ======================================= EPILOGUE ===========================================
+    int as = 0;
+    uint32_t pacc = 0;
+    const uint32_t plane = (uint32_t)(p.Hp * p.Wp);
+    const int n_groups = p.n_pad >> 4;
+    const int n_chunks = p.N >> 2;
+    const bool relu = p.flags & QBN_FLAG_RELU, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int z = tile / p.tiles_per_sample;
+      const int q0 = (tile - z * p.tiles_per_sample) * TM;
+      PROF_BEGIN();
+      const int q = q0 + tid;
+      const bool qv = q < p.Qs;
+      uint32_t b, rem, hh, ww;
+      divmod(qv ? (uint32_t)q : 0u, plane, p.mg_plane, b, rem);
+      divmod(rem, (uint32_t)p.Wp, p.mg_wp, hh, ww);
+      const bool interior = qv && (int)hh >= p.bh && (int)hh < p.Hp - p.bh && (int)ww >= p.bw && (int)ww < p.Wp - p.bw;
+      const long long in_row = (long long)z * p.Qs + q;
+      long long orow = in_row;
+      bool store = qv;
+      if (p.out_split) {
+        // phase-split output for a stride-2 consumer: pixel (h, w) -> map (h&1, w&1), position (h>>1, w>>1)
+        const int h = (int)hh - p.bh, w = (int)ww - p.bw;
+        orow = (long long)((h & 1) * 2 + (w & 1)) * p.q2_total + ((long long)(z * p.B + (int)b) * p.Hp2 + (h >> 1) + 1) * p.Wp2 + (w >> 1) + 1;
+        store = interior;                                   // its border is never written (pre-zeroed buffer)
+      }
+      float* optr = p.out + (store ? orow : 0) * 4;
+      const float* rptr = (p.residual && interior) ? p.residual + in_row * 4 : nullptr;
+      float4 rres[4], rnext[4];
+      uint32_t v[16], vn[16];
+      auto prefetch = [&](float4* dst, int g) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = g * 4 + i;
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rptr && ch < n_chunks) dst[i] = ld_nc4(rptr + (size_t)ch * p.res_plane * 4);
+        }
+      };
+      prefetch(rres, 0);
+      PROF_ADD(0);
+      warp_wait(&acc_full[as], pacc, lane);
+      PROF_ADD(1);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
+      if (!(dbg & 8)) tmem_ld16(tlane, v);
+      for (int g = 0; g < n_groups; ++g) {
+        tmem_ld_wait();
+        if (g + 1 < n_groups) {
+          if (!(dbg & 8)) tmem_ld16(tlane + (uint32_t)((g + 1) * 16), vn);
+          prefetch(rnext, g + 1);
+        } else {                                            // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+        }
+        PROF_ADD(2);
+        if (store && !(dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ch = g * 4 + i;
+            if (ch < n_chunks) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (interior) {
+                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[ch * 4]);
+                const float4 sh = *reinterpret_cast<const float4*>(&s_shift[ch * 4]);
+                o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x) + rres[i].x;
+                o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y) + rres[i].y;
+                o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z) + rres[i].z;
+                o.w = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w) + rres[i].w;
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (rnd) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
+              }
+              *reinterpret_cast<float4*>(optr + (size_t)ch * p.out_plane * 4) = o;
+            }
+          }
+        }
+        if (g + 1 < n_groups) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rres[i] = rnext[i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = vn[i];
+        }
+        PROF_ADD(3);
+      }
+      if (++as == p.ACC) { as = 0; pacc ^= 1; }
+    }
+  }
+  if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {
+    const int role = warp == 0 ? 0 : 16;
+    for (int i = 0; i < 8; ++i) g_p4_prof[role + i] = prof_acc[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+extern "C" int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long long* out_floats) {
+  QBN_CHECK_ARG(out_floats && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
+  const int CB = qbn_p4_block_channels(C, stride, R * S);
+  if (C % 8 != 0 || CB == 0 || N > 256) {
+    qbn_set_error("planar-C4 conv: needs C %% 8 == 0 and N <= 256 (C=%d N=%d)", C, N);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  *out_floats = (long long)(C / CB) * R * S * (CB / 4) * qbn_p4_n_pad(N) * 4;
+  return QBN_OK;
+}
+
+extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
+                               const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
+                               int flags, float* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QBN_CHECK_ARG(x && w && out, "null pointer");
+  QBN_CHECK_ARG(n_samples > 0 && B > 0 && Hp > 2 && Wp > 2 && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
+  const int CB = qbn_p4_block_channels(C, stride, R * S);
+  const bool s1 = stride == 1 && (R & 1) && (S & 1);
+  const bool s2 = stride == 2 && ((R == 3 && S == 3) || (R == 1 && S == 1));
+  if (C % 8 != 0 || CB == 0 || N % 4 != 0 || N > 256 || !(s1 || s2) || R * S > MAX_TAPS) {
+    qbn_set_error("qbn_conv_p4_fwd: needs C %% 8 == 0, N %% 4 == 0, N <= 256 and stride 1 (odd kernel) or stride 2 (3x3 / 1x1) "
+                  "(C=%d N=%d R=%d S=%d stride=%d)", C, N, R, S, stride);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  P4Params p;
+  memset(&p, 0, sizeof(p));
+  p.Hp = Hp; p.Wp = Wp; p.B = B; p.N = N;
+  p.bh = s1 ? (R - 1) / 2 : 1;
+  p.bw = s1 ? (S - 1) / 2 : 1;
+  QBN_CHECK_ARG(Hp > 2 * p.bh && Wp > 2 * p.bw, "padded extent must exceed the border");
+  p.Qs = B * Hp * Wp;
+  p.tiles_per_sample = (p.Qs + TM - 1) / TM;
+  p.total_tiles = p.tiles_per_sample * n_samples;
+  p.n_pad = qbn_p4_n_pad(N);
+  p.n_cb = C / CB;
+  p.cbc = CB / 4;
+  p.nk = p.cbc / 2;
+  p.taps = R * S;
+  p.strip_rows = (long long)n_samples * p.Qs;
+  int d_after = 0;
+  if (s1) {
+    p.n_strips = 1;
+    p.d_before = p.bh * Wp + p.bw;
+    d_after = p.d_before;
+  } else {
+    p.n_strips = (R == 3) ? 4 : 1;
+    p.d_before = (R == 3) ? Wp + 1 : 0;
+  }
+  p.x_plane = p.strip_rows * ((s2 && R == 1) ? 4 : p.n_strips);   // a 1x1 stride-2 conv reads phase (0,0) of a 4-phase tensor
+  p.RA = TM + p.d_before + d_after;
+  p.RA_p = (p.RA + 7) / 8 * 8;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int strip = 0, sh;
+      if (s1) {
+        sh = (r - p.bh) * Wp + (s - p.bw);
+      } else if (R == 3) {
+        const int dr = r - 1, ds = s - 1;
+        strip = (dr & 1) * 2 + (ds & 1);
+        sh = (dr < 0 ? -1 : 0) * Wp + (ds < 0 ? -1 : 0);
+      } else {
+        sh = 0;
+      }
+      p.tap_off[r * S + s] = strip * p.cbc * p.RA_p + p.d_before + sh;
+      if (getenv("QBN_P4_ALIGN")) p.tap_off[r * S + s] &= ~7;      // timing experiment only (wrong results): 128-byte aligned operand starts
+    }
+  p.a_bytes = (uint32_t)p.n_strips * p.cbc * p.RA_p * 16;
+  p.bt_bytes = (uint32_t)p.cbc * p.n_pad * 16;
+  p.w_sample_floats = (long long)p.n_cb * p.taps * p.bt_bytes / 4;
+  p.flags = flags; p.w_shared = w_shared;
+  p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  p.mg_plane = (uint32_t)(0x100000000ull / (uint64_t)(Hp * Wp));
+  p.mg_wp = (uint32_t)(0x100000000ull / (uint64_t)Wp);
+  p.res_plane = p.strip_rows;
+  p.out_plane = p.strip_rows;
+  if (flags & QBN_FLAG_OUT_PHASE_SPLIT) {
+    const int H = Hp - 2 * p.bh, W = Wp - 2 * p.bw;
+    QBN_CHECK_ARG((H % 2 == 0) && (W % 2 == 0), "phase-split output needs even H, W");
+    p.out_split = 1;
+    p.Hp2 = H / 2 + 2; p.Wp2 = W / 2 + 2;
+    p.q2_total = (long long)n_samples * B * p.Hp2 * p.Wp2;
+    p.out_plane = 4 * p.q2_total;
+  }
+  // ---- shared memory / occupancy policy ----
+  const size_t b_all = (size_t)p.bt_bytes * p.n_cb * p.taps;
+  const size_t fixed = 2 * 256 * 4 + 16 + 8 * 64;
+  const size_t cap = 225 * 1024;
+  int want_occ;
+  size_t smem;
+  const char* e_occ = getenv("QBN_P4_OCC");
+  if (b_all <= 100 * 1024 && b_all < (1u << 20)) {
+    p.b_res = 1; p.SB = 1; p.b_slot_bytes = (uint32_t)b_all;
+    want_occ = e_occ ? atoi(e_occ) : 3;
+    while (want_occ > 1 && 2 * (size_t)p.a_bytes + b_all + fixed > cap / want_occ - 1024) --want_occ;
+    p.SA = 2;
+    while (p.SA < 4 && (size_t)(p.SA + 1) * p.a_bytes + b_all + fixed <= cap / want_occ - 1024) ++p.SA;
+    smem = (size_t)p.SA * p.a_bytes + b_all + fixed;
+  } else {
+    p.b_res = 0; p.b_slot_bytes = p.bt_bytes;
+    want_occ = e_occ ? atoi(e_occ) : 2;
+    while (want_occ > 1 && 2 * (size_t)p.a_bytes + 3 * (size_t)p.bt_bytes + fixed > cap / want_occ - 1024) --want_occ;
+    p.SA = 2; p.SB = 2;
+    while (p.SB < 8 && (size_t)p.SA * p.a_bytes + (size_t)(p.SB + 1) * p.bt_bytes + fixed <= cap / want_occ - 1024) ++p.SB;
+    smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.bt_bytes + fixed;
+  }
+  if (getenv("QBN_P4_SA")) {
+    const int sa_new = atoi(getenv("QBN_P4_SA"));
+    smem += (size_t)(sa_new - p.SA) * p.a_bytes;
+    p.SA = sa_new;
+  }
+  if (smem > cap || p.SA < 1) {
+    qbn_set_error("qbn_conv_p4_fwd: tile does not fit shared memory (%zu bytes)", smem);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  {
+    int share = 512 / want_occ, c2 = 32;
+    while (c2 * 2 <= share) c2 <<= 1;
+    p.ACC = c2 / p.n_pad;
+    if (p.ACC > 4) p.ACC = 4;
+    if (p.ACC < 1) { p.ACC = 1; }
+    if (getenv("QBN_P4_ACC")) p.ACC = atoi(getenv("QBN_P4_ACC"));
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.ACC * p.n_pad) p.tmem_cols <<= 1;
+    if (p.tmem_cols > 512) { p.ACC = 512 / p.n_pad; p.tmem_cols = 512; }
+    while (p.tmem_cols * want_occ > 512) --want_occ;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  int occ = (int)((227 * 1024) / (smem + 1024));
+  if (occ > want_occ) occ = want_occ;
+  if (occ < 1) occ = 1;
+  int grid = qbn_sm_count() * occ;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (getenv("QBN_P4_VERBOSE"))
+    fprintf(stderr, "[p4] C=%d N=%d %dx%d k%d s%d: tiles=%d grid=%d occ=%d SA=%d SB=%d ACC=%d b_res=%d smem=%zu a_bytes=%u bt=%u tmem=%d\n", C, N, Hp,
+            Wp, R, stride, p.total_tiles, grid, occ, p.SA, p.SB, p.ACC, p.b_res, smem, p.a_bytes, p.bt_bytes, p.tmem_cols);
+  if (getenv("QBN_P4_PROF")) {
+    unsigned long long h[32] = {0};
+    cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
+    umma_conv_p4_kernel<1><<<grid, P4_THREADS, smem, st>>>(p);
+    QBN_CHECK_LAUNCH();
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_p4_prof, sizeof(h));
+    const unsigned long long t0 = (unsigned long long)(p.total_tiles / grid > 0 ? p.total_tiles / grid : 1);
+    fprintf(stderr, "[p4 prof] C=%d N=%d k%d s%d grid=%d tiles/CTA=%llu SA=%d SB=%d ACC=%d b_res=%d | epi: pre %llu wait_acc %llu tmem_ld %llu "
+            "compute+store %llu | mma: bres %llu wait_acc_empty %llu wait_a %llu wait_b %llu issue %llu commit %llu | prod: bres %llu "
+            "wait_a_empty %llu issueA %llu wait_b_empty %llu issueB %llu (cycles per tile)\n",
+            C, N, R, stride, grid, t0, p.SA, p.SB, p.ACC, p.b_res, h[0] / t0, h[1] / t0, h[2] / t0, h[3] / t0, h[8] / t0, h[9] / t0, h[10] / t0,
+            h[11] / t0, h[12] / t0, h[13] / t0, h[16] / t0, h[17] / t0, h[18] / t0, h[19] / t0, h[20] / t0);
+    return QBN_OK;
+  }
+  if (getenv("QBN_P4_DBG")) {
+    p.dbg = atoi(getenv("QBN_P4_DBG"));
+    umma_conv_p4_kernel<2><<<grid, P4_THREADS, smem, st>>>(p);
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
+  }
+  umma_conv_p4_kernel<0><<<grid, P4_THREADS, smem, st>>>(p);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

@@ -248,6 +248,109 @@ class MCEngine:
         self._reg_pad = {r: p for r, p in want.items() if r not in bad}
         return self._reg_pad
 
+    # ---- planar-C4 planning: which convs run on qbn_conv_p4_fwd and which registers are planar -------
+    def _p4_eligible(self, st):
+        """('s1', pad) / ('s2', None) if qbn_conv_p4_fwd takes this conv (include/qbn.h, planar-C4 path)."""
+        if not isinstance(st, _ConvStep) or st.is_linear or self.math_mode != QBN_MATH_TF32:
+            return None
+        m = st.mod
+        R, S_ = m.kernel_size
+        if m.in_channels % 8 != 0 or m.out_channels % 4 != 0 or m.out_channels > 256 or tuple(m.dilation) != (1, 1):
+            return None
+        if tuple(m.stride) == (1, 1) and R % 2 == 1 and S_ % 2 == 1 and R * S_ > 1 and tuple(m.padding) == ((R - 1) // 2, (S_ - 1) // 2):
+            return ("s1", ((R - 1) // 2, (S_ - 1) // 2))
+        if tuple(m.stride) == (2, 2) and ((R, S_) == (3, 3) and tuple(m.padding) == (1, 1) or (R, S_) == (1, 1) and tuple(m.padding) == (0, 0)):
+            return ("s2", None)
+        return None
+
+    def _plan_p4(self):
+        """Fixpoint: start from 'every eligible conv runs planar', drop convs / registers until every planar
+        register has a producer that can write its layout and only consumers that read it.
+        Returns (reg -> ('p4', border) | ('p4s', (1, 1)), set of conv-step ids on the planar kernel)."""
+        if hasattr(self, "_p4_plan"):
+            return self._p4_plan
+        convs = [st for st in self.steps if isinstance(st, _ConvStep)]
+        producers = {st.dst: st for st in self.steps}
+        on = {id(st): self._p4_eligible(st) for st in convs}
+        on = {k: v for k, v in on.items() if v is not None}
+        while True:
+            need = {}          # reg -> set of layouts demanded by planar convs
+            for st in convs:
+                e = on.get(id(st))
+                if e is None:
+                    continue
+                need.setdefault(st.src, set()).add(("p4", e[1]) if e[0] == "s1" else ("p4s", (1, 1)))
+                out_border = e[1] if e[0] == "s1" else (1, 1)
+                if st.residual is not None:
+                    need.setdefault(st.residual, set()).add(("p4", out_border))
+            layout = {}
+            for r, kinds in need.items():
+                if len(kinds) == 1:
+                    layout[r] = next(iter(kinds))
+            # a planar conv's output is planar too: its layout is what its consumers need (default: its own border)
+            for st in convs:
+                e = on.get(id(st))
+                if e is not None and st.dst not in layout and st.dst not in need:
+                    layout[st.dst] = ("p4", e[1] if e[0] == "s1" else (1, 1))
+            bad_regs = set(r for r, kinds in need.items() if len(kinds) != 1)
+            for r, lay in list(layout.items()):
+                pr = producers.get(r)
+                ok = isinstance(pr, _ConvStep) and not pr.is_linear and self.math_mode == QBN_MATH_TF32
+                if ok and id(pr) in on:
+                    e = on[id(pr)]
+                    own = e[1] if e[0] == "s1" else (1, 1)
+                    ok = lay[0] == "p4s" or lay[1] == own          # a planar conv writes its own geometry (or phase-split)
+                elif ok:
+                    ok = lay[0] == "p4" and pr.mod.out_channels % 4 == 0     # gather kernel: QBN_FLAG_OUT_P4, interior only
+                for st in self.steps:                                # every consumer must read this layout
+                    if isinstance(st, _PoolStep) and st.src == r:
+                        ok = ok and st.kind == "avg" and lay[0] == "p4"
+                    elif isinstance(st, _ConvStep):
+                        if st.src == r and id(st) not in on:
+                            ok = False
+                        if st.residual == r and id(st) not in on:
+                            ok = False
+                if r == getattr(self, "out_reg", None) or (self.regression and r in (self.head_mu.src,)):
+                    ok = False
+                if not ok:
+                    bad_regs.add(r)
+            drop = set()
+            for st in convs:
+                e = on.get(id(st))
+                if e is None:
+                    continue
+                regs_used = [st.src, st.dst] + ([st.residual] if st.residual is not None else [])
+                if any(r in bad_regs or r not in layout for r in regs_used):
+                    drop.add(id(st))
+                elif layout[st.dst][0] == "p4s":
+                    H_even = True   # checked at run time (needs even H, W)
+            if not drop and not bad_regs:
+                break
+            if not drop:          # registers went bad but no conv depends on them any more
+                for r in bad_regs:
+                    layout.pop(r, None)
+                break
+            for k in drop:
+                on.pop(k)
+        self._p4_plan = (layout, set(on))
+        return self._p4_plan
+
+    def _p4_weights(self, st, prep, info, stride):
+        """mu / sigma blocked once per call for the planar kernel (they are shared by all samples)."""
+        e = prep[id(st)]
+        key = ("p4w", stride)
+        if key not in e:
+            N, C, R, S_ = info["wshape"]
+            e[key] = (ops.p4_block_weights(info["mu"], N, C, R * S_, stride)[0], ops.p4_block_weights(info["sigma"], N, C, R * S_, stride)[0])
+        return e[key]
+
+    def _p4_buffer(self, key, n_img, C, Hp, Wp, border, phases, device, zero):
+        cache = self.__dict__.setdefault("_bufs", {})
+        k = (key, n_img, C, Hp, Wp, phases)
+        if k not in cache:
+            cache[k] = ops.P4Map.empty(n_img, C, Hp, Wp, border, phases, device, zero=zero)
+        return cache[k]
+
     def _buffer(self, key, shape, device, zero):
         """Output buffers are cached per (step, chunk size): stable pointers, no allocator churn, and the
         zero border of a zero-bordered map is written only once."""
@@ -262,6 +365,9 @@ class MCEngine:
     def _run_chunk(self, x, n, sample0, prep, injected):
         """Advance samples [sample0, sample0+n) through every step.  Returns the head output(s)."""
         reg_pad = self._plan_layout()
+        p4_layout, p4_convs = self._plan_p4()
+        if p4_convs:
+            reg_pad = {r: v for r, v in reg_pad.items() if r not in p4_layout}
         regs = {0: x}
         shared = {0: True}
         ready = {0: False}   # register holds TF32-exact values (written by a TF32 epilogue with OUT_ROUND_TF32)
@@ -271,7 +377,10 @@ class MCEngine:
             src = regs[st.src]
             spad = reg_pad.get(st.src, (0, 0)) if st.src in reg_pad else (0, 0)
             if isinstance(st, _PoolStep):
-                if st.kind == "max":
+                if isinstance(src, ops.P4Map):
+                    bh, bw = src.border
+                    regs[st.dst] = ops.avgpool_p4(src, float((src.Hp - 2 * bh) * (src.Wp - 2 * bw))).reshape(src.n_img, src.C, 1, 1)
+                elif st.kind == "max":
                     regs[st.dst] = ops.maxpool2x2(src)
                 else:
                     interior = (src.shape[2] - 2 * spad[0]) * (src.shape[3] - 2 * spad[1])
@@ -279,6 +388,12 @@ class MCEngine:
                 shared[st.dst] = shared[st.src]
                 ready[st.dst] = ready[st.src] and st.kind == "max"   # max of TF32-exact values is TF32-exact
                 self.launches += 1
+                continue
+            if id(st) in p4_convs:
+                regs[st.dst] = self._run_p4_conv(st, si, src, regs, n, sample0, prep, injected, p4_layout, seed)
+                self.launches += 2
+                shared[st.dst] = False
+                ready[st.dst] = True
                 continue
             # geometry of this conv on the UNPADDED map
             if src.dim() == 2:
@@ -310,6 +425,22 @@ class MCEngine:
                 res = res.repeat(n, 1, 1, 1).contiguous(memory_format=ops.CL)   # only if a block reads the raw input
             dpad = reg_pad.get(st.dst, (0, 0))
             flags = ops.QBN_FLAG_OUT_ROUND_TF32 if tf32 else 0
+            if st.dst in p4_layout:
+                # gather kernel writing the planar-C4 layout directly (first layer: shared input, stacked samples)
+                border = p4_layout[st.dst][1]
+                d = ops.make_desc(nb, src.shape[2], src.shape[3], C, N, R, S_, info["stride"], info["pad"], info["dil"])
+                d.out_pad_h, d.out_pad_w = border
+                outp = self._p4_buffer(("v1p4", si), n * nb, N, d.Ho + 2 * border[0], d.Wo + 2 * border[1], border, 1, src.device, zero=True)
+                if tf32 and ready[st.src] and not info["cpad"]:
+                    flags |= ops.QBN_FLAG_A_TF32_READY
+                ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], None, st.relu, None, 1.0, mode, outp.buf,
+                                 flags | ops.QBN_FLAG_OUT_P4)
+                assert res is None
+                self.launches += 2
+                regs[st.dst] = outp
+                shared[st.dst] = False
+                ready[st.dst] = True
+                continue
             s1 = self._s1_eligible(st)
             if s1 is not None and tf32 and spad == s1 and dpad == s1 and ready[st.src] and not shared[st.src] and not info["cpad"]:
                 out = self._buffer(("s1", si, n), (src.shape[0], N, src.shape[2], src.shape[3]), src.device, zero=False)
@@ -335,6 +466,40 @@ class MCEngine:
             return regs[self.head_mu.dst].reshape(n, B), regs[self.head_lv.dst].reshape(n, B)
         logits = regs[self.out_reg]
         return logits.reshape(n, B, -1)
+
+    def _run_p4_conv(self, st, si, src, regs, n, sample0, prep, injected, p4_layout, seed):
+        """One BBB conv on the planar-C4 kernel: blocked sampling launch + qbn_conv_p4_fwd."""
+        assert isinstance(src, ops.P4Map), "planar conv fed by a non-planar register (planner bug)"
+        m = st.mod
+        stride = m.stride[0]
+        if src.phases == 4:
+            H0, W0 = 2 * (src.Hp - 2), 2 * (src.Wp - 2)
+        else:
+            H0, W0 = src.Hp - 2 * src.border[0], src.Wp - 2 * src.border[1]
+        info = self._packed(st, prep, torch.empty((0, src.C, H0, W0), device="meta"))
+        N, C, R, S_ = info["wshape"]
+        mu_b, sg_b = self._p4_weights(st, prep, info, stride)
+        eps = None
+        if injected is not None:
+            eps = torch.stack([ops.pack_ohwi(injected[s][st.ref_idx].reshape(info["orig_shape"]).float()) for s in range(n)]).contiguous()
+        w = ops.sample_weights_blocked(mu_b, sg_b, N, C, R * S_, n, eps, seed, m._qbn_layer_id, sample0, True, None, stride)
+        e = prep[id(st)]
+        lay = p4_layout[st.dst]
+        split = lay[0] == "p4s"
+        if stride == 2:
+            Hp_o, Wp_o, border = src.Hp, src.Wp, (1, 1)
+        else:
+            Hp_o, Wp_o, border = src.Hp, src.Wp, src.border
+        if split:
+            Ho, Wo = Hp_o - 2 * border[0], Wp_o - 2 * border[1]
+            if Ho % 2 or Wo % 2:
+                raise RuntimeError("phase-split output needs even H, W")
+            out = self._p4_buffer(("p4", si), src.n_img, N, Ho // 2 + 2, Wo // 2 + 2, (1, 1), 4, src.buf.device, zero=True)
+        else:
+            out = self._p4_buffer(("p4", si), src.n_img, N, Hp_o, Wp_o, border, 1, src.buf.device, zero=False)
+        res = regs[st.residual] if st.residual is not None else None
+        ops.conv_p4_forward(src, w, n, N, R, S_, stride, e["scale"], e["shift"], res, st.relu, ops.QBN_FLAG_OUT_ROUND_TF32, False, out, split)
+        return out
 
     @torch.no_grad()
     def predict_sum(self, x, samples, sample0=0, injected=None):

@@ -9,8 +9,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, I8SampleParams, QBN_FLAG_A_TF32_READY, QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU,  # noqa: F401
-                   QBN_MATH_FP32, QBN_MATH_TF32)
+from ._lib import (ConvDesc, I8SampleParams, QBN_FLAG_A_TF32_READY, QBN_FLAG_OUT_P4, QBN_FLAG_OUT_PHASE_SPLIT,  # noqa: F401
+                   QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU, QBN_MATH_FP32, QBN_MATH_TF32)
 
 CL = torch.channels_last
 
@@ -466,4 +466,107 @@ def nchw_to_nhwc(x):
     xc = _f32(x).contiguous()
     out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device, memory_format=CL)
     _lib.call("qbn_nchw_to_nhwc", _ptr(xc), B, C, H * W, _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# planar-C4 path (include/qbn.h "planar-C4 path", csrc/p4_layout.cuh)
+# ------------------------------------------------------------------------------------------------
+class P4Map:
+    """A batch of zero-bordered maps in the planar-C4 layout: buf [C/4][phases * n_img*Hp*Wp][4].
+    phases == 4: phase-split storage of a (2*(Hp-2)) x (2*(Wp-2)) map for a stride-2 consumer."""
+    __slots__ = ("buf", "n_img", "C", "Hp", "Wp", "border", "phases")
+
+    def __init__(self, buf, n_img, C, Hp, Wp, border, phases=1):
+        self.buf, self.n_img, self.C, self.Hp, self.Wp, self.border, self.phases = buf, n_img, C, Hp, Wp, border, phases
+
+    @staticmethod
+    def empty(n_img, C, Hp, Wp, border, phases=1, device="cuda", zero=False):
+        shape = (C // 4, phases * n_img * Hp * Wp, 4)
+        buf = torch.zeros(shape, dtype=torch.float32, device=device) if zero else torch.empty(shape, dtype=torch.float32, device=device)
+        return P4Map(buf, n_img, C, Hp, Wp, border, phases)
+
+    @staticmethod
+    def from_nchw(x, border, phase_split=False):
+        """Layout conversion with torch ops (tests / entry only): x [n_img, C, H, W] unpadded."""
+        n, C, H, W = x.shape
+        xh = x.permute(0, 2, 3, 1)
+        if phase_split:
+            parts = [torch.nn.functional.pad(xh[:, a::2, b::2, :], (0, 0, 1, 1, 1, 1)) for a in (0, 1) for b in (0, 1)]
+            Hp, Wp = H // 2 + 2, W // 2 + 2
+            rows = torch.stack(parts).reshape(4 * n * Hp * Wp, C)
+            border, phases = (1, 1), 4
+        else:
+            bh, bw = border
+            Hp, Wp = H + 2 * bh, W + 2 * bw
+            rows = torch.nn.functional.pad(xh, (0, 0, bw, bw, bh, bh)).reshape(n * Hp * Wp, C)
+            phases = 1
+        buf = rows.reshape(-1, C // 4, 4).permute(1, 0, 2).contiguous()
+        return P4Map(buf, n, C, Hp, Wp, tuple(border), phases)
+
+    def to_nchw(self, keep_border=False):
+        rows = self.buf.permute(1, 0, 2).reshape(self.phases, self.n_img, self.Hp, self.Wp, self.C)
+        if self.phases == 4:
+            H, W = 2 * (self.Hp - 2), 2 * (self.Wp - 2)
+            out = torch.empty((self.n_img, H, W, self.C), dtype=self.buf.dtype, device=self.buf.device)
+            k = 0
+            for a in (0, 1):
+                for b in (0, 1):
+                    out[:, a::2, b::2, :] = rows[k][:, 1:-1, 1:-1, :]
+                    k += 1
+            return out.permute(0, 3, 1, 2)
+        m = rows[0]
+        if not keep_border:
+            bh, bw = self.border
+            m = m[:, bh:self.Hp - bh, bw:self.Wp - bw, :]
+        return m.permute(0, 3, 1, 2)
+
+
+def p4_weight_floats(C, N, R, S, stride=1):
+    n = ctypes.c_longlong(0)
+    _lib.call("qbn_p4_weight_floats", C, N, R, S, stride, ctypes.byref(n))
+    return int(n.value)
+
+
+def p4_block_weights(w_ohwi, N, C, taps, stride=1):
+    """[n_mats, N*taps*C] packed OHWI -> blocked [n_mats, p4_weight_floats] (the blocking depends on the stride)."""
+    w_ohwi = w_ohwi.reshape(-1, N * taps * C).contiguous()
+    n_mats = w_ohwi.shape[0]
+    R = taps
+    out = torch.empty((n_mats, p4_weight_floats(C, N, R, 1, stride)), dtype=torch.float32, device=w_ohwi.device)
+    _lib.call("qbn_p4_block_weights", _ptr(w_ohwi), n_mats, N, C, taps, stride, _ptr(out), _stream())
+    return out
+
+
+def sample_weights_blocked(mu_b, sigma_b, N, C, taps, n_samples=1, eps=None, seed=0, layer_id=0, sample0=0, round_tf32=True, out=None, stride=1):
+    if out is None:
+        out = torch.empty((n_samples, mu_b.numel()), dtype=torch.float32, device=mu_b.device)
+    _lib.call("qbn_sample_weights_blocked", _ptr(mu_b), _ptr(sigma_b), N, C, taps, stride, n_samples, _ptr(eps), seed, layer_id, sample0, _ptr(out),
+              int(round_tf32), _stream())
+    return out
+
+
+def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, residual=None, relu=False, flags=0, w_shared=False,
+                    out=None, phase_split_out=False):
+    """qbn_conv_p4_fwd.  x: P4Map (phase-split when stride == 2); w: blocked sampled weights [n_samples, ...];
+    residual: P4Map with the output geometry.  Returns a P4Map."""
+    B = x.n_img // n_samples
+    if stride == 2 and x.phases != 4:
+        raise _lib.QbnError("stride-2 planar conv needs a phase-split input")
+    border = ((R - 1) // 2, (S - 1) // 2) if stride == 1 else (1, 1)
+    if out is None:
+        if phase_split_out:
+            H, W = x.Hp - 2 * border[0], x.Wp - 2 * border[1]
+            out = P4Map.empty(x.n_img, N, H // 2 + 2, W // 2 + 2, (1, 1), 4, x.buf.device, zero=True)
+        else:
+            out = P4Map.empty(x.n_img, N, x.Hp, x.Wp, border, 1, x.buf.device)
+    fl = int(bool(relu)) | int(flags) | (QBN_FLAG_OUT_PHASE_SPLIT if phase_split_out else 0)
+    _lib.call("qbn_conv_p4_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, stride, _ptr(x.buf), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
+              _ptr(residual.buf if residual is not None else None), fl, _ptr(out.buf), _stream())
+    return out
+
+
+def avgpool_p4(x, divisor):
+    out = torch.empty((x.n_img, x.C), dtype=torch.float32, device=x.buf.device)
+    _lib.call("qbn_avgpool_p4", _ptr(x.buf), x.n_img, x.Hp * x.Wp, x.C, float(divisor), _ptr(out), _stream())
     return out

@@ -14,3 +14,15 @@ for n_cols in (32, 64, 128):
         o = out.cpu().tolist()
         print("N=%d reps=%d: " % (n_cols, reps) + "; ".join("%s=%d" % (n, v) for n, v in zip(names, o)))
         print("   4 warps issuing concurrently (issue, issue+complete per MMA): " + ", ".join("w%d=(%d,%d)" % (w, o[12 + w] >> 32, o[12 + w] & 0xffffffff) for w in range(4)))
+
+print("multi-CTA / multi-issuer overlap (cycles per MMA seen by each issuer of CTA 0: issue, issue+complete)")
+for n_cols in (32, 64, 128):
+    for (k, w) in [(1, 1), (1, 2), (1, 3), (1, 4), (2, 1), (3, 1), (4, 1), (2, 2)]:
+        if w * n_cols * k > 512:
+            continue
+        out = torch.zeros(4, dtype=torch.int64, device="cuda")
+        _lib.call("qbn_ubench_tcgen05_multi", ctypes.c_void_p(out.data_ptr()), n_cols, 64, k, w, ops._stream())
+        torch.cuda.synchronize()
+        o = out.cpu().tolist()
+        per = [(v >> 32, v & 0xffffffff) for v in o[:w]]
+        print("N=%d  %d CTA/SM x %d issuer warps: " % (n_cols, k, w) + ", ".join("(%d,%d)" % p for p in per) + "   -> SM-wide %.0f cycles/MMA" % (per[0][1] / (k * w)))

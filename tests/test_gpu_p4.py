@@ -1,0 +1,180 @@
+"""GPU (pytest -m gpu): the planar-C4 path — blocked weight sampler, qbn_conv_p4_fwd (stride 1, stride 2 on
+phase-split input, phase-split output), planar output of the gather kernel, planar pooling — against the
+fp32 CUDA-core convolution on the same TF32-exact operands (rtol 1e-3, north_star's TF32 tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, ref, rtol, atol_rel):
+    got, ref = got.detach().float().cpu().numpy(), ref.detach().float().cpu().numpy()
+    atol = atol_rel * max(1e-30, float(np.abs(ref).max()))
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    import __graft_entry__ as g
+    g.build()
+
+
+def _tf32_round_(t):
+    ti = t.view(torch.int32)
+    ti.add_(0x1000).bitwise_and_(~0x1FFF)
+    return t
+
+
+def _rand_weights(g, S, N, k, C):
+    return _tf32_round_((torch.randn(S, N, k, k, C, generator=g) / (C * k * k) ** 0.5).cuda()).reshape(S, -1).contiguous()
+
+
+@pytest.mark.parametrize("shape", [(24, 24, 9, 1), (48, 96, 9, 2), (96, 96, 9, 1), (192, 192, 9, 1), (72, 20, 9, 1), (24, 48, 1, 2), (8, 10, 25, 1),
+                                   (96, 192, 9, 2)])
+def test_p4_blocked_sampler_matches_canonical(shape):
+    """qbn_sample_weights_blocked == qbn_p4_block_weights(qbn_sample_weights): same Philox counters, same roundings."""
+    from qbn_b200 import ops
+    C, N, taps, stride = shape
+    g = torch.Generator().manual_seed(3)
+    mu = torch.randn(N * taps * C, generator=g).cuda()
+    sg = torch.rand(N * taps * C, generator=g).cuda()
+    S = 3
+    canon = ops.sample_weights(mu, sg, S, None, 1234, 7, 5, round_tf32=True)
+    want = ops.p4_block_weights(canon, N, C, taps, stride)
+    mu_b, sg_b = ops.p4_block_weights(mu, N, C, taps, stride)[0], ops.p4_block_weights(sg, N, C, taps, stride)[0]
+    got = ops.sample_weights_blocked(mu_b, sg_b, N, C, taps, S, None, 1234, 7, 5, True, stride=stride)
+    assert torch.equal(got, want)
+    assert got.shape[1] == ops.p4_weight_floats(C, N, taps, 1, stride)
+    eps = torch.randn(S, N * taps * C, generator=g).cuda()
+    canon = ops.sample_weights(mu, sg, S, eps, 0, 0, 0, round_tf32=False)
+    got = ops.sample_weights_blocked(mu_b, sg_b, N, C, taps, S, eps, 0, 0, 0, False, stride=stride)
+    assert torch.equal(got, ops.p4_block_weights(canon, N, C, taps, stride))
+    # every canonical element appears exactly once, the rest is zero padding
+    assert float(got.abs().sum(dtype=torch.float64)) == pytest.approx(float(canon.abs().sum(dtype=torch.float64)), rel=1e-6)
+
+
+P4_S1 = [
+    # B, C, H, W, N, k
+    (2, 24, 32, 32, 24, 3), (2, 48, 16, 16, 48, 3), (3, 96, 8, 8, 96, 3), (5, 192, 4, 4, 192, 3),
+    (2, 8, 9, 7, 12, 3), (2, 40, 6, 6, 16, 5), (2, 72, 6, 5, 24, 3), (1, 64, 12, 12, 256, 3),
+]
+
+
+@pytest.mark.parametrize("shape", P4_S1)
+def test_p4_conv_stride1(shape):
+    from qbn_b200 import ops
+    B, C, H, W, N, k = shape
+    pad = (k - 1) // 2
+    g = torch.Generator().manual_seed(11 + C + N)
+    S = 3
+    x = _tf32_round_(torch.randn(S * B, C, H, W, generator=g).cuda())
+    w = _rand_weights(g, S, N, k, C)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    res = torch.randn(S * B, N, H, W, generator=g).cuda()
+    d = ops.make_desc(B, H, W, C, N, k, k, 1, pad, 1)
+    ref = ops.conv_forward(ops.nhwc(x), w, d, S, False, False, scale, shift, ops.nhwc(res), True, None, 1.0, ops.QBN_MATH_FP32)
+    xb = ops.P4Map.from_nchw(x, (pad, pad))
+    rb = ops.P4Map.from_nchw(res, (pad, pad))
+    wb = ops.p4_block_weights(w, N, C, k * k)
+    got = ops.conv_p4_forward(xb, wb, S, N, k, k, 1, scale, shift, rb, True, ops.QBN_FLAG_OUT_ROUND_TF32)
+    close(got.to_nchw(), ref, 1e-3, 1e-3)
+    full = got.to_nchw(keep_border=True).clone()
+    full[:, :, pad:pad + H, pad:pad + W] = 0
+    assert float(full.abs().max()) == 0.0                                   # zero border written
+    assert int((got.buf.view(torch.int32) & 0x1FFF).abs().max()) == 0        # TF32-exact outputs
+    # chained without re-padding
+    w2 = _rand_weights(g, S, N, k, N) if N % 8 == 0 else None
+    if w2 is not None:
+        got2 = ops.conv_p4_forward(got, ops.p4_block_weights(w2, N, N, k * k), S, N, k, k, 1)
+        d2 = ops.make_desc(B, H, W, N, N, k, k, 1, pad, 1)
+        ref2 = ops.conv_forward(ops.nhwc(got.to_nchw().contiguous()), w2, d2, S, False, False, None, None, None, False, None, 1.0,
+                                ops.QBN_MATH_FP32)
+        close(got2.to_nchw(), ref2, 1e-3, 1e-3)
+    # phase-split output (for a stride-2 consumer) holds the same values
+    if H % 2 == 0 and W % 2 == 0 and k == 3:
+        ps = ops.conv_p4_forward(xb, wb, S, N, k, k, 1, scale, shift, rb, True, ops.QBN_FLAG_OUT_ROUND_TF32, phase_split_out=True)
+        assert ps.phases == 4
+        assert torch.equal(ps.to_nchw(), got.to_nchw())
+        rows = ps.buf.permute(1, 0, 2).reshape(4, S * B, ps.Hp, ps.Wp, N).clone()
+        rows[:, :, 1:-1, 1:-1, :] = 0
+        assert float(rows.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 32, 48, 3), (2, 24, 32, 48, 1), (3, 48, 16, 96, 3), (3, 48, 16, 96, 1), (2, 96, 8, 192, 3),
+                                   (2, 96, 8, 192, 1), (1, 8, 6, 12, 3)])
+def test_p4_conv_stride2_phase_split(shape):
+    from qbn_b200 import ops
+    B, C, H, N, k = shape
+    pad = (k - 1) // 2
+    g = torch.Generator().manual_seed(5 + C + k)
+    S = 2
+    x = _tf32_round_(torch.randn(S * B, C, H, H, generator=g).cuda())
+    w = _rand_weights(g, S, N, k, C)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    d = ops.make_desc(B, H, H, C, N, k, k, 2, pad, 1)
+    ref = ops.conv_forward(ops.nhwc(x), w, d, S, False, False, scale, shift, None, False, None, 1.0, ops.QBN_MATH_FP32)
+    xs = ops.P4Map.from_nchw(x, None, phase_split=True)
+    assert torch.equal(xs.to_nchw(), x)
+    got = ops.conv_p4_forward(xs, ops.p4_block_weights(w, N, C, k * k, 2), S, N, k, k, 2, scale, shift, None, False, ops.QBN_FLAG_OUT_ROUND_TF32)
+    assert (got.Hp, got.Wp) == (H // 2 + 2, H // 2 + 2)
+    close(got.to_nchw(), ref, 1e-3, 1e-3)
+    full = got.to_nchw(keep_border=True).clone()
+    full[:, :, 1:-1, 1:-1] = 0
+    assert float(full.abs().max()) == 0.0
+
+
+def test_v1_planar_output_and_pool():
+    """The gather kernel (first layer: shared input, sample-stacked weights) writing planar C4 directly,
+    and the planar global average pool."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    B, S, N = 3, 4, 24
+    x = torch.randn(B, 4, 16, 16, generator=g).cuda()
+    w = _rand_weights(g, S, N, 3, 4)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    d = ops.make_desc(B, 16, 16, 4, N, 3, 3, 1, 1, 1)
+    ref = ops.conv_forward(ops.nhwc(x), w, d, S, True, False, scale, shift, None, True, None, 1.0, ops.QBN_MATH_TF32)
+    d.out_pad_h = d.out_pad_w = 1
+    out = ops.P4Map.empty(S * B, N, 18, 18, (1, 1), 1, "cuda", zero=True)
+    ops.conv_forward(ops.nhwc(x), w, d, S, True, False, scale, shift, None, True, None, 1.0, ops.QBN_MATH_TF32, out.buf, ops.QBN_FLAG_OUT_P4)
+    assert torch.equal(out.to_nchw(), ref.reshape(S * B, N, 16, 16))
+    # per-sample (not stacked) launch with a planar residual
+    res = ops.P4Map.from_nchw(torch.randn(S * B, N, 16, 16, generator=g).cuda(), (1, 1))
+    xs = _tf32_round_(torch.randn(S * B, 8, 16, 16, generator=g).cuda())
+    w8 = _rand_weights(g, S, N, 3, 8)
+    d8 = ops.make_desc(B, 16, 16, 8, N, 3, 3, 1, 1, 1)
+    ref = ops.conv_forward(ops.nhwc(xs), w8, d8, S, False, False, scale, shift, ops.nhwc(res.to_nchw().contiguous()), True, None, 1.0,
+                           ops.QBN_MATH_TF32)
+    d8.out_pad_h = d8.out_pad_w = 1
+    out2 = ops.P4Map.empty(S * B, N, 18, 18, (1, 1), 1, "cuda", zero=True)
+    ops.conv_forward(ops.nhwc(xs), w8, d8, S, False, False, scale, shift, res.buf, True, None, 1.0, ops.QBN_MATH_TF32, out2.buf,
+                     ops.QBN_FLAG_OUT_P4)
+    assert torch.equal(out2.to_nchw(), ref)
+    pooled = ops.avgpool_p4(out2, 16 * 16)
+    close(pooled, ref.mean(dim=(2, 3)), 1e-5, 1e-6)
+
+
+def test_p4_conv_full_size_linearity():
+    """BASELINE-size tile counts (B=256, 10 samples, 23 120 tiles): conv(x, w1 + w2) == conv(x, w1) + conv(x, w2) up to
+    TF32 operand rounding, and a second run is bit-identical (no race in the persistent pipeline)."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    S, B, C, H = 10, 256, 24, 32
+    x = _tf32_round_(torch.randn(S * B, C, H, H, generator=g).cuda())
+    xb = ops.P4Map.from_nchw(x, (1, 1))
+    del x
+    w1 = _rand_weights(g, S, C, 3, C)
+    w2 = _rand_weights(g, S, C, 3, C)
+    w12 = _tf32_round_((w1 + w2).clone())
+    blk = lambda w: ops.p4_block_weights(w, C, C, 9)
+    a = ops.conv_p4_forward(xb, blk(w1), S, C, 3, 3, 1).buf
+    b = ops.conv_p4_forward(xb, blk(w2), S, C, 3, 3, 1).buf
+    c = ops.conv_p4_forward(xb, blk(w12), S, C, 3, 3, 1).buf
+    c2 = ops.conv_p4_forward(xb, blk(w12), S, C, 3, 3, 1).buf
+    assert torch.equal(c, c2)
+    err = float((a + b - c).abs().max()) / float(c.abs().max())
+    assert err < 2e-3, err
