@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 
 B, S, K_CLASSES = 256, 100, 10
 FLOP_PER_SAMPLE_IMAGE = 1.5704e8          # SURVEY.md §8d, one contraction per layer
+# mean dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one 10-sample chunk (ncu --set full)
+P4_DRAM_BYTES_PER_LAUNCH = None
+P4_TRAFFIC_SOURCE = "not captured yet for the planar-C4 kernel"
 ACT_BYTES_PER_SAMPLE_IMAGE = 1.929e6      # fp32 NHWC activations in+out of the 21 stochastic layers
 
 
@@ -261,28 +264,46 @@ def main():
             H, W = x.shape[2] - (R - 1), x.shape[3] - (S_ - 1)       # algorithmic flops: interior pixels only
             evs.append((e0, e1, 2.0 * x.shape[0] * H * W * N * R * S_ * x.shape[1], 1))
             return out
-        mc.ops.conv_forward, mc.ops.conv_s1_forward = timed_conv, timed_s1
+        orig_p4 = mc.ops.conv_p4_forward
+
+        def timed_p4(x, w, n, N, R, S_, stride=1, *a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_p4(x, w, n, N, R, S_, stride, *a, **k)
+            e1.record()
+            bh, bw = ((R - 1) // 2, (S_ - 1) // 2) if stride == 1 else (1, 1)
+            H, W = x.Hp - 2 * bh, x.Wp - 2 * bw                     # output pixels (the map geometry is the output's)
+            evs.append((e0, e1, 2.0 * x.n_img * H * W * N * R * S_ * x.C, 2))
+            return out
+        mc.ops.conv_forward, mc.ops.conv_s1_forward, mc.ops.conv_p4_forward = timed_conv, timed_s1, timed_p4
         flush.fill_(1.0)
         torch.cuda.synchronize()
+        engine.use_graph = False                      # per-launch events need the eager launch sequence (the timed loop replays a CUDA graph)
         engine.predict_sum(x_dev, count, sample0=start)
+        engine.use_graph = True
         torch.cuda.synchronize()
-        mc.ops.conv_forward, mc.ops.conv_s1_forward = orig, orig_s1
-        um = [(a.elapsed_time(b), f) for a, b, f, m in evs if m == 1]
+        mc.ops.conv_forward, mc.ops.conv_s1_forward, mc.ops.conv_p4_forward = orig, orig_s1, orig_p4
+        um = [(a.elapsed_time(b), f) for a, b, f, m in evs if m >= 1]
+        n_p4 = sum(1 for e in evs if e[3] == 2)
         if um:
             t_ms = sum(t for t, _ in um)
             fl = sum(f for _, f in um)
             ach = fl / (t_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"] / 2.0
             alg_bytes = ACT_BYTES_PER_SAMPLE_IMAGE * B * count
-            roof = {"kernel": "umma_conv_s1_kernel + umma_conv_kernel<EVAL> (tcgen05 kind::tf32)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": 290.05e6, "launches": len(um), "avg_launch_ms": t_ms / len(um),
-                    "peak_source": "1/2 x sustained bf16 of %s (TF32 peak not in MEASURED_PEAKS.json)" % peaks["source"],
-                    "traffic_source": "dram read+write bytes per launch, mean over the 21 conv launches of one 10-sample chunk, ncu --set full (profiles/r01_conv_kernels_ncu_full.csv)",
+            # with fp32 activations the eval path's arithmetic intensity (81 flop/B) is below the TF32 ridge
+            # (~105 flop/B at the measured peaks), so HBM is the binding roofline; the tensor-pipe view is reported beside it.
+            hbm = alg_bytes / (t_ms * 1e-3) / 1e9
+            roof = {"kernel": "umma_conv_p4_kernel (%d launches) + umma_conv_kernel<EVAL> (%d) — tcgen05 kind::tf32" % (n_p4, len(um) - n_p4),
+                    "bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
+                    "traffic": P4_DRAM_BYTES_PER_LAUNCH, "launches": len(um), "avg_launch_ms": t_ms / len(um),
+                    "peak_source": "hbm_gbs of %s" % peaks["source"],
+                    "traffic_source": P4_TRAFFIC_SOURCE,
                     "algorithmic_bytes_per_launch": alg_bytes / len(um),
-                    "hbm_view": {"achieved_gbs": alg_bytes / (t_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                                 "frac": alg_bytes / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                 "note": "algorithmic activation bytes (1.929 MB/sample-image, fp32 NHWC) over the same launches; "
-                                         "layers 0-1 are HBM-bound at fp32 activations (SURVEY 8d)"},
+                    "algorithmic_bytes_note": "1.929 MB per sample-image (SURVEY 8d: activations in + out of the 21 stochastic layers, fp32) x the "
+                                              "sample-images of the step / conv launches",
+                    "tensor_view": {"achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak,
+                                    "peak_source": "1/2 x sustained bf16 of %s (TF32 peak not in MEASURED_PEAKS.json)" % peaks["source"]},
                     "share_of_step": t_ms / (total_ms / args.steps)}
     if rank == 0:
         value = B * args.steps / (total_ms * 1e-3)

@@ -154,6 +154,13 @@ int qbn_p4_block_weights(const float* w_ohwi /* [n_mats][N][taps][C] */, int n_m
 int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_b, int N, int C, int taps, int stride, int n_samples,
                                const float* eps /* nullable, canonical [n_samples][N][taps][C] */, uint64_t seed,
                                uint32_t layer_id, uint32_t sample0, float* w, int round_tf32, void* stream);
+/* the same for several layers in ONE launch: jobs_dev = device array of qbn_p4_sample_job (blockIdx.z = job) */
+typedef struct qbn_p4_sample_job {
+  const float* mu_b; const float* sigma_b; const float* eps /* nullable */; float* w;
+  int32_t N, C, taps, stride; uint32_t layer_id; int32_t pad_;
+} qbn_p4_sample_job;
+int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
+                                     uint64_t seed, uint32_t sample0, int round_tf32, void* stream);
 int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
                     const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
                     int flags, float* out, void* stream);

@@ -22,6 +22,11 @@ class ConvDesc(Structure):
                                         "dil_h", "dil_w", "Ho", "Wo", "out_pad_h", "out_pad_w")]
 
 
+class P4SampleJob(Structure):
+    _fields_ = [("mu_b", c_void_p), ("sigma_b", c_void_p), ("eps", c_void_p), ("w", c_void_p), ("N", c_int32), ("C", c_int32),
+                ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("pad_", c_int32)]
+
+
 class I8SampleParams(Structure):
     _fields_ = [("s_mu", c_float), ("z_mu", c_int32), ("s_sigma", c_float), ("z_sigma", c_int32),
                 ("s_eps", c_float), ("z_eps", c_int32), ("s_mul", c_float), ("z_mul", c_int32),
@@ -70,6 +75,7 @@ _SIGNATURES = {
     "qbn_p4_weight_floats": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_longlong)]),
     "qbn_p4_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "qbn_sample_weights_blocked": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, c_uint64, c_uint32, c_uint32, P, c_int, P]),
+    "qbn_sample_weights_blocked_multi": (c_int, [P, c_int, c_int64, c_int, c_uint64, c_uint32, c_int, P]),
     "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
     "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
 }

@@ -847,3 +847,53 @@ extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, floa
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
+
+// All planar layers of one Monte-Carlo chunk in ONE launch (21 launches -> 1): blockIdx.z = layer job.
+struct qbn_p4_sample_job_dev {
+  const float* mu_b; const float* sigma_b; const float* eps; float* w;
+  int N, C, taps, stride; uint32_t layer_id; int pad_;
+};
+__global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev* __restrict__ jobs, uint64_t seed, uint32_t sample0,
+                                                    int round_tf32) {
+  const qbn_p4_sample_job_dev jb = jobs[blockIdx.z];
+  P4Block g;
+  g.N = jb.N; g.C = jb.C; g.taps = jb.taps;
+  g.CB = qbn_p4_block_channels(jb.C, jb.stride, jb.taps);
+  g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(jb.N); g.K = jb.taps * jb.C;
+  g.total4 = (int64_t)(jb.C / g.CB) * jb.taps * g.cbc * g.n_pad;
+  const int s = blockIdx.y;
+  float4* ws = reinterpret_cast<float4*>(jb.w) + (int64_t)s * g.total4;
+  const float* es = jb.eps ? jb.eps + (int64_t)s * g.N * g.K : nullptr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = p4_canonical(g, i);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx >= 0) {
+      float z[4];
+      if (es) {
+        const float4 e = *reinterpret_cast<const float4*>(es + idx);
+        z[0] = e.x; z[1] = e.y; z[2] = e.z; z[3] = e.w;
+      } else {
+        philox_normal4(seed, jb.layer_id, sample0 + (uint32_t)s, (uint64_t)(idx >> 2), z);
+      }
+      const float4 m = reinterpret_cast<const float4*>(jb.mu_b)[i];
+      const float4 sg = reinterpret_cast<const float4*>(jb.sigma_b)[i];
+      o.x = __fadd_rn(m.x, __fmul_rn(z[0], sg.x));
+      o.y = __fadd_rn(m.y, __fmul_rn(z[1], sg.y));
+      o.z = __fadd_rn(m.z, __fmul_rn(z[2], sg.z));
+      o.w = __fadd_rn(m.w, __fmul_rn(z[3], sg.w));
+      if (round_tf32) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
+    }
+    ws[i] = o;
+  }
+}
+extern "C" int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
+                                                uint64_t seed, uint32_t sample0, int round_tf32, void* stream) {
+  QBN_CHECK_ARG(jobs_dev && n_jobs > 0 && n_jobs <= 65535 && n_samples > 0 && n_samples <= 65535 && max_floats_per_sample > 0, "args");
+  int64_t gx = (max_floats_per_sample / 4 + 1023) / 1024;      // up to four float4 per thread for the largest layer
+  if (gx < 1) gx = 1;
+  if (gx > 4096) gx = 4096;
+  sample_weights_blocked_multi_kernel<<<dim3((unsigned)gx, n_samples, n_jobs), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const qbn_p4_sample_job_dev*>(jobs_dev), seed, sample0, round_tf32);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

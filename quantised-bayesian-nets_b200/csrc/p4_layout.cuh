@@ -13,7 +13,7 @@
 
 // channels per block: whole C when small, else the largest of {32, 48, 40, 24, 16, 8} dividing C.
 // A stride-2 3x3 conv stages four phase strips per block, so its blocks are at most 24 channels.
-static inline int qbn_p4_block_channels(int C, int stride = 1, int taps = 9) {
+static __host__ __device__ inline int qbn_p4_block_channels(int C, int stride = 1, int taps = 9) {
   if (stride == 2 && taps > 1) {
     const int c2[3] = {24, 16, 8};
     for (int i = 0; i < 3; ++i)
@@ -26,4 +26,4 @@ static inline int qbn_p4_block_channels(int C, int stride = 1, int taps = 9) {
     if (C % cand[i] == 0) return cand[i];
   return 0;
 }
-static inline int qbn_p4_n_pad(int N) { return (N + 15) / 16 * 16; }
+static __host__ __device__ inline int qbn_p4_n_pad(int N) { return (N + 15) / 16 * 16; }

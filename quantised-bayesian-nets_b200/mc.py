@@ -47,8 +47,9 @@ class MCEngine:
     (LinearNetwork / ConvNetwork_LeNet / ConvNetwork_ResNet of models_bbb.py, or their qbn_b200.zoo
     mirrors).  predict() == `_evaluate_with_loader`'s inner loop for one batch."""
 
-    def __init__(self, model, math_mode="tf32", chunk=10):
+    def __init__(self, model, math_mode="tf32", chunk=10, use_graph=True):
         self.model = model
+        self.use_graph = bool(use_graph)
         self.math_mode = {"fp32": QBN_MATH_FP32, "tf32": QBN_MATH_TF32}[math_mode] if isinstance(math_mode, str) else math_mode
         self.chunk = int(chunk)
         self.steps = []
@@ -162,7 +163,7 @@ class MCEngine:
         """Pack (mu, sigma) for the geometry this step sees (depends on the input's H, W for the
         flatten->linear case, which runs as an HxW 'valid' convolution over the NHWC map)."""
         e = prep[id(st)]
-        key = ("packed", tuple(x.shape[1:]))
+        key = ("packed", tuple(x.shape[1:]) if st.is_linear else None)     # only flatten->linear depends on the map size
         if key in e:
             return e[key]
         m = st.mod
@@ -336,13 +337,50 @@ class MCEngine:
         return self._p4_plan
 
     def _p4_weights(self, st, prep, info, stride):
-        """mu / sigma blocked once per call for the planar kernel (they are shared by all samples)."""
+        """mu / sigma blocked once per call for the planar kernel (they are shared by all samples).  The blocked
+        buffers are persistent (stable pointers for the multi-layer sampler's job table and for CUDA graphs) and
+        refreshed in place, so parameter updates between calls are honoured."""
         e = prep[id(st)]
         key = ("p4w", stride)
         if key not in e:
             N, C, R, S_ = info["wshape"]
-            e[key] = (ops.p4_block_weights(info["mu"], N, C, R * S_, stride)[0], ops.p4_block_weights(info["sigma"], N, C, R * S_, stride)[0])
+            store = self.__dict__.setdefault("_p4_wbufs", {})
+            if id(st) not in store:
+                nfl = ops.p4_weight_floats(C, N, R, S_, stride)
+                store[id(st)] = (torch.empty((1, nfl), dtype=torch.float32, device=info["mu"].device),
+                                 torch.empty((1, nfl), dtype=torch.float32, device=info["mu"].device))
+            mu_b, sg_b = store[id(st)]
+            ops.p4_block_weights(info["mu"], N, C, R * S_, stride, out=mu_b)
+            ops.p4_block_weights(info["sigma"], N, C, R * S_, stride, out=sg_b)
+            e[key] = (mu_b[0], sg_b[0])
         return e[key]
+
+    def _p4_sample_all(self, n, sample0, prep, seed, p4_convs, device):
+        """ONE sampling launch for every planar conv of the chunk (qbn_sample_weights_blocked_multi)."""
+        import ctypes
+        from ._lib import P4SampleJob
+        steps = [st for st in self.steps if id(st) in p4_convs]
+        tables = self.__dict__.setdefault("_p4_jobs", {})
+        for st in steps:                       # refresh the blocked parameters of this call (once per call, not per chunk)
+            info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"))
+            self._p4_weights(st, prep, info, st.mod.stride[0])
+        if n not in tables:
+            jobs = (P4SampleJob * len(steps))()
+            wbufs, max_fl = {}, 0
+            for i, st in enumerate(steps):
+                info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"))
+                N, C, R, S_ = info["wshape"]
+                mu_b, sg_b = self._p4_weights(st, prep, info, st.mod.stride[0])
+                w = torch.empty((n, mu_b.numel()), dtype=torch.float32, device=device)
+                wbufs[id(st)] = w
+                max_fl = max(max_fl, mu_b.numel())
+                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), None, w.data_ptr(), N, C, R * S_, st.mod.stride[0], st.mod._qbn_layer_id, 0)
+            raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
+            tables[n] = (raw, len(steps), max_fl, wbufs)
+        raw, n_jobs, max_fl, wbufs = tables[n]
+        ops.sample_weights_blocked_multi(raw, n_jobs, max_fl, n, seed, sample0, True)
+        self.launches += 1
+        return wbufs
 
     def _p4_buffer(self, key, n_img, C, Hp, Wp, border, phases, device, zero):
         cache = self.__dict__.setdefault("_bufs", {})
@@ -368,6 +406,9 @@ class MCEngine:
         p4_layout, p4_convs = self._plan_p4()
         if p4_convs:
             reg_pad = {r: v for r, v in reg_pad.items() if r not in p4_layout}
+        self._p4_presampled = None
+        if p4_convs and injected is None:
+            self._p4_presampled = self._p4_sample_all(n, sample0, prep, noise.seed(), p4_convs, x.device)
         regs = {0: x}
         shared = {0: True}
         ready = {0: False}   # register holds TF32-exact values (written by a TF32 epilogue with OUT_ROUND_TF32)
@@ -391,7 +432,7 @@ class MCEngine:
                 continue
             if id(st) in p4_convs:
                 regs[st.dst] = self._run_p4_conv(st, si, src, regs, n, sample0, prep, injected, p4_layout, seed)
-                self.launches += 2
+                self.launches += 1 if self._p4_presampled is not None else 2
                 shared[st.dst] = False
                 ready[st.dst] = True
                 continue
@@ -479,10 +520,13 @@ class MCEngine:
         info = self._packed(st, prep, torch.empty((0, src.C, H0, W0), device="meta"))
         N, C, R, S_ = info["wshape"]
         mu_b, sg_b = self._p4_weights(st, prep, info, stride)
-        eps = None
-        if injected is not None:
-            eps = torch.stack([ops.pack_ohwi(injected[s][st.ref_idx].reshape(info["orig_shape"]).float()) for s in range(n)]).contiguous()
-        w = ops.sample_weights_blocked(mu_b, sg_b, N, C, R * S_, n, eps, seed, m._qbn_layer_id, sample0, True, None, stride)
+        if self._p4_presampled is not None:
+            w = self._p4_presampled[id(st)]
+        else:
+            eps = None
+            if injected is not None:
+                eps = torch.stack([ops.pack_ohwi(injected[s][st.ref_idx].reshape(info["orig_shape"]).float()) for s in range(n)]).contiguous()
+            w = ops.sample_weights_blocked(mu_b, sg_b, N, C, R * S_, n, eps, seed, m._qbn_layer_id, sample0, True, None, stride)
         e = prep[id(st)]
         lay = p4_layout[st.dst]
         split = lay[0] == "p4s"
@@ -504,9 +548,45 @@ class MCEngine:
     @torch.no_grad()
     def predict_sum(self, x, samples, sample0=0, injected=None):
         """Sum over samples [sample0, sample0+samples) of softmax(logits) -> [B,K] (classification) or
-        (sum mu, sum mu^2, sum var) building blocks (regression: returns stacked [S,B] mu and var)."""
+        (sum mu, sum mu^2, sum var) building blocks (regression: returns stacked [S,B] mu and var).
+
+        With use_graph (classification, Philox noise) the ~45 launches per chunk of a call are captured once per
+        (input shape, sample range, seed) into a CUDA graph and replayed: the step is launch-bound otherwise."""
         if not x.is_cuda:
             raise RuntimeError("MCEngine needs CUDA tensors (no CPU fallback)")
+        if self.use_graph and injected is None and not self.regression:
+            return self._predict_sum_graph(x, samples, sample0)
+        return self._predict_sum_eager(x, samples, sample0, injected)
+
+    def _predict_sum_graph(self, x, samples, sample0):
+        key = (tuple(x.shape), x.dtype, int(samples), int(sample0), noise.seed(), x.device.index)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        ent = graphs.get(key)
+        if ent is None:
+            static_x = x.clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                      # warm-up: allocates the cached buffers, sets kernel attributes
+                self._predict_sum_eager(static_x, samples, sample0, None)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            l0 = self.launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._predict_sum_eager(static_x, samples, sample0, None)
+            ent = (g, static_x, static_out, self.launches - l0)
+            self.launches = l0
+            graphs[key] = ent
+            if len(graphs) > 16:
+                graphs.pop(next(iter(graphs)))
+        g, static_x, static_out, n_launch = ent
+        static_x.copy_(x)
+        g.replay()
+        self.launches += n_launch
+        return static_out.clone()
+
+    def _predict_sum_eager(self, x, samples, sample0=0, injected=None):
         x = ops.nhwc(x.float()) if x.dim() == 4 else x.float().contiguous().reshape(x.shape[0], -1, 1, 1)
         prep = self._prepare(x.device)
         psum = None

@@ -528,12 +528,13 @@ def p4_weight_floats(C, N, R, S, stride=1):
     return int(n.value)
 
 
-def p4_block_weights(w_ohwi, N, C, taps, stride=1):
+def p4_block_weights(w_ohwi, N, C, taps, stride=1, out=None):
     """[n_mats, N*taps*C] packed OHWI -> blocked [n_mats, p4_weight_floats] (the blocking depends on the stride)."""
     w_ohwi = w_ohwi.reshape(-1, N * taps * C).contiguous()
     n_mats = w_ohwi.shape[0]
     R = taps
-    out = torch.empty((n_mats, p4_weight_floats(C, N, R, 1, stride)), dtype=torch.float32, device=w_ohwi.device)
+    if out is None:
+        out = torch.empty((n_mats, p4_weight_floats(C, N, R, 1, stride)), dtype=torch.float32, device=w_ohwi.device)
     _lib.call("qbn_p4_block_weights", _ptr(w_ohwi), n_mats, N, C, taps, stride, _ptr(out), _stream())
     return out
 
@@ -544,6 +545,11 @@ def sample_weights_blocked(mu_b, sigma_b, N, C, taps, n_samples=1, eps=None, see
     _lib.call("qbn_sample_weights_blocked", _ptr(mu_b), _ptr(sigma_b), N, C, taps, stride, n_samples, _ptr(eps), seed, layer_id, sample0, _ptr(out),
               int(round_tf32), _stream())
     return out
+
+
+def sample_weights_blocked_multi(jobs_dev, n_jobs, max_floats, n_samples, seed, sample0, round_tf32=True):
+    """jobs_dev: uint8 CUDA tensor holding an array of _lib.P4SampleJob (all planar layers of a chunk, one launch)."""
+    _lib.call("qbn_sample_weights_blocked_multi", _ptr(jobs_dev), n_jobs, max_floats, n_samples, seed, sample0, int(round_tf32), _stream())
 
 
 def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, residual=None, relu=False, flags=0, w_shared=False,

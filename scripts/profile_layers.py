@@ -38,6 +38,18 @@ mc.ops.conv_forward = wrap("conv_v1", ops.conv_forward, d_conv)
 mc.ops.conv_s1_forward = wrap("conv_s1", ops.conv_s1_forward, d_s1)
 mc.ops.sample_weights = wrap("sample_w", ops.sample_weights, d_samp)
 mc.ops.avgpool_all = wrap("avgpool", ops.avgpool_all, d_other)
+def d_p4(a, k, out):
+    x_, w, n, N, R, S_ = a[:6]
+    stride = a[6] if len(a) > 6 else 1
+    H, W = x_.Hp - 2, x_.Wp - 2
+    fl = 2.0 * x_.n_img * H * W * N * R * S_ * x_.C
+    res = a[9] if len(a) > 9 else None
+    by = 4.0 * (x_.buf.numel() * (0.25 if (stride == 2 and R == 1) else 1.0) + out.buf.numel() + (res.buf.numel() if res is not None else 0))
+    return dict(shape="SB%d out%dx%d C%d->N%d k%d s%d%s%s" % (x_.n_img, H, W, x_.C, N, R, stride, " +res" if res is not None else "", " split" if out.phases == 4 else ""),
+                flops=fl, bytes=by, mode=1)
+mc.ops.conv_p4_forward = wrap("conv_p4", ops.conv_p4_forward, d_p4)
+mc.ops.sample_weights_blocked = wrap("sample_wb", ops.sample_weights_blocked, d_other)
+mc.ops.avgpool_p4 = wrap("avgpool_p4", ops.avgpool_p4, d_other)
 mc.ops.softmax_accumulate = wrap("softmax_acc", ops.softmax_accumulate, d_other)
 for _ in range(2):
     rows.clear()
