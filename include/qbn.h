@@ -121,6 +121,9 @@ int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n
 #define QBN_FLAG_OUT_ROUND_TF32 4  /* TF32 mode: round the stored activations to TF32 (RNA) so the
                                       next layer can take the cp.async path                      */
 #define QBN_FLAG_OUT_PHASE_SPLIT 8 /* qbn_conv_p4_fwd: write the output phase-split for a stride-2 consumer */
+#define QBN_FLAG_X_SHARED_STACKED 32 /* qbn_conv_p4_fwd: x holds ONE set of B maps read by all n_samples samples (first layer);
+                                      w is ONE blocked tensor whose N rows are the samples' weights stacked (row s*N + n), so
+                                      the input is staged once and one accumulator tile holds every sample (n_samples*N <= 256) */
 #define QBN_FLAG_OUT_P4 16         /* qbn_conv_fwd (TF32): out and residual are planar-C4 (see below)         */
 int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x,
                  const float* w, int w_shared, const float* scale, const float* shift,
@@ -157,7 +160,8 @@ int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_b, int N, i
 /* the same for several layers in ONE launch: jobs_dev = device array of qbn_p4_sample_job (blockIdx.z = job) */
 typedef struct qbn_p4_sample_job {
   const float* mu_b; const float* sigma_b; const float* eps /* nullable */; float* w;
-  int32_t N, C, taps, stride; uint32_t layer_id; int32_t pad_;
+  int32_t N, C, taps, stride; uint32_t layer_id;
+  int32_t n_stack;   /* > 0: write the n_stack samples stacked along N (row s*N + n of ONE blocked tensor, QBN_FLAG_X_SHARED_STACKED) */
 } qbn_p4_sample_job;
 int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
                                      uint64_t seed, uint32_t sample0, int round_tf32, void* stream);

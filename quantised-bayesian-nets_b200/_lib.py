@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libqbn.so")
+LIB_PATH = os.environ.get("QBN_LIB_PATH") or os.path.join(HERE, "csrc", "libqbn.so")   # (override: A/B kernel tuning only)
 
 QBN_MATH_FP32 = 0
 QBN_MATH_TF32 = 1
@@ -15,6 +15,7 @@ QBN_FLAG_A_TF32_READY = 2
 QBN_FLAG_OUT_ROUND_TF32 = 4
 QBN_FLAG_OUT_PHASE_SPLIT = 8
 QBN_FLAG_OUT_P4 = 16
+QBN_FLAG_X_SHARED_STACKED = 32
 
 
 class ConvDesc(Structure):
@@ -24,7 +25,7 @@ class ConvDesc(Structure):
 
 class P4SampleJob(Structure):
     _fields_ = [("mu_b", c_void_p), ("sigma_b", c_void_p), ("eps", c_void_p), ("w", c_void_p), ("N", c_int32), ("C", c_int32),
-                ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("pad_", c_int32)]
+                ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("n_stack", c_int32)]
 
 
 class I8SampleParams(Structure):

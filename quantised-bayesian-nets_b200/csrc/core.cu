@@ -851,7 +851,7 @@ extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, floa
 // All planar layers of one Monte-Carlo chunk in ONE launch (21 launches -> 1): blockIdx.z = layer job.
 struct qbn_p4_sample_job_dev {
   const float* mu_b; const float* sigma_b; const float* eps; float* w;
-  int N, C, taps, stride; uint32_t layer_id; int pad_;
+  int N, C, taps, stride; uint32_t layer_id; int n_stack;
 };
 __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev* __restrict__ jobs, uint64_t seed, uint32_t sample0,
                                                     int round_tf32) {
@@ -862,10 +862,13 @@ __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev*
   g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(jb.N); g.K = jb.taps * jb.C;
   g.total4 = (int64_t)(jb.C / g.CB) * jb.taps * g.cbc * g.n_pad;
   const int s = blockIdx.y;
-  float4* ws = reinterpret_cast<float4*>(jb.w) + (int64_t)s * g.total4;
+  // stacked: ONE blocked tensor of n_stack*N rows; this sample fills rows [s*N, (s+1)*N) of every (cb, tap, chunk) column
+  const int n_pad_out = jb.n_stack > 0 ? qbn_p4_n_pad(jb.n_stack * jb.N) : g.n_pad;
+  float4* ws = reinterpret_cast<float4*>(jb.w) + (jb.n_stack > 0 ? (int64_t)s * g.N : (int64_t)s * g.total4);
   const float* es = jb.eps ? jb.eps + (int64_t)s * g.N * g.K : nullptr;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t idx = p4_canonical(g, i);
+    if (jb.n_stack > 0 && idx < 0) continue;               // padding rows of the stacked tensor are zeroed by the caller
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (idx >= 0) {
       float z[4];
@@ -883,7 +886,8 @@ __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev*
       o.w = __fadd_rn(m.w, __fmul_rn(z[3], sg.w));
       if (round_tf32) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
     }
-    ws[i] = o;
+    const int64_t col = i / g.n_pad;                         // (cb, tap, chunk) column, row n = i % n_pad
+    ws[jb.n_stack > 0 ? col * n_pad_out + (i - col * g.n_pad) : i] = o;
   }
 }
 extern "C" int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,

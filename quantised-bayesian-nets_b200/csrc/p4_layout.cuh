@@ -11,7 +11,8 @@
 // (cb, tap) block is already the smem image of the B operand, so it is one bulk copy too.
 #pragma once
 
-// channels per block: whole C when small, else the largest of {32, 48, 40, 24, 16, 8} dividing C.
+// channels per block: whole C up to 32, else the first of {32, 16, 24, 8} dividing C — small enough that two
+// CTAs (two tcgen05 issuers) share an SM even when the whole sampled tensor of a 48-channel layer is resident.
 // A stride-2 3x3 conv stages four phase strips per block, so its blocks are at most 24 channels.
 static __host__ __device__ inline int qbn_p4_block_channels(int C, int stride = 1, int taps = 9) {
   if (stride == 2 && taps > 1) {
@@ -20,9 +21,9 @@ static __host__ __device__ inline int qbn_p4_block_channels(int C, int stride = 
       if (C % c2[i] == 0) return c2[i];
     return 0;
   }
-  if (C <= 48) return C;
-  const int cand[6] = {32, 48, 40, 24, 16, 8};
-  for (int i = 0; i < 6; ++i)
+  if (C <= 32) return C;
+  const int cand[4] = {32, 16, 24, 8};
+  for (int i = 0; i < 4; ++i)
     if (C % cand[i] == 0) return cand[i];
   return 0;
 }

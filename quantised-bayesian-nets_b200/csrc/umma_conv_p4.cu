@@ -35,11 +35,12 @@ struct P4Params {
   int N, n_pad, Qs, tiles_per_sample, total_tiles;
   int cbc, n_cb, n_strips, taps, nk;
   int RA, RA_p, d_before;
-  int SA, SB, b_res, ACC, tmem_cols, flags, w_shared, dbg;
+  int SA, SB, TG, b_res, ACC, tmem_cols, flags, w_shared, dbg;
   uint32_t a_bytes, bt_bytes, b_slot_bytes;
   uint32_t idesc, mg_plane, mg_wp;
   long long x_plane, strip_rows, out_plane, res_plane, w_sample_floats;
   int out_split, Hp2, Wp2;
+  int stacked, n_chunks, cps;     // stacked: the N columns are `n_chunks / cps` samples x cps channel chunks (shared input)
   long long q2_total;
   int tap_off[MAX_TAPS];          // 16-byte units inside an A slot: strip * cbc * RA_p + d_before + shift
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; float* out;
@@ -74,7 +75,7 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
   if (r >= d) { ++q; r -= d; }
 }
 
-template <int DBG_MODE>
+template <int DBG_MODE, bool STACKED>
 __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
 
   if (warp == 5) {
     // ======================================= PRODUCER (one lane) ================================
+    // (issuing a tile's copies from several lanes was measured: no gain, the producer runs ahead of the MMAs anyway)
     if (lane == 0) {
       int sa = 0, sb = 0, cur_z = -1;
       uint32_t pa = 0, pb = 0;
@@ -147,20 +149,21 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
           if (dbg & 4) { mbar_arrive(bar); if (++sa == p.SA) { sa = 0; pa ^= 1; } continue; }
           mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(p.cbc * p.n_strips));
           const uint32_t slot = smem_u32(a_ring + (size_t)sa * p.a_bytes) + dst_off;
-          for (int s = 0; s < p.n_strips; ++s) {
-            const float* src = p.x + ((size_t)(cb * p.cbc) * p.x_plane + (size_t)s * p.strip_rows + lo) * 4;
+          for (int s2 = 0; s2 < p.n_strips; ++s2) {
+            const float* src = p.x + ((size_t)(cb * p.cbc) * p.x_plane + (size_t)s2 * p.strip_rows + lo) * 4;
             for (int j = 0; j < p.cbc; ++j)
-              bulk_load_g2s(slot + (uint32_t)s * strip_bytes + (uint32_t)(j * p.RA_p) * 16, src + (size_t)j * p.x_plane * 4, row_bytes, bar);
+              bulk_load_g2s(slot + (uint32_t)s2 * strip_bytes + (uint32_t)(j * p.RA_p) * 16, src + (size_t)j * p.x_plane * 4, row_bytes, bar);
           }
           if (++sa == p.SA) { sa = 0; pa ^= 1; }
           PROF_ADD(18);
           if (!p.b_res) {
             const uint8_t* wb = reinterpret_cast<const uint8_t*>(ws) + (size_t)cb * p.taps * p.bt_bytes;
-            for (int t = 0; t < p.taps; ++t) {
+            for (int t0 = 0; t0 < p.taps; t0 += p.TG) {
               mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
               PROF_ADD(19);
-              mbar_arrive_expect_tx(smem_u32(&b_full[sb]), p.bt_bytes);
-              bulk_load_g2s(smem_u32(b_ring + (size_t)sb * p.b_slot_bytes), wb + (size_t)t * p.bt_bytes, p.bt_bytes, smem_u32(&b_full[sb]));
+              const uint32_t bytes = p.bt_bytes * (uint32_t)min(p.TG, p.taps - t0);
+              mbar_arrive_expect_tx(smem_u32(&b_full[sb]), bytes);
+              bulk_load_g2s(smem_u32(b_ring + (size_t)sb * p.b_slot_bytes), wb + (size_t)t0 * p.bt_bytes, bytes, smem_u32(&b_full[sb]));
               if (++sb == p.SB) { sb = 0; pb ^= 1; }
               PROF_ADD(20);
             }
@@ -200,26 +203,30 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
           tc_fence_after();
           const uint32_t a16 = smem_u32(a_ring + (size_t)sa * p.a_bytes) >> 4;
           uint32_t b16 = (smem_u32(b_ring) >> 4) + (uint32_t)(cb * p.taps) * bt16;
+          // taps in groups of TG: one streamed weight slot per group (resident weights: a single group, no handshake)
 #pragma unroll 1
-          for (int t = 0; t < p.taps; ++t) {
+          for (int t0 = 0; t0 < p.taps; t0 += p.TG) {
             if (!p.b_res) {
               mbar_wait(smem_u32(&b_full[sb]), pb);
               PROF_ADD(11);
               tc_fence_after();
               b16 = smem_u32(b_ring + (size_t)sb * p.b_slot_bytes) >> 4;
             }
-            uint32_t ad = a16 + (uint32_t)p.tap_off[t], bd = b16;
+            const int t1 = min(t0 + p.TG, p.taps);
 #pragma unroll 1
-            for (int jj = 0; jj < ((dbg & 2) ? (t == 0 && cb == 0 ? 1 : 0) : p.nk); ++jj) {
-              umma_mma<MODE_EVAL>(tacc, adesc_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
-              accum = 1;
-              ad += a_k; bd += b_k;
+            for (int t = t0; t < t1; ++t) {
+              uint32_t ad = a16 + (uint32_t)p.tap_off[t], bd = b16;
+#pragma unroll 1
+              for (int jj = 0; jj < ((dbg & 2) ? (t == 0 && cb == 0 ? 1 : 0) : p.nk); ++jj) {
+                umma_mma<MODE_EVAL>(tacc, adesc_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
+                accum = 1;
+                ad += a_k; bd += b_k;
+              }
+              b16 += bt16;
             }
             if (!p.b_res) {
               umma_commit(smem_u32(&b_empty[sb]));
               if (++sb == p.SB) { sb = 0; pb ^= 1; }
-            } else {
-              b16 += bt16;
             }
             PROF_ADD(12);
           }
@@ -241,7 +248,8 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
     uint32_t pacc = 0;
     const uint32_t plane = (uint32_t)(p.Hp * p.Wp);
     const int n_groups = p.n_pad >> 4;
-    const int n_chunks = p.N >> 2;
+    const int n_chunks = p.n_chunks;                         // 16-byte output chunks per row (all stacked samples)
+    const int cps = p.cps;                                   // chunks per sample
     const bool relu = p.flags & QBN_FLAG_RELU, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int z = tile / p.tiles_per_sample;
@@ -281,6 +289,7 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
       if (!(dbg & 8)) tmem_ld16(tlane, v);
+      int jc0 = 0, s0 = 0;                                   // channel chunk / stacked sample of the group's first chunk
       for (int g = 0; g < n_groups; ++g) {
         tmem_ld_wait();
         if (g + 1 < n_groups) {
@@ -297,10 +306,15 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
           for (int i = 0; i < 4; ++i) {
             const int ch = g * 4 + i;
             if (ch < n_chunks) {
+              int jc = ch, sidx = 0;
+              if (STACKED) {
+                jc = jc0 + i; sidx = s0;
+                while (jc >= cps) { jc -= cps; ++sidx; }
+              }
               float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
               if (interior) {
-                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[ch * 4]);
-                const float4 sh = *reinterpret_cast<const float4*>(&s_shift[ch * 4]);
+                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[jc * 4]);
+                const float4 sh = *reinterpret_cast<const float4*>(&s_shift[jc * 4]);
                 o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x) + rres[i].x;
                 o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y) + rres[i].y;
                 o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z) + rres[i].z;
@@ -308,9 +322,13 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
                 if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 if (rnd) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
               }
-              *reinterpret_cast<float4*>(optr + (size_t)ch * p.out_plane * 4) = o;
+              *reinterpret_cast<float4*>(optr + ((size_t)jc * p.out_plane + (STACKED ? (size_t)sidx * p.Qs : (size_t)0)) * 4) = o;
             }
           }
+        }
+        if (STACKED) {
+          jc0 += 4;
+          while (jc0 >= cps) { jc0 -= cps; ++s0; }
         }
         if (g + 1 < n_groups) {
 #pragma unroll
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
       if (++as == p.ACC) { as = 0; pacc ^= 1; }
     }
   }
-  if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {
+  if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {   // (producer numbers: lane 0's view)
     const int role = warp == 0 ? 0 : 16;
     for (int i = 0; i < 8; ++i) g_p4_prof[role + i] = prof_acc[i];
   }
@@ -362,21 +380,30 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
                   "(C=%d N=%d R=%d S=%d stride=%d)", C, N, R, S, stride);
     return QBN_ERR_UNSUPPORTED;
   }
+  const bool stacked = flags & QBN_FLAG_X_SHARED_STACKED;
+  if (stacked && (n_samples * N > 256 || residual || (flags & QBN_FLAG_OUT_PHASE_SPLIT) || w_shared || stride != 1)) {
+    qbn_set_error("qbn_conv_p4_fwd: sample-stacked mode needs n_samples * N <= 256, stride 1, no residual, normal output (n_samples=%d N=%d)",
+                  n_samples, N);
+    return QBN_ERR_UNSUPPORTED;
+  }
   P4Params p;
   memset(&p, 0, sizeof(p));
   p.Hp = Hp; p.Wp = Wp; p.B = B; p.N = N;
+  p.stacked = stacked ? 1 : 0;
+  p.cps = N / 4;
+  p.n_chunks = (stacked ? n_samples : 1) * N / 4;
   p.bh = s1 ? (R - 1) / 2 : 1;
   p.bw = s1 ? (S - 1) / 2 : 1;
   QBN_CHECK_ARG(Hp > 2 * p.bh && Wp > 2 * p.bw, "padded extent must exceed the border");
   p.Qs = B * Hp * Wp;
   p.tiles_per_sample = (p.Qs + TM - 1) / TM;
-  p.total_tiles = p.tiles_per_sample * n_samples;
-  p.n_pad = qbn_p4_n_pad(N);
+  p.total_tiles = p.tiles_per_sample * (stacked ? 1 : n_samples);
+  p.n_pad = qbn_p4_n_pad(stacked ? n_samples * N : N);
   p.n_cb = C / CB;
   p.cbc = CB / 4;
   p.nk = p.cbc / 2;
   p.taps = R * S;
-  p.strip_rows = (long long)n_samples * p.Qs;
+  p.strip_rows = (long long)(stacked ? 1 : n_samples) * p.Qs;
   int d_after = 0;
   if (s1) {
     p.n_strips = 1;
@@ -407,13 +434,13 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   p.a_bytes = (uint32_t)p.n_strips * p.cbc * p.RA_p * 16;
   p.bt_bytes = (uint32_t)p.cbc * p.n_pad * 16;
   p.w_sample_floats = (long long)p.n_cb * p.taps * p.bt_bytes / 4;
-  p.flags = flags; p.w_shared = w_shared;
+  p.flags = flags; p.w_shared = stacked ? 1 : w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   p.mg_plane = (uint32_t)(0x100000000ull / (uint64_t)(Hp * Wp));
   p.mg_wp = (uint32_t)(0x100000000ull / (uint64_t)Wp);
   p.res_plane = p.strip_rows;
-  p.out_plane = p.strip_rows;
+  p.out_plane = (long long)n_samples * p.Qs;
   if (flags & QBN_FLAG_OUT_PHASE_SPLIT) {
     const int H = Hp - 2 * p.bh, W = Wp - 2 * p.bw;
     QBN_CHECK_ARG((H % 2 == 0) && (W % 2 == 0), "phase-split output needs even H, W");
@@ -430,19 +457,32 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   size_t smem;
   const char* e_occ = getenv("QBN_P4_OCC");
   if (b_all <= 100 * 1024 && b_all < (1u << 20)) {
-    p.b_res = 1; p.SB = 1; p.b_slot_bytes = (uint32_t)b_all;
+    p.b_res = 1; p.SB = 1; p.TG = p.taps; p.b_slot_bytes = (uint32_t)b_all;
     want_occ = e_occ ? atoi(e_occ) : 3;
     while (want_occ > 1 && 2 * (size_t)p.a_bytes + b_all + fixed > cap / want_occ - 1024) --want_occ;
     p.SA = 2;
     while (p.SA < 4 && (size_t)(p.SA + 1) * p.a_bytes + b_all + fixed <= cap / want_occ - 1024) ++p.SA;
     smem = (size_t)p.SA * p.a_bytes + b_all + fixed;
   } else {
-    p.b_res = 0; p.b_slot_bytes = p.bt_bytes;
-    want_occ = e_occ ? atoi(e_occ) : 2;
-    while (want_occ > 1 && 2 * (size_t)p.a_bytes + 3 * (size_t)p.bt_bytes + fixed > cap / want_occ - 1024) --want_occ;
+    // streamed weights: one slot = TG consecutive taps of a channel block (contiguous in the blocked layout).
+    // Wide outputs (n_pad > 128) get ONE CTA per SM — two accumulators in TMEM so the epilogue overlaps the MMAs —
+    // and big slots (few handshakes); narrower ones two CTAs (two issuers) with ~16-28 KB slots.  (measured)
+    p.b_res = 0;
+    want_occ = e_occ ? atoi(e_occ) : (p.n_pad > 128 ? 1 : 2);
+    const size_t slot_cap = want_occ == 1 ? 76 * 1024 : 28 * 1024;
+    p.TG = 1;
+    for (int tg = 2; tg <= p.taps; ++tg)
+      if (p.taps % tg == 0 && (size_t)tg * p.bt_bytes <= slot_cap) p.TG = tg;
+    if (getenv("QBN_P4_TG")) p.TG = atoi(getenv("QBN_P4_TG"));
+    p.b_slot_bytes = p.bt_bytes * (uint32_t)p.TG;
+    while (want_occ > 1 && 2 * (size_t)p.a_bytes + 3 * (size_t)p.b_slot_bytes + fixed > cap / want_occ - 1024) --want_occ;
+    while (p.TG > 1 && 2 * (size_t)p.a_bytes + 2 * (size_t)p.b_slot_bytes + fixed > cap / want_occ - 1024) {   // shrink the slots until two fit
+      do { --p.TG; } while (p.taps % p.TG != 0);
+      p.b_slot_bytes = p.bt_bytes * (uint32_t)p.TG;
+    }
     p.SA = 2; p.SB = 2;
-    while (p.SB < 8 && (size_t)p.SA * p.a_bytes + (size_t)(p.SB + 1) * p.bt_bytes + fixed <= cap / want_occ - 1024) ++p.SB;
-    smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.bt_bytes + fixed;
+    while (p.SB < 8 && (size_t)p.SA * p.a_bytes + (size_t)(p.SB + 1) * p.b_slot_bytes + fixed <= cap / want_occ - 1024) ++p.SB;
+    smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.b_slot_bytes + fixed;
   }
   if (getenv("QBN_P4_SA")) {
     const int sa_new = atoi(getenv("QBN_P4_SA"));
@@ -467,9 +507,10 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
@@ -478,12 +519,17 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   int grid = qbn_sm_count() * occ;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (getenv("QBN_P4_VERBOSE"))
-    fprintf(stderr, "[p4] C=%d N=%d %dx%d k%d s%d: tiles=%d grid=%d occ=%d SA=%d SB=%d ACC=%d b_res=%d smem=%zu a_bytes=%u bt=%u tmem=%d\n", C, N, Hp,
-            Wp, R, stride, p.total_tiles, grid, occ, p.SA, p.SB, p.ACC, p.b_res, smem, p.a_bytes, p.bt_bytes, p.tmem_cols);
+    fprintf(stderr, "[p4] C=%d N=%d %dx%d k%d s%d: tiles=%d grid=%d occ=%d SA=%d SB=%d TG=%d ACC=%d b_res=%d smem=%zu a_bytes=%u bt=%u tmem=%d\n", C, N, Hp,
+            Wp, R, stride, p.total_tiles, grid, occ, p.SA, p.SB, p.TG, p.ACC, p.b_res, smem, p.a_bytes, p.bt_bytes, p.tmem_cols);
+  if (stacked) {
+    umma_conv_p4_kernel<0, true><<<grid, P4_THREADS, smem, st>>>(p);
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
+  }
   if (getenv("QBN_P4_PROF")) {
     unsigned long long h[32] = {0};
     cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
-    umma_conv_p4_kernel<1><<<grid, P4_THREADS, smem, st>>>(p);
+    umma_conv_p4_kernel<1, false><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     cudaStreamSynchronize(st);
     cudaMemcpyFromSymbol(h, g_p4_prof, sizeof(h));
@@ -497,11 +543,11 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   }
   if (getenv("QBN_P4_DBG")) {
     p.dbg = atoi(getenv("QBN_P4_DBG"));
-    umma_conv_p4_kernel<2><<<grid, P4_THREADS, smem, st>>>(p);
+    umma_conv_p4_kernel<2, false><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
-  umma_conv_p4_kernel<0><<<grid, P4_THREADS, smem, st>>>(p);
+  umma_conv_p4_kernel<0, false><<<grid, P4_THREADS, smem, st>>>(p);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

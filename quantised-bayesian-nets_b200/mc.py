@@ -159,11 +159,11 @@ class MCEngine:
             prep[id(st)].update(scale=scale, shift=shift)
         return prep
 
-    def _packed(self, st, prep, x):
+    def _packed(self, st, prep, x, cmult=4):
         """Pack (mu, sigma) for the geometry this step sees (depends on the input's H, W for the
         flatten->linear case, which runs as an HxW 'valid' convolution over the NHWC map)."""
         e = prep[id(st)]
-        key = ("packed", tuple(x.shape[1:]) if st.is_linear else None)     # only flatten->linear depends on the map size
+        key = ("packed", tuple(x.shape[1:]) if st.is_linear else None, cmult)     # only flatten->linear depends on the map size
         if key in e:
             return e[key]
         m = st.mod
@@ -181,8 +181,8 @@ class MCEngine:
             stride, pad, dil = m.stride, m.padding, m.dilation
         C = w4.shape[1]
         cpad = 0
-        if self.math_mode == QBN_MATH_TF32 and C % 4 != 0 and C < 4:
-            cpad = 4 - C % 4   # 3-channel input layer: pad channels so 16-byte K-chunks stay inside a tap
+        if self.math_mode == QBN_MATH_TF32 and C % cmult != 0 and C < cmult:
+            cpad = cmult - C % cmult   # 3-channel input layer: pad channels so 16-byte K-chunks stay inside a tap (8 for the planar kernel)
             w4 = torch.nn.functional.pad(w4, (0, 0, 0, 0, 0, cpad))
             rho4 = torch.nn.functional.pad(rho4, (0, 0, 0, 0, 0, cpad), value=-200.0)  # softplus -> 0
         packed = ops.weight_prep(w4.contiguous(), rho4.contiguous(), False, None, want=("mu", "sigma"))
@@ -333,6 +333,14 @@ class MCEngine:
                 break
             for k in drop:
                 on.pop(k)
+        # first layer (shared input, <= 8 channels): sample-stacked planar launch instead of the gather kernel
+        self._p4_first = None
+        for st in convs:
+            m = st.mod
+            if (st.src == 0 and not st.is_linear and id(st) not in on and layout.get(st.dst, (None, None)) == ("p4", (1, 1)) and st.residual is None
+                    and m.in_channels <= 8 and tuple(m.kernel_size) == (3, 3) and tuple(m.stride) == (1, 1) and tuple(m.padding) == (1, 1)
+                    and tuple(m.dilation) == (1, 1) and m.out_channels % 4 == 0):
+                self._p4_first = id(st)
         self._p4_plan = (layout, set(on))
         return self._p4_plan
 
@@ -359,22 +367,30 @@ class MCEngine:
         """ONE sampling launch for every planar conv of the chunk (qbn_sample_weights_blocked_multi)."""
         import ctypes
         from ._lib import P4SampleJob
-        steps = [st for st in self.steps if id(st) in p4_convs]
+        first = self._p4_first
+        def stack_ok(st):
+            return id(st) == first and n * st.mod.out_channels <= 256
+        steps = [st for st in self.steps if id(st) in p4_convs or (isinstance(st, _ConvStep) and stack_ok(st))]
         tables = self.__dict__.setdefault("_p4_jobs", {})
+        def pinfo(st):
+            return self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"), 8 if id(st) == first else 4)
         for st in steps:                       # refresh the blocked parameters of this call (once per call, not per chunk)
-            info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"))
-            self._p4_weights(st, prep, info, st.mod.stride[0])
+            self._p4_weights(st, prep, pinfo(st), st.mod.stride[0])
         if n not in tables:
             jobs = (P4SampleJob * len(steps))()
             wbufs, max_fl = {}, 0
             for i, st in enumerate(steps):
-                info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"))
+                info = pinfo(st)
                 N, C, R, S_ = info["wshape"]
                 mu_b, sg_b = self._p4_weights(st, prep, info, st.mod.stride[0])
-                w = torch.empty((n, mu_b.numel()), dtype=torch.float32, device=device)
+                if stack_ok(st):   # one blocked tensor, the chunk's samples stacked along N (padding rows stay zero)
+                    w = torch.zeros((1, ops.p4_weight_floats(C, n * N, R, S_, 1)), dtype=torch.float32, device=device)
+                else:
+                    w = torch.empty((n, mu_b.numel()), dtype=torch.float32, device=device)
                 wbufs[id(st)] = w
                 max_fl = max(max_fl, mu_b.numel())
-                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), None, w.data_ptr(), N, C, R * S_, st.mod.stride[0], st.mod._qbn_layer_id, 0)
+                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), None, w.data_ptr(), N, C, R * S_, st.mod.stride[0], st.mod._qbn_layer_id,
+                                      n if stack_ok(st) else 0)
             raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
             tables[n] = (raw, len(steps), max_fl, wbufs)
         raw, n_jobs, max_fl, wbufs = tables[n]
@@ -429,6 +445,26 @@ class MCEngine:
                 shared[st.dst] = shared[st.src]
                 ready[st.dst] = ready[st.src] and st.kind == "max"   # max of TF32-exact values is TF32-exact
                 self.launches += 1
+                continue
+            if self._p4_presampled is not None and id(st) in self._p4_presampled and id(st) == self._p4_first:
+                # first layer on the planar kernel: the shared input is staged once, the chunk's samples are stacked along N
+                info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"), 8)
+                N, C, R, S_ = info["wshape"]
+                if "x_p4" not in prep:
+                    xn = src.permute(0, 1, 2, 3) if src.dim() == 4 else src
+                    xp = torch.nn.functional.pad(xn.contiguous(), (0, 0, 0, 0, 0, C - xn.shape[1]))
+                    xi = xp.contiguous().view(torch.int32)
+                    xp = ((xi + 0x1000) & ~0x1FFF).view(torch.float32)      # RNA to TF32 (the tensor core would truncate)
+                    prep["x_p4"] = ops.P4Map.from_nchw(xp, (1, 1))
+                xm = prep["x_p4"]
+                outp = self._p4_buffer(("p4first", si), n * xm.n_img, N, xm.Hp, xm.Wp, (1, 1), 1, src.device, zero=False)
+                e = prep[id(st)]
+                ops.conv_p4_forward(xm, self._p4_presampled[id(st)], n, N, R, S_, 1, e["scale"], e["shift"], None, st.relu,
+                                    ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED, False, outp)
+                self.launches += 1
+                regs[st.dst] = outp
+                shared[st.dst] = False
+                ready[st.dst] = True
                 continue
             if id(st) in p4_convs:
                 regs[st.dst] = self._run_p4_conv(st, si, src, regs, n, sample0, prep, injected, p4_layout, seed)

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, I8SampleParams, QBN_FLAG_A_TF32_READY, QBN_FLAG_OUT_P4, QBN_FLAG_OUT_PHASE_SPLIT,  # noqa: F401
-                   QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU, QBN_MATH_FP32, QBN_MATH_TF32)
+                   QBN_FLAG_X_SHARED_STACKED, QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU, QBN_MATH_FP32, QBN_MATH_TF32)
 
 CL = torch.channels_last
 
@@ -556,16 +556,18 @@ def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, 
                     out=None, phase_split_out=False):
     """qbn_conv_p4_fwd.  x: P4Map (phase-split when stride == 2); w: blocked sampled weights [n_samples, ...];
     residual: P4Map with the output geometry.  Returns a P4Map."""
-    B = x.n_img // n_samples
+    stacked = bool(int(flags) & QBN_FLAG_X_SHARED_STACKED)
+    B = x.n_img if stacked else x.n_img // n_samples
+    n_out = x.n_img * n_samples if stacked else x.n_img
     if stride == 2 and x.phases != 4:
         raise _lib.QbnError("stride-2 planar conv needs a phase-split input")
     border = ((R - 1) // 2, (S - 1) // 2) if stride == 1 else (1, 1)
     if out is None:
         if phase_split_out:
             H, W = x.Hp - 2 * border[0], x.Wp - 2 * border[1]
-            out = P4Map.empty(x.n_img, N, H // 2 + 2, W // 2 + 2, (1, 1), 4, x.buf.device, zero=True)
+            out = P4Map.empty(n_out, N, H // 2 + 2, W // 2 + 2, (1, 1), 4, x.buf.device, zero=True)
         else:
-            out = P4Map.empty(x.n_img, N, x.Hp, x.Wp, border, 1, x.buf.device)
+            out = P4Map.empty(n_out, N, x.Hp, x.Wp, border, 1, x.buf.device)
     fl = int(bool(relu)) | int(flags) | (QBN_FLAG_OUT_PHASE_SPLIT if phase_split_out else 0)
     _lib.call("qbn_conv_p4_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, stride, _ptr(x.buf), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
               _ptr(residual.buf if residual is not None else None), fl, _ptr(out.buf), _stream())

@@ -10,7 +10,7 @@ chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 P = O.ResNetBBBParams(seed=1)
 model = zoo.resnet_from_params(P).cuda().eval()
 noise.manual_seed(1)
-eng = mc.MCEngine(model, math_mode="tf32", chunk=chunk)
+eng = mc.MCEngine(model, math_mode="tf32", chunk=chunk, use_graph=False)
 x = torch.randn(256, 3, 32, 32, generator=torch.Generator().manual_seed(2)).cuda()
 rows = []
 def wrap(name, fn, describe):

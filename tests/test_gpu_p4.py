@@ -178,3 +178,68 @@ def test_p4_conv_full_size_linearity():
     assert torch.equal(c, c2)
     err = float((a + b - c).abs().max()) / float(c.abs().max())
     assert err < 2e-3, err
+
+
+def _stack_blocked(wb, N, n_pad, S):
+    """[S, cols*n_pad*4] per-sample blocked weights -> ONE blocked tensor whose rows are the samples stacked."""
+    cols = wb.shape[1] // (n_pad * 4)
+    rows = wb.reshape(S, cols, n_pad, 4)[:, :, :N, :]                 # [S, cols, N, 4]
+    st = rows.permute(1, 0, 2, 3).reshape(cols, S * N, 4)
+    n_pad_st = (S * N + 15) // 16 * 16
+    out = torch.zeros(cols, n_pad_st, 4, device=wb.device)
+    out[:, :S * N] = st
+    return out.reshape(1, -1).contiguous()
+
+
+def test_p4_first_layer_sample_stacked():
+    """Shared input + the samples' weights stacked along N (QBN_FLAG_X_SHARED_STACKED) == per-sample convolutions."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    B, S, C, N, H = 3, 4, 8, 24, 16
+    x = _tf32_round_(torch.randn(B, C, H, H, generator=g).cuda())
+    x[:, 3:] = 0
+    w = _rand_weights(g, S, N, 3, C)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    d = ops.make_desc(B, H, H, C, N, 3, 3, 1, 1, 1)
+    ref = ops.conv_forward(ops.nhwc(x), w, d, S, True, False, scale, shift, None, True, None, 1.0, ops.QBN_MATH_FP32).reshape(S * B, N, H, H)
+    wb = ops.p4_block_weights(w, N, C, 9)
+    wst = _stack_blocked(wb, N, 32, S)
+    assert wst.shape[1] == ops.p4_weight_floats(C, S * N, 3, 3, 1)
+    xm = ops.P4Map.from_nchw(x, (1, 1))
+    got = ops.conv_p4_forward(xm, wst, S, N, 3, 3, 1, scale, shift, None, True, ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED)
+    assert got.n_img == S * B
+    close(got.to_nchw(), ref, 1e-3, 1e-3)
+    full = got.to_nchw(keep_border=True).clone()
+    full[:, :, 1:-1, 1:-1] = 0
+    assert float(full.abs().max()) == 0.0
+
+
+def test_p4_multi_layer_sampler():
+    """qbn_sample_weights_blocked_multi (all layers of a chunk in one launch, incl. the stacked first layer) is
+    bit-identical to the per-layer sampler."""
+    import ctypes
+    from qbn_b200 import ops
+    from qbn_b200._lib import P4SampleJob
+    g = torch.Generator().manual_seed(41)
+    S = 5
+    layers = [(8, 24, 9, 1, 11, True), (24, 24, 9, 1, 12, False), (24, 48, 9, 2, 13, False), (24, 48, 1, 2, 14, False), (96, 96, 9, 1, 15, False)]
+    jobs = (P4SampleJob * len(layers))()
+    keep, want = [], []
+    for i, (C, N, taps, stride, lid, stack) in enumerate(layers):
+        mu = torch.randn(N * taps * C, generator=g).cuda()
+        sg = torch.rand(N * taps * C, generator=g).cuda()
+        mu_b, sg_b = ops.p4_block_weights(mu, N, C, taps, stride)[0], ops.p4_block_weights(sg, N, C, taps, stride)[0]
+        single = ops.sample_weights_blocked(mu_b, sg_b, N, C, taps, S, None, 77, lid, 3, True, None, stride)
+        if stack:
+            single = _stack_blocked(single, N, (N + 15) // 16 * 16, S)
+            w = torch.zeros_like(single)
+        else:
+            w = torch.empty_like(single)
+        jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), None, w.data_ptr(), N, C, taps, stride, lid, S if stack else 0)
+        keep.append((mu_b, sg_b, w))
+        want.append(single)
+    raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).cuda()
+    ops.sample_weights_blocked_multi(raw, len(layers), max(k[0].numel() for k in keep), S, 77, 3, True)
+    for (mu_b, sg_b, w), ref in zip(keep, want):
+        assert torch.equal(w, ref)
