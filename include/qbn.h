@@ -124,6 +124,7 @@ int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n
 #define QBN_FLAG_X_SHARED_STACKED 32 /* qbn_conv_p4_fwd: x holds ONE set of B maps read by all n_samples samples (first layer);
                                       w is ONE blocked tensor whose N rows are the samples' weights stacked (row s*N + n), so
                                       the input is staged once and one accumulator tile holds every sample (n_samples*N <= 256) */
+#define QBN_FLAG_RELU_PRE 64        /* qbn_conv_p4_fwd: ReLU right after the affine, before the output mask / residual */
 #define QBN_FLAG_OUT_P4 16         /* qbn_conv_fwd (TF32): out and residual are planar-C4 (see below)         */
 int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x,
                  const float* w, int w_shared, const float* scale, const float* shift,
@@ -165,9 +166,17 @@ typedef struct qbn_p4_sample_job {
 } qbn_p4_sample_job;
 int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
                                      uint64_t seed, uint32_t sample0, int round_tf32, void* stream);
+/* epilogue order: affine -> [RELU_PRE] -> [out_mask: MC-Dropout of the OUTPUT, x*mask[img][n]*mult, A8] -> [+residual]
+ * -> [RELU] -> [RNA]; that is conv-BN-ReLU-dropout (models_mc.py:125-129) and conv-BN-dropout-add-ReLU (:130-157) */
 int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
                     const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
-                    int flags, float* out, void* stream);
+                    const float* out_mask /* nullable [n_samples*B][N] */, float out_mask_mult, int flags, float* out,
+                    void* stream);
+/* Bernoulli(keep) masks of several dropout sites in ONE launch: jobs_dev = device array of qbn_mask_job; the mask of
+ * site j, sample s is out[j][s][elems], Philox(seed, site_id, sample0 + s, element) */
+typedef struct qbn_mask_job { float* out; int64_t elems; uint32_t site_id; int32_t pad_; } qbn_mask_job;
+int qbn_dropout_masks_multi(const void* jobs_dev, int n_jobs, int64_t max_elems, int n_samples, float keep_prob,
+                            uint64_t seed, uint32_t sample0, void* stream);
 /* global average pool of planar-C4 maps -> [n_img][C] (divisor = interior pixel count) */
 int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, float divisor, float* out, void* stream);
 

@@ -272,6 +272,43 @@ def gen_models(src):
     save("mlp", y_mu=npy(mu), y_var=npy(var), kl=npy(net.get_kl_divergence()))
 
 
+def gen_mc_models(src):
+    """MC-Dropout networks (configs 2 and 5): reference models_mc.py ConvNetwork_ResNet / ConvNetwork_LeNet, p = 0.15 / 0.2,
+    two seeded stochastic forwards each.  Weights: the mu tensors of the seed-generated BBB containers."""
+    import oracle.qbn_oracle as O
+    from src.models.stochastic.mcdropout.models_mc import ConvNetwork_LeNet, ConvNetwork_ResNet
+    P = O.ResNetBBBParams(seed=51)
+    args = Args(p=0.15, model="conv_resnet_mc")
+    net = ConvNetwork_ResNet([4, 3, 32, 32], 10, False, args)
+    sd = net.state_dict()
+    sd.update(O.resnet_mc_state_dict(P))
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(52))
+    arrays = {}
+    for s in range(2):
+        torch.manual_seed(1100 + s)
+        with torch.no_grad():
+            arrays["y%d" % s] = npy(net(x))
+    save("resnet_mc", **arrays)
+
+    P = O.LeNetBBBParams(seed=61)
+    args = Args(p=0.2, model="conv_lenet_mc")
+    net = ConvNetwork_LeNet([1, 1, 28, 28], 10, False, args)
+    sd = net.state_dict()
+    for ref_name, key in (("layers.0", "layers.0"), ("layers.3", "layers.2"), ("layers.7", "layers.5"), ("layers.10", "layers.7")):
+        sd[ref_name + ".weight"] = P.layers[key][0]
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.rand(4, 1, 28, 28, generator=torch.Generator().manual_seed(62))
+    arrays = {}
+    for s in range(2):
+        torch.manual_seed(1200 + s)
+        with torch.no_grad():
+            arrays["y%d" % s] = npy(net(x))
+    save("lenet_mc", **arrays)
+
+
 def _tiny_qnet(src, args):
     """The reference's ConvNetwork_LeNet forward/fuse_model (models_bbb.py:98-143) over the
     reference's own layer classes, with small layer sizes so the int8 fixture stays small."""
@@ -503,9 +540,17 @@ def main():
     gen_metrics(src)
     gen_losses(src)
     gen_models(src)
+    gen_mc_models(src)
     gen_quant_ops(src)
     gen_qat_int8(src)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1:                  # regenerate selected fixtures only, e.g. `python oracle/make_golden.py gen_mc_models`
+        _src = import_reference()
+        torch.set_num_threads(1)
+        for _name in sys.argv[1:]:
+            globals()[_name](_src)
+    else:
+        main()

@@ -527,3 +527,83 @@ def mlp_bbb_eval_forward(P, x, eps_fn):
     mu, rho, b = P.layers["log_var"]
     out_lv = eval_linear_fwd(h, mu, rho, b, eps_fn("log_var", mu.shape))
     return out_mu, out_lv.exp()
+
+
+# ------------------------------------------------------------------------------------------------
+# MC-Dropout networks (models_mc.py): deterministic weights, Bernoulli masks per (image, channel)
+# ------------------------------------------------------------------------------------------------
+def resnet_mc_forward(P, x, mask_fn, p):
+    """One forward of mcdropout/models_mc.py:159-226 (ConvNetwork_ResNet) with the BasicBlock of :117-157.
+    P: ResNetBBBParams (only the mu tensors are used as the nn.Conv2d / nn.Linear weights).
+    mask_fn(name, shape) supplies the Bernoulli(1-p) masks in the reference's draw order (dropout.py:19-30):
+    after layers.0-2, then per block stem.3 (after conv-bn-relu), stem.6 (after conv-bn), shortcut.2."""
+
+    def conv(name, h, stride, pad):
+        return F.conv2d(h, P.convs[name][0], None, stride, pad)
+
+    def bn(name, h):
+        w, b, rm, rv, eps = P.bns[name]
+        return F.batch_norm(h, rm, rv, w, b, False, 0.0, eps)
+
+    def drop(name, h):
+        return dropout_fwd(h, mask_fn(name, tuple(h.shape[:2])), p)
+
+    h = drop("layers.3", F.relu(bn("layers.1", conv("layers.0", x, 1, 1))))
+    for pfx, stride, has_sc in P.blocks:
+        out = drop(pfx + ".stem.3", F.relu(bn(pfx + ".stem.1", conv(pfx + ".stem.0", h, stride, 1))))
+        out = drop(pfx + ".stem.6", bn(pfx + ".stem.4", conv(pfx + ".stem.3", out, 1, 1)))
+        sc = drop(pfx + ".shortcut.2", bn(pfx + ".shortcut.1", conv(pfx + ".shortcut.0", h, stride, 0))) if has_sc else h
+        h = F.relu(out + sc)
+    h = F.avg_pool2d(h, 4).reshape(h.size(0), -1)
+    return F.softmax(F.linear(h, P.fc[0]), dim=-1)
+
+
+def resnet_mc_mask_plan(P, batch):
+    """Draw order and shapes of the dropout masks of one forward -> [(name, (B, C))]."""
+    plan = [("layers.3", (batch, 24))]
+    for pfx, _, has_sc in P.blocks:
+        c = P.convs[pfx + ".stem.0"][0].shape[0]
+        plan += [(pfx + ".stem.3", (batch, c)), (pfx + ".stem.6", (batch, c))]
+        if has_sc:
+            plan.append((pfx + ".shortcut.2", (batch, c)))
+    return plan
+
+
+def replay_masks(seed, shapes, p):
+    """dropout.py:21-30: `torch.zeros(shape).bernoulli_(1 - self.p)` with self.p a 1-element tensor, global generator."""
+    torch.manual_seed(seed)
+    keep = 1.0 - torch.ones(1) * p
+    return [torch.empty(tuple(s)).bernoulli_(keep) for s in shapes]
+
+
+def lenet_mc_forward(P, x, mask_fn, p):
+    """mcdropout/models_mc.py:75-110 (ConvNetwork_LeNet): conv5x5-drop-pool, conv5x5-drop-pool, fc-relu-drop-fc.
+    P: LeNetBBBParams (mu tensors as the deterministic weights)."""
+    w0, w1, w2, w3 = (P.layers[k][0] for k in ("layers.0", "layers.2", "layers.5", "layers.7"))   # BBB container keys
+    h = F.conv2d(x, w0, None, 1, 2)
+    h = F.max_pool2d(dropout_fwd(h, mask_fn("layers.1", tuple(h.shape[:2])), p), 2, 2)
+    h = F.conv2d(h, w1, None, 1, 2)
+    h = F.max_pool2d(dropout_fwd(h, mask_fn("layers.4", tuple(h.shape[:2])), p), 2, 2)
+    h = F.relu(F.linear(h.reshape(h.size(0), -1), w2))
+    h = dropout_fwd(h, mask_fn("layers.9", tuple(h.shape)), p)
+    return F.softmax(F.linear(h, w3), dim=-1)
+
+
+def resnet_mc_state_dict(P):
+    """ResNetBBBParams -> state-dict entries under the module names of models_mc.py's ConvNetwork_ResNet
+    (one more top-level module — the dropout after layers.0-2 — and dropouts inside the stem shift the indices)."""
+    sd = {"layers.0.weight": P.convs["layers.0"][0]}
+    w, b, rm, rv, _ = P.bns["layers.1"]
+    sd.update({"layers.1.weight": w, "layers.1.bias": b, "layers.1.running_mean": rm, "layers.1.running_var": rv})
+    for pfx, _, has_sc in P.blocks:
+        li, bi = int(pfx.split(".")[1]), int(pfx.split(".")[2])
+        q = "layers.%d.%d" % (li + 1, bi)
+        for src, dst in ((".stem.0", ".stem.0"), (".stem.3", ".stem.4"), (".shortcut.0", ".shortcut.0")):
+            if pfx + src in P.convs:
+                sd[q + dst + ".weight"] = P.convs[pfx + src][0]
+        for src, dst in ((".stem.1", ".stem.1"), (".stem.4", ".stem.5"), (".shortcut.1", ".shortcut.1")):
+            if pfx + src in P.bns:
+                w, b, rm, rv, _ = P.bns[pfx + src]
+                sd.update({q + dst + ".weight": w, q + dst + ".bias": b, q + dst + ".running_mean": rm, q + dst + ".running_var": rv})
+    sd["layers.10.weight"] = P.fc[0]
+    return sd

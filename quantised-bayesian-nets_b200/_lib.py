@@ -16,6 +16,7 @@ QBN_FLAG_OUT_ROUND_TF32 = 4
 QBN_FLAG_OUT_PHASE_SPLIT = 8
 QBN_FLAG_OUT_P4 = 16
 QBN_FLAG_X_SHARED_STACKED = 32
+QBN_FLAG_RELU_PRE = 64
 
 
 class ConvDesc(Structure):
@@ -26,6 +27,10 @@ class ConvDesc(Structure):
 class P4SampleJob(Structure):
     _fields_ = [("mu_b", c_void_p), ("sigma_b", c_void_p), ("eps", c_void_p), ("w", c_void_p), ("N", c_int32), ("C", c_int32),
                 ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("n_stack", c_int32)]
+
+
+class MaskJob(Structure):
+    _fields_ = [("out", c_void_p), ("elems", c_int64), ("site_id", c_uint32), ("pad_", c_int32)]
 
 
 class I8SampleParams(Structure):
@@ -77,7 +82,8 @@ _SIGNATURES = {
     "qbn_p4_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "qbn_sample_weights_blocked": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, c_uint64, c_uint32, c_uint32, P, c_int, P]),
     "qbn_sample_weights_blocked_multi": (c_int, [P, c_int, c_int64, c_int, c_uint64, c_uint32, c_int, P]),
-    "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
+    "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, c_float, c_int, P, P]),
+    "qbn_dropout_masks_multi": (c_int, [P, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, P]),
     "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
 }
 

@@ -901,3 +901,23 @@ extern "C" int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
+
+// A8 masks of every dropout site of a Monte-Carlo chunk in one launch (blockIdx.z = site, blockIdx.y = sample)
+struct qbn_mask_job_dev { float* out; int64_t elems; uint32_t site_id; int pad_; };
+__global__ void dropout_masks_multi_kernel(const qbn_mask_job_dev* __restrict__ jobs, float keep, uint64_t seed, uint32_t sample0) {
+  const qbn_mask_job_dev jb = jobs[blockIdx.z];
+  const int s = blockIdx.y;
+  float* o = jb.out + (int64_t)s * jb.elems;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < jb.elems; i += (int64_t)gridDim.x * blockDim.x)
+    o[i] = philox_uniform1(seed, jb.site_id, sample0 + (uint32_t)s, (uint64_t)i) < keep ? 1.0f : 0.0f;
+}
+extern "C" int qbn_dropout_masks_multi(const void* jobs_dev, int n_jobs, int64_t max_elems, int n_samples, float keep_prob, uint64_t seed,
+                                       uint32_t sample0, void* stream) {
+  QBN_CHECK_ARG(jobs_dev && n_jobs > 0 && n_jobs <= 65535 && n_samples > 0 && n_samples <= 65535 && max_elems > 0, "args");
+  int64_t gx = (max_elems + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  dropout_masks_multi_kernel<<<dim3((unsigned)gx, n_samples, n_jobs), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const qbn_mask_job_dev*>(jobs_dev), keep_prob, seed, sample0);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

@@ -44,6 +44,7 @@ struct P4Params {
   long long q2_total;
   int tap_off[MAX_TAPS];          // 16-byte units inside an A slot: strip * cbc * RA_p + d_before + shift
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; float* out;
+  const float* out_mask; float out_mask_mult;     // A8: MC-Dropout of the OUTPUT, mask [n_img][N] (dropout.py:35-39)
 };
 
 // cycle accounting of CTA 0 (QBN_P4_PROF=1): [role*8 + category], summed over its tiles
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
     const int n_groups = p.n_pad >> 4;
     const int n_chunks = p.n_chunks;                         // 16-byte output chunks per row (all stacked samples)
     const int cps = p.cps;                                   // chunks per sample
-    const bool relu = p.flags & QBN_FLAG_RELU, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
+    const bool relu = p.flags & QBN_FLAG_RELU, relu_pre = p.flags & QBN_FLAG_RELU_PRE, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int z = tile / p.tiles_per_sample;
       const int q0 = (tile - z * p.tiles_per_sample) * TM;
@@ -271,6 +272,8 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
         store = interior;                                   // its border is never written (pre-zeroed buffer)
       }
       float* optr = p.out + (store ? orow : 0) * 4;
+      // dropout mask row of this pixel's image (stacked: sample sidx of the shared input adds sidx * B images)
+      const float* mrow = (p.out_mask && interior) ? p.out_mask + (size_t)(z * p.B + (int)b) * p.N : nullptr;
       const float* rptr = (p.residual && interior) ? p.residual + in_row * 4 : nullptr;
       float4 rres[4], rnext[4];
       uint32_t v[16], vn[16];
@@ -315,10 +318,17 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
               if (interior) {
                 const float4 sc = *reinterpret_cast<const float4*>(&s_scale[jc * 4]);
                 const float4 sh = *reinterpret_cast<const float4*>(&s_shift[jc * 4]);
-                o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x) + rres[i].x;
-                o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y) + rres[i].y;
-                o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z) + rres[i].z;
-                o.w = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w) + rres[i].w;
+                o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x);
+                o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
+                o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
+                o.w = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
+                if (relu_pre) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (mrow) {     // x = mul(x, mask); x = mul_scalar(x, multiplier): two roundings like the reference
+                  const float4 mk = *reinterpret_cast<const float4*>(mrow + (STACKED ? (size_t)sidx * p.B * p.N : (size_t)0) + jc * 4);
+                  o.x = __fmul_rn(__fmul_rn(o.x, mk.x), p.out_mask_mult); o.y = __fmul_rn(__fmul_rn(o.y, mk.y), p.out_mask_mult);
+                  o.z = __fmul_rn(__fmul_rn(o.z, mk.z), p.out_mask_mult); o.w = __fmul_rn(__fmul_rn(o.w, mk.w), p.out_mask_mult);
+                }
+                o.x += rres[i].x; o.y += rres[i].y; o.z += rres[i].z; o.w += rres[i].w;
                 if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 if (rnd) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
               }
@@ -368,7 +378,7 @@ extern "C" int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long
 
 extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
                                const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
-                               int flags, float* out, void* stream) {
+                               const float* out_mask, float out_mask_mult, int flags, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   QBN_CHECK_ARG(x && w && out, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && Hp > 2 && Wp > 2 && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
@@ -381,7 +391,7 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
     return QBN_ERR_UNSUPPORTED;
   }
   const bool stacked = flags & QBN_FLAG_X_SHARED_STACKED;
-  if (stacked && (n_samples * N > 256 || residual || (flags & QBN_FLAG_OUT_PHASE_SPLIT) || w_shared || stride != 1)) {
+  if (stacked && (n_samples * N > 256 || residual || (flags & QBN_FLAG_OUT_PHASE_SPLIT) || stride != 1)) {
     qbn_set_error("qbn_conv_p4_fwd: sample-stacked mode needs n_samples * N <= 256, stride 1, no residual, normal output (n_samples=%d N=%d)",
                   n_samples, N);
     return QBN_ERR_UNSUPPORTED;
@@ -436,6 +446,7 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   p.w_sample_floats = (long long)p.n_cb * p.taps * p.bt_bytes / 4;
   p.flags = flags; p.w_shared = stacked ? 1 : w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
+  p.out_mask = out_mask; p.out_mask_mult = out_mask_mult;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   p.mg_plane = (uint32_t)(0x100000000ull / (uint64_t)(Hp * Wp));
   p.mg_wp = (uint32_t)(0x100000000ull / (uint64_t)Wp);

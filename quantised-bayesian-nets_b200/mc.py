@@ -22,13 +22,17 @@ from .stochastic.bbb.linear import Linear as BBBLinear
 
 
 class _ConvStep:
-    __slots__ = ("mod", "src", "dst", "bn", "relu", "residual", "ref_idx", "is_linear", "flatten_hw")
+    """conv/linear -> [BN] -> [ReLU (relu_pre)] -> [MC-Dropout of the output] -> [+ residual] -> [ReLU (relu)].
+    det: a plain nn.Conv2d / nn.Linear (MC-Dropout networks) = a Bayesian layer with sigma == 0."""
+    __slots__ = ("mod", "src", "dst", "bn", "relu", "relu_pre", "dropout", "residual", "ref_idx", "is_linear", "flatten_hw", "det")
 
-    def __init__(self, mod, src, dst, ref_idx):
+    def __init__(self, mod, src, dst, ref_idx, det=False):
         self.mod, self.src, self.dst, self.ref_idx = mod, src, dst, ref_idx
-        self.bn, self.relu, self.residual = None, False, None
-        self.is_linear = isinstance(mod, BBBLinear)
+        self.bn, self.relu, self.relu_pre, self.residual = None, False, False, None
+        self.dropout = None            # (p, site layer id, ref_idx of its mask draw)
+        self.is_linear = isinstance(mod, (BBBLinear, nn.Linear))
         self.flatten_hw = False
+        self.det = det
 
 
 class _PoolStep:
@@ -40,6 +44,10 @@ class _PoolStep:
 
 def _is_bbb(m):
     return isinstance(m, (BBBConv2d, BBBLinear))
+
+
+def _is_det(m):
+    return isinstance(m, (nn.Conv2d, nn.Linear)) and not _is_bbb(m)
 
 
 class MCEngine:
@@ -67,8 +75,10 @@ class MCEngine:
         return self._nreg
 
     def _conv(self, mod, src):
-        st = _ConvStep(mod, src, self._new(), self._ref_idx)
-        self._ref_idx += 1
+        det = _is_det(mod)
+        st = _ConvStep(mod, src, self._new(), None if det else self._ref_idx, det)
+        if not det:
+            self._ref_idx += 1          # one noise draw per Bayesian layer per forward (conv.py:34-35)
         self.steps.append(st)
         return st
 
@@ -76,14 +86,21 @@ class MCEngine:
         """Fuse Conv -> [BN] -> [ReLU] runs; returns (last register, last conv step or None)."""
         last = None
         for m in mods:
-            if _is_bbb(m):
+            if _is_bbb(m) or _is_det(m):
                 last = self._conv(m, cur)
                 cur = last.dst
+            elif type(m).__name__ == "BernoulliDropout":
+                if float(m._p) > 0.0:
+                    assert last is not None and last.dropout is None, "MC-Dropout must follow a conv/linear (+BN, +ReLU)"
+                    last.dropout = (float(m._p), m._qbn_layer_id, self._ref_idx)      # one mask draw per site per forward (dropout.py:21-30)
+                    self._ref_idx += 1
+                    if last.relu:                  # conv-BN-ReLU-dropout: the ReLU precedes the mask
+                        last.relu, last.relu_pre = False, True
             elif isinstance(m, nn.BatchNorm2d):
-                assert last is not None and last.bn is None and not last.relu, "BatchNorm must follow a BBB conv"
+                assert last is not None and last.bn is None and not last.relu and last.dropout is None, "BatchNorm must follow a conv"
                 last.bn = m
             elif isinstance(m, nn.ReLU):
-                assert last is not None and not last.relu, "ReLU must follow a BBB layer"
+                assert last is not None and not last.relu and last.dropout is None, "ReLU must follow a conv/linear layer"
                 last.relu = True
             elif isinstance(m, nn.MaxPool2d):
                 assert m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2)), "only 2x2/2 max-pool (models_bbb.py:106-108)"
@@ -145,7 +162,7 @@ class MCEngine:
             if not isinstance(st, _ConvStep):
                 continue
             m = st.mod
-            w, rho = m.weight.detach(), m.std.detach()
+            w, rho = m.weight.detach(), (None if st.det else m.std.detach())
             prep[id(st)] = {"w": w, "rho": rho}
             scale = shift = None
             if st.bn is not None:
@@ -168,6 +185,9 @@ class MCEngine:
             return e[key]
         m = st.mod
         w, rho = e["w"], e["rho"]
+        det = rho is None
+        if det:
+            rho = torch.zeros_like(w)              # placeholder; sigma is forced to exactly 0 below
         if st.is_linear:
             if x.dim() == 4 and (x.shape[2] > 1 or x.shape[3] > 1):
                 C, H, W = x.shape[1], x.shape[2], x.shape[3]
@@ -188,6 +208,8 @@ class MCEngine:
         packed = ops.weight_prep(w4.contiguous(), rho4.contiguous(), False, None, want=("mu", "sigma"))
         if cpad:
             packed["sigma"] = torch.where(packed["sigma"] < 1e-30, torch.zeros_like(packed["sigma"]), packed["sigma"])
+        if det:
+            packed["sigma"] = torch.zeros_like(packed["sigma"])       # W[s] = mu + 0 * eps = mu for every sample
         info = dict(mu=packed["mu"], sigma=packed["sigma"], wshape=tuple(w4.shape), stride=stride, pad=pad, dil=dil, cpad=cpad,
                     orig_shape=tuple(w.shape) if not st.is_linear else (w.shape[0], w4.shape[1] - cpad, w4.shape[2], w4.shape[3]))
         e[key] = info
@@ -363,8 +385,9 @@ class MCEngine:
             e[key] = (mu_b[0], sg_b[0])
         return e[key]
 
-    def _p4_sample_all(self, n, sample0, prep, seed, p4_convs, device):
-        """ONE sampling launch for every planar conv of the chunk (qbn_sample_weights_blocked_multi)."""
+    def _p4_sample_all(self, n, sample0, prep, seed, p4_convs, device, injected=None):
+        """ONE sampling launch for every planar conv of the chunk (qbn_sample_weights_blocked_multi).
+        injected: per-sample lists of noise tensors in the reference's draw order (parity tests) -> eps pointers."""
         import ctypes
         from ._lib import P4SampleJob
         first = self._p4_first
@@ -376,9 +399,10 @@ class MCEngine:
             return self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"), 8 if id(st) == first else 4)
         for st in steps:                       # refresh the blocked parameters of this call (once per call, not per chunk)
             self._p4_weights(st, prep, pinfo(st), st.mod.stride[0])
-        if n not in tables:
+        if n not in tables or injected is not None:
             jobs = (P4SampleJob * len(steps))()
             wbufs, max_fl = {}, 0
+            keep_eps = []
             for i, st in enumerate(steps):
                 info = pinfo(st)
                 N, C, R, S_ = info["wshape"]
@@ -389,14 +413,69 @@ class MCEngine:
                     w = torch.empty((n, mu_b.numel()), dtype=torch.float32, device=device)
                 wbufs[id(st)] = w
                 max_fl = max(max_fl, mu_b.numel())
-                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), None, w.data_ptr(), N, C, R * S_, st.mod.stride[0], st.mod._qbn_layer_id,
-                                      n if stack_ok(st) else 0)
+                eps_ptr = None
+                if injected is not None and not st.det:
+                    es = []
+                    for s_ in range(n):
+                        e_ = injected[s_][st.ref_idx].reshape(info["orig_shape"]).float()
+                        if info["cpad"]:
+                            e_ = torch.nn.functional.pad(e_, (0, 0, 0, 0, 0, info["cpad"]))
+                        es.append(ops.pack_ohwi(e_))
+                    keep_eps.append(torch.stack(es).contiguous())
+                    eps_ptr = keep_eps[-1].data_ptr()
+                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), eps_ptr, w.data_ptr(), N, C, R * S_, st.mod.stride[0],
+                                      getattr(st.mod, "_qbn_layer_id", 0), n if stack_ok(st) else 0)
             raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
-            tables[n] = (raw, len(steps), max_fl, wbufs)
-        raw, n_jobs, max_fl, wbufs = tables[n]
+            entry = (raw, len(steps), max_fl, wbufs)
+            if injected is None:
+                tables[n] = entry
+            else:
+                self._p4_keep = (keep_eps, entry)          # keep the eps tensors alive until the chunk has run
+        else:
+            entry = tables[n]
+        raw, n_jobs, max_fl, wbufs = entry
         ops.sample_weights_blocked_multi(raw, n_jobs, max_fl, n, seed, sample0, True)
         self.launches += 1
         return wbufs
+
+    def _chunk_masks(self, n, B, sample0, seed, injected, device):
+        """MC-Dropout masks of every site for the chunk: {id(step): ([n*B, C] mask, multiplier)}.
+        Philox: one launch for all sites, keyed (seed, site id, GLOBAL sample index); injected: the reference's draws."""
+        sites = [st for st in self.steps if isinstance(st, _ConvStep) and st.dropout is not None]
+        if not sites:
+            return {}
+        from ._lib import MaskJob
+        out = {}
+        if injected is not None:
+            for st in sites:
+                p_, _, ridx = st.dropout
+                m = torch.stack([injected[s_][ridx].float().reshape(B, -1) for s_ in range(n)]).reshape(n * B, -1).contiguous().to(device)
+                out[id(st)] = (m, float(torch.ones(1) / (1.0 - torch.ones(1) * p_)))
+            return out
+        cache = self.__dict__.setdefault("_mask_jobs", {})
+        key = (n, B)
+        if key not in cache:
+            by_p = {}
+            for st in sites:
+                C = st.mod.out_channels if not st.is_linear else st.mod.out_features
+                buf = torch.empty((n * B, C), dtype=torch.float32, device=device)
+                by_p.setdefault(st.dropout[0], []).append((st, buf, C))
+            groups = []
+            for p_, lst in by_p.items():
+                jobs = (MaskJob * len(lst))()
+                for i, (st, buf, C) in enumerate(lst):
+                    jobs[i] = MaskJob(buf.data_ptr(), B * C, st.dropout[1], 0)
+                raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
+                groups.append((p_, raw, len(lst), max(B * c for _, _, c in lst), lst))
+            cache[key] = groups
+        for p_, raw, n_jobs, max_elems, lst in cache[key]:
+            keep = float(torch.ones(1) - torch.ones(1) * p_)           # dropout.py:21: bernoulli_(1. - self.p), fp32
+            ops.dropout_masks_multi(raw, n_jobs, max_elems, n, keep, seed, sample0)
+            self.launches += 1
+            mult = float(torch.ones(1) / (1.0 - torch.ones(1) * p_))    # dropout.py:10
+            for st, buf, C in lst:
+                out[id(st)] = (buf, mult)
+        return out
 
     def _p4_buffer(self, key, n_img, C, Hp, Wp, border, phases, device, zero):
         cache = self.__dict__.setdefault("_bufs", {})
@@ -423,8 +502,10 @@ class MCEngine:
         if p4_convs:
             reg_pad = {r: v for r, v in reg_pad.items() if r not in p4_layout}
         self._p4_presampled = None
-        if p4_convs and injected is None:
-            self._p4_presampled = self._p4_sample_all(n, sample0, prep, noise.seed(), p4_convs, x.device)
+        if p4_convs:
+            self._p4_presampled = self._p4_sample_all(n, sample0, prep, noise.seed(), p4_convs, x.device, injected)
+        masks = self._chunk_masks(n, x.shape[0], sample0, noise.seed(), injected, x.device)
+        pending = {}         # register -> (mask, mult): MC-Dropout applied in the operand load of its consumers (gather / fp32 kernels)
         regs = {0: x}
         shared = {0: True}
         ready = {0: False}   # register holds TF32-exact values (written by a TF32 epilogue with OUT_ROUND_TF32)
@@ -444,6 +525,8 @@ class MCEngine:
                     regs[st.dst] = ops.avgpool_all(src, float(interior)).reshape(src.shape[0], src.shape[1], 1, 1)
                 shared[st.dst] = shared[st.src]
                 ready[st.dst] = ready[st.src] and st.kind == "max"   # max of TF32-exact values is TF32-exact
+                if st.src in pending:      # x*m*c with m in {0,1}, c > 0 commutes with max- and average-pooling
+                    pending[st.dst] = pending[st.src]
                 self.launches += 1
                 continue
             if self._p4_presampled is not None and id(st) in self._p4_presampled and id(st) == self._p4_first:
@@ -459,15 +542,18 @@ class MCEngine:
                 xm = prep["x_p4"]
                 outp = self._p4_buffer(("p4first", si), n * xm.n_img, N, xm.Hp, xm.Wp, (1, 1), 1, src.device, zero=False)
                 e = prep[id(st)]
+                mk, mult = masks.get(id(st), (None, 1.0))
                 ops.conv_p4_forward(xm, self._p4_presampled[id(st)], n, N, R, S_, 1, e["scale"], e["shift"], None, st.relu,
-                                    ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED, False, outp)
+                                    ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED | (ops.QBN_FLAG_RELU_PRE if st.relu_pre else 0),
+                                    False, outp, False, mk, mult)
                 self.launches += 1
                 regs[st.dst] = outp
                 shared[st.dst] = False
                 ready[st.dst] = True
                 continue
             if id(st) in p4_convs:
-                regs[st.dst] = self._run_p4_conv(st, si, src, regs, n, sample0, prep, injected, p4_layout, seed)
+                assert st.src not in pending, "planar conv fed by a register with a pending dropout mask (planner bug)"
+                regs[st.dst] = self._run_p4_conv(st, si, src, regs, n, sample0, prep, injected, p4_layout, seed, masks)
                 self.launches += 1 if self._p4_presampled is not None else 2
                 shared[st.dst] = False
                 ready[st.dst] = True
@@ -485,7 +571,7 @@ class MCEngine:
             N, C, R, S_ = info["wshape"]
             nb = src.shape[0] if shared[st.src] else src.shape[0] // n
             eps = None
-            if injected is not None:
+            if injected is not None and not st.det:
                 es = []
                 for s in range(n):
                     e = injected[s][st.ref_idx].reshape(info["orig_shape"]).float()
@@ -496,8 +582,13 @@ class MCEngine:
             e = prep[id(st)]
             mode = self.math_mode if config.tf32_eligible(C, N, False) else QBN_MATH_FP32
             tf32 = mode == QBN_MATH_TF32
-            w = ops.sample_weights(info["mu"], info["sigma"], n, eps, seed, st.mod._qbn_layer_id, sample0, round_tf32=tf32)
+            w = ops.sample_weights(info["mu"], info["sigma"], n, eps, seed, getattr(st.mod, "_qbn_layer_id", 0), sample0, round_tf32=tf32)
             res = regs[st.residual] if st.residual is not None else None
+            # MC-Dropout on the gather / fp32 kernels: the mask of the producing site rides the operand load of its consumers
+            in_mask, in_mult = pending.get(st.src, (None, 1.0))
+            relu_eff = st.relu or st.relu_pre
+            if st.dropout is not None and (st.residual is not None or st.dst in p4_layout):
+                raise NotImplementedError("MC-Dropout before a residual add needs the planar kernel (epilogue mask)")
             if res is not None and shared.get(st.residual, False):
                 res = res.repeat(n, 1, 1, 1).contiguous(memory_format=ops.CL)   # only if a block reads the raw input
             dpad = reg_pad.get(st.dst, (0, 0))
@@ -510,7 +601,7 @@ class MCEngine:
                 outp = self._p4_buffer(("v1p4", si), n * nb, N, d.Ho + 2 * border[0], d.Wo + 2 * border[1], border, 1, src.device, zero=True)
                 if tf32 and ready[st.src] and not info["cpad"]:
                     flags |= ops.QBN_FLAG_A_TF32_READY
-                ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], None, st.relu, None, 1.0, mode, outp.buf,
+                ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], None, relu_eff, in_mask, in_mult, mode, outp.buf,
                                  flags | ops.QBN_FLAG_OUT_P4)
                 assert res is None
                 self.launches += 2
@@ -519,9 +610,9 @@ class MCEngine:
                 ready[st.dst] = True
                 continue
             s1 = self._s1_eligible(st)
-            if s1 is not None and tf32 and spad == s1 and dpad == s1 and ready[st.src] and not shared[st.src] and not info["cpad"]:
+            if s1 is not None and tf32 and spad == s1 and dpad == s1 and ready[st.src] and not shared[st.src] and not info["cpad"] and in_mask is None:
                 out = self._buffer(("s1", si, n), (src.shape[0], N, src.shape[2], src.shape[3]), src.device, zero=False)
-                ops.conv_s1_forward(src, w, n, N, R, S_, e["scale"], e["shift"], res, st.relu, flags, False, out)
+                ops.conv_s1_forward(src, w, n, N, R, S_, e["scale"], e["shift"], res, relu_eff, flags, False, out)
             else:
                 pad_eff = (info["pad"][0] - spad[0], info["pad"][1] - spad[1])      # reading the interior of a bordered map
                 d = ops.make_desc(nb, src.shape[2], src.shape[3], C, N, R, S_, info["stride"], pad_eff, info["dil"])
@@ -534,17 +625,21 @@ class MCEngine:
                     out = self._buffer(("v1", si, n), (n * nb, N, d.Ho, d.Wo), src.device, zero=False)
                 if tf32 and ready[st.src] and not info["cpad"]:
                     flags |= ops.QBN_FLAG_A_TF32_READY
-                ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, st.relu, None, 1.0, mode, out, flags)
+                ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], res, relu_eff, in_mask, in_mult, mode, out, flags)
             self.launches += 2
             regs[st.dst] = out
             shared[st.dst] = False
             ready[st.dst] = tf32
+            if st.dropout is not None:
+                pending[st.dst] = masks[id(st)]
+        if self.out_reg in pending or (self.regression and (self.head_mu.src in pending)):
+            raise NotImplementedError("MC-Dropout on the network output")
         if self.regression:
             return regs[self.head_mu.dst].reshape(n, B), regs[self.head_lv.dst].reshape(n, B)
         logits = regs[self.out_reg]
         return logits.reshape(n, B, -1)
 
-    def _run_p4_conv(self, st, si, src, regs, n, sample0, prep, injected, p4_layout, seed):
+    def _run_p4_conv(self, st, si, src, regs, n, sample0, prep, injected, p4_layout, seed, masks):
         """One BBB conv on the planar-C4 kernel: blocked sampling launch + qbn_conv_p4_fwd."""
         assert isinstance(src, ops.P4Map), "planar conv fed by a non-planar register (planner bug)"
         m = st.mod
@@ -578,7 +673,9 @@ class MCEngine:
         else:
             out = self._p4_buffer(("p4", si), src.n_img, N, Hp_o, Wp_o, border, 1, src.buf.device, zero=False)
         res = regs[st.residual] if st.residual is not None else None
-        ops.conv_p4_forward(src, w, n, N, R, S_, stride, e["scale"], e["shift"], res, st.relu, ops.QBN_FLAG_OUT_ROUND_TF32, False, out, split)
+        mk, mult = masks.get(id(st), (None, 1.0))
+        ops.conv_p4_forward(src, w, n, N, R, S_, stride, e["scale"], e["shift"], res, st.relu,
+                            ops.QBN_FLAG_OUT_ROUND_TF32 | (ops.QBN_FLAG_RELU_PRE if st.relu_pre else 0), False, out, split, mk, mult)
         return out
 
     @torch.no_grad()

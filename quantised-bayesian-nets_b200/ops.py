@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, I8SampleParams, QBN_FLAG_A_TF32_READY, QBN_FLAG_OUT_P4, QBN_FLAG_OUT_PHASE_SPLIT,  # noqa: F401
-                   QBN_FLAG_X_SHARED_STACKED, QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU, QBN_MATH_FP32, QBN_MATH_TF32)
+                   QBN_FLAG_RELU_PRE, QBN_FLAG_X_SHARED_STACKED, QBN_FLAG_OUT_ROUND_TF32, QBN_FLAG_RELU, QBN_MATH_FP32, QBN_MATH_TF32)
 
 CL = torch.channels_last
 
@@ -552,8 +552,13 @@ def sample_weights_blocked_multi(jobs_dev, n_jobs, max_floats, n_samples, seed, 
     _lib.call("qbn_sample_weights_blocked_multi", _ptr(jobs_dev), n_jobs, max_floats, n_samples, seed, sample0, int(round_tf32), _stream())
 
 
+def dropout_masks_multi(jobs_dev, n_jobs, max_elems, n_samples, keep_prob, seed, sample0):
+    """jobs_dev: uint8 CUDA tensor holding an array of _lib.MaskJob (all dropout sites of a chunk, one launch)."""
+    _lib.call("qbn_dropout_masks_multi", _ptr(jobs_dev), n_jobs, max_elems, n_samples, float(keep_prob), seed, sample0, _stream())
+
+
 def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, residual=None, relu=False, flags=0, w_shared=False,
-                    out=None, phase_split_out=False):
+                    out=None, phase_split_out=False, out_mask=None, out_mask_mult=1.0):
     """qbn_conv_p4_fwd.  x: P4Map (phase-split when stride == 2); w: blocked sampled weights [n_samples, ...];
     residual: P4Map with the output geometry.  Returns a P4Map."""
     stacked = bool(int(flags) & QBN_FLAG_X_SHARED_STACKED)
@@ -570,7 +575,7 @@ def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, 
             out = P4Map.empty(n_out, N, x.Hp, x.Wp, border, 1, x.buf.device)
     fl = int(bool(relu)) | int(flags) | (QBN_FLAG_OUT_PHASE_SPLIT if phase_split_out else 0)
     _lib.call("qbn_conv_p4_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, stride, _ptr(x.buf), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
-              _ptr(residual.buf if residual is not None else None), fl, _ptr(out.buf), _stream())
+              _ptr(residual.buf if residual is not None else None), _ptr(out_mask), float(out_mask_mult), fl, _ptr(out.buf), _stream())
     return out
 
 

@@ -258,6 +258,23 @@ class ConvNetwork_ResNet_MC(nn.Module):
         return F.softmax(x, dim=-1)
 
 
+class ConvNetwork_LeNet_MC(nn.Module):
+    """models_mc.py:75-110: conv5x5-dropout-pool, conv5x5-dropout-pool, fc-relu-dropout-fc (config 2)."""
+
+    def __init__(self, input_size, output_size, q, args):
+        super().__init__()
+        self.args = args
+        self.layers = nn.ModuleList([
+            nn.Conv2d(input_size[0], 20, 5, padding=2, bias=False), BernoulliDropout(args.p), nn.MaxPool2d(2, 2),
+            nn.Conv2d(20, 50, 5, padding=2, bias=False), BernoulliDropout(args.p), nn.MaxPool2d(2, 2),
+            Flatten(), nn.Linear(50 * 7 * 7, 500, bias=False), nn.ReLU(), BernoulliDropout(args.p), nn.Linear(500, output_size, bias=False)])
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return F.softmax(x, dim=-1)
+
+
 # ---- loaders from seed-generated parameter containers (duck-typed: .convs/.bns/.fc/.blocks etc.) ----
 def resnet_from_params(P, n_classes=10, args=None):
     args = args or Args(sigma_prior=0.05, model="conv_resnet_bbb")
@@ -288,5 +305,26 @@ def mlp_from_params(P, args=None):
     sd = net.state_dict()
     for name, (mu, rho, b) in P.layers.items():
         sd[name + ".weight"], sd[name + ".std"], sd[name + ".bias"] = mu, rho, b
+    net.load_state_dict(sd)
+    return net
+
+
+def resnet_mc_from_params(P, p=0.15, n_classes=10, state_dict=None):
+    """MC-Dropout ResNet (models_mc.py) with the mu tensors of a ResNetBBBParams container as its weights;
+    `state_dict`: entries under the reference's module names (oracle.qbn_oracle.resnet_mc_state_dict)."""
+    args = Args(p=p, model="conv_resnet_mc")
+    net = ConvNetwork_ResNet_MC([1, P.convs["layers.0"][0].shape[1], 32, 32], n_classes, False, args)
+    sd = net.state_dict()
+    sd.update(state_dict)
+    net.load_state_dict(sd)
+    return net
+
+
+def lenet_mc_from_params(P, p=0.2, n_classes=10):
+    args = Args(p=p, model="conv_lenet_mc")
+    net = ConvNetwork_LeNet_MC([P.layers["layers.0"][0].shape[1], 1, 28, 28], n_classes, False, args)
+    sd = net.state_dict()
+    for ref_name, key in (("layers.0", "layers.0"), ("layers.3", "layers.2"), ("layers.7", "layers.5"), ("layers.10", "layers.7")):
+        sd[ref_name + ".weight"] = P.layers[key][0]
     net.load_state_dict(sd)
     return net

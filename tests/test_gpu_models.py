@@ -198,3 +198,64 @@ def test_full_size_properties_batch256():
     torch.manual_seed(0)
     ref = O.resnet_bbb_mc_predict(P, x[:8].cpu(), 20)
     assert float(((s20[:8] / 20).cpu() - ref).abs().max()) < 0.25
+
+
+# ---- MC-Dropout networks (configs 2 and 5): deterministic weights, masks per (image, channel) -------------------
+def _mc_masks(plan, seed, p):
+    return O.replay_masks(seed, [sh for _, sh in plan], p)
+
+
+def test_resnet_mc_dropout_modules_and_engine(golden):
+    """models_mc.py ResNet: (a) the drop-in modules with replayed masks, (b) the MC engine on the planar kernel with the
+    masks fused into the producing epilogues, both against the reference's seeded forwards."""
+    from qbn_b200 import mc, noise, zoo
+    g = golden("resnet_mc")
+    P = O.ResNetBBBParams(seed=51)
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(52)).cuda()
+    net = zoo.resnet_mc_from_params(P, 0.15, state_dict=O.resnet_mc_state_dict(P)).cuda().eval()
+    plan = O.resnet_mc_mask_plan(P, 4)
+    masks = [_mc_masks(plan, 1100 + s, 0.15) for s in range(2)]
+    for s in range(2):
+        with noise.inject([m.cuda() for m in masks[s]]), torch.no_grad():
+            y = net(x)
+        close(y, g["y%d" % s], 2e-3, 1e-4)        # torch's own conv runs TF32-free fp32 (cuDNN), dropout on libqbn
+    eng = mc.MCEngine(net, math_mode="tf32", chunk=2)
+    assert eng.n_noise == len(plan)
+    psum = eng.predict_sum(x, 2, injected=[[m.cuda() for m in masks[s]] for s in range(2)])
+    ref = torch.as_tensor(g["y0"]) + torch.as_tensor(g["y1"])
+    close(psum, ref, 5e-3, 5e-4)
+    # one sample at a time (chunk boundaries do not matter)
+    eng1 = mc.MCEngine(net, math_mode="tf32", chunk=1)
+    close(eng1.predict_sum(x, 2, injected=[[m.cuda() for m in masks[s]] for s in range(2)]), psum, 1e-6, 1e-7)
+    # Philox masks: sharding by global sample index reproduces the unsharded sum
+    noise.manual_seed(77)
+    a = mc.MCEngine(net, math_mode="tf32", chunk=3).predict_sum(x, 6, sample0=0)
+    b = mc.MCEngine(net, math_mode="tf32", chunk=2)
+    b = b.predict_sum(x, 2, sample0=0) + b.predict_sum(x, 4, sample0=2)
+    close(a, b, 1e-5, 1e-6)
+    assert float(a.sum()) == pytest.approx(6 * 4, rel=1e-4)
+    # the masks matter (different seeds differ) and keep ~1-p of the channels
+    noise.manual_seed(78)
+    c = mc.MCEngine(net, math_mode="tf32", chunk=3).predict_sum(x, 6, sample0=0)
+    assert not torch.allclose(a, c)
+
+
+@pytest.mark.parametrize("mode,rtol", [("fp32", 1e-4), ("tf32", 3e-3)])
+def test_lenet_mc_dropout_engine(golden, mode, rtol):
+    """Config 2: conv5x5-dropout-pool x2, fc-relu-dropout-fc; the masks ride the operand load of the consuming layer."""
+    from qbn_b200 import mc, noise, zoo
+    g = golden("lenet_mc")
+    P = O.LeNetBBBParams(seed=61)
+    x = torch.rand(4, 1, 28, 28, generator=torch.Generator().manual_seed(62)).cuda()
+    net = zoo.lenet_mc_from_params(P, 0.2).cuda().eval()
+    shapes = [(4, 20), (4, 50), (4, 500)]
+    masks = [O.replay_masks(1200 + s, shapes, 0.2) for s in range(2)]
+    with noise.inject([m.cuda() for m in masks[0]]), torch.no_grad():
+        close(net(x), g["y0"], 2e-3, 1e-4)
+    eng = mc.MCEngine(net, math_mode=mode, chunk=2)
+    psum = eng.predict_sum(x, 2, injected=[[m.cuda() for m in masks[s]] for s in range(2)])
+    close(psum, torch.as_tensor(g["y0"]) + torch.as_tensor(g["y1"]), rtol, rtol * 0.1)
+    noise.manual_seed(5)
+    a = mc.MCEngine(net, math_mode=mode, chunk=4).predict_sum(x, 8)
+    e2 = mc.MCEngine(net, math_mode=mode, chunk=3)
+    close(a, e2.predict_sum(x, 3, sample0=0) + e2.predict_sum(x, 5, sample0=3), 1e-5, 1e-6)

@@ -243,3 +243,37 @@ def test_p4_multi_layer_sampler():
     ops.sample_weights_blocked_multi(raw, len(layers), max(k[0].numel() for k in keep), S, 77, 3, True)
     for (mu_b, sg_b, w), ref in zip(keep, want):
         assert torch.equal(w, ref)
+
+
+def test_p4_conv_output_dropout_mask():
+    """Epilogue order affine -> ReLU(pre) -> mask*mult -> +residual -> ReLU(post): the MC-Dropout BasicBlock of models_mc.py."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(91)
+    S, B, C, N, H = 2, 3, 24, 24, 8
+    x = _tf32_round_(torch.randn(S * B, C, H, H, generator=g).cuda())
+    w = _rand_weights(g, 1, N, 3, C)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    res = torch.randn(S * B, N, H, H, generator=g).cuda()
+    mask = (torch.rand(S * B, N, generator=g) < 0.8).float().cuda()
+    mult = 1.0 / 0.85
+    conv = torch.nn.functional.conv2d(x.double(), w.reshape(N, 3, 3, C).permute(0, 3, 1, 2).double(), None, 1, 1)
+    aff = conv * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    m4 = mask.double().view(S * B, N, 1, 1)
+    xb, rb, wb = ops.P4Map.from_nchw(x, (1, 1)), ops.P4Map.from_nchw(res, (1, 1)), ops.p4_block_weights(w, N, C, 9)
+    # conv-BN-ReLU-dropout
+    got = ops.conv_p4_forward(xb, wb, S, N, 3, 3, 1, scale, shift, None, False, ops.QBN_FLAG_RELU_PRE, True, None, False, mask, mult)
+    close(got.to_nchw(), (aff.clamp(min=0) * m4 * mult).float(), 1e-3, 1e-3)
+    # conv-BN-dropout-add-ReLU
+    got = ops.conv_p4_forward(xb, wb, S, N, 3, 3, 1, scale, shift, rb, True, 0, True, None, False, mask, mult)
+    close(got.to_nchw(), ((aff * m4 * mult + res.double()).clamp(min=0)).float(), 1e-3, 1e-3)
+    # first layer, shared input, per-sample masks on identical (stacked) weights
+    x1 = _tf32_round_(torch.randn(B, 8, H, H, generator=g).cuda())
+    w1 = _rand_weights(g, 1, N, 3, 8)
+    wst = _stack_blocked(ops.p4_block_weights(w1, N, 8, 9).repeat(S, 1), N, 32, S)
+    got = ops.conv_p4_forward(ops.P4Map.from_nchw(x1, (1, 1)), wst, S, N, 3, 3, 1, scale, shift, None, False,
+                              ops.QBN_FLAG_RELU_PRE | ops.QBN_FLAG_X_SHARED_STACKED, False, None, False, mask, mult)
+    conv1 = torch.nn.functional.conv2d(x1.double(), w1.reshape(N, 3, 3, 8).permute(0, 3, 1, 2).double(), None, 1, 1)
+    aff1 = (conv1 * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)).clamp(min=0)
+    ref = (aff1.unsqueeze(0) * mask.double().view(S, B, N, 1, 1) * mult).reshape(S * B, N, H, H)
+    close(got.to_nchw(), ref.float(), 1e-3, 1e-3)

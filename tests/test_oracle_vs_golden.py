@@ -166,3 +166,23 @@ def test_lenet_and_mlp_eval(golden):
     mu, var = O.mlp_bbb_eval_forward(P, x, _eps_fn_from(noise))
     close(mu, g["y_mu"], 1e-4, 1e-6)
     close(var, g["y_var"], 1e-4, 1e-6)
+
+
+def test_mc_dropout_networks(golden):
+    """models_mc.py ResNet / LeNet restatements + the mask replay order against the reference's seeded forwards."""
+    g = golden("resnet_mc")
+    P = O.ResNetBBBParams(seed=51)
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(52))
+    plan = O.resnet_mc_mask_plan(P, 4)
+    for s in range(2):
+        masks = dict(zip([n for n, _ in plan], O.replay_masks(1100 + s, [sh for _, sh in plan], 0.15)))
+        y = O.resnet_mc_forward(P, x, lambda name, shape: masks[name], 0.15)
+        np.testing.assert_allclose(y.numpy(), g["y%d" % s], rtol=1e-5, atol=1e-7)
+    g = golden("lenet_mc")
+    P = O.LeNetBBBParams(seed=61)
+    x = torch.rand(4, 1, 28, 28, generator=torch.Generator().manual_seed(62))
+    shapes = [("layers.1", (4, 20)), ("layers.4", (4, 50)), ("layers.9", (4, 500))]
+    for s in range(2):
+        masks = dict(zip([n for n, _ in shapes], O.replay_masks(1200 + s, [sh for _, sh in shapes], 0.2)))
+        y = O.lenet_mc_forward(P, x, lambda name, shape: masks[name], 0.2)
+        np.testing.assert_allclose(y.numpy(), g["y%d" % s], rtol=1e-5, atol=1e-7)
