@@ -76,8 +76,8 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
   if (r >= d) { ++q; r -= d; }
 }
 
-template <int DBG_MODE, bool STACKED>
-__global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
+template <int DBG_MODE, bool STACKED, bool MASKED>
+__global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting
   const int dbg = DBG_MODE == 2 ? p.dbg : 0;              // ablation knobs (QBN_P4_DBG): 1 no stores, 2 one MMA per tile, 4 no A copies, 8 no TMEM loads
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
       }
       float* optr = p.out + (store ? orow : 0) * 4;
       // dropout mask row of this pixel's image (stacked: sample sidx of the shared input adds sidx * B images)
-      const float* mrow = (p.out_mask && interior) ? p.out_mask + (size_t)(z * p.B + (int)b) * p.N : nullptr;
+      const float* mrow = (MASKED && p.out_mask && interior) ? p.out_mask + (size_t)(z * p.B + (int)b) * p.N : nullptr;
       const float* rptr = (p.residual && interior) ? p.residual + in_row * 4 : nullptr;
       float4 rres[4], rnext[4];
       uint32_t v[16], vn[16];
@@ -318,17 +318,24 @@ __global__ void __launch_bounds__(P4_THREADS) umma_conv_p4_kernel(const __grid_c
               if (interior) {
                 const float4 sc = *reinterpret_cast<const float4*>(&s_scale[jc * 4]);
                 const float4 sh = *reinterpret_cast<const float4*>(&s_shift[jc * 4]);
-                o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x);
-                o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
-                o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
-                o.w = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
-                if (relu_pre) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                if (mrow) {     // x = mul(x, mask); x = mul_scalar(x, multiplier): two roundings like the reference
-                  const float4 mk = *reinterpret_cast<const float4*>(mrow + (STACKED ? (size_t)sidx * p.B * p.N : (size_t)0) + jc * 4);
-                  o.x = __fmul_rn(__fmul_rn(o.x, mk.x), p.out_mask_mult); o.y = __fmul_rn(__fmul_rn(o.y, mk.y), p.out_mask_mult);
-                  o.z = __fmul_rn(__fmul_rn(o.z, mk.z), p.out_mask_mult); o.w = __fmul_rn(__fmul_rn(o.w, mk.w), p.out_mask_mult);
+                if (MASKED) {   // general order: affine -> ReLU(pre) -> mask*mult -> +residual
+                  o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x);
+                  o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
+                  o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
+                  o.w = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
+                  if (relu_pre) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                  if (mrow) {     // x = mul(x, mask); x = mul_scalar(x, multiplier): two roundings like the reference
+                    const float4 mk = *reinterpret_cast<const float4*>(mrow + (STACKED ? (size_t)sidx * p.B * p.N : (size_t)0) + jc * 4);
+                    o.x = __fmul_rn(__fmul_rn(o.x, mk.x), p.out_mask_mult); o.y = __fmul_rn(__fmul_rn(o.y, mk.y), p.out_mask_mult);
+                    o.z = __fmul_rn(__fmul_rn(o.z, mk.z), p.out_mask_mult); o.w = __fmul_rn(__fmul_rn(o.w, mk.w), p.out_mask_mult);
+                  }
+                  o.x += rres[i].x; o.y += rres[i].y; o.z += rres[i].z; o.w += rres[i].w;
+                } else {
+                  o.x = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x) + rres[i].x;
+                  o.y = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y) + rres[i].y;
+                  o.z = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z) + rres[i].z;
+                  o.w = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w) + rres[i].w;
                 }
-                o.x += rres[i].x; o.y += rres[i].y; o.z += rres[i].z; o.w += rres[i].w;
                 if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 if (rnd) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
               }
@@ -518,10 +525,12 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
@@ -532,15 +541,23 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   if (getenv("QBN_P4_VERBOSE"))
     fprintf(stderr, "[p4] C=%d N=%d %dx%d k%d s%d: tiles=%d grid=%d occ=%d SA=%d SB=%d TG=%d ACC=%d b_res=%d smem=%zu a_bytes=%u bt=%u tmem=%d\n", C, N, Hp,
             Wp, R, stride, p.total_tiles, grid, occ, p.SA, p.SB, p.TG, p.ACC, p.b_res, smem, p.a_bytes, p.bt_bytes, p.tmem_cols);
-  if (stacked) {
-    umma_conv_p4_kernel<0, true><<<grid, P4_THREADS, smem, st>>>(p);
+  // the general epilogue order (pre-ReLU, output mask) is a separate instantiation: the plain one keeps its fused fma + residual
+  bool masked = out_mask != nullptr;
+  if (!masked && (p.flags & QBN_FLAG_RELU_PRE)) {
+    if (residual) masked = true;                                  // ReLU before the residual add: general order
+    else p.flags = (p.flags & ~QBN_FLAG_RELU_PRE) | QBN_FLAG_RELU;  // no mask, no residual: pre == post
+  }
+  if (stacked || masked) {
+    if (stacked && masked) umma_conv_p4_kernel<0, true, true><<<grid, P4_THREADS, smem, st>>>(p);
+    else if (stacked) umma_conv_p4_kernel<0, true, false><<<grid, P4_THREADS, smem, st>>>(p);
+    else umma_conv_p4_kernel<0, false, true><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
   if (getenv("QBN_P4_PROF")) {
     unsigned long long h[32] = {0};
     cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
-    umma_conv_p4_kernel<1, false><<<grid, P4_THREADS, smem, st>>>(p);
+    umma_conv_p4_kernel<1, false, false><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     cudaStreamSynchronize(st);
     cudaMemcpyFromSymbol(h, g_p4_prof, sizeof(h));
@@ -554,11 +571,11 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   }
   if (getenv("QBN_P4_DBG")) {
     p.dbg = atoi(getenv("QBN_P4_DBG"));
-    umma_conv_p4_kernel<2, false><<<grid, P4_THREADS, smem, st>>>(p);
+    umma_conv_p4_kernel<2, false, false><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
-  umma_conv_p4_kernel<0, false><<<grid, P4_THREADS, smem, st>>>(p);
+  umma_conv_p4_kernel<0, false, false><<<grid, P4_THREADS, smem, st>>>(p);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
