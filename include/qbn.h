@@ -154,7 +154,7 @@ int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, i
  * out / residual: planar C4 [N/4][n_samples*B*Hp*Wp][4]; border rows of out are written as zeros. */
 int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long long* out_floats /* host */);
 int qbn_p4_block_weights(const float* w_ohwi /* [n_mats][N][taps][C] */, int n_mats, int N, int C, int taps,
-                         int stride, float* out, void* stream);
+                         int stride, int cb_override /* 0: layout rule */, float* out, void* stream);
 int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_b, int N, int C, int taps, int stride, int n_samples,
                                const float* eps /* nullable, canonical [n_samples][N][taps][C] */, uint64_t seed,
                                uint32_t layer_id, uint32_t sample0, float* w, int round_tf32, void* stream);
@@ -163,6 +163,9 @@ typedef struct qbn_p4_sample_job {
   const float* mu_b; const float* sigma_b; const float* eps /* nullable */; float* w;
   int32_t N, C, taps, stride; uint32_t layer_id;
   int32_t n_stack;   /* > 0: write the n_stack samples stacked along N (row s*N + n of ONE blocked tensor, QBN_FLAG_X_SHARED_STACKED) */
+  const float* chan_scale; /* nullable [N]: W[n][.] *= chan_scale[n] before rounding (BatchNorm scale folded into the weights) */
+  int32_t cb_override;     /* > 0: channels per block (qbn_p4_shortcut_block_channels) instead of the layout rule */
+  int32_t w_sample_stride4;/* > 0: float4 units between consecutive samples in w (several jobs filling one tensor) */
 } qbn_p4_sample_job;
 int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
                                      uint64_t seed, uint32_t sample0, int round_tf32, void* stream);
@@ -172,6 +175,14 @@ int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, i
                     const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
                     const float* out_mask /* nullable [n_samples*B][N] */, float out_mask_mult, int flags, float* out,
                     void* stream);
+/* Stride-1 conv with the BasicBlock's 1x1 stride-2 shortcut FUSED as extra K blocks (models_bbb.py:163-178):
+ *   out = act( conv_RxS(x, W) + conv_1x1,stride2(x_block, Wsc) + shift ),  W and Wsc carrying their BatchNorm scales
+ * (qbn_p4_sample_job.chan_scale), so both branches accumulate in ONE TMEM tile: no shortcut launch, no residual round trip.
+ * x2 = the block input, phase-split (its phase (0,0) IS the stride-2 sampling grid), C2 channels; every sample's weight tensor
+ * is [main blocks][shortcut blocks of qbn_p4_shortcut_block_channels(C, C2) channels, one tap]. */
+int qbn_p4_shortcut_block_channels(int C, int C2);
+int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x, const float* w,
+                             const float* x2, int C2, const float* scale, const float* shift, int flags, float* out, void* stream);
 /* Bernoulli(keep) masks of several dropout sites in ONE launch: jobs_dev = device array of qbn_mask_job; the mask of
  * site j, sample s is out[j][s][elems], Philox(seed, site_id, sample0 + s, element) */
 typedef struct qbn_mask_job { float* out; int64_t elems; uint32_t site_id; int32_t pad_; } qbn_mask_job;

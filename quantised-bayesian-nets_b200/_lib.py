@@ -26,7 +26,8 @@ class ConvDesc(Structure):
 
 class P4SampleJob(Structure):
     _fields_ = [("mu_b", c_void_p), ("sigma_b", c_void_p), ("eps", c_void_p), ("w", c_void_p), ("N", c_int32), ("C", c_int32),
-                ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("n_stack", c_int32)]
+                ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("n_stack", c_int32), ("chan_scale", c_void_p),
+                ("cb_override", c_int32), ("w_sample_stride4", c_int32)]
 
 
 class MaskJob(Structure):
@@ -79,10 +80,12 @@ _SIGNATURES = {
     "qbn_conv_s1_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
     "qbn_nchw_to_nhwc": (c_int, [P, c_int64, c_int, c_int, P, P]),
     "qbn_p4_weight_floats": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_longlong)]),
-    "qbn_p4_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "qbn_p4_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "qbn_sample_weights_blocked": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, c_uint64, c_uint32, c_uint32, P, c_int, P]),
     "qbn_sample_weights_blocked_multi": (c_int, [P, c_int, c_int64, c_int, c_uint64, c_uint32, c_int, P]),
     "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, c_float, c_int, P, P]),
+    "qbn_p4_shortcut_block_channels": (c_int, [c_int, c_int]),
+    "qbn_conv_p4_shortcut_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P, P]),
     "qbn_dropout_masks_multi": (c_int, [P, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, P]),
     "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
 }

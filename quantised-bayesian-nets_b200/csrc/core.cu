@@ -719,8 +719,9 @@ extern "C" int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float*
 #include "p4_layout.cuh"
 
 struct P4Block { int N, C, taps, CB, cbc, n_pad, K; int64_t total4; };
-static bool p4_block_geom(int N, int C, int taps, int stride, P4Block& g) {
-  g.N = N; g.C = C; g.taps = taps; g.CB = qbn_p4_block_channels(C, stride, taps);
+static bool p4_block_geom(int N, int C, int taps, int stride, P4Block& g, int cb_override = 0) {
+  g.N = N; g.C = C; g.taps = taps; g.CB = cb_override > 0 ? cb_override : qbn_p4_block_channels(C, stride, taps);
+  if (g.CB > 0 && (C % g.CB != 0 || g.CB % 8 != 0)) return false;
   if (C % 8 != 0 || g.CB == 0 || N > 256 || N <= 0 || taps <= 0) return false;
   g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(N); g.K = taps * C;
   g.total4 = (int64_t)(C / g.CB) * taps * g.cbc * g.n_pad;
@@ -746,10 +747,11 @@ __global__ void p4_block_weights_kernel(const float* __restrict__ w, P4Block g, 
     os[i] = idx < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(ws + idx);
   }
 }
-extern "C" int qbn_p4_block_weights(const float* w_ohwi, int n_mats, int N, int C, int taps, int stride, float* out, void* stream) {
+extern "C" int qbn_p4_block_weights(const float* w_ohwi, int n_mats, int N, int C, int taps, int stride, int cb_override, float* out,
+                                    void* stream) {
   QBN_CHECK_ARG(w_ohwi && out && n_mats > 0 && n_mats <= 65535, "args");
   P4Block g;
-  if (!p4_block_geom(N, C, taps, stride, g)) {
+  if (!p4_block_geom(N, C, taps, stride, g, cb_override)) {
     qbn_set_error("qbn_p4_block_weights: needs C %% 8 == 0 and N <= 256 (C=%d N=%d)", C, N);
     return QBN_ERR_UNSUPPORTED;
   }
@@ -852,19 +854,21 @@ extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, floa
 struct qbn_p4_sample_job_dev {
   const float* mu_b; const float* sigma_b; const float* eps; float* w;
   int N, C, taps, stride; uint32_t layer_id; int n_stack;
+  const float* chan_scale; int cb_override; int w_sample_stride4;
 };
 __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev* __restrict__ jobs, uint64_t seed, uint32_t sample0,
                                                     int round_tf32) {
   const qbn_p4_sample_job_dev jb = jobs[blockIdx.z];
   P4Block g;
   g.N = jb.N; g.C = jb.C; g.taps = jb.taps;
-  g.CB = qbn_p4_block_channels(jb.C, jb.stride, jb.taps);
+  g.CB = jb.cb_override > 0 ? jb.cb_override : qbn_p4_block_channels(jb.C, jb.stride, jb.taps);
   g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(jb.N); g.K = jb.taps * jb.C;
   g.total4 = (int64_t)(jb.C / g.CB) * jb.taps * g.cbc * g.n_pad;
   const int s = blockIdx.y;
   // stacked: ONE blocked tensor of n_stack*N rows; this sample fills rows [s*N, (s+1)*N) of every (cb, tap, chunk) column
   const int n_pad_out = jb.n_stack > 0 ? qbn_p4_n_pad(jb.n_stack * jb.N) : g.n_pad;
-  float4* ws = reinterpret_cast<float4*>(jb.w) + (jb.n_stack > 0 ? (int64_t)s * g.N : (int64_t)s * g.total4);
+  float4* ws = reinterpret_cast<float4*>(jb.w) +
+               (jb.n_stack > 0 ? (int64_t)s * g.N : (int64_t)s * (jb.w_sample_stride4 > 0 ? (int64_t)jb.w_sample_stride4 : g.total4));
   const float* es = jb.eps ? jb.eps + (int64_t)s * g.N * g.K : nullptr;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t idx = p4_canonical(g, i);
@@ -884,6 +888,10 @@ __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev*
       o.y = __fadd_rn(m.y, __fmul_rn(z[1], sg.y));
       o.z = __fadd_rn(m.z, __fmul_rn(z[2], sg.z));
       o.w = __fadd_rn(m.w, __fmul_rn(z[3], sg.w));
+      if (jb.chan_scale) {     // eval BatchNorm scale folded into the sampled weights (two branches share one accumulator)
+        const float cs = jb.chan_scale[(int)(i % g.n_pad)];
+        o.x *= cs; o.y *= cs; o.z *= cs; o.w *= cs;
+      }
       if (round_tf32) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
     }
     const int64_t col = i / g.n_pad;                         // (cb, tap, chunk) column, row n = i % n_pad

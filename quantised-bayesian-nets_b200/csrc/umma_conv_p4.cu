@@ -44,6 +44,9 @@ struct P4Params {
   long long q2_total;
   int tap_off[MAX_TAPS];          // 16-byte units inside an A slot: strip * cbc * RA_p + d_before + shift
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; float* out;
+  // fused 1x1 stride-2 shortcut (models_bbb.py:163-166): a second input (phase (0,0) of the block input) accumulated into the
+  // same tile by n_cb2 extra channel blocks of one tap; its weight blocks follow the main ones in every sample's weight tensor
+  const float* x2; long long x2_plane; int n_cb2, cbc2, nk2; uint32_t bt2_bytes;
   const float* out_mask; float out_mask_mult;     // A8: MC-Dropout of the OUTPUT, mask [n_img][N] (dropout.py:35-39)
 };
 
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         PROF_BEGIN();
         if (p.b_res && z != cur_z) {
           mbar_wait(smem_u32(&b_empty[0]), pb ^ 1);          // MMAs of the previous sample have retired
-          const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * p.taps);
+          const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * p.taps) + p.bt2_bytes * (uint32_t)p.n_cb2;
           mbar_arrive_expect_tx(smem_u32(&b_full[0]), total);
           for (uint32_t off = 0; off < total; off += 32768u)
             bulk_load_g2s(smem_u32(b_ring) + off, reinterpret_cast<const uint8_t*>(ws) + off, min(32768u, total - off), smem_u32(&b_full[0]));
@@ -167,6 +170,29 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
               bulk_load_g2s(smem_u32(b_ring + (size_t)sb * p.b_slot_bytes), wb + (size_t)t0 * p.bt_bytes, bytes, smem_u32(&b_full[sb]));
               if (++sb == p.SB) { sb = 0; pb ^= 1; }
               PROF_ADD(20);
+            }
+          }
+        }
+        // ---- fused shortcut: rows [q0, q0+128) of the second input, no halo, one tap
+        if (p.n_cb2) {
+          const long long r0 = (long long)z * p.Qs + q0;
+          const long long r1 = (r0 + TM > p.strip_rows) ? p.strip_rows : r0 + TM;
+          const uint32_t rb2 = (uint32_t)(r1 - r0) * 16;
+          for (int cb = 0; cb < p.n_cb2; ++cb) {
+            mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
+            const uint32_t bar = smem_u32(&a_full[sa]);
+            mbar_arrive_expect_tx(bar, rb2 * (uint32_t)p.cbc2);
+            const uint32_t slot = smem_u32(a_ring + (size_t)sa * p.a_bytes);
+            const float* src = p.x2 + ((size_t)(cb * p.cbc2) * p.x2_plane + r0) * 4;
+            for (int j = 0; j < p.cbc2; ++j)
+              bulk_load_g2s(slot + (uint32_t)(j * TM) * 16, src + (size_t)j * p.x2_plane * 4, rb2, bar);
+            if (++sa == p.SA) { sa = 0; pa ^= 1; }
+            if (!p.b_res) {
+              const uint8_t* wb = reinterpret_cast<const uint8_t*>(ws) + (size_t)p.n_cb * p.taps * p.bt_bytes + (size_t)cb * p.bt2_bytes;
+              mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
+              mbar_arrive_expect_tx(smem_u32(&b_full[sb]), p.bt2_bytes);
+              bulk_load_g2s(smem_u32(b_ring + (size_t)sb * p.b_slot_bytes), wb, p.bt2_bytes, smem_u32(&b_full[sb]));
+              if (++sb == p.SB) { sb = 0; pb ^= 1; }
             }
           }
         }
@@ -230,6 +256,32 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
               if (++sb == p.SB) { sb = 0; pb ^= 1; }
             }
             PROF_ADD(12);
+          }
+          umma_commit(smem_u32(&a_empty[sa]));
+          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+        }
+        for (int cb = 0; cb < p.n_cb2; ++cb) {              // fused shortcut blocks: one tap at row 0 of the slot
+          mbar_wait(smem_u32(&a_full[sa]), pa);
+          tc_fence_after();
+          uint32_t ad = smem_u32(a_ring + (size_t)sa * p.a_bytes) >> 4;
+          uint32_t bd;
+          if (p.b_res) {
+            bd = (smem_u32(b_ring) >> 4) + (uint32_t)(p.n_cb * p.taps) * bt16 + (uint32_t)cb * (p.bt2_bytes >> 4);
+          } else {
+            mbar_wait(smem_u32(&b_full[sb]), pb);
+            tc_fence_after();
+            bd = smem_u32(b_ring + (size_t)sb * p.b_slot_bytes) >> 4;
+          }
+          const uint64_t adesc2_hi = make_smem_desc(0, TM * 16, 128);      // chunk planes of 128 rows, no halo
+#pragma unroll 1
+          for (int jj = 0; jj < p.nk2; ++jj) {
+            umma_mma<MODE_EVAL>(tacc, adesc2_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
+            accum = 1;
+            ad += (2 * TM * 16) >> 4; bd += b_k;
+          }
+          if (!p.b_res) {
+            umma_commit(smem_u32(&b_empty[sb]));
+            if (++sb == p.SB) { sb = 0; pb ^= 1; }
           }
           umma_commit(smem_u32(&a_empty[sa]));
           if (++sa == p.SA) { sa = 0; pa ^= 1; }
@@ -383,9 +435,44 @@ extern "C" int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long
   return QBN_OK;
 }
 
+static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
+                          int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
+                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, void* stream);
+
 extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
                                const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
                                const float* out_mask, float out_mask_mult, int flags, float* out, void* stream) {
+  return conv_p4_launch(n_samples, B, Hp, Wp, C, N, R, S, stride, x, w, w_shared, scale, shift, residual, out_mask, out_mask_mult, flags, out,
+                        nullptr, 0, 0, stream);
+}
+
+// channels per block of the fused shortcut input: largest multiple of 8 dividing C2 that fits the main conv's activation slot
+// (geometry-free rule, shared with the sampler: at most the main conv's block, so the slots — and the occupancy — stay the
+// same; a bigger shortcut block was measured slower on the 48-channel layer: it costs the second CTA per SM)
+static int p4_shortcut_block(int C, int C2) {
+  const int cb_main = qbn_p4_block_channels(C, 1, 9);
+  const int cap = cb_main;
+  for (int cb = (C2 < cap ? C2 : cap) / 8 * 8; cb >= 8; cb -= 8)
+    if (C2 % cb == 0) return cb;
+  return 0;
+}
+extern "C" int qbn_p4_shortcut_block_channels(int C, int C2) { return p4_shortcut_block(C, C2); }
+
+extern "C" int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x, const float* w,
+                                        const float* x2, int C2, const float* scale, const float* shift, int flags, float* out,
+                                        void* stream) {
+  QBN_CHECK_ARG(x2 && C2 > 0 && C2 % 8 == 0, "second input");
+  const int cb2 = p4_shortcut_block(C, C2);
+  if (cb2 == 0) {
+    qbn_set_error("qbn_conv_p4_shortcut_fwd: no channel blocking for C2=%d", C2);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  return conv_p4_launch(n_samples, B, Hp, Wp, C, N, R, S, 1, x, w, 0, scale, shift, nullptr, nullptr, 1.0f, flags, out, x2, C2, cb2, stream);
+}
+
+static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
+                          int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
+                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   QBN_CHECK_ARG(x && w && out, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && Hp > 2 && Wp > 2 && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
@@ -450,7 +537,16 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
     }
   p.a_bytes = (uint32_t)p.n_strips * p.cbc * p.RA_p * 16;
   p.bt_bytes = (uint32_t)p.cbc * p.n_pad * 16;
-  p.w_sample_floats = (long long)p.n_cb * p.taps * p.bt_bytes / 4;
+  if (x2) {
+    QBN_CHECK_ARG(stride == 1 && !stacked && !(flags & QBN_FLAG_OUT_PHASE_SPLIT), "fused shortcut: stride-1 main conv, normal output");
+    p.x2 = x2;
+    p.x2_plane = 4 * p.strip_rows;                       // phase (0,0) of the phase-split block input
+    p.cbc2 = CB2 / 4; p.n_cb2 = C2 / CB2; p.nk2 = p.cbc2 / 2;
+    p.bt2_bytes = (uint32_t)p.cbc2 * p.n_pad * 16;
+    if ((uint32_t)p.cbc2 * TM * 16 > p.a_bytes) p.a_bytes = (uint32_t)p.cbc2 * TM * 16;       // the slots must hold a shortcut block too
+    QBN_CHECK_ARG(p.bt2_bytes <= p.bt_bytes * (uint32_t)p.taps, "shortcut weight block larger than the main conv's");
+  }
+  p.w_sample_floats = ((long long)p.n_cb * p.taps * p.bt_bytes + (long long)p.n_cb2 * p.bt2_bytes) / 4;
   p.flags = flags; p.w_shared = stacked ? 1 : w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.out_mask = out_mask; p.out_mask_mult = out_mask_mult;
@@ -468,7 +564,7 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
     p.out_plane = 4 * p.q2_total;
   }
   // ---- shared memory / occupancy policy ----
-  const size_t b_all = (size_t)p.bt_bytes * p.n_cb * p.taps;
+  const size_t b_all = (size_t)p.bt_bytes * p.n_cb * p.taps + (size_t)p.bt2_bytes * p.n_cb2;
   const size_t fixed = 2 * 256 * 4 + 16 + 8 * 64;
   const size_t cap = 225 * 1024;
   int want_occ;
@@ -506,6 +602,10 @@ extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
     const int sa_new = atoi(getenv("QBN_P4_SA"));
     smem += (size_t)(sa_new - p.SA) * p.a_bytes;
     p.SA = sa_new;
+  }
+  if (p.n_cb2 && !p.b_res && p.bt2_bytes > p.b_slot_bytes) {
+    qbn_set_error("qbn_conv_p4_shortcut_fwd: shortcut weight block (%u B) exceeds the streamed weight slot (%u B)", p.bt2_bytes, p.b_slot_bytes);
+    return QBN_ERR_UNSUPPORTED;
   }
   if (smem > cap || p.SA < 1) {
     qbn_set_error("qbn_conv_p4_fwd: tile does not fit shared memory (%zu bytes)", smem);

@@ -363,55 +363,85 @@ class MCEngine:
                     and m.in_channels <= 8 and tuple(m.kernel_size) == (3, 3) and tuple(m.stride) == (1, 1) and tuple(m.padding) == (1, 1)
                     and tuple(m.dilation) == (1, 1) and m.out_channels % 4 == 0):
                 self._p4_first = id(st)
+        # BasicBlock downsampling shortcut (1x1 stride 2 -> BN) fused into the second stem conv as extra K blocks
+        self._p4_fused, self._p4_skip = {}, set()
+        for st in convs:
+            if (id(st) not in on or on[id(st)][0] != "s1" or st.residual is None or st.dropout is not None or st.bn is None
+                    or layout.get(st.dst, ("p4",))[0] != "p4"):
+                continue
+            sc = producers.get(st.residual)
+            if (isinstance(sc, _ConvStep) and id(sc) in on and on[id(sc)][0] == "s2" and tuple(sc.mod.kernel_size) == (1, 1) and sc.bn is not None
+                    and sc.residual is None and sc.dropout is None and not sc.relu and not sc.relu_pre
+                    and sum(1 for t in self.steps if isinstance(t, _ConvStep) and (t.src == sc.dst or t.residual == sc.dst)) == 1
+                    and not any(isinstance(t, _PoolStep) and t.src == sc.dst for t in self.steps)
+                    and ops.p4_shortcut_block_channels(st.mod.in_channels, sc.mod.in_channels) > 0):
+                self._p4_fused[id(st)] = sc
+                self._p4_skip.add(id(sc))
         self._p4_plan = (layout, set(on))
         return self._p4_plan
 
-    def _p4_weights(self, st, prep, info, stride):
+    def _p4_weights(self, st, prep, info, stride, cb=0):
         """mu / sigma blocked once per call for the planar kernel (they are shared by all samples).  The blocked
         buffers are persistent (stable pointers for the multi-layer sampler's job table and for CUDA graphs) and
         refreshed in place, so parameter updates between calls are honoured."""
         e = prep[id(st)]
-        key = ("p4w", stride)
+        key = ("p4w", stride, cb)
         if key not in e:
             N, C, R, S_ = info["wshape"]
             store = self.__dict__.setdefault("_p4_wbufs", {})
-            if id(st) not in store:
-                nfl = ops.p4_weight_floats(C, N, R, S_, stride)
-                store[id(st)] = (torch.empty((1, nfl), dtype=torch.float32, device=info["mu"].device),
-                                 torch.empty((1, nfl), dtype=torch.float32, device=info["mu"].device))
-            mu_b, sg_b = store[id(st)]
-            ops.p4_block_weights(info["mu"], N, C, R * S_, stride, out=mu_b)
-            ops.p4_block_weights(info["sigma"], N, C, R * S_, stride, out=sg_b)
-            e[key] = (mu_b[0], sg_b[0])
+            if (id(st), cb) not in store:
+                nfl = ops.p4_weight_floats(C, N, R, S_, stride) if cb == 0 else (C // cb) * R * S_ * (cb // 4) * ((N + 15) // 16 * 16) * 4
+                store[(id(st), cb)] = (torch.empty((1, nfl), dtype=torch.float32, device=info["mu"].device),
+                                       torch.empty((1, nfl), dtype=torch.float32, device=info["mu"].device),
+                                       torch.ones(((N + 15) // 16 * 16,), dtype=torch.float32, device=info["mu"].device))
+            mu_b, sg_b, sc_b = store[(id(st), cb)]
+            ops.p4_block_weights(info["mu"], N, C, R * S_, stride, out=mu_b, cb=cb)
+            ops.p4_block_weights(info["sigma"], N, C, R * S_, stride, out=sg_b, cb=cb)
+            if prep[id(st)]["scale"] is not None:
+                sc_b[:N].copy_(prep[id(st)]["scale"])          # persistent copy: the sampler's job table keeps this pointer
+            e[key] = (mu_b[0], sg_b[0], sc_b)
         return e[key]
 
     def _p4_sample_all(self, n, sample0, prep, seed, p4_convs, device, injected=None):
         """ONE sampling launch for every planar conv of the chunk (qbn_sample_weights_blocked_multi).
-        injected: per-sample lists of noise tensors in the reference's draw order (parity tests) -> eps pointers."""
-        import ctypes
+        injected: per-sample lists of noise tensors in the reference's draw order (parity tests) -> eps pointers.
+        A conv with a fused shortcut and the shortcut itself are two jobs filling ONE weight tensor per sample
+        ([main blocks][shortcut blocks]), both carrying their BatchNorm scale."""
         from ._lib import P4SampleJob
         first = self._p4_first
+        fused, skip = self._p4_fused, self._p4_skip
+        fused_of = {id(sc): st for st_id, sc in fused.items() for st in self.steps if id(st) == st_id}     # shortcut -> main step
+
         def stack_ok(st):
             return id(st) == first and n * st.mod.out_channels <= 256
         steps = [st for st in self.steps if id(st) in p4_convs or (isinstance(st, _ConvStep) and stack_ok(st))]
         tables = self.__dict__.setdefault("_p4_jobs", {})
+
         def pinfo(st):
             return self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"), 8 if id(st) == first else 4)
+
+        def cb_of(st):
+            return ops.p4_shortcut_block_channels(fused_of[id(st)].mod.in_channels, st.mod.in_channels) if id(st) in skip else 0
         for st in steps:                       # refresh the blocked parameters of this call (once per call, not per chunk)
-            self._p4_weights(st, prep, pinfo(st), st.mod.stride[0])
+            self._p4_weights(st, prep, pinfo(st), st.mod.stride[0], cb_of(st))
         if n not in tables or injected is not None:
             jobs = (P4SampleJob * len(steps))()
             wbufs, max_fl = {}, 0
             keep_eps = []
+            sizes = {id(st): self._p4_weights(st, prep, pinfo(st), st.mod.stride[0], cb_of(st))[0].numel() for st in steps}
+            for st in steps:                   # weight tensors: fused pairs share one [n, main + shortcut] tensor
+                if id(st) in skip:
+                    continue
+                if stack_ok(st):   # one blocked tensor, the chunk's samples stacked along N (padding rows stay zero)
+                    N, C, R, S_ = pinfo(st)["wshape"]
+                    wbufs[id(st)] = torch.zeros((1, ops.p4_weight_floats(C, n * N, R, S_, 1)), dtype=torch.float32, device=device)
+                else:
+                    extra = sizes[id(fused[id(st)])] if id(st) in fused else 0
+                    wbufs[id(st)] = torch.empty((n, sizes[id(st)] + extra), dtype=torch.float32, device=device)
             for i, st in enumerate(steps):
                 info = pinfo(st)
                 N, C, R, S_ = info["wshape"]
-                mu_b, sg_b = self._p4_weights(st, prep, info, st.mod.stride[0])
-                if stack_ok(st):   # one blocked tensor, the chunk's samples stacked along N (padding rows stay zero)
-                    w = torch.zeros((1, ops.p4_weight_floats(C, n * N, R, S_, 1)), dtype=torch.float32, device=device)
-                else:
-                    w = torch.empty((n, mu_b.numel()), dtype=torch.float32, device=device)
-                wbufs[id(st)] = w
+                mu_b, sg_b, sc_b = self._p4_weights(st, prep, info, st.mod.stride[0], cb_of(st))
                 max_fl = max(max_fl, mu_b.numel())
                 eps_ptr = None
                 if injected is not None and not st.det:
@@ -423,8 +453,18 @@ class MCEngine:
                         es.append(ops.pack_ohwi(e_))
                     keep_eps.append(torch.stack(es).contiguous())
                     eps_ptr = keep_eps[-1].data_ptr()
-                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), eps_ptr, w.data_ptr(), N, C, R * S_, st.mod.stride[0],
-                                      getattr(st.mod, "_qbn_layer_id", 0), n if stack_ok(st) else 0)
+                scale_ptr, stride4, w_ptr = None, 0, None
+                if id(st) in skip:             # shortcut half of a fused pair: after the main blocks of every sample
+                    main = fused_of[id(st)]
+                    w = wbufs[id(main)]
+                    w_ptr, stride4, scale_ptr = w.data_ptr() + sizes[id(main)] * 4, w.shape[1] // 4, sc_b.data_ptr()
+                elif id(st) in fused:
+                    w = wbufs[id(st)]
+                    w_ptr, stride4, scale_ptr = w.data_ptr(), w.shape[1] // 4, sc_b.data_ptr()
+                else:
+                    w_ptr = wbufs[id(st)].data_ptr()
+                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), eps_ptr, w_ptr, N, C, R * S_, st.mod.stride[0],
+                                      getattr(st.mod, "_qbn_layer_id", 0), n if stack_ok(st) else 0, scale_ptr, cb_of(st), stride4)
             raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
             entry = (raw, len(steps), max_fl, wbufs)
             if injected is None:
@@ -551,6 +591,8 @@ class MCEngine:
                 shared[st.dst] = False
                 ready[st.dst] = True
                 continue
+            if id(st) in self._p4_skip and self._p4_presampled is not None:
+                continue                       # 1x1 stride-2 shortcut: accumulated inside the block's second stem conv
             if id(st) in p4_convs:
                 assert st.src not in pending, "planar conv fed by a register with a pending dropout mask (planner bug)"
                 regs[st.dst] = self._run_p4_conv(st, si, src, regs, n, sample0, prep, injected, p4_layout, seed, masks)
@@ -650,7 +692,16 @@ class MCEngine:
             H0, W0 = src.Hp - 2 * src.border[0], src.Wp - 2 * src.border[1]
         info = self._packed(st, prep, torch.empty((0, src.C, H0, W0), device="meta"))
         N, C, R, S_ = info["wshape"]
-        mu_b, sg_b = self._p4_weights(st, prep, info, stride)
+        mu_b, sg_b, _ = self._p4_weights(st, prep, info, stride)
+        if self._p4_presampled is not None and id(st) in self._p4_fused:
+            # out = relu(conv3x3(y) * s2 + conv1x1/2(x_block) * ssc + (b2 + bsc)): both branches in one accumulator
+            sc = self._p4_fused[id(st)]
+            e, esc = prep[id(st)], prep[id(sc)]
+            out = self._p4_buffer(("p4", si), src.n_img, N, src.Hp, src.Wp, src.border, 1, src.buf.device, zero=False)
+            assert p4_layout[st.dst][0] == "p4"
+            ops.conv_p4_shortcut_forward(src, self._p4_presampled[id(st)], regs[sc.src], n, N, R, S_, None, e["shift"] + esc["shift"], st.relu,
+                                         ops.QBN_FLAG_OUT_ROUND_TF32, out)
+            return out
         if self._p4_presampled is not None:
             w = self._p4_presampled[id(st)]
         else:

@@ -528,14 +528,14 @@ def p4_weight_floats(C, N, R, S, stride=1):
     return int(n.value)
 
 
-def p4_block_weights(w_ohwi, N, C, taps, stride=1, out=None):
+def p4_block_weights(w_ohwi, N, C, taps, stride=1, out=None, cb=0):
     """[n_mats, N*taps*C] packed OHWI -> blocked [n_mats, p4_weight_floats] (the blocking depends on the stride)."""
     w_ohwi = w_ohwi.reshape(-1, N * taps * C).contiguous()
     n_mats = w_ohwi.shape[0]
     R = taps
     if out is None:
         out = torch.empty((n_mats, p4_weight_floats(C, N, R, 1, stride)), dtype=torch.float32, device=w_ohwi.device)
-    _lib.call("qbn_p4_block_weights", _ptr(w_ohwi), n_mats, N, C, taps, stride, _ptr(out), _stream())
+    _lib.call("qbn_p4_block_weights", _ptr(w_ohwi), n_mats, N, C, taps, stride, int(cb), _ptr(out), _stream())
     return out
 
 
@@ -576,6 +576,23 @@ def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, 
     fl = int(bool(relu)) | int(flags) | (QBN_FLAG_OUT_PHASE_SPLIT if phase_split_out else 0)
     _lib.call("qbn_conv_p4_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, stride, _ptr(x.buf), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
               _ptr(residual.buf if residual is not None else None), _ptr(out_mask), float(out_mask_mult), fl, _ptr(out.buf), _stream())
+    return out
+
+
+def p4_shortcut_block_channels(C, C2):
+    return int(_lib.load().qbn_p4_shortcut_block_channels(C, C2))
+
+
+def conv_p4_shortcut_forward(x, w, x2, n_samples, N, R, S, scale=None, shift=None, relu=False, flags=0, out=None):
+    """qbn_conv_p4_shortcut_fwd: stride-1 conv of x plus the 1x1 stride-2 shortcut of the phase-split block input x2 in
+    one accumulator.  w: [n_samples, main blocks + shortcut blocks] (both carrying their BatchNorm scale)."""
+    B = x.n_img // n_samples
+    if x2.phases != 4 or (x2.Hp, x2.Wp, x2.n_img) != (x.Hp, x.Wp, x.n_img):
+        raise _lib.QbnError("fused shortcut: x2 must be the phase-split block input with the output geometry")
+    if out is None:
+        out = P4Map.empty(x.n_img, N, x.Hp, x.Wp, x.border, 1, x.buf.device)
+    _lib.call("qbn_conv_p4_shortcut_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, _ptr(x.buf), _ptr(w), _ptr(x2.buf), x2.C, _ptr(scale),
+              _ptr(shift), int(bool(relu)) | int(flags), _ptr(out.buf), _stream())
     return out
 
 

@@ -40,6 +40,17 @@ for (C, H, N, k, stride, res, split) in [(24, 32, 24, 3, 1, False, False), (24, 
     fl = 2.0 * S * B * H * H * N * k * k * C
     by = 4.0 * (x.buf.numel() + out.buf.numel() + (r.buf.numel() if res else 0))
     print("p4  C%3d out%2dx%-2d N%3d k%d s%d res=%d split=%d : %7.1f us  %6.1f TF/s  %6.0f GB/s" % (C, H, H, N, k, stride, res, split, ms * 1e3, fl / ms / 1e9, by / ms / 1e6))
+for (C2, N, H) in [(24, 48, 16), (48, 96, 8), (96, 192, 4)]:
+    Hp = H + 2
+    y = ops.P4Map(rnd(torch.randn(N // 4, S * B * Hp * Hp, 4, device="cuda")), S * B, N, Hp, Hp, (1, 1), 1)
+    x2 = ops.P4Map(rnd(torch.randn(C2 // 4, 4 * S * B * Hp * Hp, 4, device="cuda")), S * B, C2, Hp, Hp, (1, 1), 4)
+    cb2 = ops.p4_shortcut_block_channels(N, C2)
+    nfl = ops.p4_weight_floats(N, N, 3, 3, 1) + (C2 // cb2) * (cb2 // 4) * ((N + 15) // 16 * 16) * 4
+    w = rnd(torch.randn(S, nfl, device="cuda") * 0.05)
+    out = ops.P4Map.empty(S * B, N, Hp, Hp, (1, 1), 1, "cuda")
+    sh = torch.randn(N, device="cuda")
+    ms = timeit(lambda: ops.conv_p4_shortcut_forward(y, w, x2, S, N, 3, 3, None, sh, True, ops.QBN_FLAG_OUT_ROUND_TF32, out))
+    print("p4  fused shortcut C%3d->N%3d out%2dx%-2d (3x3 + 1x1/2 of C%d) : %7.1f us" % (N, N, H, H, C2, ms * 1e3))
 n = 1571592
 mu = torch.randn(n, device="cuda"); sg = torch.rand(n, device="cuda")
 ms = timeit(lambda: ops.sample_weights(mu, sg, S, None, 1, 2, 0, True))

@@ -48,6 +48,14 @@ def d_p4(a, k, out):
     return dict(shape="SB%d out%dx%d C%d->N%d k%d s%d%s%s" % (x_.n_img, H, W, x_.C, N, R, stride, " +res" if res is not None else "", " split" if out.phases == 4 else ""),
                 flops=fl, bytes=by, mode=1)
 mc.ops.conv_p4_forward = wrap("conv_p4", ops.conv_p4_forward, d_p4)
+def d_p4sc(a, k, out):
+    x_, w, x2 = a[:3]
+    n, N, R, S_ = a[3:7]
+    H, W = x_.Hp - 2, x_.Wp - 2
+    fl = 2.0 * x_.n_img * H * W * N * (R * S_ * x_.C + x2.C)
+    by = 4.0 * (x_.buf.numel() + 0.25 * x2.buf.numel() + out.buf.numel())
+    return dict(shape="SB%d out%dx%d C%d->N%d k%d + fused 1x1/2 of C%d" % (x_.n_img, H, W, x_.C, N, R, x2.C), flops=fl, bytes=by, mode=1)
+mc.ops.conv_p4_shortcut_forward = wrap("conv_p4", ops.conv_p4_shortcut_forward, d_p4sc)
 mc.ops.sample_weights_blocked = wrap("sample_wb", ops.sample_weights_blocked, d_other)
 mc.ops.avgpool_p4 = wrap("avgpool_p4", ops.avgpool_p4, d_other)
 mc.ops.softmax_accumulate = wrap("softmax_acc", ops.softmax_accumulate, d_other)

@@ -277,3 +277,36 @@ def test_p4_conv_output_dropout_mask():
     aff1 = (conv1 * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)).clamp(min=0)
     ref = (aff1.unsqueeze(0) * mask.double().view(S, B, N, 1, 1) * mult).reshape(S * B, N, H, H)
     close(got.to_nchw(), ref.float(), 1e-3, 1e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 48, 16), (2, 48, 96, 8), (3, 96, 192, 4)])
+def test_p4_conv_fused_shortcut(shape):
+    """conv3x3(y) * s2 + conv1x1,stride2(x) * ssc + shift in ONE accumulator (scales folded into the weights) ==
+    BN2(conv2(y)) + BNsc(convsc(x)) of models_bbb.py:170-178."""
+    from qbn_b200 import ops
+    B, C2, N, Ho = shape          # block input x: C2 channels at 2*Ho; main conv: N -> N at Ho
+    g = torch.Generator().manual_seed(100 + N)
+    S = 3
+    x = _tf32_round_(torch.randn(S * B, C2, 2 * Ho, 2 * Ho, generator=g).cuda())
+    y = _tf32_round_(torch.randn(S * B, N, Ho, Ho, generator=g).cuda())
+    w = _rand_weights(g, S, N, 3, N)
+    wsc = _rand_weights(g, S, N, 1, C2)
+    s2, ssc = (torch.rand(N, generator=g) + 0.5).cuda(), (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    d = ops.make_desc(B, Ho, Ho, N, N, 3, 3, 1, 1, 1)
+    dsc = ops.make_desc(B, 2 * Ho, 2 * Ho, C2, N, 1, 1, 2, 0, 1)
+    sc = ops.conv_forward(ops.nhwc(x), wsc, dsc, S, False, False, ssc, None, None, False, None, 1.0, ops.QBN_MATH_FP32)
+    ref = ops.conv_forward(ops.nhwc(y), w, d, S, False, False, s2, shift, sc, True, None, 1.0, ops.QBN_MATH_FP32)
+    # fold the scales into the (TF32-rounded) weights like the sampler does
+    wf = _tf32_round_((w.reshape(S, N, -1) * s2.view(1, N, 1)).reshape(S, -1).contiguous())
+    wscf = _tf32_round_((wsc.reshape(S, N, -1) * ssc.view(1, N, 1)).reshape(S, -1).contiguous())
+    cb2 = ops.p4_shortcut_block_channels(N, C2)
+    assert cb2 % 8 == 0 and C2 % cb2 == 0
+    wb = torch.cat([ops.p4_block_weights(wf, N, N, 9), ops.p4_block_weights(wscf, N, C2, 1, 2, None, cb2)], dim=1).contiguous()
+    yb = ops.P4Map.from_nchw(y, (1, 1))
+    xs = ops.P4Map.from_nchw(x, None, phase_split=True)
+    got = ops.conv_p4_shortcut_forward(yb, wb, xs, S, N, 3, 3, None, shift, True, ops.QBN_FLAG_OUT_ROUND_TF32)
+    close(got.to_nchw(), ref, 2e-3, 2e-3)
+    full = got.to_nchw(keep_border=True).clone()
+    full[:, :, 1:-1, 1:-1] = 0
+    assert float(full.abs().max()) == 0.0
