@@ -267,6 +267,21 @@ __global__ void dropout_apply_kernel(const float* __restrict__ x, int64_t rows, 
   }
 }
 
+// C % 4 == 0: one float4 per thread, the mask row is indexed by the image of the pixel (no 64-bit division per element)
+__global__ void dropout_apply4_kernel(const float4* __restrict__ x, int64_t rows, int hw, int C4, const float4* __restrict__ mask, float mult,
+                                      float4* __restrict__ out) {
+  const int64_t n_pix = rows * hw;
+  for (int64_t pix = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; pix < n_pix; pix += (int64_t)gridDim.x * blockDim.y) {
+    const int64_t b = pix / hw;
+    for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+      const float4 v = x[pix * C4 + c], m = mask[b * C4 + c];
+      // dropout.py:38-39: x = mul(x, mask) ; x = mul_scalar(x, multiplier)
+      out[pix * C4 + c] = make_float4(__fmul_rn(__fmul_rn(v.x, m.x), mult), __fmul_rn(__fmul_rn(v.y, m.y), mult),
+                                      __fmul_rn(__fmul_rn(v.z, m.z), mult), __fmul_rn(__fmul_rn(v.w, m.w), mult));
+    }
+  }
+}
+
 extern "C" int qbn_dropout_fwd(const float* x, int64_t rows, int64_t hw, int64_t C, const float* mask, float keep_prob,
                                float mult, uint64_t seed, uint32_t sa, uint32_t sb, float* out, float* mask_out, void* stream) {
   QBN_CHECK_ARG(x && out, "x/out");
@@ -278,6 +293,21 @@ extern "C" int qbn_dropout_fwd(const float* x, int64_t rows, int64_t hw, int64_t
     QBN_CHECK_LAUNCH();
     m = mask_out;
   }
+  if (C % 4 == 0 && hw < (1 << 30) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(m)) & 15) == 0) {
+    const int C4 = (int)(C / 4);
+    int tx = 1;
+    while (tx < C4 && tx < 32) tx <<= 1;                 // lanes over channel chunks, the rest of the block over pixels
+    const dim3 block(tx, 256 / tx);
+    const int64_t n_pix = rows * hw;
+    int64_t gx = (n_pix + block.y - 1) / block.y;
+    const int64_t cap = (int64_t)qbn_sm_count() * 16;
+    if (gx > cap) gx = cap;
+    dropout_apply4_kernel<<<(unsigned)gx, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), rows, (int)hw, C4,
+                                                                            reinterpret_cast<const float4*>(m), mult,
+                                                                            reinterpret_cast<float4*>(out));
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
+  }
   dropout_apply_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, hw, C, m, mult, out);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
@@ -286,18 +316,43 @@ extern "C" int qbn_dropout_fwd(const float* x, int64_t rows, int64_t hw, int64_t
 // ---------------------------------------------------------------------------------------------
 // A5: KL + gradient, one pass
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float kl_term(float m, float r, float sp, float inv_sp, float inv_sp2, float gscale, float& gm, float& gr) {
+  const float sg = softplus_f(r);
+  const float a = sg * inv_sp, b = m * inv_sp;
+  gm = gscale * m * inv_sp2;
+  gr = gscale * (sg * inv_sp2 - 1.0f / sg) * sigmoid_f(r);
+  return 2.0f * logf(sp / sg) - 1.0f + a * a + b * b;
+}
 __global__ void kl_kernel(const float* __restrict__ mu, const float* __restrict__ rho, int64_t n, float sp,
                           float* __restrict__ kl_out, float* __restrict__ d_mu, float* __restrict__ d_rho, float gscale) {
   double acc = 0.0;
   const float inv_sp = 1.0f / sp;
   const float inv_sp2 = inv_sp * inv_sp;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float m = mu[i], r = rho[i];
-    float sg = softplus_f(r);
-    float a = sg * inv_sp, b = m * inv_sp;
-    acc += (double)(2.0f * logf(sp / sg) - 1.0f + a * a + b * b);
-    if (d_mu) d_mu[i] += gscale * m * inv_sp2;
-    if (d_rho) d_rho[i] += gscale * (sg * inv_sp2 - 1.0f / sg) * sigmoid_f(r);
+  const bool vec = ((reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(rho) | reinterpret_cast<uintptr_t>(d_mu) |
+                     reinterpret_cast<uintptr_t>(d_rho)) & 15) == 0;
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 m = reinterpret_cast<const float4*>(mu)[i], r = reinterpret_cast<const float4*>(rho)[i];
+    float4 gm, gr;
+    float t = kl_term(m.x, r.x, sp, inv_sp, inv_sp2, gscale, gm.x, gr.x);      // per-thread partial in fp32 over 4 terms, then fp64
+    t += kl_term(m.y, r.y, sp, inv_sp, inv_sp2, gscale, gm.y, gr.y);
+    t += kl_term(m.z, r.z, sp, inv_sp, inv_sp2, gscale, gm.z, gr.z);
+    t += kl_term(m.w, r.w, sp, inv_sp, inv_sp2, gscale, gm.w, gr.w);
+    acc += (double)t;
+    if (d_mu) {
+      float4 o = reinterpret_cast<float4*>(d_mu)[i];
+      reinterpret_cast<float4*>(d_mu)[i] = make_float4(o.x + gm.x, o.y + gm.y, o.z + gm.z, o.w + gm.w);
+    }
+    if (d_rho) {
+      float4 o = reinterpret_cast<float4*>(d_rho)[i];
+      reinterpret_cast<float4*>(d_rho)[i] = make_float4(o.x + gr.x, o.y + gr.y, o.z + gr.z, o.w + gr.w);
+    }
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gm, gr;
+    acc += (double)kl_term(mu[i], rho[i], sp, inv_sp, inv_sp2, gscale, gm, gr);
+    if (d_mu) d_mu[i] += gm;
+    if (d_rho) d_rho[i] += gr;
   }
   // block reduction in double, one atomic per block
   __shared__ double sh[32];
@@ -316,7 +371,7 @@ extern "C" int qbn_kl_fwd_bwd(const float* mu, const float* rho, int64_t n, floa
                               float* d_rho, float grad_scale, void* stream) {
   QBN_CHECK_ARG(mu && rho && kl_out, "null pointer");
   QBN_CHECK_ARG(n > 0 && sigma_prior > 0.f, "n>0, sigma_prior>0");
-  kl_kernel<<<qbn_grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(mu, rho, n, sigma_prior, kl_out, d_mu, d_rho, grad_scale);
+  kl_kernel<<<qbn_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(mu, rho, n, sigma_prior, kl_out, d_mu, d_rho, grad_scale);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -166,9 +166,61 @@ __global__ void reg_metrics_kernel(const float* __restrict__ mean, const float* 
 
 }  // namespace
 
+// K <= 16 (the 10-class nets): one thread per (image, sample group) keeps its row in registers — consecutive lanes read
+// consecutive images, i.e. contiguous rows — and the sample groups are reduced through shared memory in a fixed order.
+template <int SG>
+__global__ void softmax_accumulate_smallk_kernel(const float* __restrict__ logits, int S, int B, int K, float* __restrict__ psum,
+                                                 int accumulate) {
+  __shared__ float sh[SG][32][17];
+  const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  if (b < B) {
+    for (int s = sg; s < S; s += SG) {
+      const float* row = logits + ((int64_t)s * B + b) * K;
+      float v[16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        v[k] = k < K ? __ldg(row + k) : -INFINITY;
+        mx = fmaxf(mx, v[k]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        v[k] = k < K ? expf(v[k] - mx) : 0.f;
+        sum += v[k];
+      }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] += v[k] * inv;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) sh[sg][lane][k] = acc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
+    const int l = i / K, k = i - l * K;
+    const int bb = blockIdx.x * 32 + l;
+    if (bb >= B) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < SG; ++g) t += sh[g][l][k];
+    const int64_t o = (int64_t)bb * K + k;
+    psum[o] = accumulate ? psum[o] + t : t;
+  }
+}
+
 extern "C" int qbn_softmax_accumulate(const float* logits, int n_samples, int B, int K, float* psum, int accumulate, void* stream) {
   QBN_CHECK_ARG(logits && psum, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && K > 0 && K <= 128, "S,B > 0 and 0 < K <= 128");
+  if (K <= 16) {
+    softmax_accumulate_smallk_kernel<8><<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(logits, n_samples, B, K, psum, accumulate);
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
+  }
   softmax_accumulate_kernel<<<B, 256, 8 * K * sizeof(float), (cudaStream_t)stream>>>(logits, n_samples, B, K, psum, accumulate);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
