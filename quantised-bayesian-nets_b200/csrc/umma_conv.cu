@@ -42,6 +42,8 @@ struct UParams {
   int oph, opw;     // zero-bordered output layout (interior written only)
   int n_split;      // >0: the N columns are n_split channels of N/n_split stacked Monte-Carlo samples (shared input)
   long long sample_out_stride;   // elements between consecutive samples' output tensors
+  long long w_ld;                // elements between consecutive samples' weight tensors (0: N*K); N-split launches of wide layers
+  int out_ld;                    // channels per stored output row (0: N)
   long long out_plane;           // QBN_FLAG_OUT_P4: rows per chunk plane of the planar-C4 output (all samples)
   uint32_t idesc;
   // tensors
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     const int kc = tid & 7;          // this thread's 16-byte K-chunk inside every stage
     const int r0 = tid >> 3;         // rows r0 + 16*i
     const uint8_t* xs = reinterpret_cast<const uint8_t*>(p.x) + (p.x_shared ? 0 : (size_t)z * p.B * p.H * p.W * p.C * ESZ);
-    const uint8_t* ws = reinterpret_cast<const uint8_t*>(p.w) + (p.w_shared ? 0 : (size_t)z * p.N * p.K * ESZ);
+    const uint8_t* ws = reinterpret_cast<const uint8_t*>(p.w) + (p.w_shared ? 0 : (size_t)z * (p.w_ld ? (size_t)p.w_ld : (size_t)p.N * p.K) * ESZ);
     const uint8_t* ws2 = LRT ? reinterpret_cast<const uint8_t*>(p.w2) : nullptr;
     const float* msk = p.in_mask ? p.in_mask + (size_t)z * p.B * p.C : nullptr;
 
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     const int m = m0 + warp * 32 + lane;        // TMEM lane == tile row
     const bool mv = m < p.M;
     const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int Nrow = p.n_split ? p.n_split : p.N;      // channels per stored row
+    const int Nrow = p.n_split ? p.n_split : (p.out_ld ? p.out_ld : p.N);      // channels per stored row
     size_t prow = (size_t)z * p.M + (mv ? m : 0);          // pixel row of the output tensor
     if (p.oph | p.opw) {
       const int mm = mv ? m : 0;
@@ -489,6 +491,28 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
     p.N = n_samples * d->N;
     p.sample_out_stride = (long long)d->B * (d->Ho + 2 * d->out_pad_h) * (d->Wo + 2 * d->out_pad_w) * d->N;
     return launch_umma<MODE_EVAL>(p, 1, st, "qbn_conv_fwd(TF32, sample-stacked)");
+  }
+  // Wide linear layers (N > 256, e.g. LeNet's 2450 -> 500): one accumulator tile holds at most 256 columns, so the output
+  // channels are split over several launches that write column ranges of the same rows.
+  if (d->N > 256) {
+    if (!(d->R == 1 && d->S == 1 && d->H == 1 && d->W == 1 && d->out_pad_h == 0 && d->out_pad_w == 0) || (flags & QBN_FLAG_OUT_P4)) {
+      qbn_set_error("qbn_conv_fwd(TF32): N=%d > 256 is supported for linear (1x1 on a 1x1 map) geometry only", d->N);
+      return QBN_ERR_UNSUPPORTED;
+    }
+    for (int n0 = 0; n0 < d->N; n0 += 256) {
+      UParams q = p;
+      q.N = d->N - n0 < 256 ? d->N - n0 : 256;
+      q.w = w + (size_t)n0 * q.K;
+      q.w_ld = (long long)d->N * q.K;
+      q.out = out + n0;
+      q.out_ld = d->N;
+      if (scale) q.scale = scale + n0;
+      if (shift) q.shift = shift + n0;
+      if (residual) q.residual = residual + n0;
+      int rc = launch_umma<MODE_EVAL>(q, n_samples, st, "qbn_conv_fwd(TF32, N-split)");
+      if (rc != QBN_OK) return rc;
+    }
+    return QBN_OK;
   }
   return launch_umma<MODE_EVAL>(p, n_samples, st, "qbn_conv_fwd(TF32)");
 }

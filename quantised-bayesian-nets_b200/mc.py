@@ -188,8 +188,21 @@ class MCEngine:
         det = rho is None
         if det:
             rho = torch.zeros_like(w)              # placeholder; sigma is forced to exactly 0 below
+        flat = None
         if st.is_linear:
-            if x.dim() == 4 and (x.shape[2] > 1 or x.shape[3] > 1):
+            if x.dim() == 4 and (x.shape[2] > 1 or x.shape[3] > 1) and self.math_mode == QBN_MATH_TF32 and x.shape[1] % 4 != 0:
+                # flatten -> linear over a map whose channel count is not a multiple of 4 (LeNet: 50 x 7 x 7): run it as a
+                # 1x1 layer over the NHWC-flattened vector, K padded to a multiple of 4, so it stays on the tcgen05 path
+                C, H, W = x.shape[1], x.shape[2], x.shape[3]
+                K = C * H * W
+                Kp = (K + 3) // 4 * 4
+                wf = w.reshape(w.shape[0], C, H, W).permute(0, 2, 3, 1).reshape(w.shape[0], K)
+                rf = rho.reshape(w.shape[0], C, H, W).permute(0, 2, 3, 1).reshape(w.shape[0], K)
+                w4 = torch.nn.functional.pad(wf, (0, Kp - K)).reshape(w.shape[0], Kp, 1, 1)
+                rho4 = torch.nn.functional.pad(rf, (0, Kp - K), value=-200.0).reshape(w.shape[0], Kp, 1, 1)
+                flat = (K, Kp, H * W, (w.shape[0], C, H, W))
+                stride, pad, dil = (1, 1), (0, 0), (1, 1)
+            elif x.dim() == 4 and (x.shape[2] > 1 or x.shape[3] > 1):
                 C, H, W = x.shape[1], x.shape[2], x.shape[3]
                 w4, rho4 = w.reshape(w.shape[0], C, H, W), rho.reshape(w.shape[0], C, H, W)
                 stride, pad, dil = (1, 1), (0, 0), (1, 1)
@@ -206,11 +219,11 @@ class MCEngine:
             w4 = torch.nn.functional.pad(w4, (0, 0, 0, 0, 0, cpad))
             rho4 = torch.nn.functional.pad(rho4, (0, 0, 0, 0, 0, cpad), value=-200.0)  # softplus -> 0
         packed = ops.weight_prep(w4.contiguous(), rho4.contiguous(), False, None, want=("mu", "sigma"))
-        if cpad:
+        if cpad or flat:
             packed["sigma"] = torch.where(packed["sigma"] < 1e-30, torch.zeros_like(packed["sigma"]), packed["sigma"])
         if det:
             packed["sigma"] = torch.zeros_like(packed["sigma"])       # W[s] = mu + 0 * eps = mu for every sample
-        info = dict(mu=packed["mu"], sigma=packed["sigma"], wshape=tuple(w4.shape), stride=stride, pad=pad, dil=dil, cpad=cpad,
+        info = dict(mu=packed["mu"], sigma=packed["sigma"], wshape=tuple(w4.shape), stride=stride, pad=pad, dil=dil, cpad=cpad, flat=flat,
                     orig_shape=tuple(w.shape) if not st.is_linear else (w.shape[0], w4.shape[1] - cpad, w4.shape[2], w4.shape[3]))
         e[key] = info
         return info
@@ -610,24 +623,41 @@ class MCEngine:
             info = self._packed(st, prep, unp)
             if info["cpad"]:
                 src = torch.nn.functional.pad(src, (0, 0, 0, 0, 0, info["cpad"])).contiguous(memory_format=ops.CL)
+            if info["flat"]:
+                K_, Kp_, HW_, _ = info["flat"]
+                assert spad == (0, 0)
+                flat_x = src.permute(0, 2, 3, 1).reshape(src.shape[0], K_)          # NHWC memory order: a view
+                src = torch.nn.functional.pad(flat_x, (0, Kp_ - K_)).reshape(src.shape[0], Kp_, 1, 1)
             N, C, R, S_ = info["wshape"]
             nb = src.shape[0] if shared[st.src] else src.shape[0] // n
             eps = None
             if injected is not None and not st.det:
                 es = []
                 for s in range(n):
+                    if info["flat"]:
+                        K_, Kp_, HW_, shp = info["flat"]
+                        e = ops.pack_ohwi(injected[s][st.ref_idx].reshape(shp).float()).reshape(shp[0], K_)
+                        es.append(torch.nn.functional.pad(e, (0, Kp_ - K_)).reshape(-1))
+                        continue
                     e = injected[s][st.ref_idx].reshape(info["orig_shape"]).float()
                     if info["cpad"]:
                         e = torch.nn.functional.pad(e, (0, 0, 0, 0, 0, info["cpad"]))
                     es.append(ops.pack_ohwi(e))
                 eps = torch.stack(es).contiguous()
             e = prep[id(st)]
-            mode = self.math_mode if config.tf32_eligible(C, N, False) else QBN_MATH_FP32
+            # tcgen05 eligibility: 16-byte K chunks; one accumulator tile holds <= 256 channels, except that linear (1x1 on a 1x1 map)
+            # layers of any width are split over N by the library
+            lin_geom = R == 1 and S_ == 1 and src.shape[2] == 1 and src.shape[3] == 1
+            elig = config.tf32_eligible(C, N, False) or (C % 4 == 0 and lin_geom and st.residual is None)
+            mode = self.math_mode if elig else QBN_MATH_FP32
             tf32 = mode == QBN_MATH_TF32
             w = ops.sample_weights(info["mu"], info["sigma"], n, eps, seed, getattr(st.mod, "_qbn_layer_id", 0), sample0, round_tf32=tf32)
             res = regs[st.residual] if st.residual is not None else None
             # MC-Dropout on the gather / fp32 kernels: the mask of the producing site rides the operand load of its consumers
             in_mask, in_mult = pending.get(st.src, (None, 1.0))
+            if in_mask is not None and info["flat"]:        # mask[b, c] broadcast over the flattened (h, w, c) vector
+                K_, Kp_, HW_, _ = info["flat"]
+                in_mask = torch.nn.functional.pad(in_mask.repeat(1, HW_), (0, Kp_ - K_)).contiguous()
             relu_eff = st.relu or st.relu_pre
             if st.dropout is not None and (st.residual is not None or st.dst in p4_layout):
                 raise NotImplementedError("MC-Dropout before a residual add needs the planar kernel (epilogue mask)")
@@ -776,8 +806,11 @@ class MCEngine:
         psum = None
         mus, lvs = [], []
         done = 0
-        while done < samples:
-            n = min(self.chunk, samples - done)
+        # balanced chunks: ceil(S / chunk) launches of near-equal size (13 samples -> 7 + 6 rather than 10 + 3: a small tail
+        # chunk pays the per-launch fixed costs for little work; matters when the samples are sharded over 8 GPUs)
+        n_chunks = (samples + self.chunk - 1) // self.chunk
+        sizes = [samples // n_chunks + (1 if i < samples % n_chunks else 0) for i in range(n_chunks)]
+        for n in sizes:
             inj = injected[done:done + n] if injected is not None else None
             out = self._run_chunk(x, n, sample0 + done, prep, inj)
             if self.regression:
