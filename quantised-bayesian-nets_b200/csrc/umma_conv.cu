@@ -18,6 +18,7 @@
 //   tcgen05.ld -> LRT: mean + sqrt(1e-8+var)*eps(+Philox) + bias | eval: affine (BN/bias),
 //   residual add, ReLU | int8: FBGEMM requantisation -> global.
 // All mbarrier waits are bounded (trap instead of hanging the GPU).
+#include <stdlib.h>
 #include <string.h>
 #include "umma_common.cuh"
 
@@ -259,38 +260,41 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     }
   } else {
     // =========================== MMA ISSUER (warp 4) =============================================
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t lbo_a = (uint32_t)p.a_pitch * 16, lbo_b = (uint32_t)p.b_pitch * 16;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      if (lane == 0) mbar_wait(smem_u32(&full_bar[stage]), phase);
-      __syncwarp();
-      fence_proxy_async();            // cp.async (generic proxy) data -> ordered before the MMAs' async-proxy reads
-      tc_fence_after();
-      if (lane == 0) {
+    // One elected thread runs the whole loop: inside an elect.sync region ptxas keeps the per-MMA descriptors in uniform
+    // registers (an `if (lane == 0)` region made it wrap every MMA in an ELECT / R2UR.BROADCAST waterfall loop).
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t lbo_a = (uint32_t)p.a_pitch * 16, lbo_b = (uint32_t)p.b_pitch * 16;
+      const uint64_t adesc_hi = make_smem_desc(0, lbo_a, 128), bdesc_hi = make_smem_desc(0, lbo_b, 128);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        fence_proxy_async();            // cp.async / st.shared (generic proxy) data -> ordered before the MMAs' async-proxy reads
+        tc_fence_after();
         const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
         const uint32_t sa2 = sa + a_bytes;
         const uint32_t sb = sa + (LRT ? 2 : 1) * a_bytes;
         const uint32_t sb2 = sb + b_bytes;
         const int krem = p.K - kb * BLOCK_K;
         const int nmma = krem >= BLOCK_K ? KCH / 2 : (krem + MMA_K - 1) / MMA_K;
+#pragma unroll 1
         for (int j = 0; j < nmma; ++j) {
           const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-          uint64_t ad = make_smem_desc(sa + 2 * j * lbo_a, lbo_a, 128);
-          uint64_t bd = make_smem_desc(sb + 2 * j * lbo_b, lbo_b, 128);
+          const uint64_t ad = adesc_hi | (uint64_t)(((sa + 2 * j * lbo_a) >> 4) & 0x3FFF);
+          const uint64_t bd = bdesc_hi | (uint64_t)(((sb + 2 * j * lbo_b) >> 4) & 0x3FFF);
           umma_mma<MODE>(tmem_base, ad, bd, p.idesc, acc);
           if constexpr (LRT) {
-            uint64_t ad2 = make_smem_desc(sa2 + 2 * j * lbo_a, lbo_a, 128);
-            uint64_t bd2 = make_smem_desc(sb2 + 2 * j * lbo_b, lbo_b, 128);
+            const uint64_t ad2 = adesc_hi | (uint64_t)(((sa2 + 2 * j * lbo_a) >> 4) & 0x3FFF);
+            const uint64_t bd2 = bdesc_hi | (uint64_t)(((sb2 + 2 * j * lbo_b) >> 4) & 0x3FFF);
             umma_mma<MODE>(tmem_base + (uint32_t)p.n_pad, ad2, bd2, p.idesc, acc);
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));            // slot free once these MMAs retire
         if (kb == num_kb - 1) umma_commit(smem_u32(accum_bar));  // accumulators complete
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    __syncwarp();
   }
 
   // =============================== EPILOGUE (warps 0-3) ==========================================
@@ -421,7 +425,10 @@ static int launch_umma(UParams& p, int n_samples, cudaStream_t st, const char* w
   const size_t stage_bytes = (size_t)(LRT ? 2 : 1) * KCH * 16 * (p.a_pitch + p.b_pitch);
   constexpr int BLOCK_K = KCH * (I8 ? 16 : 4);
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  // The kernel is not persistent and its epilogue does not overlap its main loop, so co-resident CTAs are what keeps an SM busy:
+  // size the ring for TWO CTAs per SM when at least two stages fit in half the shared memory (else one CTA with a deeper ring).
+  int stages = (int)((110 * 1024) / stage_bytes);
+  if (getenv("QBN_V1_DEEP") || stages < 2) stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages > num_kb) stages = num_kb;
   if (stages < 1) {
