@@ -26,8 +26,8 @@ sys.path.insert(0, ROOT)
 B, S, K_CLASSES = 256, 100, 10
 FLOP_PER_SAMPLE_IMAGE = 1.5704e8          # SURVEY.md §8d, one contraction per layer
 # mean dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one 10-sample chunk (ncu --set full)
-P4_DRAM_BYTES_PER_LAUNCH = 322.1e6
-P4_TRAFFIC_SOURCE = "dram__bytes_read.sum + dram__bytes_write.sum, mean over 18 umma_conv_p4_kernel launches of one 10-sample chunk, ncu --set full (profiles/r01_p4_kernels_ncu_full.csv); above the algorithmic figure by the residual reads and the zero border"
+P4_DRAM_BYTES_PER_LAUNCH = 361.1e6
+P4_TRAFFIC_SOURCE = "dram__bytes_read.sum + dram__bytes_write.sum, mean over the 17 umma_conv_p4_kernel launches of one 10-sample chunk, ncu --set full (profiles/r01_p4_kernels_ncu_full.csv); above the algorithmic figure by the residual reads and the zero border"
 ACT_BYTES_PER_SAMPLE_IMAGE = 1.929e6      # fp32 NHWC activations in+out of the 21 stochastic layers
 
 
@@ -275,7 +275,18 @@ def main():
             H, W = x.Hp - 2 * bh, x.Wp - 2 * bw                     # output pixels (the map geometry is the output's)
             evs.append((e0, e1, 2.0 * x.n_img * H * W * N * R * S_ * x.C, 2))
             return out
+        orig_p4sc = mc.ops.conv_p4_shortcut_forward
+
+        def timed_p4sc(x, w, x2, n, N, R, S_, *a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_p4sc(x, w, x2, n, N, R, S_, *a, **k)
+            e1.record()
+            H, W = x.Hp - (R - 1), x.Wp - (S_ - 1)
+            evs.append((e0, e1, 2.0 * x.n_img * H * W * N * (R * S_ * x.C + x2.C), 2))     # 3x3 conv + the fused 1x1 stride-2 shortcut
+            return out
         mc.ops.conv_forward, mc.ops.conv_s1_forward, mc.ops.conv_p4_forward = timed_conv, timed_s1, timed_p4
+        mc.ops.conv_p4_shortcut_forward = timed_p4sc
         flush.fill_(1.0)
         torch.cuda.synchronize()
         engine.use_graph = False                      # per-launch events need the eager launch sequence (the timed loop replays a CUDA graph)
@@ -283,6 +294,7 @@ def main():
         engine.use_graph = True
         torch.cuda.synchronize()
         mc.ops.conv_forward, mc.ops.conv_s1_forward, mc.ops.conv_p4_forward = orig, orig_s1, orig_p4
+        mc.ops.conv_p4_shortcut_forward = orig_p4sc
         um = [(a.elapsed_time(b), f) for a, b, f, m in evs if m >= 1]
         n_p4 = sum(1 for e in evs if e[3] == 2)
         if um:
