@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int BM = 64;
+constexpr int BM_DEFAULT = 64;
 constexpr int BK = 16;
 constexpr int NT = 256;
 
@@ -54,9 +54,9 @@ struct Info {  // generic per-row / per-col / per-reduction-index decoded coordi
 // ---------------------------------------------------------------------------------------------
 template <class P>
 __global__ void __launch_bounds__(NT) igemm_kernel(P p) {
-  constexpr int BN = P::BN;
-  constexpr int TN = BN / 16;  // 16x16 thread grid, TM = 4
-  constexpr int TM = 4;
+  constexpr int BN = P::BN, BM = P::BM;
+  constexpr int TN = BN / 16;  // 16x16 thread grid
+  constexpr int TM = BM / 16;
   constexpr bool DUAL = P::DUAL;
   constexpr bool SEP_A2 = DUAL && !P::A2_SQUARE;
   constexpr bool SEP_B2 = DUAL && !P::B2_SQUARE;
@@ -95,26 +95,41 @@ __global__ void __launch_bounds__(NT) igemm_kernel(P p) {
   const int lr = tid / BK;   // 0..15
   const int64_t rbeg = p.red_begin(z), rend = p.red_end(z);
 
-  for (int64_t r0 = rbeg; r0 < rend; r0 += BK) {
+  // Software pipeline: the gather loads of reduction tile t+1 are issued into registers before tile t is multiplied,
+  // so their latency hides behind the FMAs (one smem stage, two barriers per tile).
+  float pa1[BM / 16], pa2[SEP_A2 ? BM / 16 : 1], pb1[BN / 16], pb2[SEP_B2 ? BN / 16 : 1];
+  auto fetch = [&](int64_t r0) {
     const int64_t kred = r0 + lk;
     Info red = p.red_info(kred, kred < rend);
 #pragma unroll
     for (int i = 0; i < BM / 16; ++i) {
-      int row = lr + 16 * i;
       float a1 = 0.f, a2 = 0.f;
-      p.load_a(rows[row], red, a1, a2);
-      As1[lk][row] = a1;
-      if constexpr (SEP_A2) As2[lk][row] = a2;
+      p.load_a(rows[lr + 16 * i], red, a1, a2);
+      pa1[i] = a1;
+      if constexpr (SEP_A2) pa2[i] = a2;
     }
 #pragma unroll
     for (int i = 0; i < BN / 16; ++i) {
-      int col = lr + 16 * i;
       float b1 = 0.f, b2 = 0.f;
-      p.load_b(cols[col], red, b1, b2);
-      Bs1[lk][col] = b1;
-      if constexpr (SEP_B2) Bs2[lk][col] = b2;
+      p.load_b(cols[lr + 16 * i], red, b1, b2);
+      pb1[i] = b1;
+      if constexpr (SEP_B2) pb2[i] = b2;
+    }
+  };
+  if (rbeg < rend) fetch(rbeg);
+  for (int64_t r0 = rbeg; r0 < rend; r0 += BK) {
+#pragma unroll
+    for (int i = 0; i < BM / 16; ++i) {
+      As1[lk][lr + 16 * i] = pa1[i];
+      if constexpr (SEP_A2) As2[lk][lr + 16 * i] = pa2[i];
+    }
+#pragma unroll
+    for (int i = 0; i < BN / 16; ++i) {
+      Bs1[lk][lr + 16 * i] = pb1[i];
+      if constexpr (SEP_B2) Bs2[lk][lr + 16 * i] = pb2[i];
     }
     __syncthreads();
+    if (r0 + BK < rend) fetch(r0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN], a2[TM], b2[TN];
@@ -200,7 +215,7 @@ struct PixelRows {  // rows = output pixels of the conv
 // ---- A1/A2 forward ------------------------------------------------------------------------
 template <int BN_>
 struct FwdLRT : PixelRows {
-  static constexpr int BN = BN_;
+  static constexpr int BN = BN_, BM = BM_DEFAULT;
   static constexpr bool DUAL = true, A2_SQUARE = true, B2_SQUARE = false;
   const float* x; const float* mu; const float* sig2; const float* bias; const float* eps;
   float* out; float* std_out;
@@ -235,7 +250,7 @@ struct FwdLRT : PixelRows {
 // ---- A4 forward (per-sample weights) ------------------------------------------------------------
 template <int BN_>
 struct FwdEval : PixelRows {
-  static constexpr int BN = BN_;
+  static constexpr int BN = BN_, BM = BM_DEFAULT;
   static constexpr bool DUAL = false, A2_SQUARE = false, B2_SQUARE = false;
   const float* x; const float* w; const float* scale; const float* shift; const float* residual; const float* in_mask;
   float* out;
@@ -279,7 +294,7 @@ struct FwdEval : PixelRows {
 // ---- A3 dx ----------------------------------------------------------------------------------
 template <int BN_>
 struct Dgrad {
-  static constexpr int BN = BN_;
+  static constexpr int BN = BN_, BM = BM_DEFAULT;   // (128-row tiles were measured: no gain, 147 registers)
   static constexpr bool DUAL = true, A2_SQUARE = false, B2_SQUARE = false;
   Geom g;
   const float* gout; const float* dv; const float* mu; const float* sig2; const float* x; float* dx;
@@ -334,7 +349,7 @@ struct Dgrad {
 // ---- A3 dmu / dsigma^2 (split over output pixels) ---------------------------------------------
 template <int BN_>
 struct Wgrad : PixelRows {
-  static constexpr int BN = BN_;
+  static constexpr int BN = BN_, BM = BM_DEFAULT;
   static constexpr bool DUAL = true, A2_SQUARE = false, B2_SQUARE = true;
   const float* gout; const float* dv; const float* x;
   float* part1; float* part2;  // [splits][N][K]
@@ -399,7 +414,7 @@ __global__ void colsum_kernel(const float* __restrict__ g, int64_t M, int N, flo
 
 static int wgrad_splits(const Geom& g) {
   // enough CTAs to fill the machine, but keep each slice >= 256 pixels
-  int tiles = (int)(ceil_div64(g.N, BM) * ceil_div64(g.K, 64));
+  int tiles = (int)(ceil_div64(g.N, BM_DEFAULT) * ceil_div64(g.K, 64));
   int want = (2 * qbn_sm_count() + tiles - 1) / tiles;
   int64_t maxs = ceil_div64(g.M, 256);
   if (want > maxs) want = (int)maxs;
@@ -410,7 +425,7 @@ static int wgrad_splits(const Geom& g) {
 
 template <class P>
 static void launch(P& p, int64_t rows, int cols, int nz, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div64(rows, BM), (unsigned)ceil_div64(cols, P::BN), (unsigned)nz);
+  dim3 grid((unsigned)ceil_div64(rows, P::BM), (unsigned)ceil_div64(cols, P::BN), (unsigned)nz);
   igemm_kernel<P><<<grid, NT, 0, st>>>(p);
 }
 
