@@ -140,6 +140,11 @@ int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, i
                     const float* w, int w_shared, const float* scale, const float* shift,
                     const float* residual, int flags, float* out, void* stream);
 
+/* A5 for every Bayesian layer of a model in ONE launch: jobs_dev = device array of qbn_kl_job; kl_out (zeroed by the caller)
+ * receives the sum over layers (models_bbb.py:254-259), d_mu / d_rho (nullable) the gradients times grad_scale (overwritten). */
+typedef struct qbn_kl_job { const float* mu; const float* rho; float* d_mu; float* d_rho; int64_t n; float sigma_prior; int32_t pad_; } qbn_kl_job;
+int qbn_kl_multi(const void* jobs_dev, int n_jobs, int64_t max_n, float* kl_out, float grad_scale, void* stream);
+
 /* ---- planar-C4 path: the S-batched eval convolution (A4 + A11 glue) with NO operand handling by threads.
  * Activations "planar C4": [C/4 chunk planes][rows][4 floats], rows = the pixels of the zero-bordered maps
  * [n_samples*B][Hp][Wp] (border = the conv padding, must be zero, TF32-exact values).  Sampled weights

@@ -30,6 +30,11 @@ class P4SampleJob(Structure):
                 ("cb_override", c_int32), ("w_sample_stride4", c_int32)]
 
 
+class KLJob(Structure):
+    _fields_ = [("mu", c_void_p), ("rho", c_void_p), ("d_mu", c_void_p), ("d_rho", c_void_p), ("n", c_int64), ("sigma_prior", c_float),
+                ("pad_", c_int32)]
+
+
 class MaskJob(Structure):
     _fields_ = [("out", c_void_p), ("elems", c_int64), ("site_id", c_uint32), ("pad_", c_int32)]
 
@@ -86,6 +91,7 @@ _SIGNATURES = {
     "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, c_float, c_int, P, P]),
     "qbn_p4_shortcut_block_channels": (c_int, [c_int, c_int]),
     "qbn_conv_p4_shortcut_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P, P]),
+    "qbn_kl_multi": (c_int, [P, c_int, c_int64, P, c_float, P]),
     "qbn_dropout_masks_multi": (c_int, [P, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, P]),
     "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
 }

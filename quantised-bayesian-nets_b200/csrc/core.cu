@@ -984,3 +984,36 @@ extern "C" int qbn_dropout_masks_multi(const void* jobs_dev, int n_jobs, int64_t
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
+
+// A5 for a whole model in ONE launch (21 launches -> 1): blockIdx.y = layer job; the total goes to one scalar
+struct qbn_kl_job_dev { const float* mu; const float* rho; float* d_mu; float* d_rho; int64_t n; float sigma_prior; int pad_; };
+__global__ void kl_multi_kernel(const qbn_kl_job_dev* __restrict__ jobs, float* __restrict__ kl_out, float gscale) {
+  const qbn_kl_job_dev jb = jobs[blockIdx.y];
+  const float sp = jb.sigma_prior, inv_sp = 1.0f / sp, inv_sp2 = inv_sp * inv_sp;
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < jb.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gm, gr;
+    acc += (double)kl_term(jb.mu[i], jb.rho[i], sp, inv_sp, inv_sp2, gscale, gm, gr);
+    if (jb.d_mu) jb.d_mu[i] = gm;
+    if (jb.d_rho) jb.d_rho[i] = gr;
+  }
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && acc != 0.0) atomicAdd(kl_out, (float)(0.5 * acc));
+  }
+}
+extern "C" int qbn_kl_multi(const void* jobs_dev, int n_jobs, int64_t max_n, float* kl_out, float grad_scale, void* stream) {
+  QBN_CHECK_ARG(jobs_dev && kl_out && n_jobs > 0 && n_jobs <= 65535 && max_n > 0, "args");
+  int64_t gx = (max_n + 1023) / 1024;
+  if (gx > 64) gx = 64;
+  kl_multi_kernel<<<dim3((unsigned)gx, n_jobs), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const qbn_kl_job_dev*>(jobs_dev), kl_out,
+                                                                                grad_scale);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

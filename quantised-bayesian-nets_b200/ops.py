@@ -255,6 +255,62 @@ def kl_divergence(mu, rho, sigma_prior):
     return KLFunction.apply(mu, rho, float(sigma_prior))
 
 
+class KLMultiFunction(torch.autograd.Function):
+    """Sum of the closed-form KL over every Bayesian layer of a model (models_bbb.py:254-259) in ONE launch, with all
+    gradients produced by the same pass into one flat buffer.  Inputs: sigma priors (host floats), then mu_0, rho_0, mu_1, ..."""
+
+    _tables = {}
+
+    @staticmethod
+    def forward(ctx, priors, *tensors):
+        from ._lib import KLJob
+        _need_cuda(*tensors)
+        dev = tensors[0].device
+        key = (tuple((t.data_ptr(), t.numel()) for t in tensors), tuple(priors), dev.index)
+        ent = KLMultiFunction._tables.get(key)
+        if ent is None:
+            if len(KLMultiFunction._tables) > 8:
+                KLMultiFunction._tables.clear()
+            for t in tensors:
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.QbnError("kl_divergence_multi needs contiguous fp32 parameters")
+            sizes = [t.numel() for t in tensors]
+            offs = [0]
+            for n in sizes:
+                offs.append(offs[-1] + (n + 3) // 4 * 4)
+            flat = torch.zeros(offs[-1], dtype=torch.float32, device=dev)
+            jobs = (KLJob * (len(tensors) // 2))()
+            for i in range(len(tensors) // 2):
+                mu, rho = tensors[2 * i], tensors[2 * i + 1]
+                jobs[i] = KLJob(mu.data_ptr(), rho.data_ptr(), flat.data_ptr() + 4 * offs[2 * i], flat.data_ptr() + 4 * offs[2 * i + 1],
+                                mu.numel(), float(priors[i]), 0)
+            raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(dev)
+            ent = (raw, flat, offs, sizes, max(sizes))
+            KLMultiFunction._tables[key] = ent
+        raw, flat, offs, sizes, max_n = ent
+        kl = torch.zeros((), dtype=torch.float32, device=dev)
+        _lib.call("qbn_kl_multi", _ptr(raw), len(tensors) // 2, max_n, _ptr(kl), 1.0, _stream())
+        ctx.ent = ent
+        ctx.shapes = [t.shape for t in tensors]
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, flat, offs, sizes, _ = ctx.ent
+        scaled = flat * g                      # one launch for every layer's gradient
+        grads = [scaled[offs[i]:offs[i] + sizes[i]].view(ctx.shapes[i]) for i in range(len(sizes))]
+        return (None, *grads)
+
+
+def kl_divergence_multi(pairs):
+    """pairs: [(mu, rho, sigma_prior float), ...] -> scalar sum of the per-layer KL terms."""
+    priors = tuple(float(p[2]) for p in pairs)
+    tensors = []
+    for mu, rho, _ in pairs:
+        tensors += [mu, rho]
+    return KLMultiFunction.apply(priors, *tensors)
+
+
 # ------------------------------------------------------------------------------------------------
 # A8 MC-Dropout
 # ------------------------------------------------------------------------------------------------

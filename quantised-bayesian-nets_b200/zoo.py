@@ -10,6 +10,7 @@ import torch.nn.functional as F
 
 from .stochastic.bbb.conv import Conv2d, ConvReLU2d, fuse_conv_bn, fuse_conv_bn_relu  # noqa: F401
 from .stochastic.bbb.linear import Linear, LinearReLU  # noqa: F401
+from .stochastic.bbb.utils_bbb import model_kl_divergence
 from .stochastic.mcdropout.dropout import BernoulliDropout
 
 UINT_BOUNDS = {8: [0, 255], 7: [0, 127], 6: [0, 63], 5: [0, 31], 4: [0, 15], 3: [0, 7], 2: [0, 3]}      # src/utils.py:18
@@ -97,7 +98,7 @@ class LinearNetwork(nn.Module):
         return (self.mu(x), self.log_var(x).exp())
 
     def get_kl_divergence(self):
-        return sum(m.get_kl_divergence() for m in self.modules() if isinstance(m, (Linear, Conv2d)))
+        return model_kl_divergence(self)
 
 
 class ConvNetwork_LeNet(nn.Module):
@@ -132,7 +133,7 @@ class ConvNetwork_LeNet(nn.Module):
         return F.softmax(x, dim=-1)
 
     def get_kl_divergence(self):
-        return sum(m.get_kl_divergence() for m in self.modules() if isinstance(m, (Linear, Conv2d)))
+        return model_kl_divergence(self)
 
     def fuse_model(self):
         """models_bbb.py:142-143: fuse layers 5,6 (Linear + ReLU) into a LinearReLU container."""
@@ -203,7 +204,7 @@ class ConvNetwork_ResNet(nn.Module):
         return F.softmax(x, dim=-1)
 
     def get_kl_divergence(self):
-        return sum(m.get_kl_divergence() for m in self.modules() if isinstance(m, (Linear, Conv2d)))
+        return model_kl_divergence(self)
 
 
 # ---- MC-Dropout variants (models_mc.py): stock conv/linear parameters + BernoulliDropout ----------

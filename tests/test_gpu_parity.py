@@ -361,3 +361,27 @@ def test_sample_weights_philox_matches_oracle_stream():
     # sharding independence: samples 11..12 drawn alone equal rows 1..2 of the full draw
     w2 = ops.sample_weights(mu, sg, 2, None, seed=77, layer_id=4, sample0=11)
     assert torch.equal(w2, w[1:])
+
+
+def test_kl_multi_matches_per_layer_sum():
+    """qbn_kl_multi (all layers, one launch) == the sum of the per-layer KL terms, values and gradients."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    shapes = [(24, 3, 3, 3), (48, 24, 3, 3), (10, 192), (7,)]
+    priors = [0.05, 0.05, 0.1, 1.0]
+    ps = [(torch.randn(s, generator=g).cuda().requires_grad_(True), (torch.randn(s, generator=g) - 3).cuda().requires_grad_(True)) for s in shapes]
+    ref = sum(ops.kl_divergence(mu, rho, sp) for (mu, rho), sp in zip(ps, priors))
+    (ref * 0.37).backward()
+    ref_g = [(mu.grad.clone(), rho.grad.clone()) for mu, rho in ps]
+    for mu, rho in ps:
+        mu.grad = None
+        rho.grad = None
+    for _ in range(2):                                   # second call reuses the cached job table
+        got = ops.kl_divergence_multi([(mu, rho, sp) for (mu, rho), sp in zip(ps, priors)])
+        (got * 0.37).backward()
+        np.testing.assert_allclose(float(got), float(ref), rtol=1e-6)
+        for (mu, rho), (gm, gr) in zip(ps, ref_g):
+            np.testing.assert_allclose(mu.grad.cpu().numpy(), gm.cpu().numpy(), rtol=1e-5, atol=1e-8)
+            np.testing.assert_allclose(rho.grad.cpu().numpy(), gr.cpu().numpy(), rtol=1e-5, atol=1e-8)
+            mu.grad = None
+            rho.grad = None
