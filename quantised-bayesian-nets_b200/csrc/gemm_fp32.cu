@@ -491,13 +491,40 @@ extern "C" int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared,
   return QBN_OK;
 }
 
+int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, const float* mu_t, const float* sig2_t, const float* x,
+                       float* dx, cudaStream_t st);
+
+// tcgen05 dgrad: stride-1 undilated layers whose channel counts fit the 16-byte K chunks / one TMEM tile
+static bool dgrad_tf32_ok(const qbn_conv_desc* d) {
+  return d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1 && d->N % 4 == 0 && d->C <= 256 &&
+         d->pad_h <= d->R - 1 && d->pad_w <= d->S - 1 && d->pad_h >= 0 && d->pad_w >= 0 && d->out_pad_h == 0 && d->out_pad_w == 0;
+}
+
+// mu_p / sig2_p [N][R][S][C] -> [C][R'][S'][N] with (r', s') = (R-1-r, S-1-s), RNA-rounded to TF32
+__global__ void dgrad_weights_kernel(const float* __restrict__ mu_p, const float* __restrict__ sig2_p, int N, int R, int S, int C,
+                                     float* __restrict__ mu_t, float* __restrict__ sig2_t) {
+  const int64_t total = (int64_t)N * R * S * C;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(o % N);
+    int64_t t = o / N;
+    const int s2 = (int)(t % S);
+    t /= S;
+    const int r2 = (int)(t % R);
+    const int c = (int)(t / R);
+    const int64_t src = (((int64_t)n * R + (R - 1 - r2)) * S + (S - 1 - s2)) * C + c;
+    mu_t[o] = tf32_round(mu_p[src]);
+    sig2_t[o] = tf32_round(sig2_p[src]);
+  }
+}
+
 extern "C" size_t qbn_lrt_bwd_workspace_bytes(const qbn_conv_desc* d) {
   if (!check_desc(d)) return 0;
   Geom g = make_geom(d);
   int splits = wgrad_splits(g);
   size_t dv = (size_t)g.M * g.N * sizeof(float);
   size_t parts = (size_t)2 * splits * g.N * g.K * sizeof(float);
-  return dv + parts + 256;
+  size_t wt = (size_t)2 * g.N * g.K * sizeof(float);     // flipped / transposed weights of the tcgen05 dgrad
+  return dv + parts + wt + 512;
 }
 
 extern "C" int qbn_lrt_bwd(const qbn_conv_desc* d, const float* x, const float* mu_p, const float* sig2_p, const float* grad_out,
@@ -522,7 +549,15 @@ extern "C" int qbn_lrt_bwd(const qbn_conv_desc* d, const float* x, const float* 
 
   lrt_dv_kernel<<<qbn_grid_for(MN, 256), 256, 0, st>>>(grad_out, std_saved, eps, MN, seed, sa, sb, dv);
   QBN_CHECK_LAUNCH();
-  if (dx) {
+  if (dx && math_mode == QBN_MATH_TF32 && dgrad_tf32_ok(d)) {
+    float* mu_t = part2 + (int64_t)splits * g.N * g.K;
+    mu_t = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(mu_t) + 255) / 256 * 256);
+    float* sig2_t = mu_t + (int64_t)g.N * g.K;
+    dgrad_weights_kernel<<<qbn_grid_for((int64_t)g.N * g.K, 256), 256, 0, st>>>(mu_p, sig2_p, g.N, g.R, g.S, g.C, mu_t, sig2_t);
+    QBN_CHECK_LAUNCH();
+    int rc = qbn_umma_lrt_dgrad(d, grad_out, dv, mu_t, sig2_t, x, dx, st);
+    if (rc != QBN_OK) return rc;
+  } else if (dx) {
     if (g.C <= 32) {
       Dgrad<32> p; p.g = g; p.gout = grad_out; p.dv = dv; p.mu = mu_p; p.sig2 = sig2_p; p.x = x; p.dx = dx;
       launch(p, (int64_t)g.B * g.H * g.W, g.C, 1, st);

@@ -50,6 +50,7 @@ struct UParams {
   // tensors
   const void* x; const void* w; const void* w2;
   const float* scale; const float* shift; const float* residual; const float* in_mask; float in_mult;
+  const float* mul2x;            // LRT dgrad: acc *= 2 * mul2x[out index] before the residual add (dx = dx_mean + 2x .* dx_var)
   const float* bias; const float* eps; uint64_t seed; uint32_t sa, sb;
   void* out; float* std_out;
   // int8
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
           if (j < nvalid) {
             if (p.scale) a = __fmul_rn(a, __ldg(p.scale + ch0 + j));
             if (p.shift) a = __fadd_rn(a, __ldg(p.shift + ch0 + j));
+            if (p.mul2x) a = __fmul_rn(a, 2.0f * __ldg(p.mul2x + obase + ch0 + j));
             if (p.residual) a = __fadd_rn(a, __ldg(p.residual + (out_p4 ? p4_index(ch0 + j) : obase + ch0 + j)));
             if (p.flags & QBN_FLAG_RELU) a = fmaxf(a, 0.f);
             if (p.flags & QBN_FLAG_OUT_ROUND_TF32) a = __uint_as_float(tf32_rna(a));
@@ -522,6 +524,27 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
     return QBN_OK;
   }
   return launch_umma<MODE_EVAL>(p, n_samples, st, "qbn_conv_fwd(TF32)");
+}
+
+// A3 dx on the tensor cores (stride-1, undilated layers): the transposed convolution is the forward kernel run on the
+// output gradient with flipped, transposed weights;  dx = conv(g, mu') + 2x .* conv(dv, sigma2')  as two launches, the second
+// accumulating onto the first through the epilogue (residual = dx, multiplier = 2x).
+int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, const float* mu_t, const float* sig2_t, const float* x,
+                       float* dx, cudaStream_t st) {
+  qbn_conv_desc t;
+  memset(&t, 0, sizeof(t));
+  t.B = d->B; t.H = d->Ho; t.W = d->Wo; t.C = d->N; t.N = d->C; t.R = d->R; t.S = d->S;
+  t.stride_h = t.stride_w = 1; t.dil_h = t.dil_w = 1;
+  t.pad_h = d->R - 1 - d->pad_h; t.pad_w = d->S - 1 - d->pad_w;
+  t.Ho = d->H; t.Wo = d->W;
+  UParams p;
+  fill_geom(p, &t);
+  p.x = g; p.w = mu_t; p.x_shared = 1; p.w_shared = 1; p.out = dx;
+  int rc = launch_umma<MODE_EVAL>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad, mean)");
+  if (rc != QBN_OK) return rc;
+  fill_geom(p, &t);
+  p.x = dv; p.w = sig2_t; p.x_shared = 1; p.w_shared = 1; p.out = dx; p.residual = dx; p.mul2x = x;
+  return launch_umma<MODE_EVAL>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad, variance)");
 }
 
 int qbn_umma_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const uint8_t* x, int z_x, const int8_t* w,

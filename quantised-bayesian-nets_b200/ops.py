@@ -187,8 +187,10 @@ class LRTFunction(torch.autograd.Function):
         xc, mu_p, sig2_p, std, eps_c, second = ctx.saved_tensors
         gc = nhwc(_f32(g))
         need_dx = ctx.needs_input_grad[0]
+        # TF32 mode: dx of the stride-1 layers runs on tcgen05 (two launches of the forward kernel on flipped weights); the
+        # weight gradients and every other shape stay on the fp32 CUDA-core kernels (the library decides per descriptor)
         dx, dmu_p, dsig2_p, dbias = lrt_backward(xc, mu_p, sig2_p, gc, std, ctx.d, eps_c, ctx.key, need_dx, ctx.has_bias,
-                                                 QBN_MATH_FP32)
+                                                 ctx.math_mode)
         if ctx.chan_scale is not None:
             raise _lib.QbnError("LRTFunction.backward with chan_scale: fold the scale outside (QAT ConvBn2d does)")
         d_mu, d_second = weight_grad_post(dmu_p, dsig2_p, second, ctx.second_is_sigma, ctx.wshape)

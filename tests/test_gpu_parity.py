@@ -379,7 +379,7 @@ def test_kl_multi_matches_per_layer_sum():
     for _ in range(2):                                   # second call reuses the cached job table
         got = ops.kl_divergence_multi([(mu, rho, sp) for (mu, rho), sp in zip(ps, priors)])
         (got * 0.37).backward()
-        np.testing.assert_allclose(float(got), float(ref), rtol=1e-6)
+        np.testing.assert_allclose(float(got.detach()), float(ref.detach()), rtol=1e-6)
         for (mu, rho), (gm, gr) in zip(ps, ref_g):
             np.testing.assert_allclose(mu.grad.cpu().numpy(), gm.cpu().numpy(), rtol=1e-5, atol=1e-8)
             np.testing.assert_allclose(rho.grad.cpu().numpy(), gr.cpu().numpy(), rtol=1e-5, atol=1e-8)

@@ -205,3 +205,24 @@ def test_tf32_v1_bordered_io():
         b = out.clone()
         b[:, :, 1:-1, 1:-1] = 0
         assert float(b.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(4, 24, 16, 24, 3, 1, 1), (2, 48, 8, 96, 3, 1, 1), (3, 96, 8, 48, 1, 1, 0), (2, 20, 14, 52, 5, 1, 2),
+                                   (2, 24, 16, 48, 3, 2, 1), (8, 192, 1, 12, 1, 1, 0)])
+def test_tf32_lrt_backward_dgrad(shape):
+    """A3 in TF32 mode: dx of stride-1 layers on tcgen05 (forward kernel on flipped weights, second launch accumulating
+    2x .* conv(dv, sigma2')) against the fp32 kernels; the weight gradients are the fp32 kernels' in both modes."""
+    from qbn_b200 import ops
+    B, C, H, N, k, stride, pad = shape
+    g = torch.Generator().manual_seed(13 + C + N)
+    x = ops.nhwc(torch.randn(B, C, H, H, generator=g).cuda())
+    mu = (torch.randn(N, C, k, k, generator=g) / (C * k * k) ** 0.5).cuda()
+    rho = (torch.rand(N, C, k, k, generator=g) * 2 - 5).cuda()
+    p = ops.weight_prep(mu, rho, False, None, want=("mu", "sigma2"))
+    d = ops.make_desc(B, H, H, C, N, k, k, stride, pad, 1)
+    out, std = ops.lrt_forward(x, p["mu"], p["sigma2"], None, d, None, (5, 6, 7), ops.QBN_MATH_FP32)
+    go = torch.randn(out.shape, generator=g).cuda().contiguous(memory_format=torch.channels_last) if out.dim() == 4 else torch.randn(out.shape, generator=g).cuda()
+    ref = ops.lrt_backward(x, p["mu"], p["sigma2"], go, std, d, None, (5, 6, 7), True, False, ops.QBN_MATH_FP32)
+    got = ops.lrt_backward(x, p["mu"], p["sigma2"], go, std, d, None, (5, 6, 7), True, False, ops.QBN_MATH_TF32)
+    close(got[0], ref[0], 2e-3, 2e-3)
+    assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
