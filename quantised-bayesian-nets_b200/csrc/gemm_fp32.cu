@@ -494,9 +494,9 @@ extern "C" int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared,
 int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, const float* mu_t, const float* sig2_t, const float* x,
                        float* dx, cudaStream_t st);
 
-// tcgen05 dgrad: stride-1 undilated layers whose channel counts fit the 16-byte K chunks / one TMEM tile
+// tcgen05 dgrad: undilated layers (any stride) whose channel counts fit the 16-byte K chunks / one TMEM tile
 static bool dgrad_tf32_ok(const qbn_conv_desc* d) {
-  return d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1 && d->N % 4 == 0 && d->C <= 256 &&
+  return d->dil_h == 1 && d->dil_w == 1 && d->N % 4 == 0 && d->C <= 256 &&
          d->pad_h <= d->R - 1 && d->pad_w <= d->S - 1 && d->pad_h >= 0 && d->pad_w >= 0 && d->out_pad_h == 0 && d->out_pad_w == 0;
 }
 

@@ -50,6 +50,7 @@ struct UParams {
   // tensors
   const void* x; const void* w; const void* w2;
   const float* scale; const float* shift; const float* residual; const float* in_mask; float in_mult;
+  int tr_sh, tr_sw;              // transposed convolution (dgrad of a strided conv): input coordinate = (h0 + r) / tr_s when divisible
   const float* mul2x;            // LRT dgrad: acc *= 2 * mul2x[out index] before the residual add (dx = dx_mean + 2x .* dx_var)
   const float* bias; const float* eps; uint64_t seed; uint32_t sa, sb;
   void* out; float* std_out;
@@ -151,8 +152,13 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
         const bool kv = k < p.K;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int hi = rh0[i] + dr, wi = rw0[i] + ds;
-          const bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+          int hi = rh0[i] + dr, wi = rw0[i] + ds;
+          bool ok = kv && hi >= 0 && wi >= 0;
+          if (p.tr_sh > 1 || p.tr_sw > 1) {       // transposed conv: only coordinates on the stride grid carry a gradient
+            ok = ok && (hi % p.tr_sh == 0) && (wi % p.tr_sw == 0);
+            hi /= p.tr_sh; wi /= p.tr_sw;
+          }
+          ok = ok && hi < p.H && wi < p.W;
           areg[i] = make_uint4(0u, 0u, 0u, 0u);
           if (ok) areg[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(xs) + rbase[i] + (hi * p.W + wi) * p.C + c));
         }
@@ -225,8 +231,13 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
         const bool kv = k < p.K;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int hi = rh0[i] + dr, wi = rw0[i] + ds;
-          const bool ok = kv && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+          int hi = rh0[i] + dr, wi = rw0[i] + ds;
+          bool ok = kv && hi >= 0 && wi >= 0;
+          if (p.tr_sh > 1 || p.tr_sw > 1) {
+            ok = ok && (hi % p.tr_sh == 0) && (wi % p.tr_sw == 0);
+            hi /= p.tr_sh; wi /= p.tr_sw;
+          }
+          ok = ok && hi < p.H && wi < p.W;
           const float* src = reinterpret_cast<const float*>(xs) + (ok ? rbase[i] + (hi * p.W + wi) * p.C + c : 0);
           cp_async16(smem_u32(sa + ((size_t)kc * p.a_pitch + r0 + 16 * i) * 16), src, ok ? 16u : 0u);
         }
@@ -536,13 +547,15 @@ int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, 
   t.B = d->B; t.H = d->Ho; t.W = d->Wo; t.C = d->N; t.N = d->C; t.R = d->R; t.S = d->S;
   t.stride_h = t.stride_w = 1; t.dil_h = t.dil_w = 1;
   t.pad_h = d->R - 1 - d->pad_h; t.pad_w = d->S - 1 - d->pad_w;
-  t.Ho = d->H; t.Wo = d->W;
+  t.Ho = d->H; t.Wo = d->W;                       // rows of the GEMM = input pixels of the forward conv
   UParams p;
   fill_geom(p, &t);
+  p.tr_sh = d->stride_h; p.tr_sw = d->stride_w;   // strided forward conv: its gradient lives on the stride grid (transposed conv)
   p.x = g; p.w = mu_t; p.x_shared = 1; p.w_shared = 1; p.out = dx;
   int rc = launch_umma<MODE_EVAL>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad, mean)");
   if (rc != QBN_OK) return rc;
   fill_geom(p, &t);
+  p.tr_sh = d->stride_h; p.tr_sw = d->stride_w;
   p.x = dv; p.w = sig2_t; p.x_shared = 1; p.w_shared = 1; p.out = dx; p.residual = dx; p.mul2x = x;
   return launch_umma<MODE_EVAL>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad, variance)");
 }

@@ -208,7 +208,7 @@ def test_tf32_v1_bordered_io():
 
 
 @pytest.mark.parametrize("shape", [(4, 24, 16, 24, 3, 1, 1), (2, 48, 8, 96, 3, 1, 1), (3, 96, 8, 48, 1, 1, 0), (2, 20, 14, 52, 5, 1, 2),
-                                   (2, 24, 16, 48, 3, 2, 1), (8, 192, 1, 12, 1, 1, 0)])
+                                   (2, 24, 16, 48, 3, 2, 1), (8, 192, 1, 12, 1, 1, 0), (2, 24, 16, 48, 1, 2, 0), (2, 8, 7, 12, 3, 2, 1)])
 def test_tf32_lrt_backward_dgrad(shape):
     """A3 in TF32 mode: dx of stride-1 layers on tcgen05 (forward kernel on flipped weights, second launch accumulating
     2x .* conv(dv, sigma2')) against the fp32 kernels; the weight gradients are the fp32 kernels' in both modes."""
