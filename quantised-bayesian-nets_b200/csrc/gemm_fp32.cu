@@ -493,6 +493,8 @@ extern "C" int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared,
 
 int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, const float* mu_t, const float* sig2_t, const float* x,
                        float* dx, cudaStream_t st);
+int qbn_umma_lrt_wgrad(const qbn_conv_desc* d, const float* x, const float* g, const float* dv, float* part1, float* part2, int splits,
+                       cudaStream_t st);
 
 // tcgen05 dgrad: undilated layers (any stride) whose channel counts fit the 16-byte K chunks / one TMEM tile
 static bool dgrad_tf32_ok(const qbn_conv_desc* d) {
@@ -567,7 +569,22 @@ extern "C" int qbn_lrt_bwd(const qbn_conv_desc* d, const float* x, const float* 
     }
     QBN_CHECK_LAUNCH();
   }
-  {
+  if (math_mode == QBN_MATH_TF32) {
+    // tcgen05 weight gradients: pixels as the reduction dimension, split over CTAs into the same workspace
+    const int kt = g.K >= 128 ? 128 : (g.K + 15) / 16 * 16;
+    const int tiles = (int)(ceil_div64(g.N, 128) * ceil_div64(g.K, kt));
+    int splits_t = (2 * qbn_sm_count() + tiles - 1) / tiles;
+    const int64_t maxs = ceil_div64(g.M, 256);
+    if (splits_t > maxs) splits_t = (int)maxs;
+    if (splits_t > splits) splits_t = splits;
+    if (splits_t < 1) splits_t = 1;
+    int rc = qbn_umma_lrt_wgrad(d, x, grad_out, dv, part1, part2, splits_t, st);
+    if (rc != QBN_OK) return rc;
+    int64_t nk = (int64_t)g.N * g.K;
+    split_reduce_kernel<<<qbn_grid_for(nk, 256), 256, 0, st>>>(part1, splits_t, nk, dmu_p);
+    split_reduce_kernel<<<qbn_grid_for(nk, 256), 256, 0, st>>>(part2, splits_t, nk, dsig2_p);
+    QBN_CHECK_LAUNCH();
+  } else {
     Wgrad<64> p; p.g = g; p.gout = grad_out; p.dv = dv; p.x = x; p.part1 = part1; p.part2 = part2;
     p.chunk = ceil_div64(ceil_div64(g.M, splits), BK) * BK;
     launch(p, g.N, g.K, splits, st);

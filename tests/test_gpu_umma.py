@@ -210,8 +210,8 @@ def test_tf32_v1_bordered_io():
 @pytest.mark.parametrize("shape", [(4, 24, 16, 24, 3, 1, 1), (2, 48, 8, 96, 3, 1, 1), (3, 96, 8, 48, 1, 1, 0), (2, 20, 14, 52, 5, 1, 2),
                                    (2, 24, 16, 48, 3, 2, 1), (8, 192, 1, 12, 1, 1, 0), (2, 24, 16, 48, 1, 2, 0), (2, 8, 7, 12, 3, 2, 1)])
 def test_tf32_lrt_backward_dgrad(shape):
-    """A3 in TF32 mode: dx of stride-1 layers on tcgen05 (forward kernel on flipped weights, second launch accumulating
-    2x .* conv(dv, sigma2')) against the fp32 kernels; the weight gradients are the fp32 kernels' in both modes."""
+    """A3 in TF32 mode against the fp32 kernels: dx on tcgen05 (forward kernel on flipped weights, second launch accumulating
+    2x .* conv(dv, sigma2'); transposed-conv gather for strided layers) and the weight gradients on tcgen05 (umma_wgrad.cu)."""
     from qbn_b200 import ops
     B, C, H, N, k, stride, pad = shape
     g = torch.Generator().manual_seed(13 + C + N)
@@ -225,4 +225,5 @@ def test_tf32_lrt_backward_dgrad(shape):
     ref = ops.lrt_backward(x, p["mu"], p["sigma2"], go, std, d, None, (5, 6, 7), True, False, ops.QBN_MATH_FP32)
     got = ops.lrt_backward(x, p["mu"], p["sigma2"], go, std, d, None, (5, 6, 7), True, False, ops.QBN_MATH_TF32)
     close(got[0], ref[0], 2e-3, 2e-3)
-    assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+    close(got[1], ref[1], 2e-3, 2e-3)          # dmu: g^T * im2col(x) with the pixels as the tcgen05 reduction dimension
+    close(got[2], ref[2], 2e-3, 2e-3)          # dsigma^2: dv^T * im2col(x)^2
