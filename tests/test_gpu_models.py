@@ -104,9 +104,13 @@ def test_resnet_engine_philox_sharding_invariance():
     assert not torch.allclose(a, c)
 
 
-def test_resnet_lrt_training_step(golden):
-    """trainer.py:95-104 on the drop-in model: LRT forward, KL, ELBO, backward; BN in batch-stat mode."""
-    from qbn_b200 import noise
+@pytest.mark.parametrize("mode,tol", [("fp32", 1.0), ("tf32", 20.0)])
+def test_resnet_lrt_training_step(golden, mode, tol):
+    """trainer.py:95-104 on the drop-in model: LRT forward, KL, ELBO, backward; BN in batch-stat mode.
+    tf32: forward AND backward contractions on tcgen05 (dual-accumulator LRT forward, dgrad on flipped weights, wgrad with the
+    pixels as the reduction dimension); tolerances scaled by 20 (21 stacked TF32 layers, batch-norm renormalisation in between)."""
+    from qbn_b200 import config, noise
+    config.set_math_mode(mode)
     g = golden("resnet")
     P, x, net = _resnet()
     order = _bbb_modules_in_forward_order(net, x.cuda())
@@ -115,15 +119,15 @@ def test_resnet_lrt_training_step(golden):
     eps = O.replay_noise(710, [o[1] for o in order])
     with noise.inject([e.cuda() for e in eps]):
         y = net(x.cuda())
-    close(y, g["y_train"], 1e-3, 1e-4)
+    close(y, g["y_train"], 1e-3 * tol, 1e-4 * tol)
     kl = net.get_kl_divergence()
     loss = torch.nn.functional.nll_loss(torch.log(y + 1e-8), tgt.cuda()) + 0.01 * kl / (4 * 176)
-    close(loss, g["loss"], 1e-4, 1e-5)
+    close(loss, g["loss"], 1e-4 * tol, 1e-5 * tol)
     loss.backward()
     sd = dict(net.named_parameters())
     # The classifier's gradients see no ReLU downstream: strict.
     for key in ("layers.9.weight", "layers.9.std"):
-        close(sd[key].grad, g["g." + key], 1e-3, 1e-4)
+        close(sd[key].grad, g["g." + key], 1e-3 * tol, 1e-4 * tol)
     # Deeper gradients pass through ReLU masks.  A pre-activation within ~1e-5 of zero flips its mask
     # under ANY fp32 re-association (measured on the B200: torch's own cuDNN twin of this network in
     # channels_last vs NCHW flips exactly one of 12288 masks of layers.6.1 and moves layers.0.weight's
@@ -132,8 +136,8 @@ def test_resnet_lrt_training_step(golden):
     for key in ("layers.0.weight", "layers.0.std", "layers.5.0.shortcut.0.weight", "layers.5.0.shortcut.0.std", "layers.1.weight"):
         got, ref = sd[key].grad.detach().cpu().double(), torch.as_tensor(g["g." + key]).double()
         l2 = float((got - ref).norm() / ref.norm())
-        assert l2 < 0.05, (key, l2)
-    close(net.layers[1].running_mean, g["bn1.running_mean"], 1e-4, 1e-5)
+        assert l2 < (0.05 if mode == "fp32" else 0.1), (key, l2)
+    close(net.layers[1].running_mean, g["bn1.running_mean"], 1e-4 * tol, 1e-5 * tol)
 
 
 def test_lenet_eval_train_and_mlp(golden):
