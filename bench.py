@@ -272,7 +272,7 @@ def main():
             out = orig_p4(x, w, n, N, R, S_, stride, *a, **k)
             e1.record()
             bh, bw = ((R - 1) // 2, (S_ - 1) // 2) if stride == 1 else (1, 1)
-            H, W = x.Hp - 2 * bh, x.Wp - 2 * bw                     # output pixels (the map geometry is the output's)
+            H, W = x.Hp - bh, x.Wp - bw                             # output pixels (the map geometry is the output's)
             evs.append((e0, e1, 2.0 * x.n_img * H * W * N * R * S_ * x.C, 2))
             return out
         orig_p4sc = mc.ops.conv_p4_shortcut_forward
@@ -282,7 +282,7 @@ def main():
             e0.record()
             out = orig_p4sc(x, w, x2, n, N, R, S_, *a, **k)
             e1.record()
-            H, W = x.Hp - (R - 1), x.Wp - (S_ - 1)
+            H, W = x.Hp - (R - 1) // 2, x.Wp - (S_ - 1) // 2
             evs.append((e0, e1, 2.0 * x.n_img * H * W * N * (R * S_ * x.C + x2.C), 2))     # 3x3 conv + the fused 1x1 stride-2 shortcut
             return out
         mc.ops.conv_forward, mc.ops.conv_s1_forward, mc.ops.conv_p4_forward = timed_conv, timed_s1, timed_p4

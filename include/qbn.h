@@ -125,7 +125,8 @@ int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64_t n, int n
                                       w is ONE blocked tensor whose N rows are the samples' weights stacked (row s*N + n), so
                                       the input is staged once and one accumulator tile holds every sample (n_samples*N <= 256) */
 #define QBN_FLAG_RELU_PRE 64        /* qbn_conv_p4_fwd: ReLU right after the affine, before the output mask / residual */
-#define QBN_FLAG_OUT_P4 16         /* qbn_conv_fwd (TF32): out and residual are planar-C4 (see below)         */
+#define QBN_FLAG_OUT_P4 16         /* qbn_conv_fwd (TF32): out and residual are planar-C4 with out_pad zero rows on top /
+                                      zero columns on the left of every map and a zero tail (see below)          */
 int qbn_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const float* x,
                  const float* w, int w_shared, const float* scale, const float* shift,
                  const float* residual, int flags, const float* in_mask, float in_mult, float* out,
@@ -146,17 +147,20 @@ typedef struct qbn_kl_job { const float* mu; const float* rho; float* d_mu; floa
 int qbn_kl_multi(const void* jobs_dev, int n_jobs, int64_t max_n, float* kl_out, float grad_scale, void* stream);
 
 /* ---- planar-C4 path: the S-batched eval convolution (A4 + A11 glue) with NO operand handling by threads.
- * Activations "planar C4": [C/4 chunk planes][rows][4 floats], rows = the pixels of the zero-bordered maps
- * [n_samples*B][Hp][Wp] (border = the conv padding, must be zero, TF32-exact values).  Sampled weights
+ * Activations "planar C4": [C/4 chunk planes][plane_rows][4 floats]; a plane holds the pixels of the zero-bordered maps
+ * [n_samples*B][Hp][Wp] followed by a zero tail.  The zeros are SHARED between neighbours: ph zero rows on TOP of every map
+ * (= the bottom padding of the map above), pw zero columns on the LEFT of every row (= the right padding of the row above),
+ * Hp = H + ph, Wp = W + pw, tail = ph*Wp + pw pixels after the last map; *_plane_rows = rows per chunk plane of that tensor.
+ * Values TF32-exact; the caller zero-initialises buffers once (kernels write border pixels as zeros, never the tail).  Sampled weights
  * "blocked": [sample][C/CB][R*S][CB/4][n_pad][4] (CB depends on C and the stride, n_pad = N rounded up to 16: qbn_p4_weight_floats), written by
  * qbn_sample_weights_blocked from mu/sigma blocked once by qbn_p4_block_weights.  A tile's operands are then
  * contiguous runs moved by bulk copies, every filter tap is a row-shifted UMMA descriptor on one smem image
  * (zero-copy im2col), and the epilogue's 16-byte stores are contiguous across a warp.
- *   stride 1: odd RxS "same" conv, Hp = H + R - 1.
- *   stride 2: 3x3 pad 1 or 1x1 pad 0; Hp = H_out + 2; x is PHASE-SPLIT: [C/4][4 phases][n_samples*B*Hp*Wp][4]
+ *   stride 1: odd RxS "same" conv, Hp = H + (R-1)/2.
+ *   stride 2: 3x3 pad 1 or 1x1 pad 0; Hp = H_out + 1; x is PHASE-SPLIT: [C/4][4 phases x n_samples*B*Hp*Wp (+ tail)][4]
  *             where phase (a,b) holds pixels (2i+a, 2j+b) of the full-resolution map at (i+1, j+1), as written
  *             by the producing qbn_conv_p4_fwd with QBN_FLAG_OUT_PHASE_SPLIT (into a pre-zeroed buffer).
- * out / residual: planar C4 [N/4][n_samples*B*Hp*Wp][4]; border rows of out are written as zeros. */
+ * out / residual: planar C4 [N/4][out_plane_rows][4] with the output geometry; border pixels of out are written as zeros. */
 int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long long* out_floats /* host */);
 int qbn_p4_block_weights(const float* w_ohwi /* [n_mats][N][taps][C] */, int n_mats, int N, int C, int taps,
                          int stride, int cb_override /* 0: layout rule */, float* out, void* stream);
@@ -177,24 +181,26 @@ int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t m
 /* epilogue order: affine -> [RELU_PRE] -> [out_mask: MC-Dropout of the OUTPUT, x*mask[img][n]*mult, A8] -> [+residual]
  * -> [RELU] -> [RNA]; that is conv-BN-ReLU-dropout (models_mc.py:125-129) and conv-BN-dropout-add-ReLU (:130-157) */
 int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
-                    const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
-                    const float* out_mask /* nullable [n_samples*B][N] */, float out_mask_mult, int flags, float* out,
-                    void* stream);
+                    long long x_plane_rows, const float* w, int w_shared, const float* scale, const float* shift,
+                    const float* residual, long long res_plane_rows, const float* out_mask /* nullable [n_samples*B][N] */,
+                    float out_mask_mult, int flags, float* out, long long out_plane_rows, void* stream);
 /* Stride-1 conv with the BasicBlock's 1x1 stride-2 shortcut FUSED as extra K blocks (models_bbb.py:163-178):
  *   out = act( conv_RxS(x, W) + conv_1x1,stride2(x_block, Wsc) + shift ),  W and Wsc carrying their BatchNorm scales
  * (qbn_p4_sample_job.chan_scale), so both branches accumulate in ONE TMEM tile: no shortcut launch, no residual round trip.
  * x2 = the block input, phase-split (its phase (0,0) IS the stride-2 sampling grid), C2 channels; every sample's weight tensor
  * is [main blocks][shortcut blocks of qbn_p4_shortcut_block_channels(C, C2) channels, one tap]. */
 int qbn_p4_shortcut_block_channels(int C, int C2);
-int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x, const float* w,
-                             const float* x2, int C2, const float* scale, const float* shift, int flags, float* out, void* stream);
+int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x,
+                             long long x_plane_rows, const float* w, const float* x2, long long x2_plane_rows, int C2,
+                             const float* scale, const float* shift, int flags, float* out, long long out_plane_rows,
+                             void* stream);
 /* Bernoulli(keep) masks of several dropout sites in ONE launch: jobs_dev = device array of qbn_mask_job; the mask of
  * site j, sample s is out[j][s][elems], Philox(seed, site_id, sample0 + s, element) */
 typedef struct qbn_mask_job { float* out; int64_t elems; uint32_t site_id; int32_t pad_; } qbn_mask_job;
 int qbn_dropout_masks_multi(const void* jobs_dev, int n_jobs, int64_t max_elems, int n_samples, float keep_prob,
                             uint64_t seed, uint32_t sample0, void* stream);
 /* global average pool of planar-C4 maps -> [n_img][C] (divisor = interior pixel count) */
-int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, float divisor, float* out, void* stream);
+int qbn_avgpool_p4(const float* x, int64_t n_img, int HW /* Hp*Wp */, int64_t plane_rows, int C, float divisor, float* out, void* stream);
 
 /* ---- A8 standalone: x[b,h,w,c] * mask[b,c] * mult (dropout.py:35-39); mask NULL -> Philox ---- */
 int qbn_dropout_fwd(const float* x, int64_t rows /*B*/, int64_t hw, int64_t C, const float* mask,

@@ -88,12 +88,14 @@ _SIGNATURES = {
     "qbn_p4_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "qbn_sample_weights_blocked": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, c_uint64, c_uint32, c_uint32, P, c_int, P]),
     "qbn_sample_weights_blocked_multi": (c_int, [P, c_int, c_int64, c_int, c_uint64, c_uint32, c_int, P]),
-    "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, c_float, c_int, P, P]),
+    "qbn_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int, P, P, P, c_int64, P, c_float,
+                                c_int, P, c_int64, P]),
     "qbn_p4_shortcut_block_channels": (c_int, [c_int, c_int]),
-    "qbn_conv_p4_shortcut_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P, P]),
+    "qbn_conv_p4_shortcut_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P, P, c_int64, c_int, P, P, c_int, P,
+                                         c_int64, P]),
     "qbn_kl_multi": (c_int, [P, c_int, c_int64, P, c_float, P]),
     "qbn_dropout_masks_multi": (c_int, [P, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, P]),
-    "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
+    "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int64, c_int, c_float, P, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

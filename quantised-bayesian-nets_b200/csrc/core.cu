@@ -870,11 +870,10 @@ extern "C" int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_
 
 // global average pool of planar-C4 maps: x [C/4][n_img * HW][4] -> out [n_img][C]; one warp per (image, chunk)
 // reads HW contiguous 16-byte rows.  The zero border contributes nothing; divisor = interior size.
-__global__ void avgpool_p4_kernel(const float* __restrict__ x, int64_t n_img, int HW, int C, float inv, float* __restrict__ out) {
+__global__ void avgpool_p4_kernel(const float* __restrict__ x, int64_t n_img, int HW, int64_t plane, int C, float inv, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int chunks = C >> 2;
-  const int64_t plane = n_img * HW;
   for (int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < n_img * chunks; wi += warps) {
     const int64_t img = wi / chunks;
     const int j = (int)(wi - img * chunks);
@@ -894,13 +893,13 @@ __global__ void avgpool_p4_kernel(const float* __restrict__ x, int64_t n_img, in
     if (lane == 0) *reinterpret_cast<float4*>(out + img * C + 4 * j) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
   }
 }
-extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int C, float divisor, float* out, void* stream) {
-  QBN_CHECK_ARG(x && out && n_img > 0 && HW > 0 && C > 0 && C % 4 == 0 && divisor > 0.f, "args");
+extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int64_t plane_rows, int C, float divisor, float* out, void* stream) {
+  QBN_CHECK_ARG(x && out && n_img > 0 && HW > 0 && C > 0 && C % 4 == 0 && divisor > 0.f && plane_rows >= n_img * HW, "args");
   const int64_t warps = n_img * (C / 4);
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = (int64_t)qbn_sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  avgpool_p4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_img, HW, C, 1.0f / divisor, out);
+  avgpool_p4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_img, HW, plane_rows, C, 1.0f / divisor, out);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -2,7 +2,8 @@
 // layout helpers (core.cu).
 //
 // Activations, "planar C4":  [C/4 chunk planes][rows][4 floats], rows = n_samples * B * Hp * Wp pixels of the
-// zero-bordered maps.  One 16-byte K-chunk of a pixel is contiguous and consecutive pixels of one chunk plane
+// zero-bordered maps + a zero tail.  Zeros are shared between neighbours: ph zero rows on TOP of every map, pw zero
+// columns on the LEFT of every row (Hp = H + ph, Wp = W + pw), tail = ph * Wp + pw pixels after the last map.  One 16-byte K-chunk of a pixel is contiguous and consecutive pixels of one chunk plane
 // are contiguous, which is exactly one column of UMMA's K-major no-swizzle operand layout: a tile's chunk
 // plane is ONE bulk (TMA-engine) copy, and an epilogue thread (= one pixel) stores 16 bytes next to its
 // neighbour's (fully coalesced).

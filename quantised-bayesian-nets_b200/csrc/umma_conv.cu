@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     if (p.oph | p.opw) {
       const int mm = mv ? m : 0;
       const int wo = mm % p.Wo, t2 = mm / p.Wo, ho = t2 % p.Ho, b = t2 / p.Ho;
-      const int Hop = p.Ho + 2 * p.oph, Wop = p.Wo + 2 * p.opw;
+      // planar-C4 maps share their zeros: borders on top / left only (p4_layout.cuh); NHWC bordered maps have them all around
+      const bool p4 = p.flags & QBN_FLAG_OUT_P4;
+      const int Hop = p.Ho + (p4 ? 1 : 2) * p.oph, Wop = p.Wo + (p4 ? 1 : 2) * p.opw;
       prow = (((size_t)z * p.B + b) * Hop + ho + p.oph) * Wop + wo + p.opw;
     }
     const size_t orow = prow * Nrow;
@@ -502,14 +504,16 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
       qbn_set_error("qbn_conv_fwd: planar-C4 output needs N %% 4 == 0 (N=%d)", d->N);
       return QBN_ERR_UNSUPPORTED;
     }
-    p.out_plane = (long long)n_samples * d->B * (d->Ho + 2 * d->out_pad_h) * (d->Wo + 2 * d->out_pad_w);
+    const long long hop = d->Ho + d->out_pad_h, wop = d->Wo + d->out_pad_w;
+    p.out_plane = (long long)n_samples * d->B * hop * wop + (long long)d->out_pad_h * wop + d->out_pad_w;     // maps + zero tail
   }
   // Shared input (first layer): stack the samples' weights along N — [S][N][K] IS an [S*N][K] matrix — so
   // the input tile is staged once for all samples and one accumulator tile holds every sample's channels.
   if (x_shared && !w_shared && n_samples > 1 && d->N % 8 == 0 && n_samples * d->N <= 256 && !residual && !in_mask) {
     p.n_split = d->N;
     p.N = n_samples * d->N;
-    p.sample_out_stride = (long long)d->B * (d->Ho + 2 * d->out_pad_h) * (d->Wo + 2 * d->out_pad_w) * d->N;
+    const int bmul = (flags & QBN_FLAG_OUT_P4) ? 1 : 2;
+    p.sample_out_stride = (long long)d->B * (d->Ho + bmul * d->out_pad_h) * (d->Wo + bmul * d->out_pad_w) * d->N;
     return launch_umma<MODE_EVAL>(p, 1, st, "qbn_conv_fwd(TF32, sample-stacked)");
   }
   // Wide linear layers (N > 256, e.g. LeNet's 2450 -> 500): one accumulator tile holds at most 256 columns, so the output

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         // rows [g0, g0 + RA) of every strip, clamped to the tensor (rows outside feed border outputs only)
         const long long g0 = (long long)z * p.Qs + q0 - p.d_before;
         const long long lo = g0 < 0 ? 0 : g0;
-        const long long hi = (g0 + p.RA > p.strip_rows) ? p.strip_rows : g0 + p.RA;
+        const long long lim = p.x_plane - (long long)(p.n_strips - 1) * p.strip_rows;      // rows readable from a strip's start (incl. the zero tail)
+        const long long hi = (g0 + p.RA > lim) ? lim : g0 + p.RA;
         const uint32_t row_bytes = (uint32_t)(hi - lo) * 16;
         const uint32_t dst_off = (uint32_t)(lo - g0) * 16;
         for (int cb = 0; cb < p.n_cb; ++cb) {
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         // ---- fused shortcut: rows [q0, q0+128) of the second input, no halo, one tap
         if (p.n_cb2) {
           const long long r0 = (long long)z * p.Qs + q0;
-          const long long r1 = (r0 + TM > p.strip_rows) ? p.strip_rows : r0 + TM;
+          const long long r1 = (r0 + TM > p.x2_plane) ? p.x2_plane : r0 + TM;
           const uint32_t rb2 = (uint32_t)(r1 - r0) * 16;
           for (int cb = 0; cb < p.n_cb2; ++cb) {
             mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
       uint32_t b, rem, hh, ww;
       divmod(qv ? (uint32_t)q : 0u, plane, p.mg_plane, b, rem);
       divmod(rem, (uint32_t)p.Wp, p.mg_wp, hh, ww);
-      const bool interior = qv && (int)hh >= p.bh && (int)hh < p.Hp - p.bh && (int)ww >= p.bw && (int)ww < p.Wp - p.bw;
+      const bool interior = qv && (int)hh >= p.bh && (int)ww >= p.bw;      // zero rows on TOP of every map, zero columns on its LEFT
       const long long in_row = (long long)z * p.Qs + q;
       long long orow = in_row;
       bool store = qv;
@@ -435,15 +436,18 @@ extern "C" int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long
   return QBN_OK;
 }
 
+struct P4Planes { long long x, res, out, x2; };      // rows per chunk plane of each tensor (phases * maps + zero tail)
 static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
                           int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
-                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, void* stream);
+                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream);
 
 extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
-                               const float* w, int w_shared, const float* scale, const float* shift, const float* residual,
-                               const float* out_mask, float out_mask_mult, int flags, float* out, void* stream) {
+                               long long x_plane_rows, const float* w, int w_shared, const float* scale, const float* shift,
+                               const float* residual, long long res_plane_rows, const float* out_mask, float out_mask_mult, int flags,
+                               float* out, long long out_plane_rows, void* stream) {
+  P4Planes pl = {x_plane_rows, res_plane_rows, out_plane_rows, 0};
   return conv_p4_launch(n_samples, B, Hp, Wp, C, N, R, S, stride, x, w, w_shared, scale, shift, residual, out_mask, out_mask_mult, flags, out,
-                        nullptr, 0, 0, stream);
+                        nullptr, 0, 0, pl, stream);
 }
 
 // channels per block of the fused shortcut input: largest multiple of 8 dividing C2 that fits the main conv's activation slot
@@ -458,8 +462,9 @@ static int p4_shortcut_block(int C, int C2) {
 }
 extern "C" int qbn_p4_shortcut_block_channels(int C, int C2) { return p4_shortcut_block(C, C2); }
 
-extern "C" int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x, const float* w,
-                                        const float* x2, int C2, const float* scale, const float* shift, int flags, float* out,
+extern "C" int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, const float* x,
+                                        long long x_plane_rows, const float* w, const float* x2, long long x2_plane_rows, int C2,
+                                        const float* scale, const float* shift, int flags, float* out, long long out_plane_rows,
                                         void* stream) {
   QBN_CHECK_ARG(x2 && C2 > 0 && C2 % 8 == 0, "second input");
   const int cb2 = p4_shortcut_block(C, C2);
@@ -467,12 +472,13 @@ extern "C" int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, in
     qbn_set_error("qbn_conv_p4_shortcut_fwd: no channel blocking for C2=%d", C2);
     return QBN_ERR_UNSUPPORTED;
   }
-  return conv_p4_launch(n_samples, B, Hp, Wp, C, N, R, S, 1, x, w, 0, scale, shift, nullptr, nullptr, 1.0f, flags, out, x2, C2, cb2, stream);
+  P4Planes pl = {x_plane_rows, 0, out_plane_rows, x2_plane_rows};
+  return conv_p4_launch(n_samples, B, Hp, Wp, C, N, R, S, 1, x, w, 0, scale, shift, nullptr, nullptr, 1.0f, flags, out, x2, C2, cb2, pl, stream);
 }
 
 static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
                           int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
-                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, void* stream) {
+                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   QBN_CHECK_ARG(x && w && out, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && Hp > 2 && Wp > 2 && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
@@ -498,7 +504,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.n_chunks = (stacked ? n_samples : 1) * N / 4;
   p.bh = s1 ? (R - 1) / 2 : 1;
   p.bw = s1 ? (S - 1) / 2 : 1;
-  QBN_CHECK_ARG(Hp > 2 * p.bh && Wp > 2 * p.bw, "padded extent must exceed the border");
+  QBN_CHECK_ARG(Hp > p.bh && Wp > p.bw, "padded extent must exceed the border");
   p.Qs = B * Hp * Wp;
   p.tiles_per_sample = (p.Qs + TM - 1) / TM;
   p.total_tiles = p.tiles_per_sample * (stacked ? 1 : n_samples);
@@ -517,7 +523,13 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     p.n_strips = (R == 3) ? 4 : 1;
     p.d_before = (R == 3) ? Wp + 1 : 0;
   }
-  p.x_plane = p.strip_rows * ((s2 && R == 1) ? 4 : p.n_strips);   // a 1x1 stride-2 conv reads phase (0,0) of a 4-phase tensor
+  // plane strides come from the caller: a plane = phases * maps + the zero tail that the last map's bottom/right taps read
+  const long long tail = s1 ? (long long)p.bh * Wp + p.bw : 0;
+  p.x_plane = pl.x;
+  if (p.x_plane < p.strip_rows * (s2 ? 4 : 1) + tail) {
+    qbn_set_error("qbn_conv_p4_fwd: x plane has %lld rows, needs %lld (maps) + %lld (zero tail)", p.x_plane, p.strip_rows * (s2 ? 4 : 1), tail);
+    return QBN_ERR_INVALID_ARG;
+  }
   p.RA = TM + p.d_before + d_after;
   p.RA_p = (p.RA + 7) / 8 * 8;
   for (int r = 0; r < R; ++r)
@@ -540,7 +552,8 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   if (x2) {
     QBN_CHECK_ARG(stride == 1 && !stacked && !(flags & QBN_FLAG_OUT_PHASE_SPLIT), "fused shortcut: stride-1 main conv, normal output");
     p.x2 = x2;
-    p.x2_plane = 4 * p.strip_rows;                       // phase (0,0) of the phase-split block input
+    p.x2_plane = pl.x2;                                  // phase (0,0) of the phase-split block input is read
+    QBN_CHECK_ARG(p.x2_plane >= 4 * p.strip_rows, "x2 plane too small");
     p.cbc2 = CB2 / 4; p.n_cb2 = C2 / CB2; p.nk2 = p.cbc2 / 2;
     p.bt2_bytes = (uint32_t)p.cbc2 * p.n_pad * 16;
     if ((uint32_t)p.cbc2 * TM * 16 > p.a_bytes) p.a_bytes = (uint32_t)p.cbc2 * TM * 16;       // the slots must hold a shortcut block too
@@ -553,15 +566,16 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   p.mg_plane = (uint32_t)(0x100000000ull / (uint64_t)(Hp * Wp));
   p.mg_wp = (uint32_t)(0x100000000ull / (uint64_t)Wp);
-  p.res_plane = p.strip_rows;
-  p.out_plane = (long long)n_samples * p.Qs;
+  p.res_plane = pl.res;
+  p.out_plane = pl.out;
+  QBN_CHECK_ARG(!residual || p.res_plane >= p.strip_rows, "residual plane too small");
   if (flags & QBN_FLAG_OUT_PHASE_SPLIT) {
-    const int H = Hp - 2 * p.bh, W = Wp - 2 * p.bw;
+    const int H = Hp - p.bh, W = Wp - p.bw;
     QBN_CHECK_ARG((H % 2 == 0) && (W % 2 == 0), "phase-split output needs even H, W");
     p.out_split = 1;
-    p.Hp2 = H / 2 + 2; p.Wp2 = W / 2 + 2;
+    p.Hp2 = H / 2 + 1; p.Wp2 = W / 2 + 1;
     p.q2_total = (long long)n_samples * B * p.Hp2 * p.Wp2;
-    p.out_plane = 4 * p.q2_total;
+    QBN_CHECK_ARG(p.out_plane >= 4 * p.q2_total, "phase-split out plane too small");
   }
   // ---- shared memory / occupancy policy ----
   const size_t b_all = (size_t)p.bt_bytes * p.n_cb * p.taps + (size_t)p.bt2_bytes * p.n_cb2;

@@ -592,7 +592,7 @@ class MCEngine:
             if isinstance(st, _PoolStep):
                 if isinstance(src, ops.P4Map):
                     bh, bw = src.border
-                    regs[st.dst] = ops.avgpool_p4(src, float((src.Hp - 2 * bh) * (src.Wp - 2 * bw))).reshape(src.n_img, src.C, 1, 1)
+                    regs[st.dst] = ops.avgpool_p4(src, float((src.Hp - bh) * (src.Wp - bw))).reshape(src.n_img, src.C, 1, 1)
                 elif st.kind == "max":
                     regs[st.dst] = ops.maxpool2x2(src)
                 else:
@@ -692,7 +692,7 @@ class MCEngine:
                 border = p4_layout[st.dst][1]
                 d = ops.make_desc(nb, src.shape[2], src.shape[3], C, N, R, S_, info["stride"], info["pad"], info["dil"])
                 d.out_pad_h, d.out_pad_w = border
-                outp = self._p4_buffer(("v1p4", si), n * nb, N, d.Ho + 2 * border[0], d.Wo + 2 * border[1], border, 1, src.device, zero=True)
+                outp = self._p4_buffer(("v1p4", si), n * nb, N, d.Ho + border[0], d.Wo + border[1], border, 1, src.device, zero=True)
                 if tf32 and ready[st.src] and not info["cpad"]:
                     flags |= ops.QBN_FLAG_A_TF32_READY
                 ops.conv_forward(src, w, d, n, shared[st.src], False, e["scale"], e["shift"], None, relu_eff, in_mask, in_mult, mode, outp.buf,
@@ -739,9 +739,9 @@ class MCEngine:
         m = st.mod
         stride = m.stride[0]
         if src.phases == 4:
-            H0, W0 = 2 * (src.Hp - 2), 2 * (src.Wp - 2)
+            H0, W0 = 2 * (src.Hp - 1), 2 * (src.Wp - 1)
         else:
-            H0, W0 = src.Hp - 2 * src.border[0], src.Wp - 2 * src.border[1]
+            H0, W0 = src.Hp - src.border[0], src.Wp - src.border[1]
         info = self._packed(st, prep, torch.empty((0, src.C, H0, W0), device="meta"))
         N, C, R, S_ = info["wshape"]
         mu_b, sg_b, _ = self._p4_weights(st, prep, info, stride)
@@ -771,10 +771,10 @@ class MCEngine:
         else:
             Hp_o, Wp_o, border = src.Hp, src.Wp, src.border
         if split:
-            Ho, Wo = Hp_o - 2 * border[0], Wp_o - 2 * border[1]
+            Ho, Wo = Hp_o - border[0], Wp_o - border[1]
             if Ho % 2 or Wo % 2:
                 raise RuntimeError("phase-split output needs even H, W")
-            out = self._p4_buffer(("p4", si), src.n_img, N, Ho // 2 + 2, Wo // 2 + 2, (1, 1), 4, src.buf.device, zero=True)
+            out = self._p4_buffer(("p4", si), src.n_img, N, Ho // 2 + 1, Wo // 2 + 1, (1, 1), 4, src.buf.device, zero=True)
         else:
             out = self._p4_buffer(("p4", si), src.n_img, N, Hp_o, Wp_o, border, 1, src.buf.device, zero=False)
         res = regs[st.residual] if st.residual is not None else None

@@ -531,18 +531,29 @@ def nchw_to_nhwc(x):
 # planar-C4 path (include/qbn.h "planar-C4 path", csrc/p4_layout.cuh)
 # ------------------------------------------------------------------------------------------------
 class P4Map:
-    """A batch of zero-bordered maps in the planar-C4 layout: buf [C/4][phases * n_img*Hp*Wp][4].
-    phases == 4: phase-split storage of a (2*(Hp-2)) x (2*(Wp-2)) map for a stride-2 consumer."""
+    """A batch of zero-bordered maps in the planar-C4 layout: buf [C/4][phases * n_img*Hp*Wp + tail][4].
+    The zeros are SHARED between neighbours: `bh` zero rows on top of every map (they are the bottom padding of the map
+    above), `bw` zero columns on the left of every row (the right padding of the row above), Hp = H + bh, Wp = W + bw, and
+    a zero tail of bh*Wp + bw pixels after the last map.  phases == 4: phase-split storage of a 2(Hp-1) x 2(Wp-1) map for
+    a stride-2 consumer (phase (a, b) holds the pixels (2i+a, 2j+b))."""
     __slots__ = ("buf", "n_img", "C", "Hp", "Wp", "border", "phases")
 
     def __init__(self, buf, n_img, C, Hp, Wp, border, phases=1):
         self.buf, self.n_img, self.C, self.Hp, self.Wp, self.border, self.phases = buf, n_img, C, Hp, Wp, border, phases
 
+    @property
+    def plane_rows(self):
+        return self.buf.shape[1]
+
     @staticmethod
-    def empty(n_img, C, Hp, Wp, border, phases=1, device="cuda", zero=False):
-        shape = (C // 4, phases * n_img * Hp * Wp, 4)
-        buf = torch.zeros(shape, dtype=torch.float32, device=device) if zero else torch.empty(shape, dtype=torch.float32, device=device)
-        return P4Map(buf, n_img, C, Hp, Wp, border, phases)
+    def tail_rows(Hp, Wp, border):
+        return border[0] * Wp + border[1]
+
+    @staticmethod
+    def empty(n_img, C, Hp, Wp, border, phases=1, device="cuda", zero=True):
+        """Always zero-initialised: kernels never write the tail (and never the border of a phase-split map)."""
+        shape = (C // 4, phases * n_img * Hp * Wp + P4Map.tail_rows(Hp, Wp, border), 4)
+        return P4Map(torch.zeros(shape, dtype=torch.float32, device=device), n_img, C, Hp, Wp, tuple(border), phases)
 
     @staticmethod
     def from_nchw(x, border, phase_split=False):
@@ -550,34 +561,39 @@ class P4Map:
         n, C, H, W = x.shape
         xh = x.permute(0, 2, 3, 1)
         if phase_split:
-            parts = [torch.nn.functional.pad(xh[:, a::2, b::2, :], (0, 0, 1, 1, 1, 1)) for a in (0, 1) for b in (0, 1)]
-            Hp, Wp = H // 2 + 2, W // 2 + 2
+            parts = [torch.nn.functional.pad(xh[:, a::2, b::2, :], (0, 0, 1, 0, 1, 0)) for a in (0, 1) for b in (0, 1)]
+            Hp, Wp = H // 2 + 1, W // 2 + 1
             rows = torch.stack(parts).reshape(4 * n * Hp * Wp, C)
             border, phases = (1, 1), 4
         else:
             bh, bw = border
-            Hp, Wp = H + 2 * bh, W + 2 * bw
-            rows = torch.nn.functional.pad(xh, (0, 0, bw, bw, bh, bh)).reshape(n * Hp * Wp, C)
+            Hp, Wp = H + bh, W + bw
+            rows = torch.nn.functional.pad(xh, (0, 0, bw, 0, bh, 0)).reshape(n * Hp * Wp, C)
             phases = 1
+        rows = torch.nn.functional.pad(rows, (0, 0, 0, P4Map.tail_rows(Hp, Wp, border)))
         buf = rows.reshape(-1, C // 4, 4).permute(1, 0, 2).contiguous()
         return P4Map(buf, n, C, Hp, Wp, tuple(border), phases)
 
     def to_nchw(self, keep_border=False):
-        rows = self.buf.permute(1, 0, 2).reshape(self.phases, self.n_img, self.Hp, self.Wp, self.C)
+        body = self.phases * self.n_img * self.Hp * self.Wp
+        rows = self.buf[:, :body].permute(1, 0, 2).reshape(self.phases, self.n_img, self.Hp, self.Wp, self.C)
         if self.phases == 4:
-            H, W = 2 * (self.Hp - 2), 2 * (self.Wp - 2)
+            H, W = 2 * (self.Hp - 1), 2 * (self.Wp - 1)
             out = torch.empty((self.n_img, H, W, self.C), dtype=self.buf.dtype, device=self.buf.device)
             k = 0
             for a in (0, 1):
                 for b in (0, 1):
-                    out[:, a::2, b::2, :] = rows[k][:, 1:-1, 1:-1, :]
+                    out[:, a::2, b::2, :] = rows[k][:, 1:, 1:, :]
                     k += 1
             return out.permute(0, 3, 1, 2)
         m = rows[0]
         if not keep_border:
             bh, bw = self.border
-            m = m[:, bh:self.Hp - bh, bw:self.Wp - bw, :]
+            m = m[:, bh:, bw:, :]
         return m.permute(0, 3, 1, 2)
+
+    def tail(self):
+        return self.buf[:, self.phases * self.n_img * self.Hp * self.Wp:]
 
 
 def p4_weight_floats(C, N, R, S, stride=1):
@@ -627,13 +643,14 @@ def conv_p4_forward(x, w, n_samples, N, R, S, stride=1, scale=None, shift=None, 
     border = ((R - 1) // 2, (S - 1) // 2) if stride == 1 else (1, 1)
     if out is None:
         if phase_split_out:
-            H, W = x.Hp - 2 * border[0], x.Wp - 2 * border[1]
-            out = P4Map.empty(n_out, N, H // 2 + 2, W // 2 + 2, (1, 1), 4, x.buf.device, zero=True)
+            H, W = x.Hp - border[0], x.Wp - border[1]
+            out = P4Map.empty(n_out, N, H // 2 + 1, W // 2 + 1, (1, 1), 4, x.buf.device)
         else:
             out = P4Map.empty(n_out, N, x.Hp, x.Wp, border, 1, x.buf.device)
     fl = int(bool(relu)) | int(flags) | (QBN_FLAG_OUT_PHASE_SPLIT if phase_split_out else 0)
-    _lib.call("qbn_conv_p4_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, stride, _ptr(x.buf), _ptr(w), int(w_shared), _ptr(scale), _ptr(shift),
-              _ptr(residual.buf if residual is not None else None), _ptr(out_mask), float(out_mask_mult), fl, _ptr(out.buf), _stream())
+    _lib.call("qbn_conv_p4_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, stride, _ptr(x.buf), x.plane_rows, _ptr(w), int(w_shared), _ptr(scale),
+              _ptr(shift), _ptr(residual.buf if residual is not None else None), residual.plane_rows if residual is not None else 0,
+              _ptr(out_mask), float(out_mask_mult), fl, _ptr(out.buf), out.plane_rows, _stream())
     return out
 
 
@@ -649,12 +666,12 @@ def conv_p4_shortcut_forward(x, w, x2, n_samples, N, R, S, scale=None, shift=Non
         raise _lib.QbnError("fused shortcut: x2 must be the phase-split block input with the output geometry")
     if out is None:
         out = P4Map.empty(x.n_img, N, x.Hp, x.Wp, x.border, 1, x.buf.device)
-    _lib.call("qbn_conv_p4_shortcut_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, _ptr(x.buf), _ptr(w), _ptr(x2.buf), x2.C, _ptr(scale),
-              _ptr(shift), int(bool(relu)) | int(flags), _ptr(out.buf), _stream())
+    _lib.call("qbn_conv_p4_shortcut_fwd", n_samples, B, x.Hp, x.Wp, x.C, N, R, S, _ptr(x.buf), x.plane_rows, _ptr(w), _ptr(x2.buf), x2.plane_rows,
+              x2.C, _ptr(scale), _ptr(shift), int(bool(relu)) | int(flags), _ptr(out.buf), out.plane_rows, _stream())
     return out
 
 
 def avgpool_p4(x, divisor):
     out = torch.empty((x.n_img, x.C), dtype=torch.float32, device=x.buf.device)
-    _lib.call("qbn_avgpool_p4", _ptr(x.buf), x.n_img, x.Hp * x.Wp, x.C, float(divisor), _ptr(out), _stream())
+    _lib.call("qbn_avgpool_p4", _ptr(x.buf), x.n_img, x.Hp * x.Wp, x.plane_rows, x.C, float(divisor), _ptr(out), _stream())
     return out

@@ -26,13 +26,17 @@ for (C, H, N, k, stride, res, split) in [(24, 32, 24, 3, 1, False, False), (24, 
                                          (96, 8, 96, 3, 1, True, False), (96, 4, 192, 3, 2, False, False), (96, 4, 192, 1, 2, False, False),
                                          (192, 4, 192, 3, 1, True, False)]:
     # H = OUTPUT resolution
-    Hp = H + 2
+    Hp = H + 1
     phases = 4 if stride == 2 else 1
-    x = ops.P4Map(rnd(torch.randn(C // 4, phases * S * B * Hp * Hp, 4, device="cuda")), S * B, C, Hp, Hp, (1, 1), phases)
+    x = ops.P4Map.empty(S * B, C, Hp, Hp, (1, 1), phases, "cuda")
+    x.buf[:, :phases * S * B * Hp * Hp].copy_(rnd(torch.randn(C // 4, phases * S * B * Hp * Hp, 4, device="cuda")))
     w = rnd(torch.randn(S, ops.p4_weight_floats(C, N, k, k, stride), device="cuda") * 0.05)
-    r = ops.P4Map(torch.randn(N // 4, S * B * Hp * Hp, 4, device="cuda"), S * B, N, Hp, Hp, (1, 1), 1) if res else None
+    r = None
+    if res:
+        r = ops.P4Map.empty(S * B, N, Hp, Hp, (1, 1), 1, "cuda")
+        r.buf.normal_()
     if split:
-        out = ops.P4Map.empty(S * B, N, H // 2 + 2, H // 2 + 2, (1, 1), 4, "cuda", zero=True)
+        out = ops.P4Map.empty(S * B, N, H // 2 + 1, H // 2 + 1, (1, 1), 4, "cuda")
     else:
         out = ops.P4Map.empty(S * B, N, Hp, Hp, (1, 1), 1, "cuda")
     sc = torch.rand(N, device="cuda") + 0.5; sh = torch.randn(N, device="cuda")
@@ -41,9 +45,11 @@ for (C, H, N, k, stride, res, split) in [(24, 32, 24, 3, 1, False, False), (24, 
     by = 4.0 * (x.buf.numel() + out.buf.numel() + (r.buf.numel() if res else 0))
     print("p4  C%3d out%2dx%-2d N%3d k%d s%d res=%d split=%d : %7.1f us  %6.1f TF/s  %6.0f GB/s" % (C, H, H, N, k, stride, res, split, ms * 1e3, fl / ms / 1e9, by / ms / 1e6))
 for (C2, N, H) in [(24, 48, 16), (48, 96, 8), (96, 192, 4)]:
-    Hp = H + 2
-    y = ops.P4Map(rnd(torch.randn(N // 4, S * B * Hp * Hp, 4, device="cuda")), S * B, N, Hp, Hp, (1, 1), 1)
-    x2 = ops.P4Map(rnd(torch.randn(C2 // 4, 4 * S * B * Hp * Hp, 4, device="cuda")), S * B, C2, Hp, Hp, (1, 1), 4)
+    Hp = H + 1
+    y = ops.P4Map.empty(S * B, N, Hp, Hp, (1, 1), 1, "cuda")
+    y.buf[:, :S * B * Hp * Hp].copy_(rnd(torch.randn(N // 4, S * B * Hp * Hp, 4, device="cuda")))
+    x2 = ops.P4Map.empty(S * B, C2, Hp, Hp, (1, 1), 4, "cuda")
+    x2.buf.copy_(rnd(torch.randn_like(x2.buf)))
     cb2 = ops.p4_shortcut_block_channels(N, C2)
     nfl = ops.p4_weight_floats(N, N, 3, 3, 1) + (C2 // cb2) * (cb2 // 4) * ((N + 15) // 16 * 16) * 4
     w = rnd(torch.randn(S, nfl, device="cuda") * 0.05)

@@ -41,7 +41,7 @@ mc.ops.avgpool_all = wrap("avgpool", ops.avgpool_all, d_other)
 def d_p4(a, k, out):
     x_, w, n, N, R, S_ = a[:6]
     stride = a[6] if len(a) > 6 else 1
-    H, W = x_.Hp - 2, x_.Wp - 2
+    H, W = x_.Hp - 1, x_.Wp - 1
     fl = 2.0 * x_.n_img * H * W * N * R * S_ * x_.C
     res = a[9] if len(a) > 9 else None
     by = 4.0 * (x_.buf.numel() * (0.25 if (stride == 2 and R == 1) else 1.0) + out.buf.numel() + (res.buf.numel() if res is not None else 0))
@@ -51,7 +51,7 @@ mc.ops.conv_p4_forward = wrap("conv_p4", ops.conv_p4_forward, d_p4)
 def d_p4sc(a, k, out):
     x_, w, x2 = a[:3]
     n, N, R, S_ = a[3:7]
-    H, W = x_.Hp - 2, x_.Wp - 2
+    H, W = x_.Hp - 1, x_.Wp - 1
     fl = 2.0 * x_.n_img * H * W * N * (R * S_ * x_.C + x2.C)
     by = 4.0 * (x_.buf.numel() + 0.25 * x2.buf.numel() + out.buf.numel())
     return dict(shape="SB%d out%dx%d C%d->N%d k%d + fused 1x1/2 of C%d" % (x_.n_img, H, W, x_.C, N, R, x2.C), flops=fl, bytes=by, mode=1)
