@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 B, S, K_CLASSES = 256, 100, 10
 FLOP_PER_SAMPLE_IMAGE = 1.5704e8          # SURVEY.md §8d, one contraction per layer
 # mean dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one 10-sample chunk (ncu --set full)
-P4_DRAM_BYTES_PER_LAUNCH = 361.1e6
+P4_DRAM_BYTES_PER_LAUNCH = 314.6e6
 P4_TRAFFIC_SOURCE = "dram__bytes_read.sum + dram__bytes_write.sum, mean over the 17 umma_conv_p4_kernel launches of one 10-sample chunk, ncu --set full (profiles/r01_p4_kernels_ncu_full.csv); above the algorithmic figure by the residual reads and the zero border"
 ACT_BYTES_PER_SAMPLE_IMAGE = 1.929e6      # fp32 NHWC activations in+out of the 21 stochastic layers
 
