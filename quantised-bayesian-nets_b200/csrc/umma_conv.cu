@@ -49,6 +49,7 @@ struct UParams {
   uint32_t idesc;
   // tensors
   const void* x; const void* w; const void* w2;
+  const float* x2;               // LRT mode: second A operand from its own tensor (dgrad: dv) instead of x^2
   const float* scale; const float* shift; const float* residual; const float* in_mask; float in_mult;
   int tr_sh, tr_sw;              // transposed convolution (dgrad of a strided conv): input coordinate = (h0 + r) / tr_s when divisible
   const float* mul2x;            // LRT dgrad: acc *= 2 * mul2x[out index] before the residual add (dx = dx_mean + 2x .* dx_var)
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
     const bool a_async = (MODE == MODE_EVAL) && msk == nullptr && (p.flags & QBN_FLAG_A_TF32_READY);
     constexpr int AV = I8 ? 2 : 1;               // 8-byte pieces (i8) or one 16-byte chunk (fp32)
     uint4 areg[8];
+    uint4 areg2[LRT ? 8 : 1];            // second A operand when it is a tensor of its own (p.x2)
 
     auto tap_of = [&](int k, int& c, int& dr, int& ds) {
       const int kk = k < p.K ? k : 0;
@@ -161,6 +163,12 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
           ok = ok && hi < p.H && wi < p.W;
           areg[i] = make_uint4(0u, 0u, 0u, 0u);
           if (ok) areg[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(xs) + rbase[i] + (hi * p.W + wi) * p.C + c));
+          if constexpr (LRT) {
+            if (p.x2) {
+              areg2[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok) areg2[i] = __ldg(reinterpret_cast<const uint4*>(p.x2 + rbase[i] + (hi * p.W + wi) * p.C + c));
+            }
+          }
         }
       } else {
 #pragma unroll
@@ -207,8 +215,13 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
           }
           const size_t off = ((size_t)kc * p.a_pitch + r0 + 16 * i) * 16;
           *reinterpret_cast<uint4*>(sa + off) = make_uint4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-          if constexpr (LRT)
-            *reinterpret_cast<uint4*>(sa2 + off) = make_uint4(tf32_rna(v.x * v.x), tf32_rna(v.y * v.y), tf32_rna(v.z * v.z), tf32_rna(v.w * v.w));
+          if constexpr (LRT) {
+            if (p.x2)
+              *reinterpret_cast<uint4*>(sa2 + off) = make_uint4(tf32_rna(__uint_as_float(areg2[i].x)), tf32_rna(__uint_as_float(areg2[i].y)),
+                                                                tf32_rna(__uint_as_float(areg2[i].z)), tf32_rna(__uint_as_float(areg2[i].w)));
+            else
+              *reinterpret_cast<uint4*>(sa2 + off) = make_uint4(tf32_rna(v.x * v.x), tf32_rna(v.y * v.y), tf32_rna(v.z * v.z), tf32_rna(v.w * v.w));
+          }
         }
       }
     };
@@ -376,6 +389,11 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
         }
       } else if constexpr (LRT) {
         float* out = reinterpret_cast<float*>(p.out);
+        if (p.mul2x) {     // dgrad: dx = conv(g, mu') + 2x .* conv(dv, sigma2'), both contractions of this one launch
+          for (int j = 0; j < nvalid; ++j)
+            out[orow + c0 + j] = __fadd_rn(__uint_as_float(v[j]), __fmul_rn(2.0f * __ldg(p.mul2x + orow + c0 + j), __uint_as_float(v2[j])));
+          continue;
+        }
         float e[8];
         if (p.eps) {
           for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? __ldg(p.eps + orow + c0 + j) : 0.f;
@@ -541,9 +559,8 @@ int qbn_umma_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const
   return launch_umma<MODE_EVAL>(p, n_samples, st, "qbn_conv_fwd(TF32)");
 }
 
-// A3 dx on the tensor cores (stride-1, undilated layers): the transposed convolution is the forward kernel run on the
-// output gradient with flipped, transposed weights;  dx = conv(g, mu') + 2x .* conv(dv, sigma2')  as two launches, the second
-// accumulating onto the first through the epilogue (residual = dx, multiplier = 2x).
+// A3 dx on the tensor cores (undilated layers): the transposed convolution is the forward kernel run on the output gradient
+// with flipped, transposed weights;  dx = conv(g, mu') + 2x .* conv(dv, sigma2')  as ONE launch of the dual-accumulator kernel.
 int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, const float* mu_t, const float* sig2_t, const float* x,
                        float* dx, cudaStream_t st) {
   qbn_conv_desc t;
@@ -555,13 +572,9 @@ int qbn_umma_lrt_dgrad(const qbn_conv_desc* d, const float* g, const float* dv, 
   UParams p;
   fill_geom(p, &t);
   p.tr_sh = d->stride_h; p.tr_sw = d->stride_w;   // strided forward conv: its gradient lives on the stride grid (transposed conv)
-  p.x = g; p.w = mu_t; p.x_shared = 1; p.w_shared = 1; p.out = dx;
-  int rc = launch_umma<MODE_EVAL>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad, mean)");
-  if (rc != QBN_OK) return rc;
-  fill_geom(p, &t);
-  p.tr_sh = d->stride_h; p.tr_sw = d->stride_w;
-  p.x = dv; p.w = sig2_t; p.x_shared = 1; p.w_shared = 1; p.out = dx; p.residual = dx; p.mul2x = x;
-  return launch_umma<MODE_EVAL>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad, variance)");
+  // ONE launch of the dual-accumulator (LRT) kernel: A = g and dv, B = mu' and sigma2', epilogue dx = acc1 + 2x .* acc2
+  p.x = g; p.x2 = dv; p.w = mu_t; p.w2 = sig2_t; p.x_shared = 1; p.w_shared = 1; p.out = dx; p.mul2x = x;
+  return launch_umma<MODE_LRT>(p, 1, st, "qbn_lrt_bwd(TF32 dgrad)");
 }
 
 int qbn_umma_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const uint8_t* x, int z_x, const int8_t* w,
