@@ -330,12 +330,19 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
       const float* rptr = (p.residual && interior) ? p.residual + in_row * 4 : nullptr;
       float4 rres[4], rnext[4];
       uint32_t v[16], vn[16];
+      // running pointers: one 64-bit add per 16-byte chunk instead of a 64-bit multiply (60 chunks per row on the stacked first layer)
+      const long long res_step = p.res_plane * 4, out_step = p.out_plane * 4;
+      const long long out_wrap = STACKED ? ((long long)p.Qs - (long long)cps * p.out_plane) * 4 : 0;    // next stacked sample
+      const float* rp = rptr;
       auto prefetch = [&](float4* dst, int g) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ch = g * 4 + i;
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rptr && ch < n_chunks) dst[i] = ld_nc4(rptr + (size_t)ch * p.res_plane * 4);
+          if (rptr && ch < n_chunks) {
+            dst[i] = ld_nc4(rp);
+            rp += res_step;
+          }
         }
       };
       prefetch(rres, 0);
@@ -345,7 +352,8 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
       if (!(dbg & 8)) tmem_ld16(tlane, v);
-      int jc0 = 0, s0 = 0;                                   // channel chunk / stacked sample of the group's first chunk
+      float* oc = optr;                                      // output pointer of the current chunk
+      int jc = 0, sidx = 0;                                  // channel chunk inside the sample / stacked sample
       for (int g = 0; g < n_groups; ++g) {
         tmem_ld_wait();
         if (g + 1 < n_groups) {
@@ -362,11 +370,6 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
           for (int i = 0; i < 4; ++i) {
             const int ch = g * 4 + i;
             if (ch < n_chunks) {
-              int jc = ch, sidx = 0;
-              if (STACKED) {
-                jc = jc0 + i; sidx = s0;
-                while (jc >= cps) { jc -= cps; ++sidx; }
-              }
               float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
               if (interior) {
                 const float4 sc = *reinterpret_cast<const float4*>(&s_scale[jc * 4]);
@@ -392,13 +395,12 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
                 if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 if (rnd) { o.x = tf32_round(o.x); o.y = tf32_round(o.y); o.z = tf32_round(o.z); o.w = tf32_round(o.w); }
               }
-              *reinterpret_cast<float4*>(optr + ((size_t)jc * p.out_plane + (STACKED ? (size_t)sidx * p.Qs : (size_t)0)) * 4) = o;
+              *reinterpret_cast<float4*>(oc) = o;
+              oc += out_step;
+              ++jc;
+              if (STACKED && jc == cps) { jc = 0; ++sidx; oc += out_wrap; }
             }
           }
-        }
-        if (STACKED) {
-          jc0 += 4;
-          while (jc0 >= cps) { jc0 -= cps; ++s0; }
         }
         if (g + 1 < n_groups) {
 #pragma unroll
