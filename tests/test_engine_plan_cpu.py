@@ -68,3 +68,32 @@ def test_balanced_chunks():
     n_chunks = (13 + 9) // 10
     sizes = [13 // n_chunks + (1 if i < 13 % n_chunks else 0) for i in range(n_chunks)]
     assert sizes == [7, 6]
+
+
+def test_p4map_layout_roundtrip_cpu():
+    """The planar-C4 layout with shared zero borders (pure torch, CPU): round trips, zero rows on top / zero columns on the
+    left of every map, zero tail, and the phase-split storage of a map for a stride-2 consumer."""
+    from qbn_b200.ops import P4Map
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 8, 6, 4, generator=g)
+    m = P4Map.from_nchw(x, (1, 1))
+    assert (m.Hp, m.Wp, m.phases) == (7, 5, 1) and m.plane_rows == 3 * 7 * 5 + 5 + 1 and m.buf.shape == (2, m.plane_rows, 4)
+    assert torch.equal(m.to_nchw(), x)
+    full = m.to_nchw(keep_border=True)
+    assert float(full[:, :, 0, :].abs().max()) == 0.0 and float(full[:, :, :, 0].abs().max()) == 0.0 and float(m.tail().abs().max()) == 0.0
+    # flat-index property the kernel relies on: pixel (b, h, w) sits at row b*Hp*Wp + (h+1)*Wp + (w+1) of every chunk plane,
+    # and its (dr, ds) neighbour at + dr*Wp + ds — zero whenever it falls outside the map
+    rows = m.buf.permute(1, 0, 2).reshape(m.plane_rows, 8)
+    b, h, w = 1, 5, 3                       # bottom-right pixel of image 1
+    q = b * 35 + (h + 1) * 5 + (w + 1)
+    assert torch.equal(rows[q], x[b, :, h, w])
+    assert float(rows[q + 1].abs().max()) == 0.0 and float(rows[q + 5].abs().max()) == 0.0 and float(rows[q + 6].abs().max()) == 0.0
+    assert torch.equal(rows[q - 6], x[b, :, h - 1, w - 1])
+    q_last = 2 * 35 + 6 * 5 + 4              # bottom-right pixel of the LAST image: its bottom/right neighbours are the tail
+    assert q_last + 6 < m.plane_rows and float(rows[q_last + 1:].abs().max()) == 0.0
+    # phase split: phase (a, b) holds pixels (2i+a, 2j+b) at (i+1, j+1) of a (H/2+1) x (W/2+1) map
+    ps = P4Map.from_nchw(x, None, phase_split=True)
+    assert (ps.Hp, ps.Wp, ps.phases) == (4, 3, 4) and torch.equal(ps.to_nchw(), x)
+    prow = ps.buf.permute(1, 0, 2).reshape(ps.plane_rows, 8)
+    phase, i, j = 1 * 2 + 0, 2, 1            # pixel (2*2+1, 2*1+0) = (5, 2)
+    assert torch.equal(prow[phase * 3 * 12 + 0 * 12 + (i + 1) * 3 + (j + 1)], x[0, :, 5, 2])
