@@ -782,15 +782,17 @@ static bool p4_block_geom(int N, int C, int taps, int stride, P4Block& g, int cb
   g.total4 = (int64_t)(C / g.CB) * taps * g.cbc * g.n_pad;
   return true;
 }
-// blocked float4 index -> canonical OHWI element index (or -1 for the zero rows n >= N)
-__device__ __forceinline__ int64_t p4_canonical(const P4Block& g, int64_t i) {
-  const int n = (int)(i % g.n_pad);
-  int64_t t1 = i / g.n_pad;
-  const int j = (int)(t1 % g.cbc);
-  t1 /= g.cbc;
-  const int t = (int)(t1 % g.taps);
-  const int cb = (int)(t1 / g.taps);
-  if (n >= g.N) return -1;
+// blocked float4 index -> canonical OHWI element index (or -1 for the zero rows n >= N).  32-bit arithmetic: a layer's
+// blocked tensor has < 2^31 chunks (64-bit divisions were most of the sampler's instructions)
+__device__ __forceinline__ int64_t p4_canonical(const P4Block& g, int64_t i64) {
+  const uint32_t i = (uint32_t)i64;
+  const uint32_t t1 = i / (uint32_t)g.n_pad;
+  const uint32_t n = i - t1 * (uint32_t)g.n_pad;
+  const uint32_t t2 = t1 / (uint32_t)g.cbc;
+  const uint32_t j = t1 - t2 * (uint32_t)g.cbc;
+  const uint32_t cb = t2 / (uint32_t)g.taps;
+  const uint32_t t = t2 - cb * (uint32_t)g.taps;
+  if ((int)n >= g.N) return -1;
   return (int64_t)n * g.K + (int64_t)t * g.C + cb * g.CB + 4 * j;
 }
 
