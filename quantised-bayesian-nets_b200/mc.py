@@ -3,11 +3,17 @@
 The reference runs S sequential Python-level forwards, each re-sampling every layer's weights
 through 4 elementwise kernels, appends S [B,10] outputs to a list, stacks and averages.  Here the
 model is compiled once into a short plan of fused steps and ALL samples of a chunk advance through
-a layer together (grid.z = sample):
+a layer together:
 
-    sample_weights   W[s] = mu + sigma*eps_s      (Philox, one launch per layer, L2-resident output)
-    conv_forward     y[s] = act(bn(conv(x[s], W[s])) + residual[s])      (tcgen05, one launch per layer)
-    softmax_accumulate  psum += sum_s softmax(logits[s])                 (no [B,S,10] stack)
+    sample_weights_blocked_multi   W[s] = mu + sigma*eps_s for EVERY layer of the chunk (Philox, one launch)
+    conv_p4_forward (per layer)    y[s] = act(bn(conv(x[s], W[s])) (*mask) + residual[s])   planar-C4, tcgen05, zero-copy im2col
+    softmax_accumulate             psum += sum_s softmax(logits[s])                          (no [B,S,10] stack)
+
+Layers the planar kernel does not take (3-channel first layer when it cannot be sample-stacked, LeNet's
+1/20-channel convs, linear layers, fp32 mode) run on the gather / fp32 kernels over NHWC tensors.
+BatchNorm(eval), bias, ReLU, the residual add, the BasicBlock's 1x1 stride-2 shortcut and MC-Dropout masks are
+folded into the conv launches (_plan_p4).  The prepared operands are cached by parameter version and the whole
+S-sample pass is replayed from a CUDA graph.
 
 Noise is keyed by the GLOBAL sample index, so any sharding of the S samples over GPUs (dist.py)
 reproduces the single-GPU result up to summation order.
