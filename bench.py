@@ -163,12 +163,11 @@ def main():
         dist.barrier()
     if rank != 0:
         ge.build()
-    import oracle.qbn_oracle as O   # parameter generator only (shared with the CPU baseline); never on the timed path
     from qbn_b200 import dist as qdist
-    from qbn_b200 import mc, metrics, noise, zoo
+    from qbn_b200 import mc, metrics, noise, synthetic, zoo   # the GPU arm never imports oracle/ (only the cpu_baseline leg does)
 
     dev = torch.device("cuda", local_rank)
-    P = O.ResNetBBBParams(seed=1)
+    P = synthetic.ResNetBBBParams(seed=1)
     model = zoo.resnet_from_params(P).to(dev).eval()
     noise.manual_seed(20261017)
     engine = mc.MCEngine(model, math_mode=args.math, chunk=args.chunk)

@@ -312,7 +312,10 @@ def mlp_from_params(P, args=None):
 
 def resnet_mc_from_params(P, p=0.15, n_classes=10, state_dict=None):
     """MC-Dropout ResNet (models_mc.py) with the mu tensors of a ResNetBBBParams container as its weights;
-    `state_dict`: entries under the reference's module names (oracle.qbn_oracle.resnet_mc_state_dict)."""
+    `state_dict`: entries under the reference's module names (default: synthetic.resnet_mc_state_dict(P))."""
+    if state_dict is None:
+        from .synthetic import resnet_mc_state_dict
+        state_dict = resnet_mc_state_dict(P)
     args = Args(p=p, model="conv_resnet_mc")
     net = ConvNetwork_ResNet_MC([1, P.convs["layers.0"][0].shape[1], 32, 32], n_classes, False, args)
     sd = net.state_dict()

@@ -21,7 +21,7 @@ if rank == 0:
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dist.barrier()
-import oracle.qbn_oracle as O      # parameter generator only
+from qbn_b200 import synthetic as O      # seeded parameter containers
 from qbn_b200 import config, noise, zoo
 from qbn_b200 import dist as qdist
 config.set_math_mode(args.math)

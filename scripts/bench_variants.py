@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import __graft_entry__ as ge
 ge.build()
-import oracle.qbn_oracle as O      # parameter generators only
+from qbn_b200 import synthetic as O      # seeded parameter containers
 from qbn_b200 import mc, noise, zoo
 
 def run(name, net, x, S=100, chunk=10, steps=5, warmup=3):

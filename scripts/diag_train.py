@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import __graft_entry__ as ge
 ge.build()
-import oracle.qbn_oracle as O
+from qbn_b200 import synthetic as O
 from qbn_b200 import config, noise, zoo, ops
 config.set_math_mode(sys.argv[1] if len(sys.argv) > 1 else "tf32")
 model = zoo.resnet_from_params(O.ResNetBBBParams(seed=1)).cuda().train()

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import __graft_entry__ as ge
 ge.build()
-import oracle.qbn_oracle as O
+from qbn_b200 import synthetic as O
 from qbn_b200 import mc, noise, zoo, ops
 chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 P = O.ResNetBBBParams(seed=1)
