@@ -53,3 +53,24 @@ def test_sass_has_tcgen05(lib):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", lib.LIB_PATH], stdout=subprocess.PIPE).stdout.decode()
     assert "UTCHMMA" in sass and "UTCIMMA" in sass and "LDTM" in sass
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package (nor the GPU arm of bench.py) may import it."""
+    import ast
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "quantised-bayesian-nets_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(dirpath, f)).read())
+                for node in ast.walk(tree):
+                    names = [a.name for a in node.names] if isinstance(node, ast.Import) else ([node.module or ""] if isinstance(node, ast.ImportFrom) else [])
+                    assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (f, names)
+    # bench.py: oracle imports only inside the CPU-baseline function
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        imports = [a.name for n in ast.walk(fn) if isinstance(n, ast.Import) for a in n.names]
+        if any(i.startswith("oracle") for i in imports):
+            assert "cpu" in fn.name.lower() or "reference" in fn.name.lower(), fn.name
