@@ -140,7 +140,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("QBN_CHUNK", "10")))
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("QBN_CHUNK", "50")))
+    ap.add_argument("--chunk-max", type=int, default=int(os.environ.get("QBN_CHUNK_MAX", "0")), help="largest chunk (0: same as --chunk)")
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -170,7 +171,7 @@ def main():
     P = synthetic.ResNetBBBParams(seed=1)
     model = zoo.resnet_from_params(P).to(dev).eval()
     noise.manual_seed(20261017)
-    engine = mc.MCEngine(model, math_mode=args.math, chunk=args.chunk)
+    engine = mc.MCEngine(model, math_mode=args.math, chunk=args.chunk, chunk_max=args.chunk_max)
     x_host = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(2)).pin_memory()
     t_host = torch.randint(0, K_CLASSES, (B,), generator=torch.Generator().manual_seed(3)).pin_memory()
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)

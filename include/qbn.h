@@ -175,6 +175,8 @@ typedef struct qbn_p4_sample_job {
   const float* chan_scale; /* nullable [N]: W[n][.] *= chan_scale[n] before rounding (BatchNorm scale folded into the weights) */
   int32_t cb_override;     /* > 0: channels per block (qbn_p4_shortcut_block_channels) instead of the layout rule */
   int32_t w_sample_stride4;/* > 0: float4 units between consecutive samples in w (several jobs filling one tensor) */
+  int32_t s_off;           /* stacked jobs: the job covers the chunk's samples [s_off, s_off + n_stack) */
+  int32_t pad_;
 } qbn_p4_sample_job;
 int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
                                      uint64_t seed, uint32_t sample0, int round_tf32, void* stream);

@@ -27,7 +27,7 @@ class ConvDesc(Structure):
 class P4SampleJob(Structure):
     _fields_ = [("mu_b", c_void_p), ("sigma_b", c_void_p), ("eps", c_void_p), ("w", c_void_p), ("N", c_int32), ("C", c_int32),
                 ("taps", c_int32), ("stride", c_int32), ("layer_id", c_uint32), ("n_stack", c_int32), ("chan_scale", c_void_p),
-                ("cb_override", c_int32), ("w_sample_stride4", c_int32)]
+                ("cb_override", c_int32), ("w_sample_stride4", c_int32), ("s_off", c_int32), ("pad_", c_int32)]
 
 
 class KLJob(Structure):

@@ -911,6 +911,7 @@ struct qbn_p4_sample_job_dev {
   const float* mu_b; const float* sigma_b; const float* eps; float* w;
   int N, C, taps, stride; uint32_t layer_id; int n_stack;
   const float* chan_scale; int cb_override; int w_sample_stride4;
+  int s_off; int pad_;          // stacked jobs: this job covers the chunk's samples [s_off, s_off + n_stack)
 };
 __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev* __restrict__ jobs, uint64_t seed, uint32_t sample0,
                                                     int round_tf32) {
@@ -921,10 +922,12 @@ __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev*
   g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(jb.N); g.K = jb.taps * jb.C;
   g.total4 = (int64_t)(jb.C / g.CB) * jb.taps * g.cbc * g.n_pad;
   const int s = blockIdx.y;
-  // stacked: ONE blocked tensor of n_stack*N rows; this sample fills rows [s*N, (s+1)*N) of every (cb, tap, chunk) column
+  // stacked: ONE blocked tensor of n_stack*N rows; sample s fills rows [(s-s_off)*N, (s-s_off+1)*N) of every (cb, tap, chunk)
+  // column; a chunk larger than one accumulator tile is covered by several stacked jobs (groups of samples)
+  if (jb.n_stack > 0 && (s < jb.s_off || s >= jb.s_off + jb.n_stack)) return;
   const int n_pad_out = jb.n_stack > 0 ? qbn_p4_n_pad(jb.n_stack * jb.N) : g.n_pad;
   float4* ws = reinterpret_cast<float4*>(jb.w) +
-               (jb.n_stack > 0 ? (int64_t)s * g.N : (int64_t)s * (jb.w_sample_stride4 > 0 ? (int64_t)jb.w_sample_stride4 : g.total4));
+               (jb.n_stack > 0 ? (int64_t)(s - jb.s_off) * g.N : (int64_t)s * (jb.w_sample_stride4 > 0 ? (int64_t)jb.w_sample_stride4 : g.total4));
   const float* es = jb.eps ? jb.eps + (int64_t)s * g.N * g.K : nullptr;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t idx = p4_canonical(g, i);

@@ -61,9 +61,10 @@ class MCEngine:
     (LinearNetwork / ConvNetwork_LeNet / ConvNetwork_ResNet of models_bbb.py, or their qbn_b200.zoo
     mirrors).  predict() == `_evaluate_with_loader`'s inner loop for one batch."""
 
-    def __init__(self, model, math_mode="tf32", chunk=10, use_graph=True):
+    def __init__(self, model, math_mode="tf32", chunk=50, use_graph=True, chunk_max=None):
         self.model = model
         self.use_graph = bool(use_graph)
+        self.chunk_max = int(chunk_max) if chunk_max else int(chunk)   # a call's samples are split into ceil(S / chunk_max) balanced chunks
         self.math_mode = {"fp32": QBN_MATH_FP32, "tf32": QBN_MATH_TF32}[math_mode] if isinstance(math_mode, str) else math_mode
         self.chunk = int(chunk)
         self.steps = []
@@ -454,7 +455,14 @@ class MCEngine:
         fused_of = {id(sc): st for st_id, sc in fused.items() for st in self.steps if id(st) == st_id}     # shortcut -> main step
 
         def stack_ok(st):
-            return id(st) == first and n * st.mod.out_channels <= 256
+            return id(st) == first
+
+        def stack_groups(st):
+            """(first sample, count) groups of the chunk whose stacked channels fit one accumulator tile (256 columns)."""
+            gmax = max(1, 256 // st.mod.out_channels)
+            ng = (n + gmax - 1) // gmax
+            sizes_ = [n // ng + (1 if i < n % ng else 0) for i in range(ng)]
+            return [(sum(sizes_[:i]), sizes_[i]) for i in range(ng)]
         steps = [st for st in self.steps if id(st) in p4_convs or (isinstance(st, _ConvStep) and stack_ok(st))]
         tables = self.__dict__.setdefault("_p4_jobs", {})
 
@@ -466,16 +474,19 @@ class MCEngine:
         for st in steps:                       # refresh the blocked parameters of this call (once per call, not per chunk)
             self._p4_weights(st, prep, pinfo(st), st.mod.stride[0], cb_of(st))
         if n not in tables or injected is not None:
-            jobs = (P4SampleJob * len(steps))()
+            n_jobs_total = sum(len(stack_groups(st)) if stack_ok(st) else 1 for st in steps)
+            jobs = (P4SampleJob * n_jobs_total)()
+            ji = 0
             wbufs, max_fl = {}, 0
             keep_eps = []
             sizes = {id(st): self._p4_weights(st, prep, pinfo(st), st.mod.stride[0], cb_of(st))[0].numel() for st in steps}
             for st in steps:                   # weight tensors: fused pairs share one [n, main + shortcut] tensor
                 if id(st) in skip:
                     continue
-                if stack_ok(st):   # one blocked tensor, the chunk's samples stacked along N (padding rows stay zero)
+                if stack_ok(st):   # one blocked tensor per group of samples, stacked along N (padding rows stay zero)
                     N, C, R, S_ = pinfo(st)["wshape"]
-                    wbufs[id(st)] = torch.zeros((1, ops.p4_weight_floats(C, n * N, R, S_, 1)), dtype=torch.float32, device=device)
+                    wbufs[id(st)] = [(s0_, cnt, torch.zeros((1, ops.p4_weight_floats(C, cnt * N, R, S_, 1)), dtype=torch.float32, device=device))
+                                     for s0_, cnt in stack_groups(st)]
                 else:
                     extra = sizes[id(fused[id(st)])] if id(st) in fused else 0
                     wbufs[id(st)] = torch.empty((n, sizes[id(st)] + extra), dtype=torch.float32, device=device)
@@ -502,12 +513,19 @@ class MCEngine:
                 elif id(st) in fused:
                     w = wbufs[id(st)]
                     w_ptr, stride4, scale_ptr = w.data_ptr(), w.shape[1] // 4, sc_b.data_ptr()
+                elif stack_ok(st):
+                    for s0_, cnt, wg in wbufs[id(st)]:
+                        jobs[ji] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), eps_ptr, wg.data_ptr(), N, C, R * S_, st.mod.stride[0],
+                                               getattr(st.mod, "_qbn_layer_id", 0), cnt, None, 0, 0, s0_, 0)
+                        ji += 1
+                    continue
                 else:
                     w_ptr = wbufs[id(st)].data_ptr()
-                jobs[i] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), eps_ptr, w_ptr, N, C, R * S_, st.mod.stride[0],
-                                      getattr(st.mod, "_qbn_layer_id", 0), n if stack_ok(st) else 0, scale_ptr, cb_of(st), stride4)
+                jobs[ji] = P4SampleJob(mu_b.data_ptr(), sg_b.data_ptr(), eps_ptr, w_ptr, N, C, R * S_, st.mod.stride[0],
+                                       getattr(st.mod, "_qbn_layer_id", 0), 0, scale_ptr, cb_of(st), stride4, 0, 0)
+                ji += 1
             raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
-            entry = (raw, len(steps), max_fl, wbufs)
+            entry = (raw, n_jobs_total, max_fl, wbufs)
             if injected is None:
                 tables[n] = entry
             else:
@@ -624,10 +642,12 @@ class MCEngine:
                 outp = self._p4_buffer(("p4first", si), n * xm.n_img, N, xm.Hp, xm.Wp, (1, 1), 1, src.device, zero=False)
                 e = prep[id(st)]
                 mk, mult = masks.get(id(st), (None, 1.0))
-                ops.conv_p4_forward(xm, self._p4_presampled[id(st)], n, N, R, S_, 1, e["scale"], e["shift"], None, st.relu,
-                                    ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED | (ops.QBN_FLAG_RELU_PRE if st.relu_pre else 0),
-                                    False, outp, False, mk, mult)
-                self.launches += 1
+                for s0_, cnt, wg in self._p4_presampled[id(st)]:      # one launch per group of <= 256 / N stacked samples
+                    ops.conv_p4_forward(xm, wg, cnt, N, R, S_, 1, e["scale"], e["shift"], None, st.relu,
+                                        ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED | (ops.QBN_FLAG_RELU_PRE if st.relu_pre else 0),
+                                        False, outp.images(s0_ * xm.n_img, cnt * xm.n_img), False,
+                                        mk[s0_ * xm.n_img:] if mk is not None else None, mult)
+                    self.launches += 1
                 regs[st.dst] = outp
                 shared[st.dst] = False
                 ready[st.dst] = True
@@ -837,9 +857,10 @@ class MCEngine:
         psum = None
         mus, lvs = [], []
         done = 0
-        # balanced chunks: ceil(S / chunk) launches of near-equal size (13 samples -> 7 + 6 rather than 10 + 3: a small tail
-        # chunk pays the per-launch fixed costs for little work; matters when the samples are sharded over 8 GPUs)
-        n_chunks = (samples + self.chunk - 1) // self.chunk
+        # balanced chunks: ceil(S / chunk) passes of near-equal size.  Every launch has ~14 us of ramp / tail, so fewer, larger
+        # chunks win (measured at S=100: chunk 10 -> 19.8 ms, 20 -> 18.6, 50 -> 18.2, 100 -> 18.6); the first layer's
+        # sample-stacked launch is split into groups of <= 256 / N samples inside a chunk
+        n_chunks = (samples + self.chunk_max - 1) // self.chunk_max
         sizes = [samples // n_chunks + (1 if i < samples % n_chunks else 0) for i in range(n_chunks)]
         for n in sizes:
             inj = injected[done:done + n] if injected is not None else None

@@ -543,7 +543,13 @@ class P4Map:
 
     @property
     def plane_rows(self):
-        return self.buf.shape[1]
+        return self.buf.stride(0) // 4          # distance between chunk planes (a view of a larger buffer keeps it)
+
+    def images(self, i0, n):
+        """View of images [i0, i0 + n) (same planes, pointer offset): an output slice for a launch that covers part of the batch."""
+        assert self.phases == 1
+        hw = self.Hp * self.Wp
+        return P4Map(self.buf[:, i0 * hw:], n, self.C, self.Hp, self.Wp, self.border, 1)
 
     @staticmethod
     def tail_rows(Hp, Wp, border):
