@@ -27,7 +27,7 @@ B, S, K_CLASSES = 256, 100, 10
 FLOP_PER_SAMPLE_IMAGE = 1.5704e8          # SURVEY.md §8d, one contraction per layer
 # mean dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one 10-sample chunk (ncu --set full)
 P4_DRAM_BYTES_PER_LAUNCH = 314.6e6
-P4_TRAFFIC_SOURCE = "dram__bytes_read.sum + dram__bytes_write.sum, mean over the 17 umma_conv_p4_kernel launches of one 10-sample chunk, ncu --set full (profiles/r01_p4_kernels_ncu_full.csv); above the algorithmic figure by the residual reads and the zero border"
+P4_TRAFFIC_SOURCE = "dram__bytes_read.sum + dram__bytes_write.sum, mean over the 17 umma_conv_p4_kernel launches of one 10-sample chunk, ncu --set full (profiles/r01_p4_kernels_ncu_full.csv: 314.6 MB), scaled linearly to this run's samples per chunk; the residual reads add to SURVEY's algorithmic figure, the shared borders subtract"
 ACT_BYTES_PER_SAMPLE_IMAGE = 1.929e6      # fp32 NHWC activations in+out of the 21 stochastic layers
 
 
@@ -308,7 +308,8 @@ def main():
             hbm = alg_bytes / (t_ms * 1e-3) / 1e9
             roof = {"kernel": "umma_conv_p4_kernel (%d launches) + umma_conv_kernel<EVAL> (%d) — tcgen05 kind::tf32" % (n_p4, len(um) - n_p4),
                     "bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
-                    "traffic": P4_DRAM_BYTES_PER_LAUNCH, "launches": len(um), "avg_launch_ms": t_ms / len(um),
+                    "traffic": P4_DRAM_BYTES_PER_LAUNCH * (count / float(-(-count // (args.chunk_max or args.chunk)))) / 10.0,
+                    "launches": len(um), "avg_launch_ms": t_ms / len(um),
                     "peak_source": "hbm_gbs of %s" % peaks["source"],
                     "traffic_source": P4_TRAFFIC_SOURCE,
                     "algorithmic_bytes_per_launch": alg_bytes / len(um),
