@@ -823,6 +823,7 @@ class MCEngine:
         return self._predict_sum_eager(x, samples, sample0, injected)
 
     def _predict_sum_graph(self, x, samples, sample0):
+        self._get_prep(x.device)        # a parameter update since the capture invalidates the graphs (they replay prepared operands)
         key = (tuple(x.shape), x.dtype, int(samples), int(sample0), noise.seed(), x.device.index)
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)

@@ -263,3 +263,23 @@ def test_lenet_mc_dropout_engine(golden, mode, rtol):
     a = mc.MCEngine(net, math_mode=mode, chunk=4).predict_sum(x, 8)
     e2 = mc.MCEngine(net, math_mode=mode, chunk=3)
     close(a, e2.predict_sum(x, 3, sample0=0) + e2.predict_sum(x, 5, sample0=3), 1e-5, 1e-6)
+
+
+def test_engine_graph_follows_parameter_updates():
+    """The CUDA graph replays prepared (blocked, BN-folded) operands: an in-place parameter update between two predict
+    calls must invalidate it (train -> eval loops), and the replayed result must equal the eager one."""
+    from qbn_b200 import mc, noise
+    P, x, net = _resnet()
+    net.eval()
+    noise.manual_seed(3)
+    eng = mc.MCEngine(net, math_mode="tf32", chunk=4)
+    a1 = eng.predict_sum(x.cuda(), 4)
+    a2 = eng.predict_sum(x.cuda(), 4)                     # replay
+    assert torch.equal(a1, a2)
+    with torch.no_grad():
+        net.layers[0].weight.mul_(1.5)                    # "optimizer step"
+        net.layers[1].running_mean.add_(0.1)
+    b_graph = eng.predict_sum(x.cuda(), 4)
+    assert not torch.allclose(b_graph, a1)
+    eager = mc.MCEngine(net, math_mode="tf32", chunk=4, use_graph=False).predict_sum(x.cuda(), 4)
+    close(b_graph, eager, 1e-6, 1e-7)
