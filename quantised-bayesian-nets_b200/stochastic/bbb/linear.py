@@ -6,43 +6,36 @@ import torch.nn as nn
 from torch.nn import ReLU
 
 from ... import config, noise, ops
+from ._shared import attach_bayes_state, noise_key, typed_container
 from .utils_bbb import kl_divergence
 
 
 class Linear(nn.Linear):
     def __init__(self, in_features, out_features, bias, sigma_prior=1.0, args=None):
-        super(Linear, self).__init__(in_features, out_features, bias)
-        self.std_prior = torch.nn.Parameter(torch.ones((1,)) * sigma_prior, requires_grad=False)  # linear.py:11-12
-        self.weight.data.uniform_(-0.01, 0.01)                                                    # linear.py:14
-        self.std = nn.Parameter(torch.zeros_like(self.weight).uniform_(-3, -3))                   # linear.py:15
-        self.add_weight = torch.ao.nn.quantized.FloatFunctional()
-        self.mul_noise = torch.ao.nn.quantized.FloatFunctional()
-        self.args = args
+        nn.Linear.__init__(self, in_features, out_features, bias)
+        # linear.py:11-19: rho = -3 everywhere, prior std as a float32 [1] tensor, small uniform bias
+        attach_bayes_state(self, -3.0, torch.ones((1,)) * sigma_prior, args)
         if self.bias is not None:
-            self.bias.data.uniform_(-0.01, 0.01)
-        self._qbn_layer_id = noise.new_layer_id()
+            with torch.no_grad():
+                self.bias.uniform_(-0.01, 0.01)
+
+    _key = noise_key
 
     def get_kl_divergence(self):
         """linear.py:24-28."""
         return kl_divergence(self.weight, self.std, None, self.std_prior)
 
-    def _key(self):
-        return (noise.seed(), self._qbn_layer_id, noise.next_draw())
-
     def forward(self, x):
-        squeeze = x.dim() == 1
-        if squeeze:
-            x = x.unsqueeze(0)
-        K, N = self.in_features, self.out_features
+        vector = x.dim() == 1
+        rows = x.unsqueeze(0) if vector else x
         if self.training:
             # linear.py:32-40 — LRT: both contractions + noise + bias in one kernel
-            mode = config.pick_math_mode(K, N, lrt=True)
-            eps = noise.pop_injected()
-            out = ops.LRTFunction.apply(x, self.weight, self.std, self.bias, 1, 0, 1, eps, self._key(), mode, False, None)
+            mode = config.pick_math_mode(self.in_features, self.out_features, lrt=True)
+            out = ops.LRTFunction.apply(rows, self.weight, self.std, self.bias, 1, 0, 1, noise.pop_injected(), self._key(), mode, False, None)
         else:
             # linear.py:42-50 — one weight draw per forward, W = mu + softplus(rho)*eps
-            out = eval_forward(self, x.detach(), 1, 0, 1)
-        return out.squeeze(0) if squeeze else out
+            out = eval_forward(self, rows.detach(), 1, 0, 1)
+        return out[0] if vector else out
 
 
 def eval_forward(mod, x, stride, padding, dilation, relu=False):
@@ -59,8 +52,4 @@ def eval_forward(mod, x, stride, padding, dilation, relu=False):
         return ops.conv_forward(xc, w, d, 1, True, False, None, mod.bias, None, relu, None, 1.0, mode)
 
 
-class LinearReLU(torch.nn.Sequential):
-    def __init__(self, linear, relu):
-        assert type(linear) == Linear and type(relu) == ReLU, \
-            'Incorrect types for input modules{}{}'.format(type(linear), type(relu))
-        super(LinearReLU, self).__init__(linear, relu)
+LinearReLU = typed_container("LinearReLU", "Linear + ReLU awaiting QAT / conversion (linear.py:54-59).", Linear, ReLU, module=__name__)

@@ -5,9 +5,9 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .... import config, noise, ops
+from .._shared import QATMixin
 from ..conv import Conv2d as Conv2dBBB
 from ..conv import ConvBn2d as ConvBn2dBBB
 from ..conv import ConvBnReLU2d as ConvBnReLU2dBBB
@@ -27,150 +27,104 @@ def _contract(mod, X, weight, std):
     return ops.conv_forward(xc, ops.pack_ohwi(w.detach()).reshape(1, -1), d, 1, True, False, None, None, None, False, None, 1.0, ops.QBN_MATH_FP32)
 
 
-class Conv2d(Conv2dBBB):
+def _per_channel(v):
+    return v.reshape(1, -1, 1, 1)
+
+
+def _conv_ctor_args(conv):
+    return (conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups,
+            conv.bias is not None, conv.padding_mode)
+
+
+class Conv2d(QATMixin, Conv2dBBB):
     _FLOAT_MODULE = Conv2dBBB
+    _NAME = 'QATConv2d'
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=False,
                  padding_mode='zeros', qconfig=None, args=None):
-        super(Conv2d, self).__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, padding_mode, args=args)
-        assert qconfig, 'qconfig must be provided for QAT module'
-        self.qconfig = qconfig
-        self.weight_fake_quant = qconfig.weight()
-        self.activation_post_process = qconfig.activation()
-        self.std_fake_quant = qconfig.weight()
+        Conv2dBBB.__init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, padding_mode, args=args)
+        self._attach_qat(qconfig)
 
     def _forward(self, X):
-        weight = self.weight_fake_quant(self.weight)
-        std = self.std_fake_quant(F.softplus(self.std))
-        Z = _contract(self, X, weight, std)
-        if self.bias is not None:
-            Z = Z + self.bias.reshape(1, -1, 1, 1)
-        return Z
-
-    def forward(self, input):
-        return self.activation_post_process(self._forward(input))
-
-    def _get_name(self):
-        return 'QATConv2d'
+        out = _contract(self, X, *self._fake_quantised())
+        return out if self.bias is None else out + _per_channel(self.bias)
 
     @classmethod
     def from_float(cls, mod, qconfig=None):
-        assert type(mod) == cls._FLOAT_MODULE, ' qat.' + cls.__name__ + '.from_float only works for ' + cls._FLOAT_MODULE.__name__
-        if not qconfig:
-            assert hasattr(mod, 'qconfig'), 'Input float module must have qconfig defined'
-            assert mod.qconfig, 'Input float module must have a valid qconfig'
-        if isinstance(mod, ConvReLU2dBBB):
-            mod = mod[0]
-        qconfig = mod.qconfig
-        q = cls(mod.in_channels, mod.out_channels, mod.kernel_size, mod.stride, mod.padding, mod.dilation, mod.groups,
-                mod.bias is not None, mod.padding_mode, qconfig)
-        q.activation_post_process = mod.activation_post_process
-        q.weight, q.std, q.std_prior, q.bias, q.args = mod.weight, mod.std, mod.std_prior, mod.bias, mod.args
-        q.add_weight, q.mul_noise = mod.add_weight, mod.mul_noise
-        q.add_weight.activation_post_process = qconfig.weight()
-        q.mul_noise.activation_post_process = qconfig.weight()
-        q._qbn_layer_id = mod._qbn_layer_id
-        return q
+        cls._check_float(mod, qconfig)
+        src = mod[0] if isinstance(mod, ConvReLU2dBBB) else mod
+        return cls._adopt(cls(*_conv_ctor_args(src), src.qconfig), src, src.qconfig)
 
 
 class ConvBn2d(Conv2d):
     _version = 1
     _FLOAT_MODULE = ConvBn2dBBB
+    _NAME = 'QATConvBn2d'
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=False,
                  padding_mode='zeros', eps=1e-05, momentum=0.1, freeze_bn=False, qconfig=None, args=None):
-        super(ConvBn2d, self).__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
-                                       padding_mode, qconfig, args)
-        self.freeze_bn = freeze_bn if self.training else True
+        Conv2d.__init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, padding_mode, qconfig, args)
         self.bn = nn.BatchNorm2d(out_channels, eps, momentum, True, True)
         self.reset_bn_parameters()
-        if self.training:
-            if freeze_bn:
-                self.freeze_bn_stats()
-            else:
-                self.update_bn_stats()
-        else:
-            self.freeze_bn_stats()
+        # conv_qat.py:97-106: statistics move only in training mode and only when not frozen
+        self.freeze_bn = bool(freeze_bn) or not self.training
+        (self.freeze_bn_stats if self.freeze_bn else self.update_bn_stats)()
 
     def reset_running_stats(self):
         self.bn.reset_running_stats()
 
     def reset_bn_parameters(self):
-        self.bn.reset_running_stats()
-        torch.nn.init.uniform_(self.bn.weight)
-        torch.nn.init.zeros_(self.bn.bias)
+        """conv_qat.py:111-120: gamma ~ U(0,1), beta = 0, conv bias ~ U(+-1/sqrt(fan_in))."""
+        self.reset_running_stats()
+        nn.init.uniform_(self.bn.weight)
+        nn.init.zeros_(self.bn.bias)
         if self.bias is not None:
-            fan_in, _ = torch.nn.init._calculate_fan_in_and_fan_out(self.weight)
-            bound = 1 / math.sqrt(fan_in)
-            torch.nn.init.uniform_(self.bias, -bound, bound)
+            bound = 1 / math.sqrt(nn.init._calculate_fan_in_and_fan_out(self.weight)[0])
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def _set_bn_frozen(self, frozen):
+        self.freeze_bn, self.bn.training = frozen, not frozen
+        return self
 
     def update_bn_stats(self):
-        self.freeze_bn = False
-        self.bn.training = True
-        return self
+        return self._set_bn_frozen(False)
 
     def freeze_bn_stats(self):
-        self.freeze_bn = True
-        self.bn.training = False
-        return self
+        return self._set_bn_frozen(True)
 
     def train(self, mode=True):
+        """conv_qat.py:131-137: a frozen BatchNorm stays in eval mode whatever the parent does."""
         self.training = mode
-        if not self.freeze_bn:
-            for module in self.children():
-                module.train(mode)
+        for child in (() if self.freeze_bn else self.children()):
+            child.train(mode)
         return self
 
     def _forward(self, X):
         # conv_qat.py:139-167: scale mu and sigma by gamma/sqrt(running_var+eps) BEFORE fake-quant,
         # contract, divide the scale back out, add the conv bias, run the real BatchNorm.
-        running_std = torch.sqrt(self.bn.running_var + self.bn.eps)
-        scale_factor = self.bn.weight / running_std
-        weight = self.weight_fake_quant(self.weight * scale_factor.reshape([-1, 1, 1, 1]))
-        std = self.std_fake_quant(F.softplus(self.std) * scale_factor.reshape([-1, 1, 1, 1]))
-        Z = _contract(self, X, weight, std)
-        Z_orig = Z / scale_factor.reshape([1, -1, 1, 1])
-        if self.bias is not None:
-            Z_orig = Z_orig + self.bias.reshape([1, -1, 1, 1])
-        return self.bn(Z_orig)
-
-    def _get_name(self):
-        return 'QATConvBn2d'
+        scale = self.bn.weight / torch.sqrt(self.bn.running_var + self.bn.eps)
+        out = _contract(self, X, *self._fake_quantised(scale.reshape(-1, 1, 1, 1))) / _per_channel(scale)
+        return self.bn(out if self.bias is None else out + _per_channel(self.bias))
 
     @classmethod
     def from_float(cls, mod, qconfig=None):
-        assert type(mod) == cls._FLOAT_MODULE, 'qat.' + cls.__name__ + '.from_float only works for ' + cls._FLOAT_MODULE.__name__
+        if type(mod) != cls._FLOAT_MODULE:
+            raise AssertionError('qat.' + cls.__name__ + '.from_float only works for ' + cls._FLOAT_MODULE.__name__)
         conv, bn = mod[0], mod[1]
-        if not qconfig:
-            qconfig = getattr(mod, 'qconfig', None) or conv.qconfig
-        q = cls(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups,
-                conv.bias is not None, conv.padding_mode, bn.eps, bn.momentum, False, qconfig)
-        q.activation_post_process = conv.activation_post_process
-        q.mul_noise, q.add_weight = conv.mul_noise, conv.add_weight
-        q.mul_noise.activation_post_process = qconfig.weight()
-        q.add_weight.activation_post_process = qconfig.weight()
-        q.weight, q.std, q.std_prior, q.bias, q.args = conv.weight, conv.std, conv.std_prior, conv.bias, conv.args
-        q.bn.weight, q.bn.bias = bn.weight, bn.bias
-        q.bn.running_mean, q.bn.running_var, q.bn.num_batches_tracked = bn.running_mean, bn.running_var, bn.num_batches_tracked
-        q._qbn_layer_id = conv._qbn_layer_id
+        qconfig = qconfig or getattr(mod, 'qconfig', None) or conv.qconfig
+        q = cls._adopt(cls(*_conv_ctor_args(conv), bn.eps, bn.momentum, False, qconfig), conv, qconfig)
+        for name in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            setattr(q.bn, name, getattr(bn, name))
         return q
 
 
 class ConvBnReLU2d(ConvBn2d):
     _FLOAT_MODULE = ConvBnReLU2dBBB
-
-    def forward(self, input):
-        return self.activation_post_process(F.relu(self._forward(input)))
-
-    def _get_name(self):
-        return 'QATConvBnReLU2d'
+    _NAME = 'QATConvBnReLU2d'
+    _RELU = True
 
 
 class ConvReLU2d(Conv2d):
     _FLOAT_MODULE = ConvReLU2dBBB
-
-    def forward(self, input):
-        return self.activation_post_process(F.relu(self._forward(input)))
-
-    def _get_name(self):
-        return 'QATConvReLU2d'
+    _NAME = 'QATConvReLU2d'
+    _RELU = True
