@@ -1,0 +1,163 @@
+"""CPU (pytest -m "not gpu"): host-side behaviour of the drop-in modules that needs no kernel — construction and seeded
+initialisation, the exact-type fused containers, BatchNorm folding, the QAT swap done by prepare_model and the BN
+freeze/update API.  The reference behaviour each check follows is cited inline."""
+import copy
+import pickle
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import qbn_b200  # noqa: F401
+from qbn_b200 import quant_utils as qu, zoo
+from qbn_b200.stochastic.bbb import conv as C, linear as L
+from qbn_b200.stochastic.bbb.quantized import conv_qat as CQ, linear_qat as LQ
+from qbn_b200.stochastic.mcdropout.dropout import BernoulliDropout
+
+
+def test_initialisation_follows_the_reference_recipe():
+    # src/models/stochastic/bbb/conv.py:15-18, linear.py:11-19
+    torch.manual_seed(3)
+    c = C.Conv2d(3, 8, 3, padding=1, sigma_prior=-2)
+    assert c.weight.abs().max() <= 0.01 and torch.all(c.std == -10) and c.bias is None
+    assert c.std_prior.dtype == torch.int64 and c.std_prior.item() == -2 and not c.std_prior.requires_grad
+    lin = L.Linear(16, 4, True, sigma_prior=0.5)
+    assert lin.weight.abs().max() <= 0.01 and torch.all(lin.std == -3) and lin.bias.abs().max() <= 0.01
+    assert lin.std_prior.dtype == torch.float32 and lin.std_prior.item() == 0.5
+    assert sorted(n for n, _ in lin.named_parameters()) == ["bias", "std", "std_prior", "weight"]
+    # seeded construction consumes the generator like the reference: mu ~ U, then rho via uniform_(a, a), then the bias
+    # (nn.Conv2d's own reset_parameters runs first, so replay it on a plain conv before comparing)
+    torch.manual_seed(3)
+    nn.Conv2d(3, 8, 3, padding=1, bias=False)
+    w = torch.empty(8, 3, 3, 3).uniform_(-0.01, 0.01)
+    torch.empty(8, 3, 3, 3).uniform_(-10, -10)
+    after = torch.rand(4)
+    torch.manual_seed(3)
+    c2 = C.Conv2d(3, 8, 3, padding=1)
+    assert torch.equal(c2.weight, w) and torch.equal(torch.rand(4), after)
+    assert c._qbn_layer_id != c2._qbn_layer_id
+
+
+def test_unsupported_conv_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        C.Conv2d(4, 4, 3, groups=2)
+    with pytest.raises(NotImplementedError):
+        C.Conv2d(4, 4, 3, padding_mode="reflect")
+
+
+def test_fused_containers_accept_exact_types_only():
+    # conv.py:49-68, linear.py:54-59
+    c, bn, r = C.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU()
+    assert [type(m) for m in C.ConvBnReLU2d(c, bn, r)] == [C.Conv2d, nn.BatchNorm2d, nn.ReLU]
+    for bad in (lambda: C.ConvBn2d(nn.Conv2d(3, 8, 3), bn), lambda: C.ConvReLU2d(c, nn.ReLU6()), lambda: C.ConvBnReLU2d(c, bn),
+                lambda: L.LinearReLU(nn.Linear(4, 4), r), lambda: C.ConvBn2d(CQ.Conv2d(3, 8, 3, qconfig=qu.qconfig_for(_args())), bn)):
+        with pytest.raises(AssertionError, match="Incorrect types"):
+            bad()
+    box = C.ConvBn2d(c, bn)
+    assert isinstance(box, nn.Sequential) and type(box).__name__ == "ConvBn2d" and type(box).__module__ == C.__name__
+    clone = pickle.loads(pickle.dumps(box))
+    assert type(clone) is C.ConvBn2d and torch.equal(clone[0].weight, c.weight)
+    assert type(copy.deepcopy(L.LinearReLU(L.Linear(4, 4, False), r))) is L.LinearReLU
+
+
+def _args():
+    return zoo.Args(sigma_prior=0.1, model="conv_lenet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+
+
+def _random_bn(n):
+    bn = nn.BatchNorm2d(n)
+    with torch.no_grad():
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    return bn
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_batchnorm_fold_matches_the_closed_form(bias):
+    # conv.py:70-88: mu and sigma scale by c = gamma/sqrt(var+eps) per output channel, bias' = (b - mean)*c + beta
+    torch.manual_seed(0)
+    c, bn = C.Conv2d(3, 8, 3, padding=1, bias=bias).eval(), _random_bn(8).eval()
+    with torch.no_grad():
+        c.std.uniform_(-4, -1)
+    folded = C.fuse_conv_bn(c, bn)
+    assert type(folded) is C.Conv2d and folded is not c and folded._qbn_layer_id == c._qbn_layer_id
+    k = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).double()
+    b0 = c.bias.double() if bias else torch.zeros(8, dtype=torch.double)
+    torch.testing.assert_close(folded.weight.double(), c.weight.double() * k.view(-1, 1, 1, 1), rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(F.softplus(folded.std).double(), F.softplus(c.std).double() * k.view(-1, 1, 1, 1), rtol=2e-5, atol=1e-9)
+    torch.testing.assert_close(folded.bias.double(), (b0 - bn.running_mean.double()) * k + bn.bias.double(), rtol=1e-5, atol=1e-6)
+    with_relu = C.fuse_conv_bn_relu(c, bn, nn.ReLU().eval())
+    assert type(with_relu) is C.ConvReLU2d and torch.equal(with_relu[0].weight, folded.weight)
+
+
+def test_fuse_hooks_by_mode():
+    # conv.py:90-115
+    c, bn, r = C.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU()
+    assert type(C.fuse_conv_bn(c, bn)) is C.ConvBn2d and type(C.fuse_conv_bn_relu(c, bn, r)) is C.ConvBnReLU2d
+    with pytest.raises(AssertionError, match="same mode"):
+        C.fuse_conv_bn(c, copy.deepcopy(bn).eval())
+    with pytest.raises(AssertionError, match="num_features"):
+        C.fuse_conv_bn(c, nn.BatchNorm2d(4))
+    with pytest.raises(AssertionError, match="affine"):
+        C.fuse_conv_bn(c, nn.BatchNorm2d(8, affine=False))
+    with pytest.raises(AssertionError, match="eval"):
+        C.fuse_conv_bn_eval(c, bn)
+    with pytest.raises(NotImplementedError):
+        C.fuse_conv_bn_relu(nn.Conv2d(3, 8, 3), bn, r)
+
+
+def test_prepare_model_swaps_in_the_qat_classes_and_shares_state():
+    # quant_utils.py:112-147, linear_qat.py:46-70, conv_qat.py:52-80,169-208
+    args = _args()
+    c, bn, lin = C.Conv2d(3, 8, 3, padding=1), _random_bn(8), L.Linear(8, 4, False)
+    net = nn.Sequential()
+    net.add_module("block", C.fuse_conv_bn_relu(c, bn, nn.ReLU()))
+    net.add_module("plain", C.Conv2d(8, 8, 1))
+    net.add_module("head", L.LinearReLU(lin, nn.ReLU()))
+    qu.prepare_model(net.train(), args)
+    assert [type(m) for m in net] == [CQ.ConvBnReLU2d, CQ.Conv2d, LQ.LinearReLU]
+    assert [m._get_name() for m in net] == ["QATConvBnReLU2d", "QATConv2d", "QATLinearReLU"]
+    q = net.block
+    assert q.weight is c.weight and q.std is c.std and q.std_prior is c.std_prior and q._qbn_layer_id == c._qbn_layer_id
+    assert q.bn.weight is bn.weight and q.bn.running_var is bn.running_var and q.bn.eps == bn.eps
+    assert net.head.weight is lin.weight and net.head.add_weight is lin.add_weight
+    for m in net:
+        assert {"weight_fake_quant", "std_fake_quant", "activation_post_process"} <= set(dict(m.named_children()))
+        assert isinstance(m.add_weight.activation_post_process, qu.FakeQuantize)
+        assert m.weight_fake_quant.quant_min == -128 and m.activation_post_process.quant_max == 127
+    with pytest.raises(AssertionError, match="from_float only works for"):
+        CQ.ConvBn2d.from_float(C.Conv2d(3, 8, 3))
+    with pytest.raises(AssertionError, match="qconfig"):
+        LQ.Linear(4, 4)
+
+
+def test_qat_batchnorm_freeze_api():
+    # conv_qat.py:97-137
+    q = CQ.ConvBn2d(3, 8, 3, qconfig=qu.qconfig_for(_args()))
+    assert q.freeze_bn is False and q.bn.training
+    assert q.freeze_bn_stats() is q and q.freeze_bn and not q.bn.training
+    q.train()
+    assert q.training and not q.bn.training            # a frozen BN ignores .train()
+    assert q.update_bn_stats() is q and q.bn.training
+    q.eval()
+    assert not q.training and not q.bn.training
+    q.train()
+    assert q.bn.training
+    frozen = CQ.ConvBnReLU2d(3, 8, 3, freeze_bn=True, qconfig=qu.qconfig_for(_args()))
+    assert frozen.freeze_bn and not frozen.bn.training
+    q.bn.running_mean.fill_(1.0)
+    q.reset_running_stats()
+    assert torch.all(q.bn.running_mean == 0)
+
+
+def test_bernoulli_dropout_state_and_identity():
+    # src/models/stochastic/mcdropout/dropout.py:9-17
+    d = BernoulliDropout(0.25)
+    assert set(d.state_dict()) == {"p", "multiplier"} and d.p.item() == 0.25
+    torch.testing.assert_close(d.multiplier, torch.tensor([1 / 0.75]))
+    x = torch.randn(4, 3)
+    assert BernoulliDropout(0.0).eval()(x) is x
+    assert "p=0.25" in repr(d)
