@@ -454,6 +454,125 @@ def gen_qat_int8(src):
     save("tiny_int8", **arrays)
 
 
+def _tiny_qresnet(src, args):
+    """The reference's ConvNetwork_ResNet forward/fuse_model (models_bbb.py:191-259) and BasicBlock (:146-188) over the
+    reference's own layer classes: stem conv + one identity block + one stride-2 block with a 1x1 shortcut, 8x8 inputs."""
+    from src.models.stochastic.bbb.conv import Conv2d
+    from src.models.stochastic.bbb.linear import Linear
+    from src.models.stochastic.bbb.models_bbb import BasicBlock, ConvNetwork_ResNet
+    from src.utils import Flatten
+    net = ConvNetwork_ResNet([1, 3, 32, 32], 10, True, args)
+    sp = args.sigma_prior
+    net.layers = torch.nn.ModuleList([
+        Conv2d(3, 8, kernel_size=3, stride=1, padding=1, bias=False, sigma_prior=sp, args=args), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+        torch.nn.ModuleList([BasicBlock(8, 8, 1, True, args), BasicBlock(8, 16, 2, True, args)]),
+        torch.nn.AvgPool2d(4), Flatten(), Linear(16, 10, sigma_prior=sp, bias=False, args=args)])
+    return net
+
+
+def gen_resnet_int8(src):
+    """Config C3 on a ResNet-shaped net (conv+BN+ReLU fusion, BN fold at convert, quantised residual add, quantised
+    ReLU / average pool): prepare_model, one train + one eval forward, convert, one int8 forward with replayed noise.
+    Every int8 module's integer input/output, every residual add and the pooled map are captured in call order."""
+    import src.quant_utils as qu
+    from src.models.stochastic.bbb.models_bbb import BasicBlock
+    from src.models.stochastic.bbb.quantized import NOISE_SCALE, NOISE_ZERO_POINT
+    from src.utils import Add
+    g = torch.Generator().manual_seed(23)
+    args = Args(sigma_prior=0.1, model="conv_resnet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    net = _tiny_qresnet(src, args)
+    arrays = {}
+    with torch.no_grad():
+        for n, m in net.named_modules():
+            if hasattr(m, "std") and hasattr(m, "weight"):
+                trained_like_(m, g)
+                m.std.uniform_(-6.0, -3.0, generator=g)
+                arrays["p.%s.weight" % n], arrays["p.%s.std" % n] = npy(m.weight), npy(m.std)
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+                m.weight.uniform_(0.5, 1.5, generator=g)
+                m.bias.normal_(0, 0.1, generator=g)
+                for k in ("running_mean", "running_var", "weight", "bias"):
+                    arrays["p.%s.%s" % (n, k)] = npy(getattr(m, k))
+    net.train()
+    qu.prepare_model(net, args)
+    for m in net.modules():                  # keep the BatchNorm statistics fixed so the fixture's parameters are the ones used
+        if hasattr(m, "freeze_bn_stats"):
+            m.freeze_bn_stats()
+    x = torch.rand(8, 3, 8, 8, generator=g)
+    arrays["x"] = npy(x)
+    torch.manual_seed(2000)
+    arrays["tr.y"] = npy(net(x))
+    net.eval()
+    torch.manual_seed(2001)
+    with torch.no_grad():
+        arrays["ev.y"] = npy(net(x))
+    qat_names = [n for n, m in net.named_modules() if hasattr(m, "weight_fake_quant")]
+    arrays["qat_names"] = np.array(qat_names)
+    arrays["qat_types"] = np.array([type(dict(net.named_modules())[n]).__name__ for n in qat_names])
+
+    qu.convert(net)
+    net.eval()
+    mods = dict(net.named_modules())
+    order, caps = [], {}
+
+    def cap(name):
+        def hook(mod, inp, out):
+            order.append(name)
+            caps[name] = (tuple(t.detach().clone() for t in inp), out.detach().clone())
+        return hook
+
+    watched = [n for n, m in mods.items() if (hasattr(m, "mul_noise") and hasattr(m, "scale")) or isinstance(m, (Add, BasicBlock, torch.nn.AvgPool2d))]
+    hooks = [mods[n].register_forward_hook(cap(n)) for n in watched]
+    torch.manual_seed(2002)
+    with torch.no_grad():
+        yq = net(x)
+    for h in hooks:
+        h.remove()
+
+    def qp(t):
+        return np.array([t.q_scale(), t.q_zero_point()], np.float64)
+
+    arrays["quant_qp"] = np.array([float(net.quant.scale), int(net.quant.zero_point)], np.float64)
+    q_names = [n for n in order if hasattr(mods[n], "mul_noise")]
+    torch.manual_seed(2002)
+    for n in q_names:                        # noise replay in call order (stem, stem, shortcut inside a block)
+        m = mods[n]
+        eps = torch.empty(m.std.shape).normal_()
+        (xin,), out = caps[n]
+        arrays["%s.eps" % n] = npy(eps)
+        arrays["%s.x_q" % n], arrays["%s.x_qp" % n] = npy(xin.int_repr()), qp(xin)
+        arrays["%s.y_q" % n], arrays["%s.y_qp" % n] = npy(out.int_repr()), qp(out)
+        arrays["%s.mu_q" % n], arrays["%s.mu_qp" % n] = npy(m.weight.int_repr()), qp(m.weight)
+        arrays["%s.sigma_q" % n], arrays["%s.sigma_qp" % n] = npy(m.std.int_repr()), qp(m.std)
+        arrays["%s.mul_qp" % n] = np.array([m.mul_noise.scale, m.mul_noise.zero_point], np.float64)
+        arrays["%s.add_qp" % n] = np.array([m.add_weight.scale, m.add_weight.zero_point], np.float64)
+        arrays["%s.out_qp" % n] = np.array([m.scale, m.zero_point], np.float64)
+        arrays["%s.relu" % n] = np.array("ReLU" in type(m).__name__)
+        bias = m.bias() if callable(getattr(m, "bias", None)) else None
+        arrays["%s.bias" % n] = npy(bias) if bias is not None else np.zeros(0, np.float32)
+        nq = torch.quantize_per_tensor(eps, NOISE_SCALE, NOISE_ZERO_POINT, dtype=torch.qint8)
+        arrays["%s.w_q" % n] = npy(m.add_weight.add(m.weight, m.mul_noise.mul(m.std, nq)).int_repr())
+        if m.weight.dim() == 4:
+            arrays["%s.conv" % n] = np.array([m.stride[0], m.padding[0]])
+    for n in order:
+        m = mods[n]
+        if isinstance(m, Add):
+            (a, b), out = caps[n]
+            arrays["%s.a_q" % n], arrays["%s.a_qp" % n] = npy(a.int_repr()), qp(a)
+            arrays["%s.b_q" % n], arrays["%s.b_qp" % n] = npy(b.int_repr()), qp(b)
+            arrays["%s.y_q" % n], arrays["%s.y_qp" % n] = npy(out.int_repr()), qp(out)
+        elif isinstance(m, (BasicBlock, torch.nn.AvgPool2d)):
+            (xin,), out = caps[n]
+            arrays["%s.x_q" % n], arrays["%s.y_q" % n], arrays["%s.y_qp" % n] = npy(xin.int_repr()), npy(out.int_repr()), qp(out)
+    arrays["order"] = np.array(order)
+    arrays["q_names"] = np.array(q_names)
+    arrays["y"] = npy(yq)
+    save("tiny_resnet_int8", **arrays)
+
+
+
 def gen_quant_ops(src):
     """Direct pins of the third-party integer ops (torch.ops.quantized.*) the A6 recipe calls."""
     rng = np.random.default_rng(18)
@@ -543,6 +662,7 @@ def main():
     gen_mc_models(src)
     gen_quant_ops(src)
     gen_qat_int8(src)
+    gen_resnet_int8(src)
 
 
 if __name__ == "__main__":

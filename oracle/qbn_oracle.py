@@ -274,6 +274,24 @@ def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=8, n_vec=None):
     return np.clip(q, amin, amax).astype(np.int32)
 
 
+def i8_relu(x_q, z_x, act_bits=8):
+    """torch.relu on a quint8 tensor (BasicBlock.end, models_bbb.py:186) + clamp_activation: ints below the zero
+    point are raised to it; qparams unchanged."""
+    amin, amax = UINT_BOUNDS[act_bits]
+    return np.clip(np.maximum(np.asarray(x_q, np.int32), z_x), amin, amax).astype(np.int32)
+
+
+def i8_avgpool(x_q, z_x, k, act_bits=8):
+    """nn.AvgPool2d(k) on a quint8 NCHW tensor (models_bbb.py:211; ATen qavg_pool2d, output qparams = input's):
+    acc = sum(window) - k*k*z int32; q = clamp(rint(fp32(acc) * fp32(1/(k*k))) + z, 0, 255), then clamp_activation."""
+    x = np.asarray(x_q, np.int32)
+    B, C, H, W = x.shape
+    win = x.reshape(B, C, H // k, k, W // k, k).sum(axis=(3, 5)) - k * k * z_x
+    q = np.clip(np.rint(win.astype(f32) * f32(f32(1.0) / f32(k * k))) + z_x, 0, 255)
+    amin, amax = UINT_BOUNDS[act_bits]
+    return np.clip(q, amin, amax).astype(np.int32)
+
+
 def i8_dropout(x_q, s_x, z_x, mask, s_m, z_m, multiplier, act_bits=8):
     """dropout.py:31-39 in the int8 model: mask -> quint8 at (s_m,z_m); quantized.mul with the
     output at (s_m,z_m); mul_scalar keeps the ints and multiplies the scale by `multiplier`.

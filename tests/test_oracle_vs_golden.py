@@ -136,6 +136,74 @@ def test_tiny_int8_layers_bit_exact(golden):
         assert np.array_equal(y, g[n + ".y_q"]), n
 
 
+def _i8_layer(g, n, x_q=None, x_qp=None, act_bits=8):
+    """One converted BBB layer of an int8 fixture through the oracle: (sampled int8 weight, integer output)."""
+    qp = lambda k: (float(g[n + k][0]), int(g[n + k][1]))
+    (s_mu, z_mu), (s_sg, z_sg), (s_mul, z_mul), (s_add, z_add), (s_o, z_o) = qp(".mu_qp"), qp(".sigma_qp"), qp(".mul_qp"), qp(".add_qp"), qp(".out_qp")
+    s_x, z_x = qp(".x_qp") if x_qp is None else x_qp
+    x_q = g[n + ".x_q"] if x_q is None else x_q
+    w = O.i8_sample_weight(g[n + ".mu_q"], s_mu, z_mu, g[n + ".sigma_q"], s_sg, z_sg, g[n + ".eps"], s_mul, z_mul, s_add, z_add, w_bits=8)
+    relu = bool(g[n + ".relu"])
+    bias = g[n + ".bias"] if (n + ".bias") in g.files and g[n + ".bias"].size else None
+    if w.ndim == 4:
+        stride, pad = g[n + ".conv"]
+        y, _ = O.i8_conv(x_q, s_x, z_x, w, s_add, z_add, bias, s_o, z_o, int(stride), int(pad), 1, relu, act_bits=act_bits)
+    else:
+        y, _ = O.i8_linear(x_q, s_x, z_x, w, s_add, z_add, bias, s_o, z_o, relu, act_bits=act_bits)
+    return w, y, (s_o, z_o)
+
+
+def test_tiny_resnet_int8_layers_bit_exact(golden):
+    """Every captured node of the converted ResNet-shaped net, one at a time from the reference's own integer inputs."""
+    g = golden("tiny_resnet_int8")
+    for n in [str(v) for v in g["order"]]:
+        if n + ".mu_q" in g.files:
+            w, y, _ = _i8_layer(g, n)
+            assert np.array_equal(w, g[n + ".w_q"]), n
+            assert np.array_equal(y, g[n + ".y_q"]), n
+        elif n.endswith(".add"):
+            (sa, za), (sb, zb), (so, zo) = g[n + ".a_qp"], g[n + ".b_qp"], g[n + ".y_qp"]
+            # the reference's operands are channels_last: ATen walks them in NHWC memory order
+            a, b = (np.ascontiguousarray(g[n + k].transpose(0, 2, 3, 1)) for k in (".a_q", ".b_q"))
+            y = O.i8_add(a, sa, int(za), b, sb, int(zb), so, int(zo), act_bits=8).transpose(0, 3, 1, 2)
+            assert np.array_equal(y, g[n + ".y_q"]), n
+        elif n + ".add.y_q" in g.files:                       # BasicBlock: checked as a whole by the chained test
+            continue
+        else:
+            assert np.array_equal(O.i8_avgpool(g[n + ".x_q"], int(g[n + ".y_qp"][1]), 4, act_bits=7), g[n + ".y_q"]), n
+
+
+def test_tiny_resnet_int8_chained_end_to_end(golden):
+    """The whole int8 network chained through the oracle from the float input: quantise, stem, identity block,
+    stride-2 block with its 1x1 shortcut, quantised ReLU / add / average pool, linear, dequantise, softmax."""
+    g = golden("tiny_resnet_int8")
+    A = 7                                                         # activation_precision of the fixture
+    s, z = float(g["quant_qp"][0]), int(g["quant_qp"][1])
+    h = np.clip(O.quantize(g["x"], s, z, 0, 255), *O.UINT_BOUNDS[A])
+    _, h, (s, z) = _i8_layer(g, "layers.0", h, (s, z), act_bits=A)
+    assert np.array_equal(h, g["layers.0.y_q"])
+    for blk in ("layers.3.0", "layers.3.1"):
+        assert np.array_equal(h, g[blk + ".x_q"]), blk
+        _, t, qp1 = _i8_layer(g, blk + ".stem.0", h, (s, z), act_bits=A)
+        _, t, qp2 = _i8_layer(g, blk + ".stem.3", t, qp1, act_bits=A)
+        if blk + ".shortcut.0.mu_q" in g.files:
+            _, sc, qps = _i8_layer(g, blk + ".shortcut.0", h, (s, z), act_bits=A)
+        else:
+            sc, qps = h, (s, z)
+        so, zo = float(g[blk + ".add.y_qp"][0]), int(g[blk + ".add.y_qp"][1])
+        nhwc = lambda v: np.ascontiguousarray(v.transpose(0, 2, 3, 1))
+        t = O.i8_add(nhwc(t), qp2[0], qp2[1], nhwc(sc), qps[0], qps[1], so, zo, act_bits=A).transpose(0, 3, 1, 2)
+        assert np.array_equal(t, g[blk + ".add.y_q"]), blk
+        h, (s, z) = O.i8_relu(t, zo, act_bits=A), (so, zo)
+        assert np.array_equal(h, g[blk + ".y_q"]), blk
+    h = O.i8_avgpool(h, z, 4, act_bits=A)
+    assert np.array_equal(h, g["layers.4.y_q"])
+    _, h, (s, z) = _i8_layer(g, "layers.6", h.reshape(h.shape[0], -1), (s, z), act_bits=A)
+    assert np.array_equal(h, g["layers.6.y_q"])
+    logits = torch.as_tensor(O.dequantize(h, s, z))
+    close(torch.softmax(logits, dim=-1), g["y"], 1e-6, 1e-7)
+
+
 def _eps_fn_from(noise_by_name):
     return lambda name, shape: noise_by_name[name]
 
