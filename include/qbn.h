@@ -268,6 +268,14 @@ int qbn_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const u
 int qbn_i8_add(const uint8_t* a, float sa, int32_t za, const uint8_t* b, float sb, int32_t zb,
                int64_t n, int64_t n_vec, float so, int32_t zo, int lo, int hi, uint8_t* out,
                void* stream);
+/* torch.relu on quint8 (BasicBlock.end, models_bbb.py:186) fused with clamp_activation (src/utils.py:25-30):
+ * out = clamp(max(x, z_x), lo, hi); qparams unchanged.                                          */
+int qbn_i8_relu(const uint8_t* x, int64_t n, int32_t z_x, int lo, int hi, uint8_t* out, void* stream);
+/* nn.AvgPool2d(k) on a quint8 map (models_bbb.py:211; ATen qavg_pool2d, output qparams = input's), x NHWC
+ * [B][H][W][C] -> out [B][H/k][W/k][C]: q = clamp(rint(fp32(sum - k*k*z) * fp32(1/(k*k))) + z, 0, 255), then
+ * clamp_activation to [lo, hi].                                                                 */
+int qbn_i8_avgpool(const uint8_t* x, int64_t B, int H, int W, int C, int k, int32_t z_x, int lo, int hi,
+                   uint8_t* out, void* stream);
 /* int8 MC-Dropout (dropout.py:31-39): mask quantised at (s_m,z_m) then quantized::mul with the
  * output at the same (s_m,z_m); mul_scalar only rescales.  mask fp32 {0,1} [rows][C] injected
  * or NULL -> Philox.                                                                         */

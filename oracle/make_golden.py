@@ -502,13 +502,24 @@ def gen_resnet_int8(src):
             m.freeze_bn_stats()
     x = torch.rand(8, 3, 8, 8, generator=g)
     arrays["x"] = npy(x)
+    qat_names = [n for n, m in net.named_modules() if hasattr(m, "weight_fake_quant")]     # = call order (stem, stem, shortcut)
+    qat_mods = dict(net.named_modules())
+    out_shapes = {}
+    hooks = [qat_mods[n].register_forward_hook(lambda m, i, o, n=n: out_shapes.__setitem__(n, tuple(o.shape))) for n in qat_names]
     torch.manual_seed(2000)
     arrays["tr.y"] = npy(net(x))
+    for h in hooks:
+        h.remove()
+    torch.manual_seed(2000)
+    for n in qat_names:                      # LRT noise has the layer-output shape, one draw per layer in call order
+        arrays["tr.%s.eps" % n] = npy(torch.empty(out_shapes[n]).normal_())
     net.eval()
     torch.manual_seed(2001)
     with torch.no_grad():
         arrays["ev.y"] = npy(net(x))
-    qat_names = [n for n, m in net.named_modules() if hasattr(m, "weight_fake_quant")]
+    torch.manual_seed(2001)
+    for n in qat_names:                      # eval draws one weight-shaped eps per layer
+        arrays["ev.%s.eps" % n] = npy(torch.empty(qat_mods[n].weight.shape).normal_())
     arrays["qat_names"] = np.array(qat_names)
     arrays["qat_types"] = np.array([type(dict(net.named_modules())[n]).__name__ for n in qat_names])
 

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "qbn_i8_conv_fwd": (c_int, [POINTER(ConvDesc), c_int, c_int, P, c_float, c_int32, P, c_int, c_float, c_int32, P, c_float,
                                 c_int32, c_int, c_int, c_int, P, P, c_int, P]),
     "qbn_i8_add": (c_int, [P, c_float, c_int32, P, c_float, c_int32, c_int64, c_int64, c_float, c_int32, c_int, c_int, P, P]),
+    "qbn_i8_relu": (c_int, [P, c_int64, c_int32, c_int, c_int, P, P]),
+    "qbn_i8_avgpool": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int32, c_int, c_int, P, P]),
     "qbn_i8_dropout": (c_int, [P, c_float, c_int32, c_int64, c_int64, c_int64, P, c_float, c_float, c_int32, c_uint64, c_uint32,
                                c_uint32, c_int, c_int, P, P]),
     "qbn_softmax_accumulate": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),

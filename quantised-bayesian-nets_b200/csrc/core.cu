@@ -673,6 +673,54 @@ extern "C" int qbn_i8_add(const uint8_t* a, float sa, int32_t za, const uint8_t*
   return QBN_OK;
 }
 
+// quint8 ReLU (zero point is the floor) + clamp_activation, and k x k average pooling of an NHWC quint8 map
+// (ATen qavg_pool2d: acc = sum - k*k*z ; q = clamp(rint(fp32(acc) * fp32(1/(k*k))) + z, 0, 255))
+__global__ void i8_relu_kernel(const uint8_t* __restrict__ x, int64_t n, int floor_q, int lo, int hi, uint8_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int q = (int)x[i];
+    q = q < floor_q ? floor_q : q;
+    out[i] = (uint8_t)clampi(q, lo, hi);
+  }
+}
+extern "C" int qbn_i8_relu(const uint8_t* x, int64_t n, int32_t z_x, int lo, int hi, uint8_t* out, void* stream) {
+  QBN_CHECK_ARG(x && out && n > 0, "null pointer / n");
+  QBN_CHECK_ARG(lo >= 0 && hi <= 255 && lo <= hi && z_x >= 0 && z_x <= 255, "0<=lo<=hi<=255, zero point in range");
+  i8_relu_kernel<<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, z_x, lo, hi, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+__global__ void i8_avgpool_kernel(const uint8_t* __restrict__ x, int64_t B, int H, int W, int C, int k, int zx, float inv_area,
+                                  int lo, int hi, uint8_t* __restrict__ out) {
+  const int Ho = H / k, Wo = W / k;
+  const int64_t total = B * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int64_t b = t / Ho;
+    int acc = 0;
+    for (int r = 0; r < k; ++r)
+      for (int q = 0; q < k; ++q) acc += (int)x[((b * H + ho * k + r) * W + wo * k + q) * C + c];
+    acc -= k * k * zx;
+    int v = (int)rintf(__fmul_rn((float)acc, inv_area)) + zx;
+    v = clampi(v, 0, 255);
+    out[i] = (uint8_t)clampi(v, lo, hi);
+  }
+}
+extern "C" int qbn_i8_avgpool(const uint8_t* x, int64_t B, int H, int W, int C, int k, int32_t z_x, int lo, int hi, uint8_t* out,
+                              void* stream) {
+  QBN_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && C > 0, "args");
+  QBN_CHECK_ARG(k > 0 && H % k == 0 && W % k == 0, "k must divide H and W (AvgPool2d(k), stride k, no padding)");
+  QBN_CHECK_ARG(lo >= 0 && hi <= 255 && lo <= hi, "0<=lo<=hi<=255");
+  i8_avgpool_kernel<<<qbn_grid_for(B * (H / k) * (W / k) * C, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, k, z_x,
+                                                                                                 1.0f / (float)(k * k), lo, hi, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
 __global__ void i8_dropout_kernel(const uint8_t* __restrict__ x, int zx, int64_t rows, int64_t hw, int64_t C,
                                   const float* __restrict__ mask, float keep, float inv_sm, int zm, float mult, uint64_t seed,
                                   uint32_t sa, uint32_t sb, int lo, int hi, uint8_t* __restrict__ out) {

@@ -430,6 +430,23 @@ def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=7, n_vec=-1):
     return out
 
 
+def i8_relu(x_q, z_x, act_bits=7):
+    """quint8 ReLU + clamp_activation in one pass (any layout: elementwise)."""
+    out = torch.empty_like(x_q)
+    _lib.call("qbn_i8_relu", _ptr(x_q), x_q.numel(), int(z_x), 0, (1 << act_bits) - 1, _ptr(out), _stream())
+    return out
+
+
+def i8_avgpool(x_q, z_x, k, act_bits=7):
+    """x_q uint8 NCHW-logical / NHWC-dense [B,C,H,W] -> [B,C,H/k,W/k] (same memory format)."""
+    assert x_q.dim() == 4 and x_q.dtype == torch.uint8
+    x_q = x_q.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x_q.shape
+    out = torch.empty((B, C, H // k, W // k), dtype=torch.uint8, device=x_q.device, memory_format=torch.channels_last)
+    _lib.call("qbn_i8_avgpool", _ptr(x_q), B, H, W, C, int(k), int(z_x), 0, (1 << act_bits) - 1, _ptr(out), _stream())
+    return out
+
+
 def i8_dropout(x_q, s_x, z_x, p, s_m, z_m, mask=None, key=(0, 0, 0), act_bits=7):
     if x_q.dim() == 4:
         B, C, H, W = x_q.shape

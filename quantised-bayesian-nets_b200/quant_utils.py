@@ -163,6 +163,32 @@ class DeQuantize(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+class QFunctional(nn.Module):
+    """nnq.QFunctional as the reference uses it (src/utils.py:49-55, the residual add of BasicBlock): quantized::add of two
+    quint8 activations with the output at this module's calibrated (scale, zero_point)."""
+
+    def __init__(self, scale=1.0, zero_point=0):
+        super().__init__()
+        self.scale, self.zero_point = float(scale), int(zero_point)
+        self.activation_post_process = nn.Identity()
+
+    def add(self, x, y):
+        assert isinstance(x, QTensor) and isinstance(y, QTensor), "QFunctional.add takes two QTensor activations"
+        assert x.q.shape == y.q.shape, "residual add: operand shapes differ"
+        a = x.q.contiguous(memory_format=torch.channels_last) if x.q.dim() == 4 else x.q.contiguous()
+        b = y.q.contiguous(memory_format=torch.channels_last) if y.q.dim() == 4 else y.q.contiguous()
+        q = ops.i8_add(a, x.scale, x.zero_point, b, y.scale, y.zero_point, self.scale, self.zero_point, act_bits=8)
+        return QTensor(q, self.scale, self.zero_point)
+
+    def extra_repr(self):
+        return "scale={}, zero_point={}".format(self.scale, self.zero_point)
+
+    @classmethod
+    def from_float(cls, mod):
+        s, z = mod.activation_post_process.calculate_qparams()
+        return cls(float(s), int(z))
+
+
 def qconfig_for(args):
     """quant_utils.py:129-138: activations quint8 [0, 2^a-1], weights qint8 [-2^(w-1), 2^(w-1)-1]."""
     assert 2 <= args.activation_precision <= 7 and 2 <= args.weight_precision <= 8     # quant_utils.py:120-121
@@ -193,6 +219,8 @@ def convert(model, mapping=None, inplace=True):
         if type(child) in mapping:
             new = mapping[type(child)].from_float(child)
             model._modules[name] = new
+        elif isinstance(child, torch.ao.nn.quantized.FloatFunctional) and hasattr(child.activation_post_process, "calculate_qparams"):
+            model._modules[name] = QFunctional.from_float(child)       # torch's default mapping FloatFunctional -> QFunctional
         else:
             convert(child, mapping, inplace=True)
     return model

@@ -8,6 +8,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
+from .quant_utils import QTensor
 from .stochastic.bbb.conv import Conv2d, ConvReLU2d, fuse_conv_bn, fuse_conv_bn_relu  # noqa: F401
 from .stochastic.bbb.linear import Linear, LinearReLU  # noqa: F401
 from .stochastic.bbb.utils_bbb import model_kl_divergence
@@ -40,19 +42,20 @@ def clamp_activation(x, args):
     return x
 
 
-def _apply(layer, x):
+def _apply(layer, x, args=None):
     """Run a non-stochastic glue layer; on int8 activations (QTensor) pooling/ReLU act on the integers
-    (order-preserving per-tensor affine map), like torch's quantised max_pool2d / relu."""
-    from .quant_utils import QTensor
+    (order-preserving per-tensor affine map), like torch's quantised max_pool2d / relu / avg_pool2d."""
     if not isinstance(x, QTensor):
         return layer(x)
+    bits = getattr(args, "activation_precision", 8) if args is not None else 8
     if isinstance(layer, nn.MaxPool2d):
         q = F.max_pool2d(x.q.float(), layer.kernel_size, layer.stride).to(torch.uint8).contiguous(memory_format=torch.channels_last)
         return QTensor(q, x.scale, x.zero_point)
     if isinstance(layer, nn.ReLU):
-        return QTensor(torch.clamp(x.q, min=x.zero_point), x.scale, x.zero_point)
-    if isinstance(layer, (Flatten, nn.Identity)):
-        return layer(x)
+        return QTensor(ops.i8_relu(x.q, x.zero_point, act_bits=bits), x.scale, x.zero_point)
+    if isinstance(layer, nn.AvgPool2d):
+        k = layer.kernel_size if isinstance(layer.kernel_size, int) else layer.kernel_size[0]
+        return QTensor(ops.i8_avgpool(x.q, x.zero_point, k, act_bits=bits), x.scale, x.zero_point)
     return layer(x)
 
 
@@ -127,7 +130,7 @@ class ConvNetwork_LeNet(nn.Module):
         if self.q:
             x = clamp_activation(self.quant(x), self.args)
         for layer in self.layers:
-            x = clamp_activation(_apply(layer, x), self.args)
+            x = clamp_activation(_apply(layer, x, self.args), self.args)
         if self.q:
             x = self.dequant(x)
         return F.softmax(x, dim=-1)
@@ -164,11 +167,21 @@ class BasicBlock(nn.Module):
     def forward(self, x):
         out = x
         for layer in self.stem:
-            out = layer(out)
+            out = clamp_activation(_apply(layer, out, self.args), self.args)
         shortcut = x
         for layer in self.shortcut:
-            shortcut = layer(shortcut)
-        return self.end(self.add(out, shortcut))
+            shortcut = clamp_activation(_apply(layer, shortcut, self.args), self.args)
+        out = clamp_activation(self.add(out, shortcut), self.args)
+        return clamp_activation(_apply(self.end, out, self.args), self.args)
+
+    def fuse_model(self):
+        """models_bbb.py:182-188: conv+BN+ReLU, conv+BN and the shortcut's conv+BN become one module each (a typed
+        container for QAT in training mode, a BN-folded conv in eval mode); the absorbed slots turn into Identity."""
+        st = self.stem
+        st[0], st[1], st[2] = fuse_conv_bn_relu(st[0], st[1], st[2]), nn.Identity(), nn.Identity()
+        st[3], st[4] = fuse_conv_bn(st[3], st[4]), nn.Identity()
+        if len(self.shortcut) == 2:
+            self.shortcut[0], self.shortcut[1] = fuse_conv_bn(self.shortcut[0], self.shortcut[1]), nn.Identity()
 
 
 class ConvNetwork_ResNet(nn.Module):
@@ -193,15 +206,27 @@ class ConvNetwork_ResNet(nn.Module):
         self.layers.append(Flatten())
         self.layers.append(Linear(192, output_size, sigma_prior=sp, bias=False, args=args))
         self.q = q
+        if self.q:
+            self.quant = torch.ao.quantization.QuantStub()
+            self.dequant = torch.ao.quantization.DeQuantStub()
 
     def forward(self, x):
+        if self.q:
+            x = clamp_activation(self.quant(x), self.args)
         for layer in self.layers:
-            if isinstance(layer, nn.ModuleList):
-                for sub in layer:
-                    x = sub(x)
-            else:
-                x = layer(x)
+            for sub in (layer if isinstance(layer, nn.ModuleList) else (layer,)):
+                x = clamp_activation(_apply(sub, x, self.args), self.args)
+        if self.q:
+            x = self.dequant(x)
         return F.softmax(x, dim=-1)
+
+    def fuse_model(self):
+        """models_bbb.py:245-249: the input conv+BN+ReLU, then every block."""
+        L = self.layers
+        L[0], L[1], L[2] = fuse_conv_bn_relu(L[0], L[1], L[2]), nn.Identity(), nn.Identity()
+        for m in self.modules():
+            if isinstance(m, BasicBlock):
+                m.fuse_model()
 
     def get_kl_divergence(self):
         return model_kl_divergence(self)

@@ -142,3 +142,131 @@ def test_int8_modules_bit_exact_with_reference_qparams(golden):
             y = m(x)
         assert np.array_equal(y.q.cpu().numpy(), g[n + ".y_q"]), n
         assert abs(y.scale - g[n + ".y_qp"][0]) < 1e-12 and y.zero_point == int(g[n + ".y_qp"][1])
+
+
+# ---- ResNet-shaped net: conv+BN(+ReLU) fusion, BN fold at convert, quantised residual add / ReLU / average pool ----------
+def _tiny_resnet(args):
+    from qbn_b200 import zoo
+    from qbn_b200.stochastic.bbb.conv import Conv2d
+    from qbn_b200.stochastic.bbb.linear import Linear
+    net = zoo.ConvNetwork_ResNet([1, 3, 32, 32], 10, True, args)
+    sp = args.sigma_prior
+    net.layers = nn.ModuleList([
+        Conv2d(3, 8, kernel_size=3, stride=1, padding=1, bias=False, sigma_prior=sp, args=args), nn.BatchNorm2d(8), nn.ReLU(),
+        nn.ModuleList([zoo.BasicBlock(8, 8, 1, True, args), zoo.BasicBlock(8, 16, 2, True, args)]),
+        nn.AvgPool2d(4), zoo.Flatten(), Linear(16, 10, sigma_prior=sp, bias=False, args=args)])
+    return net
+
+
+def _load_float_state(net, g):
+    mods = dict(net.named_modules())
+    with torch.no_grad():
+        for key in g.files:
+            if key.startswith("p."):
+                name, _, leaf = key[2:].rpartition(".")
+                getattr(mods[name], leaf).copy_(torch.as_tensor(g[key]))
+
+
+def _set_module(net, name, new):
+    parent, _, leaf = name.rpartition(".")
+    (net.get_submodule(parent) if parent else net)._modules[leaf] = new
+
+
+def _int8_module(g, n, args):
+    """A drop-in int8 layer carrying the reference's own int8 state for node `n` of a fixture."""
+    from qbn_b200.stochastic.bbb.quantized import conv_q, linear_q
+    mu_q, relu = g[n + ".mu_q"], bool(g[n + ".relu"])
+    if mu_q.ndim == 4:
+        stride, pad = [int(v) for v in g[n + ".conv"]]
+        cls = conv_q.ConvReLU2d if relu else conv_q.Conv2d
+        m = cls(mu_q.shape[1], mu_q.shape[0], mu_q.shape[2:], stride=(stride, stride), padding=(pad, pad), dilation=(1, 1), args=args)
+    else:
+        m = (linear_q.LinearReLU if relu else linear_q.Linear)(mu_q.shape[1], mu_q.shape[0], args=args)
+    m.weight, m.std = torch.as_tensor(mu_q).cuda(), torch.as_tensor(g[n + ".sigma_q"]).cuda()
+    for attr in ("mu_qp", "sigma_qp", "mul_qp", "add_qp"):
+        setattr(m, attr, (float(g["%s.%s" % (n, attr)][0]), int(g["%s.%s" % (n, attr)][1])))
+    m.scale, m.zero_point = float(g[n + ".out_qp"][0]), int(g[n + ".out_qp"][1])
+    if (n + ".bias") in g.files and g[n + ".bias"].size:          # the folded BatchNorm shift (conv_q.py:130-133)
+        m.bias_ = torch.as_tensor(g[n + ".bias"]).cuda()
+    return m
+
+
+def test_resnet_qat_then_int8_lifecycle(golden):
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import noise, quant_utils as qu, zoo
+    g = golden("tiny_resnet_int8")
+    args = zoo.Args(sigma_prior=0.1, model="conv_resnet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    net = _tiny_resnet(args)
+    _load_float_state(net, g)
+    net.train()
+    qu.prepare_model(net, args)
+    mods = dict(net.named_modules())
+    names = [str(n) for n in g["qat_names"]]
+    assert [type(mods[n]).__name__ for n in names] == [str(t) for t in g["qat_types"]]
+    for m in net.modules():
+        if hasattr(m, "freeze_bn_stats"):
+            m.freeze_bn_stats()
+    net = net.cuda()
+    x = torch.as_tensor(g["x"]).cuda()
+    with noise.inject([torch.as_tensor(g["tr.%s.eps" % n]).cuda() for n in names]):
+        y = net(x)                                       # QAT train forward: LRT over fake-quantised, BN-scaled (mu~, sigma~)
+    assert y.shape == (8, 10) and torch.isfinite(y).all()
+    assert float((y.detach().cpu() - torch.as_tensor(g["tr.y"])).abs().max()) < 0.05
+    y.sum().backward()
+    assert all(mods[n].weight.grad is not None and torch.isfinite(mods[n].weight.grad).all() for n in names)
+    net.eval()
+    with torch.no_grad(), noise.inject([torch.as_tensor(g["ev.%s.eps" % n]).cuda() for n in names]):
+        ye = net(x)                                      # calibrates add_weight / mul_noise
+    assert float((ye.cpu() - torch.as_tensor(g["ev.y"])).abs().max()) < 0.05
+    qu.convert(net)
+    net.eval()
+    mods = dict(net.named_modules())
+    q_names = [str(n) for n in g["q_names"]]
+    assert [type(mods[n]).__name__ for n in q_names] == ["ConvReLU2d", "ConvReLU2d", "Conv2d", "ConvReLU2d", "Conv2d", "Conv2d", "Linear"]
+    assert type(net.layers[3][0].add.add).__name__ == "QFunctional" and type(net.quant).__name__ == "Quantize"
+    np.testing.assert_allclose(net.quant.scale, g["quant_qp"][0], rtol=1e-5)
+    for n in q_names:                                    # BN folded into (mu, sigma) before quantisation, like the reference
+        np.testing.assert_allclose(mods[n].mu_qp[0], g[n + ".mu_qp"][0], rtol=5e-4)
+        np.testing.assert_allclose(mods[n].sigma_qp[0], g[n + ".sigma_qp"][0], rtol=5e-4)
+        assert (mods[n].weight.cpu().numpy() == g[n + ".mu_q"]).mean() > 0.97, n
+    with torch.no_grad(), noise.inject([torch.as_tensor(g[n + ".eps"]).cuda() for n in q_names]):
+        yq = net(x)
+    assert yq.shape == (8, 10) and torch.isfinite(yq).all()
+    assert float((yq.cpu() - torch.as_tensor(g["y"])).abs().max()) < 0.1
+
+
+def test_resnet_int8_network_bit_exact_with_reference_state(golden):
+    """The whole converted network — quantise, stem conv, identity block, stride-2 block with its 1x1 shortcut, quantised
+    ReLU / residual add / average pool, linear, dequantise — loaded with the reference's int8 state and replayed noise:
+    every intermediate integer map equals the reference's FBGEMM forward."""
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import noise, quant_utils as qu, zoo
+    g = golden("tiny_resnet_int8")
+    args = zoo.Args(sigma_prior=0.1, model="conv_resnet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    net = _tiny_resnet(args).eval()
+    net.fuse_model()                                     # eval-mode fusion: BN slots -> Identity
+    q_names = [str(n) for n in g["q_names"]]
+    for n in q_names:
+        _set_module(net, n, _int8_module(g, n, args))
+    for blk in ("layers.3.0", "layers.3.1"):
+        s, z = g[blk + ".add.y_qp"]
+        _set_module(net, blk + ".add.add", qu.QFunctional(float(s), int(z)))
+    net.quant, net.dequant = qu.Quantize(float(g["quant_qp"][0]), int(g["quant_qp"][1])), qu.DeQuantize()
+    net = net.cuda()
+    mods, seen = dict(net.named_modules()), {}
+    watch = [str(n) for n in g["order"] if str(n) != "layers.4"]
+    hooks = [mods[n].register_forward_hook(lambda m, i, o, n=n: seen.__setitem__(n, (i, o))) for n in watch]
+    with torch.no_grad(), noise.inject([torch.as_tensor(g[n + ".eps"]).cuda() for n in q_names]):
+        y = net(torch.as_tensor(g["x"]).cuda())
+    for h in hooks:
+        h.remove()
+    for n in watch:
+        out = seen[n][1]
+        assert np.array_equal(out.q.cpu().numpy().reshape(g[n + ".y_q"].shape), g[n + ".y_q"]), n
+        assert abs(out.scale - g[n + ".y_qp"][0]) < 1e-12 and out.zero_point == int(g[n + ".y_qp"][1]), n
+    pooled = seen["layers.6"][0][0]                       # AvgPool2d(4) + Flatten feed the classifier
+    assert np.array_equal(pooled.q.cpu().numpy(), g["layers.6.x_q"])
+    assert np.array_equal(pooled.q.cpu().numpy().reshape(8, 16, 1, 1), g["layers.4.y_q"])
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-5, atol=1e-7)
