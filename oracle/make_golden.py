@@ -581,6 +581,11 @@ def gen_resnet_int8(src):
     arrays["q_names"] = np.array(q_names)
     arrays["y"] = npy(yq)
     save("tiny_resnet_int8", **arrays)
+    # the checkpoint the reference itself writes for this model (postprocess_model -> utils.save_model: torch.save of the
+    # converted state-dict, quant_utils.py:101-110): int8 tensors as torch per-tensor-affine qint8, qparams as 0-d tensors
+    path = os.path.join(GOLD, "tiny_resnet_int8_weights.pt")
+    torch.save(net.state_dict(), path)
+    print("wrote %-28s %7.1f KB" % (os.path.basename(path), os.path.getsize(path) / 1024))
 
 
 

@@ -152,6 +152,17 @@ class Quantize(nn.Module):
         s, z = mod.activation_post_process.calculate_qparams()
         return cls(float(s), int(z))
 
+    # nnq.Quantize keeps (scale, zero_point) as [1] buffers: same checkpoint keys
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        destination[prefix + 'scale'] = torch.tensor([self.scale])
+        destination[prefix + 'zero_point'] = torch.tensor([self.zero_point])
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        self.scale = float(state_dict.pop(prefix + 'scale').reshape(-1)[0])
+        self.zero_point = int(state_dict.pop(prefix + 'zero_point').reshape(-1)[0])
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, False, missing_keys, unexpected_keys, error_msgs)
+
 
 class DeQuantize(nn.Module):
     def forward(self, x):
@@ -187,6 +198,17 @@ class QFunctional(nn.Module):
     def from_float(cls, mod):
         s, z = mod.activation_post_process.calculate_qparams()
         return cls(float(s), int(z))
+
+    # checkpoint keys of nnq.QFunctional: `<prefix>scale`, `<prefix>zero_point` as 0-d tensors
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        destination[prefix + 'scale'] = torch.tensor(self.scale)
+        destination[prefix + 'zero_point'] = torch.tensor(self.zero_point)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        self.scale = float(state_dict.pop(prefix + 'scale'))
+        self.zero_point = int(state_dict.pop(prefix + 'zero_point'))
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, False, missing_keys, unexpected_keys, error_msgs)
 
 
 def qconfig_for(args):
@@ -263,6 +285,22 @@ def _with_observer(mod, qconfig):
         inner.activation_post_process = qconfig.activation()
     mod.qconfig = qconfig
     return mod
+
+
+def load_model(model, model_path, replace=True):
+    """src/utils.py:112-123: load a checkpoint written by the reference (`weights*.pt`, float or converted int8) into
+    `model`, keeping only the keys the model has; `model_path` may also be an already loaded state-dict.  For an int8
+    checkpoint build the skeleton the way the reference does — prepare_model(model, args); model.cuda(); convert(model) —
+    then call this; int8 tensors and every quantisation parameter come from the file."""
+    state_dict = model_path if isinstance(model_path, dict) else torch.load(model_path, map_location=torch.device('cpu'))
+    own = model.state_dict()
+    for key, value in state_dict.items():
+        if replace:
+            key = key.replace('module.', '').replace('main_net.', '')
+        if key in own:
+            own[key] = value
+    model.load_state_dict(own)
+    return model
 
 
 def postprocess_model(model, args, q=None, at=None, special_info=""):

@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .... import noise, ops
-from ....quant_utils import INT_BOUNDS, QTensor
+from ....quant_utils import INT_BOUNDS, QFunctional, QTensor
 from . import NOISE_SCALE, NOISE_ZERO_POINT
 
 
@@ -35,7 +35,26 @@ class _I8Base(nn.Module):
         self.scale, self.zero_point = 1.0, 0
         self.bias_ = None
         self.std_prior = torch.nn.Parameter(torch.ones((1,)), requires_grad=False)
+        # the two QFunctionals of the reference module (linear_q.py:30-31, conv_q.py:62-63): they hold the output
+        # qparams of sigma_q*eps_q and of mu_q + (.), and give the checkpoint its `add_weight.*` / `mul_noise.*` keys
+        self.add_weight, self.mul_noise = QFunctional(), QFunctional()
         self._qbn_layer_id = noise.new_layer_id()
+
+    @property
+    def mul_qp(self):
+        return (self.mul_noise.scale, self.mul_noise.zero_point)
+
+    @mul_qp.setter
+    def mul_qp(self, qp):
+        self.mul_noise.scale, self.mul_noise.zero_point = float(qp[0]), int(qp[1])
+
+    @property
+    def add_qp(self):
+        return (self.add_weight.scale, self.add_weight.zero_point)
+
+    @add_qp.setter
+    def add_qp(self, qp):
+        self.add_weight.scale, self.add_weight.zero_point = float(qp[0]), int(qp[1])
 
     def bias(self):
         return self.bias_
@@ -76,7 +95,8 @@ class _I8Base(nn.Module):
         s = state_dict.pop(prefix + 'std')
         self.weight, self.mu_qp = w.int_repr().to(dev), (float(w.q_scale()), int(w.q_zero_point()))
         self.std, self.sigma_qp = s.int_repr().to(dev), (float(s.q_scale()), int(s.q_zero_point()))
-        self.bias_ = state_dict.pop(prefix + 'bias_')
+        b = state_dict.pop(prefix + 'bias_')
+        self.bias_ = None if b is None else b.detach().to(device=dev, dtype=torch.float32).contiguous()
         super()._load_from_state_dict(state_dict, prefix, local_metadata, False, missing_keys, unexpected_keys, error_msgs)
 
 

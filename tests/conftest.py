@@ -35,3 +35,10 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    import pathlib
+    return pathlib.Path(GOLDEN)
+

@@ -254,7 +254,13 @@ def test_resnet_int8_network_bit_exact_with_reference_state(golden):
         s, z = g[blk + ".add.y_qp"]
         _set_module(net, blk + ".add.add", qu.QFunctional(float(s), int(z)))
     net.quant, net.dequant = qu.Quantize(float(g["quant_qp"][0]), int(g["quant_qp"][1])), qu.DeQuantize()
-    net = net.cuda()
+    _check_int8_forward_bit_exact(net.cuda(), g)
+
+
+def _check_int8_forward_bit_exact(net, g):
+    """Replay the fixture's noise through the converted net and compare every captured integer map with the reference's."""
+    from qbn_b200 import noise
+    q_names = [str(n) for n in g["q_names"]]
     mods, seen = dict(net.named_modules()), {}
     watch = [str(n) for n in g["order"] if str(n) != "layers.4"]
     hooks = [mods[n].register_forward_hook(lambda m, i, o, n=n: seen.__setitem__(n, (i, o))) for n in watch]
@@ -270,3 +276,21 @@ def test_resnet_int8_network_bit_exact_with_reference_state(golden):
     assert np.array_equal(pooled.q.cpu().numpy(), g["layers.6.x_q"])
     assert np.array_equal(pooled.q.cpu().numpy().reshape(8, 16, 1, 1), g["layers.4.y_q"])
     np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-5, atol=1e-7)
+
+
+def test_reference_int8_checkpoint_runs_bit_exact(golden, golden_dir):
+    """the checkpoint the reference writes after convert (`weights.pt`: qint8 tensors + qparams) loaded the
+    way the reference's evaluation scripts do — fresh model -> prepare_model -> convert -> load_model
+    (experiments/utils.py:153-158) — runs on the CUDA int8 path and reproduces the reference's integers."""
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import quant_utils as qu, zoo
+    g = golden("tiny_resnet_int8")
+    args = zoo.Args(sigma_prior=0.1, model="conv_resnet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    net = _tiny_resnet(args)
+    qu.prepare_model(net, args)
+    qu.convert(net.cuda())                                # un-calibrated skeleton; every number comes from the file
+    qu.load_model(net, str(golden_dir / "tiny_resnet_int8_weights.pt"))
+    net.eval()
+    assert set(net.state_dict().keys()) == set(torch.load(golden_dir / "tiny_resnet_int8_weights.pt", map_location="cpu").keys())
+    _check_int8_forward_bit_exact(net, g)

@@ -4,6 +4,7 @@ freeze/update API.  The reference behaviour each check follows is cited inline."
 import copy
 import pickle
 
+import numpy as np
 import pytest
 import torch
 import torch.nn as nn
@@ -161,3 +162,60 @@ def test_bernoulli_dropout_state_and_identity():
     x = torch.randn(4, 3)
     assert BernoulliDropout(0.0).eval()(x) is x
     assert "p=0.25" in repr(d)
+
+
+# ---- int8 checkpoint format: the reference's converted state-dict loads into the drop-in skeleton --------
+def _int8_skeleton_cpu(g, args):
+    """The converted tiny ResNet with empty int8 modules on the CPU (state-dict plumbing only — no kernel runs here)."""
+    from test_gpu_quant_lifecycle import _set_module, _tiny_resnet
+    from qbn_b200.stochastic.bbb.quantized import conv_q, linear_q
+    net = _tiny_resnet(args).eval()
+    net.fuse_model()
+    for n in [str(v) for v in g["q_names"]]:
+        old = net.get_submodule(n)
+        old = old[0] if isinstance(old, nn.Sequential) else old
+        relu = bool(g[n + ".relu"])
+        if hasattr(old, "in_channels"):
+            cls = conv_q.ConvReLU2d if relu else conv_q.Conv2d
+            new = cls(old.in_channels, old.out_channels, old.kernel_size, old.stride, old.padding, old.dilation, bias=True, args=args, device="cpu")
+        else:
+            new = (linear_q.LinearReLU if relu else linear_q.Linear)(old.in_features, old.out_features, args=args, device="cpu")
+        _set_module(net, n, new)
+    for blk in ("layers.3.0", "layers.3.1"):
+        _set_module(net, blk + ".add.add", qu.QFunctional())
+    net.quant, net.dequant = qu.Quantize(1.0, 0), qu.DeQuantize()
+    return net
+
+
+def test_reference_int8_checkpoint_loads_into_the_skeleton(golden, golden_dir):
+    g = golden("tiny_resnet_int8")
+    path = golden_dir / "tiny_resnet_int8_weights.pt"
+    ref_sd = torch.load(path, map_location="cpu")
+    net = _int8_skeleton_cpu(g, _args())
+    assert set(net.state_dict().keys()) == set(ref_sd.keys())          # identical key set, incl. add_weight.* / mul_noise.*
+    qu.load_model(net, str(path))
+    mods = dict(net.named_modules())
+    for n in [str(v) for v in g["q_names"]]:
+        m = mods[n]
+        assert m.weight.dtype == torch.int8 and np.array_equal(m.weight.numpy(), g[n + ".mu_q"])
+        assert np.array_equal(m.std.numpy(), g[n + ".sigma_q"])
+        for attr in ("mu_qp", "sigma_qp", "mul_qp", "add_qp"):
+            want = g["%s.%s" % (n, attr)]
+            assert getattr(m, attr) == (float(want[0]), int(want[1])), (n, attr)
+        assert (m.scale, m.zero_point) == (float(g[n + ".out_qp"][0]), int(g[n + ".out_qp"][1]))
+        bias = g[n + ".bias"]
+        assert (m.bias() is None) if bias.size == 0 else np.array_equal(m.bias().numpy(), bias)
+    for blk in ("layers.3.0", "layers.3.1"):
+        f = mods[blk + ".add.add"]
+        assert (f.scale, f.zero_point) == (float(g[blk + ".add.y_qp"][0]), int(g[blk + ".add.y_qp"][1]))
+    assert (net.quant.scale, net.quant.zero_point) == (float(g["quant_qp"][0]), int(g["quant_qp"][1]))
+    # and back: what the drop-in saves is what the reference saved (values and dtypes)
+    out = net.state_dict()
+    for k, v in ref_sd.items():
+        if v is None:
+            assert out[k] is None
+        elif v.is_quantized:
+            assert out[k].is_quantized and torch.equal(out[k].int_repr(), v.int_repr()), k
+            assert out[k].q_scale() == v.q_scale() and out[k].q_zero_point() == v.q_zero_point(), k
+        else:
+            assert out[k].dtype == v.dtype and out[k].shape == v.shape and torch.equal(out[k].detach(), v.detach()), k
