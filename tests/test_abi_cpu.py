@@ -74,3 +74,28 @@ def test_product_never_imports_the_oracle():
         imports = [a.name for n in ast.walk(fn) if isinstance(n, ast.Import) for a in n.names]
         if any(i.startswith("oracle") for i in imports):
             assert "cpu" in fn.name.lower() or "reference" in fn.name.lower(), fn.name
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    """Error behaviour of the boundary (include/qbn.h:8-12): invalid arguments are rejected up front with
+    QBN_ERR_INVALID_ARG and a message naming the function — before any CUDA call, so this runs without a device."""
+    l = lib.load()
+    buf = ctypes.create_string_buffer(64)               # a non-null pointer that is never dereferenced
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    cases = {
+        "qbn_i8_add": lambda: l.qbn_i8_add(p, 0.1, 0, p, 0.1, 0, 0, -1, 0.1, 0, 0, 255, p, None),                  # n == 0
+        "qbn_i8_relu": lambda: l.qbn_i8_relu(p, 16, 0, 200, 100, p, None),                                          # lo > hi
+        "qbn_i8_avgpool": lambda: l.qbn_i8_avgpool(p, 1, 6, 6, 8, 4, 0, 0, 255, p, None),                           # 4 does not divide 6
+        "qbn_quantize_u8": lambda: l.qbn_quantize_u8(p, 16, 0.0, 0, 0, 255, p, None),                               # scale == 0
+        "qbn_dequantize_u8": lambda: l.qbn_dequantize_u8(None, 16, 0.1, 0, p, None),                                # null input
+        "qbn_softmax_accumulate": lambda: l.qbn_softmax_accumulate(p, 4, 8, 129, p, 0, None),                       # K > 128
+        "qbn_cls_metrics": lambda: l.qbn_cls_metrics(p, p, 8, 10, 1.0, 64, p, None),                                # n_bins > 32
+        "qbn_maxpool2x2": lambda: l.qbn_maxpool2x2(p, 1, 1, 8, 4, p, None),                                         # H == 1
+        "qbn_nchw_to_nhwc": lambda: l.qbn_nchw_to_nhwc(p, 70000, 3, 16, p, None),                                   # B > 65535
+        "qbn_avgpool_all": lambda: l.qbn_avgpool_all(p, 0, 16, 8, 0.0, p, None),                                    # B == 0
+    }
+    for name, call in cases.items():
+        assert call() == -1, name
+        msg = l.qbn_last_error()
+        msg = msg.decode() if isinstance(msg, bytes) else msg
+        assert name in msg and "invalid argument" in msg, (name, msg)
