@@ -8,7 +8,7 @@ import contextlib
 
 import torch
 
-_state = {"seed": None, "counter": 0, "queue": None, "next_layer_id": 1, "sample_index": None}
+_state = {"seed": None, "counter": 0, "queue": None, "next_layer_id": 1, "sample_index": None, "sample_batch": None}
 
 
 def manual_seed(seed):
@@ -66,3 +66,25 @@ def sample_index(idx):
         yield
     finally:
         _state["sample_index"] = old
+
+
+@contextlib.contextmanager
+def sample_batch(n_samples, sample0, batch, act_bits=8):
+    """Run `n_samples` Monte-Carlo samples (global indices sample0 .. sample0+n_samples-1) through ONE forward of an int8
+    model: every int8 layer draws n_samples weight tensors (Philox stream_b = global sample index, as under
+    `sample_index`) and contracts all samples in one launch; activations carry the samples in their leading dimension
+    ([n_samples*batch, ...]; a [batch, ...] input is shared by all samples).  `act_bits` is the width the model clamps its
+    activations to (lets the layers pick the tcgen05 kind::i8 kernel, which needs 7-bit inputs)."""
+    if _state["queue"] is not None:
+        raise RuntimeError("noise.sample_batch(): injected noise is per forward, not per sample batch")
+    old = _state["sample_batch"]
+    _state["sample_batch"] = (int(n_samples), int(sample0), int(batch), int(act_bits))
+    try:
+        yield
+    finally:
+        _state["sample_batch"] = old
+
+
+def sample_batch_state():
+    return _state["sample_batch"]
+

@@ -3,7 +3,7 @@
 import torch
 import torch.nn.functional as F
 
-from .... import ops
+from .... import noise, ops
 from ....quant_utils import QTensor
 from ..conv import fuse_conv_bn_weights
 from .conv_qat import ConvBn2d as ConvBn2dQAT
@@ -38,11 +38,20 @@ class Conv2d(_I8Base):
         assert isinstance(x, QTensor), "int8 modules take qbn_b200.quant_utils.QTensor activations"
         if x.q.dim() != 4:
             raise ValueError("Input shape must be `(N, C, H, W)`!")
-        w = self.sampled_weight()                                   # OIHW int8
-        wp = w.permute(0, 2, 3, 1).contiguous().reshape(1, -1)      # packed OHWI
         xq = x.q.contiguous(memory_format=torch.channels_last)
         B, C, H, W = xq.shape
         N, _, R, S = self.weight.shape
+        sb = noise.sample_batch_state()
+        if sb is not None:                                          # all samples of an MC chunk in one launch
+            n, s0, batch, bits = sb
+            shared = self._batch_layout(x, n, batch)
+            wp = self.sampled_weights(n, s0).permute(0, 1, 3, 4, 2).contiguous().reshape(n, -1)     # [n][OHWI]
+            d = ops.make_desc(batch, H, W, C, N, R, S, self.stride, self.padding, self.dilation)
+            y = ops.i8_conv_forward(xq, x.scale, x.zero_point, wp, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale,
+                                    self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared)
+            return QTensor(y, self.scale, self.zero_point)
+        w = self.sampled_weight()                                   # OIHW int8
+        wp = w.permute(0, 2, 3, 1).contiguous().reshape(1, -1)      # packed OHWI
         d = ops.make_desc(B, H, W, C, N, R, S, self.stride, self.padding, self.dilation)
         y = ops.i8_conv_forward(xq, x.scale, x.zero_point, wp, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale, self.zero_point,
                                 self.RELU, act_bits=8)

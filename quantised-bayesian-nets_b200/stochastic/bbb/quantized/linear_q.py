@@ -78,6 +78,21 @@ class _I8Base(nn.Module):
                                   eps.float().reshape(1, -1).contiguous() if eps is not None else None, key[0], key[1], key[2])
         return w.reshape(self.weight.shape)
 
+    def sampled_weights(self, n_samples, sample0):
+        """[n_samples, *weight.shape] int8: the draws of global samples sample0.. (same stream as `noise.sample_index(s)`)."""
+        w = ops.i8_sample_weights(self.weight.reshape(-1), self.std.reshape(-1), self._sample_params(), n_samples, None,
+                                  noise.seed(), self._qbn_layer_id, sample0)
+        return w.reshape((n_samples,) + tuple(self.weight.shape))
+
+    @staticmethod
+    def _batch_layout(x, n_samples, batch):
+        """Is the activation shared by the samples ([batch, ...]) or already per sample ([n_samples*batch, ...])?"""
+        rows = x.q.shape[0]
+        if rows != batch and rows != n_samples * batch:
+            raise ValueError("sample-batched forward: leading dimension %d is neither batch (%d) nor n_samples*batch (%d)"
+                             % (rows, batch, n_samples * batch))
+        return rows == batch
+
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         super()._save_to_state_dict(destination, prefix, keep_vars)
         destination[prefix + 'scale'] = torch.tensor(self.scale)
@@ -122,8 +137,17 @@ class Linear(_I8Base):
 
     def forward(self, x):
         assert isinstance(x, QTensor), "int8 modules take qbn_b200.quant_utils.QTensor activations"
-        w = self.sampled_weight()
         xq = x.q.reshape(x.q.shape[0], -1).contiguous()
+        sb = noise.sample_batch_state()
+        if sb is not None:                                          # all samples of an MC chunk in one launch
+            n, s0, batch, bits = sb
+            shared = self._batch_layout(x, n, batch)
+            w = self.sampled_weights(n, s0).reshape(n, -1)
+            d = ops.make_desc(batch, 1, 1, self.in_features, self.out_features, 1, 1)
+            y = ops.i8_conv_forward(xq, x.scale, x.zero_point, w, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale,
+                                    self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared, linear=True)
+            return QTensor(y.reshape(-1, self.out_features), self.scale, self.zero_point)
+        w = self.sampled_weight()
         d = ops.make_desc(xq.shape[0], 1, 1, self.in_features, self.out_features, 1, 1)
         y = ops.i8_conv_forward(xq, x.scale, x.zero_point, w.reshape(1, -1), self.add_qp[0], self.add_qp[1], d, self.bias(),
                                 self.scale, self.zero_point, self.RELU, act_bits=8, linear=True)

@@ -294,3 +294,44 @@ def test_reference_int8_checkpoint_runs_bit_exact(golden, golden_dir):
     net.eval()
     assert set(net.state_dict().keys()) == set(torch.load(golden_dir / "tiny_resnet_int8_weights.pt", map_location="cpu").keys())
     _check_int8_forward_bit_exact(net, g)
+
+
+def _converted_tiny_resnet(golden, golden_dir):
+    from qbn_b200 import quant_utils as qu, zoo
+    args = zoo.Args(sigma_prior=0.1, model="conv_resnet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    net = _tiny_resnet(args)
+    qu.prepare_model(net, args)
+    qu.convert(net.cuda())
+    qu.load_model(net, str(golden_dir / "tiny_resnet_int8_weights.pt"))
+    return net.eval()
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_int8_sample_batched_engine_equals_the_per_sample_loop(golden, golden_dir, tensor_cores):
+    """All MC samples of a chunk in one forward (Int8MCEngine) == the reference's loop of single forwards with the same
+    per-sample Philox streams, bit for bit; independent of the chunk size and of the first sample index (sharding)."""
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import noise
+    from qbn_b200.mc_int8 import Int8MCEngine
+    g = golden("tiny_resnet_int8")
+    net = _converted_tiny_resnet(golden, golden_dir)
+    x = torch.as_tensor(g["x"]).cuda()
+    noise.manual_seed(77)
+    S = 6
+    with torch.no_grad():
+        loop = []
+        for s in range(S):
+            with noise.sample_index(s):
+                loop.append(net(x))
+    want = torch.stack(loop).sum(0)
+    assert float((loop[0] - loop[1]).abs().max()) > 0            # the samples really differ
+    got = Int8MCEngine(net, chunk=4, tensor_cores=tensor_cores).predict_sum(x, S)
+    assert got.shape == (8, 10)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=2e-6)    # same ints; fp32 sum order only
+    one = Int8MCEngine(net, chunk=1, tensor_cores=tensor_cores)
+    np.testing.assert_allclose(one.predict_sum(x, S).cpu().numpy(), got.cpu().numpy(), rtol=0, atol=2e-6)
+    tail = Int8MCEngine(net, chunk=8, tensor_cores=tensor_cores).predict_sum(x, 2, sample0=4)
+    np.testing.assert_allclose(tail.cpu().numpy(), (loop[4] + loop[5]).cpu().numpy(), rtol=0, atol=2e-6)
+    p = Int8MCEngine(net, tensor_cores=tensor_cores).predict(x, S)
+    np.testing.assert_allclose(p.sum(-1).cpu().numpy(), np.ones(8), atol=1e-5)
