@@ -219,3 +219,41 @@ def test_reference_int8_checkpoint_loads_into_the_skeleton(golden, golden_dir):
             assert out[k].q_scale() == v.q_scale() and out[k].q_zero_point() == v.q_zero_point(), k
         else:
             assert out[k].dtype == v.dtype and out[k].shape == v.shape and torch.equal(out[k].detach(), v.detach()), k
+
+
+def test_sample_batch_context_and_engine_guards():
+    from qbn_b200 import noise
+    from qbn_b200.mc_int8 import Int8MCEngine, balanced_chunks
+    assert noise.sample_batch_state() is None
+    with noise.sample_batch(5, 40, 256, act_bits=7):
+        assert noise.sample_batch_state() == (5, 40, 256, 7)
+        with noise.sample_batch(2, 0, 8):
+            assert noise.sample_batch_state() == (2, 0, 8, 8)
+        assert noise.sample_batch_state() == (5, 40, 256, 7)
+    assert noise.sample_batch_state() is None
+    with noise.inject([torch.zeros(1)]):
+        with pytest.raises(RuntimeError, match="injected noise"):
+            with noise.sample_batch(2, 0, 8):
+                pass
+    # chunks: sizes differ by at most one, never exceed the limit, cover every sample once
+    for total, chunk in ((100, 25), (100, 30), (13, 50), (7, 1), (12, 5)):
+        parts = balanced_chunks(total, chunk)
+        assert sum(parts) == total and max(parts) <= chunk and max(parts) - min(parts) <= 1
+    assert balanced_chunks(0, 4) == []
+    with pytest.raises(ValueError, match="converted model"):
+        Int8MCEngine(nn.Sequential(nn.Linear(4, 4)))
+    from qbn_b200.stochastic.bbb.quantized import linear_q
+    q = nn.Sequential(linear_q.Linear(4, 4, device="cpu"), BernoulliDropout(0.5))
+    with pytest.raises(NotImplementedError, match="MC-Dropout"):
+        Int8MCEngine(q)
+    eng = Int8MCEngine(nn.Sequential(linear_q.Linear(4, 4, device="cpu")))
+    assert eng.act_bits == 8 and not eng.regression                # no args on the model: nothing is assumed about its clamping
+    with pytest.raises(RuntimeError, match="CUDA"):
+        eng.predict_sum(torch.zeros(2, 4), 3)
+    # the layout rule of the sample-batched layers
+    from qbn_b200.quant_utils import QTensor
+    lay = linear_q.Linear._batch_layout
+    assert lay(QTensor(torch.zeros(8, 4, dtype=torch.uint8), 1.0, 0), 3, 8) is True
+    assert lay(QTensor(torch.zeros(24, 4, dtype=torch.uint8), 1.0, 0), 3, 8) is False
+    with pytest.raises(ValueError, match="leading dimension"):
+        lay(QTensor(torch.zeros(16, 4, dtype=torch.uint8), 1.0, 0), 3, 8)
