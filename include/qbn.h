@@ -255,7 +255,10 @@ int qbn_i8_sample_weights(const int8_t* mu_q, const int8_t* sigma_q, int64_t n, 
 /* u8 x s8 -> s32 contraction with FBGEMM's requantisation (A6 step 6):
  * acc = sum (x-z_x)(w-z_w); y = clamp(rint((fp32(acc) + bias/(s_x*s_w)) * (s_x*s_w/s_out)) + z_out,
  * lo, hi), lo = max(z_out if relu else 0, act_min), hi = min(255, act_max) (clamp_activation,
- * src/utils.py:25-30).  acc_dump (nullable, int32 like out) exposes raw accumulators to tests.  */
+ * src/utils.py:25-30).  [act_min, act_max] is the MODEL's activation range (activation_precision): the
+ * caller guarantees that x lies in it too (the reference clamps after every module, models_bbb.py:125-127);
+ * with act_max <= 127 QBN_I8_AUTO picks the tcgen05 kernel, which feeds (x - z_x) as s8.  Pass 255 when
+ * the input range is unknown.  acc_dump (nullable, int32 like out) exposes raw accumulators to tests.  */
 int qbn_i8_conv_fwd(const qbn_conv_desc* d, int n_samples, int x_shared, const uint8_t* x,
                     float s_x, int32_t z_x, const int8_t* w, int w_shared, float s_w, int32_t z_w,
                     const float* bias, float s_out, int32_t z_out, int relu, int act_min,
