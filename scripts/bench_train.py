@@ -2,7 +2,7 @@
 One process per GPU (torchrun) or a single process; B=256 per GPU (weak scaling), Adam lr 1e-3, gamma=.01,
 n_batches=176.  A step = LRT forward, KL, ELBO, backward, NaN scrub, gradient allreduce, Adam.
 Prints one JSON line (secondary metric; the headline bench is bench.py)."""
-import argparse, json, os, sys, time
+import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist

@@ -1,5 +1,5 @@
 """Per-launch timing table of one MC chunk (CUDA events around every libqbn call of the engine)."""
-import os, sys, json
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import __graft_entry__ as ge

@@ -3,7 +3,6 @@ allreduce of probability sums; data-parallel gradient allreduce after the per-re
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

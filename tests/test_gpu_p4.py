@@ -218,7 +218,6 @@ def test_p4_first_layer_sample_stacked():
 def test_p4_multi_layer_sampler():
     """qbn_sample_weights_blocked_multi (all layers of a chunk in one launch, incl. the stacked first layer) is
     bit-identical to the per-layer sampler."""
-    import ctypes
     from qbn_b200 import ops
     from qbn_b200._lib import P4SampleJob
     g = torch.Generator().manual_seed(41)
