@@ -167,13 +167,28 @@ def gen_metrics(src):
 
 
 def gen_losses(src):
+    """src/losses.py: both tasks, both scalings (losses.py:18-29,37-52), forward values and the gradient w.r.t. the output."""
     import src.losses as L
     g = torch.Generator().manual_seed(15)
-    args = Args()
+    args = Args(loss_multiplier=0.5)
     out = torch.softmax(torch.randn(16, 10, generator=g), dim=1)
     tgt = torch.randint(0, 10, (16,), generator=g)
-    loss, ce, kl = L.ClassificationLoss(args, "batch")(out, tgt, torch.tensor(123.4), 0.01, 176, 45000)
-    save("losses", out=npy(out), target=npy(tgt), loss=npy(loss), ce=npy(ce), kl=npy(kl))
+    loss, ce, kl = L.ClassificationLoss(Args(), "batch")(out, tgt, torch.tensor(123.4), 0.01, 176, 45000)
+    arrays = dict(out=npy(out), target=npy(tgt), loss=npy(loss), ce=npy(ce), kl=npy(kl))
+    mean, var = torch.randn(16, 3, generator=g), torch.rand(16, 3, generator=g) + 0.05
+    rtgt = torch.randn(16, 3, generator=g)
+    arrays.update(r_mean=npy(mean), r_var=npy(var), r_target=npy(rtgt))
+    for scaling in ("batch", "whole"):
+        o = out.clone().requires_grad_(True)
+        vals = L.LOSS_FACTORY["classification"](args, scaling)(o, tgt, torch.tensor(123.4), 0.01, 176, 45000)
+        vals[0].backward()
+        arrays["cls_%s" % scaling], arrays["cls_%s_dout" % scaling] = np.array([v.item() for v in vals]), npy(o.grad)
+        m, v = mean.clone().requires_grad_(True), var.clone().requires_grad_(True)
+        vals = L.LOSS_FACTORY["regression"](args, scaling)((m, v), rtgt, torch.tensor(55.5), 0.1, 8, 1000)
+        vals[0].backward()
+        arrays["reg_%s" % scaling] = np.array([x.item() for x in vals])
+        arrays["reg_%s_dmean" % scaling], arrays["reg_%s_dvar" % scaling] = npy(m.grad), npy(v.grad)
+    save("losses", **arrays)
 
 
 def _load_resnet_state(net, P):

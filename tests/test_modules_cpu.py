@@ -257,3 +257,30 @@ def test_sample_batch_context_and_engine_guards():
     assert lay(QTensor(torch.zeros(24, 4, dtype=torch.uint8), 1.0, 0), 3, 8) is False
     with pytest.raises(ValueError, match="leading dimension"):
         lay(QTensor(torch.zeros(16, 4, dtype=torch.uint8), 1.0, 0), 3, 8)
+
+
+def test_losses_match_the_reference(golden):
+    """src/losses.py through the mirror: ELBO value, its two terms and the gradient w.r.t. the model output, for both tasks
+    and both scalings (fixtures from the reference, oracle/make_golden.py:gen_losses)."""
+    from qbn_b200 import losses as L
+    g = golden("losses")
+    args = zoo.Args(loss_multiplier=0.5)
+    out, tgt = torch.as_tensor(g["out"]), torch.as_tensor(g["target"])
+    loss, ce, kl = L.ClassificationLoss(zoo.Args(loss_multiplier=1.0), "batch")(out, tgt, torch.tensor(123.4), 0.01, 176, 45000)
+    for got, key in ((loss, "loss"), (ce, "ce"), (kl, "kl")):
+        torch.testing.assert_close(got, torch.as_tensor(g[key]), rtol=1e-6, atol=1e-7)
+    mean, var, rtgt = (torch.as_tensor(g[k]) for k in ("r_mean", "r_var", "r_target"))
+    for scaling in ("batch", "whole"):
+        o = out.clone().requires_grad_(True)
+        vals = L.LOSS_FACTORY["classification"](args, scaling)(o, tgt, torch.tensor(123.4), 0.01, 176, 45000)
+        vals[0].backward()
+        np.testing.assert_allclose([v.item() for v in vals], g["cls_%s" % scaling], rtol=1e-6)
+        np.testing.assert_allclose(o.grad.numpy(), g["cls_%s_dout" % scaling], rtol=1e-5, atol=1e-7)
+        m, v = mean.clone().requires_grad_(True), var.clone().requires_grad_(True)
+        vals = L.LOSS_FACTORY["regression"](args, scaling)((m, v), rtgt, torch.tensor(55.5), 0.1, 8, 1000)
+        vals[0].backward()
+        np.testing.assert_allclose([v.item() for v in vals], g["reg_%s" % scaling], rtol=1e-5)
+        np.testing.assert_allclose(m.grad.numpy(), g["reg_%s_dmean" % scaling], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(v.grad.numpy(), g["reg_%s_dvar" % scaling], rtol=1e-4, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        L.ClassificationLoss(args, "per-sample")(out, tgt, torch.tensor(1.0), 0.01, 176, 45000)
