@@ -335,3 +335,22 @@ def test_int8_sample_batched_engine_equals_the_per_sample_loop(golden, golden_di
     np.testing.assert_allclose(tail.cpu().numpy(), (loop[4] + loop[5]).cpu().numpy(), rtol=0, atol=2e-6)
     p = Int8MCEngine(net, tensor_cores=tensor_cores).predict(x, S)
     np.testing.assert_allclose(p.sum(-1).cpu().numpy(), np.ones(8), atol=1e-5)
+
+
+def test_int8_engine_full_resnet_tensor_core_and_imad_paths_agree():
+    """Full-size int8 ResNet-18 (24/48/96/192 channels, B=64): lifecycle on the device, then the sample-batched engine on the
+    tcgen05 kind::i8 kernel and on the CUDA-core integer kernel — integer arithmetic is exact, so the class probabilities
+    must be identical, not just close."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "bench_int8.py")
+    spec = importlib.util.spec_from_file_location("bench_int8", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from qbn_b200.mc_int8 import Int8MCEngine
+    net, x, _ = mod.build_model(B=64)
+    fast = Int8MCEngine(net, chunk=3, tensor_cores=True).predict(x, 3)
+    slow = Int8MCEngine(net, chunk=3, tensor_cores=False).predict(x, 3)
+    assert fast.shape == (64, 10) and torch.isfinite(fast).all()
+    assert torch.equal(fast, slow)
+    assert float((fast.sum(-1) - 1).abs().max()) < 1e-5
