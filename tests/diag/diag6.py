@@ -1,5 +1,5 @@
 import sys, os, copy
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "diag2.py")).read().split("y1, g1 = run(False)")[0])
 def run6(cl):
     net = zoo.resnet_from_params(P).cuda()

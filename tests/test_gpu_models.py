@@ -131,7 +131,7 @@ def test_resnet_lrt_training_step(golden, mode, tol):
     # Deeper gradients pass through ReLU masks.  A pre-activation within ~1e-5 of zero flips its mask
     # under ANY fp32 re-association (measured on the B200: torch's own cuDNN twin of this network in
     # channels_last vs NCHW flips exactly one of 12288 masks of layers.6.1 and moves layers.0.weight's
-    # gradient by 1.2e-2 in max-norm, scripts/diag4.py/diag6.py).  So: a small relative L2 error — a
+    # gradient by 1.2e-2 in max-norm, tests/diag/diag4.py, diag6.py).  So: a small relative L2 error — a
     # wrong kernel gives O(1) errors, one flipped mask gives ~1e-2.
     for key in ("layers.0.weight", "layers.0.std", "layers.5.0.shortcut.0.weight", "layers.5.0.shortcut.0.std", "layers.1.weight"):
         got, ref = sd[key].grad.detach().cpu().double(), torch.as_tensor(g["g." + key]).double()
