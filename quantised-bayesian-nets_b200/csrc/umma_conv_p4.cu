@@ -72,6 +72,10 @@ QBN_DEVINL float4 ld_nc4(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// fire-and-forget L2 prefetch on the bulk-copy engine (no smem, no barrier)
+QBN_DEVINL void bulk_prefetch_l2(const void* src_global, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_global), "r"(bytes) : "memory");
+}
 // n / d for n*1 < 2^32 with m = floor(2^32 / d): estimate is exact or one too small
 QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
   q = __umulhi(n, m);
@@ -79,7 +83,12 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
   if (r >= d) { ++q; r -= d; }
 }
 
-template <int DBG_MODE, bool STACKED, bool MASKED>
+// RESP (opt-in, QBN_P4_RESP=1, to be measured): the producer, which runs 2-3 tiles ahead of the epilogue, prefetches the
+// tile's residual rows into L2 (one bulk prefetch per chunk plane: a tile's rows are contiguous inside a plane).  The
+// epilogue's residual ld.global — issued only once the accumulator is ready, its latency exposed once per tile
+// (profiles/r01_p4_stall_reasons.txt) — then hits L2 instead of HBM.  A smem ring for the residual tile does not fit: the
+// operand rings already fill the per-CTA budget at 3 CTAs/SM (layer 1) and 2 CTAs/SM (layer 2).
+template <int DBG_MODE, bool STACKED, bool MASKED, bool RESP = false>
 __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting
@@ -130,6 +139,11 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         const int q0 = (tile - z * p.tiles_per_sample) * TM;
         const float* ws = p.w + (p.w_shared ? 0 : (size_t)z * p.w_sample_floats);
         PROF_BEGIN();
+        if (RESP) {
+          const uint32_t rb = (uint32_t)min(TM, p.Qs - q0) * 16;
+          const float* src = p.residual + ((size_t)z * p.Qs + q0) * 4;
+          for (int ch = 0; ch < p.n_chunks; ++ch) bulk_prefetch_l2(src + (size_t)ch * p.res_plane * 4, rb);
+        }
         if (p.b_res && z != cur_z) {
           mbar_wait(smem_u32(&b_empty[0]), pb ^ 1);          // MMAs of the previous sample have retired
           const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * p.taps) + p.bt2_bytes * (uint32_t)p.n_cb2;
@@ -639,8 +653,12 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (p.tmem_cols > 512) { p.ACC = 512 / p.n_pad; p.tmem_cols = 512; }
     while (p.tmem_cols * want_occ > 512) --want_occ;
   }
+  const char* e_resp = getenv("QBN_P4_RESP");
+  const bool resp = residual && !stacked && e_resp && atoi(e_resp) > 0;
   static bool attr_set = false;
   if (!attr_set) {
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -662,6 +680,12 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   if (!masked && (p.flags & QBN_FLAG_RELU_PRE)) {
     if (residual) masked = true;                                  // ReLU before the residual add: general order
     else p.flags = (p.flags & ~QBN_FLAG_RELU_PRE) | QBN_FLAG_RELU;  // no mask, no residual: pre == post
+  }
+  if (resp) {
+    if (masked) umma_conv_p4_kernel<0, false, true, true><<<grid, P4_THREADS, smem, st>>>(p);
+    else umma_conv_p4_kernel<0, false, false, true><<<grid, P4_THREADS, smem, st>>>(p);
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
   }
   if (stacked || masked) {
     if (stacked && masked) umma_conv_p4_kernel<0, true, true><<<grid, P4_THREADS, smem, st>>>(p);
