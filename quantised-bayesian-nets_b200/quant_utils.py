@@ -12,7 +12,7 @@ import copy
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import noise, ops
 
 UINT_BOUNDS = {8: [0, 255], 7: [0, 127], 6: [0, 63], 5: [0, 31], 4: [0, 15], 3: [0, 7], 2: [0, 3]}            # src/utils.py:18
 INT_BOUNDS = {8: [-128, 127], 7: [-64, 63], 6: [-32, 31], 5: [-16, 15], 4: [-8, 7], 3: [-4, 3], 2: [-2, 1]}  # src/utils.py:19-20
@@ -102,8 +102,10 @@ class FakeQuantize(nn.Module):
 class QTensor:
     """Per-tensor-affine quint8 activation on the GPU: `q` uint8 (NCHW-logical, NHWC-dense, or [B,K])."""
 
-    def __init__(self, q, scale, zero_point):
-        self.q, self.scale, self.zero_point = q, float(scale), int(zero_point)
+    def __init__(self, q, scale, zero_point, bits=8):
+        # `bits`: the integers are known to lie in [0, 2^bits - 1] (the producing kernel clamped them); lets
+        # clamp_activation skip a full pass over the tensor when the producer already applied the model's activation width
+        self.q, self.scale, self.zero_point, self.bits = q, float(scale), int(zero_point), int(bits)
 
     @property
     def shape(self):
@@ -127,10 +129,12 @@ class QTensor:
     def clamp_activation(self, args):
         """src/utils.py:25-30: integer clamp to [0, 2^a - 1] (qparams unchanged)."""
         lo, hi = UINT_BOUNDS[args.activation_precision]
-        return QTensor(torch.clamp(self.q, lo, hi), self.scale, self.zero_point)
+        if self.bits <= args.activation_precision:          # already inside [0, 2^a - 1]: the clamp is the identity
+            return self
+        return QTensor(torch.clamp(self.q, lo, hi), self.scale, self.zero_point, args.activation_precision)
 
     def reshape(self, *shape):
-        return QTensor(self.q.reshape(*shape), self.scale, self.zero_point)
+        return QTensor(self.q.reshape(*shape), self.scale, self.zero_point, self.bits)
 
     def size(self, i=None):
         return self.q.size() if i is None else self.q.size(i)
@@ -188,8 +192,10 @@ class QFunctional(nn.Module):
         assert x.q.shape == y.q.shape, "residual add: operand shapes differ"
         a = x.q.contiguous(memory_format=torch.channels_last) if x.q.dim() == 4 else x.q.contiguous()
         b = y.q.contiguous(memory_format=torch.channels_last) if y.q.dim() == 4 else y.q.contiguous()
-        q = ops.i8_add(a, x.scale, x.zero_point, b, y.scale, y.zero_point, self.scale, self.zero_point, act_bits=8)
-        return QTensor(q, self.scale, self.zero_point)
+        sb = noise.sample_batch_state()
+        bits = sb[3] if sb is not None else 8               # MC engine: clamp to the model's activation width in the same pass
+        q = ops.i8_add(a, x.scale, x.zero_point, b, y.scale, y.zero_point, self.scale, self.zero_point, act_bits=bits)
+        return QTensor(q, self.scale, self.zero_point, bits)
 
     def extra_repr(self):
         return "scale={}, zero_point={}".format(self.scale, self.zero_point)

@@ -49,7 +49,7 @@ class Conv2d(_I8Base):
             d = ops.make_desc(batch, H, W, C, N, R, S, self.stride, self.padding, self.dilation)
             y = ops.i8_conv_forward(xq, x.scale, x.zero_point, wp, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale,
                                     self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared)
-            return QTensor(y, self.scale, self.zero_point)
+            return QTensor(y, self.scale, self.zero_point, bits)
         w = self.sampled_weight()                                   # OIHW int8
         wp = w.permute(0, 2, 3, 1).contiguous().reshape(1, -1)      # packed OHWI
         d = ops.make_desc(B, H, W, C, N, R, S, self.stride, self.padding, self.dilation)

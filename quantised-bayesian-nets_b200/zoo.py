@@ -50,12 +50,12 @@ def _apply(layer, x, args=None):
     bits = getattr(args, "activation_precision", 8) if args is not None else 8
     if isinstance(layer, nn.MaxPool2d):
         q = F.max_pool2d(x.q.float(), layer.kernel_size, layer.stride).to(torch.uint8).contiguous(memory_format=torch.channels_last)
-        return QTensor(q, x.scale, x.zero_point)
+        return QTensor(q, x.scale, x.zero_point, x.bits)
     if isinstance(layer, nn.ReLU):
-        return QTensor(ops.i8_relu(x.q, x.zero_point, act_bits=bits), x.scale, x.zero_point)
+        return QTensor(ops.i8_relu(x.q, x.zero_point, act_bits=bits), x.scale, x.zero_point, min(bits, x.bits))
     if isinstance(layer, nn.AvgPool2d):
         k = layer.kernel_size if isinstance(layer.kernel_size, int) else layer.kernel_size[0]
-        return QTensor(ops.i8_avgpool(x.q, x.zero_point, k, act_bits=bits), x.scale, x.zero_point)
+        return QTensor(ops.i8_avgpool(x.q, x.zero_point, k, act_bits=bits), x.scale, x.zero_point, min(bits, x.bits))
     return layer(x)
 
 

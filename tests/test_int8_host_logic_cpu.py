@@ -58,3 +58,23 @@ def test_sample_batched_forward_equals_the_per_sample_loop(net, bits):
     assert float((loop[0] - loop[1]).abs().max()) > 0
     for s in range(S):
         assert torch.equal(batched[s * B:(s + 1) * B], loop[s]), s          # same integers -> same probabilities
+
+
+def test_engine_mode_skips_redundant_activation_clamps(net, monkeypatch):
+    """clamp_activation runs after every module (models_bbb.py:172-182); when the producing kernel already clamped to the
+    model's activation width the pass is the identity and is skipped: in engine mode only the quantised input needs one."""
+    m, g = net
+    calls = []
+    real = torch.clamp
+    monkeypatch.setattr(torch, "clamp", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    x = torch.as_tensor(g["x"])
+    noise.manual_seed(9)
+    with torch.no_grad(), noise.sample_batch(2, 0, x.shape[0], act_bits=7):
+        m(x)
+    in_engine = len(calls)
+    calls.clear()
+    with torch.no_grad(), noise.sample_index(0):
+        m(x)
+    per_sample = len(calls)
+    assert in_engine == 1, in_engine                       # the input, quantised to the full uint8 range
+    assert per_sample == 1 + 7 + 2, per_sample             # + one per int8 layer (8-bit outputs) + one per residual add
