@@ -423,10 +423,11 @@ def i8_conv_forward(x_q, s_x, z_x, w_q, s_w, z_w, d, bias, s_out, z_out, relu, a
     return (out, acc) if want_acc else out
 
 
-def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=7, n_vec=-1):
+def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=7, n_vec=-1, relu=False):
+    """quantized::add; relu=True is quantized::add_relu: on quint8 the ReLU is a floor at the output zero point."""
     out = torch.empty_like(a)
-    _lib.call("qbn_i8_add", _ptr(a), float(sa), int(za), _ptr(b), float(sb), int(zb), a.numel(), n_vec, float(so), int(zo), 0,
-              (1 << act_bits) - 1, _ptr(out), _stream())
+    _lib.call("qbn_i8_add", _ptr(a), float(sa), int(za), _ptr(b), float(sb), int(zb), a.numel(), n_vec, float(so), int(zo),
+              max(0, int(zo)) if relu else 0, (1 << act_bits) - 1, _ptr(out), _stream())
     return out
 
 

@@ -187,14 +187,18 @@ class QFunctional(nn.Module):
         self.scale, self.zero_point = float(scale), int(zero_point)
         self.activation_post_process = nn.Identity()
 
-    def add(self, x, y):
+    def add_relu(self, x, y):
+        """quantized::add_relu (torch's QFunctional.add_relu): the ReLU rides the add's output clamp."""
+        return self.add(x, y, relu=True)
+
+    def add(self, x, y, relu=False):
         assert isinstance(x, QTensor) and isinstance(y, QTensor), "QFunctional.add takes two QTensor activations"
         assert x.q.shape == y.q.shape, "residual add: operand shapes differ"
         a = x.q.contiguous(memory_format=torch.channels_last) if x.q.dim() == 4 else x.q.contiguous()
         b = y.q.contiguous(memory_format=torch.channels_last) if y.q.dim() == 4 else y.q.contiguous()
         sb = noise.sample_batch_state()
         bits = sb[3] if sb is not None else 8               # MC engine: clamp to the model's activation width in the same pass
-        q = ops.i8_add(a, x.scale, x.zero_point, b, y.scale, y.zero_point, self.scale, self.zero_point, act_bits=bits)
+        q = ops.i8_add(a, x.scale, x.zero_point, b, y.scale, y.zero_point, self.scale, self.zero_point, act_bits=bits, relu=relu)
         return QTensor(q, self.scale, self.zero_point, bits)
 
     def extra_repr(self):

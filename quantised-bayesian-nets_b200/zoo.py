@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import noise, ops
 from .quant_utils import QTensor
 from .stochastic.bbb.conv import Conv2d, ConvReLU2d, fuse_conv_bn, fuse_conv_bn_relu  # noqa: F401
 from .stochastic.bbb.linear import Linear, LinearReLU  # noqa: F401
@@ -171,6 +171,10 @@ class BasicBlock(nn.Module):
         shortcut = x
         for layer in self.shortcut:
             shortcut = clamp_activation(_apply(layer, shortcut, self.args), self.args)
+        if isinstance(out, QTensor) and noise.sample_batch_state() is not None and hasattr(self.add.add, "add_relu"):
+            # int8 MC engine: residual add, ReLU and the activation clamp in ONE pass (quantized::add_relu floors at the output
+            # zero point, which is what add -> clamp -> ReLU -> clamp computes)
+            return clamp_activation(self.add.add.add_relu(out, shortcut), self.args)
         out = clamp_activation(self.add(out, shortcut), self.args)
         return clamp_activation(_apply(self.end, out, self.args), self.args)
 

@@ -61,10 +61,11 @@ def i8_conv_forward(x_q, s_x, z_x, w_q, s_w, z_w, d, bias, s_out, z_out, relu, a
     return _like_cl(np.concatenate(outs, 0))
 
 
-def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=7, n_vec=-1):
+def i8_add(a, sa, za, b, sb, zb, so, zo, act_bits=7, n_vec=-1, relu=False):
     def mem_order(t):                                           # the kernel walks memory: NHWC for channels_last operands
         return t.permute(0, 2, 3, 1).contiguous().numpy().astype(np.int32) if t.dim() == 4 else t.numpy().astype(np.int32)
-    y = O.i8_add(mem_order(a), sa, za, mem_order(b), sb, zb, so, zo, act_bits=act_bits, n_vec=None if n_vec < 0 else n_vec)
+    y = O.qadd(mem_order(a), sa, za, mem_order(b), sb, zb, so, zo, 0, 255, n_vec=None if n_vec < 0 else n_vec)
+    y = np.clip(y, max(0, int(zo)) if relu else 0, O.UINT_BOUNDS[act_bits][1])      # the kernel's output clamp [lo, hi]; relu: lo = zero point
     return _like_cl(y.transpose(0, 3, 1, 2)) if a.dim() == 4 else torch.as_tensor(y.astype(np.uint8))
 
 

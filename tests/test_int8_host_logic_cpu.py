@@ -67,14 +67,21 @@ def test_engine_mode_skips_redundant_activation_clamps(net, monkeypatch):
     calls = []
     real = torch.clamp
     monkeypatch.setattr(torch, "clamp", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    from qbn_b200 import ops
+    relus, adds = [], []
+    real_relu, real_add = ops.i8_relu, ops.i8_add
+    monkeypatch.setattr(ops, "i8_relu", lambda *a, **k: (relus.append(1), real_relu(*a, **k))[1])
+    monkeypatch.setattr(ops, "i8_add", lambda *a, **k: (adds.append(k.get("relu", False)), real_add(*a, **k))[1])
     x = torch.as_tensor(g["x"])
     noise.manual_seed(9)
     with torch.no_grad(), noise.sample_batch(2, 0, x.shape[0], act_bits=7):
         m(x)
-    in_engine = len(calls)
-    calls.clear()
+    in_engine = (len(calls), len(relus), list(adds))
+    calls.clear(), relus.clear(), adds.clear()
     with torch.no_grad(), noise.sample_index(0):
         m(x)
-    per_sample = len(calls)
-    assert in_engine == 1, in_engine                       # the input, quantised to the full uint8 range
-    assert per_sample == 1 + 7 + 2, per_sample             # + one per int8 layer (8-bit outputs) + one per residual add
+    per_sample = (len(calls), len(relus), list(adds))
+    # engine: one clamp (the input, quantised to the full uint8 range); each block's add + ReLU + clamp is ONE launch
+    assert in_engine == (1, 0, [True, True]), in_engine
+    # module mode keeps the reference's sequence: + a clamp per int8 layer (8-bit outputs) and per add, separate ReLU launches
+    assert per_sample == (1 + 7 + 2, 2, [False, False]), per_sample

@@ -117,3 +117,14 @@ def test_fake_quantize_sweep(seed):
         t = torch.as_tensor(x).requires_grad_(True)
         torch.fake_quantize_per_tensor_affine(t, s, z, qmin, qmax).sum().backward()
         assert np.array_equal(mask, t.grad.numpy() != 0)              # straight-through gradient only where not clamped
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_add_relu_is_a_floor_at_the_output_zero_point(seed):
+    """What `ops.i8_add(relu=True)` relies on: quantized::add_relu == quantized::add followed by max(q, zero_point)."""
+    rng = np.random.default_rng(400 + seed)
+    n = 4096
+    a, b = rng.integers(0, 256, n), rng.integers(0, 256, n)
+    (sa, za), (sb, zb), (so, zo) = _qparams(rng, False), _qparams(rng, False), _qparams(rng, False)
+    ref = torch.ops.quantized.add_relu(_qtensor(a, sa, za, False), _qtensor(b, sb, zb, False), so, zo).int_repr().numpy()
+    assert np.array_equal(np.maximum(O.qadd(a, sa, za, b, sb, zb, so, zo, 0, 255), zo), ref)
