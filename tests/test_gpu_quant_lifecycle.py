@@ -354,3 +354,30 @@ def test_int8_engine_full_resnet_tensor_core_and_imad_paths_agree():
     assert fast.shape == (64, 10) and torch.isfinite(fast).all()
     assert torch.equal(fast, slow)
     assert float((fast.sum(-1) - 1).abs().max()) < 1e-5
+
+
+def test_lenet_int8_network_with_reference_state_end_to_end(golden):
+    """The LeNet-shaped converted net (max-pooling between the convolutions, fused Linear+ReLU) loaded with the reference's
+    int8 state and replayed noise reproduces the reference's int8 forward end to end; the sample-batched engine equals the
+    per-sample loop.  (Same checks as tests/test_int8_host_logic_cpu.py, here with the CUDA kernels instead of the stand-ins.)"""
+    import __graft_entry__ as ge
+    ge.build()
+    from qbn_b200 import noise, zoo
+    from qbn_b200.mc_int8 import Int8MCEngine
+    from test_int8_host_logic_cpu import _lenet_int8
+    g = golden("tiny_int8")
+    args = zoo.Args(sigma_prior=0.1, model="conv_lenet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    m = _lenet_int8(g, args, device="cuda").cuda()
+    q_names = [str(n) for n in g["q_names"]]
+    x = torch.as_tensor(g["x"]).cuda()
+    with torch.no_grad(), noise.inject([torch.as_tensor(g[n + ".eps"]).cuda() for n in q_names]):
+        y = m(x)
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-5, atol=1e-7)
+    noise.manual_seed(4)
+    with torch.no_grad():
+        loop = []
+        for s in range(3):
+            with noise.sample_index(s):
+                loop.append(m(x))
+    got = Int8MCEngine(m, chunk=3).predict_sum(x, 3)
+    np.testing.assert_allclose(got.cpu().numpy(), torch.stack(loop).sum(0).cpu().numpy(), rtol=0, atol=2e-6)

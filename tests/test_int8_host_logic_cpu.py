@@ -85,3 +85,48 @@ def test_engine_mode_skips_redundant_activation_clamps(net, monkeypatch):
     assert in_engine == (1, 0, [True, True]), in_engine
     # module mode keeps the reference's sequence: + a clamp per int8 layer (8-bit outputs) and per add, separate ReLU launches
     assert per_sample == (1 + 7 + 2, 2, [False, False]), per_sample
+
+
+# ---- LeNet-shaped net (max-pooling between the convolutions, Linear+ReLU fused): tests/golden/tiny_int8.npz ---------------
+def _lenet_int8(g, args, device="cpu"):
+    from test_gpu_quant_lifecycle import _set_module, _tiny_net
+    from qbn_b200.stochastic.bbb.quantized import conv_q, linear_q
+    m = _tiny_net(args).eval()
+    m.fuse_model()
+    for n in [str(v) for v in g["q_names"]]:
+        mu_q, relu = g[n + ".mu_q"], bool(g[n + ".relu"])
+        if mu_q.ndim == 4:
+            stride, pad = [int(v) for v in g[n + ".conv"]]
+            new = (conv_q.ConvReLU2d if relu else conv_q.Conv2d)(mu_q.shape[1], mu_q.shape[0], mu_q.shape[2:], stride=(stride, stride),
+                                                                  padding=(pad, pad), dilation=(1, 1), args=args, device=device)
+        else:
+            new = (linear_q.LinearReLU if relu else linear_q.Linear)(mu_q.shape[1], mu_q.shape[0], args=args, device=device)
+        new.weight, new.std = torch.as_tensor(mu_q).to(device), torch.as_tensor(g[n + ".sigma_q"]).to(device)
+        for attr in ("mu_qp", "sigma_qp", "mul_qp", "add_qp"):
+            setattr(new, attr, (float(g["%s.%s" % (n, attr)][0]), int(g["%s.%s" % (n, attr)][1])))
+        new.scale, new.zero_point = float(g[n + ".out_qp"][0]), int(g[n + ".out_qp"][1])
+        _set_module(m, n, new)
+    m.quant, m.dequant = qu.Quantize(float(g["quant_qp"][0]), int(g["quant_qp"][1])), qu.DeQuantize()
+    return m
+
+
+def test_lenet_shaped_int8_network_and_its_sample_batching(golden, monkeypatch):
+    emulated_int8_ops(monkeypatch)
+    g = golden("tiny_int8")
+    m = _lenet_int8(g, _args())
+    q_names = [str(n) for n in g["q_names"]]
+    x = torch.as_tensor(g["x"])
+    with torch.no_grad(), noise.inject([torch.as_tensor(g[n + ".eps"]) for n in q_names]):
+        y = m(x)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-5, atol=1e-7)       # the reference's int8 forward, end to end
+    noise.manual_seed(4)
+    S, B = 3, x.shape[0]
+    with torch.no_grad():
+        loop = []
+        for s in range(S):
+            with noise.sample_index(s):
+                loop.append(m(x))
+        with noise.sample_batch(S, 0, B, act_bits=7):
+            batched = m(x)
+    for s in range(S):
+        assert torch.equal(batched[s * B:(s + 1) * B], loop[s]), s
