@@ -214,6 +214,10 @@ int qbn_dropout_fwd(const float* x, int64_t rows /*B*/, int64_t hw, int64_t C, c
  * If d_mu/d_rho are non-NULL they are ACCUMULATED with grad_scale * dKL/d(.).                */
 int qbn_kl_fwd_bwd(const float* mu, const float* rho, int64_t n, float sigma_prior, float* kl_out,
                    float* d_mu, float* d_rho, float grad_scale, void* stream);
+/* utils_bbb.py:3-5 with the reference's own arguments: sigma (not rho), scalar mu_prior and sigma_prior.
+ * kl_out += 0.5*sum(2*log(sp/sigma) - 1 + (sigma/sp)^2 + ((mu_prior-mu)/sp)^2); d_mu / d_sigma accumulated if non-NULL. */
+int qbn_kl_sigma_fwd_bwd(const float* mu, const float* sigma, int64_t n, float mu_prior, float sigma_prior,
+                         float* kl_out, float* d_mu, float* d_sigma, float grad_scale, void* stream);
 
 /* ---- A7: fake quantisation + MovingAverageMinMax observer (linear_qat.py:18-41,
  * conv_qat.py:26-52,139-170; torch/ao/quantization/observer.py:374-410,668-683) -------------
@@ -286,6 +290,11 @@ int qbn_i8_dropout(const uint8_t* x, float s_x, int32_t z_x, int64_t rows, int64
                    const float* mask, float keep_prob, float s_m, int32_t z_m, uint64_t seed,
                    uint32_t stream_a, uint32_t stream_b, int lo, int hi, uint8_t* out,
                    void* stream);
+/* the same for a chunk of Monte-Carlo samples in one launch: x [n_samples][rows_per_sample][hw][C], sample s draws its
+ * mask from Philox(seed, site, sample0 + s) — equal to n_samples calls of qbn_i8_dropout with stream_b = sample0 + s */
+int qbn_i8_dropout_mc(const uint8_t* x, float s_x, int32_t z_x, int n_samples, int64_t rows_per_sample, int64_t hw,
+                      int64_t C, float keep_prob, float s_m, int32_t z_m, uint64_t seed, uint32_t site,
+                      uint32_t sample0, int lo, int hi, uint8_t* out, void* stream);
 
 /* ---- A9: Monte-Carlo aggregation (experiments/utils.py:344-355) ----------------------------
  * logits [n_samples][B][K] -> psum[B][K] (+)= sum_s softmax(logits_s)  (models_bbb.py:131,243)

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "qbn_conv_fwd": (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, c_int, P, P, P, c_int, P, c_float, P, c_int, P]),
     "qbn_dropout_fwd": (c_int, [P, c_int64, c_int64, c_int64, P, c_float, c_float, c_uint64, c_uint32, c_uint32, P, P, P]),
     "qbn_kl_fwd_bwd": (c_int, [P, P, c_int64, c_float, P, P, P, c_float, P]),
+    "qbn_kl_sigma_fwd_bwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P, c_float, P]),
     "qbn_fake_quant_fwd": (c_int, [P, c_int64, P, c_float, c_int, c_int, c_int, P, P, P, P, P, P]),
     "qbn_fake_quant_bwd": (c_int, [P, P, c_int64, P, P]),
     "qbn_quantize_u8": (c_int, [P, c_int64, c_float, c_int32, c_int, c_int, P, P]),
@@ -75,6 +76,8 @@ _SIGNATURES = {
     "qbn_i8_avgpool": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int32, c_int, c_int, P, P]),
     "qbn_i8_dropout": (c_int, [P, c_float, c_int32, c_int64, c_int64, c_int64, P, c_float, c_float, c_int32, c_uint64, c_uint32,
                                c_uint32, c_int, c_int, P, P]),
+    "qbn_i8_dropout_mc": (c_int, [P, c_float, c_int32, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_int32, c_uint64, c_uint32,
+                                  c_uint32, c_int, c_int, P, P]),
     "qbn_softmax_accumulate": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
     "qbn_mc_mean": (c_int, [P, c_int, c_int64, P, P]),
     "qbn_reg_mc_reduce": (c_int, [P, P, c_int, c_int64, P, P, P]),

@@ -376,6 +376,40 @@ extern "C" int qbn_kl_fwd_bwd(const float* mu, const float* rho, int64_t n, floa
   return QBN_OK;
 }
 
+// utils_bbb.py:3-5 with its own argument list: sigma given (not rho), scalar mu_prior / sigma_prior.  The layers call the
+// rho form above; this one serves callers that follow the reference's signature literally.
+__global__ void kl_sigma_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, int64_t n, float mp, float sp,
+                                float* __restrict__ kl_out, float* __restrict__ d_mu, float* __restrict__ d_sigma, float gscale) {
+  double acc = 0.0;
+  const float inv_sp = 1.0f / sp, inv_sp2 = inv_sp * inv_sp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float sg = sigma[i], dm = mp - mu[i];
+    const float a = sg * inv_sp, b = dm * inv_sp;
+    acc += (double)(2.0f * logf(sp / sg) - 1.0f + a * a + b * b);
+    if (d_mu) d_mu[i] += -gscale * dm * inv_sp2;
+    if (d_sigma) d_sigma[i] += gscale * (sg * inv_sp2 - 1.0f / sg);
+  }
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(kl_out, (float)(0.5 * acc));
+  }
+}
+extern "C" int qbn_kl_sigma_fwd_bwd(const float* mu, const float* sigma, int64_t n, float mu_prior, float sigma_prior, float* kl_out,
+                                    float* d_mu, float* d_sigma, float grad_scale, void* stream) {
+  QBN_CHECK_ARG(mu && sigma && kl_out, "null pointer");
+  QBN_CHECK_ARG(n > 0 && sigma_prior > 0.f, "n>0, sigma_prior>0");
+  kl_sigma_kernel<<<qbn_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(mu, sigma, n, mu_prior, sigma_prior, kl_out, d_mu, d_sigma,
+                                                                            grad_scale);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // A7: fused observer (min/max + EMA + qparams) and fake-quantise
 //   workspace: [0] uint32 ticket counter (zero on entry, reset on exit), [16..] float2 partials
@@ -723,12 +757,15 @@ extern "C" int qbn_i8_avgpool(const uint8_t* x, int64_t B, int H, int W, int C, 
 
 __global__ void i8_dropout_kernel(const uint8_t* __restrict__ x, int zx, int64_t rows, int64_t hw, int64_t C,
                                   const float* __restrict__ mask, float keep, float inv_sm, int zm, float mult, uint64_t seed,
-                                  uint32_t sa, uint32_t sb, int lo, int hi, uint8_t* __restrict__ out) {
+                                  uint32_t sa, uint32_t sb, int64_t rows_per_sample, int lo, int hi, uint8_t* __restrict__ out) {
   int64_t total = rows * hw * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t c = i % C;
     int64_t b = i / (hw * C);
-    float m = mask ? mask[b * C + c] : (philox_uniform1(seed, sa, sb, (uint64_t)(b * C + c)) < keep ? 1.0f : 0.0f);
+    // rows_per_sample > 0: the rows are n Monte-Carlo samples x rows_per_sample images; sample s draws stream sb + s
+    const int64_t s_idx = rows_per_sample > 0 ? b / rows_per_sample : 0;
+    const int64_t bl = rows_per_sample > 0 ? b - s_idx * rows_per_sample : b;
+    float m = mask ? mask[b * C + c] : (philox_uniform1(seed, sa, sb + (uint32_t)s_idx, (uint64_t)(bl * C + c)) < keep ? 1.0f : 0.0f);
     int mq = clampi((int)rintf(__fmul_rn(m, inv_sm)) + zm, 0, 255);  // dropout.py:34
     int prod = ((int)x[i] - zx) * (mq - zm);
     int q = (int)rintf(__fmul_rn((float)prod, mult)) + zm;           // quantized::mul, out at (s_m, z_m)
@@ -743,7 +780,20 @@ extern "C" int qbn_i8_dropout(const uint8_t* x, float s_x, int32_t z_x, int64_t 
   QBN_CHECK_ARG(rows > 0 && hw > 0 && C > 0 && s_x > 0 && s_m > 0, "sizes/scales");
   float mult = s_x * s_m * (1.0f / s_m);
   i8_dropout_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, z_x, rows, hw, C, mask, keep_prob,
-                                                                                     1.0f / s_m, z_m, mult, seed, sa, sb, lo, hi, out);
+                                                                                     1.0f / s_m, z_m, mult, seed, sa, sb, 0, lo, hi, out);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+extern "C" int qbn_i8_dropout_mc(const uint8_t* x, float s_x, int32_t z_x, int n_samples, int64_t rows_per_sample, int64_t hw, int64_t C,
+                                 float keep_prob, float s_m, int32_t z_m, uint64_t seed, uint32_t site, uint32_t sample0, int lo, int hi,
+                                 uint8_t* out, void* stream) {
+  QBN_CHECK_ARG(x && out, "x/out");
+  QBN_CHECK_ARG(n_samples > 0 && rows_per_sample > 0 && hw > 0 && C > 0 && s_x > 0 && s_m > 0, "sizes/scales");
+  float mult = s_x * s_m * (1.0f / s_m);
+  const int64_t rows = (int64_t)n_samples * rows_per_sample;
+  i8_dropout_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, z_x, rows, hw, C, nullptr, keep_prob, 1.0f / s_m, z_m,
+                                                                                     mult, seed, site, sample0, rows_per_sample, lo, hi, out);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

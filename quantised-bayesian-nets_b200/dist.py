@@ -28,7 +28,8 @@ def world():
 
 
 class ShardedMCPredictor:
-    """predict(x, S): every rank gets the full batch x; returns the same p-bar on every rank."""
+    """predict(x, S): every rank gets the full batch x; returns the same result on every rank — p-bar [B, K] for
+    classification, (mean, variance) of experiments/utils.py:349-353 for regression."""
 
     def __init__(self, engine):
         self.engine = engine
@@ -36,14 +37,34 @@ class ShardedMCPredictor:
     def predict(self, x, samples):
         rank, ws = world()
         start, count = shard_range(samples, rank, ws)
-        out = self.engine.predict_sum(x, count, sample0=start) if count > 0 else None
         if self.engine.regression:
-            raise NotImplementedError("regression sharding: reduce (sum mu, sum mu^2, sum var) — see reduce_regression()")
-        if out is None:
-            raise RuntimeError("more ranks than samples")
+            # the three running sums of the reference's formula; a rank without samples contributes zeros and still
+            # enters the collective (raising here would leave the other ranks hanging in all_reduce)
+            if count > 0:
+                mu, var = self.engine.predict_sum(x, count, sample0=start)          # [count, B] each
+                sums = (mu.sum(0), (mu * mu).sum(0), var.sum(0))
+            else:
+                z = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
+                sums = (z, z.clone(), z.clone())
+            return reduce_regression(*sums, samples)
+        if count > 0:
+            out = self.engine.predict_sum(x, count, sample0=start)
+        else:
+            out = torch.zeros((x.shape[0], self._n_classes(x)), dtype=torch.float32, device=x.device)
         if ws > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM)
         return out / float(samples)
+
+    def _n_classes(self, x):
+        """Width of the probability rows, for a rank that owns no sample (more ranks than samples)."""
+        k = getattr(self.engine, "n_classes", None)
+        if k is None:
+            model = self.engine.model
+            k = getattr(model, "output_size", None)
+            if k is None:
+                last = [m for m in model.modules() if hasattr(m, "out_features")]
+                k = last[-1].out_features
+        return int(k)
 
 
 def allreduce_prob_sums(psum):

@@ -257,6 +257,34 @@ def kl_divergence(mu, rho, sigma_prior):
     return KLFunction.apply(mu, rho, float(sigma_prior))
 
 
+class KLSigmaFunction(torch.autograd.Function):
+    """utils_bbb.py:3-5 with the reference's argument list (sigma, scalar priors); value and gradient in one pass."""
+
+    @staticmethod
+    def forward(ctx, mu, sigma, mu_prior, sigma_prior):
+        _need_cuda(mu, sigma)
+        mu_c, sg_c = _f32(mu).contiguous(), _f32(sigma).contiguous()
+        kl = torch.zeros((), dtype=torch.float32, device=mu.device)
+        need = mu.requires_grad or sigma.requires_grad
+        d_mu = torch.zeros_like(mu_c) if need else None
+        d_sg = torch.zeros_like(sg_c) if need else None
+        _lib.call("qbn_kl_sigma_fwd_bwd", _ptr(mu_c), _ptr(sg_c), mu_c.numel(), float(mu_prior), float(sigma_prior), _ptr(kl), _ptr(d_mu),
+                  _ptr(d_sg), 1.0, _stream())
+        if need:
+            ctx.save_for_backward(d_mu, d_sg)
+        ctx.shapes = (mu.shape, sigma.shape)
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        d_mu, d_sg = ctx.saved_tensors
+        return (g * d_mu).reshape(ctx.shapes[0]), (g * d_sg).reshape(ctx.shapes[1]), None, None
+
+
+def kl_divergence_sigma(mu, sigma, mu_prior, sigma_prior):
+    return KLSigmaFunction.apply(mu, sigma, float(mu_prior), float(sigma_prior))
+
+
 class KLMultiFunction(torch.autograd.Function):
     """Sum of the closed-form KL over every Bayesian layer of a model (models_bbb.py:254-259) in ONE launch, with all
     gradients produced by the same pass into one flat buffer.  Inputs: sigma priors (host floats), then mu_0, rho_0, mu_1, ..."""
@@ -316,8 +344,9 @@ def kl_divergence_multi(pairs):
 # ------------------------------------------------------------------------------------------------
 # A8 MC-Dropout
 # ------------------------------------------------------------------------------------------------
-def dropout_forward(x, p, mask=None, key=(0, 0, 0)):
-    """dropout.py:15-40 (float branch).  x NCHW-logical/NHWC-dense or [B,C]; mask [B,C] injected or Philox."""
+def dropout_forward(x, p, mask=None, key=(0, 0, 0), return_mask=False):
+    """dropout.py:15-40 (float branch).  x NCHW-logical/NHWC-dense or [B,C]; mask [B,C] injected or Philox.
+    return_mask: also return the [B,C] mask that was applied (the backward multiplies the gradient by it)."""
     _need_cuda(x)
     xc = nhwc(_f32(x))
     if xc.dim() == 4:
@@ -331,7 +360,25 @@ def dropout_forward(x, p, mask=None, key=(0, 0, 0)):
     mask_out = torch.empty((B, C), dtype=torch.float32, device=x.device) if mask is None else None
     _lib.call("qbn_dropout_fwd", _ptr(xc), B, hw, C, _ptr(mask.contiguous() if mask is not None else None), float(1.0 - p), mult,
               key[0], key[1], key[2], _ptr(out), _ptr(mask_out), _stream())
+    if return_mask:
+        return out, (mask_out if mask is None else mask)
     return out
+
+
+class DropoutFunction(torch.autograd.Function):
+    """y = x * mask * 1/(1-p) (dropout.py:35-39); dy/dx = mask * 1/(1-p): the same kernel with the saved mask."""
+
+    @staticmethod
+    def forward(ctx, x, p, mask, key):
+        out, used = dropout_forward(x.detach(), p, mask, key, return_mask=True)
+        ctx.save_for_backward(used)
+        ctx.p = p
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (used,) = ctx.saved_tensors
+        return dropout_forward(g, ctx.p, used), None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -373,6 +420,14 @@ def fake_quantize(x, fq, observe=True):
     return FakeQuantFunction.apply(x, fq, observe)
 
 
+def fake_quant_observe(x, fq):
+    """Observer pass only (min/max EMA + scale/zero_point), no quantisation: FakeQuantize with fake-quant disabled."""
+    _need_cuda(x)
+    xc = _f32(x.detach()).contiguous()
+    _lib.call("qbn_fake_quant_fwd", _ptr(xc), xc.numel(), _ptr(fq.state), fq.c, 1, fq.qmin, fq.qmax, _ptr(fq.scale), _ptr(fq.zero_point),
+              None, None, _ptr(fq.workspace), _stream())
+
+
 # ------------------------------------------------------------------------------------------------
 # A6 int8
 # ------------------------------------------------------------------------------------------------
@@ -406,8 +461,13 @@ def i8_sample_weights(mu_q, sigma_q, params, n_samples=1, eps=None, seed=0, laye
 
 
 def i8_conv_forward(x_q, s_x, z_x, w_q, s_w, z_w, d, bias, s_out, z_out, relu, act_bits=7, n_samples=1, x_shared=True,
-                    w_shared=False, want_acc=False, path=0, linear=False):
-    """x_q uint8 NHWC-dense; w_q int8 [S][N][K] packed.  Returns uint8 NHWC-dense output (+ int32 acc)."""
+                    w_shared=False, want_acc=False, path=0, linear=False, x_bits=8):
+    """x_q uint8 NHWC-dense; w_q int8 [S][N][K] packed.  Returns uint8 NHWC-dense output (+ int32 acc).
+    x_bits: width the INPUT integers are known to fit (QTensor.bits).  The tcgen05 kind::i8 kernel stages (x - z_x) as s8,
+    which only holds for 7-bit inputs; the library's AUTO choice looks at the OUTPUT clamp, so an input that may use the
+    full quint8 range (Quantize output, un-clamped model) is pinned to the exact CUDA-core kernel here."""
+    if path == 0 and int(x_bits) > 7:
+        path = 1        # QBN_I8_IMAD
     lead = n_samples if (n_samples > 1 or not x_shared) else None
     if linear:
         shape = (d.B, d.N) if lead is None else (lead, d.B, d.N)
@@ -458,6 +518,21 @@ def i8_dropout(x_q, s_x, z_x, p, s_m, z_m, mask=None, key=(0, 0, 0), act_bits=7)
     out = torch.empty_like(x_q)
     _lib.call("qbn_i8_dropout", _ptr(x_q), float(s_x), int(z_x), B, hw, C, _ptr(mask), float(1.0 - p), float(s_m), int(z_m),
               key[0], key[1], key[2], 0, (1 << act_bits) - 1, _ptr(out), _stream())
+    return out
+
+
+def i8_dropout_batched(x_q, s_x, z_x, p, s_m, z_m, n_samples, key, act_bits=8):
+    """int8 MC-Dropout of a chunk of samples: x_q [n_samples*B, C(, H, W)], key = (seed, site, sample0)."""
+    if x_q.dim() == 4:
+        rows, C, H, W = x_q.shape
+        hw = H * W
+    else:
+        rows, C = x_q.shape
+        hw = 1
+    assert rows % n_samples == 0
+    out = torch.empty_like(x_q)
+    _lib.call("qbn_i8_dropout_mc", _ptr(x_q), float(s_x), int(z_x), int(n_samples), rows // n_samples, hw, C, float(1.0 - p), float(s_m),
+              int(z_m), key[0], key[1], key[2], 0, (1 << act_bits) - 1, _ptr(out), _stream())
     return out
 
 

@@ -19,7 +19,8 @@ INT_BOUNDS = {8: [-128, 127], 7: [-64, 63], 6: [-32, 31], 5: [-16, 15], 4: [-8, 
 
 
 class _ObserverView(nn.Module):
-    """`fq.activation_post_process.min_val / max_val` like torch's MovingAverageMinMaxObserver."""
+    """`fq.activation_post_process.min_val / max_val / eps` like torch's MovingAverageMinMaxObserver (views of the owner's
+    device-side state; the state-dict keys are written by the owning FakeQuantize)."""
 
     def __init__(self, owner):
         super().__init__()
@@ -33,14 +34,23 @@ class _ObserverView(nn.Module):
     def max_val(self):
         return self._owner.state[1]
 
+    @property
+    def eps(self):
+        return torch.tensor([torch.finfo(torch.float32).eps])
+
     def calculate_qparams(self):
         return self._owner.calculate_qparams()
 
 
-class FakeQuantize(nn.Module):
+class FakeQuantize(torch.ao.quantization.FakeQuantizeBase):
     """y = (clamp(rint(x/s)+z, qmin, qmax) - z) * s with an EMA(min,max; c=0.01) observer
     (torch/ao/quantization/fake_quantize.py:228-260, observer.py:374-410,668-683) in two CUDA
-    kernels; gradients pass where the un-clamped integer is inside [qmin, qmax] (STE)."""
+    kernels; gradients pass where the un-clamped integer is inside [qmin, qmax] (STE).
+
+    A FakeQuantizeBase, so `model.apply(torch.ao.quantization.disable_observer)` and friends reach it, and its state-dict
+    is torch's own key set (`fake_quant_enabled`, `observer_enabled`, `scale`, `zero_point`,
+    `activation_post_process.{eps,min_val,max_val}`): a QAT checkpoint written by the reference restores the trained EMA
+    range here, and the other way round."""
 
     def __init__(self, observer=None, quant_min=0, quant_max=255, dtype=torch.quint8, qscheme=torch.per_tensor_affine,
                  averaging_constant=0.01, **kw):
@@ -49,10 +59,11 @@ class FakeQuantize(nn.Module):
         self.quant_min, self.quant_max = int(quant_min), int(quant_max)
         self.dtype, self.qscheme = dtype, qscheme
         self.averaging_constant = float(averaging_constant)
-        self.register_buffer("state", torch.tensor([float("inf"), float("-inf"), 0.0]))     # min, max, initialised
         self.register_buffer("scale", torch.ones(1))
         self.register_buffer("zero_point", torch.zeros(1, dtype=torch.int32))
-        self._observer_on, self._fq_on = True, True       # host-side switches (no device sync on the hot path)
+        # min, max, initialised — the observer kernel's state; saved as activation_post_process.{min_val,max_val}
+        self.register_buffer("state", torch.tensor([float("inf"), float("-inf"), 0.0]), persistent=False)
+        self._observer_on, self._fq_on = True, True       # host-side mirrors of the two uint8 buffers (no device sync on the hot path)
         self.register_buffer("workspace", torch.zeros(16 + 8 * 1024, dtype=torch.uint8), persistent=False)
         self.activation_post_process = _ObserverView(self)
 
@@ -67,10 +78,12 @@ class FakeQuantize(nn.Module):
 
     def enable_observer(self, enabled=True):
         self._observer_on = bool(enabled)
+        self.observer_enabled[0] = 1 if enabled else 0
         return self
 
     def enable_fake_quant(self, enabled=True):
         self._fq_on = bool(enabled)
+        self.fake_quant_enabled[0] = 1 if enabled else 0
         return self
 
     def disable_fake_quant(self):
@@ -91,8 +104,36 @@ class FakeQuantize(nn.Module):
         if self.state.device != x.device:
             self.to(x.device)
         if not self._fq_on:
+            if self._observer_on:         # torch observes (and refreshes scale / zero_point) even when it does not quantise
+                ops.fake_quant_observe(x, self._fq_state())
             return x
         return ops.fake_quantize(x, self._fq_state(), observe=self._observer_on)
+
+    # ---- torch's FakeQuantize / MovingAverageMinMaxObserver checkpoint keys
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        st = self.state.detach()
+        destination[prefix + "activation_post_process.eps"] = torch.tensor([torch.finfo(torch.float32).eps])
+        destination[prefix + "activation_post_process.min_val"] = st[0].clone()
+        destination[prefix + "activation_post_process.max_val"] = st[1].clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        lo = state_dict.pop(prefix + "activation_post_process.min_val", None)
+        hi = state_dict.pop(prefix + "activation_post_process.max_val", None)
+        state_dict.pop(prefix + "activation_post_process.eps", None)
+        legacy = state_dict.pop(prefix + "state", None)                  # round-1 checkpoints of this package
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        with torch.no_grad():
+            if lo is not None and hi is not None and lo.numel() == 1 and hi.numel() == 1:
+                lo_f, hi_f = float(lo.reshape(-1)[0]), float(hi.reshape(-1)[0])
+                seen = 1.0 if (lo_f != float("inf") and hi_f != float("-inf")) else 0.0
+                self.state.copy_(torch.tensor([lo_f, hi_f, seen]))
+            elif legacy is not None:
+                self.state.copy_(legacy.to(self.state.device))
+            elif strict and lo is None:
+                missing_keys.append(prefix + "activation_post_process.min_val")
+        self._observer_on = bool(int(self.observer_enabled.reshape(-1)[0]))
+        self._fq_on = bool(int(self.fake_quant_enabled.reshape(-1)[0]))
 
     def extra_repr(self):
         return "quant_min=%d, quant_max=%d, dtype=%s" % (self.quant_min, self.quant_max, self.dtype)

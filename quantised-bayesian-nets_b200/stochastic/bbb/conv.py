@@ -6,7 +6,7 @@ from torch.nn import ReLU
 from ... import config, noise, ops
 from ._shared import attach_bayes_state, check_bn_fusable, fold_batchnorm, folded_copy, noise_key, typed_container
 from .linear import eval_forward
-from .utils_bbb import kl_divergence
+from .utils_bbb import kl_divergence_from_rho
 
 
 class Conv2d(nn.Conv2d):
@@ -22,7 +22,7 @@ class Conv2d(nn.Conv2d):
 
     def forward(self, X):
         if not self.training:
-            return eval_forward(self, X.detach(), self.stride, self.padding, self.dilation)      # conv.py:33-39
+            return eval_forward(self, X, self.stride, self.padding, self.dilation)      # conv.py:33-39
         # conv.py:24-32.  NOTE the reference adds a [N] bias to an NCHW tensor without reshaping (conv.py:32), which only
         # broadcasts when Wo == N; every reference model uses bias=False.  Here the bias is added per output channel.
         mode = config.pick_math_mode(self.in_channels, self.out_channels, lrt=True)
@@ -31,7 +31,7 @@ class Conv2d(nn.Conv2d):
 
     def get_kl_divergence(self):
         """conv.py:43-47."""
-        return kl_divergence(self.weight, self.std, None, self.std_prior)
+        return kl_divergence_from_rho(self.weight, self.std, self.std_prior)
 
 
 ConvBn2d = typed_container("ConvBn2d", "Conv2d + BatchNorm2d awaiting QAT / folding (conv.py:49-54).", Conv2d, nn.BatchNorm2d, module=__name__)

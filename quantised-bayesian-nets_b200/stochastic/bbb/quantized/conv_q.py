@@ -48,13 +48,13 @@ class Conv2d(_I8Base):
             wp = self.sampled_weights(n, s0).permute(0, 1, 3, 4, 2).contiguous().reshape(n, -1)     # [n][OHWI]
             d = ops.make_desc(batch, H, W, C, N, R, S, self.stride, self.padding, self.dilation)
             y = ops.i8_conv_forward(xq, x.scale, x.zero_point, wp, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale,
-                                    self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared)
+                                    self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared, x_bits=x.bits)
             return QTensor(y, self.scale, self.zero_point, bits)
         w = self.sampled_weight()                                   # OIHW int8
         wp = w.permute(0, 2, 3, 1).contiguous().reshape(1, -1)      # packed OHWI
         d = ops.make_desc(B, H, W, C, N, R, S, self.stride, self.padding, self.dilation)
         y = ops.i8_conv_forward(xq, x.scale, x.zero_point, wp, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale, self.zero_point,
-                                self.RELU, act_bits=8)
+                                self.RELU, act_bits=8, x_bits=x.bits)
         return QTensor(y, self.scale, self.zero_point)
 
     @classmethod

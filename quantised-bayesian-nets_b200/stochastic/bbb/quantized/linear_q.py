@@ -145,12 +145,12 @@ class Linear(_I8Base):
             w = self.sampled_weights(n, s0).reshape(n, -1)
             d = ops.make_desc(batch, 1, 1, self.in_features, self.out_features, 1, 1)
             y = ops.i8_conv_forward(xq, x.scale, x.zero_point, w, self.add_qp[0], self.add_qp[1], d, self.bias(), self.scale,
-                                    self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared, linear=True)
+                                    self.zero_point, self.RELU, act_bits=bits, n_samples=n, x_shared=shared, linear=True, x_bits=x.bits)
             return QTensor(y.reshape(-1, self.out_features), self.scale, self.zero_point, bits)
         w = self.sampled_weight()
         d = ops.make_desc(xq.shape[0], 1, 1, self.in_features, self.out_features, 1, 1)
         y = ops.i8_conv_forward(xq, x.scale, x.zero_point, w.reshape(1, -1), self.add_qp[0], self.add_qp[1], d, self.bias(),
-                                self.scale, self.zero_point, self.RELU, act_bits=8, linear=True)
+                                self.scale, self.zero_point, self.RELU, act_bits=8, linear=True, x_bits=x.bits)
         return QTensor(y, self.scale, self.zero_point)
 
     @classmethod

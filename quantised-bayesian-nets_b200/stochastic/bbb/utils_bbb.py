@@ -4,13 +4,31 @@ import torch
 from ... import ops
 
 
-def kl_divergence(mu, sigma_or_rho, mu_prior=None, sigma_prior=1.0, from_rho=True):
-    """Closed-form Gaussian KL (utils_bbb.py:3-5) with mu_prior = 0 and a scalar sigma_prior, as
-    every reference call site uses it (linear.py:24-28, conv.py:43-47).  One fused CUDA pass that
-    also produces the gradient (ops.KLFunction); takes rho (sigma = softplus(rho))."""
-    if not from_rho:
-        raise NotImplementedError("kl_divergence takes rho; the reference always passes softplus(self.std)")
-    return ops.kl_divergence(mu, sigma_or_rho, prior_value(sigma_prior))
+def _uniform_value(t, what):
+    """Host value of a prior given the way the reference passes it: a scalar, a 1-element tensor, or a weight-shaped
+    constant tensor (`torch.zeros_like(w)`, `torch.ones_like(w) * std_prior`: linear.py:24-28, conv.py:43-47)."""
+    if not torch.is_tensor(t):
+        return float(t)
+    if t.numel() == 1:
+        return prior_value(t)
+    lo, hi = torch.aminmax(t.detach())
+    lo, hi = float(lo), float(hi)
+    if lo != hi:
+        raise NotImplementedError("kl_divergence: a non-uniform %s tensor is outside the hot path (every reference call site passes a constant)" % what)
+    return lo
+
+
+def kl_divergence(mu, sigma, mu_prior, sigma_prior):
+    """utils_bbb.py:3-5, same arguments and meaning: `sigma` IS the standard deviation (the reference's layers pass
+    softplus(self.std)), `mu_prior` / `sigma_prior` are the prior's mean and standard deviation.  One fused CUDA pass
+    that also produces the gradients w.r.t. mu and sigma.  The drop-in layers call `kl_divergence_from_rho`, which
+    fuses the softplus as well."""
+    return ops.kl_divergence_sigma(mu, sigma, _uniform_value(mu_prior, "mu_prior"), _uniform_value(sigma_prior, "sigma_prior"))
+
+
+def kl_divergence_from_rho(mu, rho, sigma_prior):
+    """KL(N(mu, softplus(rho)^2) || N(0, sigma_prior^2)): what linear.py:24-28 / conv.py:43-47 evaluate, softplus included."""
+    return ops.kl_divergence(mu, rho, prior_value(sigma_prior))
 
 
 def prior_value(sigma_prior):

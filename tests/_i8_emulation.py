@@ -39,7 +39,7 @@ def i8_sample_weights(mu_q, sigma_q, params, n_samples=1, eps=None, seed=0, laye
 
 
 def i8_conv_forward(x_q, s_x, z_x, w_q, s_w, z_w, d, bias, s_out, z_out, relu, act_bits=7, n_samples=1, x_shared=True,
-                    w_shared=False, want_acc=False, path=0, linear=False):
+                    w_shared=False, want_acc=False, path=0, linear=False, x_bits=8):
     assert not want_acc
     b = None if bias is None else bias.detach().cpu().numpy()
     outs = []
