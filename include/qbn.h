@@ -296,6 +296,42 @@ int qbn_i8_dropout_mc(const uint8_t* x, float s_x, int32_t z_x, int n_samples, i
                       int64_t C, float keep_prob, float s_m, int32_t z_m, uint64_t seed, uint32_t site,
                       uint32_t sample0, int lo, int hi, uint8_t* out, void* stream);
 
+/* ---- A6 on the planar zero-copy kernel ("planar C16", csrc/p4_layout.cuh) ---------------------------------------------
+ * Activations: int8 maps holding (q - zero_point) — quint8 activations of at most 7 bits (quant_utils.py:120) — laid out
+ * [C_pad/16 chunk planes][n_img*(H+1)*(W+1) pixels + tail][16], one shared zero row on top / zero column on the left of every
+ * map (the zero IS the zero-point padding of a quint8 convolution), channel count zero-padded to a multiple of 32.  A tensor
+ * feeding a stride-2 conv is stored phase-split like its float twin.  Sampled weights: blocked
+ * [sample][C_pad/CB][tap][CB/16][n_pad][16] with row N = ones over the real channels (accumulator column N = sum_k (x - z_x),
+ * the z_w correction), n_pad = ceil16(N + 1).
+ *
+ * qbn_i8_conv_p16_fwd = conv_q.py:107-125,189-209 step 6 for a chunk of Monte-Carlo samples (x_shared: all samples read the
+ * same input maps) + the glue that follows in models_bbb.py:170-183: clamp_activation, quantized::add with `residual`
+ * (add_relu: the block's final ReLU) — all in the epilogue.  q = clamp(rint((fp32(acc) + bias/(s_x*s_w)) * (s_x*s_w/s_out))
+ * + z_out, relu ? z_out : 0, act_max); with a residual r: clamp(rint((s_out*(q - z_out) + s_res*(r - z_res)) / s_add) + z_add,
+ * add_relu ? z_add : 0, act_max) in ATen's vector-body arithmetic (maps whose element count is a multiple of 64, as every
+ * ResNet map is).  The output map holds q - z_out (or q - z_add).  acc_dump (nullable): [n_samples*B*Hp*Wp][N] accumulators. */
+typedef struct qbn_i8_requant {
+  float s_x, s_w; int32_t z_w; float s_out; int32_t z_out; int32_t relu; int32_t act_max;
+  float s_res; int32_t z_res; float s_add; int32_t z_add; int32_t add_relu;
+} qbn_i8_requant;
+int qbn_i8_conv_p16_fwd(int n_samples, int B, int Hp, int Wp, int C_pad, int N, int R, int S, int stride,
+                        const int8_t* x, long long x_plane_rows, int x_shared, const int8_t* w_blocked, int w_shared,
+                        const float* bias, const qbn_i8_requant* rq, const int8_t* residual, long long res_plane_rows,
+                        int flags /* QBN_FLAG_OUT_PHASE_SPLIT */, int8_t* out, long long out_plane_rows,
+                        int32_t* acc_dump, void* stream);
+int qbn_p16_weight_bytes(int C_pad, int N, int R, int S, int stride, long long* out_bytes);
+/* sampled weights [n_samples][N][C][taps] (the sampler's OIHW order) -> blocked operands of qbn_i8_conv_p16_fwd */
+int qbn_i8_p16_block_weights(const int8_t* w_oihw, int n_samples, int N, int C, int C_pad, int taps, int stride,
+                             int8_t* out, void* stream);
+/* entry / exit of the layout: quint8 NHWC [n_img][H][W][C] <-> planar C16 (border 1), and the global average pool
+ * (nn.AvgPool2d(H), ATen qavg_pool2d rounding) to quint8 [n_img][C] clamped to [lo, hi] */
+int qbn_i8_p16_from_nhwc(const uint8_t* x, int64_t n_img, int H, int W, int C, int C_pad, int32_t z_x,
+                         int64_t plane_rows, int8_t* out, void* stream);
+int qbn_i8_p16_to_nhwc(const int8_t* x, int64_t n_img, int H, int W, int C, int32_t z_x, int64_t plane_rows,
+                       uint8_t* out, void* stream);
+int qbn_i8_p16_avgpool(const int8_t* x, int64_t n_img, int H, int W, int C, int32_t z_x, int64_t plane_rows,
+                       int lo, int hi, uint8_t* out, void* stream);
+
 /* ---- A9: Monte-Carlo aggregation (experiments/utils.py:344-355) ----------------------------
  * logits [n_samples][B][K] -> psum[B][K] (+)= sum_s softmax(logits_s)  (models_bbb.py:131,243)
  * accumulate==0 overwrites.  The caller divides by the GLOBAL S after the allreduce.           */

@@ -39,6 +39,11 @@ class MaskJob(Structure):
     _fields_ = [("out", c_void_p), ("elems", c_int64), ("site_id", c_uint32), ("pad_", c_int32)]
 
 
+class I8Requant(Structure):
+    _fields_ = [("s_x", c_float), ("s_w", c_float), ("z_w", c_int32), ("s_out", c_float), ("z_out", c_int32), ("relu", c_int32),
+                ("act_max", c_int32), ("s_res", c_float), ("z_res", c_int32), ("s_add", c_float), ("z_add", c_int32), ("add_relu", c_int32)]
+
+
 class I8SampleParams(Structure):
     _fields_ = [("s_mu", c_float), ("z_mu", c_int32), ("s_sigma", c_float), ("z_sigma", c_int32),
                 ("s_eps", c_float), ("z_eps", c_int32), ("s_mul", c_float), ("z_mul", c_int32),
@@ -78,6 +83,13 @@ _SIGNATURES = {
                                c_uint32, c_int, c_int, P, P]),
     "qbn_i8_dropout_mc": (c_int, [P, c_float, c_int32, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_int32, c_uint64, c_uint32,
                                   c_uint32, c_int, c_int, P, P]),
+    "qbn_i8_conv_p16_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, ctypes.c_longlong, c_int, P, c_int, P,
+                                    POINTER(I8Requant), P, ctypes.c_longlong, c_int, P, ctypes.c_longlong, P, P]),
+    "qbn_p16_weight_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_longlong)]),
+    "qbn_i8_p16_block_weights": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "qbn_i8_p16_from_nhwc": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int32, c_int64, P, P]),
+    "qbn_i8_p16_to_nhwc": (c_int, [P, c_int64, c_int, c_int, c_int, c_int32, c_int64, P, P]),
+    "qbn_i8_p16_avgpool": (c_int, [P, c_int64, c_int, c_int, c_int, c_int32, c_int64, c_int, c_int, P, P]),
     "qbn_softmax_accumulate": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
     "qbn_mc_mean": (c_int, [P, c_int, c_int64, P, P]),
     "qbn_reg_mc_reduce": (c_int, [P, P, c_int, c_int64, P, P, P]),

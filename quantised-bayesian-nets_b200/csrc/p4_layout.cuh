@@ -29,3 +29,18 @@ static __host__ __device__ inline int qbn_p4_block_channels(int C, int stride = 
   return 0;
 }
 static __host__ __device__ inline int qbn_p4_n_pad(int N) { return (N + 15) / 16 * 16; }
+
+// ---- int8 twin, "planar C16": the same byte layout with 16 s8 channels per 16-byte chunk; maps hold (q - zero_point), so the
+// shared zero border is the padding of a quint8 convolution.  Channel counts are zero-padded to a multiple of 32 (one kind::i8
+// MMA consumes K = 32 = two chunks).  Blocked weights carry one extra output row N of ones over the real input channels: its
+// accumulator column is sum_k (x - z_x), the z_w correction of sum (x - z_x)(w - z_w).
+static __host__ __device__ inline int qbn_p16_block_channels(int C, int stride = 1, int taps = 9) {
+  if (C % 32 != 0) return 0;
+  const int cap = (stride == 2 && taps > 1) ? 96 : 192;      // a stride-2 3x3 conv stages four phase strips per block
+  if (C <= cap) return C;
+  const int cand[4] = {192, 96, 64, 32};
+  for (int i = 0; i < 4; ++i)
+    if (cand[i] <= cap && C % cand[i] == 0) return cand[i];
+  return 0;
+}
+static __host__ __device__ inline int qbn_p16_n_pad(int N) { return (N + 1 + 15) / 16 * 16; }

@@ -35,7 +35,7 @@ struct P4Params {
   int N, n_pad, Qs, tiles_per_sample, total_tiles;
   int cbc, n_cb, n_strips, taps, nk;
   int RA, RA_p, d_before;
-  int SA, SB, TG, b_res, ACC, tmem_cols, flags, w_shared, dbg;
+  int SA, SB, TG, b_res, ACC, tmem_cols, flags, w_shared;
   uint32_t a_bytes, bt_bytes, b_slot_bytes;
   uint32_t idesc, mg_plane, mg_wp;
   long long x_plane, strip_rows, out_plane, res_plane, w_sample_floats;
@@ -48,7 +48,15 @@ struct P4Params {
   // same tile by n_cb2 extra channel blocks of one tap; its weight blocks follow the main ones in every sample's weight tensor
   const float* x2; long long x2_plane; int n_cb2, cbc2, nk2; uint32_t bt2_bytes;
   const float* out_mask; float out_mask_mult;     // A8: MC-Dropout of the OUTPUT, mask [n_img][N] (dropout.py:35-39)
+  int x_shared;                                   // every sample reads the SAME input maps (first layer of the int8 network)
+  // ---- int8 (KIND_I8): operands are (q - zero_point) as s8, 16 channels per 16-byte chunk; FBGEMM requantisation epilogue
+  int z_w, z_out, q_lo, q_hi, n_out_chunks;       // q = clamp(rint((acc - z_w*rowsum + bias/atw) * mult) + z_out, q_lo, q_hi)
+  float atw, mult;
+  int has_add, z_res, z_add, add_lo, add_hi, z_fin;   // quantized::add[_relu] with the residual, then stored as q - z_fin
+  float s_a, p_a, s_b, p_b, inv_s_add;
+  int32_t* acc_dump;                              // optional [rows][N] int32 accumulators (tests)
 };
+enum { KIND_TF32 = 0, KIND_I8 = 1 };
 
 // cycle accounting of CTA 0 (QBN_P4_PROF=1): [role*8 + category], summed over its tiles
 __device__ unsigned long long g_p4_prof[32];
@@ -72,10 +80,6 @@ QBN_DEVINL float4 ld_nc4(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-// fire-and-forget L2 prefetch on the bulk-copy engine (no smem, no barrier)
-QBN_DEVINL void bulk_prefetch_l2(const void* src_global, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_global), "r"(bytes) : "memory");
-}
 // n / d for n*1 < 2^32 with m = floor(2^32 / d): estimate is exact or one too small
 QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
   q = __umulhi(n, m);
@@ -83,16 +87,11 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
   if (r >= d) { ++q; r -= d; }
 }
 
-// RESP (opt-in, QBN_P4_RESP=1, to be measured): the producer, which runs 2-3 tiles ahead of the epilogue, prefetches the
-// tile's residual rows into L2 (one bulk prefetch per chunk plane: a tile's rows are contiguous inside a plane).  The
-// epilogue's residual ld.global — issued only once the accumulator is ready, its latency exposed once per tile
-// (profiles/r01_p4_stall_reasons.txt) — then hits L2 instead of HBM.  A smem ring for the residual tile does not fit: the
-// operand rings already fill the per-CTA budget at 3 CTAs/SM (layer 1) and 2 CTAs/SM (layer 2).
-template <int DBG_MODE, bool STACKED, bool MASKED, bool RESP = false>
+template <int DBG_MODE, bool STACKED, bool MASKED, int KIND = KIND_TF32>
 __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting
-  const int dbg = DBG_MODE == 2 ? p.dbg : 0;              // ablation knobs (QBN_P4_DBG): 1 no stores, 2 one MMA per tile, 4 no A copies, 8 no TMEM loads
+  constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting (QBN_P4_PROF, diagnostics only)
+  constexpr bool I8 = KIND == KIND_I8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + (size_t)p.SA * p.a_bytes;
@@ -108,7 +107,8 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
   float* s_shift = s_scale + 256;
   for (int i = tid; i < 256; i += P4_THREADS) {
     s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
-    s_shift[i] = (p.shift && i < p.N) ? p.shift[i] : 0.f;
+    // int8: the bias enters the accumulator domain exactly like FBGEMM's: fp32(bias) / fp32(s_x * s_w)
+    s_shift[i] = (p.shift && i < p.N) ? (I8 ? __fdiv_rn(p.shift[i], p.atw) : p.shift[i]) : 0.f;
   }
   if (tid == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
@@ -139,11 +139,6 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         const int q0 = (tile - z * p.tiles_per_sample) * TM;
         const float* ws = p.w + (p.w_shared ? 0 : (size_t)z * p.w_sample_floats);
         PROF_BEGIN();
-        if (RESP) {
-          const uint32_t rb = (uint32_t)min(TM, p.Qs - q0) * 16;
-          const float* src = p.residual + ((size_t)z * p.Qs + q0) * 4;
-          for (int ch = 0; ch < p.n_chunks; ++ch) bulk_prefetch_l2(src + (size_t)ch * p.res_plane * 4, rb);
-        }
         if (p.b_res && z != cur_z) {
           mbar_wait(smem_u32(&b_empty[0]), pb ^ 1);          // MMAs of the previous sample have retired
           const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * p.taps) + p.bt2_bytes * (uint32_t)p.n_cb2;
@@ -154,7 +149,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
           cur_z = z;
         }
         // rows [g0, g0 + RA) of every strip, clamped to the tensor (rows outside feed border outputs only)
-        const long long g0 = (long long)z * p.Qs + q0 - p.d_before;
+        const long long g0 = (long long)(p.x_shared ? 0 : z) * p.Qs + q0 - p.d_before;
         const long long lo = g0 < 0 ? 0 : g0;
         const long long lim = p.x_plane - (long long)(p.n_strips - 1) * p.strip_rows;      // rows readable from a strip's start (incl. the zero tail)
         const long long hi = (g0 + p.RA > lim) ? lim : g0 + p.RA;
@@ -165,7 +160,6 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
           mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
           PROF_ADD(17);
           const uint32_t bar = smem_u32(&a_full[sa]);
-          if (dbg & 4) { mbar_arrive(bar); if (++sa == p.SA) { sa = 0; pa ^= 1; } continue; }
           mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(p.cbc * p.n_strips));
           const uint32_t slot = smem_u32(a_ring + (size_t)sa * p.a_bytes) + dst_off;
           for (int s2 = 0; s2 < p.n_strips; ++s2) {
@@ -259,8 +253,8 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
             for (int t = t0; t < t1; ++t) {
               uint32_t ad = a16 + (uint32_t)p.tap_off[t], bd = b16;
 #pragma unroll 1
-              for (int jj = 0; jj < ((dbg & 2) ? (t == 0 && cb == 0 ? 1 : 0) : p.nk); ++jj) {
-                umma_mma<MODE_EVAL>(tacc, adesc_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
+              for (int jj = 0; jj < p.nk; ++jj) {
+                umma_mma<I8 ? MODE_I8 : MODE_EVAL>(tacc, adesc_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
                 accum = 1;
                 ad += a_k; bd += b_k;
               }
@@ -290,7 +284,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
           const uint64_t adesc2_hi = make_smem_desc(0, TM * 16, 128);      // chunk planes of 128 rows, no halo
 #pragma unroll 1
           for (int jj = 0; jj < p.nk2; ++jj) {
-            umma_mma<MODE_EVAL>(tacc, adesc2_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
+            umma_mma<I8 ? MODE_I8 : MODE_EVAL>(tacc, adesc2_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
             accum = 1;
             ad += (2 * TM * 16) >> 4; bd += b_k;
           }
@@ -338,6 +332,82 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         orow = (long long)((h & 1) * 2 + (w & 1)) * p.q2_total + ((long long)(z * p.B + (int)b) * p.Hp2 + (h >> 1) + 1) * p.Wp2 + (w >> 1) + 1;
         store = interior;                                   // its border is never written (pre-zeroed buffer)
       }
+      if constexpr (I8) {
+        // ---- int8: one TMEM column group = 16 output channels = ONE 16-byte chunk of the planar-C16 s8 map.
+        // FBGEMM's ReQuantizeOutput with a float bias (conv_q.py:120-125): every fp32 step rounded separately (no FMA).
+        int8_t* optr8 = reinterpret_cast<int8_t*>(p.out) + (store ? orow : 0) * 16;
+        const int8_t* rptr8 = (p.has_add && interior) ? reinterpret_cast<const int8_t*>(p.residual) + in_row * 16 : nullptr;
+        const long long res_step8 = p.res_plane * 16, out_step8 = p.out_plane * 16;
+        uint32_t v[16], vn[16];
+        uint4 rres = make_uint4(0, 0, 0, 0), rnext = make_uint4(0, 0, 0, 0);
+        auto ld_res = [&](int g) {
+          uint4 r = make_uint4(0, 0, 0, 0);
+          if (rptr8) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(rptr8 + (long long)g * res_step8));
+          return r;
+        };
+        rres = ld_res(0);
+        PROF_ADD(0);
+        warp_wait(&acc_full[as], pacc, lane);
+        PROF_ADD(1);
+        tc_fence_after();
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
+        // column N of the accumulator = sum_k (x - z_x) (an all-ones weight row): the z_w correction of sum (x-z_x)(w-z_w)
+        int corr = 0;
+        if (p.z_w != 0) {
+          tmem_ld16(tlane + (uint32_t)(p.N & ~15), v);
+          tmem_ld_wait();
+          int rowsum = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rowsum = (j == (p.N & 15)) ? (int)v[j] : rowsum;
+          corr = p.z_w * rowsum;
+        }
+        tmem_ld16(tlane, v);
+        const int n_out = p.n_out_chunks;
+        for (int g = 0; g < n_out; ++g) {
+          tmem_ld_wait();
+          if (g + 1 < n_out) {
+            tmem_ld16(tlane + (uint32_t)((g + 1) * 16), vn);
+            rnext = ld_res(g + 1);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+          }
+          PROF_ADD(2);
+          if (store) {
+            uint32_t packed[4] = {0u, 0u, 0u, 0u};
+            if (interior) {
+              const uint32_t rw[4] = {rres.x, rres.y, rres.z, rres.w};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c = g * 16 + j;
+                const int acc = (int)v[j] - corr;
+                if (p.acc_dump && c < p.N) p.acc_dump[in_row * p.N + c] = acc;
+                const float xf = __fadd_rn((float)acc, s_shift[c]);
+                int qv = __float2int_rn(__fmul_rn(xf, p.mult)) + p.z_out;
+                qv = max(p.q_lo, min(p.q_hi, qv));
+                if (p.has_add) {
+                  // quantized::add[_relu] (vector body of ATen's kernel: dequantise with one FMA per operand)
+                  const int rb = (int)(int8_t)((rw[j >> 2] >> ((j & 3) * 8)) & 0xFF) + p.z_res;
+                  const float da = __fmaf_rn(p.s_a, (float)qv, p.p_a);
+                  const float db = __fmaf_rn(p.s_b, (float)rb, p.p_b);
+                  qv = __float2int_rn(__fmul_rn(__fadd_rn(da, db), p.inv_s_add)) + p.z_add;
+                  qv = max(p.add_lo, min(p.add_hi, qv));
+                }
+                const int sv = c < p.N ? qv - p.z_fin : 0;
+                packed[j >> 2] |= ((uint32_t)sv & 0xFFu) << ((j & 3) * 8);
+              }
+            }
+            *reinterpret_cast<uint4*>(optr8 + (long long)g * out_step8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+          if (g + 1 < n_out) {
+            rres = rnext;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = vn[i];
+          }
+          PROF_ADD(3);
+        }
+      } else {
       float* optr = p.out + (store ? orow : 0) * 4;
       // dropout mask row of this pixel's image (stacked: sample sidx of the shared input adds sidx * B images)
       const float* mrow = (MASKED && p.out_mask && interior) ? p.out_mask + (size_t)(z * p.B + (int)b) * p.N : nullptr;
@@ -365,13 +435,13 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
       PROF_ADD(1);
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
-      if (!(dbg & 8)) tmem_ld16(tlane, v);
+      tmem_ld16(tlane, v);
       float* oc = optr;                                      // output pointer of the current chunk
       int jc = 0, sidx = 0;                                  // channel chunk inside the sample / stacked sample
       for (int g = 0; g < n_groups; ++g) {
         tmem_ld_wait();
         if (g + 1 < n_groups) {
-          if (!(dbg & 8)) tmem_ld16(tlane + (uint32_t)((g + 1) * 16), vn);
+          tmem_ld16(tlane + (uint32_t)((g + 1) * 16), vn);
           prefetch(rnext, g + 1);
         } else {                                            // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
@@ -379,7 +449,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
           if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
         }
         PROF_ADD(2);
-        if (store && !(dbg & 1)) {
+        if (store) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int ch = g * 4 + i;
@@ -424,6 +494,7 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
         }
         PROF_ADD(3);
       }
+      }
       if (++as == p.ACC) { as = 0; pacc ^= 1; }
     }
   }
@@ -453,9 +524,17 @@ extern "C" int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long
 }
 
 struct P4Planes { long long x, res, out, x2; };      // rows per chunk plane of each tensor (phases * maps + zero tail)
+struct P4I8 {                                        // int8 extras of a launch (NULL: TF32)
+  int x_shared, z_w, z_out, q_lo, q_hi;
+  float atw, mult;
+  int has_add, z_res, z_add, add_lo, add_hi, z_fin;
+  float s_a, p_a, s_b, p_b, inv_s_add;
+  int32_t* acc_dump;
+};
 static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
                           int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
-                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream);
+                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream,
+                          const P4I8* i8 = nullptr);
 
 extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
                                long long x_plane_rows, const float* w, int w_shared, const float* scale, const float* shift,
@@ -494,14 +573,21 @@ extern "C" int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, in
 
 static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
                           int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
-                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream) {
+                          float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream,
+                          const P4I8* i8) {
   cudaStream_t st = (cudaStream_t)stream;
   QBN_CHECK_ARG(x && w && out, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && Hp > 2 && Wp > 2 && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
-  const int CB = qbn_p4_block_channels(C, stride, R * S);
+  const int E = i8 ? 16 : 4;                       // channels per 16-byte K-chunk
+  const int CB = i8 ? qbn_p16_block_channels(C, stride, R * S) : qbn_p4_block_channels(C, stride, R * S);
   const bool s1 = stride == 1 && (R & 1) && (S & 1);
   const bool s2 = stride == 2 && ((R == 3 && S == 3) || (R == 1 && S == 1));
-  if (C % 8 != 0 || CB == 0 || N % 4 != 0 || N > 256 || !(s1 || s2) || R * S > MAX_TAPS) {
+  if (i8 && (C % 32 != 0 || CB == 0 || N + 1 > 256 || !(s1 || s2) || R * S > MAX_TAPS || x2 || out_mask || (flags & QBN_FLAG_X_SHARED_STACKED))) {
+    qbn_set_error("qbn_i8_conv_p16_fwd: needs C %% 32 == 0 (zero-padded channels), N <= 255 and stride 1 (odd kernel) or stride 2 (3x3 / 1x1) "
+                  "(C=%d N=%d R=%d S=%d stride=%d)", C, N, R, S, stride);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  if (!i8 && (C % 8 != 0 || CB == 0 || N % 4 != 0 || N > 256 || !(s1 || s2) || R * S > MAX_TAPS)) {
     qbn_set_error("qbn_conv_p4_fwd: needs C %% 8 == 0, N %% 4 == 0, N <= 256 and stride 1 (odd kernel) or stride 2 (3x3 / 1x1) "
                   "(C=%d N=%d R=%d S=%d stride=%d)", C, N, R, S, stride);
     return QBN_ERR_UNSUPPORTED;
@@ -518,18 +604,24 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.stacked = stacked ? 1 : 0;
   p.cps = N / 4;
   p.n_chunks = (stacked ? n_samples : 1) * N / 4;
+  if (i8) {
+    p.x_shared = i8->x_shared; p.z_w = i8->z_w; p.z_out = i8->z_out; p.q_lo = i8->q_lo; p.q_hi = i8->q_hi; p.atw = i8->atw; p.mult = i8->mult;
+    p.has_add = i8->has_add; p.z_res = i8->z_res; p.z_add = i8->z_add; p.add_lo = i8->add_lo; p.add_hi = i8->add_hi; p.z_fin = i8->z_fin;
+    p.s_a = i8->s_a; p.p_a = i8->p_a; p.s_b = i8->s_b; p.p_b = i8->p_b; p.inv_s_add = i8->inv_s_add; p.acc_dump = i8->acc_dump;
+    p.n_out_chunks = (N + 15) / 16;
+  }
   p.bh = s1 ? (R - 1) / 2 : 1;
   p.bw = s1 ? (S - 1) / 2 : 1;
   QBN_CHECK_ARG(Hp > p.bh && Wp > p.bw, "padded extent must exceed the border");
   p.Qs = B * Hp * Wp;
   p.tiles_per_sample = (p.Qs + TM - 1) / TM;
   p.total_tiles = p.tiles_per_sample * (stacked ? 1 : n_samples);
-  p.n_pad = qbn_p4_n_pad(stacked ? n_samples * N : N);
+  p.n_pad = i8 ? qbn_p16_n_pad(N) : qbn_p4_n_pad(stacked ? n_samples * N : N);
   p.n_cb = C / CB;
-  p.cbc = CB / 4;
+  p.cbc = CB / E;
   p.nk = p.cbc / 2;
   p.taps = R * S;
-  p.strip_rows = (long long)(stacked ? 1 : n_samples) * p.Qs;
+  p.strip_rows = (long long)((stacked || (i8 && i8->x_shared)) ? 1 : n_samples) * p.Qs;
   int d_after = 0;
   if (s1) {
     p.n_strips = 1;
@@ -561,7 +653,6 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
         sh = 0;
       }
       p.tap_off[r * S + s] = strip * p.cbc * p.RA_p + p.d_before + sh;
-      if (getenv("QBN_P4_ALIGN")) p.tap_off[r * S + s] &= ~7;      // timing experiment only (wrong results): 128-byte aligned operand starts
     }
   p.a_bytes = (uint32_t)p.n_strips * p.cbc * p.RA_p * 16;
   p.bt_bytes = (uint32_t)p.cbc * p.n_pad * 16;
@@ -579,12 +670,13 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.flags = flags; p.w_shared = stacked ? 1 : w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.out_mask = out_mask; p.out_mask_mult = out_mask_mult;
-  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  p.idesc = i8 ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24))      // S32 += S8 x S8
+               : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24));    // F32 += TF32 x TF32
   p.mg_plane = (uint32_t)(0x100000000ull / (uint64_t)(Hp * Wp));
   p.mg_wp = (uint32_t)(0x100000000ull / (uint64_t)Wp);
   p.res_plane = pl.res;
   p.out_plane = pl.out;
-  QBN_CHECK_ARG(!residual || p.res_plane >= p.strip_rows, "residual plane too small");
+  QBN_CHECK_ARG(!residual || p.res_plane >= (long long)n_samples * p.Qs, "residual plane too small");
   if (flags & QBN_FLAG_OUT_PHASE_SPLIT) {
     const int H = Hp - p.bh, W = Wp - p.bw;
     QBN_CHECK_ARG((H % 2 == 0) && (W % 2 == 0), "phase-split output needs even H, W");
@@ -653,18 +745,14 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (p.tmem_cols > 512) { p.ACC = 512 / p.n_pad; p.tmem_cols = 512; }
     while (p.tmem_cols * want_occ > 512) --want_occ;
   }
-  const char* e_resp = getenv("QBN_P4_RESP");
-  const bool resp = residual && !stacked && e_resp && atoi(e_resp) > 0;
   static bool attr_set = false;
   if (!attr_set) {
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false, KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
@@ -681,9 +769,8 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (residual) masked = true;                                  // ReLU before the residual add: general order
     else p.flags = (p.flags & ~QBN_FLAG_RELU_PRE) | QBN_FLAG_RELU;  // no mask, no residual: pre == post
   }
-  if (resp) {
-    if (masked) umma_conv_p4_kernel<0, false, true, true><<<grid, P4_THREADS, smem, st>>>(p);
-    else umma_conv_p4_kernel<0, false, false, true><<<grid, P4_THREADS, smem, st>>>(p);
+  if (i8) {
+    umma_conv_p4_kernel<0, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
@@ -709,13 +796,55 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
             h[11] / t0, h[12] / t0, h[13] / t0, h[16] / t0, h[17] / t0, h[18] / t0, h[19] / t0, h[20] / t0);
     return QBN_OK;
   }
-  if (getenv("QBN_P4_DBG")) {
-    p.dbg = atoi(getenv("QBN_P4_DBG"));
-    umma_conv_p4_kernel<2, false, false><<<grid, P4_THREADS, smem, st>>>(p);
-    QBN_CHECK_LAUNCH();
-    return QBN_OK;
-  }
   umma_conv_p4_kernel<0, false, false><<<grid, P4_THREADS, smem, st>>>(p);
   QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// ---- int8 on the same zero-copy kernel (SURVEY 8a row A6 step 6 + A11 glue): u8 x s8 -> s32 with FBGEMM's requantisation,
+// the BasicBlock's quantized::add_relu and the activation clamp in the epilogue.  Maps hold (q - zero_point) as s8 in the
+// planar-C16 layout (16 channels per 16-byte chunk, channel count zero-padded to a multiple of 32 = one kind::i8 MMA).
+extern "C" int qbn_i8_conv_p16_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const int8_t* x,
+                                   long long x_plane_rows, int x_shared, const int8_t* w_blocked, int w_shared, const float* bias,
+                                   const qbn_i8_requant* rq, const int8_t* residual, long long res_plane_rows, int flags, int8_t* out,
+                                   long long out_plane_rows, int32_t* acc_dump, void* stream) {
+  QBN_CHECK_ARG(rq, "requantisation parameters");
+  QBN_CHECK_ARG(rq->s_x > 0 && rq->s_w > 0 && rq->s_out > 0, "scales must be > 0");
+  QBN_CHECK_ARG(rq->act_max >= 1 && rq->act_max <= 127, "activations must fit 7 bits (quant_utils.py:120): the maps hold q - zero_point as s8");
+  QBN_CHECK_ARG(rq->z_out >= 0 && rq->z_out <= 127 && rq->z_w >= -128 && rq->z_w <= 127, "zero points");
+  P4I8 e;
+  memset(&e, 0, sizeof(e));
+  e.x_shared = x_shared; e.z_w = rq->z_w; e.z_out = rq->z_out;
+  // ATen qconv (fbgemm): act_times_w = s_x * s_w ; multiplier = act_times_w / s_out, all fp32 (same as qbn_i8_conv_fwd)
+  e.atw = rq->s_x * rq->s_w;
+  e.mult = e.atw / rq->s_out;
+  e.q_lo = rq->relu ? rq->z_out : 0;
+  e.q_hi = rq->act_max;
+  e.z_fin = rq->z_out;
+  e.acc_dump = acc_dump;
+  if (residual) {
+    QBN_CHECK_ARG(rq->s_res > 0 && rq->s_add > 0 && rq->z_res >= 0 && rq->z_res <= 127 && rq->z_add >= 0 && rq->z_add <= 127, "residual add parameters");
+    e.has_add = 1; e.z_res = rq->z_res; e.z_add = rq->z_add;
+    e.s_a = rq->s_out; e.p_a = rq->s_out * (float)(-rq->z_out);
+    e.s_b = rq->s_res; e.p_b = rq->s_res * (float)(-rq->z_res);
+    e.inv_s_add = 1.0f / rq->s_add;
+    e.add_lo = rq->add_relu ? rq->z_add : 0;
+    e.add_hi = rq->act_max;
+    e.z_fin = rq->z_add;
+  }
+  P4Planes pl = {x_plane_rows, res_plane_rows, out_plane_rows, 0};
+  return conv_p4_launch(n_samples, B, Hp, Wp, C, N, R, S, stride, reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_blocked),
+                        w_shared, nullptr, bias, reinterpret_cast<const float*>(residual), nullptr, 1.0f, flags & QBN_FLAG_OUT_PHASE_SPLIT,
+                        reinterpret_cast<float*>(out), nullptr, 0, 0, pl, stream, &e);
+}
+
+extern "C" int qbn_p16_weight_bytes(int C, int N, int R, int S, int stride, long long* out_bytes) {
+  QBN_CHECK_ARG(out_bytes && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
+  const int CB = qbn_p16_block_channels(C, stride, R * S);
+  if (C % 32 != 0 || CB == 0 || N + 1 > 256) {
+    qbn_set_error("planar-C16 int8 conv: needs C %% 32 == 0 and N <= 255 (C=%d N=%d)", C, N);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  *out_bytes = (long long)(C / CB) * R * S * (CB / 16) * qbn_p16_n_pad(N) * 16;
   return QBN_OK;
 }

@@ -774,3 +774,114 @@ def avgpool_p4(x, divisor):
     out = torch.empty((x.n_img, x.C), dtype=torch.float32, device=x.buf.device)
     _lib.call("qbn_avgpool_p4", _ptr(x.buf), x.n_img, x.Hp * x.Wp, x.plane_rows, x.C, float(divisor), _ptr(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# int8 on the planar zero-copy kernel ("planar C16", csrc/p4_layout.cuh)
+# ------------------------------------------------------------------------------------------------
+def pad32(c):
+    return (int(c) + 31) // 32 * 32
+
+
+class P16Map:
+    """A batch of quint8 maps (at most 7 bits) stored as (q - zero_point) int8 in the planar-C16 layout:
+    buf [C_pad/16][phases * n_img*Hp*Wp + tail][16], one zero row on top / zero column on the left of every map (border 1),
+    C_pad = channels zero-padded to a multiple of 32.  `scale`, `zero_point`: the per-tensor affine parameters of the quint8
+    tensor it stands for (torch's q_scale / q_zero_point); phases == 4: phase-split storage for a stride-2 consumer."""
+    __slots__ = ("buf", "n_img", "C", "C_pad", "Hp", "Wp", "phases", "scale", "zero_point", "bits")
+
+    def __init__(self, buf, n_img, C, Hp, Wp, phases, scale, zero_point, bits=7):
+        self.buf, self.n_img, self.C, self.C_pad, self.Hp, self.Wp, self.phases = buf, n_img, C, buf.shape[0] * 16, Hp, Wp, phases
+        self.scale, self.zero_point, self.bits = float(scale), int(zero_point), int(bits)
+
+    @property
+    def plane_rows(self):
+        return self.buf.stride(0) // 16
+
+    @staticmethod
+    def empty(n_img, C, Hp, Wp, phases=1, device="cuda", scale=1.0, zero_point=0, bits=7):
+        """Zero-initialised: kernels never write the tail, the padded channel planes, nor the border of a phase-split map."""
+        shape = (pad32(C) // 16, phases * n_img * Hp * Wp + Wp + 1, 16)
+        return P16Map(torch.zeros(shape, dtype=torch.int8, device=device), n_img, C, Hp, Wp, phases, scale, zero_point, bits)
+
+    @staticmethod
+    def from_quint8(q_nhwc, scale, zero_point, bits=7, out=None):
+        """q_nhwc: uint8 [n_img, C, H, W] channels-last (QTensor.q) with values in [0, 2^bits - 1], bits <= 7."""
+        n, C, H, W = q_nhwc.shape
+        if bits > 7:
+            raise _lib.QbnError("the planar int8 path holds q - zero_point as int8: activations must be clamped to <= 7 bits")
+        q = q_nhwc.contiguous(memory_format=CL)
+        m = out if out is not None else P16Map.empty(n, C, H + 1, W + 1, 1, q.device, scale, zero_point, bits)
+        m.scale, m.zero_point, m.bits = float(scale), int(zero_point), int(bits)
+        _lib.call("qbn_i8_p16_from_nhwc", _ptr(q), n, H, W, C, m.C_pad, int(zero_point), m.plane_rows, _ptr(m.buf), _stream())
+        return m
+
+    def to_quint8(self):
+        """uint8 [n_img, C, H, W] channels-last (tests / exit of the layout)."""
+        if self.phases == 4:
+            H2, W2 = self.Hp - 1, self.Wp - 1
+            body = 4 * self.n_img * self.Hp * self.Wp
+            rows = self.buf[:, :body].permute(1, 0, 2).reshape(4, self.n_img, self.Hp, self.Wp, self.C_pad)
+            out = torch.empty((self.n_img, 2 * H2, 2 * W2, self.C_pad), dtype=torch.int16, device=self.buf.device)
+            k = 0
+            for a in (0, 1):
+                for b in (0, 1):
+                    out[:, a::2, b::2, :] = rows[k][:, 1:, 1:, :].to(torch.int16)
+                    k += 1
+            q = (out[..., :self.C] + self.zero_point).to(torch.uint8)
+            return q.permute(0, 3, 1, 2)
+        H, W = self.Hp - 1, self.Wp - 1
+        out = torch.empty((self.n_img, self.C, H, W), dtype=torch.uint8, device=self.buf.device, memory_format=CL)
+        _lib.call("qbn_i8_p16_to_nhwc", _ptr(self.buf), self.n_img, H, W, self.C, self.zero_point, self.plane_rows, _ptr(out), _stream())
+        return out
+
+
+def p16_weight_bytes(C_pad, N, R, S, stride):
+    out = ctypes.c_longlong(0)
+    _lib.call("qbn_p16_weight_bytes", C_pad, N, R, S, stride, ctypes.byref(out))
+    return int(out.value)
+
+
+def i8_p16_block_weights(w, C_pad, stride, out=None):
+    """w int8 [n, N, C, R, S] (or [n, N, C]) sampled weights in the sampler's order -> blocked operands [n, bytes]."""
+    n, N, C = w.shape[0], w.shape[1], w.shape[2]
+    R, S = (w.shape[3], w.shape[4]) if w.dim() == 5 else (1, 1)
+    nbytes = p16_weight_bytes(C_pad, N, R, S, stride)
+    if out is None:
+        out = torch.empty((n, nbytes), dtype=torch.int8, device=w.device)
+    _lib.call("qbn_i8_p16_block_weights", _ptr(w.contiguous()), n, N, C, C_pad, R * S, stride, _ptr(out), _stream())
+    return out
+
+
+def i8_conv_p16_forward(x, w_blocked, n_samples, N, R, S, stride, bias, s_w, z_w, s_out, z_out, relu, act_bits, out, residual=None,
+                        add_qp=None, add_relu=True, x_shared=False, w_shared=False, out_phase_split=False, acc_dump=None):
+    """x, out, residual: P16Map.  Returns `out` with its (scale, zero_point) set to the result's."""
+    rq = _lib.I8Requant()
+    rq.s_x, rq.s_w, rq.z_w, rq.s_out, rq.z_out = float(x.scale), float(s_w), int(z_w), float(s_out), int(z_out)
+    rq.relu, rq.act_max = int(bool(relu)), (1 << act_bits) - 1
+    if residual is not None:
+        rq.s_res, rq.z_res, rq.s_add, rq.z_add, rq.add_relu = float(residual.scale), int(residual.zero_point), float(add_qp[0]), int(add_qp[1]), int(add_relu)
+        if (residual.C * (residual.Hp - 1) * (residual.Wp - 1) * (residual.n_img // max(1, n_samples))) % 64 != 0:
+            raise _lib.QbnError("fused quantized::add needs maps whose element count is a multiple of 64 (ATen's vector body)")
+    if stride == 2:
+        assert x.phases == 4, "a stride-2 planar conv reads a phase-split map"
+    Hp, Wp = x.Hp, x.Wp
+    B = (x.n_img if x_shared else x.n_img // n_samples)
+    _lib.call("qbn_i8_conv_p16_fwd", n_samples, B, Hp, Wp, x.C_pad, N, R, S, stride, _ptr(x.buf), x.plane_rows, int(x_shared), _ptr(w_blocked),
+              int(w_shared), _ptr(bias), ctypes.byref(rq), _ptr(residual.buf) if residual is not None else None,
+              residual.plane_rows if residual is not None else 0, QBN_FLAG_OUT_PHASE_SPLIT if out_phase_split else 0, _ptr(out.buf),
+              out.plane_rows, _ptr(acc_dump), _stream())
+    if residual is not None:
+        out.scale, out.zero_point = float(add_qp[0]), int(add_qp[1])
+    else:
+        out.scale, out.zero_point = float(s_out), int(z_out)
+    out.bits = act_bits
+    return out
+
+
+def i8_p16_avgpool(x, act_bits=7):
+    """nn.AvgPool2d over the whole map of a P16Map -> uint8 [n_img, C] (same scale / zero point)."""
+    out = torch.empty((x.n_img, x.C), dtype=torch.uint8, device=x.buf.device)
+    _lib.call("qbn_i8_p16_avgpool", _ptr(x.buf), x.n_img, x.Hp - 1, x.Wp - 1, x.C, x.zero_point, x.plane_rows, 0, (1 << act_bits) - 1,
+              _ptr(out), _stream())
+    return out
