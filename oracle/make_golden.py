@@ -604,6 +604,95 @@ def gen_resnet_int8(src):
 
 
 
+def gen_full_resnet_int8(src):
+    """Config C5 at FULL size: the reference's own ConvNetwork_ResNet (24/48/96/192, models_bbb.py:191-259) quantised
+    A7/W8 — prepare_model, one train + one eval forward (B=16) to calibrate every observer, convert — then TWO int8 forwards
+    of a B=4 batch on FBGEMM with replayed noise.  The fixture holds the reference's own checkpoint of the converted model
+    (resnet_int8_full_weights.pt: qint8 weights, every qparam), the input, the class probabilities, every BasicBlock output /
+    pooled map / logits in full, and a SHA-1 of every int8 layer's integer output (21 layers x 2 forwards).  The noise is
+    NOT stored (6.3 MB per forward): the tests redraw it from torch's CPU generator with the recorded seeds, layer by layer
+    in call order, exactly as below; `eps_sha1` pins that the generator still yields the same stream."""
+    import hashlib
+    import src.quant_utils as qu
+    from src.models.stochastic.bbb.models_bbb import BasicBlock, ConvNetwork_ResNet
+    g = torch.Generator().manual_seed(31)
+    args = Args(sigma_prior=0.05, model="conv_resnet_bbb", q=True, at=True, activation_precision=7, weight_precision=8)
+    torch.manual_seed(30)
+    net = ConvNetwork_ResNet([1, 3, 32, 32], 10, True, args)
+    with torch.no_grad():
+        for n, m in net.named_modules():
+            if hasattr(m, "std") and hasattr(m, "weight"):
+                trained_like_(m, g)
+                m.std.uniform_(-6.0, -3.0, generator=g)
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+                m.weight.uniform_(0.5, 1.5, generator=g)
+                m.bias.normal_(0, 0.1, generator=g)
+    net.train()
+    qu.prepare_model(net, args)
+    for m in net.modules():
+        if hasattr(m, "freeze_bn_stats"):
+            m.freeze_bn_stats()
+    torch.set_num_threads(8)
+    xc = torch.randn(16, 3, 32, 32, generator=g)
+    torch.manual_seed(3000)
+    net(xc)
+    net.eval()
+    torch.manual_seed(3001)
+    with torch.no_grad():
+        net(xc)
+    qu.convert(net)
+    net.eval()
+    torch.set_num_threads(1)
+    mods = dict(net.named_modules())
+    x = torch.randn(4, 3, 32, 32, generator=g)
+    arrays = {"x": npy(x), "seeds": np.array([3002, 3003])}
+    order, caps = [], {}
+
+    def cap(name):
+        def hook(mod, inp, out):
+            order.append(name)
+            caps[name] = out.detach().clone()
+        return hook
+    watched = [n for n, m in mods.items() if (hasattr(m, "mul_noise") and hasattr(m, "scale")) or isinstance(m, (BasicBlock, torch.nn.AvgPool2d))]
+    hooks = [mods[n].register_forward_hook(cap(n)) for n in watched]
+    sha = lambda a: hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    for fi, seed in enumerate((3002, 3003)):
+        order.clear()
+        caps.clear()
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            y = net(x)
+        arrays["f%d.y" % fi] = npy(y)
+        q_names = [n for n in order if hasattr(mods[n], "mul_noise")]
+        torch.manual_seed(seed)
+        eh = hashlib.sha1()
+        for n in q_names:
+            eh.update(np.ascontiguousarray(npy(torch.empty(mods[n].std.shape).normal_())).tobytes())
+        arrays["f%d.eps_sha1" % fi] = np.array(eh.hexdigest())
+        for n in order:
+            out = caps[n]
+            ints = npy(out.int_repr())                        # logical NCHW order
+            arrays["f%d.%s.sha1" % (fi, n)] = np.array(sha(ints.astype(np.uint8)))
+            # what the NEXT module sees: the model runs clamp_activation on every module output (models_bbb.py:231-238,
+            # src/utils.py:25-30: integer clamp to [0, 2^a - 1], qparams unchanged)
+            arrays["f%d.%s.sha1_clamped" % (fi, n)] = np.array(sha(np.clip(ints, 0, 127).astype(np.uint8)))
+            arrays["f%d.%s.qp" % (fi, n)] = np.array([out.q_scale(), out.q_zero_point()], np.float64)
+            if not hasattr(mods[n], "mul_noise") or mods[n].weight.dim() == 2:
+                arrays["f%d.%s.y_q" % (fi, n)] = ints.astype(np.uint8)
+        if fi == 0:
+            arrays["order"] = np.array(order)
+            arrays["q_names"] = np.array(q_names)
+    for h in hooks:
+        h.remove()
+    arrays["quant_qp"] = np.array([float(net.quant.scale), int(net.quant.zero_point)], np.float64)
+    save("resnet_int8_full", **arrays)
+    path = os.path.join(GOLD, "resnet_int8_full_weights.pt")
+    torch.save(net.state_dict(), path)
+    print("wrote %-28s %7.1f KB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+
+
 def gen_quant_ops(src):
     """Direct pins of the third-party integer ops (torch.ops.quantized.*) the A6 recipe calls."""
     rng = np.random.default_rng(18)
@@ -694,6 +783,7 @@ def main():
     gen_quant_ops(src)
     gen_qat_int8(src)
     gen_resnet_int8(src)
+    gen_full_resnet_int8(src)
 
 
 if __name__ == "__main__":

@@ -254,3 +254,21 @@ def test_mc_dropout_networks(golden):
         masks = dict(zip([n for n, _ in shapes], O.replay_masks(1200 + s, [sh for _, sh in shapes], 0.2)))
         y = O.lenet_mc_forward(P, x, lambda name, shape: masks[name], 0.2)
         np.testing.assert_allclose(y.numpy(), g["y%d" % s], rtol=1e-5, atol=1e-7)
+
+
+def test_full_resnet_int8_fixture_noise_stream_is_reproducible(golden, golden_dir):
+    """tests/golden/resnet_int8_full.npz does not store its 2 x 6.3 MB of noise: the GPU tests redraw it from torch's CPU
+    generator with the recorded seeds (oracle/make_golden.py:gen_full_resnet_int8).  Pin that the stream is still the one the
+    fixture was made with, and that the checkpoint holds the 21 int8 layers of the full-size network."""
+    import hashlib
+    import torch
+    g = golden("resnet_int8_full")
+    sd = torch.load(golden_dir / "resnet_int8_full_weights.pt", map_location="cpu")
+    q_names = [str(n) for n in g["q_names"]]
+    assert len(q_names) == 21 and sum(int(sd[n + ".weight"].numel()) for n in q_names) == 1571592      # SURVEY 8d: stochastic weights
+    for fi in (0, 1):
+        torch.manual_seed(int(g["seeds"][fi]))
+        h = hashlib.sha1()
+        for n in q_names:
+            h.update(np.ascontiguousarray(torch.empty(tuple(sd[n + ".std"].shape)).normal_().numpy()).tobytes())
+        assert h.hexdigest() == str(g["f%d.eps_sha1" % fi])
