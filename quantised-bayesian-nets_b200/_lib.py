@@ -133,6 +133,8 @@ def load():
                        "There is no CPU/PyTorch fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
+        if os.environ.get("QBN_LIB_PATH") and not hasattr(lib, name):
+            continue             # A/B kernel tuning against an older build: entry points it lacks simply cannot be called
         fn = getattr(lib, name)  # AttributeError if the library does not export what include/qbn.h declares
         fn.restype = res
         fn.argtypes = args

@@ -95,6 +95,23 @@ QBN_DEVINL void umma_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32
         : "memory");
   }
 }
+// the same with a compile-time accumulate flag: the predicate is a constant, no register -> uniform-register move per MMA
+template <int MODE, bool ACCUMULATE>
+QBN_DEVINL void umma_mma_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (MODE == MODE_I8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+        : "memory");
+  }
+}
 // 32 lanes x 8 consecutive 32-bit columns: thread t of the warp gets lane (base+t)
 QBN_DEVINL void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -88,7 +88,7 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
 }
 
 template <int DBG_MODE, bool STACKED, bool MASKED, int KIND = KIND_TF32>
-__global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
+__global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting (QBN_P4_PROF, diagnostics only)
   constexpr bool I8 = KIND == KIND_I8;
@@ -105,6 +105,16 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + p.ACC);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_shift = s_scale + 256;
+  // operand offsets of every MMA of one channel block, in issue order (tap-major, then K step), 16-byte units: .x from the
+  // A slot's start, .y from the weight slot's start.  The issuing thread reads one entry per MMA instead of re-deriving it.
+  uint2* s_ops = reinterpret_cast<uint2*>(s_shift + 256);
+  {
+    const uint32_t a_kk = (uint32_t)(2 * p.RA_p), b_kk = (uint32_t)(2 * p.n_pad), bt16_ = p.bt_bytes >> 4;
+    for (int e = tid; e < p.taps * p.nk; e += P4_THREADS) {
+      const int t = e / p.nk, jj = e - t * p.nk;
+      s_ops[e] = make_uint2((uint32_t)p.tap_off[t] + (uint32_t)jj * a_kk, (uint32_t)(p.b_res ? t : t % p.TG) * bt16_ + (uint32_t)jj * b_kk);
+    }
+  }
   for (int i = tid; i < 256; i += P4_THREADS) {
     s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
     // int8: the bias enters the accumulator domain exactly like FBGEMM's: fp32(bias) / fp32(s_x * s_w)
@@ -248,17 +258,21 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
               tc_fence_after();
               b16 = smem_u32(b_ring + (size_t)sb * p.b_slot_bytes) >> 4;
             }
-            const int t1 = min(t0 + p.TG, p.taps);
-#pragma unroll 1
-            for (int t = t0; t < t1; ++t) {
-              uint32_t ad = a16 + (uint32_t)p.tap_off[t], bd = b16;
-#pragma unroll 1
-              for (int jj = 0; jj < p.nk; ++jj) {
-                umma_mma<I8 ? MODE_I8 : MODE_EVAL>(tacc, adesc_hi | (uint64_t)(ad & 0x3FFF), bdesc_hi | (uint64_t)(bd & 0x3FFF), p.idesc, accum);
-                accum = 1;
-                ad += a_k; bd += b_k;
-              }
-              b16 += bt16;
+            int e = t0 * p.nk;
+            const int e1 = min(t0 + p.TG, p.taps) * p.nk;
+            uint2 o = s_ops[e];
+            if (!accum) {                      // the tile's first MMA overwrites the accumulator; every other one adds (constant predicate)
+              const uint2 on = s_ops[min(e + 1, e1 - 1)];
+              umma_mma_c<I8 ? MODE_I8 : MODE_EVAL, false>(tacc, adesc_hi | (uint64_t)((a16 + o.x) & 0x3FFF), bdesc_hi | (uint64_t)((b16 + o.y) & 0x3FFF), p.idesc);
+              accum = 1;
+              o = on;
+              ++e;
+            }
+#pragma unroll 2
+            for (; e < e1; ++e) {
+              const uint2 on = s_ops[min(e + 1, e1 - 1)];
+              umma_mma_c<I8 ? MODE_I8 : MODE_EVAL, true>(tacc, adesc_hi | (uint64_t)((a16 + o.x) & 0x3FFF), bdesc_hi | (uint64_t)((b16 + o.y) & 0x3FFF), p.idesc);
+              o = on;
             }
             if (!p.b_res) {
               umma_commit(smem_u32(&b_empty[sb]));
@@ -377,25 +391,48 @@ __global__ void __launch_bounds__(P4_THREADS, 3) umma_conv_p4_kernel(const __gri
           if (store) {
             uint32_t packed[4] = {0u, 0u, 0u, 0u};
             if (interior) {
-              const uint32_t rw[4] = {rres.x, rres.y, rres.z, rres.w};
+              if (p.acc_dump) {                 // tests only
+                for (int j = 0; j < 16; ++j)
+                  if (g * 16 + j < p.N) p.acc_dump[in_row * p.N + g * 16 + j] = (int)v[j] - corr;
+              }
+              // branch-free inner loops (16 independent chains per group); the zero points ride the clamp bounds
+              int sv[16];
+              float sh[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = g * 16 + j;
-                const int acc = (int)v[j] - corr;
-                if (p.acc_dump && c < p.N) p.acc_dump[in_row * p.N + c] = acc;
-                const float xf = __fadd_rn((float)acc, s_shift[c]);
-                int qv = __float2int_rn(__fmul_rn(xf, p.mult)) + p.z_out;
-                qv = max(p.q_lo, min(p.q_hi, qv));
-                if (p.has_add) {
-                  // quantized::add[_relu] (vector body of ATen's kernel: dequantise with one FMA per operand)
-                  const int rb = (int)(int8_t)((rw[j >> 2] >> ((j & 3) * 8)) & 0xFF) + p.z_res;
-                  const float da = __fmaf_rn(p.s_a, (float)qv, p.p_a);
-                  const float db = __fmaf_rn(p.s_b, (float)rb, p.p_b);
-                  qv = __float2int_rn(__fmul_rn(__fadd_rn(da, db), p.inv_s_add)) + p.z_add;
-                  qv = max(p.add_lo, min(p.add_hi, qv));
+              for (int k = 0; k < 4; ++k) {
+                const float4 t = *reinterpret_cast<const float4*>(&s_shift[g * 16 + 4 * k]);
+                sh[4 * k] = t.x; sh[4 * k + 1] = t.y; sh[4 * k + 2] = t.z; sh[4 * k + 3] = t.w;
+              }
+              if (!p.has_add) {
+                const int lo_s = p.q_lo - p.z_out, hi_s = p.q_hi - p.z_out;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float xf = __fadd_rn((float)((int)v[j] - corr), sh[j]);
+                  sv[j] = max(lo_s, min(hi_s, __float2int_rn(__fmul_rn(xf, p.mult))));
                 }
-                const int sv = c < p.N ? qv - p.z_fin : 0;
-                packed[j >> 2] |= ((uint32_t)sv & 0xFFu) << ((j & 3) * 8);
+              } else {
+                const uint32_t rw[4] = {rres.x, rres.y, rres.z, rres.w};
+                const int lo_s = p.add_lo - p.z_add, hi_s = p.add_hi - p.z_add;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float xf = __fadd_rn((float)((int)v[j] - corr), sh[j]);
+                  const int qo = max(p.q_lo, min(p.q_hi, __float2int_rn(__fmul_rn(xf, p.mult)) + p.z_out));
+                  // quantized::add[_relu] (vector body of ATen's kernel: dequantise with one FMA per operand)
+                  const int rb = (int)(int8_t)(rw[j >> 2] >> ((j & 3) * 8)) + p.z_res;
+                  const float da = __fmaf_rn(p.s_a, (float)qo, p.p_a);
+                  const float db = __fmaf_rn(p.s_b, (float)rb, p.p_b);
+                  sv[j] = max(lo_s, min(hi_s, __float2int_rn(__fmul_rn(__fadd_rn(da, db), p.inv_s_add))));
+                }
+              }
+              const int nvalid = p.N - g * 16;               // channels >= N of the last chunk stay zero (padding planes)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t lo2 = __byte_perm((uint32_t)sv[4 * k], (uint32_t)sv[4 * k + 1], 0x0040);
+                const uint32_t hi2 = __byte_perm((uint32_t)sv[4 * k + 2], (uint32_t)sv[4 * k + 3], 0x0040);
+                uint32_t w4 = __byte_perm(lo2, hi2, 0x5410);
+                const int left = nvalid - 4 * k;
+                if (left < 4) w4 = left <= 0 ? 0u : (w4 & (0xFFFFFFFFu >> (8 * (4 - left))));
+                packed[k] = w4;
               }
             }
             *reinterpret_cast<uint4*>(optr8 + (long long)g * out_step8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -687,7 +724,8 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   }
   // ---- shared memory / occupancy policy ----
   const size_t b_all = (size_t)p.bt_bytes * p.n_cb * p.taps + (size_t)p.bt2_bytes * p.n_cb2;
-  const size_t fixed = 2 * 256 * 4 + 16 + 8 * 64;
+  const size_t fixed = 2 * 256 * 4 + 16 + 8 * 64 + 8 * 256;          // affine tables, TMEM slot, barriers, MMA operand list
+  QBN_CHECK_ARG(p.taps * p.nk <= 256, "too many MMAs per channel block");
   const size_t cap = 225 * 1024;
   int want_occ;
   size_t smem;
@@ -753,6 +791,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false, KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
@@ -769,7 +808,26 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (residual) masked = true;                                  // ReLU before the residual add: general order
     else p.flags = (p.flags & ~QBN_FLAG_RELU_PRE) | QBN_FLAG_RELU;  // no mask, no residual: pre == post
   }
+  auto prof_report = [&](const char* kind) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_p4_prof, sizeof(h));
+    const unsigned long long t0 = (unsigned long long)(p.total_tiles / grid > 0 ? p.total_tiles / grid : 1);
+    fprintf(stderr, "[p4 prof %s] C=%d N=%d k%d s%d grid=%d tiles/CTA=%llu SA=%d SB=%d ACC=%d b_res=%d | epi: pre %llu wait_acc %llu tmem_ld %llu "
+            "compute+store %llu | mma: bres %llu wait_acc_empty %llu wait_a %llu wait_b %llu issue %llu commit %llu | prod: bres %llu "
+            "wait_a_empty %llu issueA %llu wait_b_empty %llu issueB %llu (cycles per tile)\n",
+            kind, C, N, R, stride, grid, t0, p.SA, p.SB, p.ACC, p.b_res, h[0] / t0, h[1] / t0, h[2] / t0, h[3] / t0, h[8] / t0, h[9] / t0, h[10] / t0,
+            h[11] / t0, h[12] / t0, h[13] / t0, h[16] / t0, h[17] / t0, h[18] / t0, h[19] / t0, h[20] / t0);
+  };
   if (i8) {
+    if (getenv("QBN_P4_PROF")) {       // diagnostics: cycle accounting of CTA 0 (synchronises the stream)
+      unsigned long long h[32] = {0};
+      cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
+      umma_conv_p4_kernel<1, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
+      QBN_CHECK_LAUNCH();
+      prof_report("i8");
+      return QBN_OK;
+    }
     umma_conv_p4_kernel<0, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
@@ -786,14 +844,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
     umma_conv_p4_kernel<1, false, false><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
-    cudaStreamSynchronize(st);
-    cudaMemcpyFromSymbol(h, g_p4_prof, sizeof(h));
-    const unsigned long long t0 = (unsigned long long)(p.total_tiles / grid > 0 ? p.total_tiles / grid : 1);
-    fprintf(stderr, "[p4 prof] C=%d N=%d k%d s%d grid=%d tiles/CTA=%llu SA=%d SB=%d ACC=%d b_res=%d | epi: pre %llu wait_acc %llu tmem_ld %llu "
-            "compute+store %llu | mma: bres %llu wait_acc_empty %llu wait_a %llu wait_b %llu issue %llu commit %llu | prod: bres %llu "
-            "wait_a_empty %llu issueA %llu wait_b_empty %llu issueB %llu (cycles per tile)\n",
-            C, N, R, stride, grid, t0, p.SA, p.SB, p.ACC, p.b_res, h[0] / t0, h[1] / t0, h[2] / t0, h[3] / t0, h[8] / t0, h[9] / t0, h[10] / t0,
-            h[11] / t0, h[12] / t0, h[13] / t0, h[16] / t0, h[17] / t0, h[18] / t0, h[19] / t0, h[20] / t0);
+    prof_report("tf32");
     return QBN_OK;
   }
   umma_conv_p4_kernel<0, false, false><<<grid, P4_THREADS, smem, st>>>(p);

@@ -68,16 +68,24 @@ def main():
         return
     out = {"workload": "resnet18_bbb_int8_a7w8_S100_B256", "B": B, "samples": S, "lifecycle_s": round(time.time() - wall, 2)}
     results = {}
-    for name, tc, chunk, iters in (("tcgen05_i8", True, 25, 3), ("imad", False, 25, 1)):
+    from qbn_b200.mc_int8 import Int8PlanarEngine
+    import sys as _sys
+    chunks = [int(c) for c in os.environ.get("QBN_I8_CHUNKS", "50").split(",")]
+    variants = [("planar_chunk%d" % c, None, c, 5) for c in chunks] + [("tcgen05_i8", True, 25, 3)]
+    if "--imad" in _sys.argv:
+        variants.append(("imad", False, 25, 1))
+    for name, tc, chunk, iters in variants:
         try:
-            ms, p = time_engine(Int8MCEngine(net, chunk=chunk, tensor_cores=tc), x, S, iters)
+            eng = Int8PlanarEngine(net, chunk=chunk) if tc is None else Int8MCEngine(net, chunk=chunk, tensor_cores=tc)
+            ms, p = time_engine(eng, x, S, iters)
             results[name] = p
             out[name] = {"ms_per_batch": round(ms, 3), "images_per_s": round(B / ms * 1e3, 1), "chunk": chunk,
                          "finite": bool(torch.isfinite(p).all()), "row_sum_err": float((p.sum(-1) - 1).abs().max())}
         except Exception as e:                            # keep the other variant's number
             out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
-    if len(results) == 2:
-        out["max_abs_diff_between_paths"] = float((results["tcgen05_i8"] - results["imad"]).abs().max())
+    keys = list(results)
+    if len(keys) >= 2:
+        out["max_abs_diff_between_paths"] = max(float((results[keys[0]] - results[k]).abs().max()) for k in keys[1:])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "int8_bench.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -17,8 +17,9 @@ def main():
     from bench_int8 import build_model
     net, x, _ = build_model(B=256)
     from qbn_b200 import _lib
-    from qbn_b200.mc_int8 import Int8MCEngine
-    eng = Int8MCEngine(net, chunk=chunk, tensor_cores=tensor_cores)
+    from qbn_b200.mc_int8 import Int8MCEngine, Int8PlanarEngine
+    planar = len(sys.argv) > 3 and sys.argv[3] == "planar"
+    eng = Int8PlanarEngine(net, chunk=chunk, use_graph=False) if planar else Int8MCEngine(net, chunk=chunk, tensor_cores=tensor_cores)
     eng.predict(x, chunk)                                   # warm-up (kernel attributes, allocator)
     rows, real_call = [], _lib.call
 
@@ -50,8 +51,10 @@ def main():
     for name in sorted(per, key=per.get, reverse=True):
         print("  %-26s %4d launches %9.3f ms  %5.1f %%" % (name, count[name], per[name], 100 * per[name] / total))
     print("  %-26s %4s          %9.3f ms  %5.1f %%   (permutes, clamps, dequantise, softmax, allocator)" % ("torch glue between calls", "", total - inside, 100 * (total - inside) / total))
-    convs = [(e0.elapsed_time(e1)) for name, e0, e1 in rows if name == "qbn_i8_conv_fwd"]
-    print("  per-layer qbn_i8_conv_fwd ms:", " ".join("%.2f" % v for v in convs))
+    convs = [(e0.elapsed_time(e1)) for name, e0, e1 in rows if name in ("qbn_i8_conv_fwd", "qbn_i8_conv_p16_fwd")]
+    print("  per-layer conv ms:", " ".join("%.3f" % v for v in convs))
+    if planar:
+        print("  per-layer steps  :", " ".join("%s:%dx%d/%d" % (st.name.replace("layers.", "L"), st.C, st.N, st.stride) for st in eng.steps))
 
 
 if __name__ == "__main__":
