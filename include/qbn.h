@@ -332,6 +332,13 @@ int qbn_i8_p16_to_nhwc(const int8_t* x, int64_t n_img, int H, int W, int C, int3
 int qbn_i8_p16_avgpool(const int8_t* x, int64_t n_img, int H, int W, int C, int32_t z_x, int64_t plane_rows,
                        int lo, int hi, uint8_t* out, void* stream);
 
+/* Draw offset of the Monte-Carlo samplers, kept on the DEVICE: after qbn_set_sample_base(p) every sampler launch
+ * (qbn_sample_weights*, qbn_i8_sample_weights, qbn_dropout_masks_multi, qbn_i8_dropout_mc) uses the Philox stream index
+ * *p + sample0 + s instead of sample0 + s, reading *p when the kernel runs.  One captured CUDA graph then serves every batch
+ * with fresh noise (the reference redraws per batch, experiments/utils.py:342-347): bump the scalar between replays.
+ * NULL switches it off.  The pointer must stay valid while launches that captured it can still run. */
+int qbn_set_sample_base(const uint32_t* base_dev);
+
 /* ---- A9: Monte-Carlo aggregation (experiments/utils.py:344-355) ----------------------------
  * logits [n_samples][B][K] -> psum[B][K] (+)= sum_s softmax(logits_s)  (models_bbb.py:131,243)
  * accumulate==0 overwrites.  The caller divides by the GLOBAL S after the allreduce.           */

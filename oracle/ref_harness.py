@@ -16,7 +16,17 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("QBN_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the verbatim copy oracle/build_ref.py made (oracle/_ref)."""
+    if os.path.isdir(os.path.join("/root/reference", "src", "models", "stochastic")):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("QBN_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -18,6 +18,16 @@ void qbn_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Device-side draw offset of the Monte-Carlo samplers (qbn_set_sample_base): every Philox stream index `sample0 + s` becomes
+// `*base + sample0 + s`, read by the kernel at run time.  A CUDA graph captured once therefore serves every batch: the host
+// bumps the device scalar between replays instead of re-capturing with a new sample0 (experiments/utils.py:342-347 redraws
+// the noise for every batch).  One process drives one GPU (torch.distributed, one rank per device), hence a process-wide pointer.
+static const uint32_t* g_sample_base = nullptr;
+extern "C" int qbn_set_sample_base(const uint32_t* base_dev) {
+  g_sample_base = base_dev;
+  return QBN_OK;
+}
+
 int qbn_sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -197,7 +207,9 @@ extern "C" int qbn_weight_grad_post(const float* dmu_p, const float* dsig2_p, co
 // ---------------------------------------------------------------------------------------------
 __global__ void sample_weights_kernel(const float* __restrict__ mu_p, const float* __restrict__ sigma_p, int64_t n,
                                       const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
-                                      float* __restrict__ w, int round_tf32) {
+                                      float* __restrict__ w, int round_tf32, const uint32_t* __restrict__ sbase) {
+  if (sbase) sample0 += *sbase;      // per-call draw offset read on the device: one CUDA graph serves every batch
+
   int s = blockIdx.y;
   int64_t n4 = (n + 3) >> 2;
   const bool vec_ok = (n & 3) == 0;
@@ -243,7 +255,7 @@ extern "C" int qbn_sample_weights(const float* mu_p, const float* sigma_p, int64
   int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_p, sigma_p, n, eps, seed, layer_id, sample0, w, round_tf32);
+  sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_p, sigma_p, n, eps, seed, layer_id, sample0, w, round_tf32, g_sample_base);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -612,7 +624,9 @@ QBN_DEVINL int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
 
 __global__ void i8_sample_weights_kernel(const int8_t* __restrict__ mu_q, const int8_t* __restrict__ sigma_q, int64_t n,
                                          I8SampleConsts k, const float* __restrict__ eps, uint64_t seed, uint32_t layer_id,
-                                         uint32_t sample0, int8_t* __restrict__ w) {
+                                         uint32_t sample0, int8_t* __restrict__ w, const uint32_t* __restrict__ sbase) {
+  if (sbase) sample0 += *sbase;      // per-call draw offset read on the device: one CUDA graph serves every batch
+
   int s = blockIdx.y;
   int64_t n4 = (n + 3) >> 2;
   int8_t* ws = w + (int64_t)s * n;
@@ -673,7 +687,7 @@ extern "C" int qbn_i8_sample_weights(const int8_t* mu_q, const int8_t* sigma_q, 
   int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  i8_sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_q, sigma_q, n, k, eps, seed, layer_id, sample0, w);
+  i8_sample_weights_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_q, sigma_q, n, k, eps, seed, layer_id, sample0, w, eps ? nullptr : g_sample_base);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -757,7 +771,9 @@ extern "C" int qbn_i8_avgpool(const uint8_t* x, int64_t B, int H, int W, int C, 
 
 __global__ void i8_dropout_kernel(const uint8_t* __restrict__ x, int zx, int64_t rows, int64_t hw, int64_t C,
                                   const float* __restrict__ mask, float keep, float inv_sm, int zm, float mult, uint64_t seed,
-                                  uint32_t sa, uint32_t sb, int64_t rows_per_sample, int lo, int hi, uint8_t* __restrict__ out) {
+                                  uint32_t sa, uint32_t sb, int64_t rows_per_sample, int lo, int hi, uint8_t* __restrict__ out, const uint32_t* __restrict__ sbase) {
+  if (sbase) sb += *sbase;
+
   int64_t total = rows * hw * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t c = i % C;
@@ -780,7 +796,7 @@ extern "C" int qbn_i8_dropout(const uint8_t* x, float s_x, int32_t z_x, int64_t 
   QBN_CHECK_ARG(rows > 0 && hw > 0 && C > 0 && s_x > 0 && s_m > 0, "sizes/scales");
   float mult = s_x * s_m * (1.0f / s_m);
   i8_dropout_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, z_x, rows, hw, C, mask, keep_prob,
-                                                                                     1.0f / s_m, z_m, mult, seed, sa, sb, 0, lo, hi, out);
+                                                                                     1.0f / s_m, z_m, mult, seed, sa, sb, 0, lo, hi, out, nullptr);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -793,7 +809,7 @@ extern "C" int qbn_i8_dropout_mc(const uint8_t* x, float s_x, int32_t z_x, int n
   float mult = s_x * s_m * (1.0f / s_m);
   const int64_t rows = (int64_t)n_samples * rows_per_sample;
   i8_dropout_kernel<<<qbn_grid_for(rows * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(x, z_x, rows, hw, C, nullptr, keep_prob, 1.0f / s_m, z_m,
-                                                                                     mult, seed, site, sample0, rows_per_sample, lo, hi, out);
+                                                                                     mult, seed, site, sample0, rows_per_sample, lo, hi, out, g_sample_base);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -923,7 +939,9 @@ extern "C" int qbn_p4_block_weights(const float* w_ohwi, int n_mats, int N, int 
 // bit-identical to qbn_sample_weights' whatever the blocking.
 __global__ void sample_weights_blocked_kernel(const float* __restrict__ mu_b, const float* __restrict__ sigma_b, P4Block g,
                                               const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0,
-                                              float* __restrict__ w, int round_tf32) {
+                                              float* __restrict__ w, int round_tf32, const uint32_t* __restrict__ sbase) {
+  if (sbase) sample0 += *sbase;      // per-call draw offset read on the device: one CUDA graph serves every batch
+
   const int s = blockIdx.y;
   float4* ws = reinterpret_cast<float4*>(w) + (int64_t)s * g.total4;
   const float* es = eps ? eps + (int64_t)s * g.N * g.K : nullptr;
@@ -963,7 +981,7 @@ extern "C" int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_
   int cap = (qbn_sm_count() * 8 + n_samples - 1) / n_samples;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
   sample_weights_blocked_kernel<<<dim3(gx, n_samples), 256, 0, (cudaStream_t)stream>>>(mu_b, sigma_b, g, eps, seed, layer_id, sample0, w,
-                                                                                     round_tf32);
+                                                                                     round_tf32, g_sample_base);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -1012,7 +1030,9 @@ struct qbn_p4_sample_job_dev {
   int s_off; int pad_;          // stacked jobs: this job covers the chunk's samples [s_off, s_off + n_stack)
 };
 __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev* __restrict__ jobs, uint64_t seed, uint32_t sample0,
-                                                    int round_tf32) {
+                                                    int round_tf32, const uint32_t* __restrict__ sbase) {
+  if (sbase) sample0 += *sbase;      // per-call draw offset read on the device: one CUDA graph serves every batch
+
   const qbn_p4_sample_job_dev jb = jobs[blockIdx.z];
   P4Block g;
   g.N = jb.N; g.C = jb.C; g.taps = jb.taps;
@@ -1062,14 +1082,16 @@ extern "C" int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs
   if (gx < 1) gx = 1;
   if (gx > 4096) gx = 4096;
   sample_weights_blocked_multi_kernel<<<dim3((unsigned)gx, n_samples, n_jobs), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const qbn_p4_sample_job_dev*>(jobs_dev), seed, sample0, round_tf32);
+      reinterpret_cast<const qbn_p4_sample_job_dev*>(jobs_dev), seed, sample0, round_tf32, g_sample_base);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
 
 // A8 masks of every dropout site of a Monte-Carlo chunk in one launch (blockIdx.z = site, blockIdx.y = sample)
 struct qbn_mask_job_dev { float* out; int64_t elems; uint32_t site_id; int pad_; };
-__global__ void dropout_masks_multi_kernel(const qbn_mask_job_dev* __restrict__ jobs, float keep, uint64_t seed, uint32_t sample0) {
+__global__ void dropout_masks_multi_kernel(const qbn_mask_job_dev* __restrict__ jobs, float keep, uint64_t seed, uint32_t sample0, const uint32_t* __restrict__ sbase) {
+  if (sbase) sample0 += *sbase;      // per-call draw offset read on the device: one CUDA graph serves every batch
+
   const qbn_mask_job_dev jb = jobs[blockIdx.z];
   const int s = blockIdx.y;
   float* o = jb.out + (int64_t)s * jb.elems;
@@ -1082,7 +1104,7 @@ extern "C" int qbn_dropout_masks_multi(const void* jobs_dev, int n_jobs, int64_t
   int64_t gx = (max_elems + 255) / 256;
   if (gx > 1024) gx = 1024;
   dropout_masks_multi_kernel<<<dim3((unsigned)gx, n_samples, n_jobs), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const qbn_mask_job_dev*>(jobs_dev), keep_prob, seed, sample0);
+      reinterpret_cast<const qbn_mask_job_dev*>(jobs_dev), keep_prob, seed, sample0, g_sample_base);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -114,3 +114,40 @@ def broadcast_parameters(model, src=0):
         return
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
+
+
+class DPTrainStep:
+    """Data-parallel wrapper around the reference's training step (src/trainer.py:87-132): parameters replicated, the batch
+    sharded over ranks, ONE flat all-reduce of the gradients per step.
+
+        zero_grad -> output = model(input) -> kl = model.get_kl_divergence() -> criterion(output, target, kl, gamma, n_batches,
+        n_points) -> if obj == obj: backward -> NaN-grad scrub (per replica, trainer.py:105-107) -> all-reduce(mean) -> step
+
+    The KL term depends on the parameters only: every rank computes it and scales it with the GLOBAL batch (the criterion's
+    kl / (B * n_batches) with 'batch' scaling sees the rank's B, hence `kl_batch_scale = 1 / world`), so it is not reduced twice.
+    BatchNorm uses per-rank batch statistics (torch DDP's default); for bit-for-bit parity with a single-GPU run use 1 rank."""
+
+    def __init__(self, model, criterion, optimizer, gamma=0.0, check_nan_loss=True):
+        self.model, self.criterion, self.optimizer, self.gamma = model, criterion, optimizer, float(gamma)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.check_nan_loss = bool(check_nan_loss)
+        _, ws = world()
+        self.ws = ws
+        self.kl_scale = 1.0 / ws
+        if ws > 1:
+            broadcast_parameters(model)
+
+    def __call__(self, input, target, n_batches, n_points):
+        self.optimizer.zero_grad(set_to_none=True)
+        output = self.model(input)
+        kl = self.model.get_kl_divergence() if hasattr(self.model, "get_kl_divergence") else torch.zeros(1, device=input.device)
+        obj, main_obj, kl_term = self.criterion(output, target, kl * self.kl_scale, self.gamma, n_batches, n_points)
+        # trainer.py:103 `obj == obj` skips a step whose loss is NaN (one host sync per step, like the reference).  With several
+        # ranks the decision must not differ between ranks (a rank that skipped would miss the collective): there every rank
+        # always runs the backward; a NaN loss only yields NaN gradients, which the scrub below zeroes before the all-reduce.
+        if self.ws > 1 or not self.check_nan_loss or bool(obj == obj):
+            obj.backward()
+            scrub_nan_grads(self.params)
+            allreduce_gradients(self.params, average=True)
+            self.optimizer.step()
+        return output, obj, main_obj, kl_term

@@ -810,7 +810,7 @@ class MCEngine:
         return out
 
     @torch.no_grad()
-    def predict_sum(self, x, samples, sample0=0, injected=None):
+    def predict_sum(self, x, samples, sample0=0, injected=None, draw_offset=None):
         """Sum over samples [sample0, sample0+samples) of softmax(logits) -> [B,K] (classification) or
         (sum mu, sum mu^2, sum var) building blocks (regression: returns stacked [S,B] mu and var).
 
@@ -818,12 +818,15 @@ class MCEngine:
         (input shape, sample range, seed) into a CUDA graph and replayed: the step is launch-bound otherwise."""
         if not x.is_cuda:
             raise RuntimeError("MCEngine needs CUDA tensors (no CPU fallback)")
+        if draw_offset is not None:     # fresh noise for this batch: global sample indices draw_offset + sample0 + s (noise.set_draw_offset)
+            noise.set_draw_offset(draw_offset, x.device)
         if self.use_graph and injected is None and not self.regression:
             return self._predict_sum_graph(x, samples, sample0)
         return self._predict_sum_eager(x, samples, sample0, injected)
 
     def _predict_sum_graph(self, x, samples, sample0):
         self._get_prep(x.device)        # a parameter update since the capture invalidates the graphs (they replay prepared operands)
+        noise.draw_base(x.device)       # the captured samplers read the per-batch draw offset from this device scalar
         key = (tuple(x.shape), x.dtype, int(samples), int(sample0), noise.seed(), x.device.index)
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)
@@ -878,10 +881,11 @@ class MCEngine:
         return psum
 
     @torch.no_grad()
-    def predict(self, x, samples, sample0=0, injected=None):
+    def predict(self, x, samples, sample0=0, injected=None, draw_offset=None):
         """Classification: mean_s softmax (experiments/utils.py:355).  Regression: (mean, var) of
-        experiments/utils.py:349-353."""
-        out = self.predict_sum(x, samples, sample0, injected)
+        experiments/utils.py:349-353.  draw_offset: first global sample index of this batch's draws (a data loader passes
+        batch_index * S so that every batch gets fresh noise from the one captured graph)."""
+        out = self.predict_sum(x, samples, sample0, injected, draw_offset)
         if self.regression:
             mu, var = out
             self.launches += 1

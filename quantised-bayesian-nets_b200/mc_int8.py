@@ -308,13 +308,17 @@ class Int8PlanarEngine:
         return psum
 
     @torch.no_grad()
-    def predict_sum(self, x, samples, sample0=0, seed=None, injected=None):
+    def predict_sum(self, x, samples, sample0=0, seed=None, injected=None, draw_offset=None):
         """sum over `samples` MC samples (global indices sample0..) of the class probabilities: [B, K] fp32.
+        draw_offset: first global sample index of this batch's draws (fresh noise per batch from the one captured graph).
         injected: per sample, the list of eps tensors of every Bayesian layer in the reference's draw order (parity tests)."""
         if not x.is_cuda:
             raise RuntimeError("Int8PlanarEngine runs on CUDA tensors only (no CPU fallback)")
         if seed is not None:
             noise.manual_seed(seed)
+        noise.draw_base(x.device)
+        if draw_offset is not None:
+            noise.set_draw_offset(draw_offset, x.device)
         x = x.float()
         if not self.use_graph or injected is not None or self.trace is not None:
             return self._predict_sum_eager(x, samples, sample0, injected)
@@ -344,8 +348,8 @@ class Int8PlanarEngine:
         self.launches += n_launch
         return static_out.clone()
 
-    def predict(self, x, samples, sample0=0, seed=None, injected=None):
-        return self.predict_sum(x, samples, sample0, seed, injected) / float(samples)
+    def predict(self, x, samples, sample0=0, seed=None, injected=None, draw_offset=None):
+        return self.predict_sum(x, samples, sample0, seed, injected, draw_offset) / float(samples)
 
 
 def make_int8_engine(model, chunk=50, **kw):

@@ -88,3 +88,30 @@ def sample_batch(n_samples, sample0, batch, act_bits=8):
 def sample_batch_state():
     return _state["sample_batch"]
 
+
+
+# ---- per-batch draw offset, kept on the device ---------------------------------------------------------------------------
+# The Monte-Carlo engines key Philox by (seed, layer, GLOBAL sample index).  Replaying a captured CUDA graph would hand every
+# batch the same S draws; the reference redraws for every batch (experiments/utils.py:342-347).  The samplers therefore add a
+# device-side scalar to the sample index (include/qbn.h: qbn_set_sample_base): `set_draw_offset(k * S)` before batch k gives
+# batch k the sample indices k*S .. k*S+S-1 with ONE graph, no re-capture and no host synchronisation.
+_draw_base = {}
+
+
+def draw_base(device):
+    """The int32 device scalar the samplers read (created and registered with the library on first use)."""
+    from . import _lib
+    import ctypes
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _draw_base.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+        _draw_base[key] = t
+    _lib.call("qbn_set_sample_base", ctypes.c_void_p(t.data_ptr()))
+    return t
+
+
+def set_draw_offset(offset, device="cuda"):
+    """All following sampler launches on `device` (eager or graph replays) draw sample indices `offset + ...`."""
+    draw_base(device).fill_(int(offset) & 0x7FFFFFFF)
