@@ -29,10 +29,10 @@ def balanced_chunks(total, chunk):
 class Int8MCEngine:
     def __init__(self, model, chunk=25, tensor_cores=True):
         layers = [m for m in model.modules() if hasattr(m, "sampled_weights")]
-        if not layers:
-            raise ValueError("Int8MCEngine needs a converted model (quant_utils.convert) with int8 Bayesian layers")
-        if any(isinstance(m, BernoulliDropout) and m._p > 0 for m in model.modules()):
-            raise NotImplementedError("sample-batched int8 MC-Dropout is not built; run the model per sample")
+        sites = [m for m in model.modules() if isinstance(m, BernoulliDropout) and m._prob() > 0]
+        if not layers and not sites:
+            raise ValueError("Int8MCEngine needs a converted model with int8 Bayesian layers (quant_utils.convert) or int8 MC-Dropout "
+                             "sites (quant_utils.to_device_int8)")
         self.model, self.chunk, self.regression = model, int(chunk), False
         args = getattr(model, "args", None)
         bits = int(getattr(args, "activation_precision", 8)) if args is not None else 8
@@ -350,6 +350,51 @@ class Int8PlanarEngine:
 
     def predict(self, x, samples, sample0=0, seed=None, injected=None, draw_offset=None):
         return self.predict_sum(x, samples, sample0, seed, injected, draw_offset) / float(samples)
+
+
+class Int8EnsembleEngine:
+    """SGHMC ensemble evaluation (models_sgld.py:216-288): `Network(training_mode=False)` holds `args.samples` independently
+    trained members and its forward visits `ensemble[counter]` once per call, so the reference's S-loop
+    (experiments/utils.py:344-347) averages one deterministic forward per member.  Here every member is a converted stock
+    int8 network (quant_utils.to_device_int8) compiled onto the planar kind::i8 kernel with its weights blocked once; members
+    are independent, so `dist.ShardedMCPredictor` shards them over GPUs like Monte-Carlo samples (member index = sample index)
+    and all-reduces the probability sums once.  predict_sum(x, count, sample0) = sum over members sample0 .. sample0+count-1."""
+
+    def __init__(self, members, use_graph=True):
+        members = list(getattr(members, "ensemble", members))
+        if not members:
+            raise ValueError("empty ensemble")
+        self.members = members
+        self.engines = []
+        for m in members:
+            try:
+                self.engines.append(Int8PlanarEngine(m, chunk=1, use_graph=use_graph))
+            except PlanarUnsupported:
+                self.engines.append(None)                       # module-driven forward of that member (any architecture)
+        self.regression, self.model = False, members[0]
+        self.n_members = len(members)
+
+    @torch.no_grad()
+    def predict_sum(self, x, samples, sample0=0, **_):
+        if not x.is_cuda:
+            raise RuntimeError("Int8EnsembleEngine runs on CUDA tensors only (no CPU fallback)")
+        total = None
+        for i in range(int(sample0), int(sample0) + int(samples)):
+            k = i % self.n_members                              # models_sgld.py:277-284: the counter wraps around
+            eng = self.engines[k]
+            if eng is not None:
+                part = eng.predict_sum(x, 1)
+            else:
+                was = self.members[k].training
+                self.members[k].eval()
+                part = torch.softmax(self.members[k](x.float()), dim=-1)
+                self.members[k].train(was)
+            total = part.clone() if total is None else total.add_(part)
+        return total
+
+    def predict(self, x, samples=None, sample0=0):
+        samples = self.n_members if samples is None else samples
+        return self.predict_sum(x, samples, sample0) / float(samples)
 
 
 def make_int8_engine(model, chunk=50, **kw):

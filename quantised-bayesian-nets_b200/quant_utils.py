@@ -177,6 +177,61 @@ class QTensor:
     def reshape(self, *shape):
         return QTensor(self.q.reshape(*shape), self.scale, self.zero_point, self.bits)
 
+    # ---- enough of torch's quantised-tensor protocol for the REFERENCE's own model code to run on QTensors unchanged:
+    # `clamp_activation` (src/utils.py:25-30: x.dtype == torch.quint8, x.q_scale(), x.q_zero_point(), torch.clamp with float
+    # bounds), nn.ReLU / nn.AvgPool2d / nn.MaxPool2d between the layers (models_bbb.py:209, models_mc.py:177), Flatten.
+    dtype = torch.quint8
+    is_quantized = True
+
+    @property
+    def device(self):
+        return self.q.device
+
+    @property
+    def is_cuda(self):
+        return self.q.is_cuda
+
+    def _clamp_float(self, lo, hi):
+        """torch.clamp on a quint8 tensor with float bounds = integer clamp to the quantised bounds (qparams unchanged)."""
+        def to_q(v, default):
+            if v is None:
+                return default
+            return int(max(0, min(255, round(float(v) / self.scale) + self.zero_point)))
+        lo_q, hi_q = to_q(lo, 0), to_q(hi, 255)
+        bits = self.bits
+        if lo_q == 0 and hi_q + 1 == (hi_q + 1 & -(hi_q + 1)):          # [0, 2^b - 1]: remember the width
+            b = (hi_q + 1).bit_length() - 1
+            if self.bits <= b:
+                return self                                              # already inside: the clamp is the identity
+            bits = b
+        return QTensor(torch.clamp(self.q, lo_q, hi_q), self.scale, self.zero_point, bits)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        import torch.nn.functional as F
+        x = args[0] if args else kwargs.get("input")
+        if func in (torch.clamp, torch.Tensor.clamp):
+            lo = args[1] if len(args) > 1 else kwargs.get("min")
+            hi = args[2] if len(args) > 2 else kwargs.get("max")
+            return x._clamp_float(lo, hi)
+        if func in (torch.relu, F.relu, torch.Tensor.relu):
+            sb = noise.sample_batch_state()
+            bits = min(x.bits, sb[3]) if sb is not None else x.bits
+            return QTensor(ops.i8_relu(x.q, x.zero_point, act_bits=bits), x.scale, x.zero_point, bits)
+        if func in (F.avg_pool2d, torch._C._nn.avg_pool2d):
+            k = args[1] if len(args) > 1 else kwargs.get("kernel_size")
+            k = k if isinstance(k, int) else k[0]
+            return QTensor(ops.i8_avgpool(x.q, x.zero_point, k, act_bits=x.bits), x.scale, x.zero_point, x.bits)
+        if func in (F.max_pool2d, torch.max_pool2d):
+            k = args[1] if len(args) > 1 else kwargs.get("kernel_size")
+            st = args[2] if len(args) > 2 else kwargs.get("stride", None)
+            q = F.max_pool2d(x.q.float(), k, st).to(torch.uint8).contiguous(memory_format=torch.channels_last)
+            return QTensor(q, x.scale, x.zero_point, x.bits)            # order-preserving affine map: max of the integers
+        if func in (torch.flatten,):
+            return QTensor(torch.flatten(x.q, *args[1:], **kwargs), x.scale, x.zero_point, x.bits)
+        return NotImplemented
+
     def size(self, i=None):
         return self.q.size() if i is None else self.q.size(i)
 
@@ -196,6 +251,10 @@ class Quantize(nn.Module):
     def from_float(cls, mod):
         s, z = mod.activation_post_process.calculate_qparams()
         return cls(float(s), int(z))
+
+    @classmethod
+    def from_torch(cls, mod):
+        return cls(float(mod.scale.reshape(-1)[0]), int(mod.zero_point.reshape(-1)[0]))
 
     # nnq.Quantize keeps (scale, zero_point) as [1] buffers: same checkpoint keys
     def _save_to_state_dict(self, destination, prefix, keep_vars):
@@ -242,6 +301,13 @@ class QFunctional(nn.Module):
         q = ops.i8_add(a, x.scale, x.zero_point, b, y.scale, y.zero_point, self.scale, self.zero_point, act_bits=bits, relu=relu)
         return QTensor(q, self.scale, self.zero_point, bits)
 
+    def mul_scalar(self, x, y):
+        """quantized::mul_scalar with a positive scalar (dropout.py:39): the integers stay, the scale is multiplied (fp32)."""
+        y = float(y.detach().reshape(-1)[0]) if torch.is_tensor(y) else float(y)
+        if y <= 0:
+            raise NotImplementedError("QFunctional.mul_scalar: positive scalars only (the reference multiplies by 1/(1-p))")
+        return QTensor(x.q, x.scale * y, x.zero_point, x.bits)                # ATen: the quantizer's scale (double) times the scalar
+
     def extra_repr(self):
         return "scale={}, zero_point={}".format(self.scale, self.zero_point)
 
@@ -249,6 +315,11 @@ class QFunctional(nn.Module):
     def from_float(cls, mod):
         s, z = mod.activation_post_process.calculate_qparams()
         return cls(float(s), int(z))
+
+    @classmethod
+    def from_torch(cls, mod):
+        """torch's own nnq.QFunctional (a model converted by torch.quantization.convert on the CPU)."""
+        return cls(float(mod.scale), int(mod.zero_point))
 
     # checkpoint keys of nnq.QFunctional: `<prefix>scale`, `<prefix>zero_point` as 0-d tensors
     def _save_to_state_dict(self, destination, prefix, keep_vars):
@@ -357,3 +428,44 @@ def load_model(model, model_path, replace=True):
 def postprocess_model(model, args, q=None, at=None, special_info=""):
     """quant_utils.py:101-110 without the file I/O: convert the (trained, calibrated) QAT model to int8."""
     return convert(model)
+
+
+def to_device_int8(model, device="cuda"):
+    """A model converted by torch itself — the reference's MC-Dropout and SGHMC families go through stock
+    `torch.quantization.prepare_qat` / `convert` (src/quant_utils.py:140-141, models_mc.py:222, models_sgld.py:210) and run on
+    FBGEMM on the CPU — re-housed on the GPU kernels, in place: nnq.Conv2d / nniq.ConvReLU2d / nnq.Linear / nniq.LinearReLU ->
+    stochastic.quantized_det (same integers, same requantisation), nnq.Quantize / DeQuantize / QFunctional -> the classes above,
+    the reference's BernoulliDropout -> the drop-in (its converted mul_mask qparams kept).  The model's own forward (the
+    reference's code, `clamp_activation` included) then runs unchanged on QTensor activations."""
+    import torch.ao.nn.intrinsic.quantized as nniq
+    import torch.ao.nn.quantized as nnq
+    from .stochastic import quantized_det as det
+    from .stochastic.mcdropout.dropout import BernoulliDropout
+    table = {nniq.ConvReLU2d: det.QuantizedConvReLU2d, nnq.Conv2d: det.QuantizedConv2d, nniq.LinearReLU: det.QuantizedLinearReLU,
+             nnq.Linear: det.QuantizedLinear, nnq.Quantize: Quantize, nnq.DeQuantize: DeQuantize, nnq.QFunctional: QFunctional}
+
+    def swap(mod):
+        for name, child in list(mod.named_children()):
+            cls = table.get(type(child))
+            if cls is not None:
+                new = cls.from_torch(child) if cls is not DeQuantize else DeQuantize()
+                mod._modules[name] = new.to(device) if isinstance(new, nn.Module) else new
+            elif type(child).__name__ == "BernoulliDropout" and not isinstance(child, BernoulliDropout):
+                new = BernoulliDropout(float(child.p.detach().reshape(-1)[0]))
+                for fn in ("mul_mask", "mul_scalar"):
+                    f = getattr(child, fn)
+                    setattr(new, fn, QFunctional.from_torch(f) if isinstance(f, nnq.QFunctional) else f)
+                mod._modules[name] = new.to(device)
+            else:
+                if isinstance(child, BernoulliDropout):
+                    for fn in ("mul_mask", "mul_scalar"):
+                        f = getattr(child, fn)
+                        if isinstance(f, nnq.QFunctional):
+                            setattr(child, fn, QFunctional.from_torch(f))
+                swap(child)
+    swap(model)
+    for p_ in model.parameters():
+        p_.data = p_.data.to(device)
+    for b_ in model.buffers():
+        b_.data = b_.data.to(device)
+    return model

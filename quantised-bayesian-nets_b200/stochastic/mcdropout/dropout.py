@@ -68,7 +68,7 @@ class BernoulliDropout(nn.Module):
             out = ops.i8_dropout(q, x.scale, x.zero_point, p, s_m, z_m, mask, key, act_bits=8)
         mult = float(self.multiplier.detach().reshape(-1)[0]) if self.__dict__.get("_mult_ver") != self.multiplier._version else self._mult
         self._mult, self._mult_ver = mult, self.multiplier._version
-        return QTensor(out, float(torch.tensor(s_m, dtype=torch.float32) * torch.tensor(mult, dtype=torch.float32)), z_m, 8)
+        return QTensor(out, s_m * mult, z_m, 8)            # quantized::mul_scalar: scale * scalar in double, integers unchanged
 
     def extra_repr(self):
         return 'p={}, quant={}'.format(self._prob(), hasattr(self.mul_mask, 'zero_point'))

@@ -78,6 +78,16 @@ def i8_avgpool(x_q, z_x, k, act_bits=7):
     return _like_cl(O.i8_avgpool(_nchw_ints(x_q), z_x, k, act_bits=act_bits))
 
 
+def i8_dropout(x_q, s_x, z_x, p, s_m, z_m, mask=None, key=(0, 0, 0), act_bits=7):
+    assert mask is not None, "the CPU stand-in has no Philox: inject the mask"
+    m = mask.detach().cpu().numpy()
+    x = _nchw_ints(x_q)
+    mult = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    y = O.i8_dropout(x, s_x, z_x, m, s_m, z_m, float(mult), act_bits=act_bits)
+    y = y[0] if isinstance(y, tuple) else y
+    return _like_cl(y) if x_q.dim() == 4 else torch.as_tensor(np.asarray(y).astype(np.uint8))
+
+
 def mc_mean(probs):
     return probs.float().mean(0)
 
@@ -85,5 +95,5 @@ def mc_mean(probs):
 def emulated_int8_ops(monkeypatch):
     """Install the stand-ins on qbn_b200.ops for the duration of a test (pytest's monkeypatch undoes it)."""
     from qbn_b200 import ops
-    for name in ("quantize_u8", "dequantize_u8", "i8_sample_weights", "i8_conv_forward", "i8_add", "i8_relu", "i8_avgpool", "mc_mean"):
+    for name in ("quantize_u8", "dequantize_u8", "i8_sample_weights", "i8_conv_forward", "i8_add", "i8_relu", "i8_avgpool", "i8_dropout", "mc_mean"):
         monkeypatch.setattr(ops, name, globals()[name])

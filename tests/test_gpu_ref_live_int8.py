@@ -1,0 +1,80 @@
+"""GPU, live against the unmodified reference (oracle/_ref on the GPU box, /root/reference in the build container; skipped where
+neither exists): the reference's stock-quantised families of config C5 — the MC-Dropout ResNet-18 and the SGHMC ensemble —
+built and converted by the reference's own lifecycle on the CPU (FBGEMM), then re-housed on the CUDA kernels
+(quant_utils.to_device_int8) and evaluated (i) by the reference's own model code on QTensors, (ii) by the engines
+(Int8EnsembleEngine on the planar kind::i8 kernel, Int8MCEngine with all samples of a chunk per launch).  Integer arithmetic:
+the class probabilities must agree to fp32 softmax rounding (a single differing int8 logit would move them by ~1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+import _ref_models as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="reference sources not present (oracle/_ref)")]
+
+
+def _build():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def test_sghmc_ensemble_int8_matches_the_reference_on_fbgemm():
+    _build()
+    from qbn_b200 import dist as qdist, quant_utils as qu
+    from qbn_b200.mc_int8 import Int8EnsembleEngine, Int8PlanarEngine
+    torch.set_num_threads(1)
+    n = 3
+    net, args = R.sgld_ensemble(n)
+    x = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = torch.stack([net(x) for _ in range(n)])                  # experiments/utils.py:344-347 over Network.forward
+    mine = qu.to_device_int8(R.clone(net), "cuda")
+    with torch.no_grad():
+        got = torch.stack([mine(x.cuda()) for _ in range(n)])            # the reference's own forward code on the CUDA modules
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    eng = Int8EnsembleEngine(mine)
+    assert all(isinstance(e, Int8PlanarEngine) for e in eng.engines)     # every member compiled onto the planar kernel
+    p = eng.predict(x.cuda())
+    np.testing.assert_allclose(p.cpu().numpy(), want.mean(0).numpy(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(p, eng.predict(x.cuda()))                         # graph replay
+    # member sharding = sample sharding (SURVEY 8e iii): any split of the member range sums to the same probabilities
+    parts = eng.predict_sum(x.cuda(), 2, sample0=0) + eng.predict_sum(x.cuda(), 1, sample0=2)
+    np.testing.assert_allclose((parts / n).cpu().numpy(), p.cpu().numpy(), rtol=0, atol=1e-6)
+    assert qdist.ShardedMCPredictor(eng).predict(x.cuda(), n).shape == (8, 10)
+
+
+def test_mc_dropout_resnet_int8_matches_the_reference_on_fbgemm():
+    _build()
+    from qbn_b200 import noise, quant_utils as qu
+    from qbn_b200.mc_int8 import Int8MCEngine
+    torch.set_num_threads(1)
+    net, args = R.mc_dropout_resnet()
+    x = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+    sites = R.dropout_sites(net)
+    shapes = []
+    hooks = [m.register_forward_hook(lambda mod, i, o: shapes.append(tuple(i[0].shape[:2]))) for m in sites]
+    torch.manual_seed(78)
+    with torch.no_grad():
+        want = net(x)
+    for h in hooks:
+        h.remove()
+    torch.manual_seed(78)
+    masks = [torch.FloatTensor(*s).bernoulli_(1. - sites[0].p).cuda() for s in shapes]      # dropout.py:21-30, same generator stream
+    mine = qu.to_device_int8(R.clone(net), "cuda")
+    with torch.no_grad(), noise.inject(masks):
+        got = mine(x.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    # product path: Philox masks, all samples of a chunk per launch == the per-sample loop with the same streams
+    noise.manual_seed(5)
+    S = 5
+    with torch.no_grad():
+        loop = []
+        for s in range(S):
+            with noise.sample_index(s):
+                loop.append(mine(x.cuda()))
+    assert float((loop[0] - loop[1]).abs().max()) > 0
+    eng = Int8MCEngine(mine, chunk=3)
+    got_sum = eng.predict_sum(x.cuda(), S)
+    np.testing.assert_allclose(got_sum.cpu().numpy(), torch.stack(loop).sum(0).cpu().numpy(), rtol=0, atol=2e-6)
+    rate = float(torch.stack([(m == 0).float().mean() for m in masks]).mean())
+    assert 0.05 < rate < 0.25                                            # p = 0.15
