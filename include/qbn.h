@@ -360,6 +360,16 @@ int qbn_cls_metrics(const float* probs, const int64_t* target, int B, int K, flo
 int qbn_reg_metrics(const float* mean, const float* var, const float* target, int64_t B,
                     float* out, void* stream);
 
+/* ---- SGHMC / SGLD parameter update (utils_sgld.py:30-92), one fused pass per parameter tensor:
+ * grad += weight_decay * p (in place, like the reference); burn_in: tau, g, V_hat preconditioner update; resample_momentum:
+ * v = z_m * sqrt(lr^2 / (sqrt(V_hat) + eps)); v += -lr^2/(sqrt(V_hat)+eps) * grad - base_C * v + z_n * sqrt(max(2 lr^2/(sqrt(V_hat)+eps)
+ * base_C - lr^4, 1e-16)); NaN / inf momentum -> 0; p += v.  z_momentum / z_noise: injected standard normals or NULL -> Philox
+ * (seed, stream_a, stream_b [+1 for the noise], element).                                                                   */
+int qbn_sghmc_step(float* p, float* grad, float* tau, float* g, float* V_hat, float* v_momentum, int64_t n,
+                   float weight_decay, float lr, float base_C, float eps, int burn_in, int resample_momentum,
+                   const float* z_momentum, const float* z_noise, uint64_t seed, uint32_t stream_a,
+                   uint32_t stream_b, void* stream);
+
 /* ---- A11 glue kernels that survive fusion only at resolution changes ------------------------ */
 int qbn_maxpool2x2(const float* x, int64_t B, int H, int W, int C, float* out, void* stream);
 /* global average pool HxW -> 1 (nn.AvgPool2d(4) on the 4x4 map, models_bbb.py:209) */

@@ -1141,3 +1141,57 @@ extern "C" int qbn_kl_multi(const void* jobs_dev, int n_jobs, int64_t max_n, flo
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// SGHMC / SGLD parameter update (src/models/stochastic/sgld/utils_sgld.py:30-92), one fused pass per parameter tensor
+// instead of ~35 elementwise launches: weight decay into the gradient, burn-in preconditioner (tau, g, V_hat), optional momentum
+// resampling, friction + injected Gaussian noise, NaN/inf scrub of the momentum, parameter step.  z_mom / z_noise: standard
+// normals injected by the caller (parity tests) or NULL -> Philox(seed, stream_a, stream_b / stream_b + 1, element).
+// Every fp32 operation is rounded separately, in the order torch evaluates the reference's expressions.
+// ---------------------------------------------------------------------------------------------
+__global__ void sghmc_step_kernel(float* __restrict__ p, float* __restrict__ grad, float* __restrict__ tau, float* __restrict__ g,
+                                  float* __restrict__ V, float* __restrict__ v, int64_t n, float wd, float lr2, float lr4, float base_C,
+                                  float eps, int burn_in, int resample, const float* __restrict__ z_mom, const float* __restrict__ z_noise,
+                                  uint64_t seed, uint32_t sa, uint32_t sb) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = grad[i];
+    if (wd != 0.f) d = __fmaf_rn(wd, p[i], d);                          // d_p.add_(p.data, alpha=weight_decay): ATen's add-with-alpha is one fused multiply-add; in place, like the reference
+    grad[i] = d;
+    float Vh = V[i];
+    if (burn_in) {
+      float t = tau[i], gg = g[i];
+      t = __fadd_rn(t, __fadd_rn(__fdiv_rn(__fmul_rn(-t, __fmul_rn(gg, gg)), __fadd_rn(Vh, eps)), 1.0f));
+      const float ti = __fdiv_rn(1.0f, __fadd_rn(t, eps));
+      gg = __fadd_rn(gg, __fadd_rn(__fmul_rn(-ti, gg), __fmul_rn(ti, d)));
+      Vh = __fadd_rn(Vh, __fadd_rn(__fmul_rn(-ti, Vh), __fmul_rn(ti, __fmul_rn(d, d))));
+      tau[i] = t; g[i] = gg; V[i] = Vh;
+    }
+    const float vis = __fdiv_rn(1.0f, __fadd_rn(sqrtf(Vh), eps));        // V_inv_sqrt
+    float vm = v[i];
+    if (resample) {
+      const float z = z_mom ? z_mom[i] : philox_normal1(seed, sa, sb, (uint64_t)i);
+      vm = __fmul_rn(z, sqrtf(__fmul_rn(lr2, vis)));                     // torch.normal(0, sqrt(lr^2 * V_inv_sqrt))
+    }
+    const float nvar = __fadd_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.0f, lr2), vis), base_C), -lr4);
+    const float nstd = sqrtf(fmaxf(nvar, 1e-16f));
+    const float z = z_noise ? z_noise[i] : philox_normal1(seed, sa, sb + 1u, (uint64_t)i);
+    const float ns = __fmul_rn(z, nstd);
+    // v.add_(-(lr^2) * V_inv_sqrt * d_p - base_C * v + noise)
+    vm = __fadd_rn(vm, __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(-lr2, vis), d), -__fmul_rn(base_C, vm)), ns));
+    if (vm != vm || isinf(vm)) vm = 0.f;                                 // utils_sgld.py:86-88
+    v[i] = vm;
+    p[i] = __fadd_rn(p[i], vm);
+  }
+}
+extern "C" int qbn_sghmc_step(float* p, float* grad, float* tau, float* g, float* V_hat, float* v_momentum, int64_t n, float weight_decay,
+                              float lr, float base_C, float eps, int burn_in, int resample_momentum, const float* z_momentum,
+                              const float* z_noise, uint64_t seed, uint32_t stream_a, uint32_t stream_b, void* stream) {
+  QBN_CHECK_ARG(p && grad && tau && g && V_hat && v_momentum && n > 0, "null pointer / n");
+  const float lr2 = (float)((double)lr * (double)lr), lr4 = (float)((double)lr * lr * lr * lr);       // python: lr ** 2, lr ** 4 in double
+  sghmc_step_kernel<<<qbn_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, grad, tau, g, V_hat, v_momentum, n, weight_decay, lr2, lr4, base_C,
+                                                                           eps, burn_in, resample_momentum, z_momentum, z_noise, seed, stream_a,
+                                                                           stream_b);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

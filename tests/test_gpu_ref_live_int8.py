@@ -78,3 +78,49 @@ def test_mc_dropout_resnet_int8_matches_the_reference_on_fbgemm():
     np.testing.assert_allclose(got_sum.cpu().numpy(), torch.stack(loop).sum(0).cpu().numpy(), rtol=0, atol=2e-6)
     rate = float(torch.stack([(m == 0).float().mean() for m in masks]).mean())
     assert 0.05 < rate < 0.25                                            # p = 0.15
+
+
+def test_sghmc_optimiser_step_matches_the_reference():
+    """The fused SGHMC update (qbn_sghmc_step behind the drop-in SGLD optimiser) against the reference's SGLD class
+    (utils_sgld.py:30-92) on the CPU, with its Gaussian draws replayed (torch.normal(0, std) == normal_() * std on the same
+    generator stream): parameters and every state tensor after a burn-in step with momentum resampling, a burn-in step and a
+    sampling step."""
+    _build()
+    from oracle import ref_harness
+    ref_harness.import_reference()
+    from src.models.stochastic.sgld.utils_sgld import SGLD as RefSGLD
+    from qbn_b200 import noise
+    from qbn_b200.stochastic.sgld.utils_sgld import SGLD
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 33), (17,), (8, 4, 3, 3)]
+    p_ref = [torch.nn.Parameter(torch.randn(s, generator=g) * 0.3) for s in shapes]
+    p_gpu = [torch.nn.Parameter(p.detach().clone().cuda()) for p in p_ref]
+    o_ref, o_gpu = RefSGLD(p_ref, lr=1e-2, base_C=0.05, gauss_sig=0.1), SGLD(p_gpu, lr=1e-2, base_C=0.05, gauss_sig=0.1)
+    plan = [dict(burn_in=True, resample_momentum=True), dict(burn_in=True, resample_momentum=False), dict(burn_in=False, resample_momentum=False)]
+    for k, kw in enumerate(plan):
+        grads = [torch.randn(s, generator=g) for s in shapes]
+        for p, q, gr in zip(p_ref, p_gpu, grads):
+            p.grad, q.grad = gr.clone(), gr.clone().cuda()
+        torch.manual_seed(100 + k)
+        o_ref.step(**kw)
+        torch.manual_seed(100 + k)
+        zs = []
+        for s in shapes:                                   # per parameter: [momentum draw,] noise draw — the reference's order
+            if kw["resample_momentum"]:
+                zs.append(torch.empty(s).normal_().cuda())
+            zs.append(torch.empty(s).normal_().cuda())
+        with noise.inject(zs):
+            o_gpu.step(**kw)
+        for p, q in zip(p_ref, p_gpu):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(q.grad.cpu().numpy(), p.grad.numpy(), rtol=2e-6, atol=1e-7)      # weight decay folded in place
+            for name in ("tau", "g", "V_hat", "v_momentum"):
+                # tau += -tau g^2 / (V + eps) + 1 cancels to ~1e-6 per step: an ulp of g or V_hat is amplified, hence 2e-5 on tau
+                np.testing.assert_allclose(o_gpu.state[q][name].cpu().numpy(), o_ref.state[p][name].numpy(), rtol=2e-5 if name == "tau" else 2e-6,
+                                           atol=1e-7, err_msg=name)
+    # product path: Philox noise — finite, and different from step to step
+    for q in p_gpu:
+        q.grad = torch.randn_like(q)
+    before = [q.detach().clone() for q in p_gpu]
+    o_gpu.step(burn_in=False, resample_momentum=True)
+    assert all(torch.isfinite(q).all() and not torch.equal(q, b) for q, b in zip(p_gpu, before))
