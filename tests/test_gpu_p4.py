@@ -26,6 +26,29 @@ def _tf32_round_(t):
     return t
 
 
+def torch_conv_fp64(x, w, S, N, k, C, stride, pad, scale=None, shift=None, res=None, relu=False, shared_x=False):
+    """Independent reference: torch.nn.functional.conv2d in fp64 on the CPU, sample by sample.  x [S*B (or B), C, H, W], w [S, N*k*k*C]
+    packed OHWI (one weight tensor per sample) -> [S*B, N, Ho, Wo].  The TF32-exact operands make the only difference to the tensor-core
+    result its fp32 accumulation order and the final TF32 rounding of the output (rtol 1e-3 = north_star's TF32 tolerance)."""
+    import torch.nn.functional as F
+    xs = x.detach().double().cpu()
+    B = xs.shape[0] if shared_x else xs.shape[0] // S
+    outs = []
+    for s in range(S):
+        ws = w[s].detach().double().cpu().reshape(N, k, k, C).permute(0, 3, 1, 2)
+        xi = xs if shared_x else xs[s * B:(s + 1) * B]
+        y = F.conv2d(xi, ws, None, stride, pad)
+        if scale is not None:
+            y = y * scale.detach().double().cpu().reshape(1, -1, 1, 1)
+        if shift is not None:
+            y = y + shift.detach().double().cpu().reshape(1, -1, 1, 1)
+        outs.append(y)
+    y = torch.cat(outs)
+    if res is not None:
+        y = y + res.detach().double().cpu()
+    return (torch.relu(y) if relu else y).float()
+
+
 def _rand_weights(g, S, N, k, C):
     return _tf32_round_((torch.randn(S, N, k, k, C, generator=g) / (C * k * k) ** 0.5).cuda()).reshape(S, -1).contiguous()
 
@@ -80,6 +103,9 @@ def test_p4_conv_stride1(shape):
     wb = ops.p4_block_weights(w, N, C, k * k)
     got = ops.conv_p4_forward(xb, wb, S, N, k, k, 1, scale, shift, rb, True, ops.QBN_FLAG_OUT_ROUND_TF32)
     close(got.to_nchw(), ref, 1e-3, 1e-3)
+    ref64 = torch_conv_fp64(x, w, S, N, k, C, 1, pad, scale, shift, res, True)      # not our kernel: torch's conv2d in fp64
+    close(got.to_nchw(), ref64, 1e-3, 1e-3)
+    close(ref, ref64, 1e-5, 1e-5)                                                   # and the fp32 CUDA-core kernel against it
     full = got.to_nchw(keep_border=True).clone()
     full[:, :, pad:, pad:] = 0
     assert float(full.abs().max()) == 0.0 and float(got.tail().abs().max()) == 0.0       # zero border written, tail untouched
@@ -121,6 +147,7 @@ def test_p4_conv_stride2_phase_split(shape):
     got = ops.conv_p4_forward(xs, ops.p4_block_weights(w, N, C, k * k, 2), S, N, k, k, 2, scale, shift, None, False, ops.QBN_FLAG_OUT_ROUND_TF32)
     assert (got.Hp, got.Wp) == (H // 2 + 1, H // 2 + 1)
     close(got.to_nchw(), ref, 1e-3, 1e-3)
+    close(got.to_nchw(), torch_conv_fp64(x, w, S, N, k, C, 2, pad, scale, shift), 1e-3, 1e-3)
     full = got.to_nchw(keep_border=True).clone()
     full[:, :, 1:, 1:] = 0
     assert float(full.abs().max()) == 0.0
@@ -210,6 +237,7 @@ def test_p4_first_layer_sample_stacked():
     got = ops.conv_p4_forward(xm, wst, S, N, 3, 3, 1, scale, shift, None, True, ops.QBN_FLAG_OUT_ROUND_TF32 | ops.QBN_FLAG_X_SHARED_STACKED)
     assert got.n_img == S * B
     close(got.to_nchw(), ref, 1e-3, 1e-3)
+    close(got.to_nchw(), torch_conv_fp64(x, w, S, N, 3, C, 1, 1, scale, shift, None, True, shared_x=True), 1e-3, 1e-3)
     full = got.to_nchw(keep_border=True).clone()
     full[:, :, 1:, 1:] = 0
     assert float(full.abs().max()) == 0.0
@@ -306,6 +334,9 @@ def test_p4_conv_fused_shortcut(shape):
     xs = ops.P4Map.from_nchw(x, None, phase_split=True)
     got = ops.conv_p4_shortcut_forward(yb, wb, xs, S, N, 3, 3, None, shift, True, ops.QBN_FLAG_OUT_ROUND_TF32)
     close(got.to_nchw(), ref, 2e-3, 2e-3)
+    # independent fp64 reference: relu(conv3x3(y) * s2 + conv1x1/2(x) * ssc + shift)  (2e-3: the scales are folded into re-rounded weights)
+    sc64 = torch_conv_fp64(x, wsc, S, N, 1, C2, 2, 0, ssc)
+    close(got.to_nchw(), torch_conv_fp64(y, w, S, N, 3, N, 1, 1, s2, shift, sc64, True), 2e-3, 2e-3)
     full = got.to_nchw(keep_border=True).clone()
     full[:, :, 1:, 1:] = 0
     assert float(full.abs().max()) == 0.0
