@@ -45,7 +45,27 @@ def _worker(rank, world, port, ret):
     exp[0, 0] = 0.5                                                       # (1 + 0) / 2: the NaN was zeroed before the reduce
     ok3 = torch.allclose(lin.weight.grad, exp) and torch.allclose(lin.bias.grad, torch.full_like(lin.bias, 1.5))
     qd.broadcast_parameters(lin)
-    ret[rank] = bool(ok1 and ok2 and ok3)
+    # ShardedMCPredictor over a stub engine: more ranks than samples (the idle rank contributes zeros and still enters the
+    # collective), regression through the three running sums, and SGHMC member sharding (member index = sample index)
+    class _Cls:
+        regression, n_classes, model = False, K, None
+
+        def predict_sum(self, x, count, sample0=0):
+            return probs[sample0:sample0 + count].sum(0).clone()
+
+    class _Reg:
+        regression, model = True, None
+
+        def predict_sum(self, x, count, sample0=0):
+            return mu[sample0:sample0 + count].clone(), var[sample0:sample0 + count].clone()
+    xb = torch.zeros(B, 3)
+    ok4 = torch.allclose(qd.ShardedMCPredictor(_Cls()).predict(xb, 1), probs[0], atol=1e-6)           # rank 1 owns no sample
+    ok4 = ok4 and torch.allclose(qd.ShardedMCPredictor(_Cls()).predict(xb, S), probs.mean(0), atol=1e-6)
+    m2, v2 = qd.ShardedMCPredictor(_Reg()).predict(xb, S)
+    ok5 = torch.allclose(m2, mu.mean(0), atol=1e-5) and torch.allclose(v2, mu.var(0) + var.mean(0), atol=1e-4)
+    m3, v3 = qd.ShardedMCPredictor(_Reg()).predict(xb, 1)                                             # S=1 on 2 ranks: var of one draw = 0
+    ok5 = ok5 and torch.allclose(m3, mu[0], atol=1e-6)
+    ret[rank] = bool(ok1 and ok2 and ok3 and ok4 and ok5)
     dist.destroy_process_group()
 
 
