@@ -332,6 +332,43 @@ int qbn_i8_p16_to_nhwc(const int8_t* x, int64_t n_img, int H, int W, int C, int3
 int qbn_i8_p16_avgpool(const int8_t* x, int64_t n_img, int H, int W, int C, int32_t z_x, int64_t plane_rows,
                        int lo, int hi, uint8_t* out, void* stream);
 
+/* ---- A1-A3 on the planar zero-copy kernels: LRT training in TF32 mode (linear.py:32-40, conv.py:24-32 and their autograd,
+ * trainer.py:104).  The module boundary stays dense NHWC; per layer the operands are staged once into planar-C4 zero-bordered
+ * maps (phase-split for a stride-2 layer) and every contraction — forward (mean and variance side by side in TMEM), input
+ * gradient (the same kernel on flipped / transposed weights; four phase launches for a stride-2 layer), weight gradients
+ * (pixels as the reduction dimension, both operands MN-major straight from the planar maps) — runs on tcgen05 without a gather.
+ * Eligible: C_pad % 8 == 0, N % 8 == 0, N <= 256, stride 1 with an odd 'same' filter or stride 2 with 3x3 pad 1 / 1x1 pad 0.
+ * Every plane must hold ceil(rows / 128) * 128 + 128 + 2 * (Wp + 1) + 8 rows (rows = phases * n_img * Hp * Wp).            */
+/* x NHWC [n_img][H][W][C] -> x_p4 = tf32(x), xsq_p4 = tf32(x * x) (nullable), planes [C_pad/4][plane_rows][4], border (bh, bw) */
+int qbn_p4_stage_input(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
+                       long long plane_rows, float* x_p4, float* xsq_p4, void* stream);
+/* g_out, std_saved, eps (NULL -> the forward's Philox draw) NHWC [n_img][H][W][N] -> g_p4 = tf32(g), dv_p4 = tf32(g * eps / (2 std)) */
+int qbn_p4_stage_grad(const float* g_out, const float* std_saved, const float* eps, uint64_t seed, uint32_t stream_a,
+                      uint32_t stream_b, int64_t n_img, int H, int W, int N, int bh, int bw, long long plane_rows, float* g_p4,
+                      float* dv_p4, void* stream);
+/* OIHW (mu, rho | sigma) -> blocked [mu | sigma^2] operand, TF32-rounded.  mode 0: forward (input channels zero-padded to C_pad,
+ * blocked for `stride`); 1: input gradient of a stride-1 layer (taps reversed, channels swapped); 2: one phase of a stride-2
+ * layer's input gradient (parameter taps tap_list[0..n_taps)).  out: 2 * qbn_p4_weight_floats(...) floats (returned in *out_floats). */
+int qbn_lrt_p4_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int C_pad, int R, int S,
+                           int stride, int mode, const int* tap_list, int n_taps, float* out, long long* out_floats, void* stream);
+/* out = conv(x, mu) + sqrt(1e-8 + conv(x_sq, sigma^2)) .* eps + bias ; std_out = the square root.  Hp, Wp: padded extent of the
+ * OUTPUT maps.  out / std_out / eps: dense NHWC.  eps NULL -> Philox(seed, stream_a, stream_b, offset in out / 4) like qbn_lrt_fwd. */
+int qbn_lrt_conv_p4_fwd(int B, int Hp, int Wp, int C_pad, int N, int R, int S, int stride, const float* x_p4, const float* xsq_p4,
+                        long long x_plane_rows, const float* w_blocked, const float* bias, const float* eps, uint64_t seed,
+                        uint32_t stream_a, uint32_t stream_b, float* out, float* std_out, void* stream);
+/* dx = convT(g, mu) + 2 x .* convT(dv, sigma^2) of a stride-1 layer.  C: channels of g, N: channels of dx; xin, dx dense NHWC */
+int qbn_lrt_conv_p4_dgrad(int B, int Hp, int Wp, int C, int N, int R, int S, const float* g_p4, const float* dv_p4,
+                          long long g_plane_rows, const float* w_flipped_blocked, const float* xin, float* dx, void* stream);
+/* phase (a, b) of a stride-2 layer's input gradient: dx[2i+a][2j+b] = sum_t g[i + di_t][j + dj_t] * w[tap_t], shifts[t] =
+ * di_t * Wp + dj_t (di, dj in {0, 1}); xin, dx dense NHWC [B][2(Hp-1)][2(Wp-1)][N] */
+int qbn_lrt_conv_p4_dgrad_phase(int B, int Hp, int Wp, int C, int N, int n_taps, const int* shifts, int phase_a, int phase_b,
+                                const float* g_p4, const float* dv_p4, long long g_plane_rows, const float* w_phase_blocked,
+                                const float* xin, float* dx, void* stream);
+/* dmu_p / dsig2_p [N][R*S][C_real] (packed OHWI, overwritten) = sum over pixels of g (x) x and dv (x) x^2, from the planar maps */
+int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_pad, int C_real, int N, int R, int S, int stride, const float* g_p4,
+                     const float* dv_p4, long long g_plane_rows, const float* x_p4, const float* xsq_p4, long long x_plane_rows,
+                     float* dmu_p, float* dsig2_p, void* stream);
+
 /* Draw offset of the Monte-Carlo samplers, kept on the DEVICE: after qbn_set_sample_base(p) every sampler launch
  * (qbn_sample_weights*, qbn_i8_sample_weights, qbn_dropout_masks_multi, qbn_i8_dropout_mc) uses the Philox stream index
  * *p + sample0 + s instead of sample0 + s, reading *p when the kernel runs.  One captured CUDA graph then serves every batch
@@ -376,12 +413,6 @@ int qbn_maxpool2x2(const float* x, int64_t B, int H, int W, int C, float* out, v
 int qbn_avgpool_all(const float* x, int64_t B, int HW, int C, float divisor /* <=0: HW */, float* out, void* stream);
 /* NCHW <-> NHWC (entry/exit of the NHWC domain) */
 int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float* out, void* stream);
-
-/* Diagnostic: per-instruction cycle costs of tcgen05 fence / commit / mma / ld on this device (one
- * CTA); out_dev receives 12 counters.  Used to size the kernel pipelines, no product use. */
-int qbn_ubench_tcgen05(unsigned long long* out_dev, int n_cols, int reps, void* stream);
-/* same, with ctas_per_sm resident CTAs of n_warps MMA issuer warps each (cross-CTA overlap of the tensor pipe) */
-int qbn_ubench_tcgen05_multi(unsigned long long* out_dev, int n_cols, int reps, int ctas_per_sm, int n_warps, void* stream);
 
 #ifdef __cplusplus
 }

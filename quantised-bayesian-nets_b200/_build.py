@@ -9,9 +9,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libqbn.so")
-SOURCES = ["core.cu", "gemm_fp32.cu", "i8_conv.cu", "i8_p16.cu", "reduce.cu", "umma_conv.cu", "umma_conv_s1.cu", "umma_conv_p4.cu", "umma_wgrad.cu", "ubench.cu"]
+SOURCES = ["core.cu", "gemm_fp32.cu", "i8_conv.cu", "i8_p16.cu", "reduce.cu", "umma_conv.cu", "umma_conv_s1.cu", "umma_conv_p4.cu", "umma_wgrad.cu", "umma_wgrad_p4.cu", "lrt_p4.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
+if os.environ.get("QBN_TUNING"):          # kernel-tuning builds only: environment knobs / cycle accounting (scripts/p4_sweep.sh)
+    NVCC_FLAGS.append("-DQBN_TUNING")
 
 
 def _nvcc():

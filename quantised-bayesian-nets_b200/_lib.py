@@ -97,8 +97,6 @@ _SIGNATURES = {
     "qbn_reg_mc_reduce": (c_int, [P, P, c_int, c_int64, P, P, P]),
     "qbn_cls_metrics": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P]),
     "qbn_reg_metrics": (c_int, [P, P, P, c_int64, P, P]),
-    "qbn_ubench_tcgen05": (c_int, [P, c_int, c_int, P]),
-    "qbn_ubench_tcgen05_multi": (c_int, [P, c_int, c_int, c_int, c_int, P]),
     "qbn_maxpool2x2": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "qbn_avgpool_all": (c_int, [P, c_int64, c_int, c_int, c_float, P, P]),
     "qbn_conv_s1_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P]),
@@ -114,6 +112,17 @@ _SIGNATURES = {
                                          c_int64, P]),
     "qbn_kl_multi": (c_int, [P, c_int, c_int64, P, c_float, P]),
     "qbn_dropout_masks_multi": (c_int, [P, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, P]),
+    "qbn_p4_stage_input": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P]),
+    "qbn_p4_stage_grad": (c_int, [P, P, P, c_uint64, c_uint32, c_uint32, c_int64, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P]),
+    "qbn_lrt_p4_weight_prep": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, P,
+                                       POINTER(ctypes.c_longlong), P]),
+    "qbn_lrt_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, c_uint64, c_uint32,
+                                    c_uint32, P, P, P]),
+    "qbn_lrt_conv_p4_dgrad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, P]),
+    "qbn_lrt_conv_p4_dgrad_phase": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, P, P, ctypes.c_longlong, P,
+                                            P, P, P]),
+    "qbn_lrt_wgrad_p4": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, ctypes.c_longlong,
+                                 P, P, P]),
     "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int64, c_int, c_float, P, P]),
 }
 

@@ -887,29 +887,6 @@ extern "C" int qbn_nchw_to_nhwc(const float* x, int64_t B, int C, int HW, float*
 // ---------------------------------------------------------------------------------------------
 #include "p4_layout.cuh"
 
-struct P4Block { int N, C, taps, CB, cbc, n_pad, K; int64_t total4; };
-static bool p4_block_geom(int N, int C, int taps, int stride, P4Block& g, int cb_override = 0) {
-  g.N = N; g.C = C; g.taps = taps; g.CB = cb_override > 0 ? cb_override : qbn_p4_block_channels(C, stride, taps);
-  if (g.CB > 0 && (C % g.CB != 0 || g.CB % 8 != 0)) return false;
-  if (C % 8 != 0 || g.CB == 0 || N > 256 || N <= 0 || taps <= 0) return false;
-  g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(N); g.K = taps * C;
-  g.total4 = (int64_t)(C / g.CB) * taps * g.cbc * g.n_pad;
-  return true;
-}
-// blocked float4 index -> canonical OHWI element index (or -1 for the zero rows n >= N).  32-bit arithmetic: a layer's
-// blocked tensor has < 2^31 chunks (64-bit divisions were most of the sampler's instructions)
-__device__ __forceinline__ int64_t p4_canonical(const P4Block& g, int64_t i64) {
-  const uint32_t i = (uint32_t)i64;
-  const uint32_t t1 = i / (uint32_t)g.n_pad;
-  const uint32_t n = i - t1 * (uint32_t)g.n_pad;
-  const uint32_t t2 = t1 / (uint32_t)g.cbc;
-  const uint32_t j = t1 - t2 * (uint32_t)g.cbc;
-  const uint32_t cb = t2 / (uint32_t)g.taps;
-  const uint32_t t = t2 - cb * (uint32_t)g.taps;
-  if ((int)n >= g.N) return -1;
-  return (int64_t)n * g.K + (int64_t)t * g.C + cb * g.CB + 4 * j;
-}
-
 __global__ void p4_block_weights_kernel(const float* __restrict__ w, P4Block g, float* __restrict__ out) {
   const float* ws = w + (int64_t)blockIdx.y * g.N * g.K;
   float4* os = reinterpret_cast<float4*>(out) + (int64_t)blockIdx.y * g.total4;

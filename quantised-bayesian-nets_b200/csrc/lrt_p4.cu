@@ -1,0 +1,218 @@
+// Staging for the planar LRT training kernels (umma_conv_p4.cu KIND_LRT, umma_wgrad_p4.cu): the module boundary is dense NHWC
+// (ops.LRTFunction), the tcgen05 kernels read planar-C4 zero-bordered maps (p4_layout.cuh).
+//   * qbn_p4_stage_input : x NHWC -> planar x and x^2 (TF32-rounded, RNA), phase-split for a stride-2 layer (SURVEY 8a A1/A2:
+//                          the two operands of linear.py:32-35 / conv.py:24-27)
+//   * qbn_p4_stage_grad  : g NHWC (+ std, eps) -> planar g and dv = g * eps / (2 std)   (d out / d var)
+//   * qbn_lrt_p4_weight_prep : OIHW (mu, rho) -> the blocked [mu | sigma^2] operand of the forward, of the flipped / transposed
+//                          input-gradient convolution, or of one phase of a stride-2 layer's input gradient
+// Every kernel writes its whole output (borders, padding channels and the zero tail included): buffers come from torch.empty.
+#include <string.h>
+#include "common.cuh"
+#include "p4_layout.cuh"
+
+namespace {
+
+struct StageGeom {
+  int H, W, C, chunks;               // NHWC tensor: [n_img][H][W][C]; chunks = planes written (C_pad / 4)
+  int Hp, Wp, bh, bw, split;         // planar maps
+  uint32_t map_rows, body_rows;      // Hp * Wp ; phases * n_img * Hp * Wp
+  uint32_t n_img_rows;               // n_img * Hp * Wp (rows of one phase)
+  long long plane_rows;
+};
+
+// row of a chunk plane -> NHWC pixel index, or -1 for border / tail rows
+__device__ __forceinline__ long long stage_pixel(const StageGeom& g, uint32_t r) {
+  if (r >= g.body_rows) return -1;
+  uint32_t ph = 0;
+  if (g.split) { ph = r / g.n_img_rows; r -= ph * g.n_img_rows; }
+  const uint32_t img = r / g.map_rows;
+  const uint32_t rem = r - img * g.map_rows;
+  const int hh = (int)(rem / (uint32_t)g.Wp), ww = (int)(rem - (uint32_t)hh * (uint32_t)g.Wp);
+  if (hh < g.bh || ww < g.bw) return -1;
+  int h = hh - g.bh, w = ww - g.bw;
+  if (g.split) { h = 2 * h + (int)(ph >> 1); w = 2 * w + (int)(ph & 1); }
+  return ((long long)img * g.H + h) * g.W + w;
+}
+
+__device__ __forceinline__ float4 ld4_guard(const float* base, long long pix, int C, int c0) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* p = base + pix * C + c0;
+  if ((C & 3) == 0) {
+    if (c0 < C) v = *reinterpret_cast<const float4*>(p);
+  } else {
+    if (c0 + 0 < C) v.x = p[0];
+    if (c0 + 1 < C) v.y = p[1];
+    if (c0 + 2 < C) v.z = p[2];
+    if (c0 + 3 < C) v.w = p[3];
+  }
+  return v;
+}
+
+__global__ void p4_stage_input_kernel(const float* __restrict__ x, StageGeom g, float4* __restrict__ xp, float4* __restrict__ xsq) {
+  const long long total = (long long)g.chunks * g.plane_rows;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / g.plane_rows);
+    const uint32_t r = (uint32_t)(i - (long long)j * g.plane_rows);
+    const long long pix = stage_pixel(g, r);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), q = v;
+    if (pix >= 0) {
+      v = ld4_guard(x, pix, g.C, 4 * j);
+      q = make_float4(tf32_round(__fmul_rn(v.x, v.x)), tf32_round(__fmul_rn(v.y, v.y)), tf32_round(__fmul_rn(v.z, v.z)), tf32_round(__fmul_rn(v.w, v.w)));
+      v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+    }
+    xp[i] = v;
+    if (xsq) xsq[i] = q;
+  }
+}
+
+__global__ void p4_stage_grad_kernel(const float* __restrict__ gout, const float* __restrict__ sd, const float* __restrict__ eps, StageGeom g,
+                                     uint64_t seed, uint32_t sa, uint32_t sb, float4* __restrict__ gp, float4* __restrict__ dvp) {
+  const long long total = (long long)g.chunks * g.plane_rows;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / g.plane_rows);
+    const uint32_t r = (uint32_t)(i - (long long)j * g.plane_rows);
+    const long long pix = stage_pixel(g, r);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), d = v;
+    if (pix >= 0) {
+      const long long off = pix * g.C + 4 * j;
+      v = *reinterpret_cast<const float4*>(gout + off);
+      const float4 s = *reinterpret_cast<const float4*>(sd + off);
+      float e[4];
+      if (eps) {
+        const float4 t = *reinterpret_cast<const float4*>(eps + off);
+        e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+      } else {
+        philox_normal4(seed, sa, sb, (uint64_t)(off >> 2), e);      // the forward's draw: counter = offset in out / 4
+      }
+      // lrt_dv_kernel's expression (gemm_fp32.cu): g * eps / (2 std)
+      d = make_float4(tf32_round(v.x * e[0] / (2.0f * s.x)), tf32_round(v.y * e[1] / (2.0f * s.y)), tf32_round(v.z * e[2] / (2.0f * s.z)),
+                      tf32_round(v.w * e[3] / (2.0f * s.w)));
+      v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+    }
+    gp[i] = v;
+    dvp[i] = d;
+  }
+}
+
+static int stage_geom(StageGeom& g, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int split, long long plane_rows) {
+  memset(&g, 0, sizeof(g));
+  g.H = H; g.W = W; g.C = C; g.chunks = C_pad / 4; g.bh = bh; g.bw = bw; g.split = split ? 1 : 0;
+  if (split) {
+    if ((H & 1) || (W & 1) || bh != 1 || bw != 1) { qbn_set_error("phase-split staging needs even H, W and a (1, 1) border"); return QBN_ERR_INVALID_ARG; }
+    g.Hp = H / 2 + 1; g.Wp = W / 2 + 1;
+  } else {
+    g.Hp = H + bh; g.Wp = W + bw;
+  }
+  const long long body = (long long)(split ? 4 : 1) * n_img * g.Hp * g.Wp;
+  if (body >= (1ll << 31) || plane_rows < body) { qbn_set_error("staging: plane of %lld rows for %lld map rows", plane_rows, body); return QBN_ERR_INVALID_ARG; }
+  g.map_rows = (uint32_t)(g.Hp * g.Wp); g.n_img_rows = (uint32_t)(n_img * g.Hp * g.Wp); g.body_rows = (uint32_t)body;
+  g.plane_rows = plane_rows;
+  return QBN_OK;
+}
+
+}  // namespace
+
+extern "C" int qbn_p4_stage_input(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
+                                  long long plane_rows, float* x_p4, float* xsq_p4, void* stream) {
+  QBN_CHECK_ARG(x && x_p4, "null pointer");
+  QBN_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && C > 0 && C_pad >= C && C_pad % 4 == 0 && bh >= 0 && bw >= 0, "sizes");
+  StageGeom g;
+  int rc = stage_geom(g, n_img, H, W, C, C_pad, bh, bw, phase_split, plane_rows);
+  if (rc != QBN_OK) return rc;
+  const long long total = (long long)g.chunks * plane_rows;
+  p4_stage_input_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, g, reinterpret_cast<float4*>(x_p4), reinterpret_cast<float4*>(xsq_p4));
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+extern "C" int qbn_p4_stage_grad(const float* g_out, const float* std_saved, const float* eps, uint64_t seed, uint32_t stream_a,
+                                 uint32_t stream_b, int64_t n_img, int H, int W, int N, int bh, int bw, long long plane_rows, float* g_p4,
+                                 float* dv_p4, void* stream) {
+  QBN_CHECK_ARG(g_out && std_saved && g_p4 && dv_p4, "null pointer");
+  QBN_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && N > 0 && N % 4 == 0 && bh >= 0 && bw >= 0, "sizes (N % 4 == 0)");
+  StageGeom g;
+  int rc = stage_geom(g, n_img, H, W, N, N, bh, bw, 0, plane_rows);
+  if (rc != QBN_OK) return rc;
+  const long long total = (long long)g.chunks * plane_rows;
+  p4_stage_grad_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g_out, std_saved, eps, g, seed, stream_a, stream_b,
+                                                                                  reinterpret_cast<float4*>(g_p4), reinterpret_cast<float4*>(dv_p4));
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+namespace {
+
+struct WPrep {
+  P4Block g;                  // geometry of the blocked OUTPUT
+  int N, C, taps;             // the layer's parameters: OIHW [N][C][taps]
+  int transposed;             // output row n' = input channel c, output channel c' = output channel n (input gradient)
+  int tap_map[25];            // output tap -> parameter tap
+  int second_is_sigma;
+};
+
+// one thread = one float4 of the blocked tensor, for both halves ([mu | sigma^2])
+__global__ void lrt_p4_weight_prep_kernel(const float* __restrict__ mu, const float* __restrict__ second, WPrep w, float4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < w.g.total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = p4_canonical(w.g, i);            // n' * K + t' * C' + c'   (c' a multiple of 4)
+    float m[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (idx >= 0) {
+      const int np = (int)(idx / w.g.K);
+      const int rem = (int)(idx - (int64_t)np * w.g.K);
+      const int tp = rem / w.g.C, cp = rem - tp * w.g.C;
+      const int t = w.tap_map[tp];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int n = w.transposed ? cp + k : np, c = w.transposed ? np : cp + k;
+        if (n < w.N && c < w.C) {
+          const int64_t src = ((int64_t)n * w.C + c) * w.taps + t;
+          const float sg = w.second_is_sigma ? second[src] : softplus_f(second[src]);
+          m[k] = tf32_round(mu[src]);
+          s2[k] = tf32_round(__fmul_rn(sg, sg));
+        }
+      }
+    }
+    out[i] = make_float4(m[0], m[1], m[2], m[3]);
+    out[w.g.total4 + i] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  }
+}
+
+}  // namespace
+
+// mode 0: forward operand, output channels N, input channels C_pad (channels >= C are zero), taps R*S, blocked for `stride`.
+// mode 1: input gradient of a stride-1 layer: rows = the layer's input channels, K = its output channels, taps reversed.
+// mode 2: one phase of a stride-2 layer's input gradient: like mode 1 with the taps `tap_list[0..n_taps)` (parameter tap indices).
+// out: 2 x qbn_p4_weight_floats(...) floats — the mu blocks, then the sigma^2 blocks (sigma = softplus(rho) or `second` itself).
+extern "C" int qbn_lrt_p4_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int C_pad, int R, int S,
+                                      int stride, int mode, const int* tap_list, int n_taps, float* out, long long* out_floats, void* stream) {
+  QBN_CHECK_ARG(mu && second && out, "null pointer");
+  QBN_CHECK_ARG(N > 0 && C > 0 && R > 0 && S > 0 && R * S <= 25 && mode >= 0 && mode <= 2, "sizes / mode");
+  WPrep w;
+  memset(&w, 0, sizeof(w));
+  w.N = N; w.C = C; w.taps = R * S; w.second_is_sigma = second_is_sigma;
+  bool ok;
+  if (mode == 0) {
+    QBN_CHECK_ARG(C_pad >= C, "C_pad");
+    ok = p4_block_geom(N, C_pad, R * S, stride, w.g);
+    for (int t = 0; t < R * S; ++t) w.tap_map[t] = t;
+  } else if (mode == 1) {
+    w.transposed = 1;
+    ok = p4_block_geom(C, N, R * S, 1, w.g);
+    for (int t = 0; t < R * S; ++t) w.tap_map[t] = R * S - 1 - t;
+  } else {
+    QBN_CHECK_ARG(tap_list && n_taps > 0 && n_taps <= 4, "tap list");
+    w.transposed = 1;
+    ok = p4_block_geom(C, N, n_taps, 1, w.g);
+    for (int t = 0; t < n_taps; ++t) {
+      QBN_CHECK_ARG(tap_list[t] >= 0 && tap_list[t] < R * S, "tap index");
+      w.tap_map[t] = tap_list[t];
+    }
+  }
+  if (!ok) {
+    qbn_set_error("qbn_lrt_p4_weight_prep: no blocking (mode %d N=%d C=%d C_pad=%d)", mode, N, C, C_pad);
+    return QBN_ERR_UNSUPPORTED;
+  }
+  if (out_floats) *out_floats = 2 * w.g.total4 * 4;
+  lrt_p4_weight_prep_kernel<<<qbn_grid_for(w.g.total4, 256), 256, 0, (cudaStream_t)stream>>>(mu, second, w, reinterpret_cast<float4*>(out));
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

@@ -11,6 +11,7 @@
 // Sampled weights, "blocked":  [sample][channel block cb][tap t][chunk j][n_pad rows][4 floats] — every
 // (cb, tap) block is already the smem image of the B operand, so it is one bulk copy too.
 #pragma once
+#include <stdint.h>
 
 // channels per block: whole C up to 32, else the first of {32, 16, 24, 8} dividing C — small enough that two
 // CTAs (two tcgen05 issuers) share an SM even when the whole sampled tensor of a 48-channel layer is resident.
@@ -29,6 +30,31 @@ static __host__ __device__ inline int qbn_p4_block_channels(int C, int stride = 
   return 0;
 }
 static __host__ __device__ inline int qbn_p4_n_pad(int N) { return (N + 15) / 16 * 16; }
+
+// geometry of one blocked weight tensor (shared by the blocker, the samplers and the LRT weight preparation)
+struct P4Block { int N, C, taps, CB, cbc, n_pad, K; int64_t total4; };
+static inline bool p4_block_geom(int N, int C, int taps, int stride, P4Block& g, int cb_override = 0) {
+  g.N = N; g.C = C; g.taps = taps; g.CB = cb_override > 0 ? cb_override : qbn_p4_block_channels(C, stride, taps);
+  if (g.CB > 0 && (C % g.CB != 0 || g.CB % 8 != 0)) return false;
+  if (C % 8 != 0 || g.CB == 0 || N > 256 || N <= 0 || taps <= 0) return false;
+  g.cbc = g.CB / 4; g.n_pad = qbn_p4_n_pad(N); g.K = taps * C;
+  g.total4 = (int64_t)(C / g.CB) * taps * g.cbc * g.n_pad;
+  return true;
+}
+// blocked float4 index -> canonical OHWI element index (or -1 for the zero rows n >= N).  32-bit arithmetic: a layer's
+// blocked tensor has < 2^31 chunks (64-bit divisions were most of the sampler's instructions)
+static __host__ __device__ __forceinline__ int64_t p4_canonical(const P4Block& g, int64_t i64) {
+  const uint32_t i = (uint32_t)i64;
+  const uint32_t t1 = i / (uint32_t)g.n_pad;
+  const uint32_t n = i - t1 * (uint32_t)g.n_pad;
+  const uint32_t t2 = t1 / (uint32_t)g.cbc;
+  const uint32_t j = t1 - t2 * (uint32_t)g.cbc;
+  const uint32_t cb = t2 / (uint32_t)g.taps;
+  const uint32_t t = t2 - cb * (uint32_t)g.taps;
+  if ((int)n >= g.N) return -1;
+  return (int64_t)n * g.K + (int64_t)t * g.C + cb * g.CB + 4 * j;
+}
+
 
 // ---- int8 twin, "planar C16": the same byte layout with 16 s8 channels per 16-byte chunk; maps hold (q - zero_point), so the
 // shared zero border is the padding of a quint8 convolution.  Channel counts are zero-padded to a multiple of 32 (one kind::i8

@@ -22,6 +22,13 @@
 #include <string.h>
 #include "umma_common.cuh"
 
+// tuning knobs exist only in -DQBN_TUNING builds: the product library reads nothing from the environment
+#ifdef QBN_TUNING
+static inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+static inline const char* tune_env(const char*) { return nullptr; }
+#endif
+
 namespace {
 
 constexpr int UM = 128;          // rows per CTA tile = TMEM lanes
@@ -461,7 +468,7 @@ static int launch_umma(UParams& p, int n_samples, cudaStream_t st, const char* w
   // The kernel is not persistent and its epilogue does not overlap its main loop, so co-resident CTAs are what keeps an SM busy:
   // size the ring for TWO CTAs per SM when at least two stages fit in half the shared memory (else one CTA with a deeper ring).
   int stages = (int)((110 * 1024) / stage_bytes);
-  if (getenv("QBN_V1_DEEP") || stages < 2) stages = (int)((200 * 1024) / stage_bytes);
+  if (tune_env("QBN_V1_DEEP") || stages < 2) stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages > num_kb) stages = num_kb;
   if (stages < 1) {

@@ -26,6 +26,14 @@
 
 namespace {
 
+// kernel-tuning knobs (QBN_P4_OCC / _TG / _SA / _ACC / _VERBOSE / _PROF) exist only in -DQBN_TUNING builds (QBN_TUNING=1 python -m
+// ..._build; scripts/p4_sweep.sh): the product library reads nothing from the environment
+#ifdef QBN_TUNING
+static inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+static inline const char* tune_env(const char*) { return nullptr; }
+#endif
+
 constexpr int TM = 128;
 constexpr int P4_THREADS = 192;
 constexpr int MAX_TAPS = 25;
@@ -55,8 +63,21 @@ struct P4Params {
   int has_add, z_res, z_add, add_lo, add_hi, z_fin;   // quantized::add[_relu] with the residual, then stored as q - z_fin
   float s_a, p_a, s_b, p_b, inv_s_add;
   int32_t* acc_dump;                              // optional [rows][N] int32 accumulators (tests)
+  // ---- LRT (KIND_LRT): two contractions per tile, mean = x * mu and var = x^2 * sigma^2 (linear.py:32-35, conv.py:24-27), side by
+  // side in TMEM.  The second operand pair enters as n_cb more channel blocks: x_sq planes and the sigma^2 blocks that follow the
+  // mu blocks in the weight tensor.  lrt_mode 0: out = mean + sqrt(1e-8 + var) * eps + bias, out2 = sqrt(1e-8 + var).
+  // lrt_mode 1 (input gradient, SURVEY 8a A3: the operands are g and dv, the weights flipped/transposed):
+  // out = acc0 + 2 * xin .* acc1 (+ residual).
+  int dual, acc_cols, lrt_mode;
+  const float* x_sq; const float* eps; const float* xin; float* out2;
+  long long aux_plane;                            // rows per chunk plane of eps / xin / out2 (the output's geometry)
+  unsigned long long seed; uint32_t stream_a, stream_b;
+  // module boundary (ops.LRTFunction): out / out2 / eps / xin are dense NHWC [B][H_out][W_out][N] tensors; the padded pixel
+  // (b, hh, ww) of this launch's geometry is the NHWC pixel (b, (hh - bh) * oh_mul + oh_add, (ww - bw) * ow_mul + ow_add)
+  // (mul 2 / add phase: the four phase launches of a stride-2 layer's input gradient)
+  int nhwc, H_out, W_out, oh_mul, oh_add, ow_mul, ow_add;
 };
-enum { KIND_TF32 = 0, KIND_I8 = 1 };
+enum { KIND_TF32 = 0, KIND_I8 = 1, KIND_LRT = 2 };
 
 // cycle accounting of CTA 0 (QBN_P4_PROF=1): [role*8 + category], summed over its tiles
 __device__ unsigned long long g_p4_prof[32];
@@ -151,7 +172,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         PROF_BEGIN();
         if (p.b_res && z != cur_z) {
           mbar_wait(smem_u32(&b_empty[0]), pb ^ 1);          // MMAs of the previous sample have retired
-          const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * p.taps) + p.bt2_bytes * (uint32_t)p.n_cb2;
+          const uint32_t total = p.bt_bytes * (uint32_t)(p.n_cb * (p.dual ? 2 : 1) * p.taps) + p.bt2_bytes * (uint32_t)p.n_cb2;
           mbar_arrive_expect_tx(smem_u32(&b_full[0]), total);
           for (uint32_t off = 0; off < total; off += 32768u)
             bulk_load_g2s(smem_u32(b_ring) + off, reinterpret_cast<const uint8_t*>(ws) + off, min(32768u, total - off), smem_u32(&b_full[0]));
@@ -165,7 +186,10 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         const long long hi = (g0 + p.RA > lim) ? lim : g0 + p.RA;
         const uint32_t row_bytes = (uint32_t)(hi - lo) * 16;
         const uint32_t dst_off = (uint32_t)(lo - g0) * 16;
-        for (int cb = 0; cb < p.n_cb; ++cb) {
+        const int n_cb_all = p.dual ? 2 * p.n_cb : p.n_cb;     // LRT: the x^2 blocks follow the x blocks
+        for (int cb = 0; cb < n_cb_all; ++cb) {
+          const float* xsrc = cb >= p.n_cb ? p.x_sq : p.x;
+          const int cbl = cb >= p.n_cb ? cb - p.n_cb : cb;
           PROF_ADD(16);
           mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
           PROF_ADD(17);
@@ -173,7 +197,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
           mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(p.cbc * p.n_strips));
           const uint32_t slot = smem_u32(a_ring + (size_t)sa * p.a_bytes) + dst_off;
           for (int s2 = 0; s2 < p.n_strips; ++s2) {
-            const float* src = p.x + ((size_t)(cb * p.cbc) * p.x_plane + (size_t)s2 * p.strip_rows + lo) * 4;
+            const float* src = xsrc + ((size_t)(cbl * p.cbc) * p.x_plane + (size_t)s2 * p.strip_rows + lo) * 4;
             for (int j = 0; j < p.cbc; ++j)
               bulk_load_g2s(slot + (uint32_t)s2 * strip_bytes + (uint32_t)(j * p.RA_p) * 16, src + (size_t)j * p.x_plane * 4, row_bytes, bar);
           }
@@ -241,9 +265,11 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         PROF_ADD(8);
         mbar_wait(smem_u32(&acc_empty[as]), pacc ^ 1);      // epilogue has drained this accumulator
         PROF_ADD(9);
-        const uint32_t tacc = tmem_base + (uint32_t)(as * p.n_pad);
+        uint32_t tacc = tmem_base + (uint32_t)(as * p.acc_cols);
         uint32_t accum = 0;
-        for (int cb = 0; cb < p.n_cb; ++cb) {
+        const int n_cb_all = p.dual ? 2 * p.n_cb : p.n_cb;
+        for (int cb = 0; cb < n_cb_all; ++cb) {
+          if (p.dual && cb == p.n_cb) { tacc += (uint32_t)p.n_pad; accum = 0; }      // second accumulator: the variance contraction
           mbar_wait(smem_u32(&a_full[sa]), pa);
           PROF_ADD(10);
           tc_fence_after();
@@ -346,6 +372,79 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         orow = (long long)((h & 1) * 2 + (w & 1)) * p.q2_total + ((long long)(z * p.B + (int)b) * p.Hp2 + (h >> 1) + 1) * p.Wp2 + (w >> 1) + 1;
         store = interior;                                   // its border is never written (pre-zeroed buffer)
       }
+      if constexpr (KIND == KIND_LRT) {
+        // ---- LRT training: acc0 = columns [0, n_pad), acc1 = [n_pad, 2 n_pad) of this accumulator slot.
+        long long out_off, aux_off, aux_step, out_step, res_step;      // float offsets of chunk 0 / steps between chunks
+        unsigned long long ctr0;                                       // Philox counter of chunk 0 (the existing NHWC path's: out offset / 4)
+        if (p.nhwc) {
+          const long long pix = ((long long)b * p.H_out + ((int)hh - p.bh) * p.oh_mul + p.oh_add) * p.W_out + ((int)ww - p.bw) * p.ow_mul + p.ow_add;
+          store = interior;
+          out_off = aux_off = interior ? pix * p.N : 0;
+          aux_step = out_step = res_step = 4;
+          ctr0 = (unsigned long long)pix * (unsigned long long)n_chunks;
+        } else {
+          out_off = (store ? orow : 0) * 4; aux_off = in_row * 4;
+          aux_step = p.aux_plane * 4; out_step = p.out_plane * 4; res_step = p.res_plane * 4;
+          ctr0 = (unsigned long long)in_row * (unsigned long long)n_chunks;
+        }
+        float* optr = p.out + out_off;
+        float* o2 = (p.out2 && store) ? p.out2 + aux_off : nullptr;
+        const float* eptr = (p.eps && interior) ? p.eps + aux_off : nullptr;
+        const float* xptr = (p.xin && interior) ? p.xin + aux_off : nullptr;
+        const float* rptr = (p.residual && interior) ? p.residual + aux_off : nullptr;
+        uint32_t v0[16], v1[16];
+        PROF_ADD(0);
+        warp_wait(&acc_full[as], pacc, lane);
+        PROF_ADD(1);
+        tc_fence_after();
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.acc_cols);
+        for (int g = 0; g < n_groups; ++g) {
+          tmem_ld16(tlane + (uint32_t)(g * 16), v0);
+          tmem_ld16(tlane + (uint32_t)(p.n_pad + g * 16), v1);
+          tmem_ld_wait();
+          if (g + 1 == n_groups) {                              // accumulators fully read: hand the slot back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+          }
+          PROF_ADD(2);
+          if (store) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int ch = g * 4 + i;
+              if (ch < n_chunks) {
+                float o[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
+                if (interior) {
+                  if (p.lrt_mode == 0) {
+                    float e[4];
+                    if (eptr) {
+                      const float4 t = ld_nc4(eptr + (long long)ch * aux_step);
+                      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+                    } else {      // one Philox call = the four channels of this chunk; the backward regenerates the same draw
+                      philox_normal4(p.seed, p.stream_a, p.stream_b, ctr0 + (unsigned long long)ch, e);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      sd[k] = sqrtf(__fadd_rn(1e-8f, __uint_as_float(v1[4 * i + k])));
+                      o[k] = __fadd_rn(__fadd_rn(__uint_as_float(v0[4 * i + k]), __fmul_rn(sd[k], e[k])), s_shift[ch * 4 + k]);
+                    }
+                  } else {
+                    const float4 xi = xptr ? ld_nc4(xptr + (long long)ch * aux_step) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 rr = rptr ? ld_nc4(rptr + (long long)ch * res_step) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float xv[4] = {xi.x, xi.y, xi.z, xi.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)      // dx = g*mu + 2x .* (dv*sigma^2) (+ the gradient that reached x through another branch)
+                      o[k] = __fadd_rn(__fadd_rn(__uint_as_float(v0[4 * i + k]), __fmul_rn(__fmul_rn(2.0f, xv[k]), __uint_as_float(v1[4 * i + k]))), rv[k]);
+                  }
+                }
+                *reinterpret_cast<float4*>(optr + (long long)ch * out_step) = make_float4(o[0], o[1], o[2], o[3]);
+                if (o2) *reinterpret_cast<float4*>(o2 + (long long)ch * aux_step) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+              }
+            }
+          }
+          PROF_ADD(3);
+        }
+      } else
       if constexpr (I8) {
         // ---- int8: one TMEM column group = 16 output channels = ONE 16-byte chunk of the planar-C16 s8 map.
         // FBGEMM's ReQuantizeOutput with a float bias (conv_q.py:120-125): every fp32 step rounded separately (no FMA).
@@ -364,7 +463,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         warp_wait(&acc_full[as], pacc, lane);
         PROF_ADD(1);
         tc_fence_after();
-        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.acc_cols);
         // column N of the accumulator = sum_k (x - z_x) (an all-ones weight row): the z_w correction of sum (x-z_x)(w-z_w)
         int corr = 0;
         if (p.z_w != 0) {
@@ -471,7 +570,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
       warp_wait(&acc_full[as], pacc, lane);
       PROF_ADD(1);
       tc_fence_after();
-      const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
+      const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.acc_cols);
       tmem_ld16(tlane, v);
       float* oc = optr;                                      // output pointer of the current chunk
       int jc = 0, sidx = 0;                                  // channel chunk inside the sample / stacked sample
@@ -568,10 +667,18 @@ struct P4I8 {                                        // int8 extras of a launch 
   float s_a, p_a, s_b, p_b, inv_s_add;
   int32_t* acc_dump;
 };
+struct P4LRT {                                       // LRT extras of a launch (NULL: eval)
+  int mode;                                          // 0 forward, 1 input gradient
+  const float* x_sq; const float* eps; const float* xin; float* out2; long long aux_plane;
+  unsigned long long seed; uint32_t stream_a, stream_b;
+  int nhwc, H_out, W_out, oh_mul, oh_add, ow_mul, ow_add;      // dense NHWC out / out2 / eps / xin (see P4Params)
+  int n_taps;                                        // > 0: explicit tap list on maps with a (1, 1) border: tap t reads row q + shift[t] >= q
+  int shift[MAX_TAPS];
+};
 static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
                           int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
                           float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream,
-                          const P4I8* i8 = nullptr);
+                          const P4I8* i8 = nullptr, const P4LRT* lrt = nullptr);
 
 extern "C" int qbn_conv_p4_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x,
                                long long x_plane_rows, const float* w, int w_shared, const float* scale, const float* shift,
@@ -611,12 +718,13 @@ extern "C" int qbn_conv_p4_shortcut_fwd(int n_samples, int B, int Hp, int Wp, in
 static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* w,
                           int w_shared, const float* scale, const float* shift, const float* residual, const float* out_mask,
                           float out_mask_mult, int flags, float* out, const float* x2, int C2, int CB2, P4Planes pl, void* stream,
-                          const P4I8* i8) {
+                          const P4I8* i8, const P4LRT* lrt) {
   cudaStream_t st = (cudaStream_t)stream;
   QBN_CHECK_ARG(x && w && out, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && Hp > 2 && Wp > 2 && C > 0 && N > 0 && R > 0 && S > 0, "sizes");
   const int E = i8 ? 16 : 4;                       // channels per 16-byte K-chunk
   const int CB = i8 ? qbn_p16_block_channels(C, stride, R * S) : qbn_p4_block_channels(C, stride, R * S);
+  const bool ct = lrt && lrt->n_taps > 0;           // explicit taps (phase launches of a stride-2 input gradient): R x S = 1 x n_taps
   const bool s1 = stride == 1 && (R & 1) && (S & 1);
   const bool s2 = stride == 2 && ((R == 3 && S == 3) || (R == 1 && S == 1));
   if (i8 && (C % 32 != 0 || CB == 0 || N + 1 > 256 || !(s1 || s2) || R * S > MAX_TAPS || x2 || out_mask || (flags & QBN_FLAG_X_SHARED_STACKED))) {
@@ -624,7 +732,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
                   "(C=%d N=%d R=%d S=%d stride=%d)", C, N, R, S, stride);
     return QBN_ERR_UNSUPPORTED;
   }
-  if (!i8 && (C % 8 != 0 || CB == 0 || N % 4 != 0 || N > 256 || !(s1 || s2) || R * S > MAX_TAPS)) {
+  if (!i8 && (C % 8 != 0 || CB == 0 || N % 4 != 0 || N > 256 || !(s1 || s2 || ct) || R * S > MAX_TAPS)) {
     qbn_set_error("qbn_conv_p4_fwd: needs C %% 8 == 0, N %% 4 == 0, N <= 256 and stride 1 (odd kernel) or stride 2 (3x3 / 1x1) "
                   "(C=%d N=%d R=%d S=%d stride=%d)", C, N, R, S, stride);
     return QBN_ERR_UNSUPPORTED;
@@ -647,8 +755,17 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     p.s_a = i8->s_a; p.p_a = i8->p_a; p.s_b = i8->s_b; p.p_b = i8->p_b; p.inv_s_add = i8->inv_s_add; p.acc_dump = i8->acc_dump;
     p.n_out_chunks = (N + 15) / 16;
   }
-  p.bh = s1 ? (R - 1) / 2 : 1;
-  p.bw = s1 ? (S - 1) / 2 : 1;
+  if (lrt) {
+    QBN_CHECK_ARG(!i8 && !stacked && !x2 && !out_mask && n_samples == 1 && lrt->x_sq, "LRT launch: one 'sample', two operand tensors");
+    QBN_CHECK_ARG(!(flags & QBN_FLAG_OUT_PHASE_SPLIT), "LRT launch: normal output layout");
+    p.dual = 1; p.lrt_mode = lrt->mode; p.x_sq = lrt->x_sq; p.eps = lrt->eps; p.xin = lrt->xin; p.out2 = lrt->out2; p.aux_plane = lrt->aux_plane;
+    p.seed = lrt->seed; p.stream_a = lrt->stream_a; p.stream_b = lrt->stream_b;
+    p.nhwc = lrt->nhwc; p.H_out = lrt->H_out; p.W_out = lrt->W_out;
+    p.oh_mul = lrt->oh_mul; p.oh_add = lrt->oh_add; p.ow_mul = lrt->ow_mul; p.ow_add = lrt->ow_add;
+    QBN_CHECK_ARG(!ct || (stride == 1 && R == 1 && S == lrt->n_taps && S <= MAX_TAPS), "explicit tap list: R = 1, S = n_taps, stride 1");
+  }
+  p.bh = (s1 && !ct) ? (R - 1) / 2 : 1;
+  p.bw = (s1 && !ct) ? (S - 1) / 2 : 1;
   QBN_CHECK_ARG(Hp > p.bh && Wp > p.bw, "padded extent must exceed the border");
   p.Qs = B * Hp * Wp;
   p.tiles_per_sample = (p.Qs + TM - 1) / TM;
@@ -660,7 +777,11 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.taps = R * S;
   p.strip_rows = (long long)((stacked || (i8 && i8->x_shared)) ? 1 : n_samples) * p.Qs;
   int d_after = 0;
-  if (s1) {
+  if (ct) {
+    p.n_strips = 1;
+    p.d_before = 0;
+    d_after = Wp + 1;
+  } else if (s1) {
     p.n_strips = 1;
     p.d_before = p.bh * Wp + p.bw;
     d_after = p.d_before;
@@ -669,7 +790,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     p.d_before = (R == 3) ? Wp + 1 : 0;
   }
   // plane strides come from the caller: a plane = phases * maps + the zero tail that the last map's bottom/right taps read
-  const long long tail = s1 ? (long long)p.bh * Wp + p.bw : 0;
+  const long long tail = (s1 || ct) ? (long long)p.bh * Wp + p.bw : 0;
   p.x_plane = pl.x;
   if (p.x_plane < p.strip_rows * (s2 ? 4 : 1) + tail) {
     qbn_set_error("qbn_conv_p4_fwd: x plane has %lld rows, needs %lld (maps) + %lld (zero tail)", p.x_plane, p.strip_rows * (s2 ? 4 : 1), tail);
@@ -680,7 +801,10 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) {
       int strip = 0, sh;
-      if (s1) {
+      if (ct) {
+        sh = lrt->shift[s];
+        if (sh < 0 || sh > d_after) { qbn_set_error("explicit tap shift %d outside [0, Wp + 1]", sh); return QBN_ERR_INVALID_ARG; }
+      } else if (s1) {
         sh = (r - p.bh) * Wp + (s - p.bw);
       } else if (R == 3) {
         const int dr = r - 1, ds = s - 1;
@@ -723,13 +847,15 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     QBN_CHECK_ARG(p.out_plane >= 4 * p.q2_total, "phase-split out plane too small");
   }
   // ---- shared memory / occupancy policy ----
-  const size_t b_all = (size_t)p.bt_bytes * p.n_cb * p.taps + (size_t)p.bt2_bytes * p.n_cb2;
+  const size_t b_all = (size_t)p.bt_bytes * p.n_cb * (p.dual ? 2 : 1) * p.taps + (size_t)p.bt2_bytes * p.n_cb2;
+  p.acc_cols = p.dual ? 2 * p.n_pad : p.n_pad;
+  QBN_CHECK_ARG(p.acc_cols <= 512, "two accumulators of this width do not fit TMEM (N <= 256 for LRT)");
   const size_t fixed = 2 * 256 * 4 + 16 + 8 * 64 + 8 * 256;          // affine tables, TMEM slot, barriers, MMA operand list
   QBN_CHECK_ARG(p.taps * p.nk <= 256, "too many MMAs per channel block");
   const size_t cap = 225 * 1024;
   int want_occ;
   size_t smem;
-  const char* e_occ = getenv("QBN_P4_OCC");
+  const char* e_occ = tune_env("QBN_P4_OCC");
   if (b_all <= 100 * 1024 && b_all < (1u << 20)) {
     p.b_res = 1; p.SB = 1; p.TG = p.taps; p.b_slot_bytes = (uint32_t)b_all;
     want_occ = e_occ ? atoi(e_occ) : 3;
@@ -747,7 +873,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     p.TG = 1;
     for (int tg = 2; tg <= p.taps; ++tg)
       if (p.taps % tg == 0 && (size_t)tg * p.bt_bytes <= slot_cap) p.TG = tg;
-    if (getenv("QBN_P4_TG")) p.TG = atoi(getenv("QBN_P4_TG"));
+    if (tune_env("QBN_P4_TG")) p.TG = atoi(tune_env("QBN_P4_TG"));
     p.b_slot_bytes = p.bt_bytes * (uint32_t)p.TG;
     while (want_occ > 1 && 2 * (size_t)p.a_bytes + 3 * (size_t)p.b_slot_bytes + fixed > cap / want_occ - 1024) --want_occ;
     while (p.TG > 1 && 2 * (size_t)p.a_bytes + 2 * (size_t)p.b_slot_bytes + fixed > cap / want_occ - 1024) {   // shrink the slots until two fit
@@ -758,8 +884,8 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     while (p.SB < 8 && (size_t)p.SA * p.a_bytes + (size_t)(p.SB + 1) * p.b_slot_bytes + fixed <= cap / want_occ - 1024) ++p.SB;
     smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.b_slot_bytes + fixed;
   }
-  if (getenv("QBN_P4_SA")) {
-    const int sa_new = atoi(getenv("QBN_P4_SA"));
+  if (tune_env("QBN_P4_SA")) {
+    const int sa_new = atoi(tune_env("QBN_P4_SA"));
     smem += (size_t)(sa_new - p.SA) * p.a_bytes;
     p.SA = sa_new;
   }
@@ -774,24 +900,28 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   {
     int share = 512 / want_occ, c2 = 32;
     while (c2 * 2 <= share) c2 <<= 1;
-    p.ACC = c2 / p.n_pad;
+    p.ACC = c2 / p.acc_cols;
     if (p.ACC > 4) p.ACC = 4;
     if (p.ACC < 1) { p.ACC = 1; }
-    if (getenv("QBN_P4_ACC")) p.ACC = atoi(getenv("QBN_P4_ACC"));
+    if (tune_env("QBN_P4_ACC")) p.ACC = atoi(tune_env("QBN_P4_ACC"));
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.ACC * p.n_pad) p.tmem_cols <<= 1;
-    if (p.tmem_cols > 512) { p.ACC = 512 / p.n_pad; p.tmem_cols = 512; }
+    while (p.tmem_cols < p.ACC * p.acc_cols) p.tmem_cols <<= 1;
+    if (p.tmem_cols > 512) { p.ACC = 512 / p.acc_cols; p.tmem_cols = 512; }
     while (p.tmem_cols * want_occ > 512) --want_occ;
   }
   static bool attr_set = false;
   if (!attr_set) {
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false, KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false, KIND_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+#ifdef QBN_TUNING
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false, KIND_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false, KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+#endif
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_p4_kernel<1, false, false, KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
@@ -799,7 +929,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   if (occ < 1) occ = 1;
   int grid = qbn_sm_count() * occ;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  if (getenv("QBN_P4_VERBOSE"))
+  if (tune_env("QBN_P4_VERBOSE"))
     fprintf(stderr, "[p4] C=%d N=%d %dx%d k%d s%d: tiles=%d grid=%d occ=%d SA=%d SB=%d TG=%d ACC=%d b_res=%d smem=%zu a_bytes=%u bt=%u tmem=%d\n", C, N, Hp,
             Wp, R, stride, p.total_tiles, grid, occ, p.SA, p.SB, p.TG, p.ACC, p.b_res, smem, p.a_bytes, p.bt_bytes, p.tmem_cols);
   // the general epilogue order (pre-ReLU, output mask) is a separate instantiation: the plain one keeps its fused fma + residual
@@ -808,6 +938,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (residual) masked = true;                                  // ReLU before the residual add: general order
     else p.flags = (p.flags & ~QBN_FLAG_RELU_PRE) | QBN_FLAG_RELU;  // no mask, no residual: pre == post
   }
+#ifdef QBN_TUNING
   auto prof_report = [&](const char* kind) {
     unsigned long long h[32];
     cudaStreamSynchronize(st);
@@ -819,8 +950,25 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
             kind, C, N, R, stride, grid, t0, p.SA, p.SB, p.ACC, p.b_res, h[0] / t0, h[1] / t0, h[2] / t0, h[3] / t0, h[8] / t0, h[9] / t0, h[10] / t0,
             h[11] / t0, h[12] / t0, h[13] / t0, h[16] / t0, h[17] / t0, h[18] / t0, h[19] / t0, h[20] / t0);
   };
+#endif
+  if (lrt) {
+#ifdef QBN_TUNING
+    if (tune_env("QBN_P4_PROF")) {
+      unsigned long long h[32] = {0};
+      cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
+      umma_conv_p4_kernel<1, false, false, KIND_LRT><<<grid, P4_THREADS, smem, st>>>(p);
+      QBN_CHECK_LAUNCH();
+      prof_report(lrt->mode ? "lrt-dgrad" : "lrt-fwd");
+      return QBN_OK;
+    }
+#endif
+    umma_conv_p4_kernel<0, false, false, KIND_LRT><<<grid, P4_THREADS, smem, st>>>(p);
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
+  }
   if (i8) {
-    if (getenv("QBN_P4_PROF")) {       // diagnostics: cycle accounting of CTA 0 (synchronises the stream)
+#ifdef QBN_TUNING
+    if (tune_env("QBN_P4_PROF")) {       // diagnostics: cycle accounting of CTA 0 (synchronises the stream)
       unsigned long long h[32] = {0};
       cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
       umma_conv_p4_kernel<1, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
@@ -828,6 +976,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
       prof_report("i8");
       return QBN_OK;
     }
+#endif
     umma_conv_p4_kernel<0, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
@@ -839,7 +988,8 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
-  if (getenv("QBN_P4_PROF")) {
+#ifdef QBN_TUNING
+  if (tune_env("QBN_P4_PROF")) {
     unsigned long long h[32] = {0};
     cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
     umma_conv_p4_kernel<1, false, false><<<grid, P4_THREADS, smem, st>>>(p);
@@ -847,6 +997,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     prof_report("tf32");
     return QBN_OK;
   }
+#endif
   umma_conv_p4_kernel<0, false, false><<<grid, P4_THREADS, smem, st>>>(p);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
@@ -898,4 +1049,58 @@ extern "C" int qbn_p16_weight_bytes(int C, int N, int R, int S, int stride, long
   }
   *out_bytes = (long long)(C / CB) * R * S * (CB / 16) * qbn_p16_n_pad(N) * 16;
   return QBN_OK;
+}
+
+// ---- LRT training on the same zero-copy kernel (linear.py:32-40, conv.py:24-32 and their autograd).
+// Operands: planar C4 maps staged by qbn_p4_stage_input / qbn_p4_stage_grad (lrt_p4.cu); results: dense NHWC, the layout of the
+// module boundary.  Weights: blocked like the eval path, the sigma^2 blocks right after the mu blocks (qbn_lrt_p4_weight_prep).
+// Forward: out = conv(x, mu) + sqrt(1e-8 + conv(x_sq, sigma^2)) * eps + bias; std_out = the square root (kept for the backward).
+// eps: NHWC like the output, or NULL -> Philox(seed, stream_a, stream_b, offset in out / 4) — the draw qbn_lrt_fwd makes.
+// Hp, Wp: padded extent of the OUTPUT maps (Ho + border, Wo + border; border = (R-1)/2 x (S-1)/2 at stride 1, 1 x 1 at stride 2).
+extern "C" int qbn_lrt_conv_p4_fwd(int B, int Hp, int Wp, int C, int N, int R, int S, int stride, const float* x, const float* x_sq,
+                                   long long x_plane_rows, const float* w_blocked, const float* bias, const float* eps, uint64_t seed,
+                                   uint32_t stream_a, uint32_t stream_b, float* out, float* std_out, void* stream) {
+  QBN_CHECK_ARG(x_sq && std_out, "x_sq / std_out");
+  P4LRT l;
+  memset(&l, 0, sizeof(l));
+  l.mode = 0; l.x_sq = x_sq; l.eps = eps; l.out2 = std_out; l.seed = seed; l.stream_a = stream_a; l.stream_b = stream_b;
+  const int bh = stride == 1 ? (R - 1) / 2 : 1, bw = stride == 1 ? (S - 1) / 2 : 1;
+  l.nhwc = 1; l.H_out = Hp - bh; l.W_out = Wp - bw; l.oh_mul = l.ow_mul = 1;
+  P4Planes pl = {x_plane_rows, 0, 0, 0};
+  return conv_p4_launch(1, B, Hp, Wp, C, N, R, S, stride, x, w_blocked, 1, nullptr, bias, nullptr, nullptr, 1.0f, 0, out, nullptr, 0, 0, pl, stream,
+                        nullptr, &l);
+}
+// Input gradient of a stride-1 'same' layer: dx = convT(g, mu) + 2 x .* convT(dv, sigma^2), the SAME kernel on the flipped /
+// transposed weights (tap (r,s) <- (R-1-r, S-1-s), in/out channels swapped: qbn_lrt_p4_weight_prep mode 1).  C = channels of g
+// (the layer's outputs), N = channels of dx; g, dv planar with the layer's geometry; xin, dx dense NHWC [B][Hp-bh][Wp-bw][N].
+extern "C" int qbn_lrt_conv_p4_dgrad(int B, int Hp, int Wp, int C, int N, int R, int S, const float* g, const float* dv, long long g_plane_rows,
+                                     const float* w_flipped_blocked, const float* xin, float* dx, void* stream) {
+  QBN_CHECK_ARG(dv && xin, "dv / xin");
+  P4LRT l;
+  memset(&l, 0, sizeof(l));
+  l.mode = 1; l.x_sq = dv; l.xin = xin;
+  l.nhwc = 1; l.H_out = Hp - (R - 1) / 2; l.W_out = Wp - (S - 1) / 2; l.oh_mul = l.ow_mul = 1;
+  P4Planes pl = {g_plane_rows, 0, 0, 0};
+  return conv_p4_launch(1, B, Hp, Wp, C, N, R, S, 1, g, w_flipped_blocked, 1, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, dx, nullptr, 0, 0, pl,
+                        stream, nullptr, &l);
+}
+// Input gradient of a stride-2 layer (3x3 pad 1, or 1x1 pad 0), one launch per phase (a, b) of dx: the pixels (2i+a, 2j+b) receive
+// sum over the taps (r, s) with r = a+1 (mod 2), s = b+1 (mod 2) of g[i + (r == 0), j + (s == 0)] * w[r, s] — a convolution over
+// g's zero-bordered maps (Hp = Ho + 1, Wp = Wo + 1) whose taps shift by 0 / +1 rows and columns; the shared zero border supplies
+// the out-of-range reads.  shifts[t] = (r_t == 0) * Wp + (s_t == 0) in the order of the n_taps blocks of w_phase_blocked
+// (qbn_lrt_p4_weight_prep mode 2).  xin, dx: dense NHWC [B][2(Hp-1)][2(Wp-1)][N].  A 1x1 layer has the single phase (0, 0).
+extern "C" int qbn_lrt_conv_p4_dgrad_phase(int B, int Hp, int Wp, int C, int N, int n_taps, const int* shifts, int phase_a, int phase_b,
+                                           const float* g, const float* dv, long long g_plane_rows, const float* w_phase_blocked,
+                                           const float* xin, float* dx, void* stream) {
+  QBN_CHECK_ARG(dv && xin && shifts && n_taps > 0 && n_taps <= 4, "dv / xin / taps");
+  QBN_CHECK_ARG((phase_a | phase_b) >= 0 && phase_a < 2 && phase_b < 2, "phase");
+  P4LRT l;
+  memset(&l, 0, sizeof(l));
+  l.mode = 1; l.x_sq = dv; l.xin = xin;
+  l.nhwc = 1; l.H_out = 2 * (Hp - 1); l.W_out = 2 * (Wp - 1); l.oh_mul = l.ow_mul = 2; l.oh_add = phase_a; l.ow_add = phase_b;
+  l.n_taps = n_taps;
+  for (int t = 0; t < n_taps; ++t) l.shift[t] = shifts[t];
+  P4Planes pl = {g_plane_rows, 0, 0, 0};
+  return conv_p4_launch(1, B, Hp, Wp, C, N, 1, n_taps, 1, g, w_phase_blocked, 1, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, dx, nullptr, 0, 0, pl,
+                        stream, nullptr, &l);
 }

@@ -22,6 +22,13 @@
 #include <string.h>
 #include "umma_common.cuh"
 
+// tuning knobs exist only in -DQBN_TUNING builds: the product library reads nothing from the environment
+#ifdef QBN_TUNING
+static inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+static inline const char* tune_env(const char*) { return nullptr; }
+#endif
+
 namespace {
 
 QBN_DEVINL void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four epilogue warps only
@@ -439,13 +446,13 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   const size_t a_bytes = (size_t)p.cbc * p.RA_p * 16, bt_bytes = (size_t)p.cbc * p.b_pitch * 16;
-  p.bulk_out = ((size_t)TM * N * 4 <= 24 * 1024 && N % 4 == 0 && getenv("QBN_S1_BULK")) ? 1 : 0;   // measured slower than direct row stores (extra barriers); kept as a tuning knob
+  p.bulk_out = ((size_t)TM * N * 4 <= 24 * 1024 && N % 4 == 0 && tune_env("QBN_S1_BULK")) ? 1 : 0;   // measured slower than direct row stores (extra barriers); kept as a tuning knob
   const size_t epi_bytes = 16 + 2 * 260 * 4 + 16 + (p.bulk_out ? 2 * (size_t)TM * N * 4 : 0);
   const size_t cap = 220 * 1024;
   const int taps = R * S;
   const size_t b_all = bt_bytes * p.n_cb * taps;
   size_t b_bytes, smem;
-  const char* dbg_env = getenv("QBN_S1_DBG");
+  const char* dbg_env = tune_env("QBN_S1_DBG");
   p.dbg = dbg_env ? atoi(dbg_env) : 0;
   // Policy: several small CTAs per SM rather than one deep pipeline — one tcgen05.mma costs ~83 cycles to
   // issue from a thread (scripts/ubench.py), so issuers in different CTAs are what fills the tensor pipe,
@@ -484,12 +491,12 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
     while (p.tmem_cols < cols) p.tmem_cols <<= 1;
     if (p.tmem_cols * want_occ > 512) want_occ = 512 / p.tmem_cols;
   }
-  if (getenv("QBN_S1_SA")) {   // tuning: force the activation ring depth
-    const int sa_new = atoi(getenv("QBN_S1_SA"));
+  if (tune_env("QBN_S1_SA")) {   // tuning: force the activation ring depth
+    const int sa_new = atoi(tune_env("QBN_S1_SA"));
     smem += (size_t)(sa_new - p.SA) * (a_bytes + 16);
     p.SA = sa_new;
   }
-  if (getenv("QBN_S1_ACC")) { p.ACC = atoi(getenv("QBN_S1_ACC")); }
+  if (tune_env("QBN_S1_ACC")) { p.ACC = atoi(tune_env("QBN_S1_ACC")); }
   if (smem > cap) {
     qbn_set_error("qbn_conv_s1_fwd: tile does not fit shared memory (%zu bytes)", smem);
     return QBN_ERR_UNSUPPORTED;

@@ -171,30 +171,140 @@ class LRTFunction(torch.autograd.Function):
         _need_cuda(x, weight, second)
         xc = nhwc(_f32(x))
         d = _geom(xc, weight.shape, stride, padding, dilation)
-        packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))   # backward needs them unrounded
-        fw = packed if math_mode != QBN_MATH_TF32 else weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"), round_tf32=True)
         eps_c = nhwc(_f32(eps)) if eps is not None else None
-        out, std = lrt_forward(xc, fw["mu"], fw["sigma2"], _f32(bias), d, eps_c, key, math_mode)
-        ctx.save_for_backward(xc, packed["mu"], packed["sigma2"], std, eps_c, second.detach())
         ctx.d, ctx.key, ctx.math_mode, ctx.second_is_sigma = d, key, math_mode, second_is_sigma
         ctx.wshape = tuple(weight.shape)
         ctx.has_bias = bias is not None
         ctx.chan_scale = chan_scale
+        ctx.planar = (math_mode == QBN_MATH_TF32 and chan_scale is None and xc.dim() == 4
+                      and lrt_p4_eligible(d, need_dx=ctx.needs_input_grad[0]))
+        if ctx.planar:
+            # TF32 mode on the planar zero-copy kernels: operands staged once, every contraction of forward and backward on tcgen05
+            out, std, x_p4, xsq_p4 = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key)
+            ctx.save_for_backward(xc, x_p4, xsq_p4, std, eps_c, weight.detach(), second.detach())
+            return out
+        packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))   # backward needs them unrounded
+        fw = packed if math_mode != QBN_MATH_TF32 else weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"), round_tf32=True)
+        out, std = lrt_forward(xc, fw["mu"], fw["sigma2"], _f32(bias), d, eps_c, key, math_mode)
+        ctx.save_for_backward(xc, packed["mu"], packed["sigma2"], std, eps_c, second.detach())
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xc, mu_p, sig2_p, std, eps_c, second = ctx.saved_tensors
         gc = nhwc(_f32(g))
         need_dx = ctx.needs_input_grad[0]
-        # TF32 mode: dx of the stride-1 layers runs on tcgen05 (two launches of the forward kernel on flipped weights); the
-        # weight gradients and every other shape stay on the fp32 CUDA-core kernels (the library decides per descriptor)
-        dx, dmu_p, dsig2_p, dbias = lrt_backward(xc, mu_p, sig2_p, gc, std, ctx.d, eps_c, ctx.key, need_dx, ctx.has_bias,
-                                                 ctx.math_mode)
+        if ctx.planar:
+            xc, x_p4, xsq_p4, std, eps_c, weight, second = ctx.saved_tensors
+            dx, dmu_p, dsig2_p = lrt_p4_backward(xc, x_p4, xsq_p4, std, eps_c, weight, second, ctx.second_is_sigma, gc, ctx.d, ctx.key, need_dx)
+            dbias = gc.sum(dim=(0, 2, 3)) if ctx.has_bias else None
+        else:
+            xc, mu_p, sig2_p, std, eps_c, second = ctx.saved_tensors
+            # TF32 mode: dx of the stride-1 layers runs on tcgen05 (two launches of the forward kernel on flipped weights); the
+            # weight gradients and every other shape stay on the fp32 CUDA-core kernels (the library decides per descriptor)
+            dx, dmu_p, dsig2_p, dbias = lrt_backward(xc, mu_p, sig2_p, gc, std, ctx.d, eps_c, ctx.key, need_dx, ctx.has_bias,
+                                                     ctx.math_mode)
         if ctx.chan_scale is not None:
             raise _lib.QbnError("LRTFunction.backward with chan_scale: fold the scale outside (QAT ConvBn2d does)")
         d_mu, d_second = weight_grad_post(dmu_p, dsig2_p, second, ctx.second_is_sigma, ctx.wshape)
         return dx, d_mu, d_second, dbias, None, None, None, None, None, None, None, None
+
+
+# ---- A1-A3 on the planar zero-copy kernels (include/qbn.h "LRT training in TF32 mode"; csrc/lrt_p4.cu, umma_conv_p4.cu KIND_LRT,
+# umma_wgrad_p4.cu).  The NHWC tensors of the module boundary are staged once per layer into planar-C4 maps.
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+def lrt_p4_plane_rows(rows, Wp):
+    return _ceil(rows, 128) + 128 + 2 * (Wp + 1) + 8
+
+
+def lrt_p4_eligible(d, need_dx=True):
+    """Shapes the planar LRT kernels take (include/qbn.h): everything else stays on the gather kernels (qbn_lrt_fwd / qbn_lrt_bwd)."""
+    if (d.dil_h, d.dil_w) != (1, 1) or d.N % 8 or d.N > 256 or d.R > 5 or d.S > 5:
+        return False
+    if need_dx and d.C % 8:
+        return False
+    if (d.stride_h, d.stride_w) == (1, 1):
+        ok = d.R % 2 == 1 and d.S % 2 == 1 and (d.pad_h, d.pad_w) == ((d.R - 1) // 2, (d.S - 1) // 2)
+        return ok and d.H + (d.R - 1) // 2 > 2 and d.W + (d.S - 1) // 2 > 2
+    if (d.stride_h, d.stride_w) == (2, 2) and d.H % 2 == 0 and d.W % 2 == 0 and d.H >= 4 and d.W >= 4:
+        return (d.R, d.S, d.pad_h, d.pad_w) in ((3, 3, 1, 1), (1, 1, 0, 0))
+    return False
+
+
+def _lrt_p4_geom(d):
+    s2 = d.stride_h == 2
+    bh, bw = (1, 1) if s2 else ((d.R - 1) // 2, (d.S - 1) // 2)
+    return s2, bh, bw, d.Ho + bh, d.Wo + bw, _ceil(d.C, 8)
+
+
+def lrt_p4_weight_prep(weight, second, second_is_sigma, d, mode, tap_list=None):
+    C_pad = _ceil(d.C, 8)
+    if mode == 0:
+        n = 2 * p4_weight_floats(C_pad, d.N, d.R, d.S, d.stride_h)
+    elif mode == 1:
+        n = 2 * p4_weight_floats(d.N, d.C, d.R, d.S, 1)
+    else:
+        n = 2 * p4_weight_floats(d.N, d.C, 1, len(tap_list), 1)
+    out = torch.empty(n, dtype=torch.float32, device=weight.device)
+    taps = (ctypes.c_int * len(tap_list))(*tap_list) if tap_list else None
+    got = ctypes.c_longlong(0)
+    _lib.call("qbn_lrt_p4_weight_prep", _ptr(weight), _ptr(second), int(second_is_sigma), d.N, d.C, C_pad, d.R, d.S, d.stride_h, mode, taps,
+              len(tap_list) if tap_list else 0, _ptr(out), ctypes.byref(got), _stream())
+    if got.value != n:
+        raise _lib.QbnError("qbn_lrt_p4_weight_prep wrote %d floats into a buffer of %d" % (got.value, n))
+    return out
+
+
+def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(0, 0, 0)):
+    """xc NHWC-dense [B, C, H, W] (channels_last).  Returns out, std (NHWC) and the staged planar operands (kept for the backward)."""
+    s2, bh, bw, Hp, Wp, C_pad = _lrt_p4_geom(d)
+    rows = (4 if s2 else 1) * d.B * Hp * Wp
+    pr = lrt_p4_plane_rows(rows, Wp)
+    x_p4 = torch.empty((C_pad // 4, pr, 4), dtype=torch.float32, device=xc.device)
+    xsq_p4 = torch.empty_like(x_p4)
+    _lib.call("qbn_p4_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _stream())
+    w = lrt_p4_weight_prep(weight.detach().contiguous(), second.detach().contiguous(), second_is_sigma, d, 0)
+    out, std = _out_like(xc, d), _out_like(xc, d)
+    _lib.call("qbn_lrt_conv_p4_fwd", d.B, Hp, Wp, C_pad, d.N, d.R, d.S, d.stride_h, _ptr(x_p4), _ptr(xsq_p4), pr, _ptr(w), _ptr(bias), _ptr(eps),
+              key[0], key[1], key[2], _ptr(out), _ptr(std), _stream())
+    return out, std, x_p4, xsq_p4
+
+
+def lrt_p4_backward(xc, x_p4, xsq_p4, std, eps, weight, second, second_is_sigma, gc, d, key=(0, 0, 0), need_dx=True):
+    """Closed-form backward of SURVEY 8a row A3 on the planar kernels.  Returns dx (NHWC or None), dmu_p, dsig2_p (packed OHWI)."""
+    s2, bh, bw, Hp, Wp, C_pad = _lrt_p4_geom(d)
+    weight, second = weight.contiguous(), second.contiguous()
+    pr_g = lrt_p4_plane_rows(d.B * Hp * Wp, Wp)
+    g_p4 = torch.empty((d.N // 4, pr_g, 4), dtype=torch.float32, device=gc.device)
+    dv_p4 = torch.empty_like(g_p4)
+    _lib.call("qbn_p4_stage_grad", _ptr(gc), _ptr(std), _ptr(eps), key[0], key[1], key[2], d.B, d.Ho, d.Wo, d.N, bh, bw, pr_g, _ptr(g_p4),
+              _ptr(dv_p4), _stream())
+    dmu_p = torch.empty(d.N * d.R * d.S * d.C, dtype=torch.float32, device=gc.device)
+    dsig2_p = torch.empty_like(dmu_p)
+    _lib.call("qbn_lrt_wgrad_p4", d.B, Hp, Wp, C_pad, d.C, d.N, d.R, d.S, d.stride_h, _ptr(g_p4), _ptr(dv_p4), pr_g, _ptr(x_p4), _ptr(xsq_p4),
+              x_p4.stride(0) // 4, _ptr(dmu_p), _ptr(dsig2_p), _stream())
+    dx = None
+    if need_dx:
+        if not s2:
+            w_t = lrt_p4_weight_prep(weight, second, second_is_sigma, d, 1)
+            dx = torch.empty_like(xc)
+            _lib.call("qbn_lrt_conv_p4_dgrad", d.B, Hp, Wp, d.N, d.C, d.R, d.S, _ptr(g_p4), _ptr(dv_p4), pr_g, _ptr(w_t), _ptr(xc), _ptr(dx), _stream())
+        else:
+            # pixels (2i+a, 2j+b) of dx: the taps r = a+1 (mod 2), s = b+1 (mod 2); tap 0 of a 3x3 filter reads g one row / column further
+            one = d.R == 1
+            dx = torch.zeros_like(xc) if one else torch.empty_like(xc)
+            for a in ((0,) if one else (0, 1)):
+                for b in ((0,) if one else (0, 1)):
+                    rs = (0,) if one else ((1,) if a == 0 else (0, 2))
+                    ss = (0,) if one else ((1,) if b == 0 else (0, 2))
+                    taps = [r * d.S + s_ for r in rs for s_ in ss]
+                    shifts = [(0 if one else int(r == 0)) * Wp + (0 if one else int(s_ == 0)) for r in rs for s_ in ss]
+                    w_t = lrt_p4_weight_prep(weight, second, second_is_sigma, d, 2, taps)
+                    _lib.call("qbn_lrt_conv_p4_dgrad_phase", d.B, Hp, Wp, d.N, d.C, len(taps), (ctypes.c_int * len(taps))(*shifts), a, b, _ptr(g_p4),
+                              _ptr(dv_p4), pr_g, _ptr(w_t), _ptr(xc), _ptr(dx), _stream())
+    return dx, dmu_p, dsig2_p
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,151 @@
+"""GPU (pytest -m gpu): LRT training on the planar zero-copy tcgen05 kernels — staging, forward, input
+gradient (stride 1 and the phase launches of stride 2), weight gradients — against the oracle (bbb/conv.py:24-32 and its
+autograd).  TF32 tolerance per north_star: rtol 1e-3, atol 1e-3 * max|ref| (10 mantissa bits per operand, fp32 accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.qbn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # B, C, H, N, k, stride, pad
+    (2, 24, 32, 24, 3, 1, 1),     # ResNet layer1
+    (2, 3, 32, 24, 3, 1, 1),      # first layer: 3 -> 8 padded input channels (no input gradient)
+    (2, 24, 32, 48, 3, 2, 1),     # layer2 stride-2 entry
+    (2, 24, 32, 48, 1, 2, 0),     # 1x1 stride-2 shortcut
+    (2, 48, 16, 48, 3, 1, 1),
+    (3, 96, 8, 96, 3, 1, 1),
+    (3, 96, 8, 192, 3, 2, 1),
+    (3, 96, 8, 192, 1, 2, 0),
+    (5, 192, 4, 192, 3, 1, 1),    # 125 padded pixels: less than one tile
+    (2, 16, 12, 40, 5, 1, 2),     # 5x5 'same'
+    (3, 8, 9, 16, 3, 1, 1),       # odd sizes
+    (4, 32, 6, 8, 1, 1, 0),       # 1x1 stride 1 (no border)
+    (33, 24, 16, 24, 3, 1, 1),    # several tiles per CTA, ragged last tile
+]
+
+
+def close(got, ref, rtol=1e-3, atol_rel=1e-3):
+    got, ref = got.detach().float().cpu().numpy(), ref.detach().float().cpu().numpy()
+    atol = atol_rel * max(1e-30, float(np.abs(ref).max()))
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    import __graft_entry__ as g
+    g.build()
+
+
+def _case(shape, seed=0):
+    B, C, H, N, k, stride, pad = shape
+    g = torch.Generator().manual_seed(seed + (hash(shape) & 0xFFFF))
+    x = torch.randn(B, C, H, H, generator=g)
+    mu = torch.randn(N, C, k, k, generator=g) / (C * k * k) ** 0.5
+    rho = torch.empty(N, C, k, k).uniform_(-5, -2, generator=g)
+    Ho = (H + 2 * pad - k) // stride + 1
+    eps = torch.randn(B, N, Ho, Ho, generator=g)
+    go = torch.randn(B, N, Ho, Ho, generator=g)
+    return x, mu, rho, eps, go
+
+
+def test_stage_input_layout():
+    """qbn_p4_stage_input against the torch restatement of the planar layout (ops.P4Map.from_nchw), normal and phase-split."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for (B, C, H, W, border, split) in ((3, 24, 8, 6, (1, 1), False), (2, 3, 6, 6, (1, 1), False), (2, 16, 8, 12, (1, 1), True),
+                                        (2, 8, 5, 7, (2, 2), False), (2, 8, 4, 4, (0, 0), False)):
+        x = torch.randn(B, C, H, W, generator=g).cuda()
+        xc = ops.nhwc(x)
+        C_pad = (C + 7) // 8 * 8
+        Hp, Wp = (H // 2 + 1, W // 2 + 1) if split else (H + border[0], W + border[1])
+        rows = (4 if split else 1) * B * Hp * Wp
+        pr = ops.lrt_p4_plane_rows(rows, Wp)
+        xp = torch.full((C_pad // 4, pr, 4), float("nan"), device="cuda")
+        xq = torch.full((C_pad // 4, pr, 4), float("nan"), device="cuda")
+        ops._lib.call("qbn_p4_stage_input", ops._ptr(xc), B, H, W, C, C_pad, border[0], border[1], int(split), pr, ops._ptr(xp), ops._ptr(xq),
+                      ops._stream())
+        xpad = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, C_pad - C))
+        ref = ops.P4Map.from_nchw(xpad, border, phase_split=split).buf
+        assert torch.isfinite(xp).all() and torch.isfinite(xq).all()
+        np.testing.assert_allclose(xp[:, :ref.shape[1]].cpu().numpy(), ref.cpu().numpy(), rtol=6e-4, atol=0)       # RNA to 10 mantissa bits
+        np.testing.assert_allclose(xq[:, :ref.shape[1]].cpu().numpy(), (ref * ref).cpu().numpy(), rtol=6e-4, atol=0)
+        assert float(xp[:, ref.shape[1]:].abs().max()) == 0.0 and float(xq[:, rows:].abs().max()) == 0.0           # zero tail
+        assert int((xp.view(torch.int32) & 0x1FFF).abs().max()) == 0                                               # TF32-exact
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_lrt_p4_forward(shape):
+    from qbn_b200 import ops
+    B, C, H, N, k, stride, pad = shape
+    x, mu, rho, eps, _ = _case(shape)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(5))
+    d = ops.make_desc(B, H, H, C, N, k, k, stride, pad, 1)
+    assert ops.lrt_p4_eligible(d, need_dx=C % 8 == 0)
+    out, std, _, _ = ops.lrt_p4_forward(ops.nhwc(x.cuda()), mu.cuda(), rho.cuda(), False, bias.cuda(), d, ops.nhwc(eps.cuda()))
+    yo, so = O.lrt_conv_fwd(x, mu, rho, bias, eps, stride, pad)
+    close(std, so)
+    close(out, yo)
+    # Philox epilogue: the draw of the gather kernel (counter = offset in out / 4)
+    p = ops.weight_prep(mu.cuda(), rho.cuda(), want=("mu", "sigma2"))
+    r1, _ = ops.lrt_forward(ops.nhwc(x.cuda()), p["mu"], p["sigma2"], None, d, None, (5, 6, 7), ops.QBN_MATH_FP32)
+    r2, _, _, _ = ops.lrt_p4_forward(ops.nhwc(x.cuda()), mu.cuda(), rho.cuda(), False, None, d, None, (5, 6, 7))
+    close(r2, r1, 1e-3, 2e-3)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_lrt_p4_backward(shape):
+    from qbn_b200 import ops
+    B, C, H, N, k, stride, pad = shape
+    x, mu, rho, eps, go = _case(shape, 7)
+    d = ops.make_desc(B, H, H, C, N, k, k, stride, pad, 1)
+    need_dx = C % 8 == 0
+    xc = ops.nhwc(x.cuda())
+    out, std, x_p4, xsq_p4 = ops.lrt_p4_forward(xc, mu.cuda(), rho.cuda(), False, None, d, ops.nhwc(eps.cuda()))
+    dx, dmu_p, dsig2_p = ops.lrt_p4_backward(xc, x_p4, xsq_p4, std, ops.nhwc(eps.cuda()), mu.cuda(), rho.cuda(), False, ops.nhwc(go.cuda()), d,
+                                             (0, 0, 0), need_dx)
+    d_mu, d_rho = ops.weight_grad_post(dmu_p, dsig2_p, rho.cuda(), False, tuple(mu.shape))
+    _, so = O.lrt_conv_fwd(x, mu, rho, None, eps, stride, pad)
+    dx_o, dmu_o, drho_o, _ = O.lrt_conv_bwd(x, mu, rho, eps, so, go, stride, pad)
+    close(d_mu, dmu_o)
+    close(d_rho, drho_o)
+    if need_dx:
+        close(dx, dx_o)
+    else:
+        assert dx is None
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[2], SHAPES[3], SHAPES[5]])
+def test_lrt_function_takes_the_planar_path_and_matches_the_fp32_mode(shape):
+    """ops.LRTFunction (what stochastic.bbb.Conv2d.forward calls in training mode): TF32 mode runs planar, same Philox draw as fp32 mode."""
+    from qbn_b200 import ops
+    B, C, H, N, k, stride, pad = shape
+    x, mu, rho, _, go = _case(shape, 11)
+    res = {}
+    for mode in (ops.QBN_MATH_FP32, ops.QBN_MATH_TF32):
+        xx = x.cuda().requires_grad_(True)
+        m, r = mu.cuda().requires_grad_(True), rho.cuda().requires_grad_(True)
+        calls = []
+        real = ops._lib.call
+        ops._lib.call = lambda name, *a: (calls.append(name), real(name, *a))[1]
+        try:
+            out = ops.LRTFunction.apply(xx, m, r, None, (stride, stride), (pad, pad), (1, 1), None, (9, 3, 1), mode, False, None)
+            (out * go.cuda()).sum().backward()
+        finally:
+            ops._lib.call = real
+        assert ("qbn_lrt_conv_p4_fwd" in calls) == (mode == ops.QBN_MATH_TF32)
+        assert ("qbn_lrt_wgrad_p4" in calls) == (mode == ops.QBN_MATH_TF32)
+        res[mode] = (out.detach(), xx.grad, m.grad, r.grad)
+    for a, b in zip(res[ops.QBN_MATH_TF32], res[ops.QBN_MATH_FP32]):
+        close(a, b, 1e-3, 2e-3)
+
+
+def test_lrt_p4_ineligible_shapes_stay_on_the_gather_kernels():
+    from qbn_b200 import ops
+    for (C, H, N, k, stride, pad, dil) in ((20, 14, 50, 5, 1, 2, 1), (24, 16, 24, 3, 1, 0, 1), (24, 16, 24, 3, 1, 2, 2), (24, 16, 20, 3, 1, 1, 1),
+                                           (24, 15, 24, 3, 2, 1, 1), (24, 16, 264, 3, 1, 1, 1)):
+        assert not ops.lrt_p4_eligible(ops.make_desc(2, H, H, C, N, k, k, stride, pad, dil))
+    assert not ops.lrt_p4_eligible(ops.make_desc(2, 32, 32, 3, 24, 3, 3, 1, 1, 1), need_dx=True)
+    assert ops.lrt_p4_eligible(ops.make_desc(2, 32, 32, 3, 24, 3, 3, 1, 1, 1), need_dx=False)
