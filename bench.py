@@ -212,34 +212,48 @@ def train_leg(torch, dist, dev, rank, world, steps, math):
     config.set_math_mode(math)
     model = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).to(dev).train()
     noise.manual_seed(1234 + rank)                       # independent epsilon substreams per replica
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, capturable=True)
     args = zoo.Args(loss_multiplier=1.0)
     crit = losses.LOSS_FACTORY["classification"](args, "batch")
     step = qdist.DPTrainStep(model, crit, opt, gamma=0.01, check_nan_loss=False)
     g = torch.Generator().manual_seed(5 + rank)
     x = torch.randn(B, 3, 32, 32, generator=g).to(dev)
     t = torch.randint(0, K_CLASSES, (B,), generator=g).to(dev)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, out
     for _ in range(3):
         step(x, t, 176, 45000)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        _, obj, _, _ = step(x, t, 176, 45000)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms) / steps
+    ms_eager, out = timed(lambda: step(x, t, 176, 45000))
+    ms_step, mode = ms_eager, "eager (one Python-driven step per iteration)"
+    graph_note, gstep = None, None
+    try:       # the whole step replayed from one CUDA graph (dist.GraphedTrainStep): fresh noise per replay via the device-side draw offset
+        gstep = qdist.GraphedTrainStep(model, crit, opt, x, t, 176, 45000, gamma=0.01, warmup=3)
+        for _ in range(3):
+            gstep()
+        ms_graph, out = timed(lambda: gstep())
+        ms_step, mode = ms_graph, "one CUDA graph per step (dist.GraphedTrainStep), fresh noise every replay"
+    except Exception as e:      # noqa: BLE001 - reported, never hidden
+        graph_note = "graph capture failed (%s: %s); eager number reported" % (type(e).__name__, str(e)[:200])
+    obj = out[1]
     peak = _peaks()["bf16_tflops_sustained"] / 2.0
     tf = FLOP_TRAIN_PER_IMAGE * B * world / (ms_step * 1e-3) / 1e12
     loss = float(obj.detach())
-    del model, opt, step
+    del model, opt, step, gstep
     return {"metric": "resnet18_bbb_lrt_train_images_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "images/s", "ms_per_step": ms_step,
-            "steps": steps, "scaling": "weak", "dtype": math, "loss": loss,
+            "steps": steps, "scaling": "weak", "dtype": math, "loss": loss, "mode": mode, "ms_per_step_eager": ms_eager, "graph_note": graph_note,
             "config": {"workload": "ResNet-18(24/48/96/192) BBB LRT training step, B=256 per GPU, Adam lr 1e-3, gamma .01, n_batches 176",
                        "parallelism": "dp%d, one flat NCCL gradient all-reduce (12.6 MB)" % world},
             "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "unit": "TFLOP/s", "frac": tf / world / peak,
@@ -305,6 +319,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the config-4 training leg")
     ap.add_argument("--no-int8", action="store_true", help="skip the config-5 int8 leg")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-modules-on-this-GPU context leg")
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("QBN_PDL", "0")), help="programmatic dependent launch inside the captured graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -326,7 +341,9 @@ def main():
     if rank != 0:
         ge.build()
     from qbn_b200 import dist as qdist
+    from qbn_b200 import config as qconfig
     from qbn_b200 import mc, metrics, noise, synthetic, zoo   # the GPU arm never imports oracle/ (only the cpu_baseline leg does)
+    qconfig.set_pdl(bool(args.pdl))
 
     dev = torch.device("cuda", local_rank)
     P = synthetic.ResNetBBBParams(seed=1)

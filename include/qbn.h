@@ -369,6 +369,12 @@ int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_pad, int C_real, int N, int R,
                      const float* dv_p4, long long g_plane_rows, const float* x_p4, const float* xsq_p4, long long x_plane_rows,
                      float* dmu_p, float* dsig2_p, void* stream);
 
+/* Programmatic dependent launch of the planar convolution kernels (qbn_conv_p4_fwd, qbn_conv_p4_shortcut_fwd, qbn_i8_conv_p16_fwd,
+ * qbn_lrt_conv_p4_*): with enabled != 0 every such launch carries cudaLaunchAttributeProgrammaticStreamSerialization, so its
+ * prologue (barrier init, TMEM allocation, operand tables) overlaps the tail of the previous kernel of the stream; the kernel
+ * touches global memory only after that kernel has completed (griddepcontrol.wait).  Process-wide, off by default. */
+int qbn_set_pdl(int enabled);
+
 /* Draw offset of the Monte-Carlo samplers, kept on the DEVICE: after qbn_set_sample_base(p) every sampler launch
  * (qbn_sample_weights*, qbn_i8_sample_weights, qbn_dropout_masks_multi, qbn_i8_dropout_mc) uses the Philox stream index
  * *p + sample0 + s instead of sample0 + s, reading *p when the kernel runs.  One captured CUDA graph then serves every batch

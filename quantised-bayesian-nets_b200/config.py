@@ -1,7 +1,7 @@
 """Process-wide switches of the hot path."""
 from ._lib import QBN_MATH_FP32, QBN_MATH_TF32
 
-_cfg = {"math_mode": QBN_MATH_FP32}
+_cfg = {"math_mode": QBN_MATH_FP32, "pdl": False}
 
 
 def set_math_mode(mode):
@@ -25,3 +25,13 @@ def pick_math_mode(C, N, lrt):
     if m == QBN_MATH_TF32 and not tf32_eligible(C, N, lrt):
         return QBN_MATH_FP32  # still a libqbn CUDA kernel (the FFMA one), never a CPU/PyTorch path
     return m
+
+
+def set_pdl(enabled):
+    """Programmatic dependent launch inside the engines' CUDA graphs (include/qbn.h: qbn_set_pdl): the prologue of every planar
+    conv launch overlaps the tail of the previous kernel."""
+    _cfg["pdl"] = bool(enabled)
+
+
+def pdl():
+    return _cfg["pdl"]

@@ -43,6 +43,8 @@ void qbn_set_error(const char* fmt, ...);
   } while (0)
 
 int qbn_sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+// device scalar added to every Philox draw index (qbn_set_sample_base), or nullptr
+const uint32_t* qbn_sample_base_ptr();
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -27,6 +27,7 @@ extern "C" int qbn_set_sample_base(const uint32_t* base_dev) {
   g_sample_base = base_dev;
   return QBN_OK;
 }
+const uint32_t* qbn_sample_base_ptr() { return g_sample_base; }
 
 int qbn_sm_count() {
   static int cached[64] = {0};

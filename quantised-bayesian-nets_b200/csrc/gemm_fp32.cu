@@ -219,7 +219,7 @@ struct FwdLRT : PixelRows {
   static constexpr bool DUAL = true, A2_SQUARE = true, B2_SQUARE = false;
   const float* x; const float* mu; const float* sig2; const float* bias; const float* eps;
   float* out; float* std_out;
-  uint64_t seed; uint32_t sa, sb;
+  uint64_t seed; uint32_t sa, sb; const uint32_t* sbase;      // sbase: device-side draw offset (qbn_set_sample_base)
   __device__ void begin(int) {}
   __device__ int64_t rows_total() const { return g.M; }
   __device__ int cols_total() const { return g.N; }
@@ -238,7 +238,7 @@ struct FwdLRT : PixelRows {
   __device__ void store(int, int64_t m, int n, float mean, float var) const {
     int64_t o = m * g.N + n;
     float sd = sqrtf(1e-8f + var);
-    float e = eps ? eps[o] : philox_normal1(seed, sa, sb, (uint64_t)o);
+    float e = eps ? eps[o] : philox_normal1(seed, sa, sb + (sbase ? *sbase : 0u), (uint64_t)o);
     // linear.py:40 / conv.py:31-32: mean + std*noise (+ bias)
     float v = __fadd_rn(mean, __fmul_rn(sd, e));
     if (bias) v = __fadd_rn(v, bias[n]);
@@ -382,7 +382,8 @@ struct Wgrad : PixelRows {
 };
 
 __global__ void lrt_dv_kernel(const float* __restrict__ g, const float* __restrict__ sd, const float* __restrict__ eps, int64_t n,
-                              uint64_t seed, uint32_t sa, uint32_t sb, float* __restrict__ dv) {
+                              uint64_t seed, uint32_t sa, uint32_t sb, const uint32_t* __restrict__ sbase, float* __restrict__ dv) {
+  if (sbase) sb += *sbase;           // the forward's draw (device-side offset, qbn_set_sample_base)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float e = eps ? eps[i] : philox_normal1(seed, sa, sb, (uint64_t)i);
     dv[i] = g[i] * e / (2.0f * sd[i]);
@@ -452,11 +453,11 @@ extern "C" int qbn_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* 
   Geom g = make_geom(d);
   if (g.N <= 32) {
     FwdLRT<32> p; p.g = g; p.x = x; p.mu = mu_p; p.sig2 = sig2_p; p.bias = bias; p.eps = eps; p.out = out; p.std_out = std_out;
-    p.seed = seed; p.sa = sa; p.sb = sb;
+    p.seed = seed; p.sa = sa; p.sb = sb; p.sbase = qbn_sample_base_ptr();
     launch(p, g.M, g.N, 1, st);
   } else {
     FwdLRT<64> p; p.g = g; p.x = x; p.mu = mu_p; p.sig2 = sig2_p; p.bias = bias; p.eps = eps; p.out = out; p.std_out = std_out;
-    p.seed = seed; p.sa = sa; p.sb = sb;
+    p.seed = seed; p.sa = sa; p.sb = sb; p.sbase = qbn_sample_base_ptr();
     launch(p, g.M, g.N, 1, st);
   }
   QBN_CHECK_LAUNCH();
@@ -549,7 +550,7 @@ extern "C" int qbn_lrt_bwd(const qbn_conv_desc* d, const float* x, const float* 
   float* part1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + dv_bytes);
   float* part2 = part1 + (int64_t)splits * g.N * g.K;
 
-  lrt_dv_kernel<<<qbn_grid_for(MN, 256), 256, 0, st>>>(grad_out, std_saved, eps, MN, seed, sa, sb, dv);
+  lrt_dv_kernel<<<qbn_grid_for(MN, 256), 256, 0, st>>>(grad_out, std_saved, eps, MN, seed, sa, sb, qbn_sample_base_ptr(), dv);
   QBN_CHECK_LAUNCH();
   if (dx && math_mode == QBN_MATH_TF32 && dgrad_tf32_ok(d)) {
     float* mu_t = part2 + (int64_t)splits * g.N * g.K;

@@ -66,7 +66,9 @@ __global__ void p4_stage_input_kernel(const float* __restrict__ x, StageGeom g, 
 }
 
 __global__ void p4_stage_grad_kernel(const float* __restrict__ gout, const float* __restrict__ sd, const float* __restrict__ eps, StageGeom g,
-                                     uint64_t seed, uint32_t sa, uint32_t sb, float4* __restrict__ gp, float4* __restrict__ dvp) {
+                                     uint64_t seed, uint32_t sa, uint32_t sb, const uint32_t* __restrict__ sbase, float4* __restrict__ gp,
+                                     float4* __restrict__ dvp) {
+  if (sbase) sb += *sbase;           // the forward's draw (device-side offset, qbn_set_sample_base)
   const long long total = (long long)g.chunks * g.plane_rows;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i / g.plane_rows);
@@ -134,7 +136,7 @@ extern "C" int qbn_p4_stage_grad(const float* g_out, const float* std_saved, con
   int rc = stage_geom(g, n_img, H, W, N, N, bh, bw, 0, plane_rows);
   if (rc != QBN_OK) return rc;
   const long long total = (long long)g.chunks * plane_rows;
-  p4_stage_grad_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g_out, std_saved, eps, g, seed, stream_a, stream_b,
+  p4_stage_grad_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g_out, std_saved, eps, g, seed, stream_a, stream_b, qbn_sample_base_ptr(),
                                                                                   reinterpret_cast<float4*>(g_p4), reinterpret_cast<float4*>(dv_p4));
   QBN_CHECK_LAUNCH();
   return QBN_OK;

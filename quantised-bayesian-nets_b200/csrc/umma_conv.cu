@@ -60,7 +60,7 @@ struct UParams {
   const float* scale; const float* shift; const float* residual; const float* in_mask; float in_mult;
   int tr_sh, tr_sw;              // transposed convolution (dgrad of a strided conv): input coordinate = (h0 + r) / tr_s when divisible
   const float* mul2x;            // LRT dgrad: acc *= 2 * mul2x[out index] before the residual add (dx = dx_mean + 2x .* dx_var)
-  const float* bias; const float* eps; uint64_t seed; uint32_t sa, sb;
+  const float* bias; const float* eps; uint64_t seed; uint32_t sa, sb; const uint32_t* sbase;
   void* out; float* std_out;
   // int8
   int z_x, z_w, z_out, lo, hi; float atw, mult; int32_t* acc_dump;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS) umma_conv_kernel(const UParams p) {
         if (p.eps) {
           for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? __ldg(p.eps + orow + c0 + j) : 0.f;
         } else {
-          for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? philox_normal1(p.seed, p.sa, p.sb, (uint64_t)(orow + c0 + j)) : 0.f;
+          for (int j = 0; j < 8; ++j) e[j] = j < nvalid ? philox_normal1(p.seed, p.sa, p.sb + (p.sbase ? *p.sbase : 0u), (uint64_t)(orow + c0 + j)) : 0.f;
         }
         for (int j = 0; j < nvalid; ++j) {
           float sd = sqrtf(1e-8f + __uint_as_float(v2[j]));
@@ -508,7 +508,7 @@ int qbn_umma_lrt_fwd(const qbn_conv_desc* d, const float* x, const float* mu_p, 
   UParams p;
   fill_geom(p, d);
   p.x = x; p.w = mu_p; p.w2 = sig2_p; p.x_shared = 1; p.w_shared = 1;
-  p.bias = bias; p.eps = eps; p.seed = seed; p.sa = sa; p.sb = sb; p.out = out; p.std_out = std_out;
+  p.bias = bias; p.eps = eps; p.seed = seed; p.sa = sa; p.sb = sb; p.sbase = qbn_sample_base_ptr(); p.out = out; p.std_out = std_out;
   return launch_umma<MODE_LRT>(p, 1, st, "qbn_lrt_fwd(TF32)");
 }
 

@@ -48,6 +48,7 @@ struct P4Params {
   uint32_t idesc, mg_plane, mg_wp;
   long long x_plane, strip_rows, out_plane, res_plane, w_sample_floats;
   int out_split, Hp2, Wp2;
+  int tile_rr;                    // tiles dealt round-robin over the CTAs (streamed weights) instead of in contiguous ranges
   int stacked, n_chunks, cps;     // stacked: the N columns are `n_chunks / cps` samples x cps channel chunks (shared input)
   long long q2_total;
   int tap_off[MAX_TAPS];          // 16-byte units inside an A slot: strip * cbc * RA_p + d_before + shift
@@ -71,7 +72,7 @@ struct P4Params {
   int dual, acc_cols, lrt_mode;
   const float* x_sq; const float* eps; const float* xin; float* out2;
   long long aux_plane;                            // rows per chunk plane of eps / xin / out2 (the output's geometry)
-  unsigned long long seed; uint32_t stream_a, stream_b;
+  unsigned long long seed; uint32_t stream_a, stream_b; const uint32_t* sbase;      // sbase: device-side draw offset (qbn_set_sample_base)
   // module boundary (ops.LRTFunction): out / out2 / eps / xin are dense NHWC [B][H_out][W_out][N] tensors; the padded pixel
   // (b, hh, ww) of this launch's geometry is the NHWC pixel (b, (hh - bh) * oh_mul + oh_add, (ww - bw) * ow_mul + ow_add)
   // (mul 2 / add phase: the four phase launches of a stride-2 layer's input gradient)
@@ -136,11 +137,6 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
       s_ops[e] = make_uint2((uint32_t)p.tap_off[t] + (uint32_t)jj * a_kk, (uint32_t)(p.b_res ? t : t % p.TG) * bt16_ + (uint32_t)jj * b_kk);
     }
   }
-  for (int i = tid; i < 256; i += P4_THREADS) {
-    s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
-    // int8: the bias enters the accumulator domain exactly like FBGEMM's: fp32(bias) / fp32(s_x * s_w)
-    s_shift[i] = (p.shift && i < p.N) ? (I8 ? __fdiv_rn(p.shift[i], p.atw) : p.shift[i]) : 0.f;
-  }
   if (tid == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
@@ -149,14 +145,29 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
     fence_proxy_async();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  // Programmatic dependent launch (qbn_set_pdl): everything above — operand list, barrier init, TMEM allocation — overlaps the
+  // tail of the previous kernel in the stream; nothing below touches global memory before that kernel has completed.  The next
+  // kernel may be scheduled as soon as every CTA of this grid has passed this point (it then waits at its own
+  // griddepcontrol.wait).  Without the launch attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int i = tid; i < 256; i += P4_THREADS) {
+    s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
+    // int8: the bias enters the accumulator domain exactly like FBGEMM's: fp32(bias) / fp32(s_x * s_w)
+    s_shift[i] = (p.shift && i < p.N) ? (I8 ? __fdiv_rn(p.shift[i], p.atw) : p.shift[i]) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // contiguous tile range per CTA: consecutive tiles share the sample (=> the resident weights) and their halos hit L2
-  const int tile_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
-  const int tile_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  // Streamed weights (b_res == 0; the 96/192-channel layers): tiles are dealt round-robin instead, so that at any moment the whole
+  // grid works on the tiles of ~2-3 samples — the weight blocks every CTA streams per tile then come from L2 (one DRAM read per
+  // block instead of one per CTA group; ncu, profiles/r02_p4_dram_traffic.json: 0.6-1.0 GB of re-reads per layer-4 launch before).
+  const int tile_step = p.tile_rr ? (int)gridDim.x : 1;
+  const int tile_begin = p.tile_rr ? (int)blockIdx.x : (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
+  const int tile_end = p.tile_rr ? p.total_tiles : (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp == 5) {
     // ======================================= PRODUCER (one lane) ================================
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
       int sa = 0, sb = 0, cur_z = -1;
       uint32_t pa = 0, pb = 0;
       const uint32_t strip_bytes = (uint32_t)p.cbc * p.RA_p * 16;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int z = tile / p.tiles_per_sample;
         const int q0 = (tile - z * p.tiles_per_sample) * TM;
         const float* ws = p.w + (p.w_shared ? 0 : (size_t)z * p.w_sample_floats);
@@ -253,9 +264,9 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
       const uint64_t adesc_hi = make_smem_desc(0, lbo_a, 128), bdesc_hi = make_smem_desc(0, lbo_b, 128);
       const uint32_t a_k = (2 * lbo_a) >> 4, b_k = (2 * lbo_b) >> 4;      // one K=8 step = two 16-byte chunks
       const uint32_t bt16 = p.bt_bytes >> 4;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int z = tile / p.tiles_per_sample;
-        const bool last_of_z = (tile + 1 >= tile_end) || ((tile + 1) / p.tiles_per_sample != z);
+        const bool last_of_z = (tile + tile_step >= tile_end) || ((tile + tile_step) / p.tiles_per_sample != z);
         PROF_BEGIN();
         if (p.b_res && z != cur_z) {
           mbar_wait(smem_u32(&b_full[0]), pb);
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
     const int n_chunks = p.n_chunks;                         // 16-byte output chunks per row (all stacked samples)
     const int cps = p.cps;                                   // chunks per sample
     const bool relu = p.flags & QBN_FLAG_RELU, relu_pre = p.flags & QBN_FLAG_RELU_PRE, rnd = p.flags & QBN_FLAG_OUT_ROUND_TF32;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int z = tile / p.tiles_per_sample;
       const int q0 = (tile - z * p.tiles_per_sample) * TM;
       PROF_BEGIN();
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
                       const float4 t = ld_nc4(eptr + (long long)ch * aux_step);
                       e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
                     } else {      // one Philox call = the four channels of this chunk; the backward regenerates the same draw
-                      philox_normal4(p.seed, p.stream_a, p.stream_b, ctr0 + (unsigned long long)ch, e);
+                      philox_normal4(p.seed, p.stream_a, p.stream_b + (p.sbase ? *p.sbase : 0u), ctr0 + (unsigned long long)ch, e);
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -659,6 +670,28 @@ extern "C" int qbn_p4_weight_floats(int C, int N, int R, int S, int stride, long
   return QBN_OK;
 }
 
+// Programmatic dependent launch of the planar conv kernels (off by default; the MC engines switch it on for their graphs)
+static int g_p4_pdl = 0;
+extern "C" int qbn_set_pdl(int enabled) {
+  g_p4_pdl = enabled ? 1 : 0;
+  return QBN_OK;
+}
+template <typename K>
+static cudaError_t p4_launch(K kernel, int grid, size_t smem, cudaStream_t st, const P4Params& p) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(P4_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_p4_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 struct P4Planes { long long x, res, out, x2; };      // rows per chunk plane of each tensor (phases * maps + zero tail)
 struct P4I8 {                                        // int8 extras of a launch (NULL: TF32)
   int x_shared, z_w, z_out, q_lo, q_hi;
@@ -759,7 +792,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     QBN_CHECK_ARG(!i8 && !stacked && !x2 && !out_mask && n_samples == 1 && lrt->x_sq, "LRT launch: one 'sample', two operand tensors");
     QBN_CHECK_ARG(!(flags & QBN_FLAG_OUT_PHASE_SPLIT), "LRT launch: normal output layout");
     p.dual = 1; p.lrt_mode = lrt->mode; p.x_sq = lrt->x_sq; p.eps = lrt->eps; p.xin = lrt->xin; p.out2 = lrt->out2; p.aux_plane = lrt->aux_plane;
-    p.seed = lrt->seed; p.stream_a = lrt->stream_a; p.stream_b = lrt->stream_b;
+    p.seed = lrt->seed; p.stream_a = lrt->stream_a; p.stream_b = lrt->stream_b; p.sbase = qbn_sample_base_ptr();
     p.nhwc = lrt->nhwc; p.H_out = lrt->H_out; p.W_out = lrt->W_out;
     p.oh_mul = lrt->oh_mul; p.oh_add = lrt->oh_add; p.ow_mul = lrt->ow_mul; p.ow_add = lrt->ow_add;
     QBN_CHECK_ARG(!ct || (stride == 1 && R == 1 && S == lrt->n_taps && S <= MAX_TAPS), "explicit tap list: R = 1, S = n_taps, stride 1");
@@ -881,6 +914,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
       p.b_slot_bytes = p.bt_bytes * (uint32_t)p.TG;
     }
     p.SA = 2; p.SB = 2;
+    p.tile_rr = tune_env("QBN_P4_RR") ? atoi(tune_env("QBN_P4_RR")) : 1;
     while (p.SB < 8 && (size_t)p.SA * p.a_bytes + (size_t)(p.SB + 1) * p.b_slot_bytes + fixed <= cap / want_occ - 1024) ++p.SB;
     smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.b_slot_bytes + fixed;
   }
@@ -956,13 +990,13 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (tune_env("QBN_P4_PROF")) {
       unsigned long long h[32] = {0};
       cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
-      umma_conv_p4_kernel<1, false, false, KIND_LRT><<<grid, P4_THREADS, smem, st>>>(p);
+      p4_launch(umma_conv_p4_kernel<1, false, false, KIND_LRT>, grid, smem, st, p);
       QBN_CHECK_LAUNCH();
       prof_report(lrt->mode ? "lrt-dgrad" : "lrt-fwd");
       return QBN_OK;
     }
 #endif
-    umma_conv_p4_kernel<0, false, false, KIND_LRT><<<grid, P4_THREADS, smem, st>>>(p);
+    p4_launch(umma_conv_p4_kernel<0, false, false, KIND_LRT>, grid, smem, st, p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
@@ -971,20 +1005,20 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if (tune_env("QBN_P4_PROF")) {       // diagnostics: cycle accounting of CTA 0 (synchronises the stream)
       unsigned long long h[32] = {0};
       cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
-      umma_conv_p4_kernel<1, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
+      p4_launch(umma_conv_p4_kernel<1, false, false, KIND_I8>, grid, smem, st, p);
       QBN_CHECK_LAUNCH();
       prof_report("i8");
       return QBN_OK;
     }
 #endif
-    umma_conv_p4_kernel<0, false, false, KIND_I8><<<grid, P4_THREADS, smem, st>>>(p);
+    p4_launch(umma_conv_p4_kernel<0, false, false, KIND_I8>, grid, smem, st, p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
   if (stacked || masked) {
-    if (stacked && masked) umma_conv_p4_kernel<0, true, true><<<grid, P4_THREADS, smem, st>>>(p);
-    else if (stacked) umma_conv_p4_kernel<0, true, false><<<grid, P4_THREADS, smem, st>>>(p);
-    else umma_conv_p4_kernel<0, false, true><<<grid, P4_THREADS, smem, st>>>(p);
+    if (stacked && masked) p4_launch(umma_conv_p4_kernel<0, true, true>, grid, smem, st, p);
+    else if (stacked) p4_launch(umma_conv_p4_kernel<0, true, false>, grid, smem, st, p);
+    else p4_launch(umma_conv_p4_kernel<0, false, true>, grid, smem, st, p);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
@@ -992,13 +1026,13 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   if (tune_env("QBN_P4_PROF")) {
     unsigned long long h[32] = {0};
     cudaMemcpyToSymbol(g_p4_prof, h, sizeof(h));
-    umma_conv_p4_kernel<1, false, false><<<grid, P4_THREADS, smem, st>>>(p);
+    p4_launch(umma_conv_p4_kernel<1, false, false>, grid, smem, st, p);
     QBN_CHECK_LAUNCH();
     prof_report("tf32");
     return QBN_OK;
   }
 #endif
-  umma_conv_p4_kernel<0, false, false><<<grid, P4_THREADS, smem, st>>>(p);
+  p4_launch(umma_conv_p4_kernel<0, false, false>, grid, smem, st, p);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

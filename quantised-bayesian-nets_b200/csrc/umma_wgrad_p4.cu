@@ -17,7 +17,14 @@
 #include "p4_layout.cuh"
 #include "umma_common.cuh"
 
+#include <stdlib.h>
 namespace {
+
+#ifdef QBN_TUNING
+static inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+static inline const char* tune_env(const char*) { return nullptr; }
+#endif
 
 constexpr int WG_TM = 128;          // pixels per tile
 constexpr int WG_THREADS = 192;
@@ -33,7 +40,7 @@ struct WGParams {
   int CBW, TPG, n_pad;              // channels per input block, taps per group, MMA N (CBW rounded up to 16)
   int a_planes, b_planes;           // chunk planes staged per tile
   uint32_t a_bytes, b_bytes, idesc;
-  int tmem_cols;
+  int tmem_cols, variant;           // variant: descriptor experiments of -DQBN_TUNING builds (QBN_WG_V), 0 in the product
   const float* g; const float* dv; long long g_plane;
   const float* x; const float* xsq; long long x_plane;
   float* dmu; float* dsig2;
@@ -116,7 +123,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_p4_kernel(const __gr
       uint32_t ph = 0;
       // MN-major, no swizzle: 16-byte units are 4 channels of one pixel; 8 consecutive pixels = one 128-byte core matrix along K;
       // the next 4-channel group along M / N is one chunk plane further (SBO); LBO (next 8 pixels) = 128 bytes
-      const uint64_t adesc_hi = make_smem_desc(0, 128, WG_TM * 16), bdesc_hi = make_smem_desc(0, 128, (uint32_t)p.RA_p * 16);
+      const uint64_t adesc_hi = (p.variant & 1) ? make_smem_desc(0, WG_TM * 16, 128) : make_smem_desc(0, 128, WG_TM * 16);
+      const uint64_t bdesc_hi = (p.variant & 2) ? make_smem_desc(0, (uint32_t)p.RA_p * 16, 128) : make_smem_desc(0, 128, (uint32_t)p.RA_p * 16);
       bool first = true;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(smem_u32(&full[st]), ph);
@@ -254,6 +262,10 @@ extern "C" int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C, int C_real, int N,
   p.g = g; p.dv = dv; p.g_plane = g_plane_rows; p.x = x; p.xsq = x_sq; p.x_plane = x_plane_rows; p.dmu = dmu_p; p.dsig2 = dsig2_p;
   // F32 += TF32 x TF32, A and B MN-major (bits 15, 16), N at bit 17, M = 128 at bit 24
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (tune_env("QBN_WG_V")) {
+    p.variant = atoi(tune_env("QBN_WG_V"));
+    if (p.variant & 4) p.idesc &= ~((1u << 15) | (1u << 16));
+  }
   const int items = 2 * p.n_mb * p.n_cb * p.n_tg;
   p.n_ps = (2 * qbn_sm_count() + items - 1) / items;           // ~2 waves of single-CTA SMs: pixel ranges long enough to amortise the epilogue
   if (p.n_ps > p.n_tiles) p.n_ps = p.n_tiles;

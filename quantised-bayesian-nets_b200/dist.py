@@ -151,3 +151,56 @@ class DPTrainStep:
             allreduce_gradients(self.params, average=True)
             self.optimizer.step()
         return output, obj, main_obj, kl_term
+
+
+class GraphedTrainStep:
+    """The same step as DPTrainStep, captured ONCE in a CUDA graph and replayed: zero_grad -> forward -> KL -> criterion ->
+    backward -> NaN-grad scrub -> flat gradient all-reduce -> optimizer.step() (src/trainer.py:87-132).  A B=256 ResNet step is
+    ~250 kernel launches of 5-50 us each; eager, the host (autograd + ctypes) is the bottleneck, replayed the GPU never waits.
+
+    * input / target live in static device buffers (`step(input, target)` copies into them: host tensors are fine, pinned is best);
+    * fresh noise every replay without re-capturing: the layers' Philox keys are frozen in the graph, the device-side draw
+      offset (noise.set_draw_offset) advances by the number of draws of one step before every replay — the draw sequence is the
+      one the eager loop would have used;
+    * the optimizer must be capturable (torch.optim.Adam(..., capturable=True)); the reference's `obj == obj` host check
+      (trainer.py:103) is replaced by the multi-rank rule of DPTrainStep: NaN gradients are zeroed before the all-reduce.
+    `warmup` eager steps (real optimisation steps, on the first batch) run before the capture, as torch's capture recipe requires."""
+
+    def __init__(self, model, criterion, optimizer, input, target, n_batches, n_points, gamma=0.0, warmup=3):
+        from . import noise
+        for grp in optimizer.param_groups:
+            if grp.get("capturable", True) is False:
+                raise ValueError("GraphedTrainStep needs a capturable optimizer, e.g. torch.optim.Adam(params, capturable=True)")
+        self.eager = DPTrainStep(model, criterion, optimizer, gamma=gamma, check_nan_loss=False)
+        self.noise = noise
+        self.device = next(model.parameters()).device
+        self.input = torch.empty_like(input, device=self.device)
+        self.target = torch.empty_like(target, device=self.device)
+        self.input.copy_(input)
+        self.target.copy_(target)
+        self.n_batches, self.n_points = n_batches, n_points
+        noise.set_draw_offset(0, self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, int(warmup))):
+                self.eager(self.input, self.target, n_batches, n_points)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.steps_done = max(1, int(warmup))
+        optimizer.zero_grad(set_to_none=True)
+        c0 = noise._state["counter"]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self.eager(self.input, self.target, n_batches, n_points)
+        self.draws_per_step = (noise._state["counter"] - c0) & 0xFFFFFFFF
+        self.replays = 0
+
+    def __call__(self, input=None, target=None):
+        if input is not None:
+            self.input.copy_(input, non_blocking=True)
+            self.target.copy_(target, non_blocking=True)
+        self.noise.set_draw_offset(self.replays * self.draws_per_step, self.device)
+        self.graph.replay()
+        self.replays += 1
+        self.steps_done += 1
+        return self.out

@@ -21,7 +21,7 @@ reproduces the single-GPU result up to summation order.
 import torch
 import torch.nn as nn
 
-from . import config, noise, ops
+from . import _lib, config, noise, ops
 from ._lib import QBN_MATH_FP32, QBN_MATH_TF32
 from .stochastic.bbb.conv import Conv2d as BBBConv2d
 from .stochastic.bbb.linear import Linear as BBBLinear
@@ -841,8 +841,12 @@ class MCEngine:
             torch.cuda.synchronize()
             l0 = self.launches
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = self._predict_sum_eager(static_x, samples, sample0, None)
+            _lib.call("qbn_set_pdl", int(config.pdl()))      # programmatic dependent launches between the captured convs
+            try:
+                with torch.cuda.graph(g):
+                    static_out = self._predict_sum_eager(static_x, samples, sample0, None)
+            finally:
+                _lib.call("qbn_set_pdl", 0)
             ent = (g, static_x, static_out, self.launches - l0)
             self.launches = l0
             graphs[key] = ent

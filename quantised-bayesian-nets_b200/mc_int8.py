@@ -13,7 +13,7 @@ Same interface as `mc.MCEngine` where it matters (`predict`, `predict_sum(x, cou
 `dist.ShardedMCPredictor` shards the samples of an int8 model over GPUs with its single all-reduce."""
 import torch
 
-from . import noise, ops
+from . import _lib, config, noise, ops
 from .stochastic.mcdropout.dropout import BernoulliDropout
 
 
@@ -335,8 +335,12 @@ class Int8PlanarEngine:
             torch.cuda.synchronize()
             l0 = self.launches
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = self._predict_sum_eager(static_x, samples, sample0)
+            _lib.call("qbn_set_pdl", int(config.pdl()))      # programmatic dependent launches between the captured convs
+            try:
+                with torch.cuda.graph(g):
+                    static_out = self._predict_sum_eager(static_x, samples, sample0)
+            finally:
+                _lib.call("qbn_set_pdl", 0)
             ent = (g, static_x, static_out, self.launches - l0)
             self.launches = l0
             graphs[key] = ent

@@ -178,6 +178,8 @@ class LRTFunction(torch.autograd.Function):
         ctx.chan_scale = chan_scale
         ctx.planar = (math_mode == QBN_MATH_TF32 and chan_scale is None and xc.dim() == 4
                       and lrt_p4_eligible(d, need_dx=ctx.needs_input_grad[0]))
+        if not ctx.planar and math_mode == QBN_MATH_TF32 and (d.C % 4 or 2 * _ceil(d.N, 16) > 512):
+            math_mode = ctx.math_mode = QBN_MATH_FP32      # shapes the tcgen05 gather kernels do not take (config.tf32_eligible)
         if ctx.planar:
             # TF32 mode on the planar zero-copy kernels: operands staged once, every contraction of forward and backward on tcgen05
             out, std, x_p4, xsq_p4 = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key)

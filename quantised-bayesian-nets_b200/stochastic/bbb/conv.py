@@ -25,7 +25,9 @@ class Conv2d(nn.Conv2d):
             return eval_forward(self, X, self.stride, self.padding, self.dilation)      # conv.py:33-39
         # conv.py:24-32.  NOTE the reference adds a [N] bias to an NCHW tensor without reshaping (conv.py:32), which only
         # broadcasts when Wo == N; every reference model uses bias=False.  Here the bias is added per output channel.
-        mode = config.pick_math_mode(self.in_channels, self.out_channels, lrt=True)
+        # the requested mode: LRTFunction takes the planar tcgen05 path when the shape allows (TF32; C zero-padded to a multiple of 8,
+        # so the 3-channel first layer too), else the gather kernels in the mode config.pick_math_mode allows for this shape
+        mode = config.math_mode()
         return ops.LRTFunction.apply(X, self.weight, self.std, self.bias, self.stride, self.padding, self.dilation,
                                      noise.pop_injected(), self._key(), mode, False, None)
 

@@ -42,3 +42,15 @@ def golden_dir():
     import pathlib
     return pathlib.Path(GOLDEN)
 
+
+
+@pytest.fixture(autouse=True)
+def _zero_draw_offset():
+    """The device-side draw offset (noise.set_draw_offset) is process-wide state: every test starts from offset 0."""
+    yield
+    try:
+        from qbn_b200 import noise
+        for t in noise._draw_base.values():
+            t.zero_()
+    except Exception:
+        pass
