@@ -238,6 +238,8 @@ def train_leg(torch, dist, dev, rank, world, steps, math):
         step(x, t, 176, 45000)
     ms_eager, out = timed(lambda: step(x, t, 176, 45000))
     ms_step, mode = ms_eager, "eager (one Python-driven step per iteration)"
+    loss_eager = float(out[1].detach())
+    out = None        # a live loss keeps the eager autograd graph (and its default-stream AccumulateGrad nodes) alive: capture would fail
     graph_note, gstep = None, None
     try:       # the whole step replayed from one CUDA graph (dist.GraphedTrainStep): fresh noise per replay via the device-side draw offset
         gstep = qdist.GraphedTrainStep(model, crit, opt, x, t, 176, 45000, gamma=0.01, warmup=3)
@@ -247,10 +249,9 @@ def train_leg(torch, dist, dev, rank, world, steps, math):
         ms_step, mode = ms_graph, "one CUDA graph per step (dist.GraphedTrainStep), fresh noise every replay"
     except Exception as e:      # noqa: BLE001 - reported, never hidden
         graph_note = "graph capture failed (%s: %s); eager number reported" % (type(e).__name__, str(e)[:200])
-    obj = out[1]
     peak = _peaks()["bf16_tflops_sustained"] / 2.0
     tf = FLOP_TRAIN_PER_IMAGE * B * world / (ms_step * 1e-3) / 1e12
-    loss = float(obj.detach())
+    loss = float(out[1].detach()) if out is not None else loss_eager
     del model, opt, step, gstep
     return {"metric": "resnet18_bbb_lrt_train_images_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "images/s", "ms_per_step": ms_step,
             "steps": steps, "scaling": "weak", "dtype": math, "loss": loss, "mode": mode, "ms_per_step_eager": ms_eager, "graph_note": graph_note,

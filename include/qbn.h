@@ -336,7 +336,8 @@ int qbn_i8_p16_avgpool(const int8_t* x, int64_t n_img, int H, int W, int C, int3
  * trainer.py:104).  The module boundary stays dense NHWC; per layer the operands are staged once into planar-C4 zero-bordered
  * maps (phase-split for a stride-2 layer) and every contraction — forward (mean and variance side by side in TMEM), input
  * gradient (the same kernel on flipped / transposed weights; four phase launches for a stride-2 layer), weight gradients
- * (pixels as the reduction dimension, both operands MN-major straight from the planar maps) — runs on tcgen05 without a gather.
+ * (pixels as the reduction dimension, both operands MN-major from a swizzled 32-channel-block copy of the maps) — runs on tcgen05
+ * without a gather.
  * Eligible: C_pad % 8 == 0, N % 8 == 0, N <= 256, stride 1 with an odd 'same' filter or stride 2 with 3x3 pad 1 / 1x1 pad 0.
  * Every plane must hold ceil(rows / 128) * 128 + 128 + 2 * (Wp + 1) + 8 rows (rows = phases * n_img * Hp * Wp).            */
 /* x NHWC [n_img][H][W][C] -> x_p4 = tf32(x), xsq_p4 = tf32(x * x) (nullable), planes [C_pad/4][plane_rows][4], border (bh, bw) */
@@ -364,9 +365,13 @@ int qbn_lrt_conv_p4_dgrad(int B, int Hp, int Wp, int C, int N, int R, int S, con
 int qbn_lrt_conv_p4_dgrad_phase(int B, int Hp, int Wp, int C, int N, int n_taps, const int* shifts, int phase_a, int phase_b,
                                 const float* g_p4, const float* dv_p4, long long g_plane_rows, const float* w_phase_blocked,
                                 const float* xin, float* dx, void* stream);
-/* dmu_p / dsig2_p [N][R*S][C_real] (packed OHWI, overwritten) = sum over pixels of g (x) x and dv (x) x^2, from the planar maps */
-int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_pad, int C_real, int N, int R, int S, int stride, const float* g_p4,
-                     const float* dv_p4, long long g_plane_rows, const float* x_p4, const float* xsq_p4, long long x_plane_rows,
+/* planar-C4 maps [C_pad/4][plane_rows][4] (as staged above, borders and tail included) -> "W32": [ceil(C_pad/32)][plane_rows][32]
+ * floats, the four 32-byte chunks of row r XORed with r & 3 — the global image of the one shared-memory layout in which
+ * tcgen05.mma kind::tf32 accepts MN-major operands (SWIZZLE_128B_BASE32B).  src1 / dst1 nullable: a second tensor, same launch. */
+int qbn_w32_from_p4(const float* src0, const float* src1, int C_pad, long long plane_rows, float* dst0, float* dst1, void* stream);
+/* dmu_p / dsig2_p [N][R*S][C_real] (packed OHWI, overwritten) = sum over pixels of g (x) x and dv (x) x^2, operands in W32 */
+int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_real, int N, int R, int S, int stride, const float* g_w32,
+                     const float* dv_w32, long long g_plane_rows, const float* x_w32, const float* xsq_w32, long long x_plane_rows,
                      float* dmu_p, float* dsig2_p, void* stream);
 
 /* Programmatic dependent launch of the planar convolution kernels (qbn_conv_p4_fwd, qbn_conv_p4_shortcut_fwd, qbn_i8_conv_p16_fwd,

@@ -122,7 +122,8 @@ _SIGNATURES = {
     "qbn_lrt_conv_p4_dgrad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, P]),
     "qbn_lrt_conv_p4_dgrad_phase": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, P, P, ctypes.c_longlong, P,
                                             P, P, P]),
-    "qbn_lrt_wgrad_p4": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, ctypes.c_longlong,
+    "qbn_w32_from_p4": (c_int, [P, P, c_int, ctypes.c_longlong, P, P, P]),
+    "qbn_lrt_wgrad_p4": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, ctypes.c_longlong,
                                  P, P, P]),
     "qbn_avgpool_p4": (c_int, [P, c_int64, c_int, c_int64, c_int, c_float, P, P]),
 }

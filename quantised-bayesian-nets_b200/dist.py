@@ -164,10 +164,14 @@ class GraphedTrainStep:
       one the eager loop would have used;
     * the optimizer must be capturable (torch.optim.Adam(..., capturable=True)); the reference's `obj == obj` host check
       (trainer.py:103) is replaced by the multi-rank rule of DPTrainStep: NaN gradients are zeroed before the all-reduce.
-    `warmup` eager steps (real optimisation steps, on the first batch) run before the capture, as torch's capture recipe requires."""
+    `warmup` eager steps (real optimisation steps, on the first batch) run before the capture, as torch's capture recipe requires.
+    Drop every reference to losses / outputs of earlier eager steps of this model first: a live autograd graph pins the parameters'
+    AccumulateGrad nodes to the default stream and invalidates the capture."""
 
     def __init__(self, model, criterion, optimizer, input, target, n_batches, n_points, gamma=0.0, warmup=3):
+        import gc
         from . import noise
+        gc.collect()      # an autograd graph of an earlier eager step that is still referenced keeps default-stream AccumulateGrad nodes alive
         for grp in optimizer.param_groups:
             if grp.get("capturable", True) is False:
                 raise ValueError("GraphedTrainStep needs a capturable optimizer, e.g. torch.optim.Adam(params, capturable=True)")

@@ -182,8 +182,8 @@ class LRTFunction(torch.autograd.Function):
             math_mode = ctx.math_mode = QBN_MATH_FP32      # shapes the tcgen05 gather kernels do not take (config.tf32_eligible)
         if ctx.planar:
             # TF32 mode on the planar zero-copy kernels: operands staged once, every contraction of forward and backward on tcgen05
-            out, std, x_p4, xsq_p4 = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key)
-            ctx.save_for_backward(xc, x_p4, xsq_p4, std, eps_c, weight.detach(), second.detach())
+            out, std, x_w32, xsq_w32 = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key)
+            ctx.save_for_backward(xc, x_w32, xsq_w32, std, eps_c, weight.detach(), second.detach())
             return out
         packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))   # backward needs them unrounded
         fw = packed if math_mode != QBN_MATH_TF32 else weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"), round_tf32=True)
@@ -196,8 +196,8 @@ class LRTFunction(torch.autograd.Function):
         gc = nhwc(_f32(g))
         need_dx = ctx.needs_input_grad[0]
         if ctx.planar:
-            xc, x_p4, xsq_p4, std, eps_c, weight, second = ctx.saved_tensors
-            dx, dmu_p, dsig2_p = lrt_p4_backward(xc, x_p4, xsq_p4, std, eps_c, weight, second, ctx.second_is_sigma, gc, ctx.d, ctx.key, need_dx)
+            xc, x_w32, xsq_w32, std, eps_c, weight, second = ctx.saved_tensors
+            dx, dmu_p, dsig2_p = lrt_p4_backward(xc, x_w32, xsq_w32, std, eps_c, weight, second, ctx.second_is_sigma, gc, ctx.d, ctx.key, need_dx)
             dbias = gc.sum(dim=(0, 2, 3)) if ctx.has_bias else None
         else:
             xc, mu_p, sig2_p, std, eps_c, second = ctx.saved_tensors
@@ -259,8 +259,9 @@ def lrt_p4_weight_prep(weight, second, second_is_sigma, d, mode, tap_list=None):
     return out
 
 
-def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(0, 0, 0)):
-    """xc NHWC-dense [B, C, H, W] (channels_last).  Returns out, std (NHWC) and the staged planar operands (kept for the backward)."""
+def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(0, 0, 0), want_w32=True):
+    """xc NHWC-dense [B, C, H, W] (channels_last).  Returns out, std (NHWC) and the operands the backward needs: x, x^2 in the W32
+    layout of the weight-gradient kernel (want_w32=False: the planar-C4 maps the forward itself read)."""
     s2, bh, bw, Hp, Wp, C_pad = _lrt_p4_geom(d)
     rows = (4 if s2 else 1) * d.B * Hp * Wp
     pr = lrt_p4_plane_rows(rows, Wp)
@@ -271,10 +272,23 @@ def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(
     out, std = _out_like(xc, d), _out_like(xc, d)
     _lib.call("qbn_lrt_conv_p4_fwd", d.B, Hp, Wp, C_pad, d.N, d.R, d.S, d.stride_h, _ptr(x_p4), _ptr(xsq_p4), pr, _ptr(w), _ptr(bias), _ptr(eps),
               key[0], key[1], key[2], _ptr(out), _ptr(std), _stream())
-    return out, std, x_p4, xsq_p4
+    if not want_w32:
+        return out, std, x_p4, xsq_p4
+    # the weight-gradient kernel reads MN-major operands: the swizzled 32-channel-block copy is what the backward keeps
+    x_w32, xsq_w32 = w32_from_p4(x_p4, xsq_p4)
+    return out, std, x_w32, xsq_w32
 
 
-def lrt_p4_backward(xc, x_p4, xsq_p4, std, eps, weight, second, second_is_sigma, gc, d, key=(0, 0, 0), need_dx=True):
+def w32_from_p4(a, b=None):
+    """planar C4 [C_pad/4, rows, 4] -> W32 [ceil(C_pad/32), rows, 32] (include/qbn.h: qbn_w32_from_p4); b: a second tensor of the same shape."""
+    chunks, rows = a.shape[0], a.stride(0) // 4
+    oa = torch.empty(((chunks + 7) // 8, rows, 32), dtype=torch.float32, device=a.device)
+    ob = torch.empty_like(oa) if b is not None else None
+    _lib.call("qbn_w32_from_p4", _ptr(a), _ptr(b), chunks * 4, rows, _ptr(oa), _ptr(ob), _stream())
+    return (oa, ob) if b is not None else oa
+
+
+def lrt_p4_backward(xc, x_w32, xsq_w32, std, eps, weight, second, second_is_sigma, gc, d, key=(0, 0, 0), need_dx=True):
     """Closed-form backward of SURVEY 8a row A3 on the planar kernels.  Returns dx (NHWC or None), dmu_p, dsig2_p (packed OHWI)."""
     s2, bh, bw, Hp, Wp, C_pad = _lrt_p4_geom(d)
     weight, second = weight.contiguous(), second.contiguous()
@@ -285,8 +299,9 @@ def lrt_p4_backward(xc, x_p4, xsq_p4, std, eps, weight, second, second_is_sigma,
               _ptr(dv_p4), _stream())
     dmu_p = torch.empty(d.N * d.R * d.S * d.C, dtype=torch.float32, device=gc.device)
     dsig2_p = torch.empty_like(dmu_p)
-    _lib.call("qbn_lrt_wgrad_p4", d.B, Hp, Wp, C_pad, d.C, d.N, d.R, d.S, d.stride_h, _ptr(g_p4), _ptr(dv_p4), pr_g, _ptr(x_p4), _ptr(xsq_p4),
-              x_p4.stride(0) // 4, _ptr(dmu_p), _ptr(dsig2_p), _stream())
+    g_w32, dv_w32 = w32_from_p4(g_p4, dv_p4)
+    _lib.call("qbn_lrt_wgrad_p4", d.B, Hp, Wp, d.C, d.N, d.R, d.S, d.stride_h, _ptr(g_w32), _ptr(dv_w32), pr_g, _ptr(x_w32), _ptr(xsq_w32),
+              x_w32.stride(0) // 32, _ptr(dmu_p), _ptr(dsig2_p), _stream())
     dx = None
     if need_dx:
         if not s2:
