@@ -42,6 +42,8 @@ struct WGParams {
   int NB, TPG, n_cols;              // 32-channel blocks per MMA N, taps per group, MMA N = 32 * NB
   uint32_t a_bytes, b_bytes, b_blk_bytes, b_strip_bytes, idesc;
   int tmem_cols, ST;
+  int stack, stack_bw, stack_rows;   // stack = S > 0: the S column shifts of a filter row stacked along N (stride 1, one 32-channel input block)
+  uint32_t b_lbo;                    // bytes between the 32-channel blocks of the B operand
   const float* g; const float* dv; long long g_plane;       // W32 tensors: rows per block plane
   const float* x; const float* xsq; long long x_plane;
   float* dmu; float* dsig2;
@@ -74,7 +76,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_p4_kernel(const __gr
   float* out = kind ? p.dsig2 : p.dmu;
   const int a_blk0 = mb * 4, a_load = min(4, p.n_blk_a_total - a_blk0);
   const int b_blk0 = cb * p.NB, b_load = min(p.NB, p.n_blk_b_total - b_blk0);
-  const int t_begin = tg * p.TPG, t_end = min(p.taps, t_begin + p.TPG);
+  const int n_acc = p.stack ? p.taps / p.stack : p.taps;          // accumulators: filter rows when the columns are stacked, else taps
+  const int t_begin = tg * p.TPG, t_end = min(n_acc, t_begin + p.TPG);
   const int tile_begin = (int)(((long long)p.n_tiles * ps) / p.n_ps), tile_end = (int)(((long long)p.n_tiles * (ps + 1)) / p.n_ps);
 
   // stale shared memory must not hold NaNs where zeros are expected (rows in front of the first map, blocks beyond the tensor: they
@@ -102,6 +105,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_p4_kernel(const __gr
         mbar_wait(smem_u32(&empty[st]), ph ^ 1);
         const uint32_t bar = smem_u32(&full[st]);
         const uint32_t a_slot = smem_u32(a_ring + (size_t)st * p.a_bytes), b_slot = smem_u32(b_ring + (size_t)st * p.b_bytes);
+        if (p.stack) {
+          // block s = the rows shifted by (s - bw) pixels: rows [q0 - bh*Wp + s - bw, ... + stack_rows); blocks are b_lbo = RA_pad*128 + 128
+          // bytes apart, so that block s starts one row further (mod 4) and the XOR key of every block follows its global rows
+          uint32_t tx = (uint32_t)a_load * WG_TM * 128;
+          long long los[8];
+          for (int sft = 0; sft < p.stack; ++sft) {
+            const long long gs = q0 - p.d_before + p.stack_bw + (sft - p.stack_bw);
+            los[sft] = gs < 0 ? 0 : gs;
+            tx += (uint32_t)(gs + p.stack_rows - los[sft]) * 128;
+          }
+          mbar_arrive_expect_tx(bar, tx);
+          for (int j = 0; j < a_load; ++j)
+            bulk_load_g2s(a_slot + (uint32_t)j * WG_TM * 128, A + ((size_t)(a_blk0 + j) * p.g_plane + q0) * 32, WG_TM * 128, bar);
+          for (int sft = 0; sft < p.stack; ++sft) {
+            const long long gs = q0 - p.d_before + sft;
+            bulk_load_g2s(b_slot + (uint32_t)sft * p.b_lbo + (uint32_t)(p.strip_pad[0] + (int)(los[sft] - gs)) * 128,
+                          Bx + ((size_t)b_blk0 * p.x_plane + los[sft]) * 32, (uint32_t)(gs + p.stack_rows - los[sft]) * 128, bar);
+          }
+          if (++st == p.ST) { st = 0; ph ^= 1; }
+          continue;
+        }
         // x rows [g0, g0 + RA) of every strip, clamped at the tensor's first row; shared row = strip_pad + (global row - g0)
         const long long g0 = q0 - p.d_before;
         const long long lo = g0 < 0 ? 0 : g0;
@@ -120,7 +144,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_p4_kernel(const __gr
     if (elect_one()) {
       int st = 0;
       uint32_t ph = 0;
-      const uint64_t adesc_hi = make_mn_desc(WG_TM * 128, 512), bdesc_hi = make_mn_desc(p.b_blk_bytes, 512);
+      const uint64_t adesc_hi = make_mn_desc(WG_TM * 128, 512), bdesc_hi = make_mn_desc(p.b_lbo, 512);
       bool first = true;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(smem_u32(&full[st]), ph);
@@ -155,16 +179,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_p4_kernel(const __gr
       const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
       const int K = p.taps * p.C_real;
       const int c_base = b_blk0 * 32;
+      const bool vec4 = (p.C_real & 3) == 0;                     // rows of the result are 16-byte aligned
+      const int n_cg = p.stack ? 32 * p.stack : 32 * b_load;
       for (int t = t_begin; t < t_end; ++t) {
-        for (int cg = 0; cg < 32 * b_load; cg += 16) {
+        for (int cg = 0; cg < n_cg; cg += 16) {
           uint32_t v[16];
           tmem_ld16(tlane + (uint32_t)((t - t_begin) * p.n_cols + cg), v);
           tmem_ld_wait();
+          // stacked: accumulator t = filter row, column block cg / 32 = filter column; else accumulator t = tap, columns = channels
+          const int tap = p.stack ? t * p.stack + (cg >> 5) : t;
+          const int c0 = p.stack ? (cg & 31) : c_base + cg;
           if (mine) {
+            float* dst = out + (size_t)n * K + (size_t)tap * p.C_real + c0;
+            if (vec4 && c0 + 16 <= p.C_real) {
+              // 16-byte vector reductions (sm_90+): a quarter of the atomic instructions, 16 bytes per sector instead of 4
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = c_base + cg + j;
-              if (c < p.C_real) atomicAdd(out + (size_t)n * K + (size_t)t * p.C_real + c, __uint_as_float(v[j]));
+              for (int j = 0; j < 16; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                             "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.C_real) atomicAdd(dst + j, __uint_as_float(v[j]));
             }
           }
         }
@@ -182,22 +219,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_p4_kernel(const __gr
 // planar C4 [chunks][plane_rows][4] -> W32 [ceil(chunks / 8)][plane_rows][32], the 32-byte chunks of row r XORed with r & 3
 __global__ void w32_from_p4_kernel(const float4* __restrict__ s0, const float4* __restrict__ s1, int chunks, long long plane_rows, float4* __restrict__ d0,
                                    float4* __restrict__ d1) {
-  const int n_c8 = (chunks + 7) / 8 * 4;                          // 8-channel chunks, whole 32-channel blocks
-  const long long total = (long long)n_c8 * plane_rows;
+  // one thread = one 16-byte piece of a W32 row: a warp writes four whole rows (512 contiguous bytes) and reads 64 contiguous bytes
+  // (4 rows) from each of 8 planes
+  const int n_blk = (chunks + 7) / 8;
+  const long long total = (long long)n_blk * plane_rows * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i / plane_rows);                         // row fastest: coalesced planar reads, sector-sized W32 writes
-    const long long r = i - (long long)c8 * plane_rows;
-    const int blk = c8 >> 2, pos = (c8 & 3) ^ (int)(r & 3);
-    const long long dst = ((long long)blk * plane_rows + r) * 8 + pos * 2;      // float4 units: 8 per 128-byte row
+    const int piece = (int)(i & 7);
+    const long long br = i >> 3;                                  // blk * plane_rows + r
+    const int blk = (int)(br / plane_rows);
+    const long long r = br - (long long)blk * plane_rows;
+    const int c8 = (piece >> 1) ^ (int)(r & 3);                   // the 8-channel chunk stored at this position of row r
+    const int plane = blk * 8 + c8 * 2 + (piece & 1);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool h0 = 2 * c8 < chunks, h1 = 2 * c8 + 1 < chunks;
-    const long long a = (long long)(2 * c8) * plane_rows + r, b = a + plane_rows;
-    d0[dst] = h0 ? s0[a] : z;
-    d0[dst + 1] = h1 ? s0[b] : z;
-    if (s1) {
-      d1[dst] = h0 ? s1[a] : z;
-      d1[dst + 1] = h1 ? s1[b] : z;
-    }
+    const bool has = plane < chunks;
+    const long long src = (long long)plane * plane_rows + r;
+    d0[i] = has ? s0[src] : z;
+    if (s1) d1[i] = has ? s1[src] : z;
   }
 }
 
@@ -209,7 +246,7 @@ extern "C" int qbn_w32_from_p4(const float* src0, const float* src1, int C_pad, 
   QBN_CHECK_ARG(src0 && dst0 && (!src1 || dst1), "null pointer");
   QBN_CHECK_ARG(C_pad > 0 && C_pad % 4 == 0 && plane_rows > 0, "sizes");
   const int chunks = C_pad / 4;
-  const long long total = (long long)((chunks + 7) / 8 * 4) * plane_rows;
+  const long long total = (long long)((chunks + 7) / 8) * plane_rows * 8;
   w32_from_p4_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src0), reinterpret_cast<const float4*>(src1),
                                                                                 chunks, plane_rows, reinterpret_cast<float4*>(dst0),
                                                                                 reinterpret_cast<float4*>(dst1));
@@ -254,6 +291,25 @@ extern "C" int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_real, int N, int R,
   // input-channel blocks per MMA: the most (<= 3, N <= 96 columns) whose two stages fit next to the g tiles
   const size_t cap = 224 * 1024;
   size_t smem = 0;
+  // stride 1, one input block (C <= 32), all R accumulators of 32 * S columns in TMEM: the S column shifts of a filter row are stacked
+  // along N (one MMA covers S taps; its cost is set by the A operand read), each from its own copy of the rows
+  if (s1 && p.n_blk_b_total == 1 && S > 1 && S <= 8 && R * 32 * S <= 512) {
+    p.stack = S; p.stack_bw = bw;
+    p.stack_rows = WG_TM + 2 * bh * Wp;
+    p.RA_pad = (p.stack_rows + 3 + 3) / 4 * 4;
+    p.b_lbo = (uint32_t)p.RA_pad * 128 + 128;
+    p.NB = 1;
+    p.b_bytes = ((uint32_t)S * p.b_lbo + 511) / 512 * 512;
+    p.b_strip_bytes = p.b_bytes;
+    for (p.ST = WG_ST; p.ST >= 1; --p.ST) {
+      size_t need = (size_t)p.ST * ((size_t)p.a_bytes + p.b_bytes);
+      const size_t window = (size_t)(p.ST - 1) * p.a_bytes + 4 * (size_t)WG_TM * 128;
+      if (need < window) need = window;
+      if (need <= cap) { smem = need; break; }
+    }
+    if (!smem) { p.stack = 0; p.RA_pad = (p.RA + 3 + 3) / 4 * 4; }
+  }
+  if (!p.stack) {
   for (p.ST = WG_ST; p.ST >= 1 && !smem; --p.ST)
     for (p.NB = p.n_blk_b_total < 3 ? p.n_blk_b_total : 3; p.NB >= 1 && !smem; --p.NB) {
       size_t need = (size_t)p.ST * ((size_t)p.a_bytes + (size_t)p.n_strips * p.NB * p.b_blk_bytes);
@@ -267,14 +323,23 @@ extern "C" int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_real, int N, int R,
 fits:
   p.b_strip_bytes = (uint32_t)p.NB * p.b_blk_bytes;
   p.b_bytes = (uint32_t)p.n_strips * p.b_strip_bytes;
+  p.b_lbo = p.b_blk_bytes;
+  }
   p.n_cb = (p.n_blk_b_total + p.NB - 1) / p.NB;
-  p.n_cols = 32 * p.NB;
+  p.n_cols = p.stack ? 32 * p.stack : 32 * p.NB;
+  const int n_acc = p.stack ? R : p.taps;                      // accumulators: filter rows (stacked) or taps
   p.TPG = 512 / p.n_cols;
-  if (p.TPG > p.taps) p.TPG = p.taps;
-  p.n_tg = (p.taps + p.TPG - 1) / p.TPG;
-  p.TPG = (p.taps + p.n_tg - 1) / p.n_tg;                      // balanced groups
+  if (p.TPG > n_acc) p.TPG = n_acc;
+  p.n_tg = (n_acc + p.TPG - 1) / p.TPG;
+  p.TPG = (n_acc + p.n_tg - 1) / p.n_tg;                       // balanced groups
   p.tmem_cols = 32;
   while (p.tmem_cols < p.TPG * p.n_cols) p.tmem_cols <<= 1;
+  if (p.stack) {
+    // block s holds the rows from q0 - bh*Wp + (s - bw) on: its first row's parity is (s - (bh*Wp + bw)) & 3 and the block itself starts
+    // s rows further (mod 4), so one pad serves every block; filter row r starts r * Wp rows into the block
+    p.strip_pad[0] = (int)((((-(long long)p.d_before) % 4) + 4) % 4);
+    for (int r = 0; r < R; ++r) p.tap_off[r] = p.strip_pad[0] + r * Wp;
+  } else {
   for (int s = 0; s < p.n_strips; ++s) {
     const long long first = (long long)s * p.strip_rows - p.d_before;      // first needed global row of strip s for the tile q0 = 0
     p.strip_pad[s] = (int)(((first % 4) + 4) % 4);
@@ -287,6 +352,7 @@ fits:
       else sh = 0;
       p.tap_off[r * S + s] = strip * p.NB * p.RA_pad + p.strip_pad[strip] + p.d_before + sh;
     }
+  }
   const long long need_g = (long long)p.n_tiles * WG_TM, need_x = (long long)p.n_tiles * WG_TM + d_after + 8 + (long long)(p.n_strips - 1) * p.strip_rows;
   if (g_plane_rows < need_g || x_plane_rows < need_x) {
     qbn_set_error("qbn_lrt_wgrad_p4: planes too short (g %lld < %lld or x %lld < %lld rows): allocate a zero tail of 128 + 2 (Wp + 1) + 8 rows", g_plane_rows,
@@ -297,7 +363,10 @@ fits:
   // F32 += TF32 x TF32, A and B MN-major (bits 15, 16), N at bit 17, M = 128 at bit 24
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const int items = 2 * p.n_mb * p.n_cb * p.n_tg;
-  p.n_ps = (2 * qbn_sm_count() + items - 1) / items;           // ~2 waves of single-CTA SMs: pixel ranges long enough to amortise the epilogue
+  // pixel splits: every CTA adds its whole [128][taps][columns] partial to the result at the end, so a split costs TPG * n_cols * 128
+  // reductions while a tile costs TPG * 16 MMAs: one wave of CTAs, and at least ~4 tiles per CTA where the layer has them
+  p.n_ps = (qbn_sm_count() + items - 1) / items;
+  if (p.n_ps > (p.n_tiles + 3) / 4) p.n_ps = (p.n_tiles + 3) / 4;
   if (p.n_ps > p.n_tiles) p.n_ps = p.n_tiles;
   if (p.n_ps < 1) p.n_ps = 1;
   QBN_CUDA(cudaMemsetAsync(dmu_p, 0, sizeof(float) * (size_t)N * p.taps * C_real, st));
