@@ -212,7 +212,7 @@ def train_leg(torch, dist, dev, rank, world, steps, math):
     config.set_math_mode(math)
     model = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).to(dev).train()
     noise.manual_seed(1234 + rank)                       # independent epsilon substreams per replica
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, capturable=True)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, capturable=True, fused=True)
     args = zoo.Args(loss_multiplier=1.0)
     crit = losses.LOSS_FACTORY["classification"](args, "batch")
     step = qdist.DPTrainStep(model, crit, opt, gamma=0.01, check_nan_loss=False)

@@ -340,6 +340,9 @@ int qbn_i8_p16_avgpool(const int8_t* x, int64_t n_img, int H, int W, int C, int3
  * without a gather.
  * Eligible: C_pad % 8 == 0, N % 8 == 0, N <= 256, stride 1 with an odd 'same' filter or stride 2 with 3x3 pad 1 / 1x1 pad 0.
  * Every plane must hold ceil(rows / 128) * 128 + 128 + 2 * (Wp + 1) + 8 rows (rows = phases * n_img * Hp * Wp).            */
+/* eps[i] = element i of the Philox stream (seed, stream_a, stream_b + draw offset): the noise the LRT kernels draw in their epilogue
+ * when eps is NULL, materialised (the planar training path generates it at full occupancy and keeps it for the backward) */
+int qbn_lrt_noise(float* out, int64_t n, uint64_t seed, uint32_t stream_a, uint32_t stream_b, void* stream);
 /* x NHWC [n_img][H][W][C] -> x_p4 = tf32(x), xsq_p4 = tf32(x * x) (nullable), planes [C_pad/4][plane_rows][4], border (bh, bw) */
 int qbn_p4_stage_input(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
                        long long plane_rows, float* x_p4, float* xsq_p4, void* stream);

@@ -70,7 +70,8 @@ __global__ void philox_u32_kernel(uint32_t* __restrict__ out, int64_t n, uint64_
   }
 }
 
-__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb) {
+__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb, const uint32_t* __restrict__ sbase) {
+  if (sbase) sb += *sbase;           // device-side draw offset (qbn_set_sample_base)
   int64_t n4 = (n + 3) >> 2;
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n4; c += (int64_t)gridDim.x * blockDim.x) {
     float z[4];
@@ -108,7 +109,18 @@ extern "C" int qbn_philox_u32(uint32_t* out, int64_t n, uint64_t seed, uint32_t 
 extern "C" int qbn_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb, void* stream) {
   QBN_CHECK_ARG(out && n >= 0, "out/n");
   if (n == 0) return QBN_OK;
-  philox_normal_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, sa, sb);
+  philox_normal_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, sa, sb, nullptr);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+// The LRT noise of one layer and forward (linear.py:37-38, conv.py:29-30) as a tensor: eps[i] = element i of the Philox stream
+// (seed, stream_a, stream_b + *sample_base) — exactly the draw the LRT kernels make in their epilogue when eps is NULL.  At the
+// small per-launch sizes of a training step the conv epilogue (8 warps per SM) is latency-bound on the Philox / Box-Muller chain;
+// this kernel runs at full occupancy, and the backward reads the tensor instead of regenerating it.
+extern "C" int qbn_lrt_noise(float* out, int64_t n, uint64_t seed, uint32_t sa, uint32_t sb, void* stream) {
+  QBN_CHECK_ARG(out && n >= 0, "out/n");
+  if (n == 0) return QBN_OK;
+  philox_normal_kernel<<<qbn_grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, sa, sb, qbn_sample_base_ptr());
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -49,6 +49,7 @@ __device__ __forceinline__ float4 ld4_guard(const float* base, long long pix, in
 }
 
 __global__ void p4_stage_input_kernel(const float* __restrict__ x, StageGeom g, float4* __restrict__ xp, float4* __restrict__ xsq) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent planar conv launch (qbn_set_pdl) may start its prologue now
   const long long total = (long long)g.chunks * g.plane_rows;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i / g.plane_rows);
@@ -69,6 +70,7 @@ __global__ void p4_stage_grad_kernel(const float* __restrict__ gout, const float
                                      uint64_t seed, uint32_t sa, uint32_t sb, const uint32_t* __restrict__ sbase, float4* __restrict__ gp,
                                      float4* __restrict__ dvp) {
   if (sbase) sb += *sbase;           // the forward's draw (device-side offset, qbn_set_sample_base)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent planar conv launch (qbn_set_pdl) may start its prologue now
   const long long total = (long long)g.chunks * g.plane_rows;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i / g.plane_rows);
@@ -154,6 +156,7 @@ struct WPrep {
 
 // one thread = one float4 of the blocked tensor, for both halves ([mu | sigma^2])
 __global__ void lrt_p4_weight_prep_kernel(const float* __restrict__ mu, const float* __restrict__ second, WPrep w, float4* __restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent planar conv launch (qbn_set_pdl) may start its prologue now
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < w.g.total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t idx = p4_canonical(w.g, i);            // n' * K + t' * C' + c'   (c' a multiple of 4)
     float m[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};

@@ -110,7 +110,7 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
 }
 
 template <int DBG_MODE, bool STACKED, bool MASKED, int KIND = KIND_TF32>
-__global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
+__global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : (KIND == KIND_LRT ? 2 : 3)) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool PROF = DBG_MODE == 1;                    // cycle accounting (QBN_P4_PROF, diagnostics only)
   constexpr bool I8 = KIND == KIND_I8;
@@ -404,6 +404,19 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         const float* xptr = (p.xin && interior) ? p.xin + aux_off : nullptr;
         const float* rptr = (p.residual && interior) ? p.residual + aux_off : nullptr;
         uint32_t v0[16], v1[16];
+        // the per-element operand of the epilogue (forward: the noise tensor, input gradient: x) is fetched one column group ahead,
+        // the first group BEFORE the accumulator is waited for: at a training step's launch sizes (a few tiles per CTA) an exposed
+        // global-load round trip per 16-byte chunk made the epilogue, not the MMAs, the critical path
+        const float* aptr = p.lrt_mode == 0 ? eptr : xptr;
+        float4 acur[4], anext[4];
+        auto prefetch = [&](float4* dst, int g) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ch = g * 4 + i;
+            dst[i] = (aptr && ch < n_chunks) ? ld_nc4(aptr + (long long)ch * aux_step) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        prefetch(acur, 0);
         PROF_ADD(0);
         warp_wait(&acc_full[as], pacc, lane);
         PROF_ADD(1);
@@ -412,6 +425,7 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
         for (int g = 0; g < n_groups; ++g) {
           tmem_ld16(tlane + (uint32_t)(g * 16), v0);
           tmem_ld16(tlane + (uint32_t)(p.n_pad + g * 16), v1);
+          if (g + 1 < n_groups) prefetch(anext, g + 1);
           tmem_ld_wait();
           if (g + 1 == n_groups) {                              // accumulators fully read: hand the slot back to the MMA warp
             tc_fence_before();
@@ -426,32 +440,32 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : 3) umma_conv
               if (ch < n_chunks) {
                 float o[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
                 if (interior) {
+                  const float av[4] = {acur[i].x, acur[i].y, acur[i].z, acur[i].w};
                   if (p.lrt_mode == 0) {
-                    float e[4];
-                    if (eptr) {
-                      const float4 t = ld_nc4(eptr + (long long)ch * aux_step);
-                      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-                    } else {      // one Philox call = the four channels of this chunk; the backward regenerates the same draw
+                    float e[4] = {av[0], av[1], av[2], av[3]};
+                    if (!eptr)       // one Philox call = the four channels of this chunk; the backward regenerates the same draw
                       philox_normal4(p.seed, p.stream_a, p.stream_b + (p.sbase ? *p.sbase : 0u), ctr0 + (unsigned long long)ch, e);
-                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                       sd[k] = sqrtf(__fadd_rn(1e-8f, __uint_as_float(v1[4 * i + k])));
                       o[k] = __fadd_rn(__fadd_rn(__uint_as_float(v0[4 * i + k]), __fmul_rn(sd[k], e[k])), s_shift[ch * 4 + k]);
                     }
                   } else {
-                    const float4 xi = xptr ? ld_nc4(xptr + (long long)ch * aux_step) : make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4 rr = rptr ? ld_nc4(rptr + (long long)ch * res_step) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float xv[4] = {xi.x, xi.y, xi.z, xi.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+                    const float rv[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // dx = g*mu + 2x .* (dv*sigma^2) (+ the gradient that reached x through another branch)
-                      o[k] = __fadd_rn(__fadd_rn(__uint_as_float(v0[4 * i + k]), __fmul_rn(__fmul_rn(2.0f, xv[k]), __uint_as_float(v1[4 * i + k]))), rv[k]);
+                      o[k] = __fadd_rn(__fadd_rn(__uint_as_float(v0[4 * i + k]), __fmul_rn(__fmul_rn(2.0f, av[k]), __uint_as_float(v1[4 * i + k]))), rv[k]);
                   }
                 }
                 *reinterpret_cast<float4*>(optr + (long long)ch * out_step) = make_float4(o[0], o[1], o[2], o[3]);
                 if (o2) *reinterpret_cast<float4*>(o2 + (long long)ch * aux_step) = make_float4(sd[0], sd[1], sd[2], sd[3]);
               }
             }
+          }
+          if (g + 1 < n_groups) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acur[i] = anext[i];
           }
           PROF_ADD(3);
         }
@@ -891,7 +905,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   const char* e_occ = tune_env("QBN_P4_OCC");
   if (b_all <= 100 * 1024 && b_all < (1u << 20)) {
     p.b_res = 1; p.SB = 1; p.TG = p.taps; p.b_slot_bytes = (uint32_t)b_all;
-    want_occ = e_occ ? atoi(e_occ) : 3;
+    want_occ = e_occ ? atoi(e_occ) : (lrt ? 2 : 3);      // (the LRT epilogue keeps two operand groups in flight: 2 CTAs per SM by registers)
     while (want_occ > 1 && 2 * (size_t)p.a_bytes + b_all + fixed > cap / want_occ - 1024) --want_occ;
     p.SA = 2;
     while (p.SA < 4 && (size_t)(p.SA + 1) * p.a_bytes + b_all + fixed <= cap / want_occ - 1024) ++p.SA;

@@ -194,8 +194,13 @@ class GraphedTrainStep:
         optimizer.zero_grad(set_to_none=True)
         c0 = noise._state["counter"]
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self.eager(self.input, self.target, n_batches, n_points)
+        from . import _lib, config
+        _lib.call("qbn_set_pdl", int(config.pdl()))      # programmatic dependent launches of the planar conv kernels inside the graph
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = self.eager(self.input, self.target, n_batches, n_points)
+        finally:
+            _lib.call("qbn_set_pdl", 0)
         self.draws_per_step = (noise._state["counter"] - c0) & 0xFFFFFFFF
         self.replays = 0
 

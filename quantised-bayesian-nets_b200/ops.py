@@ -182,7 +182,8 @@ class LRTFunction(torch.autograd.Function):
             math_mode = ctx.math_mode = QBN_MATH_FP32      # shapes the tcgen05 gather kernels do not take (config.tf32_eligible)
         if ctx.planar:
             # TF32 mode on the planar zero-copy kernels: operands staged once, every contraction of forward and backward on tcgen05
-            out, std, x_w32, xsq_w32 = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key)
+            out, std, x_p4, xsq_p4, eps_c = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key, materialise_eps=True)
+            x_w32, xsq_w32 = w32_from_p4(x_p4, xsq_p4)
             ctx.save_for_backward(xc, x_w32, xsq_w32, std, eps_c, weight.detach(), second.detach())
             return out
         packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))   # backward needs them unrounded
@@ -259,7 +260,7 @@ def lrt_p4_weight_prep(weight, second, second_is_sigma, d, mode, tap_list=None):
     return out
 
 
-def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(0, 0, 0), want_w32=True):
+def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(0, 0, 0), want_w32=True, materialise_eps=False):
     """xc NHWC-dense [B, C, H, W] (channels_last).  Returns out, std (NHWC) and the operands the backward needs: x, x^2 in the W32
     layout of the weight-gradient kernel (want_w32=False: the planar-C4 maps the forward itself read)."""
     s2, bh, bw, Hp, Wp, C_pad = _lrt_p4_geom(d)
@@ -270,8 +271,14 @@ def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(
     _lib.call("qbn_p4_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _stream())
     w = lrt_p4_weight_prep(weight.detach().contiguous(), second.detach().contiguous(), second_is_sigma, d, 0)
     out, std = _out_like(xc, d), _out_like(xc, d)
+    if eps is None and materialise_eps:
+        # the epilogue's Philox draw as a tensor (same values): generated at full occupancy, re-read by the backward
+        eps = _out_like(xc, d)
+        _lib.call("qbn_lrt_noise", _ptr(eps), eps.numel(), key[0], key[1], key[2], _stream())
     _lib.call("qbn_lrt_conv_p4_fwd", d.B, Hp, Wp, C_pad, d.N, d.R, d.S, d.stride_h, _ptr(x_p4), _ptr(xsq_p4), pr, _ptr(w), _ptr(bias), _ptr(eps),
               key[0], key[1], key[2], _ptr(out), _ptr(std), _stream())
+    if materialise_eps:
+        return out, std, x_p4, xsq_p4, eps
     if not want_w32:
         return out, std, x_p4, xsq_p4
     # the weight-gradient kernel reads MN-major operands: the swizzled 32-channel-block copy is what the backward keeps

@@ -16,9 +16,10 @@ def main():
     from qbn_b200 import config, losses, noise, synthetic, zoo
     from qbn_b200 import dist as qdist
     config.set_math_mode("tf32")
+    config.set_pdl(os.environ.get("QBN_PDL", "0") == "1")
     model = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().train()
     noise.manual_seed(1)
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, capturable=True)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, capturable=True, fused=True)
     crit = losses.LOSS_FACTORY["classification"](zoo.Args(loss_multiplier=1.0), "batch")
     g = torch.Generator().manual_seed(5)
     x, t = torch.randn(B, 3, 32, 32, generator=g).cuda(), torch.randint(0, 10, (B,), generator=g).cuda()
@@ -53,7 +54,7 @@ def main():
     tot = sum(v[1] for v in rows.values())
     print("kernel time of one replay: %.3f ms in %d launches" % (tot / 1e3, sum(v[0] for v in rows.values())))
     for n, (c, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:40]:
-        print("  %8.1f us %5.1f %% %4d x  %s" % (us, 100 * us / tot, c, n[:110]))
+        print("  %8.1f us %5.1f %% %4d x  %s" % (us, 100 * us / tot, c, n[:110] if "Functor" not in n else n[:400]))
 
 
 if __name__ == "__main__":
