@@ -119,6 +119,12 @@ QBN_DEVINL void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
                : "r"(taddr)
                : "memory");
 }
+// one column: thread t of the warp gets lane (base+t)
+QBN_DEVINL uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
 // 16-byte LDGSTS with zero-fill: copies src_bytes (0, 8 or 16) and zero-fills the rest of the 16
 QBN_DEVINL void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");

@@ -109,6 +109,52 @@ QBN_DEVINL void divmod(uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t
   if (r >= d) { ++q; r -= d; }
 }
 
+
+// ---- int8 requantisation of one column group (FBGEMM ReQuantizeOutput + ATen quantized::add), CNT = 8 or 16 valid channels.
+// Same integers as the reference sequence rint -> + zero point -> clamp (-> dequantise -> add -> requantise), with the float<->int
+// conversions (half-rate instructions; the int8 epilogue is issue-bound, profiles/r02_i8_p4_kernels_ncu_full.csv) replaced by
+// exact float arithmetic: clamping to INTEGER bounds commutes with rint, and for |y| < 2^22  y + 1.5*2^23  rounds y to the nearest
+// even integer in one FADD (the same RN rounding as cvt.rni) and leaves it, two's complement, in the low mantissa bits.
+// out[j]: a 32-bit pattern whose LOW BYTE is the stored value (q - zero point); the packer takes the low bytes.
+constexpr float I8_MAGIC = 12582912.0f;      // 1.5 * 2^23
+template <int CNT, bool ADD>
+QBN_DEVINL void i8_requant_group(const uint32_t (&v)[16], int corr, const float* s_shift16, const uint4& rres, const P4Params& p, uint32_t (&out)[16]) {
+  float sh[16];
+#pragma unroll
+  for (int k = 0; k < CNT / 4; ++k) {
+    const float4 t = *reinterpret_cast<const float4*>(s_shift16 + 4 * k);
+    sh[4 * k] = t.x; sh[4 * k + 1] = t.y; sh[4 * k + 2] = t.z; sh[4 * k + 3] = t.w;
+  }
+  if constexpr (!ADD) {
+    const float lo = (float)(p.q_lo - p.z_out), hi = (float)(p.q_hi - p.z_out);
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+      const float y = __fmul_rn(__fadd_rn((float)((int)v[j] - corr), sh[j]), p.mult);
+      out[j] = __float_as_uint(__fadd_rn(fminf(fmaxf(y, lo), hi), I8_MAGIC));
+    }
+  } else {
+    const float lo1 = (float)(p.q_lo - p.z_out), hi1 = (float)(p.q_hi - p.z_out);
+    const float unbias1 = I8_MAGIC - (float)p.z_out;                 // (yc + M) - (M - z_out) = rint(yc) + z_out = the conv's quint8 output
+    const float lo2 = (float)(p.add_lo - p.z_add), hi2 = (float)(p.add_hi - p.z_add);
+    // residual bytes hold (q - z_res) as s8: (byte ^ 0x80) = q - z_res + 128 in [0, 255], placed in the low mantissa byte of 1.5 * 2^23
+    const uint32_t rw[4] = {rres.x ^ 0x80808080u, rres.y ^ 0x80808080u, rres.z ^ 0x80808080u, rres.w ^ 0x80808080u};
+    const float unbias_r = I8_MAGIC + 128.0f - (float)p.z_res;
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+      const float y = __fmul_rn(__fadd_rn((float)((int)v[j] - corr), sh[j]), p.mult);
+      const float qo = __fadd_rn(__fadd_rn(fminf(fmaxf(y, lo1), hi1), I8_MAGIC), -unbias1);
+      const float rb = __fadd_rn(__uint_as_float(__byte_perm(rw[j >> 2], 0x4B400000u, 0x7650u + (uint32_t)(j & 3))), -unbias_r);
+      // quantized::add[_relu] (vector body of ATen's kernel: dequantise with one FMA per operand)
+      const float da = __fmaf_rn(p.s_a, qo, p.p_a);
+      const float db = __fmaf_rn(p.s_b, rb, p.p_b);
+      const float z = __fmul_rn(__fadd_rn(da, db), p.inv_s_add);
+      out[j] = __float_as_uint(__fadd_rn(fminf(fmaxf(z, lo2), hi2), I8_MAGIC));
+    }
+  }
+#pragma unroll
+  for (int j = CNT; j < 16; ++j) out[j] = 0u;
+}
+
 template <int DBG_MODE, bool STACKED, bool MASKED, int KIND = KIND_TF32>
 __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : (KIND == KIND_LRT ? 2 : 3)) umma_conv_p4_kernel(const __grid_constant__ P4Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -490,21 +536,25 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : (KIND == KIN
         tc_fence_after();
         const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.acc_cols);
         // column N of the accumulator = sum_k (x - z_x) (an all-ones weight row): the z_w correction of sum (x-z_x)(w-z_w)
+        // TMEM reads are 64 bytes per cycle and SM, shared by the 4 resident CTAs (role accounting: the loads were 40 % of a tile's
+        // epilogue): one column for the row sum, 8 columns for a half-filled last group
         int corr = 0;
-        if (p.z_w != 0) {
-          tmem_ld16(tlane + (uint32_t)(p.N & ~15), v);
-          tmem_ld_wait();
-          int rowsum = 0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) rowsum = (j == (p.N & 15)) ? (int)v[j] : rowsum;
-          corr = p.z_w * rowsum;
-        }
-        tmem_ld16(tlane, v);
+        uint32_t rs_raw = 0;
+        if (p.z_w != 0) rs_raw = tmem_ld1(tlane + (uint32_t)p.N);
+        auto ld_group = [&](int g, uint32_t (&dst)[16]) {
+          if (p.N - g * 16 > 8) {
+            tmem_ld16(tlane + (uint32_t)(g * 16), dst);
+          } else {
+            tmem_ld8(tlane + (uint32_t)(g * 16), dst);      // (no register of dst may be touched before tcgen05.wait::ld)
+          }
+        };
+        ld_group(0, v);
         const int n_out = p.n_out_chunks;
         for (int g = 0; g < n_out; ++g) {
           tmem_ld_wait();
+          if (g == 0) corr = p.z_w * (int)rs_raw;
           if (g + 1 < n_out) {
-            tmem_ld16(tlane + (uint32_t)((g + 1) * 16), vn);
+            ld_group(g + 1, vn);
             rnext = ld_res(g + 1);
           } else {
             tc_fence_before();
@@ -519,40 +569,21 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : (KIND == KIN
                 for (int j = 0; j < 16; ++j)
                   if (g * 16 + j < p.N) p.acc_dump[in_row * p.N + g * 16 + j] = (int)v[j] - corr;
               }
-              // branch-free inner loops (16 independent chains per group); the zero points ride the clamp bounds
-              int sv[16];
-              float sh[16];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 t = *reinterpret_cast<const float4*>(&s_shift[g * 16 + 4 * k]);
-                sh[4 * k] = t.x; sh[4 * k + 1] = t.y; sh[4 * k + 2] = t.z; sh[4 * k + 3] = t.w;
-              }
+              // branch-free inner loops (independent chains per channel); the zero points ride the clamp bounds
+              uint32_t sv[16];
+              const int nvalid_g = p.N - g * 16;
               if (!p.has_add) {
-                const int lo_s = p.q_lo - p.z_out, hi_s = p.q_hi - p.z_out;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float xf = __fadd_rn((float)((int)v[j] - corr), sh[j]);
-                  sv[j] = max(lo_s, min(hi_s, __float2int_rn(__fmul_rn(xf, p.mult))));
-                }
+                if (nvalid_g > 8) i8_requant_group<16, false>(v, corr, &s_shift[g * 16], rres, p, sv);
+                else i8_requant_group<8, false>(v, corr, &s_shift[g * 16], rres, p, sv);
               } else {
-                const uint32_t rw[4] = {rres.x, rres.y, rres.z, rres.w};
-                const int lo_s = p.add_lo - p.z_add, hi_s = p.add_hi - p.z_add;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float xf = __fadd_rn((float)((int)v[j] - corr), sh[j]);
-                  const int qo = max(p.q_lo, min(p.q_hi, __float2int_rn(__fmul_rn(xf, p.mult)) + p.z_out));
-                  // quantized::add[_relu] (vector body of ATen's kernel: dequantise with one FMA per operand)
-                  const int rb = (int)(int8_t)(rw[j >> 2] >> ((j & 3) * 8)) + p.z_res;
-                  const float da = __fmaf_rn(p.s_a, (float)qo, p.p_a);
-                  const float db = __fmaf_rn(p.s_b, (float)rb, p.p_b);
-                  sv[j] = max(lo_s, min(hi_s, __float2int_rn(__fmul_rn(__fadd_rn(da, db), p.inv_s_add))));
-                }
+                if (nvalid_g > 8) i8_requant_group<16, true>(v, corr, &s_shift[g * 16], rres, p, sv);
+                else i8_requant_group<8, true>(v, corr, &s_shift[g * 16], rres, p, sv);
               }
               const int nvalid = p.N - g * 16;               // channels >= N of the last chunk stay zero (padding planes)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t lo2 = __byte_perm((uint32_t)sv[4 * k], (uint32_t)sv[4 * k + 1], 0x0040);
-                const uint32_t hi2 = __byte_perm((uint32_t)sv[4 * k + 2], (uint32_t)sv[4 * k + 3], 0x0040);
+                const uint32_t lo2 = __byte_perm(sv[4 * k], sv[4 * k + 1], 0x0040);
+                const uint32_t hi2 = __byte_perm(sv[4 * k + 2], sv[4 * k + 3], 0x0040);
                 uint32_t w4 = __byte_perm(lo2, hi2, 0x5410);
                 const int left = nvalid - 4 * k;
                 if (left < 4) w4 = left <= 0 ? 0u : (w4 & (0xFFFFFFFFu >> (8 * (4 - left))));
@@ -905,7 +936,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   const char* e_occ = tune_env("QBN_P4_OCC");
   if (b_all <= 100 * 1024 && b_all < (1u << 20)) {
     p.b_res = 1; p.SB = 1; p.TG = p.taps; p.b_slot_bytes = (uint32_t)b_all;
-    want_occ = e_occ ? atoi(e_occ) : (lrt ? 2 : 3);      // (the LRT epilogue keeps two operand groups in flight: 2 CTAs per SM by registers)
+    want_occ = e_occ ? atoi(e_occ) : (lrt ? 2 : (i8 ? 4 : 3));      // (the LRT epilogue keeps two operand groups in flight: 2 CTAs per SM by registers)
     while (want_occ > 1 && 2 * (size_t)p.a_bytes + b_all + fixed > cap / want_occ - 1024) --want_occ;
     p.SA = 2;
     while (p.SA < 4 && (size_t)(p.SA + 1) * p.a_bytes + b_all + fixed <= cap / want_occ - 1024) ++p.SA;
