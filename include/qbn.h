@@ -352,7 +352,8 @@ int qbn_p4_stage_grad(const float* g_out, const float* std_saved, const float* e
                       float* dv_p4, void* stream);
 /* OIHW (mu, rho | sigma) -> blocked [mu | sigma^2] operand, TF32-rounded.  mode 0: forward (input channels zero-padded to C_pad,
  * blocked for `stride`); 1: input gradient of a stride-1 layer (taps reversed, channels swapped); 2: one phase of a stride-2
- * layer's input gradient (parameter taps tap_list[0..n_taps)).  out: 2 * qbn_p4_weight_floats(...) floats (returned in *out_floats). */
+ * layer's input gradient (parameter taps tap_list[0..n_taps)); 3: the four phases of a 3x3 stride-2 layer, four taps each (absent
+ * taps zeroed), one [mu | sigma^2] pair per phase.  out: 2 * qbn_p4_weight_floats(...) floats per pair (total in *out_floats). */
 int qbn_lrt_p4_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int C_pad, int R, int S,
                            int stride, int mode, const int* tap_list, int n_taps, float* out, long long* out_floats, void* stream);
 /* out = conv(x, mu) + sqrt(1e-8 + conv(x_sq, sigma^2)) .* eps + bias ; std_out = the square root.  Hp, Wp: padded extent of the
@@ -363,6 +364,9 @@ int qbn_lrt_conv_p4_fwd(int B, int Hp, int Wp, int C_pad, int N, int R, int S, i
 /* dx = convT(g, mu) + 2 x .* convT(dv, sigma^2) of a stride-1 layer.  C: channels of g, N: channels of dx; xin, dx dense NHWC */
 int qbn_lrt_conv_p4_dgrad(int B, int Hp, int Wp, int C, int N, int R, int S, const float* g_p4, const float* dv_p4,
                           long long g_plane_rows, const float* w_flipped_blocked, const float* xin, float* dx, void* stream);
+/* all four phases of a 3x3 stride-2 layer's input gradient in one launch (weights: qbn_lrt_p4_weight_prep mode 3) */
+int qbn_lrt_conv_p4_dgrad_s2(int B, int Hp, int Wp, int C, int N, const float* g_p4, const float* dv_p4, long long g_plane_rows,
+                             const float* w_phases_blocked, const float* xin, float* dx, void* stream);
 /* phase (a, b) of a stride-2 layer's input gradient: dx[2i+a][2j+b] = sum_t g[i + di_t][j + dj_t] * w[tap_t], shifts[t] =
  * di_t * Wp + dj_t (di, dj in {0, 1}); xin, dx dense NHWC [B][2(Hp-1)][2(Wp-1)][N] */
 int qbn_lrt_conv_p4_dgrad_phase(int B, int Hp, int Wp, int C, int N, int n_taps, const int* shifts, int phase_a, int phase_b,

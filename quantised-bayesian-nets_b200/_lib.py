@@ -121,6 +121,7 @@ _SIGNATURES = {
     "qbn_lrt_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, c_uint64, c_uint32,
                                     c_uint32, P, P, P]),
     "qbn_lrt_conv_p4_dgrad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, P]),
+    "qbn_lrt_conv_p4_dgrad_s2": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, P]),
     "qbn_lrt_conv_p4_dgrad_phase": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, P, P, ctypes.c_longlong, P,
                                             P, P, P]),
     "qbn_w32_from_p4": (c_int, [P, P, c_int, ctypes.c_longlong, P, P, P]),

@@ -150,34 +150,41 @@ struct WPrep {
   P4Block g;                  // geometry of the blocked OUTPUT
   int N, C, taps;             // the layer's parameters: OIHW [N][C][taps]
   int transposed;             // output row n' = input channel c, output channel c' = output channel n (input gradient)
-  int tap_map[25];            // output tap -> parameter tap
+  int tap_map[25];            // output tap -> parameter tap (-1: a zero tap)
+  int n_sets;                 // mode 3: four tap maps (tap_map[4 * z + t]), one blocked [mu | sigma^2] pair per phase z
   int second_is_sigma;
 };
 
-// one thread = one float4 of the blocked tensor, for both halves ([mu | sigma^2])
+// one thread = one float4 of the blocked tensor, for both halves ([mu | sigma^2]) of every tap set
 __global__ void lrt_p4_weight_prep_kernel(const float* __restrict__ mu, const float* __restrict__ second, WPrep w, float4* __restrict__ out) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent planar conv launch (qbn_set_pdl) may start its prologue now
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < w.g.total4; i += (int64_t)gridDim.x * blockDim.x) {
+  const int n_sets = w.n_sets > 0 ? w.n_sets : 1;
+  for (int64_t ii = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ii < w.g.total4 * n_sets; ii += (int64_t)gridDim.x * blockDim.x) {
+    const int set = (int)(ii / w.g.total4);
+    const int64_t i = ii - (int64_t)set * w.g.total4;
     const int64_t idx = p4_canonical(w.g, i);            // n' * K + t' * C' + c'   (c' a multiple of 4)
     float m[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (idx >= 0) {
       const int np = (int)(idx / w.g.K);
       const int rem = (int)(idx - (int64_t)np * w.g.K);
       const int tp = rem / w.g.C, cp = rem - tp * w.g.C;
-      const int t = w.tap_map[tp];
+      const int t = w.tap_map[set * w.g.taps + tp];
+      if (t >= 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int n = w.transposed ? cp + k : np, c = w.transposed ? np : cp + k;
-        if (n < w.N && c < w.C) {
-          const int64_t src = ((int64_t)n * w.C + c) * w.taps + t;
-          const float sg = w.second_is_sigma ? second[src] : softplus_f(second[src]);
-          m[k] = tf32_round(mu[src]);
-          s2[k] = tf32_round(__fmul_rn(sg, sg));
+        for (int k = 0; k < 4; ++k) {
+          const int n = w.transposed ? cp + k : np, c = w.transposed ? np : cp + k;
+          if (n < w.N && c < w.C) {
+            const int64_t src = ((int64_t)n * w.C + c) * w.taps + t;
+            const float sg = w.second_is_sigma ? second[src] : softplus_f(second[src]);
+            m[k] = tf32_round(mu[src]);
+            s2[k] = tf32_round(__fmul_rn(sg, sg));
+          }
         }
       }
     }
-    out[i] = make_float4(m[0], m[1], m[2], m[3]);
-    out[w.g.total4 + i] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    float4* o = out + (int64_t)set * 2 * w.g.total4;
+    o[i] = make_float4(m[0], m[1], m[2], m[3]);
+    o[w.g.total4 + i] = make_float4(s2[0], s2[1], s2[2], s2[3]);
   }
 }
 
@@ -190,7 +197,7 @@ __global__ void lrt_p4_weight_prep_kernel(const float* __restrict__ mu, const fl
 extern "C" int qbn_lrt_p4_weight_prep(const float* mu, const float* second, int second_is_sigma, int N, int C, int C_pad, int R, int S,
                                       int stride, int mode, const int* tap_list, int n_taps, float* out, long long* out_floats, void* stream) {
   QBN_CHECK_ARG(mu && second && out, "null pointer");
-  QBN_CHECK_ARG(N > 0 && C > 0 && R > 0 && S > 0 && R * S <= 25 && mode >= 0 && mode <= 2, "sizes / mode");
+  QBN_CHECK_ARG(N > 0 && C > 0 && R > 0 && S > 0 && R * S <= 25 && mode >= 0 && mode <= 3, "sizes / mode");
   WPrep w;
   memset(&w, 0, sizeof(w));
   w.N = N; w.C = C; w.taps = R * S; w.second_is_sigma = second_is_sigma;
@@ -203,6 +210,19 @@ extern "C" int qbn_lrt_p4_weight_prep(const float* mu, const float* second, int 
     w.transposed = 1;
     ok = p4_block_geom(C, N, R * S, 1, w.g);
     for (int t = 0; t < R * S; ++t) w.tap_map[t] = R * S - 1 - t;
+  } else if (mode == 3) {
+    // the four phases (a, b) of a 3x3 stride-2 layer's input gradient, four taps (dr, ds) each: tap (dr, ds) of phase (a, b) exists
+    // iff (dr == 0 or a == 1) and (ds == 0 or b == 1) and is the parameter tap (dr ? 0 : (a ? 2 : 1), ds ? 0 : (b ? 2 : 1))
+    QBN_CHECK_ARG(R == 3 && S == 3 && stride == 2, "mode 3: 3x3 stride-2 layers");
+    w.transposed = 1;
+    w.n_sets = 4;
+    ok = p4_block_geom(C, N, 4, 1, w.g);
+    for (int z = 0; z < 4; ++z)
+      for (int t = 0; t < 4; ++t) {
+        const int a = z >> 1, b = z & 1, dr = t >> 1, ds = t & 1;
+        const bool valid = (dr == 0 || a == 1) && (ds == 0 || b == 1);
+        w.tap_map[4 * z + t] = valid ? (dr ? 0 : (a ? 2 : 1)) * 3 + (ds ? 0 : (b ? 2 : 1)) : -1;
+      }
   } else {
     QBN_CHECK_ARG(tap_list && n_taps > 0 && n_taps <= 4, "tap list");
     w.transposed = 1;
@@ -216,8 +236,9 @@ extern "C" int qbn_lrt_p4_weight_prep(const float* mu, const float* second, int 
     qbn_set_error("qbn_lrt_p4_weight_prep: no blocking (mode %d N=%d C=%d C_pad=%d)", mode, N, C, C_pad);
     return QBN_ERR_UNSUPPORTED;
   }
-  if (out_floats) *out_floats = 2 * w.g.total4 * 4;
-  lrt_p4_weight_prep_kernel<<<qbn_grid_for(w.g.total4, 256), 256, 0, (cudaStream_t)stream>>>(mu, second, w, reinterpret_cast<float4*>(out));
+  const int n_sets = w.n_sets > 0 ? w.n_sets : 1;
+  if (out_floats) *out_floats = 2 * w.g.total4 * 4 * n_sets;
+  lrt_p4_weight_prep_kernel<<<qbn_grid_for(w.g.total4 * n_sets, 256), 256, 0, (cudaStream_t)stream>>>(mu, second, w, reinterpret_cast<float4*>(out));
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

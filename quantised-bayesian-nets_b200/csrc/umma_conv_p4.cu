@@ -77,6 +77,7 @@ struct P4Params {
   // (b, hh, ww) of this launch's geometry is the NHWC pixel (b, (hh - bh) * oh_mul + oh_add, (ww - bw) * ow_mul + ow_add)
   // (mul 2 / add phase: the four phase launches of a stride-2 layer's input gradient)
   int nhwc, H_out, W_out, oh_mul, oh_add, ow_mul, ow_add;
+  int phase_z;                                    // the launch's 'samples' z = 0..3 are the phases (z >> 1, z & 1) of a stride-2 input gradient
 };
 enum { KIND_TF32 = 0, KIND_I8 = 1, KIND_LRT = 2 };
 
@@ -434,7 +435,8 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : (KIND == KIN
         long long out_off, aux_off, aux_step, out_step, res_step;      // float offsets of chunk 0 / steps between chunks
         unsigned long long ctr0;                                       // Philox counter of chunk 0 (the existing NHWC path's: out offset / 4)
         if (p.nhwc) {
-          const long long pix = ((long long)b * p.H_out + ((int)hh - p.bh) * p.oh_mul + p.oh_add) * p.W_out + ((int)ww - p.bw) * p.ow_mul + p.ow_add;
+          const int oh_add = p.phase_z ? (z >> 1) : p.oh_add, ow_add = p.phase_z ? (z & 1) : p.ow_add;
+          const long long pix = ((long long)b * p.H_out + ((int)hh - p.bh) * p.oh_mul + oh_add) * p.W_out + ((int)ww - p.bw) * p.ow_mul + ow_add;
           store = interior;
           out_off = aux_off = interior ? pix * p.N : 0;
           aux_step = out_step = res_step = 4;
@@ -750,6 +752,7 @@ struct P4LRT {                                       // LRT extras of a launch (
   const float* x_sq; const float* eps; const float* xin; float* out2; long long aux_plane;
   unsigned long long seed; uint32_t stream_a, stream_b;
   int nhwc, H_out, W_out, oh_mul, oh_add, ow_mul, ow_add;      // dense NHWC out / out2 / eps / xin (see P4Params)
+  int phase_z;                                       // all four phases of a stride-2 input gradient in one launch (n_samples = 4)
   int n_taps;                                        // > 0: explicit tap list on maps with a (1, 1) border: tap t reads row q + shift[t] >= q
   int shift[MAX_TAPS];
 };
@@ -834,12 +837,15 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     p.n_out_chunks = (N + 15) / 16;
   }
   if (lrt) {
-    QBN_CHECK_ARG(!i8 && !stacked && !x2 && !out_mask && n_samples == 1 && lrt->x_sq, "LRT launch: one 'sample', two operand tensors");
+    QBN_CHECK_ARG(!i8 && !stacked && !x2 && !out_mask && (n_samples == 1 || (lrt->phase_z && n_samples == 4)) && lrt->x_sq,
+                  "LRT launch: one 'sample' (or the four phases), two operand tensors");
     QBN_CHECK_ARG(!(flags & QBN_FLAG_OUT_PHASE_SPLIT), "LRT launch: normal output layout");
     p.dual = 1; p.lrt_mode = lrt->mode; p.x_sq = lrt->x_sq; p.eps = lrt->eps; p.xin = lrt->xin; p.out2 = lrt->out2; p.aux_plane = lrt->aux_plane;
     p.seed = lrt->seed; p.stream_a = lrt->stream_a; p.stream_b = lrt->stream_b; p.sbase = qbn_sample_base_ptr();
     p.nhwc = lrt->nhwc; p.H_out = lrt->H_out; p.W_out = lrt->W_out;
     p.oh_mul = lrt->oh_mul; p.oh_add = lrt->oh_add; p.ow_mul = lrt->ow_mul; p.ow_add = lrt->ow_add;
+    p.phase_z = lrt->phase_z;
+    if (lrt->phase_z) p.x_shared = 1;               // every phase reads the same g / dv maps
     QBN_CHECK_ARG(!ct || (stride == 1 && R == 1 && S == lrt->n_taps && S <= MAX_TAPS), "explicit tap list: R = 1, S = n_taps, stride 1");
   }
   p.bh = (s1 && !ct) ? (R - 1) / 2 : 1;
@@ -853,7 +859,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.cbc = CB / E;
   p.nk = p.cbc / 2;
   p.taps = R * S;
-  p.strip_rows = (long long)((stacked || (i8 && i8->x_shared)) ? 1 : n_samples) * p.Qs;
+  p.strip_rows = (long long)((stacked || (i8 && i8->x_shared) || (lrt && lrt->phase_z)) ? 1 : n_samples) * p.Qs;
   int d_after = 0;
   if (ct) {
     p.n_strips = 1;
@@ -905,7 +911,7 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
     if ((uint32_t)p.cbc2 * TM * 16 > p.a_bytes) p.a_bytes = (uint32_t)p.cbc2 * TM * 16;       // the slots must hold a shortcut block too
     QBN_CHECK_ARG(p.bt2_bytes <= p.bt_bytes * (uint32_t)p.taps, "shortcut weight block larger than the main conv's");
   }
-  p.w_sample_floats = ((long long)p.n_cb * p.taps * p.bt_bytes + (long long)p.n_cb2 * p.bt2_bytes) / 4;
+  p.w_sample_floats = ((long long)p.n_cb * (p.dual ? 2 : 1) * p.taps * p.bt_bytes + (long long)p.n_cb2 * p.bt2_bytes) / 4;
   p.flags = flags; p.w_shared = stacked ? 1 : w_shared;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.out_mask = out_mask; p.out_mask_mult = out_mask_mult;
@@ -1168,6 +1174,24 @@ extern "C" int qbn_lrt_conv_p4_dgrad(int B, int Hp, int Wp, int C, int N, int R,
 // g's zero-bordered maps (Hp = Ho + 1, Wp = Wo + 1) whose taps shift by 0 / +1 rows and columns; the shared zero border supplies
 // the out-of-range reads.  shifts[t] = (r_t == 0) * Wp + (s_t == 0) in the order of the n_taps blocks of w_phase_blocked
 // (qbn_lrt_p4_weight_prep mode 2).  xin, dx: dense NHWC [B][2(Hp-1)][2(Wp-1)][N].  A 1x1 layer has the single phase (0, 0).
+// All four phases of a 3x3 stride-2 layer's input gradient in ONE launch: phase z = (a, b) is 'sample' z with its own blocked weights
+// (qbn_lrt_p4_weight_prep mode 3: four taps (dr, ds) in {0,1}^2 per phase, shift dr * Wp + ds, the taps a phase does not have zeroed),
+// all reading the same g / dv maps.  Same result as four qbn_lrt_conv_p4_dgrad_phase calls; a training step's stride-2 layers are
+// launch-latency bound.
+extern "C" int qbn_lrt_conv_p4_dgrad_s2(int B, int Hp, int Wp, int C, int N, const float* g, const float* dv, long long g_plane_rows,
+                                        const float* w_phases_blocked, const float* xin, float* dx, void* stream) {
+  QBN_CHECK_ARG(dv && xin, "dv / xin");
+  P4LRT l;
+  memset(&l, 0, sizeof(l));
+  l.mode = 1; l.x_sq = dv; l.xin = xin;
+  l.nhwc = 1; l.H_out = 2 * (Hp - 1); l.W_out = 2 * (Wp - 1); l.oh_mul = l.ow_mul = 2;
+  l.phase_z = 1;
+  l.n_taps = 4;
+  l.shift[0] = 0; l.shift[1] = 1; l.shift[2] = Wp; l.shift[3] = Wp + 1;
+  P4Planes pl = {g_plane_rows, 0, 0, 0};
+  return conv_p4_launch(4, B, Hp, Wp, C, N, 1, 4, 1, g, w_phases_blocked, 0, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, dx, nullptr, 0, 0, pl,
+                        stream, nullptr, &l);
+}
 extern "C" int qbn_lrt_conv_p4_dgrad_phase(int B, int Hp, int Wp, int C, int N, int n_taps, const int* shifts, int phase_a, int phase_b,
                                            const float* g, const float* dv, long long g_plane_rows, const float* w_phase_blocked,
                                            const float* xin, float* dx, void* stream) {

@@ -248,6 +248,8 @@ def lrt_p4_weight_prep(weight, second, second_is_sigma, d, mode, tap_list=None):
         n = 2 * p4_weight_floats(C_pad, d.N, d.R, d.S, d.stride_h)
     elif mode == 1:
         n = 2 * p4_weight_floats(d.N, d.C, d.R, d.S, 1)
+    elif mode == 3:
+        n = 8 * p4_weight_floats(d.N, d.C, 1, 4, 1)
     else:
         n = 2 * p4_weight_floats(d.N, d.C, 1, len(tap_list), 1)
     out = torch.empty(n, dtype=torch.float32, device=weight.device)
@@ -315,19 +317,18 @@ def lrt_p4_backward(xc, x_w32, xsq_w32, std, eps, weight, second, second_is_sigm
             w_t = lrt_p4_weight_prep(weight, second, second_is_sigma, d, 1)
             dx = torch.empty_like(xc)
             _lib.call("qbn_lrt_conv_p4_dgrad", d.B, Hp, Wp, d.N, d.C, d.R, d.S, _ptr(g_p4), _ptr(dv_p4), pr_g, _ptr(w_t), _ptr(xc), _ptr(dx), _stream())
+        elif d.R == 3:
+            # pixels (2i+a, 2j+b) of dx get the taps r = a+1 (mod 2), s = b+1 (mod 2); tap 0 of the filter reads g one row / column
+            # further.  One launch: the phases are the kernel's 'samples', each with four (zero-padded) taps
+            w_t = lrt_p4_weight_prep(weight, second, second_is_sigma, d, 3)
+            dx = torch.empty_like(xc)
+            _lib.call("qbn_lrt_conv_p4_dgrad_s2", d.B, Hp, Wp, d.N, d.C, _ptr(g_p4), _ptr(dv_p4), pr_g, _ptr(w_t), _ptr(xc), _ptr(dx), _stream())
         else:
-            # pixels (2i+a, 2j+b) of dx: the taps r = a+1 (mod 2), s = b+1 (mod 2); tap 0 of a 3x3 filter reads g one row / column further
-            one = d.R == 1
-            dx = torch.zeros_like(xc) if one else torch.empty_like(xc)
-            for a in ((0,) if one else (0, 1)):
-                for b in ((0,) if one else (0, 1)):
-                    rs = (0,) if one else ((1,) if a == 0 else (0, 2))
-                    ss = (0,) if one else ((1,) if b == 0 else (0, 2))
-                    taps = [r * d.S + s_ for r in rs for s_ in ss]
-                    shifts = [(0 if one else int(r == 0)) * Wp + (0 if one else int(s_ == 0)) for r in rs for s_ in ss]
-                    w_t = lrt_p4_weight_prep(weight, second, second_is_sigma, d, 2, taps)
-                    _lib.call("qbn_lrt_conv_p4_dgrad_phase", d.B, Hp, Wp, d.N, d.C, len(taps), (ctypes.c_int * len(taps))(*shifts), a, b, _ptr(g_p4),
-                              _ptr(dv_p4), pr_g, _ptr(w_t), _ptr(xc), _ptr(dx), _stream())
+            # 1x1 stride 2: only the pixels (2i, 2j) receive a gradient
+            dx = torch.zeros_like(xc)
+            w_t = lrt_p4_weight_prep(weight, second, second_is_sigma, d, 2, [0])
+            _lib.call("qbn_lrt_conv_p4_dgrad_phase", d.B, Hp, Wp, d.N, d.C, 1, (ctypes.c_int * 1)(0), 0, 0, _ptr(g_p4), _ptr(dv_p4), pr_g, _ptr(w_t),
+                      _ptr(xc), _ptr(dx), _stream())
     return dx, dmu_p, dsig2_p
 
 
