@@ -145,6 +145,10 @@ int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int N, int R, i
  * receives the sum over layers (models_bbb.py:254-259), d_mu / d_rho (nullable) the gradients times grad_scale (overwritten). */
 typedef struct qbn_kl_job { const float* mu; const float* rho; float* d_mu; float* d_rho; int64_t n; float sigma_prior; int32_t pad_; } qbn_kl_job;
 int qbn_kl_multi(const void* jobs_dev, int n_jobs, int64_t max_n, float* kl_out, float grad_scale, void* stream);
+/* trainer.py:105-107 (NaN gradients -> 0, per parameter) for every gradient tensor of a model in ONE launch per 128 tensors;
+ * jobs_host: HOST array (it travels in the kernel parameters: no device table, capture-safe) */
+typedef struct qbn_scrub_job { float* grad; int64_t n; } qbn_scrub_job;
+int qbn_scrub_nan_multi(const qbn_scrub_job* jobs_host, int n_jobs, void* stream);
 
 /* ---- planar-C4 path: the S-batched eval convolution (A4 + A11 glue) with NO operand handling by threads.
  * Activations "planar C4": [C/4 chunk planes][plane_rows][4 floats]; a plane holds the pixels of the zero-bordered maps
@@ -350,6 +354,12 @@ int qbn_p4_stage_input(const float* x, int64_t n_img, int H, int W, int C, int C
 int qbn_p4_stage_grad(const float* g_out, const float* std_saved, const float* eps, uint64_t seed, uint32_t stream_a,
                       uint32_t stream_b, int64_t n_img, int H, int W, int N, int bh, int bw, long long plane_rows, float* g_p4,
                       float* dv_p4, void* stream);
+/* the two staging passes with the W32 copies (qbn_w32_from_p4 below) written in the same pass: what ops.LRTFunction uses */
+int qbn_lrt_stage_input(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
+                        long long plane_rows, float* x_p4, float* xsq_p4, float* x_w32, float* xsq_w32, void* stream);
+int qbn_lrt_stage_grad(const float* g_out, const float* std_saved, const float* eps, uint64_t seed, uint32_t stream_a,
+                       uint32_t stream_b, int64_t n_img, int H, int W, int N, int bh, int bw, long long plane_rows, float* g_p4,
+                       float* dv_p4, float* g_w32, float* dv_w32, void* stream);
 /* OIHW (mu, rho | sigma) -> blocked [mu | sigma^2] operand, TF32-rounded.  mode 0: forward (input channels zero-padded to C_pad,
  * blocked for `stride`); 1: input gradient of a stride-1 layer (taps reversed, channels swapped); 2: one phase of a stride-2
  * layer's input gradient (parameter taps tap_list[0..n_taps)); 3: the four phases of a 3x3 stride-2 layer, four taps each (absent

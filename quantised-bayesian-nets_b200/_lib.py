@@ -35,6 +35,10 @@ class KLJob(Structure):
                 ("pad_", c_int32)]
 
 
+class ScrubJob(Structure):
+    _fields_ = [("grad", c_void_p), ("n", c_int64)]
+
+
 class MaskJob(Structure):
     _fields_ = [("out", c_void_p), ("elems", c_int64), ("site_id", c_uint32), ("pad_", c_int32)]
 
@@ -111,11 +115,14 @@ _SIGNATURES = {
     "qbn_p4_shortcut_block_channels": (c_int, [c_int, c_int]),
     "qbn_conv_p4_shortcut_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P, P, c_int64, c_int, P, P, c_int, P,
                                          c_int64, P]),
+    "qbn_scrub_nan_multi": (c_int, [P, c_int, P]),
     "qbn_kl_multi": (c_int, [P, c_int, c_int64, P, c_float, P]),
     "qbn_dropout_masks_multi": (c_int, [P, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, P]),
     "qbn_lrt_noise": (c_int, [P, c_int64, c_uint64, c_uint32, c_uint32, P]),
     "qbn_p4_stage_input": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P]),
     "qbn_p4_stage_grad": (c_int, [P, P, P, c_uint64, c_uint32, c_uint32, c_int64, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P]),
+    "qbn_lrt_stage_input": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P, P, P]),
+    "qbn_lrt_stage_grad": (c_int, [P, P, P, c_uint64, c_uint32, c_uint32, c_int64, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P, P, P]),
     "qbn_lrt_p4_weight_prep": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, P,
                                        POINTER(ctypes.c_longlong), P]),
     "qbn_lrt_conv_p4_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, ctypes.c_longlong, P, P, P, c_uint64, c_uint32,

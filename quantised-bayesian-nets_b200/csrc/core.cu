@@ -1133,6 +1133,38 @@ extern "C" int qbn_kl_multi(const void* jobs_dev, int n_jobs, int64_t max_n, flo
 }
 
 
+// trainer.py:105-107 (`p.grad[p.grad != p.grad] = 0` for every parameter) for a whole model in ONE launch: blockIdx.y = tensor job.
+// The job list travels in the kernel parameters (no device table, nothing to copy: safe inside a CUDA graph capture, and gradient
+// tensors may move between steps).
+struct qbn_scrub_job_dev { float* g; int64_t n; };
+constexpr int SCRUB_MAX_JOBS = 128;
+struct ScrubBatch { qbn_scrub_job_dev j[SCRUB_MAX_JOBS]; };
+__global__ void scrub_nan_multi_kernel(const __grid_constant__ ScrubBatch jobs) {
+  const qbn_scrub_job_dev jb = jobs.j[blockIdx.y];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < jb.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = jb.g[i];
+    if (v != v) jb.g[i] = 0.0f;
+  }
+}
+extern "C" int qbn_scrub_nan_multi(const qbn_scrub_job* jobs_host, int n_jobs, void* stream) {
+  QBN_CHECK_ARG(jobs_host && n_jobs > 0, "args");
+  for (int j0 = 0; j0 < n_jobs; j0 += SCRUB_MAX_JOBS) {
+    const int nj = n_jobs - j0 < SCRUB_MAX_JOBS ? n_jobs - j0 : SCRUB_MAX_JOBS;
+    ScrubBatch b;
+    int64_t max_n = 1;
+    for (int j = 0; j < nj; ++j) {
+      QBN_CHECK_ARG(jobs_host[j0 + j].grad && jobs_host[j0 + j].n >= 0, "job");
+      b.j[j].g = jobs_host[j0 + j].grad; b.j[j].n = jobs_host[j0 + j].n;
+      if (b.j[j].n > max_n) max_n = b.j[j].n;
+    }
+    int64_t gx = (max_n + 1023) / 1024;
+    if (gx > 64) gx = 64;
+    scrub_nan_multi_kernel<<<dim3((unsigned)gx, nj), 256, 0, (cudaStream_t)stream>>>(b);
+    QBN_CHECK_LAUNCH();
+  }
+  return QBN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // SGHMC / SGLD parameter update (src/models/stochastic/sgld/utils_sgld.py:30-92), one fused pass per parameter tensor
 // instead of ~35 elementwise launches: weight decay into the gradient, burn-in preconditioner (tau, g, V_hat), optional momentum

@@ -98,6 +98,57 @@ __global__ void p4_stage_grad_kernel(const float* __restrict__ gout, const float
   }
 }
 
+// ---- fused staging: ONE pass over the NHWC tensor writes both layouts the planar training kernels read — planar C4 (forward /
+// input gradient, K-major operands) and W32 (weight gradients, MN-major operands: 128-byte rows of 32 channels, the 32-byte chunks of
+// row r XORed with r & 3, see umma_wgrad_p4.cu).  One thread = one 16-byte piece of a W32 row: a warp writes four whole W32 rows (512
+// contiguous bytes), 64 contiguous bytes into each of 8 chunk planes, and reads four pixels' channels.
+template <bool GRAD>
+__global__ void lrt_stage_fused_kernel(const float* __restrict__ src, const float* __restrict__ sd, const float* __restrict__ eps, StageGeom g,
+                                       uint64_t seed, uint32_t sa, uint32_t sb, const uint32_t* __restrict__ sbase, float4* __restrict__ a_p4,
+                                       float4* __restrict__ b_p4, float4* __restrict__ a_w32, float4* __restrict__ b_w32) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent planar conv launch (qbn_set_pdl) may start its prologue now
+  if (GRAD && sbase) sb += *sbase;
+  const int n_blk = (g.chunks + 7) / 8;
+  const long long total = (long long)n_blk * g.plane_rows * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int piece = (int)(i & 7);
+    const long long br = i >> 3;
+    const int blk = (int)(br / g.plane_rows);
+    const uint32_t r = (uint32_t)(br - (long long)blk * g.plane_rows);
+    const int j = blk * 8 + (((piece >> 1) ^ (int)(r & 3)) << 1) + (piece & 1);      // the 4-channel chunk stored at this position of row r
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (j < g.chunks) {
+      const long long pix = stage_pixel(g, r);
+      if (pix >= 0) {
+        if (!GRAD) {
+          const float4 v = ld4_guard(src, pix, g.C, 4 * j);
+          b = make_float4(tf32_round(__fmul_rn(v.x, v.x)), tf32_round(__fmul_rn(v.y, v.y)), tf32_round(__fmul_rn(v.z, v.z)), tf32_round(__fmul_rn(v.w, v.w)));
+          a = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        } else {
+          const long long off = pix * g.C + 4 * j;
+          const float4 v = *reinterpret_cast<const float4*>(src + off);
+          const float4 s = *reinterpret_cast<const float4*>(sd + off);
+          float e[4];
+          if (eps) {
+            const float4 t = *reinterpret_cast<const float4*>(eps + off);
+            e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+          } else {
+            philox_normal4(seed, sa, sb, (uint64_t)(off >> 2), e);
+          }
+          b = make_float4(tf32_round(v.x * e[0] / (2.0f * s.x)), tf32_round(v.y * e[1] / (2.0f * s.y)), tf32_round(v.z * e[2] / (2.0f * s.z)),
+                          tf32_round(v.w * e[3] / (2.0f * s.w)));
+          a = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        }
+      }
+      const long long pdst = (long long)j * g.plane_rows + r;
+      a_p4[pdst] = a;
+      b_p4[pdst] = b;
+    }
+    a_w32[i] = a;
+    b_w32[i] = b;
+  }
+}
+
 static int stage_geom(StageGeom& g, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int split, long long plane_rows) {
   memset(&g, 0, sizeof(g));
   g.H = H; g.W = W; g.C = C; g.chunks = C_pad / 4; g.bh = bh; g.bw = bw; g.split = split ? 1 : 0;
@@ -140,6 +191,38 @@ extern "C" int qbn_p4_stage_grad(const float* g_out, const float* std_saved, con
   const long long total = (long long)g.chunks * plane_rows;
   p4_stage_grad_kernel<<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g_out, std_saved, eps, g, seed, stream_a, stream_b, qbn_sample_base_ptr(),
                                                                                   reinterpret_cast<float4*>(g_p4), reinterpret_cast<float4*>(dv_p4));
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+
+// The two staging entry points with the W32 copies produced in the same pass (ops.LRTFunction uses these; the separate
+// qbn_p4_stage_* + qbn_w32_from_p4 pair gives identical bytes).  *_w32: [ceil(C_pad/32)][plane_rows][32] floats.
+extern "C" int qbn_lrt_stage_input(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
+                                   long long plane_rows, float* x_p4, float* xsq_p4, float* x_w32, float* xsq_w32, void* stream) {
+  QBN_CHECK_ARG(x && x_p4 && xsq_p4 && x_w32 && xsq_w32, "null pointer");
+  QBN_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && C > 0 && C_pad >= C && C_pad % 4 == 0 && bh >= 0 && bw >= 0, "sizes");
+  StageGeom g;
+  int rc = stage_geom(g, n_img, H, W, C, C_pad, bh, bw, phase_split, plane_rows);
+  if (rc != QBN_OK) return rc;
+  const long long total = (long long)((g.chunks + 7) / 8) * plane_rows * 8;
+  lrt_stage_fused_kernel<false><<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, nullptr, nullptr, g, 0, 0, 0, nullptr, reinterpret_cast<float4*>(x_p4), reinterpret_cast<float4*>(xsq_p4), reinterpret_cast<float4*>(x_w32),
+      reinterpret_cast<float4*>(xsq_w32));
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+extern "C" int qbn_lrt_stage_grad(const float* g_out, const float* std_saved, const float* eps, uint64_t seed, uint32_t stream_a,
+                                  uint32_t stream_b, int64_t n_img, int H, int W, int N, int bh, int bw, long long plane_rows, float* g_p4,
+                                  float* dv_p4, float* g_w32, float* dv_w32, void* stream) {
+  QBN_CHECK_ARG(g_out && std_saved && g_p4 && dv_p4 && g_w32 && dv_w32, "null pointer");
+  QBN_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && N > 0 && N % 4 == 0 && bh >= 0 && bw >= 0, "sizes (N % 4 == 0)");
+  StageGeom g;
+  int rc = stage_geom(g, n_img, H, W, N, N, bh, bw, 0, plane_rows);
+  if (rc != QBN_OK) return rc;
+  const long long total = (long long)((g.chunks + 7) / 8) * plane_rows * 8;
+  lrt_stage_fused_kernel<true><<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      g_out, std_saved, eps, g, seed, stream_a, stream_b, qbn_sample_base_ptr(), reinterpret_cast<float4*>(g_p4), reinterpret_cast<float4*>(dv_p4),
+      reinterpret_cast<float4*>(g_w32), reinterpret_cast<float4*>(dv_w32));
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -88,10 +88,22 @@ def reduce_regression(sum_mu, sum_mu2, sum_var, samples):
 
 
 def scrub_nan_grads(params):
-    """trainer.py:105-107: p.grad[p.grad != p.grad] = 0, per replica, BEFORE the allreduce."""
+    """trainer.py:105-107: p.grad[p.grad != p.grad] = 0, per replica, BEFORE the allreduce.  CUDA gradients: one launch for all
+    tensors (the pointer list travels in the kernel parameters); anything else: torch, tensor by tensor."""
+    import ctypes
+    from . import _lib
+    cuda = []
     for p in params:
-        if p.grad is not None:
-            torch.nan_to_num_(p.grad, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+        g = p.grad
+        if g is None:
+            continue
+        if g.is_cuda and g.dtype == torch.float32 and g.is_contiguous():
+            cuda.append(g)
+        else:
+            torch.nan_to_num_(g, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+    if cuda:
+        jobs = (_lib.ScrubJob * len(cuda))(*[_lib.ScrubJob(g.data_ptr(), g.numel()) for g in cuda])
+        _lib.call("qbn_scrub_nan_multi", jobs, len(cuda), ctypes.c_void_p(torch.cuda.current_stream(cuda[0].device).cuda_stream))
 
 
 def allreduce_gradients(params, average=True):

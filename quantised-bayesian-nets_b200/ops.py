@@ -182,8 +182,7 @@ class LRTFunction(torch.autograd.Function):
             math_mode = ctx.math_mode = QBN_MATH_FP32      # shapes the tcgen05 gather kernels do not take (config.tf32_eligible)
         if ctx.planar:
             # TF32 mode on the planar zero-copy kernels: operands staged once, every contraction of forward and backward on tcgen05
-            out, std, x_p4, xsq_p4, eps_c = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key, materialise_eps=True)
-            x_w32, xsq_w32 = w32_from_p4(x_p4, xsq_p4)
+            out, std, x_w32, xsq_w32, eps_c = lrt_p4_forward(xc, weight, second, second_is_sigma, _f32(bias), d, eps_c, key, materialise_eps=True)
             ctx.save_for_backward(xc, x_w32, xsq_w32, std, eps_c, weight.detach(), second.detach())
             return out
         packed = weight_prep(weight, second, second_is_sigma, chan_scale, want=("mu", "sigma2"))   # backward needs them unrounded
@@ -264,13 +263,19 @@ def lrt_p4_weight_prep(weight, second, second_is_sigma, d, mode, tap_list=None):
 
 def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(0, 0, 0), want_w32=True, materialise_eps=False):
     """xc NHWC-dense [B, C, H, W] (channels_last).  Returns out, std (NHWC) and the operands the backward needs: x, x^2 in the W32
-    layout of the weight-gradient kernel (want_w32=False: the planar-C4 maps the forward itself read)."""
+    layout of the weight-gradient kernel (want_w32=False: the planar-C4 maps the forward itself read) [, eps when materialise_eps]."""
     s2, bh, bw, Hp, Wp, C_pad = _lrt_p4_geom(d)
     rows = (4 if s2 else 1) * d.B * Hp * Wp
     pr = lrt_p4_plane_rows(rows, Wp)
     x_p4 = torch.empty((C_pad // 4, pr, 4), dtype=torch.float32, device=xc.device)
     xsq_p4 = torch.empty_like(x_p4)
-    _lib.call("qbn_p4_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _stream())
+    if want_w32:      # one pass over x writes both layouts (forward / input gradient: planar C4; weight gradients: W32)
+        x_w32 = torch.empty(((C_pad + 31) // 32, pr, 32), dtype=torch.float32, device=xc.device)
+        xsq_w32 = torch.empty_like(x_w32)
+        _lib.call("qbn_lrt_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _ptr(x_w32), _ptr(xsq_w32),
+                  _stream())
+    else:
+        _lib.call("qbn_p4_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _stream())
     w = lrt_p4_weight_prep(weight.detach().contiguous(), second.detach().contiguous(), second_is_sigma, d, 0)
     out, std = _out_like(xc, d), _out_like(xc, d)
     if eps is None and materialise_eps:
@@ -279,13 +284,8 @@ def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(
         _lib.call("qbn_lrt_noise", _ptr(eps), eps.numel(), key[0], key[1], key[2], _stream())
     _lib.call("qbn_lrt_conv_p4_fwd", d.B, Hp, Wp, C_pad, d.N, d.R, d.S, d.stride_h, _ptr(x_p4), _ptr(xsq_p4), pr, _ptr(w), _ptr(bias), _ptr(eps),
               key[0], key[1], key[2], _ptr(out), _ptr(std), _stream())
-    if materialise_eps:
-        return out, std, x_p4, xsq_p4, eps
-    if not want_w32:
-        return out, std, x_p4, xsq_p4
-    # the weight-gradient kernel reads MN-major operands: the swizzled 32-channel-block copy is what the backward keeps
-    x_w32, xsq_w32 = w32_from_p4(x_p4, xsq_p4)
-    return out, std, x_w32, xsq_w32
+    keep = (x_w32, xsq_w32) if want_w32 else (x_p4, xsq_p4)
+    return (out, std) + keep + ((eps,) if materialise_eps else ())
 
 
 def w32_from_p4(a, b=None):
@@ -304,11 +304,12 @@ def lrt_p4_backward(xc, x_w32, xsq_w32, std, eps, weight, second, second_is_sigm
     pr_g = lrt_p4_plane_rows(d.B * Hp * Wp, Wp)
     g_p4 = torch.empty((d.N // 4, pr_g, 4), dtype=torch.float32, device=gc.device)
     dv_p4 = torch.empty_like(g_p4)
-    _lib.call("qbn_p4_stage_grad", _ptr(gc), _ptr(std), _ptr(eps), key[0], key[1], key[2], d.B, d.Ho, d.Wo, d.N, bh, bw, pr_g, _ptr(g_p4),
-              _ptr(dv_p4), _stream())
+    g_w32 = torch.empty(((d.N + 31) // 32, pr_g, 32), dtype=torch.float32, device=gc.device)
+    dv_w32 = torch.empty_like(g_w32)
+    _lib.call("qbn_lrt_stage_grad", _ptr(gc), _ptr(std), _ptr(eps), key[0], key[1], key[2], d.B, d.Ho, d.Wo, d.N, bh, bw, pr_g, _ptr(g_p4),
+              _ptr(dv_p4), _ptr(g_w32), _ptr(dv_w32), _stream())
     dmu_p = torch.empty(d.N * d.R * d.S * d.C, dtype=torch.float32, device=gc.device)
     dsig2_p = torch.empty_like(dmu_p)
-    g_w32, dv_w32 = w32_from_p4(g_p4, dv_p4)
     _lib.call("qbn_lrt_wgrad_p4", d.B, Hp, Wp, d.C, d.N, d.R, d.S, d.stride_h, _ptr(g_w32), _ptr(dv_w32), pr_g, _ptr(x_w32), _ptr(xsq_w32),
               x_w32.stride(0) // 32, _ptr(dmu_p), _ptr(dsig2_p), _stream())
     dx = None

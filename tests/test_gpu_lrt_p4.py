@@ -98,6 +98,39 @@ def test_w32_layout():
             assert torch.equal(got.view(nblk, rows, 4, 8), exp)
 
 
+def test_fused_staging_equals_the_two_pass_staging():
+    """qbn_lrt_stage_input / _grad (one pass, both layouts) == qbn_p4_stage_* followed by qbn_w32_from_p4, bit for bit."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for (B, C, H, W, border, split) in ((3, 24, 8, 6, (1, 1), False), (2, 3, 6, 6, (1, 1), False), (2, 16, 8, 12, (1, 1), True),
+                                        (2, 40, 5, 7, (2, 2), False), (5, 96, 4, 4, (0, 0), False)):
+        x = ops.nhwc(torch.randn(B, C, H, W, generator=g).cuda())
+        C_pad = (C + 7) // 8 * 8
+        Hp, Wp = (H // 2 + 1, W // 2 + 1) if split else (H + border[0], W + border[1])
+        pr = ops.lrt_p4_plane_rows((4 if split else 1) * B * Hp * Wp, Wp)
+        mk = lambda *shape: torch.full(shape, float("nan"), device="cuda")
+        a, b = mk(C_pad // 4, pr, 4), mk(C_pad // 4, pr, 4)
+        ops._lib.call("qbn_p4_stage_input", ops._ptr(x), B, H, W, C, C_pad, border[0], border[1], int(split), pr, ops._ptr(a), ops._ptr(b), ops._stream())
+        wa, wb = ops.w32_from_p4(a, b)
+        a2, b2, wa2, wb2 = mk(C_pad // 4, pr, 4), mk(C_pad // 4, pr, 4), mk((C_pad + 31) // 32, pr, 32), mk((C_pad + 31) // 32, pr, 32)
+        ops._lib.call("qbn_lrt_stage_input", ops._ptr(x), B, H, W, C, C_pad, border[0], border[1], int(split), pr, ops._ptr(a2), ops._ptr(b2),
+                      ops._ptr(wa2), ops._ptr(wb2), ops._stream())
+        for u, v in ((a, a2), (b, b2), (wa, wa2), (wb, wb2)):
+            assert torch.equal(u, v)
+        if not split and C % 4 == 0:
+            gout, sd = ops.nhwc(torch.randn(B, C, H, W, generator=g).cuda()), ops.nhwc(torch.rand(B, C, H, W, generator=g).cuda() + 0.5)
+            for eps in (ops.nhwc(torch.randn(B, C, H, W, generator=g).cuda()), None):
+                a, b = mk(C // 4, pr, 4), mk(C // 4, pr, 4)
+                ops._lib.call("qbn_p4_stage_grad", ops._ptr(gout), ops._ptr(sd), ops._ptr(eps), 5, 6, 7, B, H, W, C, border[0], border[1], pr, ops._ptr(a),
+                              ops._ptr(b), ops._stream())
+                wa, wb = ops.w32_from_p4(a, b)
+                a2, b2, wa2, wb2 = mk(C // 4, pr, 4), mk(C // 4, pr, 4), mk((C + 31) // 32, pr, 32), mk((C + 31) // 32, pr, 32)
+                ops._lib.call("qbn_lrt_stage_grad", ops._ptr(gout), ops._ptr(sd), ops._ptr(eps), 5, 6, 7, B, H, W, C, border[0], border[1], pr, ops._ptr(a2),
+                              ops._ptr(b2), ops._ptr(wa2), ops._ptr(wb2), ops._stream())
+                for u, v in ((a, a2), (b, b2), (wa, wa2), (wb, wb2)):
+                    assert torch.equal(u, v)
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_lrt_p4_forward(shape):
     from qbn_b200 import ops
@@ -216,3 +249,23 @@ def test_graphed_train_step_matches_the_eager_loop():
         a, b = finals[0][k], finals[1][k]
         assert float((a - b).norm() / (a.norm() + 1e-12)) < 2e-3, k
     config.set_math_mode("fp32")
+
+
+def test_nan_scrub_of_all_gradients_in_one_launch():
+    """dist.scrub_nan_grads == trainer.py:105-107 (`p.grad[p.grad != p.grad] = 0` per parameter; infinities stay)."""
+    from qbn_b200 import dist as qdist
+    g = torch.Generator().manual_seed(8)
+    params = [torch.nn.Parameter(torch.randn(n, generator=g).cuda()) for n in (1, 7, 1024, 5000, 3)] + [torch.nn.Parameter(torch.randn(4).cuda())]
+    params[-1].grad = None
+    refs = []
+    for p in params[:-1]:
+        gr = torch.randn(p.shape, generator=g).cuda()
+        gr[::3] = float("nan")
+        gr[1::7] = float("inf")
+        p.grad = gr
+        r = gr.clone()
+        r[r != r] = 0
+        refs.append(r)
+    qdist.scrub_nan_grads(params)
+    for p, r in zip(params[:-1], refs):
+        assert torch.equal(p.grad, r)
