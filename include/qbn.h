@@ -425,6 +425,13 @@ int qbn_cls_metrics(const float* probs, const int64_t* target, int B, int K, flo
 int qbn_reg_metrics(const float* mean, const float* var, const float* target, int64_t B,
                     float* out, void* stream);
 
+/* ---- N4: the classification ELBO (src/losses.py:14-29, trainer.py:96-104), value and gradient in one launch ----
+ * out3 = {loss, data, kl_term}: data = data_scale * mean_b -log(probs[b][target[b]] + 1e-8), kl_term = *kl * kl_scale,
+ * loss = data + gamma * kl_term; d_probs [B][K] (nullable) = d data / d probs.  'batch' scaling: data_scale 1, kl_scale
+ * 1 / (B * n_batches); 'whole': data_scale n_points * loss_multiplier, kl_scale 1 / n_batches.                       */
+int qbn_elbo_cls(const float* probs, const int64_t* target, const float* kl, int B, int K, float data_scale,
+                 float kl_scale, float gamma, float* out3, float* d_probs, void* stream);
+
 /* ---- SGHMC / SGLD parameter update (utils_sgld.py:30-92), one fused pass per parameter tensor:
  * grad += weight_decay * p (in place, like the reference); burn_in: tau, g, V_hat preconditioner update; resample_momentum:
  * v = z_m * sqrt(lr^2 / (sqrt(V_hat) + eps)); v += -lr^2/(sqrt(V_hat)+eps) * grad - base_C * v + z_n * sqrt(max(2 lr^2/(sqrt(V_hat)+eps)

@@ -100,6 +100,7 @@ _SIGNATURES = {
     "qbn_softmax_accumulate": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
     "qbn_mc_mean": (c_int, [P, c_int, c_int64, P, P]),
     "qbn_reg_mc_reduce": (c_int, [P, P, c_int, c_int64, P, P, P]),
+    "qbn_elbo_cls": (c_int, [P, P, P, c_int, c_int, c_float, c_float, c_float, P, P, P]),
     "qbn_cls_metrics": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P]),
     "qbn_reg_metrics": (c_int, [P, P, P, c_int64, P, P]),
     "qbn_maxpool2x2": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),

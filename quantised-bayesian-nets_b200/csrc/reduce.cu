@@ -264,3 +264,47 @@ extern "C" int qbn_reg_metrics(const float* mean, const float* var, const float*
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// N4: the classification ELBO of src/losses.py:14-29 in ONE launch, value and gradient:
+//   data = data_scale * mean_b -log(p[b, t_b] + 1e-8);  kl_term = kl * kl_scale;  loss = data + gamma * kl_term
+//   d_probs[b, k] = -data_scale / (B * (p[b, t_b] + 1e-8)) at k == t_b, else 0        (d loss / d probs; the caller scales it)
+// out[0..2] = {loss, data, kl_term}.  One CTA: the [B, K] output of a training batch is a few KB.
+// ---------------------------------------------------------------------------------------------
+__global__ void elbo_cls_kernel(const float* __restrict__ probs, const int64_t* __restrict__ target, const float* __restrict__ kl, int B, int K,
+                                float data_scale, float kl_scale, float gamma, float* __restrict__ out, float* __restrict__ d_probs) {
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int64_t t = target[b];
+    const bool ok = t >= 0 && t < K;
+    const float p = ok ? probs[(int64_t)b * K + t] + 1e-8f : 1.0f;
+    acc += -logf(p);
+    if (d_probs) {
+      for (int k = 0; k < K; ++k) d_probs[(int64_t)b * K + k] = 0.f;
+      if (ok) d_probs[(int64_t)b * K + t] = -data_scale / ((float)B * p);
+    }
+  }
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float data = data_scale * (acc / (float)B);
+      const float klt = kl[0] * kl_scale;
+      out[0] = data + gamma * klt;
+      out[1] = data;
+      out[2] = klt;
+    }
+  }
+}
+extern "C" int qbn_elbo_cls(const float* probs, const int64_t* target, const float* kl, int B, int K, float data_scale, float kl_scale,
+                            float gamma, float* out3, float* d_probs, void* stream) {
+  QBN_CHECK_ARG(probs && target && kl && out3 && B > 0 && K > 0, "args");
+  elbo_cls_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(probs, target, kl, B, K, data_scale, kl_scale, gamma, out3, d_probs);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}

@@ -269,3 +269,40 @@ def test_nan_scrub_of_all_gradients_in_one_launch():
     qdist.scrub_nan_grads(params)
     for p, r in zip(params[:-1], refs):
         assert torch.equal(p.grad, r)
+
+
+@pytest.mark.parametrize("scaling", ["batch", "whole"])
+def test_fused_elbo_matches_the_reference_expressions(scaling, golden):
+    """losses.ClassificationLoss on CUDA tensors (one launch: qbn_elbo_cls) == src/losses.py:14-29 evaluated with torch on the same
+    tensors — loss, both terms, d/d output and d/d kl — and == the reference-generated fixture."""
+    import torch.nn.functional as F
+    from qbn_b200 import losses, zoo
+    g = torch.Generator().manual_seed(12)
+    B, K = 37, 10
+    out = torch.softmax(torch.randn(B, K, generator=g), -1).cuda().requires_grad_(True)
+    tgt = torch.randint(0, K, (B,), generator=g).cuda()
+    kl = torch.tensor(1234.5, device="cuda", requires_grad=True)
+    args = zoo.Args(loss_multiplier=0.7)
+    crit = losses.LOSS_FACTORY["classification"](args, scaling)
+    gamma, n_batches, n_points = 0.3, 176, 45000
+    loss, data, klt = crit(out, tgt, kl, gamma, n_batches, n_points)
+    (loss + 0.5 * data + 0.25 * klt).backward()
+    o2, k2 = out.detach().clone().requires_grad_(True), kl.detach().clone().requires_grad_(True)
+    if scaling == "whole":
+        ce = n_points * F.nll_loss(torch.log(o2 + 1e-8), tgt) * args.loss_multiplier
+        kk = k2 / n_batches
+    else:
+        ce = F.nll_loss(torch.log(o2 + 1e-8), tgt)
+        kk = k2 / (B * n_batches)
+    ref = ce + gamma * kk
+    (ref + 0.5 * ce + 0.25 * kk).backward()
+    for a, b in ((loss, ref), (data, ce), (klt, kk), (out.grad, o2.grad), (kl.grad, k2.grad)):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # the fixture generated by the unmodified reference (oracle/make_golden.py:gen_losses): loss_multiplier 0.5, kl 123.4, gamma .01
+    f = golden("losses")
+    o = torch.as_tensor(f["out"]).cuda().requires_grad_(True)
+    vals = losses.LOSS_FACTORY["classification"](zoo.Args(loss_multiplier=0.5), scaling)(o, torch.as_tensor(f["target"]).cuda(), torch.tensor(123.4).cuda(),
+                                                                                      0.01, 176, 45000)
+    vals[0].backward()
+    np.testing.assert_allclose([float(v) for v in vals], f["cls_%s" % scaling], rtol=2e-6)
+    np.testing.assert_allclose(o.grad.cpu().numpy(), f["cls_%s_dout" % scaling], rtol=1e-5, atol=1e-7)
