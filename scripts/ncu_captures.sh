@@ -1,4 +1,6 @@
 #!/bin/bash
+# The three ncu captures behind profiles/r02_p4_dram_traffic.json, r02_lrt_kernels_ncu_full.csv and r02_launches.csv (one GPU):
+#   gpurun --timeout 2400 -- bash scripts/ncu_captures.sh
 mkdir -p gpurun_out
 # (1) DRAM traffic of the benchmarked configuration, final kernels
 timeout 600 ncu --set full --clock-control none -k regex:umma_conv -c 44 -o /tmp/r02_p4 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train --no-int8 --no-gpu-eager > gpurun_out/c13_ncu_eval.log 2>&1
