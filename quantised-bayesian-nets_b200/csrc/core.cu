@@ -976,8 +976,26 @@ extern "C" int qbn_sample_weights_blocked(const float* mu_b, const float* sigma_
   return QBN_OK;
 }
 
-// global average pool of planar-C4 maps: x [C/4][n_img * HW][4] -> out [n_img][C]; one warp per (image, chunk)
-// reads HW contiguous 16-byte rows.  The zero border contributes nothing; divisor = interior size.
+// global average pool of planar-C4 maps: x [C/4][n_img * HW][4] -> out [n_img][C].  The zero border contributes nothing; divisor =
+// interior size.  Small maps (HW <= 64: the 5x5 padded map that ends the ResNet): one THREAD per (image, chunk) — HW independent
+// 16-byte loads of one contiguous run in flight per thread, consecutive threads on consecutive images of a plane, no shuffles
+// (the warp-per-map version ran at 2 TB/s: 25 of 32 lanes busy, one load per 20 shuffles).  Larger maps: one warp per (image, chunk).
+__global__ void avgpool_p4_small_kernel(const float* __restrict__ x, int64_t n_img, int HW, int64_t plane, int C, float inv, float* __restrict__ out) {
+  const int chunks = C >> 2;
+  const int64_t total = n_img * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i / n_img);
+    const int64_t img = i - (int64_t)j * n_img;
+    const float4* src = reinterpret_cast<const float4*>(x) + (int64_t)j * plane + img * HW;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+    for (int r = 0; r < HW; ++r) {
+      const float4 v = src[r];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + img * C + 4 * j) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
 __global__ void avgpool_p4_kernel(const float* __restrict__ x, int64_t n_img, int HW, int64_t plane, int C, float inv, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1003,6 +1021,11 @@ __global__ void avgpool_p4_kernel(const float* __restrict__ x, int64_t n_img, in
 }
 extern "C" int qbn_avgpool_p4(const float* x, int64_t n_img, int HW, int64_t plane_rows, int C, float divisor, float* out, void* stream) {
   QBN_CHECK_ARG(x && out && n_img > 0 && HW > 0 && C > 0 && C % 4 == 0 && divisor > 0.f && plane_rows >= n_img * HW, "args");
+  if (HW <= 64) {
+    avgpool_p4_small_kernel<<<qbn_grid_for(n_img * (C / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, n_img, HW, plane_rows, C, 1.0f / divisor, out);
+    QBN_CHECK_LAUNCH();
+    return QBN_OK;
+  }
   const int64_t warps = n_img * (C / 4);
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = (int64_t)qbn_sm_count() * 16;

@@ -340,3 +340,14 @@ def test_p4_conv_fused_shortcut(shape):
     full = got.to_nchw(keep_border=True).clone()
     full[:, :, 1:, 1:] = 0
     assert float(full.abs().max()) == 0.0
+
+
+def test_avgpool_p4_small_maps():
+    """qbn_avgpool_p4 on the 5x5 padded map that ends the ResNet (one thread per (image, chunk)) and on a larger map (one warp each)."""
+    from qbn_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for (n, C, H) in ((37, 192, 4), (5, 24, 7), (3, 48, 16)):
+        x = torch.randn(n, C, H, H, generator=g).cuda()
+        m = ops.P4Map.from_nchw(x, (1, 1))
+        pooled = ops.avgpool_p4(m, H * H)
+        close(pooled, x.mean(dim=(2, 3)), 1e-5, 1e-6)
