@@ -306,3 +306,34 @@ def test_fused_elbo_matches_the_reference_expressions(scaling, golden):
     vals[0].backward()
     np.testing.assert_allclose([float(v) for v in vals], f["cls_%s" % scaling], rtol=2e-6)
     np.testing.assert_allclose(o.grad.cpu().numpy(), f["cls_%s_dout" % scaling], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("geom", [(3, 24, 12, 20, 24, 3, 1, 1), (2, 16, 10, 6, 32, 3, 2, 1), (1, 8, 5, 9, 8, 3, 1, 1), (2, 32, 8, 14, 16, 1, 2, 0),
+                                  (1, 24, 32, 32, 24, 3, 1, 1)])
+def test_lrt_p4_non_square_maps_and_batch_one(geom):
+    """The planar LRT path on H != W maps and B = 1, through ops.LRTFunction, against the oracle (forward, dx, d_mu, d_rho)."""
+    from qbn_b200 import ops
+    B, C, H, W, N, k, stride, pad = geom
+    g = torch.Generator().manual_seed(31 + H * W)
+    x = torch.randn(B, C, H, W, generator=g)
+    mu = torch.randn(N, C, k, k, generator=g) / (C * k * k) ** 0.5
+    rho = torch.empty(N, C, k, k).uniform_(-5, -2, generator=g)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    eps = torch.randn(B, N, Ho, Wo, generator=g)
+    go = torch.randn(B, N, Ho, Wo, generator=g)
+    xx, m, r = x.cuda().requires_grad_(True), mu.cuda().requires_grad_(True), rho.cuda().requires_grad_(True)
+    calls = []
+    real = ops._lib.call
+    ops._lib.call = lambda name, *a: (calls.append(name), real(name, *a))[1]
+    try:
+        out = ops.LRTFunction.apply(xx, m, r, None, (stride, stride), (pad, pad), (1, 1), eps.cuda(), (0, 0, 0), ops.QBN_MATH_TF32, False, None)
+        (out * go.cuda()).sum().backward()
+    finally:
+        ops._lib.call = real
+    assert "qbn_lrt_conv_p4_fwd" in calls and "qbn_lrt_wgrad_p4" in calls
+    yo, so = O.lrt_conv_fwd(x, mu, rho, None, eps, stride, pad)
+    dx_o, dmu_o, drho_o, _ = O.lrt_conv_bwd(x, mu, rho, eps, so, go, stride, pad)
+    close(out, yo)
+    close(xx.grad, dx_o)
+    close(m.grad, dmu_o)
+    close(r.grad, drho_o)
