@@ -51,6 +51,17 @@ def _peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def _cublas_tf32():
+    """cuBLAS TF32 / INT8 GEMM throughput measured on a B200 of this pool (scripts/measure_peaks.py), beside the derived figure."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_measured_peaks_tf32_int8.json")) as f:
+            p = json.load(f)
+        return {"tf32_tflops": p["tf32_tflops"], "tf32_tflops_sustained": p["tf32_tflops_sustained"], "int8_tops": p["int8_tops"],
+                "source": "torch.matmul 8192^3 (scripts/measure_peaks.py, profiles/r02_measured_peaks_tf32_int8.json)"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -499,7 +510,8 @@ def main():
                     "algorithmic_bytes_note": "1.929 MB per sample-image (SURVEY 8d: activations in + out of the 21 stochastic layers, fp32) x the "
                                               "sample-images of the step / conv launches",
                     "tensor_view": {"achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak,
-                                    "peak_source": "1/2 x sustained bf16 of %s (TF32 peak not in MEASURED_PEAKS.json)" % peaks["source"]},
+                                    "peak_source": "1/2 x sustained bf16 of %s (TF32 peak not in MEASURED_PEAKS.json)" % peaks["source"],
+                                    "cublas_tf32_8192": _cublas_tf32()},
                     "share_of_step": t_ms / (total_ms / args.steps)}
     m = metric.compute() if rank == 0 else None
     n_state = metric.state.numel()
