@@ -397,6 +397,16 @@ int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_real, int N, int R, int S, int
  * touches global memory only after that kernel has completed (griddepcontrol.wait).  Process-wide, off by default. */
 int qbn_set_pdl(int enabled);
 
+/* int8 MC-Dropout (dropout.py:31-39) of a chunk of Monte-Carlo samples on planar-C16 maps, optionally followed by the BasicBlock's
+ * quantized::add[_relu] with `residual` (models_mc.py:143-157: the dropout sits between the second conv and the add).  Same integers
+ * as qbn_i8_dropout_mc + qbn_i8_add.  x holds q - z_x at scale s_x (x_shared: B images shared by all samples); mask fp32 {0,1}
+ * [n_samples*B][C] (qbn_dropout_masks_multi); out holds q - z_m at scale s_drop_out = s_m * multiplier, or q - z_add after the add
+ * (rq: s_res, z_res, s_add, z_add, add_relu).  x, residual: normal layout (Hp x Wp maps); out: normal or phase-split. */
+int qbn_i8_p16_dropout(const int8_t* x, long long x_plane_rows, int x_shared, int n_samples, int B, int Hp, int Wp,
+                       int out_phase_split, int C, float s_x, const float* mask, float s_m, int32_t z_m, float s_drop_out, int act_max,
+                       const int8_t* residual, long long res_plane_rows, const qbn_i8_requant* rq, int8_t* out,
+                       long long out_plane_rows, void* stream);
+
 /* Draw offset of the Monte-Carlo samplers, kept on the DEVICE: after qbn_set_sample_base(p) every sampler launch
  * (qbn_sample_weights*, qbn_i8_sample_weights, qbn_dropout_masks_multi, qbn_i8_dropout_mc) uses the Philox stream index
  * *p + sample0 + s instead of sample0 + s, reading *p when the kernel runs.  One captured CUDA graph then serves every batch

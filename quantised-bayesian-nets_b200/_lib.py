@@ -94,6 +94,8 @@ _SIGNATURES = {
     "qbn_i8_p16_from_nhwc": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int32, c_int64, P, P]),
     "qbn_i8_p16_to_nhwc": (c_int, [P, c_int64, c_int, c_int, c_int, c_int32, c_int64, P, P]),
     "qbn_i8_p16_avgpool": (c_int, [P, c_int64, c_int, c_int, c_int, c_int32, c_int64, c_int, c_int, P, P]),
+    "qbn_i8_p16_dropout": (c_int, [P, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, c_float, c_int32, c_float, c_int, P,
+                                   ctypes.c_longlong, POINTER(I8Requant), P, ctypes.c_longlong, P]),
     "qbn_set_sample_base": (c_int, [P]),
     "qbn_set_pdl": (c_int, [c_int]),
     "qbn_sghmc_step": (c_int, [P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_int, P, P, c_uint64, c_uint32, c_uint32, P]),

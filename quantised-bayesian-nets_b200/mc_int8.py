@@ -74,11 +74,12 @@ class PlanarUnsupported(NotImplementedError):
 
 
 class _Conv8:
-    __slots__ = ("mod", "src", "dst", "stride", "ksize", "relu", "residual", "add_qp", "add_relu", "sampled", "C", "N", "ref_idx", "name")
+    __slots__ = ("mod", "src", "dst", "stride", "ksize", "relu", "residual", "add_qp", "add_relu", "sampled", "C", "N", "ref_idx", "name", "dropout")
 
     def __init__(self, mod, src, dst, ref_idx=None, name=""):
         self.mod, self.src, self.dst, self.ref_idx, self.name = mod, src, dst, ref_idx, name
         self.residual, self.add_qp, self.add_relu = None, None, False
+        self.dropout = None          # an int8 MC-Dropout site (dropout.py:31-39) applied to this conv's output, before a residual add
         self.sampled = hasattr(mod, "sampled_weights")
         self.relu = bool(getattr(mod, "RELU", False))
         self.N, self.C = int(mod.out_channels), int(mod.in_channels)
@@ -152,7 +153,7 @@ class Int8PlanarEngine:
                 continue
             if isinstance(mod, BernoulliDropout):
                 if mod._prob() > 0:
-                    raise PlanarUnsupported("MC-Dropout sites run on Int8MCEngine")
+                    self._attach_dropout(self.steps[-1] if self.steps and self.steps[-1].dst == cur else None, mod)
                 continue
             if self._is_conv(mod):
                 cur = self._conv(mod, cur).dst
@@ -180,6 +181,16 @@ class Int8PlanarEngine:
             if (st.src in self.split and st.stride != 2) or st.residual in self.split or self.out_reg in self.split or 0 in self.split:
                 raise PlanarUnsupported("a map feeds both a stride-2 conv and a stride-1 reader")
 
+    @staticmethod
+    def _attach_dropout(step, mod):
+        """An MC-Dropout site directly behind a conv: one elementwise launch on the conv's planar output (qbn_i8_p16_dropout)."""
+        fn = mod.mul_mask
+        if step is None or step.dropout is not None:
+            raise PlanarUnsupported("an MC-Dropout site that does not directly follow a convolution")
+        if not (hasattr(fn, "scale") and hasattr(fn, "zero_point")):
+            raise PlanarUnsupported("BernoulliDropout.mul_mask is not converted (quant_utils.convert)")
+        step.dropout = mod
+
     def _block(self, blk, cur):
         def seq(mods, reg):
             last = None
@@ -188,7 +199,7 @@ class Int8PlanarEngine:
                     continue
                 if isinstance(mod, BernoulliDropout):
                     if mod._prob() > 0:
-                        raise PlanarUnsupported("MC-Dropout sites run on Int8MCEngine")
+                        self._attach_dropout(last, mod)
                     continue
                 if not self._is_conv(mod):
                     raise PlanarUnsupported("module %s inside a BasicBlock" % type(mod).__name__)
@@ -239,6 +250,32 @@ class Int8PlanarEngine:
             cache[key] = ops.i8_p16_block_weights(mod.weight.reshape((1,) + tuple(mod.weight.shape)), C_pad, st.stride)
         return cache[key], True
 
+    def _chunk_masks(self, n, B, sample0, device):
+        """Keep / drop decisions of every MC-Dropout site for the chunk, {id(module): fp32 [n*B, C]}: ONE launch, Philox keyed
+        (seed, site id, GLOBAL sample index + draw offset) — the draws BernoulliDropout._forward_int8 makes under noise.sample_batch."""
+        sites = [st for st in self.steps if st.dropout is not None]
+        if not sites:
+            return {}
+        from ._lib import MaskJob
+        ps = {round(st.dropout._prob(), 9) for st in sites}
+        if len(ps) != 1:
+            raise PlanarUnsupported("MC-Dropout sites with different probabilities")
+        key = ("masks", n, B)
+        cache = self.__dict__.setdefault("_bufs", {})
+        if key not in cache:
+            bufs = {id(st.dropout): torch.empty((n * B, st.N), dtype=torch.float32, device=device) for st in sites}
+            jobs = (MaskJob * len(sites))()
+            for i, st in enumerate(sites):
+                jobs[i] = MaskJob(bufs[id(st.dropout)].data_ptr(), B * st.N, int(st.dropout._qbn_layer_id), 0)
+            raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
+            cache[key] = (raw, bufs, max(B * st.N for st in sites))
+            for st in sites:                               # the multiplier is read once (host value of a frozen parameter)
+                st.dropout._mult = float(st.dropout.multiplier.detach().reshape(-1)[0])
+        raw, bufs, max_elems = cache[key]
+        ops.dropout_masks_multi(raw, len(sites), max_elems, n, 1.0 - next(iter(ps)), noise.seed(), sample0)
+        self.launches += 1
+        return bufs
+
     def _run_chunk(self, x, n, sample0, injected=None):
         from .quant_utils import QTensor
         B = x.shape[0]
@@ -250,6 +287,7 @@ class Int8PlanarEngine:
         regs = {0: ops.P16Map.from_quint8(q, xq.scale, xq.zero_point, bits, out=m0)}
         self.launches += 2
         shared = {0: True}
+        masks = self._chunk_masks(n, B, sample0, x.device)
         for si, st in enumerate(self.steps):
             src = regs[st.src]
             if st.stride == 2:
@@ -269,10 +307,27 @@ class Int8PlanarEngine:
             res = regs[st.residual] if st.residual is not None else None
             if res is not None and shared.get(st.residual, False):
                 raise PlanarUnsupported("residual taken from the network input")
-            ops.i8_conv_p16_forward(src, wb, n, st.N, st.ksize, st.ksize, st.stride, mod.bias(), s_w, z_w, mod.scale, mod.zero_point, st.relu,
-                                    bits, out, residual=res, add_qp=st.add_qp, add_relu=st.add_relu, x_shared=shared[st.src], w_shared=w_shared,
-                                    out_phase_split=split)
-            self.launches += 1
+            drop = st.dropout
+            if drop is None:
+                ops.i8_conv_p16_forward(src, wb, n, st.N, st.ksize, st.ksize, st.stride, mod.bias(), s_w, z_w, mod.scale, mod.zero_point, st.relu,
+                                        bits, out, residual=res, add_qp=st.add_qp, add_relu=st.add_relu, x_shared=shared[st.src], w_shared=w_shared,
+                                        out_phase_split=split)
+                self.launches += 1
+            else:
+                # conv -> (BN, ReLU folded) -> MC-Dropout [-> residual add -> ReLU] (models_mc.py:117-157): the dropout sits between the
+                # conv and the add, so conv = requantise only, then ONE elementwise launch: mask multiply (+ add + ReLU).  A conv with
+                # fixed weights on an input shared by all samples runs once; its output forks into the samples at the dropout.
+                once = shared[st.src] and w_shared
+                nc = 1 if once else n
+                pre = self._buf(("pre", si, nc, B, Ho, Wo), lambda: ops.P16Map.empty(nc * B, st.N, Ho + 1, Wo + 1, 1, x.device))     # normal layout
+                ops.i8_conv_p16_forward(src, wb, nc, st.N, st.ksize, st.ksize, st.stride, mod.bias(), s_w, z_w, mod.scale, mod.zero_point, st.relu,
+                                        bits, pre, x_shared=shared[st.src], w_shared=w_shared, out_phase_split=False)
+                if res is not None and (res.C * (res.Hp - 1) * (res.Wp - 1) * B) % 64 != 0:
+                    raise PlanarUnsupported("fused quantized::add needs maps whose element count is a multiple of 64 (ATen's vector body)")
+                ops.i8_p16_dropout(pre, masks[id(drop)], n, B, float(drop.mul_mask.scale), int(drop.mul_mask.zero_point),
+                                   float(drop.multiplier.detach().reshape(-1)[0]) if not hasattr(drop, "_mult") else drop._mult, bits, out,
+                                   x_shared=once and n > 1, residual=res, add_qp=st.add_qp, add_relu=st.add_relu)
+                self.launches += 2
             regs[st.dst] = out
             shared[st.dst] = False
             if self.trace is not None:

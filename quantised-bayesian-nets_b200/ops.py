@@ -1015,6 +1015,27 @@ def i8_conv_p16_forward(x, w_blocked, n_samples, N, R, S, stride, bias, s_w, z_w
     return out
 
 
+def i8_p16_dropout(x, mask, n_samples, B, s_m, z_m, multiplier, act_bits, out, x_shared=False, residual=None, add_qp=None, add_relu=False):
+    """int8 MC-Dropout of a chunk on planar-C16 maps (+ the BasicBlock's residual add): include/qbn.h qbn_i8_p16_dropout.
+    x, residual, out: P16Map (same geometry and phases); mask: fp32 [n_samples*B, C]; the output's qparams are set here."""
+    s_drop = float(s_m) * float(multiplier)              # quantized::mul_scalar: scale * scalar in double
+    rq = None
+    if residual is not None:
+        rq = _lib.I8Requant(1.0, 1.0, 0, 1.0, 0, 0, (1 << act_bits) - 1, float(residual.scale), int(residual.zero_point), float(add_qp[0]), int(add_qp[1]),
+                            int(bool(add_relu)))
+    if x.phases != 1 or (residual is not None and residual.phases != 1):
+        raise _lib.QbnError("qbn_i8_p16_dropout reads maps in the normal layout (the output may be phase-split)")
+    _lib.call("qbn_i8_p16_dropout", _ptr(x.buf), x.plane_rows, int(bool(x_shared)), int(n_samples), int(B), x.Hp, x.Wp, int(out.phases == 4), x.C, float(x.scale),
+              _ptr(mask), float(s_m), int(z_m), s_drop, (1 << act_bits) - 1, _ptr(residual.buf if residual is not None else None),
+              residual.plane_rows if residual is not None else 0, ctypes.byref(rq) if rq is not None else None, _ptr(out.buf), out.plane_rows, _stream())
+    if residual is not None:
+        out.scale, out.zero_point = float(add_qp[0]), int(add_qp[1])
+    else:
+        out.scale, out.zero_point = s_drop, int(z_m)
+    out.bits = act_bits
+    return out
+
+
 def i8_p16_avgpool(x, act_bits=7):
     """nn.AvgPool2d over the whole map of a P16Map -> uint8 [n_img, C] (same scale / zero point)."""
     out = torch.empty((x.n_img, x.C), dtype=torch.uint8, device=x.buf.device)

@@ -78,6 +78,16 @@ def test_mc_dropout_resnet_int8_matches_the_reference_on_fbgemm():
     np.testing.assert_allclose(got_sum.cpu().numpy(), torch.stack(loop).sum(0).cpu().numpy(), rtol=0, atol=2e-6)
     rate = float(torch.stack([(m == 0).float().mean() for m in masks]).mean())
     assert 0.05 < rate < 0.25                                            # p = 0.15
+    # the planar kind::i8 engine takes the MC-Dropout network too (one elementwise launch per site: mask multiply + the block's
+    # residual add): same Philox draws, same integers as the module-driven engine -> identical probability sums
+    from qbn_b200.mc_int8 import Int8PlanarEngine, make_int8_engine
+    pe = make_int8_engine(mine, chunk=3)
+    assert isinstance(pe, Int8PlanarEngine) and sum(st.dropout is not None for st in pe.steps) == len(sites)
+    got_planar = pe.predict_sum(x.cuda(), S)
+    np.testing.assert_allclose(got_planar.cpu().numpy(), got_sum.cpu().numpy(), rtol=0, atol=2e-6)
+    assert torch.equal(pe.predict_sum(x.cuda(), S), got_planar)          # graph replay
+    one = Int8PlanarEngine(mine, chunk=1, use_graph=False).predict_sum(x.cuda(), S)      # chunking does not change the draws
+    np.testing.assert_allclose(one.cpu().numpy(), got_planar.cpu().numpy(), rtol=0, atol=2e-6)
 
 
 def test_sghmc_optimiser_step_matches_the_reference():
