@@ -38,12 +38,18 @@ QBN_DEVINL float4 ld_nc_f4(const float* p) {
   return r;
 }
 
+// tuning/diagnostic switches are compiled out of the product build (-DQBN_TUNING enables them)
+#ifdef QBN_TUNING
+#define S1DBG (p.dbg)
+#else
+#define S1DBG 0
+#endif
 // cycle accounting of CTA 0 (QBN_S1_DBG bit 8192): [role*8 + category] summed over its tiles
 __device__ unsigned long long g_s1_prof[32];
-#define PROF_BEGIN() long long _t0 = (p.dbg & 8192) ? clock64() : 0
+#define PROF_BEGIN() long long _t0 = (S1DBG & 8192) ? clock64() : 0
 #define PROF_ADD(slot)                                                            \
   do {                                                                            \
-    if ((p.dbg & 8192) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 4 + NW_MMA)) { \
+    if ((S1DBG & 8192) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 4 + NW_MMA)) { \
       long long _t1 = clock64();                                                  \
       g_s1_prof[slot] += (unsigned long long)(_t1 - _t0);                         \
       _t0 = _t1;                                                                  \
@@ -111,14 +117,14 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
   const uint32_t tmem_base = *tmem_slot;
   const int taps = p.R * p.S;
   // contiguous tile range per CTA: consecutive tiles share the sample (=> the weights) and their halos hit L2
-  const bool rr = p.dbg & 1;
+  const bool rr = S1DBG & 1;
   const int tile_begin = rr ? (int)blockIdx.x : (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
   const int tile_end = rr ? p.total_tiles : (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
   const int tile_step = rr ? (int)gridDim.x : 1;
   // one lane polls an mbarrier on behalf of its warp (32x fewer smem polls / issue slots)
   auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
-    if (lane == 0 || (p.dbg & 2)) {
-      if (p.dbg & 256) mbar_spin(smem_u32(bar), parity); else mbar_wait(smem_u32(bar), parity);
+    if (lane == 0 || (S1DBG & 2)) {
+      if (S1DBG & 256) mbar_spin(smem_u32(bar), parity); else mbar_wait(smem_u32(bar), parity);
     }
     __syncwarp();
   };
@@ -183,9 +189,9 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
           int qq = q0 - p.D + lane_row;
           const float* src = xs + (ptrdiff_t)qq * p.C + c;
           const ptrdiff_t src_step = (ptrdiff_t)RS * p.C;
-          for (int rho = lane_row; rho < ra_iters && !(p.dbg & 4096); rho += RS) {
+          for (int rho = lane_row; rho < ra_iters && !(S1DBG & 4096); rho += RS) {
             const bool ok = cv && rho < p.RA && qq >= 0 && qq < p.Qs;
-            if (active && rho < p.RA && !(p.dbg & 64)) cp_async16(dst, ok ? src : p.x, ok ? 16u : 0u);
+            if (active && rho < p.RA && !(S1DBG & 64)) cp_async16(dst, ok ? src : p.x, ok ? 16u : 0u);
             dst += (uint32_t)RS * 16; qq += RS; src += src_step;
           }
         }
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
       const int r = t / p.S, s = t - r * p.S;
       const int shift = p.D + (r - p.ph) * p.Wp + (s - p.pw);       // slot row that output row 0 reads for this tap
       uint32_t a16 = (abase >> 4) + (uint32_t)shift, b16 = bblock >> 4;
-      for (int jj = 0; jj < ((p.dbg & 32) ? (t == 0 ? 1 : 0) : nk); ++jj) {
+      for (int jj = 0; jj < ((S1DBG & 32) ? (t == 0 ? 1 : 0) : nk); ++jj) {
         umma_mma_tf32_pred(tacc, adesc_hi | (uint64_t)(a16 & 0x3FFF), bdesc_hi | (uint64_t)(b16 & 0x3FFF), p.idesc, first ? 0u : 1u, leader);
         first = 0;
         a16 += a_k; b16 += b_k;
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
         const uint32_t abase = smem_u32(a_ring + (size_t)sa * a_bytes);
         if (p.b_res) {
           if (mine) {
-            if (!(p.dbg & 512)) fence_proxy_async();      // cp.async data (generic proxy) -> ordered before the async-proxy reads
+            if (!(S1DBG & 512)) fence_proxy_async();      // cp.async data (generic proxy) -> ordered before the async-proxy reads
             tc_fence_after();
             for (int t = 0; t < taps; ++t) issue_tap(tacc, abase, smem_u32(b_ring) + (uint32_t)(cb * taps + t) * bt_bytes, t, first);
             umma_commit_pred(smem_u32(&a_empty[sa]), leader);
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
       const size_t orow = ((size_t)z * p.Qs + (qv ? q : 0)) * p.N;
       float* optr = p.out + orow;
       float* sptr = out_stage + (size_t)buf * TM * p.N + (size_t)tid * p.N;      // this row inside the staging tile
-      const float* rptr = (p.residual && interior && !(p.dbg & 128)) ? p.residual + orow : nullptr;
+      const float* rptr = (p.residual && interior && !(S1DBG & 128)) ? p.residual + orow : nullptr;
       float4 rres[4], rnext[4];
       uint32_t v[16], vn[16];
       auto prefetch = [&](float4* dst, int cc) {
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
       tc_fence_after();
       PROF_ADD(1);
       const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.n_pad);
-      if (!(p.dbg & 2048)) tmem_ld16(tlane, v);
+      if (!(S1DBG & 2048)) tmem_ld16(tlane, v);
       if (bulk_out) {                                     // staging buffer `buf` must have been drained by its bulk store
         if (tid == 0) bulk_wait_read<1>();
         epi_sync();
@@ -350,14 +356,14 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
         const int c0 = cc * 16;
         tmem_ld_wait();                                   // chunk cc has landed in v
         if (cc + 1 < n_chunks) {
-          if (!(p.dbg & 2048)) tmem_ld16(tlane + (uint32_t)(c0 + 16), vn);
+          if (!(S1DBG & 2048)) tmem_ld16(tlane + (uint32_t)(c0 + 16), vn);
           prefetch(rnext, cc + 1);
         } else {                                          // accumulator fully read: release it to the MMA warp
           tc_fence_before();
           mbar_arrive(smem_u32(&acc_empty[as]));
         }
         PROF_ADD(2);
-        if (qv && !(p.dbg & 16)) {
+        if (qv && !(S1DBG & 16)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int col = c0 + 4 * i;
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS_S1, MIN_BLOCKS) umma_conv_s1_kernel(c
       if (bulk_out) {
         fence_proxy_async();                              // staged rows (generic proxy) -> visible to the bulk-copy engine
         epi_sync();
-        if (tid == 0 && !(p.dbg & 16)) {
+        if (tid == 0 && !(S1DBG & 16)) {
           const int rows = min(TM, p.Qs - q0);
           bulk_store_s2g(p.out + ((size_t)z * p.Qs + q0) * p.N, smem_u32(out_stage + (size_t)buf * TM * p.N), (uint32_t)(rows * p.N * 4));
           bulk_commit();
@@ -504,11 +510,11 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
   static bool attr_set = false;
   if (!attr_set) {
     QBN_CUDA(cudaFuncSetAttribute(umma_conv_s1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    QBN_CUDA(cudaFuncSetAttribute(umma_conv_s1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     attr_set = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
   if (occ > want_occ) occ = want_occ;
+  if (occ > 2) occ = 2;
   if (occ < 1) occ = 1;
   if (p.dbg & 8) occ = 1;
   int grid = qbn_sm_count() * occ;
@@ -517,8 +523,7 @@ extern "C" int qbn_conv_s1_fwd(int n_samples, int B, int Hp, int Wp, int C, int 
     unsigned long long z32[32] = {0};
     cudaMemcpyToSymbol(g_s1_prof, z32, sizeof(z32));
   }
-  if (occ >= 3) umma_conv_s1_kernel<3><<<grid, NTHREADS_S1, smem, st>>>(p);
-  else umma_conv_s1_kernel<2><<<grid, NTHREADS_S1, smem, st>>>(p);
+  umma_conv_s1_kernel<2><<<grid, NTHREADS_S1, smem, st>>>(p);  // a third resident CTA would need <= 75 registers (spills)
   QBN_CHECK_LAUNCH();
   if (p.dbg & 8192) {
     unsigned long long h[32];
