@@ -285,10 +285,16 @@ def int8_leg(torch, dist, dev, rank, world, steps, chunk):
     net, x, _ = mod.build_model(B)
     noise.manual_seed(20261017)
     eng = make_int8_engine(net, chunk=chunk)
-    start, count = qdist.shard_range(S, rank, world)
+    if getattr(eng, "supports_window", False):            # balanced (sample, image) units, like the headline
+        start, count, wf, we = qdist.shard_units(S, B, rank, world)
+        kw = {"window": (wf, we)}
+        count_eff = ((rank + 1) * S * B // world - rank * S * B // world) / B
+    else:
+        start, count = qdist.shard_range(S, rank, world)
+        kw, count_eff = {}, count
 
     def one(k):
-        psum = eng.predict_sum(x, count, sample0=start, draw_offset=k * S)
+        psum = eng.predict_sum(x, count, sample0=start, draw_offset=k * S, **kw)
         qdist.allreduce_prob_sums(psum)
         return psum
     for k in range(3):
@@ -306,7 +312,7 @@ def int8_leg(torch, dist, dev, rank, world, steps, chunk):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / steps
-    hbm = ACT_BYTES_PER_SAMPLE_IMAGE_U8 * B * count / (ms_step * 1e-3) / 1e9
+    hbm = ACT_BYTES_PER_SAMPLE_IMAGE_U8 * B * count_eff / (ms_step * 1e-3) / 1e9
     pk = _peaks()
     return {"metric": "resnet18_bbb_int8_mc_images_per_sec_S100", "value": B / (ms_step * 1e-3), "unit": "images/s", "ms_per_step": ms_step,
             "steps": steps, "scaling": "strong", "dtype": "u8 x s8 -> s32 (A7/W8), fp32 requantisation", "engine": type(eng).__name__,
@@ -365,7 +371,10 @@ def main():
     x_host = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(2)).pin_memory()
     t_host = torch.randint(0, K_CLASSES, (B,), generator=torch.Generator().manual_seed(3)).pin_memory()
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
-    start, count = qdist.shard_range(S, rank, world)
+    # balanced (sample, image) unit split: S=100 over 8 ranks = 12.5 samples each (dist.shard_units), whole samples when N | S
+    start, count, win_first, win_end = qdist.shard_units(S, B, rank, world)
+    units = (rank + 1) * S * B // world - rank * S * B // world
+    count_eff = units / B                       # samples' worth of work of this rank
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     metric = metrics.ClassificationMetric(K_CLASSES, device=dev)
     batch_no = [0]
@@ -376,16 +385,16 @@ def main():
             batch_no[0] += 1
         return batch_no[0] * S
 
+    predictor = qdist.ShardedMCPredictor(engine)
+
     def step_resident(fresh=True):
-        psum = engine.predict_sum(x_dev, count, sample0=start, draw_offset=next_offset(fresh))
-        qdist.allreduce_prob_sums(psum)
-        metric.update(psum, t_dev, scale=1.0 / S)
-        return psum
+        # the rank's samples on the launch stream; all-reduce + metric update on the predictor's side stream (they overlap the next step)
+        return predictor.predict_async(x_dev, S, then=lambda p_bar: metric.update(p_bar, t_dev), draw_offset=next_offset(fresh))[0]
 
     def step_e2e():
         xd = x_host.to(dev, non_blocking=True)
         td = t_host.to(dev, non_blocking=True)
-        psum = engine.predict_sum(xd, count, sample0=start, draw_offset=next_offset())
+        psum = predictor.local_sum(xd, S, rank, world, next_offset())
         qdist.allreduce_prob_sums(psum)
         metric.update(psum, td, scale=1.0 / S)
         probs = (psum / S).to("cpu", non_blocking=True)
@@ -398,14 +407,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, isolated=False):
+        """Device time of `steps` steps, max over ranks.  Default: ONE event bracket around the K steps (barrier + synchronize on both
+        sides), steps queued back to back as a loop over a data loader issues them; every step streams > 1 GB of activations per
+        rank, so nothing of the previous step survives in the 126 MB L2.  isolated=True: every step on an idle GPU with the L2
+        flushed first and a barrier + synchronize around it (a latency figure: it contains the host's launch path)."""
         ts = []
-        for _ in range(steps):
+        if isolated:
+            for _ in range(steps):
+                flush.fill_(1.0)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                predictor.wait_pending()
+                e1.record()
+                barrier()
+                ts.append(e0.elapsed_time(e1))
+        else:
             flush.fill_(1.0)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            for _ in range(steps):
+                fn()
+            predictor.wait_pending()
             e1.record()
             barrier()
             ts.append(e0.elapsed_time(e1))
@@ -428,6 +454,7 @@ def main():
     # the old regime for comparison: every step replays the SAME S draws
     n_replay = max(3, args.steps // 2)
     replay_ms = timed(lambda: step_resident(False), n_replay) / n_replay
+    isolated_ms = timed(step_resident, n_replay, isolated=True) / n_replay
     # ---- e2e: host buffers, H2D + D2H inside the timed region (wall clock around synchronous steps, max over ranks)
     for _ in range(2):
         step_e2e()
@@ -484,7 +511,7 @@ def main():
         flush.fill_(1.0)
         torch.cuda.synchronize()
         engine.use_graph = False                      # per-launch events need the eager launch sequence (the timed loop replays a CUDA graph)
-        engine.predict_sum(x_dev, count, sample0=start)
+        engine.predict_sum(x_dev, count, sample0=start, window=(win_first, win_end))
         engine.use_graph = True
         torch.cuda.synchronize()
         mc.ops.conv_forward, mc.ops.conv_p4_forward, mc.ops.conv_p4_shortcut_forward = orig, orig_p4, orig_p4sc
@@ -492,14 +519,14 @@ def main():
         n_p4 = sum(1 for e in evs if e[3] == 2)
         if um:
             t_ms = sum(t for t, _ in um)
-            fl = sum(f for _, f in um)
+            fl = sum(f for _, f in um) * (count_eff / count)      # the unit window skips the tiles of the other rank's images
             ach = fl / (t_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"] / 2.0
-            alg_bytes = ACT_BYTES_PER_SAMPLE_IMAGE * B * count
+            alg_bytes = ACT_BYTES_PER_SAMPLE_IMAGE * B * count_eff
             # with fp32 activations the eval path's arithmetic intensity (81 flop/B) is below the TF32 ridge
             # (~105 flop/B at the measured peaks), so HBM is the binding roofline; the tensor-pipe view is reported beside it.
             hbm = alg_bytes / (t_ms * 1e-3) / 1e9
-            traffic, traffic_source = measured_traffic(count, args.chunk_max or args.chunk, len(um))
+            traffic, traffic_source = measured_traffic(count if count_eff == count else -1, args.chunk_max or args.chunk, len(um))
             roof = {"kernel": "umma_conv_p4_kernel (%d launches) + umma_conv_kernel<EVAL> (%d) — tcgen05 kind::tf32" % (n_p4, len(um) - n_p4),
                     "bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
                     "traffic": traffic,
@@ -539,16 +566,22 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B, "samples": S,
-                       "parallelism": "mc-sample sharding x%d" % world, "chunk": args.chunk,
+                       "parallelism": "mc-sample sharding x%d (balanced (sample, image) units: %.1f samples per rank)" % (world, S / world), "chunk": args.chunk,
                        "noise": "fresh draws every step (device-side draw offset, %d captured graph%s for all steps)" % (n_graphs, "" if n_graphs == 1 else "s"),
-                       "l2": "256 MB flush between timed steps; per-layer activations (S x 25 MB) exceed the 126 MB L2"},
+                       "l2": "inputs larger than L2: every step streams > 1 GB of activations per rank (S/N x 25 MB per 24-channel layer) through the "
+                             "126 MB L2; flushed once before the timed region",
+                       "timing": "K steps in one CUDA-event bracket on the launch stream (barrier + synchronize on both sides, max over ranks); "
+                                 "the all-reduce and the metric update of step k run on a side stream under step k+1"},
             "sample_images_per_sec": value * S,
             "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8,
                     "d2h_bytes_per_step": B * K_CLASSES * 4 + n_state * 4},
+            "isolated_step": {"ms_per_step": isolated_ms, "value": B / (isolated_ms * 1e-3), "unit": "images/s",
+                              "note": "every step alone on an idle GPU: L2 flushed, barrier + synchronize around each step (the round-1/early "
+                                      "round-2 way of timing; contains the host launch path and the exposed all-reduce)"},
             "replay_same_noise": {"value": B / (replay_ms * 1e-3), "unit": "images/s", "ms_per_step": replay_ms,
                                   "note": "every step replays the same S draws (round-1 regime); fresh/replay step time = %.3f" % ((total_ms / args.steps) / replay_ms)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-            "tensor_bound_frac_whole_step": (FLOP_PER_SAMPLE_IMAGE * B * S * args.steps / (total_ms * 1e-3) / 1e12) / (_peaks()["bf16_tflops_sustained"] / 2.0),
+            "tensor_bound_frac_whole_step": (FLOP_PER_SAMPLE_IMAGE * B * S * args.steps / (total_ms * 1e-3) / 1e12) / (world * _peaks()["bf16_tflops_sustained"] / 2.0),   # per GPU
             "metrics_check": m,
         }
         if train is not None:

@@ -397,6 +397,15 @@ int qbn_lrt_wgrad_p4(int B, int Hp, int Wp, int C_real, int N, int R, int S, int
  * touches global memory only after that kernel has completed (griddepcontrol.wait).  Process-wide, off by default. */
 int qbn_set_pdl(int enabled);
 
+/* Unit window of the sample-sharded evaluation (qbn_b200.dist.shard_units; SURVEY 8e-i: MC samples partitioned over the GPUs):
+ * a rank's share is a contiguous range of (sample, image) units, so of the n_samples samples of a chunk the FIRST may only need
+ * images [first_img, B) and the LAST only [0, end_img).  While a window is set, the qbn_conv_p4_fwd / qbn_conv_p4_shortcut_fwd /
+ * qbn_i8_conv_p16_fwd launches over exactly n_samples samples cover the tiles of those rows only (rows outside keep their previous
+ * contents; the caller masks them: qbn_softmax_accumulate_window).  end_img 0 = the whole batch; n_samples 0 switches the window
+ * off.  Launches over another sample count (a fixed-weight layer on the shared input), launches with the samples stacked along N
+ * (shared-input first layer) and the LRT kinds ignore it.  Process-wide and sticky like qbn_set_pdl. */
+int qbn_p4_set_window(int first_img, int end_img, int n_samples);
+
 /* int8 MC-Dropout (dropout.py:31-39) of a chunk of Monte-Carlo samples on planar-C16 maps, optionally followed by the BasicBlock's
  * quantized::add[_relu] with `residual` (models_mc.py:143-157: the dropout sits between the second conv and the add).  Same integers
  * as qbn_i8_dropout_mc + qbn_i8_add.  x holds q - z_x at scale s_x (x_shared: B images shared by all samples); mask fp32 {0,1}
@@ -419,6 +428,10 @@ int qbn_set_sample_base(const uint32_t* base_dev);
  * accumulate==0 overwrites.  The caller divides by the GLOBAL S after the allreduce.           */
 int qbn_softmax_accumulate(const float* logits, int n_samples, int B, int K, float* psum,
                            int accumulate, void* stream);
+/* the same with the unit window of the sample-sharded evaluation (qbn_b200.dist.shard_units): sample 0 contributes images
+ * [first_img, B) only, sample n_samples - 1 images [0, end_img) only */
+int qbn_softmax_accumulate_window(const float* logits, int n_samples, int B, int K, int first_img, int end_img, float* psum,
+                                  int accumulate, void* stream);
 /* probs [n_samples][B][K] -> mean over samples (stack(...).mean(dim=1)) */
 int qbn_mc_mean(const float* probs, int n_samples, int64_t BK, float* mean, void* stream);
 /* regression (experiments/utils.py:349-353): mean_s mu, Var_s(mu) (unbiased) + mean_s var */

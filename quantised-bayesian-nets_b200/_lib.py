@@ -98,8 +98,10 @@ _SIGNATURES = {
                                    ctypes.c_longlong, POINTER(I8Requant), P, ctypes.c_longlong, P]),
     "qbn_set_sample_base": (c_int, [P]),
     "qbn_set_pdl": (c_int, [c_int]),
+    "qbn_p4_set_window": (c_int, [c_int, c_int, c_int]),
     "qbn_sghmc_step": (c_int, [P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_int, P, P, c_uint64, c_uint32, c_uint32, P]),
     "qbn_softmax_accumulate": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
+    "qbn_softmax_accumulate_window": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P]),
     "qbn_mc_mean": (c_int, [P, c_int, c_int64, P, P]),
     "qbn_reg_mc_reduce": (c_int, [P, P, c_int, c_int64, P, P, P]),
     "qbn_elbo_cls": (c_int, [P, P, P, c_int, c_int, c_float, c_float, c_float, P, P, P]),

@@ -10,13 +10,14 @@ namespace {
 
 // one block (8 warps) per image; warps stride over samples, lanes over classes
 __global__ void softmax_accumulate_kernel(const float* __restrict__ logits, int S, int B, int K, float* __restrict__ psum,
-                                          int accumulate) {
+                                          int accumulate, int b_first, int b_end) {
   extern __shared__ float sh[];  // [8][K]
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int per = (K + 31) / 32;  // classes per lane (K <= 128)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int s = wid; s < S; s += nw) {
+    if ((s == 0 && b < b_first) || (s == S - 1 && b >= b_end)) continue;   // unit window: warp-uniform
     const float* row = logits + ((int64_t)s * B + b) * K;
     float v[4];
     float mx = -INFINITY;
@@ -170,7 +171,7 @@ __global__ void reg_metrics_kernel(const float* __restrict__ mean, const float* 
 // consecutive images, i.e. contiguous rows — and the sample groups are reduced through shared memory in a fixed order.
 template <int SG>
 __global__ void softmax_accumulate_smallk_kernel(const float* __restrict__ logits, int S, int B, int K, float* __restrict__ psum,
-                                                 int accumulate) {
+                                                 int accumulate, int b_first, int b_end) {
   __shared__ float sh[SG][32][17];
   const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + lane;
@@ -179,6 +180,7 @@ __global__ void softmax_accumulate_smallk_kernel(const float* __restrict__ logit
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
   if (b < B) {
     for (int s = sg; s < S; s += SG) {
+      if ((s == 0 && b < b_first) || (s == S - 1 && b >= b_end)) continue;   // unit window (dist.shard_units)
       const float* row = logits + ((int64_t)s * B + b) * K;
       float v[16];
       float mx = -INFINITY;
@@ -213,17 +215,25 @@ __global__ void softmax_accumulate_smallk_kernel(const float* __restrict__ logit
   }
 }
 
-extern "C" int qbn_softmax_accumulate(const float* logits, int n_samples, int B, int K, float* psum, int accumulate, void* stream) {
+// first_img / end_img: the unit window of the sample-sharded evaluation — sample 0 contributes images [first_img, B) only, sample
+// n_samples - 1 images [0, end_img) only (dist.shard_units)
+extern "C" int qbn_softmax_accumulate_window(const float* logits, int n_samples, int B, int K, int first_img, int end_img, float* psum,
+                                             int accumulate, void* stream) {
   QBN_CHECK_ARG(logits && psum, "null pointer");
   QBN_CHECK_ARG(n_samples > 0 && B > 0 && K > 0 && K <= 128, "S,B > 0 and 0 < K <= 128");
+  QBN_CHECK_ARG(first_img >= 0 && first_img < B && end_img > 0 && end_img <= B, "unit window outside the batch");
   if (K <= 16) {
-    softmax_accumulate_smallk_kernel<8><<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(logits, n_samples, B, K, psum, accumulate);
+    softmax_accumulate_smallk_kernel<8><<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(logits, n_samples, B, K, psum, accumulate, first_img, end_img);
     QBN_CHECK_LAUNCH();
     return QBN_OK;
   }
-  softmax_accumulate_kernel<<<B, 256, 8 * K * sizeof(float), (cudaStream_t)stream>>>(logits, n_samples, B, K, psum, accumulate);
+  softmax_accumulate_kernel<<<B, 256, 8 * K * sizeof(float), (cudaStream_t)stream>>>(logits, n_samples, B, K, psum, accumulate, first_img, end_img);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
+}
+
+extern "C" int qbn_softmax_accumulate(const float* logits, int n_samples, int B, int K, float* psum, int accumulate, void* stream) {
+  return qbn_softmax_accumulate_window(logits, n_samples, B, K, 0, B, psum, accumulate, stream);
 }
 
 extern "C" int qbn_mc_mean(const float* probs, int n_samples, int64_t BK, float* mean, void* stream) {

@@ -48,6 +48,7 @@ struct P4Params {
   uint32_t idesc, mg_plane, mg_wp;
   long long x_plane, strip_rows, out_plane, res_plane, w_sample_floats;
   int out_split, Hp2, Wp2;
+  int tile0;                      // first tile of the launch's window (qbn_p4_set_window; 0 = the whole tile space)
   int tile_rr;                    // tiles dealt round-robin over the CTAs (streamed weights) instead of in contiguous ranges
   int stacked, n_chunks, cps;     // stacked: the N columns are `n_chunks / cps` samples x cps channel chunks (shared input)
   long long q2_total;
@@ -213,8 +214,8 @@ __global__ void __launch_bounds__(P4_THREADS, KIND == KIND_I8 ? 4 : (KIND == KIN
   // grid works on the tiles of ~2-3 samples — the weight blocks every CTA streams per tile then come from L2 (one DRAM read per
   // block instead of one per CTA group; ncu, profiles/r02_p4_dram_traffic.json: 0.6-1.0 GB of re-reads per layer-4 launch before).
   const int tile_step = p.tile_rr ? (int)gridDim.x : 1;
-  const int tile_begin = p.tile_rr ? (int)blockIdx.x : (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
-  const int tile_end = p.tile_rr ? p.total_tiles : (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int tile_begin = p.tile0 + (p.tile_rr ? (int)blockIdx.x : (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x));
+  const int tile_end = p.tile0 + (p.tile_rr ? p.total_tiles : (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x));
 
   if (warp == 5) {
     // ======================================= PRODUCER (one lane) ================================
@@ -723,6 +724,19 @@ extern "C" int qbn_set_pdl(int enabled) {
   g_p4_pdl = enabled ? 1 : 0;
   return QBN_OK;
 }
+// Unit window of the sample-sharded evaluation (dist.shard_units): of the `n_samples` samples of the following launches the FIRST
+// only needs images [first_img, B), the LAST only [0, end_img) — a launch over that many samples then covers the tiles of exactly
+// those rows (plus the top border of image end_img, which is the bottom padding of image end_img - 1).  Launches over another
+// sample count (a fixed-weight layer on the shared input runs once for all samples), launches with the samples stacked along N
+// (the shared-input first layer) and the LRT kinds ignore it.  n_samples 0 switches it off.  Sticky like qbn_set_pdl.
+static int g_p4_win_first = 0, g_p4_win_end = 0, g_p4_win_n = 0;
+extern "C" int qbn_p4_set_window(int first_img, int end_img, int n_samples) {
+  QBN_CHECK_ARG(first_img >= 0 && end_img >= 0 && n_samples >= 0, "window");
+  g_p4_win_first = first_img;
+  g_p4_win_end = end_img;
+  g_p4_win_n = n_samples;
+  return QBN_OK;
+}
 template <typename K>
 static cudaError_t p4_launch(K kernel, int grid, size_t smem, cudaStream_t st, const P4Params& p) {
   cudaLaunchConfig_t cfg;
@@ -854,6 +868,16 @@ static int conv_p4_launch(int n_samples, int B, int Hp, int Wp, int C, int N, in
   p.Qs = B * Hp * Wp;
   p.tiles_per_sample = (p.Qs + TM - 1) / TM;
   p.total_tiles = p.tiles_per_sample * (stacked ? 1 : n_samples);
+  p.tile0 = 0;
+  if (g_p4_win_n > 0 && g_p4_win_n == n_samples && (g_p4_win_first > 0 || g_p4_win_end > 0) && !stacked && !lrt) {
+    const long long map_rows = (long long)Hp * Wp;
+    const int first = g_p4_win_first, end = g_p4_win_end > 0 ? g_p4_win_end : B;
+    QBN_CHECK_ARG(first < B && end <= B && (n_samples > 1 || first < end), "unit window outside the batch");
+    long long q_end = end * map_rows + (end < B ? (long long)p.bh * Wp + p.bw : 0);
+    if (q_end > p.Qs) q_end = p.Qs;
+    p.tile0 = (int)(first * map_rows / TM);
+    p.total_tiles = (n_samples - 1) * p.tiles_per_sample + (int)((q_end + TM - 1) / TM) - p.tile0;
+  }
   p.n_pad = i8 ? qbn_p16_n_pad(N) : qbn_p4_n_pad(stacked ? n_samples * N : N);
   p.n_cb = C / CB;
   p.cbc = CB / E;

@@ -633,11 +633,9 @@ class MCEngine:
                 info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"), 8)
                 N, C, R, S_ = info["wshape"]
                 if "x_p4" not in self._call:
-                    xn = src.permute(0, 1, 2, 3) if src.dim() == 4 else src
-                    xp = torch.nn.functional.pad(xn.contiguous(), (0, 0, 0, 0, 0, C - xn.shape[1]))
-                    xi = xp.contiguous().view(torch.int32)
-                    xp = ((xi + 0x1000) & ~0x1FFF).view(torch.float32)      # RNA to TF32 (the tensor core would truncate)
-                    self._call["x_p4"] = ops.P4Map.from_nchw(xp, (1, 1))
+                    # one launch: channel padding, RNA rounding to TF32 (the tensor core would truncate), planar layout with its borders
+                    self._call["x_p4"] = ops.p4_stage_input(src, C, (1, 1))
+                    self.launches += 1
                 xm = self._call["x_p4"]
                 outp = self._p4_buffer(("p4first", si), n * xm.n_img, N, xm.Hp, xm.Wp, (1, 1), 1, src.device, zero=False)
                 e = prep[id(st)]
@@ -810,9 +808,12 @@ class MCEngine:
         return out
 
     @torch.no_grad()
-    def predict_sum(self, x, samples, sample0=0, injected=None, draw_offset=None):
+    def predict_sum(self, x, samples, sample0=0, injected=None, draw_offset=None, window=None):
         """Sum over samples [sample0, sample0+samples) of softmax(logits) -> [B,K] (classification) or
         (sum mu, sum mu^2, sum var) building blocks (regression: returns stacked [S,B] mu and var).
+
+        window = (first_img, end_img) (classification; dist.shard_units): the first sample contributes images [first_img, B)
+        only and the last images [0, end_img) only — the planar conv launches skip the tiles of the other rows.
 
         With use_graph (classification, Philox noise) the ~45 launches per chunk of a call are captured once per
         (input shape, sample range, seed) into a CUDA graph and replayed: the step is launch-bound otherwise."""
@@ -820,14 +821,22 @@ class MCEngine:
             raise RuntimeError("MCEngine needs CUDA tensors (no CPU fallback)")
         if draw_offset is not None:     # fresh noise for this batch: global sample indices draw_offset + sample0 + s (noise.set_draw_offset)
             noise.set_draw_offset(draw_offset, x.device)
+        if window is not None:
+            window = (int(window[0]), int(window[1]))
+            if window == (0, x.shape[0]):
+                window = None
+            elif self.regression or not (0 <= window[0] < x.shape[0] and 0 < window[1] <= x.shape[0] and (samples > 1 or window[0] < window[1])):
+                raise ValueError("unit window %r outside a batch of %d images (classification only)" % (window, x.shape[0]))
         if self.use_graph and injected is None and not self.regression:
-            return self._predict_sum_graph(x, samples, sample0)
-        return self._predict_sum_eager(x, samples, sample0, injected)
+            return self._predict_sum_graph(x, samples, sample0, window)
+        return self._predict_sum_eager(x, samples, sample0, injected, window)
 
-    def _predict_sum_graph(self, x, samples, sample0):
+    supports_window = True
+
+    def _predict_sum_graph(self, x, samples, sample0, window=None):
         self._get_prep(x.device)        # a parameter update since the capture invalidates the graphs (they replay prepared operands)
         noise.draw_base(x.device)       # the captured samplers read the per-batch draw offset from this device scalar
-        key = (tuple(x.shape), x.dtype, int(samples), int(sample0), noise.seed(), x.device.index)
+        key = (tuple(x.shape), x.dtype, int(samples), int(sample0), noise.seed(), x.device.index, window)
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)
         if ent is None:
@@ -836,7 +845,7 @@ class MCEngine:
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):                      # warm-up: allocates the cached buffers, sets kernel attributes
-                self._predict_sum_eager(static_x, samples, sample0, None)
+                self._predict_sum_eager(static_x, samples, sample0, None, window)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             l0 = self.launches
@@ -844,7 +853,7 @@ class MCEngine:
             _lib.call("qbn_set_pdl", int(config.pdl()))      # programmatic dependent launches between the captured convs
             try:
                 with torch.cuda.graph(g):
-                    static_out = self._predict_sum_eager(static_x, samples, sample0, None)
+                    static_out = self._predict_sum_eager(static_x, samples, sample0, None, window)
             finally:
                 _lib.call("qbn_set_pdl", 0)
             ent = (g, static_x, static_out, self.launches - l0)
@@ -858,7 +867,7 @@ class MCEngine:
         self.launches += n_launch
         return static_out.clone()
 
-    def _predict_sum_eager(self, x, samples, sample0=0, injected=None):
+    def _predict_sum_eager(self, x, samples, sample0=0, injected=None, window=None):
         x = ops.nhwc(x.float()) if x.dim() == 4 else x.float().contiguous().reshape(x.shape[0], -1, 1, 1)
         prep = self._get_prep(x.device)
         self._call = {}                 # per-call (input-dependent) cache, e.g. the planar copy of the input batch
@@ -870,14 +879,27 @@ class MCEngine:
         # sample-stacked launch is split into groups of <= 256 / N samples inside a chunk
         n_chunks = (samples + self.chunk_max - 1) // self.chunk_max
         sizes = [samples // n_chunks + (1 if i < samples % n_chunks else 0) for i in range(n_chunks)]
-        for n in sizes:
+        nB = x.shape[0]
+        for ci, n in enumerate(sizes):
             inj = injected[done:done + n] if injected is not None else None
-            out = self._run_chunk(x, n, sample0 + done, prep, inj)
+            # the call's unit window restricts the first sample of the first chunk and the last sample of the last chunk
+            win = None
+            if window is not None:
+                win = (window[0] if ci == 0 else 0, window[1] if ci == len(sizes) - 1 else nB)
+                if win == (0, nB):
+                    win = None
+            if win is not None:
+                _lib.call("qbn_p4_set_window", win[0], win[1] if win[1] < nB else 0, n)
+            try:
+                out = self._run_chunk(x, n, sample0 + done, prep, inj)
+            finally:
+                if win is not None:
+                    _lib.call("qbn_p4_set_window", 0, 0, 0)
             if self.regression:
                 mus.append(out[0].clone())      # the step buffers are reused by the next chunk
                 lvs.append(out[1].clone())
             else:
-                psum = ops.softmax_accumulate(out.contiguous(), psum)
+                psum = ops.softmax_accumulate(out.contiguous(), psum, win)
                 self.launches += 1
             done += n
         if self.regression:

@@ -353,22 +353,45 @@ class Int8PlanarEngine:
             self.trace["head"] = (y.q.clone(), y.scale, y.zero_point)
         return y.dequantize().reshape(n, B, -1)
 
-    def _predict_sum_eager(self, x, samples, sample0, injected=None):
+    supports_window = True
+
+    def _predict_sum_eager(self, x, samples, sample0, injected=None, window=None):
         psum, done = None, 0
-        for n in balanced_chunks(int(samples), self.chunk):
-            logits = self._run_chunk(x, n, sample0 + done, injected[done:done + n] if injected is not None else None)
-            psum = ops.softmax_accumulate(logits.contiguous(), psum)
+        sizes = balanced_chunks(int(samples), self.chunk)
+        nB = x.shape[0]
+        for ci, n in enumerate(sizes):
+            # the call's unit window (dist.shard_units) restricts the first sample of the first chunk and the last of the last chunk
+            win = None
+            if window is not None:
+                win = (window[0] if ci == 0 else 0, window[1] if ci == len(sizes) - 1 else nB)
+                if win == (0, nB):
+                    win = None
+            if win is not None:
+                _lib.call("qbn_p4_set_window", win[0], win[1] if win[1] < nB else 0, n)
+            try:
+                logits = self._run_chunk(x, n, sample0 + done, injected[done:done + n] if injected is not None else None)
+            finally:
+                if win is not None:
+                    _lib.call("qbn_p4_set_window", 0, 0, 0)
+            psum = ops.softmax_accumulate(logits.contiguous(), psum, win)
             self.launches += 1
             done += n
         return psum
 
     @torch.no_grad()
-    def predict_sum(self, x, samples, sample0=0, seed=None, injected=None, draw_offset=None):
+    def predict_sum(self, x, samples, sample0=0, seed=None, injected=None, draw_offset=None, window=None):
         """sum over `samples` MC samples (global indices sample0..) of the class probabilities: [B, K] fp32.
         draw_offset: first global sample index of this batch's draws (fresh noise per batch from the one captured graph).
-        injected: per sample, the list of eps tensors of every Bayesian layer in the reference's draw order (parity tests)."""
+        injected: per sample, the list of eps tensors of every Bayesian layer in the reference's draw order (parity tests).
+        window = (first_img, end_img): the first sample contributes images [first_img, B) only, the last [0, end_img) only."""
         if not x.is_cuda:
             raise RuntimeError("Int8PlanarEngine runs on CUDA tensors only (no CPU fallback)")
+        if window is not None:
+            window = (int(window[0]), int(window[1]))
+            if window == (0, x.shape[0]):
+                window = None
+            elif not (0 <= window[0] < x.shape[0] and 0 < window[1] <= x.shape[0] and (samples > 1 or window[0] < window[1])):
+                raise ValueError("unit window %r outside a batch of %d images" % (window, x.shape[0]))
         if seed is not None:
             noise.manual_seed(seed)
         noise.draw_base(x.device)
@@ -376,8 +399,8 @@ class Int8PlanarEngine:
             noise.set_draw_offset(draw_offset, x.device)
         x = x.float()
         if not self.use_graph or injected is not None or self.trace is not None:
-            return self._predict_sum_eager(x, samples, sample0, injected)
-        key = (tuple(x.shape), int(samples), int(sample0), noise.seed(), x.device.index)
+            return self._predict_sum_eager(x, samples, sample0, injected, window)
+        key = (tuple(x.shape), int(samples), int(sample0), noise.seed(), x.device.index, window)
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)
         if ent is None:
@@ -385,7 +408,7 @@ class Int8PlanarEngine:
             cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):                        # warm-up: allocates the cached buffers, sets kernel attributes
-                self._predict_sum_eager(static_x, samples, sample0)
+                self._predict_sum_eager(static_x, samples, sample0, None, window)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             l0 = self.launches
@@ -393,7 +416,7 @@ class Int8PlanarEngine:
             _lib.call("qbn_set_pdl", int(config.pdl()))      # programmatic dependent launches between the captured convs
             try:
                 with torch.cuda.graph(g):
-                    static_out = self._predict_sum_eager(static_x, samples, sample0)
+                    static_out = self._predict_sum_eager(static_x, samples, sample0, None, window)
             finally:
                 _lib.call("qbn_set_pdl", 0)
             ent = (g, static_x, static_out, self.launches - l0)

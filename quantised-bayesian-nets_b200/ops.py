@@ -675,13 +675,15 @@ def i8_dropout_batched(x_q, s_x, z_x, p, s_m, z_m, n_samples, key, act_bits=8):
 # ------------------------------------------------------------------------------------------------
 # A9 / A10
 # ------------------------------------------------------------------------------------------------
-def softmax_accumulate(logits, psum=None):
-    """logits [S,B,K] -> psum [B,K] (+)= sum_s softmax(logits_s)."""
+def softmax_accumulate(logits, psum=None, window=None):
+    """logits [S,B,K] -> psum [B,K] (+)= sum_s softmax(logits_s).  window = (first_img, end_img): sample 0 contributes images
+    [first_img, B) only and sample S-1 images [0, end_img) only (the unit window of dist.shard_units)."""
     S, B, K = logits.shape
     acc = psum is not None
     if psum is None:
         psum = torch.empty((B, K), dtype=torch.float32, device=logits.device)
-    _lib.call("qbn_softmax_accumulate", _ptr(logits.contiguous()), S, B, K, _ptr(psum), int(acc), _stream())
+    first, end = window if window is not None else (0, B)
+    _lib.call("qbn_softmax_accumulate_window", _ptr(logits.contiguous()), S, B, K, int(first), int(end), _ptr(psum), int(acc), _stream())
     return psum
 
 
@@ -829,6 +831,24 @@ class P4Map:
 
     def tail(self):
         return self.buf[:, self.phases * self.n_img * self.Hp * self.Wp:]
+
+
+def p4_stage_input(x, C_pad, border, phase_split=False):
+    """x [n_img, C, H, W] in channels_last memory -> planar-C4 map of tf32(x) with the channels zero-padded to C_pad: borders and
+    tail written by the same launch (qbn_p4_stage_input; the entry of the evaluation engines)."""
+    n, C, H, W = x.shape
+    xh = x.permute(0, 2, 3, 1)
+    if not (xh.is_contiguous() and x.dtype == torch.float32):
+        xh = xh.float().contiguous()
+    if phase_split:
+        border = (1, 1)
+        Hp, Wp, phases = H // 2 + 1, W // 2 + 1, 4
+    else:
+        Hp, Wp, phases = H + border[0], W + border[1], 1
+    rows = phases * n * Hp * Wp + P4Map.tail_rows(Hp, Wp, border)
+    buf = torch.empty((C_pad // 4, rows, 4), dtype=torch.float32, device=x.device)
+    _lib.call("qbn_p4_stage_input", _ptr(xh), n, H, W, C, C_pad, border[0], border[1], int(phase_split), rows, _ptr(buf), None, _stream())
+    return P4Map(buf, n, C_pad, Hp, Wp, tuple(border), phases)
 
 
 def p4_weight_floats(C, N, R, S, stride=1):

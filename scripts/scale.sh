@@ -17,7 +17,3 @@ except Exception as e:
     print("N=$n failed", e)
 PY
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-train --no-int8 --pdl 1 2>gpurun_out/scale_n8_pdl.err | tail -1 > gpurun_out/scale_n8_pdl.json
-python -c "
-import json
-d = json.loads(open('gpurun_out/scale_n8_pdl.json').read()); print('N=8 pdl=1 value %.0f' % d['value'])"

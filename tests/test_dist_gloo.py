@@ -65,7 +65,23 @@ def _worker(rank, world, port, ret):
     ok5 = torch.allclose(m2, mu.mean(0), atol=1e-5) and torch.allclose(v2, mu.var(0) + var.mean(0), atol=1e-4)
     m3, v3 = qd.ShardedMCPredictor(_Reg()).predict(xb, 1)                                             # S=1 on 2 ranks: var of one draw = 0
     ok5 = ok5 and torch.allclose(m3, mu[0], atol=1e-6)
-    ret[rank] = bool(ok1 and ok2 and ok3 and ok4 and ok5)
+    # an engine that takes a unit window (MCEngine.supports_window): the balanced (sample, image) split of shard_units —
+    # S=11 samples x 6 images over 2 ranks = 5.5 samples each; rank 0's last sample and rank 1's first are the same one
+    class _Win:
+        regression, n_classes, model, supports_window = False, K, None, True
+        seen = []
+
+        def predict_sum(self, x, count, sample0=0, window=None):
+            first, end = window if window is not None else (0, B)
+            self.seen.append((sample0, count, first, end))
+            mask = torch.ones(count, B, 1)
+            mask[0, :first] = 0
+            mask[count - 1, end:] = 0
+            return (probs[sample0:sample0 + count] * mask).sum(0)
+    w = _Win()
+    ok6 = torch.allclose(qd.ShardedMCPredictor(w).predict(xb, S), probs.mean(0), atol=1e-6)
+    ok6 = ok6 and w.seen[-1] == ((0, 6, 0, 3) if rank == 0 else (5, 6, 3, 6))
+    ret[rank] = bool(ok1 and ok2 and ok3 and ok4 and ok5 and ok6)
     dist.destroy_process_group()
 
 
@@ -78,6 +94,27 @@ def test_shard_range_partitions():
             assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
     assert shard_range(100, 0, 8) == (0, 13) and shard_range(100, 7, 8) == (88, 12)     # ideal speed-up 100/13 = 7.69x
+
+
+def test_shard_units_partitions():
+    """Every (sample, image) unit belongs to exactly one rank; the ranks' unit counts differ by at most one; with world | samples the
+    split is shard_range's."""
+    from qbn_b200.dist import shard_range, shard_units
+    for S, B, W in ((100, 256, 8), (100, 256, 3), (5, 7, 8), (1, 4, 3), (3, 2, 16), (12, 5, 4)):
+        seen, sizes = set(), []
+        for r in range(W):
+            s0, n, first, end = shard_units(S, B, r, W)
+            mine = 0
+            for i in range(n):
+                for im in range(first if i == 0 else 0, end if i == n - 1 else B):
+                    assert (s0 + i, im) not in seen
+                    seen.add((s0 + i, im))
+                    mine += 1
+            sizes.append(mine)
+        assert len(seen) == S * B and max(sizes) - min(sizes) <= 1
+        if S % W == 0:
+            assert all(shard_units(S, B, r, W) == (*shard_range(S, r, W), 0, B) for r in range(W))
+    assert shard_units(100, 256, 0, 8) == (0, 13, 0, 128) and shard_units(100, 256, 1, 8) == (12, 13, 128, 256)   # 12.5 samples each
 
 
 def test_world2_gloo():

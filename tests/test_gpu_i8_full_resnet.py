@@ -133,3 +133,13 @@ def test_planar_engine_equals_the_module_driven_engine_with_philox_noise(golden_
     np.testing.assert_allclose(other.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=2e-6)
     p = fast.predict(x, 4)
     np.testing.assert_allclose(p.sum(-1).cpu().numpy(), np.ones(8), atol=1e-5)
+    # unit-window sharding (dist.shard_units): 5 samples x 8 images over 4 and 16 emulated ranks add up to the unsharded sum
+    from qbn_b200.dist import shard_units
+    full = fast.predict_sum(x, 5, sample0=0)
+    for world in (4, 16):
+        tot = torch.zeros_like(full)
+        for r in range(world):
+            s0, n, first, end = shard_units(5, 8, r, world)
+            if n:
+                tot += fast.predict_sum(x, n, sample0=s0, window=(first, end))
+        np.testing.assert_allclose(tot.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=2e-6)

@@ -104,6 +104,41 @@ def test_resnet_engine_philox_sharding_invariance():
     assert not torch.allclose(a, c)
 
 
+@pytest.mark.parametrize("world,chunk,graph", [(8, 6, True), (3, 2, False), (5, 6, False), (16, 6, True)])
+def test_resnet_engine_unit_window_sharding(world, chunk, graph):
+    """dist.shard_units: the (sample, image) units of S=5 samples x B=12 images split over `world` emulated ranks — every rank's
+    windowed pass (planar launches restricted to its tile range, masked accumulation) — add up to the unsharded sum, whatever the
+    buffers held before (a full pass with another seed runs first on the same engine)."""
+    from qbn_b200 import dist as qdist
+    from qbn_b200 import mc, noise, synthetic, zoo
+    net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    x = torch.randn(12, 3, 32, 32, generator=torch.Generator().manual_seed(11)).cuda()
+    S = 5
+    noise.manual_seed(77)
+    full = mc.MCEngine(net, math_mode="tf32", chunk=6, use_graph=False).predict_sum(x, S)
+    eng = mc.MCEngine(net, math_mode="tf32", chunk=chunk, use_graph=graph)
+    assert eng.supports_window
+    noise.manual_seed(5)
+    eng.predict_sum(x, S)                                   # leaves other values in every cached activation buffer
+    noise.manual_seed(77)
+    tot = torch.zeros_like(full)
+    units = 0
+    for r in range(world):
+        s0, n, first, end = qdist.shard_units(S, x.shape[0], r, world)
+        if n == 0:
+            continue
+        part = eng.predict_sum(x, n, sample0=s0, window=(first, end))
+        # the rank's probability mass = its number of units
+        mine = n * x.shape[0] - first - (x.shape[0] - end)
+        assert abs(float(part.sum()) - mine) < 1e-3 * max(mine, 1)
+        units += mine
+        tot += part
+    assert units == S * x.shape[0]
+    close(tot, full, 1e-5, 1e-6)
+    with pytest.raises(ValueError):
+        eng.predict_sum(x, 1, window=(7, 3))
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", 1.0), ("tf32", 20.0)])
 def test_resnet_lrt_training_step(golden, mode, tol):
     """trainer.py:95-104 on the drop-in model: LRT forward, KL, ELBO, backward; BN in batch-stat mode.

@@ -88,6 +88,14 @@ def test_mc_dropout_resnet_int8_matches_the_reference_on_fbgemm():
     assert torch.equal(pe.predict_sum(x.cuda(), S), got_planar)          # graph replay
     one = Int8PlanarEngine(mine, chunk=1, use_graph=False).predict_sum(x.cuda(), S)      # chunking does not change the draws
     np.testing.assert_allclose(one.cpu().numpy(), got_planar.cpu().numpy(), rtol=0, atol=2e-6)
+    # unit-window sharding (dist.shard_units) over 3 emulated ranks: the fixed-weight first conv on the shared input runs for the
+    # whole batch (a launch over one sample is outside the window of a 2-sample chunk), the rest only on the rank's rows
+    from qbn_b200.dist import shard_units
+    tot = torch.zeros_like(got_planar)
+    for r in range(3):
+        s0, n, first, end = shard_units(S, 8, r, 3)
+        tot += pe.predict_sum(x.cuda(), n, sample0=s0, window=(first, end))
+    np.testing.assert_allclose(tot.cpu().numpy(), got_planar.cpu().numpy(), rtol=0, atol=2e-6)
 
 
 def test_sghmc_optimiser_step_matches_the_reference():
