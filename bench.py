@@ -391,16 +391,38 @@ def main():
         # the rank's samples on the launch stream; all-reduce + metric update on the predictor's side stream (they overlap the next step)
         return predictor.predict_async(x_dev, S, then=lambda p_bar: metric.update(p_bar, t_dev), draw_offset=next_offset(fresh))[0]
 
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        td = t_host.to(dev, non_blocking=True)
-        psum = predictor.local_sum(xd, S, rank, world, next_offset())
-        qdist.allreduce_prob_sums(psum)
-        metric.update(psum, td, scale=1.0 / S)
-        probs = (psum / S).to("cpu", non_blocking=True)
-        st = metric.state.to("cpu", non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return probs, st
+    # e2e: a double-buffered loader loop over HOST batches through the public API (ShardedMCPredictor.predict_async): step k's H2D
+    # copy (pinned -> device, copy stream) runs under step k-1's passes, the all-reduce, the metric update and the D2H copies of the
+    # probabilities and the metric state run on the predictor's side stream, and the host waits for step k-1's result while step k
+    # is in flight.  Every step's input crosses PCIe and every step's result reaches the host inside the timed region.
+    copy_stream = torch.cuda.Stream(dev)
+    dev_in = [(torch.empty_like(x_dev), torch.empty_like(t_dev)) for _ in range(2)]
+    host_out = [(torch.empty((B, K_CLASSES), dtype=torch.float32).pin_memory(), torch.empty_like(metric.state, device="cpu").pin_memory())
+                for _ in range(2)]
+
+    def e2e_loop(steps):
+        done = []
+        for k in range(steps):
+            xd, td = dev_in[k % 2]
+            with torch.cuda.stream(copy_stream):
+                if k >= 2:
+                    copy_stream.wait_event(done[k - 2])          # the buffers' previous consumer (step k-2) has finished
+                xd.copy_(x_host, non_blocking=True)
+                td.copy_(t_host, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready)
+            ph, sh = host_out[k % 2]
+
+            def consume(p_bar, td=td, ph=ph, sh=sh):
+                metric.update(p_bar, td)
+                ph.copy_(p_bar, non_blocking=True)
+                sh.copy_(metric.state, non_blocking=True)
+            done.append(predictor.predict_async(xd, S, then=consume, draw_offset=next_offset())[1])
+            if k >= 1:
+                done[k - 1].synchronize()                        # the host has step k-1's probabilities and metric state
+        done[-1].synchronize()
+        return host_out[(steps - 1) % 2]
 
     def barrier():
         if world > 1:
@@ -455,18 +477,19 @@ def main():
     n_replay = max(3, args.steps // 2)
     replay_ms = timed(lambda: step_resident(False), n_replay) / n_replay
     isolated_ms = timed(step_resident, n_replay, isolated=True) / n_replay
-    # ---- e2e: host buffers, H2D + D2H inside the timed region (wall clock around synchronous steps, max over ranks)
-    for _ in range(2):
-        step_e2e()
+    # ---- e2e: host buffers, H2D + D2H inside the timed region (wall clock around the double-buffered loop, max over ranks)
+    e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    e2e_loop(args.steps)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+    # the same resident loop once more: the GPU runs into its power cap within the first second of load, so the legs measured later
+    # (e2e, roofline) see a ~2 % slower device than the first timed loop; reported as `value_after_e2e`
+    resident_again_ms = timed(step_resident, n_replay) / n_replay
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream
@@ -574,7 +597,13 @@ def main():
                                  "the all-reduce and the metric update of step k run on a side stream under step k+1"},
             "sample_images_per_sec": value * S,
             "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8,
-                    "d2h_bytes_per_step": B * K_CLASSES * 4 + n_state * 4},
+                    "d2h_bytes_per_step": B * K_CLASSES * 4 + n_state * 4,
+                    "mode": "double-buffered loop over pinned host batches through ShardedMCPredictor.predict_async: H2D of step k under step "
+                            "k-1, D2H of the probabilities and the metric state on the side stream, the host reads step k-1's result while "
+                            "step k runs; wall clock around the K steps"},
+            "value_after_e2e": {"value": B / (resident_again_ms * 1e-3), "unit": "images/s", "ms_per_step": resident_again_ms,
+                                "note": "the timed resident loop repeated after the e2e leg (device under sw_power_cap by then): the e2e figure is to "
+                                        "be read against this one"},
             "isolated_step": {"ms_per_step": isolated_ms, "value": B / (isolated_ms * 1e-3), "unit": "images/s",
                               "note": "every step alone on an idle GPU: L2 flushed, barrier + synchronize around each step (the round-1/early "
                                       "round-2 way of timing; contains the host launch path and the exposed all-reduce)"},
