@@ -139,6 +139,27 @@ def test_resnet_engine_unit_window_sharding(world, chunk, graph):
         eng.predict_sum(x, 1, window=(7, 3))
 
 
+def test_sharded_predictor_async_form():
+    """ShardedMCPredictor.predict_async (collective, scaling and consumer on a side stream) == predict; the consumer sees p-bar; the
+    draw offset gives every batch fresh noise from the one captured graph."""
+    from qbn_b200 import dist as qdist
+    from qbn_b200 import mc, noise, synthetic, zoo
+    net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    x = torch.randn(6, 3, 32, 32, generator=torch.Generator().manual_seed(12)).cuda()
+    noise.manual_seed(31)
+    pred = qdist.ShardedMCPredictor(mc.MCEngine(net, math_mode="tf32", chunk=4))
+    want = pred.predict(x, 4)
+    seen = []
+    got, ev = pred.predict_async(x, 4, then=lambda p: seen.append(p.clone()))
+    other, _ = pred.predict_async(x, 4, draw_offset=4)             # next batch: sample indices 4..7
+    pred.wait_pending()
+    torch.cuda.synchronize()
+    assert ev.query() and len(seen) == 1 and torch.equal(seen[0], got)
+    close(got, want, 1e-6, 1e-7)
+    assert not torch.allclose(other, got) and torch.allclose(other.sum(1), torch.ones(6, device="cuda"), atol=1e-5)
+    noise.set_draw_offset(0)
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", 1.0), ("tf32", 20.0)])
 def test_resnet_lrt_training_step(golden, mode, tol):
     """trainer.py:95-104 on the drop-in model: LRT forward, KL, ELBO, backward; BN in batch-stat mode.
