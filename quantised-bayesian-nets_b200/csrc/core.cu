@@ -1091,7 +1091,10 @@ __global__ void sample_weights_blocked_multi_kernel(const qbn_p4_sample_job_dev*
 extern "C" int qbn_sample_weights_blocked_multi(const void* jobs_dev, int n_jobs, int64_t max_floats_per_sample, int n_samples,
                                                 uint64_t seed, uint32_t sample0, int round_tf32, void* stream) {
   QBN_CHECK_ARG(jobs_dev && n_jobs > 0 && n_jobs <= 65535 && n_samples > 0 && n_samples <= 65535 && max_floats_per_sample > 0, "args");
-  int64_t gx = (max_floats_per_sample / 4 + 1023) / 1024;      // up to four float4 per thread for the largest layer
+  // grid.x is sized for the largest layer and shared by all jobs: 16 float4 items per thread there keeps the number of blocks that
+  // find nothing to do in the small layers low (4 items: 98.6 us for 13 samples of the ResNet, 16: 88.1, 64: 128.5)
+  const int64_t per_block = 256 * 16;
+  int64_t gx = (max_floats_per_sample / 4 + per_block - 1) / per_block;
   if (gx < 1) gx = 1;
   if (gx > 4096) gx = 4096;
   sample_weights_blocked_multi_kernel<<<dim3((unsigned)gx, n_samples, n_jobs), 256, 0, (cudaStream_t)stream>>>(
