@@ -18,6 +18,8 @@ S-sample pass is replayed from a CUDA graph.
 Noise is keyed by the GLOBAL sample index, so any sharding of the S samples over GPUs (dist.py)
 reproduces the single-GPU result up to summation order.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -61,8 +63,11 @@ class MCEngine:
     (LinearNetwork / ConvNetwork_LeNet / ConvNetwork_ResNet of models_bbb.py, or their qbn_b200.zoo
     mirrors).  predict() == `_evaluate_with_loader`'s inner loop for one batch."""
 
-    def __init__(self, model, math_mode="tf32", chunk=50, use_graph=True, chunk_max=None):
+    def __init__(self, model, math_mode="tf32", chunk=50, use_graph=True, chunk_max=None, lanes=None):
         self.model = model
+        # concurrent chunk streams of a call (1 = off).  Measured on the ResNet, B=256: 2 lanes -1.8 % at 13 samples per call (the
+        # per-rank share at 8 GPUs), neutral at 100 — the per-launch cost is CTA start-up work, not idle SMs — so it stays opt-in
+        self.lanes = int(lanes) if lanes else 1
         self.use_graph = bool(use_graph)
         self.chunk_max = int(chunk_max) if chunk_max else int(chunk)   # a call's samples are split into ceil(S / chunk_max) balanced chunks
         self.math_mode = {"fp32": QBN_MATH_FP32, "tf32": QBN_MATH_TF32}[math_mode] if isinstance(math_mode, str) else math_mode
@@ -471,9 +476,12 @@ class MCEngine:
 
         def cb_of(st):
             return ops.p4_shortcut_block_channels(fused_of[id(st)].mod.in_channels, st.mod.in_channels) if id(st) in skip else 0
-        for st in steps:                       # refresh the blocked parameters of this call (once per call, not per chunk)
+        for st in steps:                       # refresh the blocked parameters (a no-op unless the parameters changed since the last call)
             self._p4_weights(st, prep, pinfo(st), st.mod.stride[0], cb_of(st))
-        if n not in tables or injected is not None:
+        if n <= 0:                             # refresh only (two-lane calls block the parameters once, before the fork)
+            return None
+        tkey = (n, self.__dict__.get("_slot", 0))      # a chunk running beside another one (two streams) owns its weight tensors
+        if tkey not in tables or injected is not None:
             n_jobs_total = sum(len(stack_groups(st)) if stack_ok(st) else 1 for st in steps)
             jobs = (P4SampleJob * n_jobs_total)()
             ji = 0
@@ -527,11 +535,11 @@ class MCEngine:
             raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
             entry = (raw, n_jobs_total, max_fl, wbufs)
             if injected is None:
-                tables[n] = entry
+                tables[tkey] = entry
             else:
                 self._p4_keep = (keep_eps, entry)          # keep the eps tensors alive until the chunk has run
         else:
-            entry = tables[n]
+            entry = tables[tkey]
         raw, n_jobs, max_fl, wbufs = entry
         ops.sample_weights_blocked_multi(raw, n_jobs, max_fl, n, seed, sample0, True)
         self.launches += 1
@@ -552,7 +560,7 @@ class MCEngine:
                 out[id(st)] = (m, float(torch.ones(1) / (1.0 - torch.ones(1) * p_)))
             return out
         cache = self.__dict__.setdefault("_mask_jobs", {})
-        key = (n, B)
+        key = (n, B, self.__dict__.get("_slot", 0))
         if key not in cache:
             by_p = {}
             for st in sites:
@@ -578,7 +586,7 @@ class MCEngine:
 
     def _p4_buffer(self, key, n_img, C, Hp, Wp, border, phases, device, zero):
         cache = self.__dict__.setdefault("_bufs", {})
-        k = (key, n_img, C, Hp, Wp, phases)
+        k = (key, n_img, C, Hp, Wp, phases, self.__dict__.get("_slot", 0))
         if k not in cache:
             cache[k] = ops.P4Map.empty(n_img, C, Hp, Wp, border, phases, device, zero=zero)
         return cache[k]
@@ -587,13 +595,25 @@ class MCEngine:
         """Output buffers are cached per (step, chunk size): stable pointers, no allocator churn, and the
         zero border of a zero-bordered map is written only once."""
         cache = self.__dict__.setdefault("_bufs", {})
-        k = (key, tuple(shape))
+        k = (key, tuple(shape), self.__dict__.get("_slot", 0))
         if k not in cache:
             buf = torch.empty(shape, dtype=torch.float32, device=device, memory_format=ops.CL if len(shape) == 4 else torch.contiguous_format)
             cache[k] = buf.zero_() if zero else buf
         return cache[k]
 
     # ---- execution -------------------------------------------------------------------------------
+    def _prestage(self, x, prep):
+        """The planar copy of the shared input batch (first layer on the planar kernel), made once per call."""
+        p4_layout, p4_convs = self._plan_p4()
+        first = getattr(self, "_p4_first", None)
+        if not p4_convs or first is None or x.dim() != 4:
+            return
+        st = next(s_ for s_ in self.steps if id(s_) == first)
+        info = self._packed(st, prep, torch.empty((0, st.mod.in_channels, 1, 1), device="meta"), 8)
+        self._call["x_p4"] = ops.p4_stage_input(x, info["wshape"][1], (1, 1))
+        self.launches += 1
+        self._p4_sample_all(0, 0, prep, noise.seed(), p4_convs, x.device)       # blocked mu / sigma of every planar layer
+
     def _run_chunk(self, x, n, sample0, prep, injected):
         """Advance samples [sample0, sample0+n) through every step.  Returns the head output(s)."""
         reg_pad = self._plan_layout()
@@ -846,6 +866,8 @@ class MCEngine:
             side.wait_stream(cur)
             with torch.cuda.stream(side):                      # warm-up: allocates the cached buffers, sets kernel attributes
                 self._predict_sum_eager(static_x, samples, sample0, None, window)
+                if self.lanes > 1:                             # ... and once more on all lanes (their buffers, their job tables)
+                    self._predict_sum_eager(static_x, samples, sample0, None, window)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             l0 = self.launches
@@ -878,8 +900,26 @@ class MCEngine:
         # chunks win (measured at S=100: chunk 10 -> 19.8 ms, 20 -> 18.6, 50 -> 18.2, 100 -> 18.6); the first layer's
         # sample-stacked launch is split into groups of <= 256 / N samples inside a chunk
         n_chunks = (samples + self.chunk_max - 1) // self.chunk_max
+        # two lanes: the chunks alternate between two streams (a fork / join inside a captured graph), each with its own activation
+        # and weight buffers, so the ramp of one chunk's launch fills the tail of the other's — every launch is persistent and
+        # occupies the whole GPU, the block scheduler hands the SMs over as the CTAs of the finishing launch retire
+        lanes = self.lanes if (injected is None and not self.regression and samples >= 2 * self.lanes and x.is_cuda) else 1
+        # the first call for an input shape after a parameter change packs / blocks the layers' operands inside the chunk that first
+        # needs them: that call runs on one lane, so no other lane can read an operand that is still being written
+        lanes_ready = prep.setdefault("_lanes_ready", set())
+        if lanes > 1 and tuple(x.shape) not in lanes_ready:
+            lanes = 1
+        if lanes > 1:
+            n_chunks = (n_chunks + lanes - 1) // lanes * lanes
         sizes = [samples // n_chunks + (1 if i < samples % n_chunks else 0) for i in range(n_chunks)]
         nB = x.shape[0]
+        cur = torch.cuda.current_stream(x.device) if lanes > 1 else None
+        streams, psums = [None], [None] * lanes
+        if lanes > 1:
+            self._prestage(x, prep)            # the shared planar input is staged once, before the fork
+            streams = self.__dict__.setdefault("_lane_streams", {}).setdefault(x.device.index, [torch.cuda.Stream(x.device) for _ in range(lanes)])
+            for st_ in streams:
+                st_.wait_stream(cur)
         for ci, n in enumerate(sizes):
             inj = injected[done:done + n] if injected is not None else None
             # the call's unit window restricts the first sample of the first chunk and the last sample of the last chunk
@@ -888,20 +928,35 @@ class MCEngine:
                 win = (window[0] if ci == 0 else 0, window[1] if ci == len(sizes) - 1 else nB)
                 if win == (0, nB):
                     win = None
-            if win is not None:
-                _lib.call("qbn_p4_set_window", win[0], win[1] if win[1] < nB else 0, n)
-            try:
-                out = self._run_chunk(x, n, sample0 + done, prep, inj)
-            finally:
+            lane = ci % lanes
+            self._slot = lane
+            with torch.cuda.stream(streams[lane]) if lanes > 1 else contextlib.nullcontext():
                 if win is not None:
-                    _lib.call("qbn_p4_set_window", 0, 0, 0)
-            if self.regression:
-                mus.append(out[0].clone())      # the step buffers are reused by the next chunk
-                lvs.append(out[1].clone())
-            else:
-                psum = ops.softmax_accumulate(out.contiguous(), psum, win)
-                self.launches += 1
+                    _lib.call("qbn_p4_set_window", win[0], win[1] if win[1] < nB else 0, n)
+                try:
+                    out = self._run_chunk(x, n, sample0 + done, prep, inj)
+                finally:
+                    if win is not None:
+                        _lib.call("qbn_p4_set_window", 0, 0, 0)
+                if self.regression:
+                    mus.append(out[0].clone())      # the step buffers are reused by the next chunk
+                    lvs.append(out[1].clone())
+                else:
+                    psums[lane] = ops.softmax_accumulate(out.contiguous(), psums[lane], win)
+                    self.launches += 1
             done += n
+        self._slot = 0
+        lanes_ready.add(tuple(x.shape))
+        psum = psums[0]
+        if lanes > 1:
+            for st_ in streams:
+                cur.wait_stream(st_)
+            for extra in psums[1:]:
+                if extra is not None:
+                    extra.record_stream(cur)
+                    psum.record_stream(cur)
+                    psum = psum + extra
+                    self.launches += 1
         if self.regression:
             return torch.cat(mus), torch.cat(lvs).exp()
         return psum

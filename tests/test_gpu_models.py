@@ -139,6 +139,27 @@ def test_resnet_engine_unit_window_sharding(world, chunk, graph):
         eng.predict_sum(x, 1, window=(7, 3))
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_resnet_engine_two_lanes(graph):
+    """lanes=2: the chunks of a call alternate between two streams with their own buffers (fork / join, also inside the captured
+    graph) — same draws, same sums as the single-stream pass, with and without a unit window, call after call."""
+    from qbn_b200 import mc, noise, synthetic, zoo
+    net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    x = torch.randn(5, 3, 32, 32, generator=torch.Generator().manual_seed(13)).cuda()
+    noise.manual_seed(41)
+    one = mc.MCEngine(net, math_mode="tf32", chunk=3, use_graph=False, lanes=1)
+    two = mc.MCEngine(net, math_mode="tf32", chunk=3, use_graph=graph, lanes=2)
+    want = one.predict_sum(x, 7, sample0=1)
+    for _ in range(3):                                    # first call: one lane (operands are packed); then two lanes / replays
+        got = two.predict_sum(x, 7, sample0=1)
+        close(got, want, 1e-5, 1e-6)
+    want_w = one.predict_sum(x, 7, sample0=1, window=(2, 4))
+    for _ in range(2):
+        close(two.predict_sum(x, 7, sample0=1, window=(2, 4)), want_w, 1e-5, 1e-6)
+    x2 = torch.randn(5, 3, 32, 32, generator=torch.Generator().manual_seed(14)).cuda()
+    close(two.predict_sum(x2, 7, sample0=1), one.predict_sum(x2, 7, sample0=1), 1e-5, 1e-6)
+
+
 def test_sharded_predictor_async_form():
     """ShardedMCPredictor.predict_async (collective, scaling and consumer on a side stream) == predict; the consumer sees p-bar; the
     draw offset gives every batch fresh noise from the one captured graph."""
