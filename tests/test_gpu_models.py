@@ -139,6 +139,30 @@ def test_resnet_engine_unit_window_sharding(world, chunk, graph):
         eng.predict_sum(x, 1, window=(7, 3))
 
 
+@pytest.mark.parametrize("B,hw,S,sample0", [(1, 32, 1, 0), (3, 32, 4, 5), (5, 32, 3, 2), (7, 32, 2, 1)])
+def test_resnet_engine_equals_the_module_forwards_on_ragged_batches(B, hw, S, sample0):
+    """Edge sizes (one image, one sample, odd batches; the network's AvgPool2d(4) fixes the input at 32x32): the planar engine (all samples of a chunk per launch,
+    BatchNorm folded into sampled weights, fused shortcuts, CUDA graph) against the drop-in modules run layer by layer, one forward
+    per sample, on the same Philox streams (stream index = global sample index): TF32 tolerance on the probabilities."""
+    from qbn_b200 import config, mc, noise, synthetic, zoo
+    net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    x = torch.randn(B, 3, hw, hw, generator=torch.Generator().manual_seed(100 + B)).cuda()
+    noise.manual_seed(2024)
+    config.set_math_mode("tf32")
+    try:
+        want = torch.zeros(B, 10, device="cuda")
+        with torch.no_grad():
+            for s in range(S):
+                with noise.sample_index(sample0 + s):
+                    want += net(x)                     # the model returns softmax probabilities (models_bbb.py:243)
+    finally:
+        config.set_math_mode("fp32")
+    for graph in (False, True):
+        got = mc.MCEngine(net, math_mode="tf32", chunk=3, use_graph=graph).predict_sum(x, S, sample0=sample0)
+        assert torch.allclose(got.sum(1), torch.full((B,), float(S), device="cuda"), atol=1e-4)
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=4e-3 * S)
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_resnet_engine_two_lanes(graph):
     """lanes=2: the chunks of a call alternate between two streams with their own buffers (fork / join, also inside the captured
