@@ -360,6 +360,11 @@ int qbn_lrt_stage_input(const float* x, int64_t n_img, int H, int W, int C, int 
 int qbn_lrt_stage_grad(const float* g_out, const float* std_saved, const float* eps, uint64_t seed, uint32_t stream_a,
                        uint32_t stream_b, int64_t n_img, int H, int W, int N, int bh, int bw, long long plane_rows, float* g_p4,
                        float* dv_p4, float* g_w32, float* dv_w32, void* stream);
+/* qbn_lrt_stage_input and qbn_lrt_noise in ONE launch: noise_out[0 .. noise_n) = the layer's eps tensor (conv.py:29-30: one draw per
+ * output element; noise_n = B * Ho * Wo * N, a multiple of 4), the same values qbn_lrt_noise writes for (seed, stream_a, stream_b) */
+int qbn_lrt_stage_input_noise(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
+                              long long plane_rows, float* x_p4, float* xsq_p4, float* x_w32, float* xsq_w32, float* noise_out,
+                              int64_t noise_n, uint64_t seed, uint32_t stream_a, uint32_t stream_b, void* stream);
 /* OIHW (mu, rho | sigma) -> blocked [mu | sigma^2] operand, TF32-rounded.  mode 0: forward (input channels zero-padded to C_pad,
  * blocked for `stride`); 1: input gradient of a stride-1 layer (taps reversed, channels swapped); 2: one phase of a stride-2
  * layer's input gradient (parameter taps tap_list[0..n_taps)); 3: the four phases of a 3x3 stride-2 layer, four taps each (absent

@@ -127,6 +127,8 @@ _SIGNATURES = {
     "qbn_p4_stage_input": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P]),
     "qbn_p4_stage_grad": (c_int, [P, P, P, c_uint64, c_uint32, c_uint32, c_int64, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P]),
     "qbn_lrt_stage_input": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P, P, P]),
+    "qbn_lrt_stage_input_noise": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P, P, P, c_int64,
+                                          c_uint64, c_uint32, c_uint32, P]),
     "qbn_lrt_stage_grad": (c_int, [P, P, P, c_uint64, c_uint32, c_uint32, c_int64, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, P, P, P, P, P]),
     "qbn_lrt_p4_weight_prep": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, P,
                                        POINTER(ctypes.c_longlong), P]),

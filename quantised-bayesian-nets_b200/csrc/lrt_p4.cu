@@ -105,11 +105,23 @@ __global__ void p4_stage_grad_kernel(const float* __restrict__ gout, const float
 template <bool GRAD>
 __global__ void lrt_stage_fused_kernel(const float* __restrict__ src, const float* __restrict__ sd, const float* __restrict__ eps, StageGeom g,
                                        uint64_t seed, uint32_t sa, uint32_t sb, const uint32_t* __restrict__ sbase, float4* __restrict__ a_p4,
-                                       float4* __restrict__ b_p4, float4* __restrict__ a_w32, float4* __restrict__ b_w32) {
+                                       float4* __restrict__ b_p4, float4* __restrict__ a_w32, float4* __restrict__ b_w32,
+                                       float4* __restrict__ noise_out, long long noise_n4) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent planar conv launch (qbn_set_pdl) may start its prologue now
-  if (GRAD && sbase) sb += *sbase;
+  if (sbase) sb += *sbase;
   const int n_blk = (g.chunks + 7) / 8;
   const long long total = (long long)n_blk * g.plane_rows * 8;
+  // forward staging with the layer's noise tensor in the same launch (qbn_lrt_stage_input_noise): the Philox / Box-Muller fill is
+  // ALU work, the staging is memory traffic — odd blocks draw first and stage second, so both kinds are in flight on every SM
+  auto draw = [&]() {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < noise_n4; i += (long long)gridDim.x * blockDim.x) {
+      float z[4];
+      philox_normal4(seed, sa, sb, (uint64_t)i, z);
+      noise_out[i] = make_float4(z[0], z[1], z[2], z[3]);
+    }
+  };
+  const bool with_noise = !GRAD && noise_out != nullptr;
+  if (with_noise && (blockIdx.x & 1)) draw();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int piece = (int)(i & 7);
     const long long br = i >> 3;
@@ -147,6 +159,7 @@ __global__ void lrt_stage_fused_kernel(const float* __restrict__ src, const floa
     a_w32[i] = a;
     b_w32[i] = b;
   }
+  if (with_noise && !(blockIdx.x & 1)) draw();
 }
 
 static int stage_geom(StageGeom& g, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int split, long long plane_rows) {
@@ -207,7 +220,25 @@ extern "C" int qbn_lrt_stage_input(const float* x, int64_t n_img, int H, int W, 
   const long long total = (long long)((g.chunks + 7) / 8) * plane_rows * 8;
   lrt_stage_fused_kernel<false><<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       x, nullptr, nullptr, g, 0, 0, 0, nullptr, reinterpret_cast<float4*>(x_p4), reinterpret_cast<float4*>(xsq_p4), reinterpret_cast<float4*>(x_w32),
-      reinterpret_cast<float4*>(xsq_w32));
+      reinterpret_cast<float4*>(xsq_w32), nullptr, 0);
+  QBN_CHECK_LAUNCH();
+  return QBN_OK;
+}
+// qbn_lrt_stage_input and qbn_lrt_noise (core.cu: the same values, counter = element / 4 of the layer's NHWC output) in one launch
+extern "C" int qbn_lrt_stage_input_noise(const float* x, int64_t n_img, int H, int W, int C, int C_pad, int bh, int bw, int phase_split,
+                                         long long plane_rows, float* x_p4, float* xsq_p4, float* x_w32, float* xsq_w32, float* noise_out,
+                                         int64_t noise_n, uint64_t seed, uint32_t stream_a, uint32_t stream_b, void* stream) {
+  QBN_CHECK_ARG(x && x_p4 && xsq_p4 && x_w32 && xsq_w32 && noise_out, "null pointer");
+  QBN_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && C > 0 && C_pad >= C && C_pad % 4 == 0 && bh >= 0 && bw >= 0, "sizes");
+  QBN_CHECK_ARG(noise_n > 0 && noise_n % 4 == 0, "noise_n: a positive multiple of 4");
+  StageGeom g;
+  int rc = stage_geom(g, n_img, H, W, C, C_pad, bh, bw, phase_split, plane_rows);
+  if (rc != QBN_OK) return rc;
+  const long long total = (long long)((g.chunks + 7) / 8) * plane_rows * 8;
+  const long long work = total > noise_n / 4 ? total : noise_n / 4;
+  lrt_stage_fused_kernel<false><<<qbn_grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, nullptr, nullptr, g, seed, stream_a, stream_b, qbn_sample_base_ptr(), reinterpret_cast<float4*>(x_p4), reinterpret_cast<float4*>(xsq_p4),
+      reinterpret_cast<float4*>(x_w32), reinterpret_cast<float4*>(xsq_w32), reinterpret_cast<float4*>(noise_out), noise_n / 4);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }
@@ -222,7 +253,7 @@ extern "C" int qbn_lrt_stage_grad(const float* g_out, const float* std_saved, co
   const long long total = (long long)((g.chunks + 7) / 8) * plane_rows * 8;
   lrt_stage_fused_kernel<true><<<qbn_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       g_out, std_saved, eps, g, seed, stream_a, stream_b, qbn_sample_base_ptr(), reinterpret_cast<float4*>(g_p4), reinterpret_cast<float4*>(dv_p4),
-      reinterpret_cast<float4*>(g_w32), reinterpret_cast<float4*>(dv_w32));
+      reinterpret_cast<float4*>(g_w32), reinterpret_cast<float4*>(dv_w32), nullptr, 0);
   QBN_CHECK_LAUNCH();
   return QBN_OK;
 }

@@ -269,16 +269,24 @@ def lrt_p4_forward(xc, weight, second, second_is_sigma, bias, d, eps=None, key=(
     pr = lrt_p4_plane_rows(rows, Wp)
     x_p4 = torch.empty((C_pad // 4, pr, 4), dtype=torch.float32, device=xc.device)
     xsq_p4 = torch.empty_like(x_p4)
+    drawn = False
     if want_w32:      # one pass over x writes both layouts (forward / input gradient: planar C4; weight gradients: W32)
         x_w32 = torch.empty(((C_pad + 31) // 32, pr, 32), dtype=torch.float32, device=xc.device)
         xsq_w32 = torch.empty_like(x_w32)
-        _lib.call("qbn_lrt_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _ptr(x_w32), _ptr(xsq_w32),
-                  _stream())
+        if eps is None and materialise_eps and (d.B * d.Ho * d.Wo * d.N) % 4 == 0:
+            # ... and the layer's noise tensor in the same launch (ALU work beside the staging's memory traffic)
+            eps = _out_like(xc, d)
+            _lib.call("qbn_lrt_stage_input_noise", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _ptr(x_w32),
+                      _ptr(xsq_w32), _ptr(eps), eps.numel(), key[0], key[1], key[2], _stream())
+            drawn = True
+        else:
+            _lib.call("qbn_lrt_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _ptr(x_w32),
+                      _ptr(xsq_w32), _stream())
     else:
         _lib.call("qbn_p4_stage_input", _ptr(xc), d.B, d.H, d.W, d.C, C_pad, bh, bw, int(s2), pr, _ptr(x_p4), _ptr(xsq_p4), _stream())
     w = lrt_p4_weight_prep(weight.detach().contiguous(), second.detach().contiguous(), second_is_sigma, d, 0)
     out, std = _out_like(xc, d), _out_like(xc, d)
-    if eps is None and materialise_eps:
+    if eps is None and materialise_eps and not drawn:
         # the epilogue's Philox draw as a tensor (same values): generated at full occupancy, re-read by the backward
         eps = _out_like(xc, d)
         _lib.call("qbn_lrt_noise", _ptr(eps), eps.numel(), key[0], key[1], key[2], _stream())

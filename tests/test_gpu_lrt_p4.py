@@ -117,6 +117,19 @@ def test_fused_staging_equals_the_two_pass_staging():
                       ops._ptr(wa2), ops._ptr(wb2), ops._stream())
         for u, v in ((a, a2), (b, b2), (wa, wa2), (wb, wb2)):
             assert torch.equal(u, v)
+        # ... and with the layer's noise tensor drawn in the same launch: same layouts, the values of qbn_lrt_noise (more and fewer
+        # noise elements than staging work; a device-side draw offset)
+        from qbn_b200 import noise
+        for n_noise, off in ((B * H * W * 8, 0), (4 * 1000 * 1000, 3)):
+            noise.set_draw_offset(off)
+            want = mk(n_noise)
+            ops._lib.call("qbn_lrt_noise", ops._ptr(want), n_noise, 11, 12, 13, ops._stream())
+            a3, b3, wa3, wb3, got = mk(C_pad // 4, pr, 4), mk(C_pad // 4, pr, 4), mk((C_pad + 31) // 32, pr, 32), mk((C_pad + 31) // 32, pr, 32), mk(n_noise)
+            ops._lib.call("qbn_lrt_stage_input_noise", ops._ptr(x), B, H, W, C, C_pad, border[0], border[1], int(split), pr, ops._ptr(a3), ops._ptr(b3),
+                          ops._ptr(wa3), ops._ptr(wb3), ops._ptr(got), n_noise, 11, 12, 13, ops._stream())
+            for u, v in ((a, a3), (b, b3), (wa, wa3), (wb, wb3), (want, got)):
+                assert torch.equal(u, v)
+        noise.set_draw_offset(0)
         if not split and C % 4 == 0:
             gout, sd = ops.nhwc(torch.randn(B, C, H, W, generator=g).cuda()), ops.nhwc(torch.rand(B, C, H, W, generator=g).cuda() + 0.5)
             for eps in (ops.nhwc(torch.randn(B, C, H, W, generator=g).cuda()), None):
