@@ -369,8 +369,13 @@ fits:
   if (p.n_ps > (p.n_tiles + 3) / 4) p.n_ps = (p.n_tiles + 3) / 4;
   if (p.n_ps > p.n_tiles) p.n_ps = p.n_tiles;
   if (p.n_ps < 1) p.n_ps = 1;
-  QBN_CUDA(cudaMemsetAsync(dmu_p, 0, sizeof(float) * (size_t)N * p.taps * C_real, st));
-  QBN_CUDA(cudaMemsetAsync(dsig2_p, 0, sizeof(float) * (size_t)N * p.taps * C_real, st));
+  const size_t grad_bytes = sizeof(float) * (size_t)N * p.taps * C_real;
+  if (reinterpret_cast<char*>(dmu_p) + grad_bytes == reinterpret_cast<char*>(dsig2_p)) {      // one allocation (ops.lrt_p4_backward): one memset
+    QBN_CUDA(cudaMemsetAsync(dmu_p, 0, 2 * grad_bytes, st));
+  } else {
+    QBN_CUDA(cudaMemsetAsync(dmu_p, 0, grad_bytes, st));
+    QBN_CUDA(cudaMemsetAsync(dsig2_p, 0, grad_bytes, st));
+  }
   static bool attr_set = false;
   if (!attr_set) {
     QBN_CUDA(cudaFuncSetAttribute(umma_wgrad_p4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

@@ -316,8 +316,8 @@ def lrt_p4_backward(xc, x_w32, xsq_w32, std, eps, weight, second, second_is_sigm
     dv_w32 = torch.empty_like(g_w32)
     _lib.call("qbn_lrt_stage_grad", _ptr(gc), _ptr(std), _ptr(eps), key[0], key[1], key[2], d.B, d.Ho, d.Wo, d.N, bh, bw, pr_g, _ptr(g_p4),
               _ptr(dv_p4), _ptr(g_w32), _ptr(dv_w32), _stream())
-    dmu_p = torch.empty(d.N * d.R * d.S * d.C, dtype=torch.float32, device=gc.device)
-    dsig2_p = torch.empty_like(dmu_p)
+    both = torch.empty((2, d.N * d.R * d.S * d.C), dtype=torch.float32, device=gc.device)     # adjacent: the kernel zeroes them with one memset
+    dmu_p, dsig2_p = both[0], both[1]
     _lib.call("qbn_lrt_wgrad_p4", d.B, Hp, Wp, d.C, d.N, d.R, d.S, d.stride_h, _ptr(g_w32), _ptr(dv_w32), pr_g, _ptr(x_w32), _ptr(xsq_w32),
               x_w32.stride(0) // 32, _ptr(dmu_p), _ptr(dsig2_p), _stream())
     dx = None
