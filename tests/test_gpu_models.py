@@ -145,7 +145,12 @@ def test_resnet_engine_equals_the_module_forwards_on_ragged_batches(B, hw, S, sa
     BatchNorm folded into sampled weights, fused shortcuts, CUDA graph) against the drop-in modules run layer by layer, one forward
     per sample, on the same Philox streams (stream index = global sample index): TF32 tolerance on the probabilities."""
     from qbn_b200 import config, mc, noise, synthetic, zoo
-    net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    saved_id = noise._state["next_layer_id"]
+    noise._state["next_layer_id"] = 5000       # fixed Philox stream ids: the draws do not depend on how many layers earlier tests built
+    try:
+        net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    finally:
+        noise._state["next_layer_id"] = max(saved_id, 5100)
     x = torch.randn(B, 3, hw, hw, generator=torch.Generator().manual_seed(100 + B)).cuda()
     noise.manual_seed(2024)
     config.set_math_mode("tf32")
@@ -160,7 +165,11 @@ def test_resnet_engine_equals_the_module_forwards_on_ragged_batches(B, hw, S, sa
     for graph in (False, True):
         got = mc.MCEngine(net, math_mode="tf32", chunk=3, use_graph=graph).predict_sum(x, S, sample0=sample0)
         assert torch.allclose(got.sum(1), torch.full((B,), float(S), device="cuda"), atol=1e-4)
-        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=4e-3 * S)
+        # single-sample probabilities of the two TF32 paths (BatchNorm folded into the sampled weights before rounding / applied after
+        # the conv) differ by up to ~1e-2 (profiles/r02_tf32_error_distribution.txt: 3e-3 on a 10-sample mean); another draw or a
+        # wrong image would be off by 1e-1 and more
+        err = (got - want).abs()
+        assert float(err.max()) < 2e-2 * S and float(err.mean()) < 4e-3 * S, (float(err.max()), float(err.mean()))
 
 
 @pytest.mark.parametrize("graph", [False, True])
