@@ -87,6 +87,10 @@ class ShardedMCPredictor:
         update, a D2H copy) run on a side stream, so the next batch's passes start while this batch's all-reduce is in flight.
         Returns (p_bar, event): p_bar is valid for a stream that has waited on the event (wait_pending() does it for the
         current stream)."""
+        if self.engine.regression:
+            raise NotImplementedError("predict_async: classification engines (regression heads reduce three sums: use predict)")
+        if not x.is_cuda:
+            raise RuntimeError("predict_async needs CUDA tensors (streams); predict() is the synchronous form")
         rank, ws = world()
         out = self.local_sum(x, samples, rank, ws, draw_offset)
         cur = torch.cuda.current_stream(x.device)
