@@ -117,6 +117,29 @@ def test_shard_units_partitions():
     assert shard_units(100, 256, 0, 8) == (0, 13, 0, 128) and shard_units(100, 256, 1, 8) == (12, 13, 128, 256)   # 12.5 samples each
 
 
+def test_shard_units_property():
+    """hypothesis: for any (samples, batch, world) the windows tile the (sample, image) grid exactly once, in rank order, balanced."""
+    from hypothesis import given, settings, strategies as st
+    from qbn_b200.dist import shard_units
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 33), st.integers(1, 24))
+    def check(S, B, W):
+        nxt, sizes = 0, []
+        for r in range(W):
+            s0, n, first, end = shard_units(S, B, r, W)
+            if n == 0:
+                sizes.append(0)
+                continue
+            assert 0 <= first < B and 0 < end <= B and (n > 1 or first < end)
+            lo, hi = s0 * B + first, (s0 + n - 1) * B + end          # unit range [lo, hi) in sample-major order
+            assert lo == nxt and hi > lo
+            nxt = hi
+            sizes.append(hi - lo)
+        assert nxt == S * B and max(sizes) - min(sizes) <= 1
+    check()
+
+
 def test_world2_gloo():
     port = _free_port()
     mgr = mp.Manager()
