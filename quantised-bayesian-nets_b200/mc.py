@@ -893,6 +893,7 @@ class MCEngine:
         x = ops.nhwc(x.float()) if x.dim() == 4 else x.float().contiguous().reshape(x.shape[0], -1, 1, 1)
         prep = self._get_prep(x.device)
         self._call = {}                 # per-call (input-dependent) cache, e.g. the planar copy of the input batch
+        self._slot = 0                  # buffer set of the lane a chunk runs on (reset: an exception may have left another lane's)
         psum = None
         mus, lvs = [], []
         done = 0
