@@ -63,11 +63,14 @@ class MCEngine:
     (LinearNetwork / ConvNetwork_LeNet / ConvNetwork_ResNet of models_bbb.py, or their qbn_b200.zoo
     mirrors).  predict() == `_evaluate_with_loader`'s inner loop for one batch."""
 
-    def __init__(self, model, math_mode="tf32", chunk=50, use_graph=True, chunk_max=None, lanes=None):
+    def __init__(self, model, math_mode="tf32", chunk=50, use_graph=True, chunk_max=None, lanes=None, sample_ahead=False):
         self.model = model
         # concurrent chunk streams of a call (1 = off).  Measured on the ResNet, B=256: 2 lanes -1.8 % at 13 samples per call (the
         # per-rank share at 8 GPUs), neutral at 100 — the per-launch cost is CTA start-up work, not idle SMs — so it stays opt-in
         self.lanes = int(lanes) if lanes else 1
+        # draw chunk i+1's weights on a second stream under chunk i's convolutions.  Measured on the ResNet, B=256, S=100: 17.315
+        # against 17.310 ms — the sampler's blocks find no room beside the resident conv CTAs — so it stays opt-in
+        self.sample_ahead = bool(sample_ahead)
         self.use_graph = bool(use_graph)
         self.chunk_max = int(chunk_max) if chunk_max else int(chunk)   # a call's samples are split into ceil(S / chunk_max) balanced chunks
         self.math_mode = {"fp32": QBN_MATH_FP32, "tf32": QBN_MATH_TF32}[math_mode] if isinstance(math_mode, str) else math_mode
@@ -480,7 +483,8 @@ class MCEngine:
             self._p4_weights(st, prep, pinfo(st), st.mod.stride[0], cb_of(st))
         if n <= 0:                             # refresh only (two-lane calls block the parameters once, before the fork)
             return None
-        tkey = (n, self.__dict__.get("_slot", 0))      # a chunk running beside another one (two streams) owns its weight tensors
+        # a chunk running beside another one (two lanes), or sampled ahead under its predecessor, owns its weight tensors
+        tkey = (n, self.__dict__.get("_slot", 0), self.__dict__.get("_wslot", 0))
         if tkey not in tables or injected is not None:
             n_jobs_total = sum(len(stack_groups(st)) if stack_ok(st) else 1 for st in steps)
             jobs = (P4SampleJob * n_jobs_total)()
@@ -614,7 +618,7 @@ class MCEngine:
         self.launches += 1
         self._p4_sample_all(0, 0, prep, noise.seed(), p4_convs, x.device)       # blocked mu / sigma of every planar layer
 
-    def _run_chunk(self, x, n, sample0, prep, injected):
+    def _run_chunk(self, x, n, sample0, prep, injected, presampled=None):
         """Advance samples [sample0, sample0+n) through every step.  Returns the head output(s)."""
         reg_pad = self._plan_layout()
         p4_layout, p4_convs = self._plan_p4()
@@ -622,7 +626,8 @@ class MCEngine:
             reg_pad = {r: v for r, v in reg_pad.items() if r not in p4_layout}
         self._p4_presampled = None
         if p4_convs:
-            self._p4_presampled = self._p4_sample_all(n, sample0, prep, noise.seed(), p4_convs, x.device, injected)
+            # presampled: this chunk's weights were drawn ahead, on the sampler stream, under the previous chunk's convolutions
+            self._p4_presampled = presampled if presampled is not None else self._p4_sample_all(n, sample0, prep, noise.seed(), p4_convs, x.device, injected)
         masks = self._chunk_masks(n, x.shape[0], sample0, noise.seed(), injected, x.device)
         pending = {}         # register -> (mask, mult): MC-Dropout applied in the operand load of its consumers (gather / fp32 kernels)
         regs = {0: x}
@@ -921,8 +926,34 @@ class MCEngine:
             streams = self.__dict__.setdefault("_lane_streams", {}).setdefault(x.device.index, [torch.cuda.Stream(x.device) for _ in range(lanes)])
             for st_ in streams:
                 st_.wait_stream(cur)
+        # sample ahead: chunk i+1's weights are drawn on a second stream (a second branch of the captured graph) while chunk i's
+        # convolutions run — double-buffered weight tensors; only the first chunk's sampling stays on the critical path
+        ahead = (self.sample_ahead and lanes == 1 and injected is None and len(sizes) > 1 and x.is_cuda and bool(self._plan_p4()[1]))
+        pending = None
+        if ahead:
+            cur = torch.cuda.current_stream(x.device)
+            sampler = self.__dict__.setdefault("_sampler_streams", {}).setdefault(x.device.index, torch.cuda.Stream(x.device))
         for ci, n in enumerate(sizes):
             inj = injected[done:done + n] if injected is not None else None
+            presampled = None
+            if ahead:
+                p4_convs = self._plan_p4()[1]
+                if pending is None:
+                    self._wslot = ci % 2
+                    presampled = self._p4_sample_all(n, sample0 + done, prep, noise.seed(), p4_convs, x.device)
+                else:
+                    presampled, ev = pending
+                    cur.wait_event(ev)
+                pending = None
+                if ci + 1 < len(sizes):
+                    sampler.wait_stream(cur)           # chunk i-1 (the last reader of these weight tensors) is already in the stream
+                    with torch.cuda.stream(sampler):
+                        self._wslot = (ci + 1) % 2
+                        nxt = self._p4_sample_all(sizes[ci + 1], sample0 + done + n, prep, noise.seed(), p4_convs, x.device)
+                        ev = torch.cuda.Event()
+                        ev.record(sampler)
+                    pending = (nxt, ev)
+                self._wslot = 0
             # the call's unit window restricts the first sample of the first chunk and the last sample of the last chunk
             win = None
             if window is not None:
@@ -935,7 +966,7 @@ class MCEngine:
                 if win is not None:
                     _lib.call("qbn_p4_set_window", win[0], win[1] if win[1] < nB else 0, n)
                 try:
-                    out = self._run_chunk(x, n, sample0 + done, prep, inj)
+                    out = self._run_chunk(x, n, sample0 + done, prep, inj, presampled)
                 finally:
                     if win is not None:
                         _lib.call("qbn_p4_set_window", 0, 0, 0)

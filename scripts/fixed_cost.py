@@ -18,7 +18,8 @@ def main():
     model = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
     noise.manual_seed(1)
     x = torch.randn(256, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
-    eng = MCEngine(model, chunk=int(os.environ.get("QBN_CHUNK", "50")), lanes=int(os.environ.get("QBN_LANES", "1")))
+    eng = MCEngine(model, chunk=int(os.environ.get("QBN_CHUNK", "50")), lanes=int(os.environ.get("QBN_LANES", "1")),
+                   sample_ahead=os.environ.get("QBN_AHEAD", "0") == "1")
     pts = []
     for S in (1, 2, 4, 6, 12, 13, 25, 50, 100):
         for _ in range(3):

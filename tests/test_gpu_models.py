@@ -193,6 +193,23 @@ def test_resnet_engine_two_lanes(graph):
     close(two.predict_sum(x2, 7, sample0=1), one.predict_sum(x2, 7, sample0=1), 1e-5, 1e-6)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_resnet_engine_sample_ahead(graph):
+    """sample_ahead: chunk i+1's weights drawn on a second stream under chunk i's convolutions (double-buffered weight tensors) —
+    the same draws and sums as the in-order pass, call after call, with a unit window too."""
+    from qbn_b200 import mc, noise, synthetic, zoo
+    net = zoo.resnet_from_params(synthetic.ResNetBBBParams(seed=1)).cuda().eval()
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(15)).cuda()
+    noise.manual_seed(43)
+    base = mc.MCEngine(net, math_mode="tf32", chunk=2, use_graph=False)
+    fast = mc.MCEngine(net, math_mode="tf32", chunk=2, use_graph=graph, sample_ahead=True)
+    want = base.predict_sum(x, 7, sample0=3)
+    for _ in range(3):
+        close(fast.predict_sum(x, 7, sample0=3), want, 1e-6, 1e-7)
+    close(fast.predict_sum(x, 7, sample0=3, window=(1, 3)), base.predict_sum(x, 7, sample0=3, window=(1, 3)), 1e-6, 1e-7)
+    close(fast.predict_sum(x, 1), base.predict_sum(x, 1), 1e-6, 1e-7)          # a single chunk: nothing to draw ahead
+
+
 def test_sharded_predictor_async_form():
     """ShardedMCPredictor.predict_async (collective, scaling and consumer on a side stream) == predict; the consumer sees p-bar; the
     draw offset gives every batch fresh noise from the one captured graph."""
